@@ -1,0 +1,170 @@
+/* rf_b200.h - C ABI of the B200-native RetrievalFuse hot path.
+ *
+ * The reference (nihalsid/retrieval-fuse) has no FFI on this path: it is Python
+ * nn.Modules + pyflann.  This header is the drop-in boundary a maintainer binds
+ * with ctypes; each entry point names the reference
+ * function (file:line under /root/reference) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - tensors are fp32, contiguous, NCDHW, exactly as the reference's torch
+ *     tensors; indices are int32; kNN distances travel as fp64 until the last
+ *     step so that shard merges stay bit-exact;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - return value 0 = ok, non-zero = error, message via rf_last_error()
+ *     (thread-local); kernels are asynchronous on `stream`;
+ *   - no hidden global state, no allocation: callers pass workspaces.
+ *   - there is NO CPU fallback: every function launches sm_100a kernels.
+ */
+#ifndef RF_B200_H
+#define RF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RF_ACT_NONE 0
+#define RF_ACT_RELU 1
+#define RF_ACT_LEAKY 2 /* slope argument */
+#define RF_ACT_TANH 3
+
+const char* rf_last_error(void);
+int rf_version(void);
+/* sm count / compute capability of `device`; fails if it is not sm_100. */
+int rf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- a2-a4  patch fold / unfold (bit-exact re-indexing) ------------------- */
+
+/* model/attention.py:186-188 Unfold3D.forward: [B,C,S,S,S] -> [B*(S/E)^3,C,E,E,E] */
+int rf_unfold3d(const float* x, float* out, int B, int C, int S, int E, void* stream);
+/* model/attention.py:170-176 Fold3D.forward: [B*R^3,C,E,E,E] -> [B,C,R*E,R*E,R*E] (contiguous) */
+int rf_fold3d(const float* x, float* out, int B, int C, int R, int E, void* stream);
+/* model/attention.py:200-203 Unfold3DPadStride.forward and util/patcher.py:14-19
+ * Patcher.__call__ (per-axis kernel/pad/stride).  x [B,C,size] -> out
+ * [B,n0,n1,n2,C,k0,k1,k2] (the reference then views it as (-1,1,k,k,k) or
+ * (-1,C,k,k,k)).  When norm_div != 0 every value (padding included) is mapped
+ * v -> (v - norm_sub) / norm_div in fp32, which fuses
+ * dataset/patched_scene_dataset.py:127-128 after dataset/scene.py:61 padding. */
+int rf_unfold3d_pad_stride(const float* x, float* out, int B, int C, const int size[3], const int kernel[3],
+                           const int pad[3], const int stride[3], float pad_val, float norm_sub, float norm_div,
+                           void* stream);
+/* util/patcher.py:21-30 Patcher.recompose_patches: patches [B,n0*n1*n2,k0,k1,k2]
+ * -> out [B,C,size] (padding cropped); later patches overwrite earlier ones. */
+int rf_recompose_patches(const float* patches, float* out, int B, int C, const int size[3], const int kernel[3],
+                         const int pad[3], const int stride[3], const int count[3], float pad_val, void* stream);
+
+/* ---- building blocks of a5-a8, a13-a16 ----------------------------------- */
+
+/* Implicit-GEMM 3D convolution / linear layer, fp32 accumulate (torch.nn.Conv3d
+ * as used by model/retrieval.py:4-388 and model/unet.py:15-16, nn.Linear as in
+ * model/retrieval.py:64-84, model/attention.py:29-46).
+ *   x  [N,Cin,Di,Hi,Wi]; wt [Cin*KS^3, Cout] = weight.reshape(Cout,-1).T
+ *   y  [N,Cout,Do,Ho,Wo], Do = (Di + 2*pad - KS)/stride + 1
+ *   optional fused GroupNorm on the INPUT ('g' before 'c', model/unet.py:54-66):
+ *     v = (x - gn_mu[n,ci]) * gn_a[n,ci] + gn_beta[ci], zero padding applied
+ *     after it; pass gn_mu = NULL to disable;
+ *   optional virtual input = concat(x [N,Cin-C2,...], nearest-2x-upsample(x2
+ *     [N,C2,Di/2,Hi/2,Wi/2])) along channels (model/unet.py:297-306 Decoder
+ *     joining); pass x2 = NULL / C2 = 0 to disable;
+ *   epilogue: y = act((acc + bias[co]) * oscale[co] + oshift[co]); any of
+ *     bias / oscale / oshift may be NULL (eval BatchNorm3d folds into them). */
+int rf_conv3d_fwd(const float* x, const float* x2, int C2, const float* wt, const float* bias, const float* oscale,
+                  const float* oshift, const float* gn_mu, const float* gn_a, const float* gn_beta, float* y, int N,
+                  int Cin, int Di, int Hi, int Wi, int Cout, int KS, int stride, int pad, int act, float slope,
+                  void* stream);
+/* y[M,N] = act(x[M,K] @ wt[K,N] + bias) - the same kernel with KS = 1. */
+int rf_linear_fwd(const float* x, const float* wt, const float* bias, float* y, int M, int K, int N, int act,
+                  float slope, void* stream);
+/* torch.nn.GroupNorm statistics (model/unet.py:66): per (n, group) mean and
+ * 1/sqrt(var+eps) over cpg*spatial elements of the virtual input (same x / x2
+ * concat rule as rf_conv3d_fwd), expanded to gn_mu[n*C+c] = mean and
+ * gn_a[n*C+c] = rstd * gamma[c]. */
+int rf_groupnorm_stats(const float* x, const float* x2, int C2, const float* gamma, float* gn_mu, float* gn_a, int N,
+                       int C, int D, int H, int W, int groups, float eps, void* stream);
+/* nn.MaxPool3d(2) (model/unet.py:238): [N,C,D,H,W] -> [N,C,D/2,H/2,W/2] */
+int rf_maxpool3d_2(const float* x, float* y, int N, int C, int D, int H, int W, void* stream);
+/* F.interpolate(mode='nearest') by exactly 2x (model/unet.py:352-358): -> [N,C,2D,2H,2W] */
+int rf_upsample_nearest_2(const float* x, float* y, int N, int C, int D, int H, int W, void* stream);
+/* F.normalize(x, dim=1) on rows (util/retrieval.py:38,66): y = x / max(||x||_2, eps) */
+int rf_l2_normalize_rows(const float* x, float* y, long M, int D, float eps, void* stream);
+
+/* ---- a5 + a9  fused query encoder --------------------------------------- */
+
+/* model/retrieval.py:64-84 Patch04.forward (+Patch05/Patch04V2: any ReLU MLP)
+ * followed by util/retrieval.py:66 normalisation, activations kept on chip.
+ *   x [M, widths[0]] rows; wt[l] = layers[2l].weight.T [widths[l], widths[l+1]];
+ *   out [M, widths[n_layers]] unit rows.  n_layers <= 8.  Hidden activations
+ *   live in `workspace` (rf_mlp_encode_workspace_bytes), never in caller tensors. */
+size_t rf_mlp_encode_workspace_bytes(long M, const int* widths_host, int n_layers);
+int rf_mlp_encode_fwd(const float* x, const float* const* wt_host, const float* const* bias_host,
+                      const int* widths_host, int n_layers, int l2_normalize, float* out, long M, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ---- a10-a11  exact kNN, merge, demotion -------------------------------- */
+
+/* Canonical exact rule (replaces util/retrieval.py:92 flann nn_index(q, 2K)):
+ *   d(q,x) = sum_i (double(q_i) - double(x_i))^2, i ascending, each op rounded
+ *   once (no fma); result = k smallest under ascending (d, global row id).
+ * bank [n_rows, D] is one shard whose first row has global id row_offset.
+ * out_idx [Q,k] int32 global ids, out_d [Q,k] fp64.  D must be 64.
+ * method: 0 = auto, 1 = exact fp64 sweep, 2 = tcgen05 candidate pass (bf16x3
+ * split, fp32 accumulate in TMEM) + fp64 re-rank + proof check + fp64 sweep of
+ * the queries whose candidate set could not be proven complete. */
+size_t rf_knn_workspace_bytes(long Q, long n_rows, int k, int method);
+int rf_knn_l2_topk(const float* bank, long n_rows, long row_offset, const float* q, long Q, int D, int k, int method,
+                   int* out_idx, double* out_d, void* workspace, size_t workspace_bytes, void* stream);
+/* Merge S sorted candidate lists per query (shards of one GPU sweep or the
+ * all-gathered per-rank lists): parts_idx/parts_d [S,Q,k] -> [Q,k]
+ * under the same (d, id) order. */
+int rf_knn_merge(const int* parts_idx, const double* parts_d, int S, long Q, int k, int* out_idx, double* out_d,
+                 void* stream);
+/* util/retrieval.py:93-100: gather database[:,0:7] for the 2K hits, move hits
+ * whose scene (meta[:,0]) equals query_scene[q] behind the others (stable),
+ * keep K.  query_scene[q] < 0 disables demotion for that query.
+ * meta [N,7] fp32; out_rows [Q,K,8] = [scene,x0,x1,y0,y1,z0,z1,(float)d];
+ * out_idx [Q,K] int32 (may be NULL). */
+int rf_knn_demote_rows(const int* idx2k, const double* d2k, const float* meta, const int* query_scene, long Q, int K2,
+                       int K, float* out_rows, int* out_idx, void* stream);
+
+/* ---- a12  compose ------------------------------------------------------- */
+
+/* util/retrieval.py:145-164 create_retrieval_from_mapping for non-overlapping
+ * patches (patch_stride == patch_size, patched_scene_dataset.py:113-115).
+ *   rows [n_chunks*P, K, 8] mapping rows in patch order; dst_extents [P,6] int32
+ *   (unpadded destination extents inside a chunk); scene_store [S,sx,sy,sz]
+ *   unpadded train targets; out [n_chunks,K,cx,cy,cz];
+ *   out[c,k,dst] = scene_store[row.scene][x0:x1,y0:y1,z0:z1] * ratio, or
+ *   trunc * ratio when row.scene < 0 (the sentinel row, :160-161). */
+int rf_compose_gather(const float* rows, const int* dst_extents, const float* scene_store, float* out, int n_chunks,
+                      int P, int K, int n_scenes, const int scene_size[3], const int chunk_size[3], float trunc,
+                      float ratio, void* stream);
+
+/* ---- a14  patch attention ------------------------------------------------ */
+
+/* model/attention.py:141-157 PatchedAttentionBlock.forward with
+ * AttentionBlock.forward :84-113 (g = o = Identity, blend or additive).
+ *   x_back [B,nf,S,S,S], x_retr [B*K,nf,S,S,S] -> out [B,nf,S,S,S]
+ *   theta_wt/phi_wt: 4 transposed Linear weights [in,out] each, *_b biases;
+ *   mode 0: softmax(32*E^3*4 * s); mode 1: hard Gumbel arg-max of 25*s + noise
+ *   (noise [B*R^3, K], required); workspace from rf_attention_workspace_bytes. */
+size_t rf_attention_workspace_bytes(int B, int nf, int S, int E, int K);
+int rf_attention_fuse_fwd(const float* x_back, const float* x_retr, const float* const* theta_wt_host,
+                          const float* const* theta_b_host, const float* const* phi_wt_host,
+                          const float* const* phi_b_host, const float* gumbel_noise, float* out, int B, int nf, int S,
+                          int E, int K, int normalize, int mode, int blend, void* workspace, size_t workspace_bytes,
+                          void* stream);
+/* model/attention.py:132-139 get_features: theta(unfold(x)), phi(unfold(t)),
+ * any(occupancy) per sub-patch.  x,t [B,nf,S,S,S]; occ [B,1,S,S,S] uint8;
+ * x_feat,p_feat [B*R^3,32]; occ_any [B*R^3] uint8. */
+int rf_attention_features(const float* x, const float* t, const uint8_t* occ, const float* const* theta_wt_host,
+                          const float* const* theta_b_host, const float* const* phi_wt_host,
+                          const float* const* phi_b_host, float* x_feat, float* p_feat, uint8_t* occ_any, int B, int nf,
+                          int S, int E, int normalize, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RF_B200_H */

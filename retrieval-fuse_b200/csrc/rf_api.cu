@@ -1,0 +1,65 @@
+// C-ABI plumbing: error string, device query, kNN dispatch.
+#include <stdarg.h>
+#include <string.h>
+
+#include "rf_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void rf_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* rf_last_error(void) { return g_err; }
+extern "C" int rf_version(void) { return 100; }
+
+extern "C" int rf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+    cudaDeviceProp p;
+    RF_CUDA_OK(cudaGetDeviceProperties(&p, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    RF_CHECK_ARG(p.major == 10, "rf_b200 kernels are built for sm_100a only; device %d is sm_%d%d", device, p.major, p.minor);
+    return 0;
+}
+
+int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, int* out_idx,
+                        double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s);
+int rf_knn_exact_nsplit(long Q, long n_rows);
+size_t rf_knn_tc_workspace_bytes(long Q, long n_rows, int k);
+int rf_knn_tc_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, int* out_idx,
+                     double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s);
+
+static size_t exact_ws(long Q, long n_rows, int k) {
+    const int ns = rf_knn_exact_nsplit(Q, n_rows);
+    return ns == 1 ? 256 : (size_t)ns * Q * k * (sizeof(int) + sizeof(double)) + 256;
+}
+
+extern "C" size_t rf_knn_workspace_bytes(long Q, long n_rows, int k, int method) {
+    if (Q <= 0 || n_rows <= 0 || k <= 0) return 0;
+    size_t a = exact_ws(Q, n_rows, k);
+    if (method != 1) {
+        const size_t b = rf_knn_tc_workspace_bytes(Q, n_rows, k);
+        if (b > a) a = b;
+    }
+    return a;
+}
+
+extern "C" int rf_knn_l2_topk(const float* bank, long n_rows, long row_offset, const float* q, long Q, int D, int k,
+                              int method, int* out_idx, double* out_d, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+    RF_CHECK_ARG(bank && q && out_idx && out_d, "rf_knn_l2_topk: null pointer");
+    RF_CHECK_ARG(D == 64, "rf_knn_l2_topk: latent_dim must be 64 (got %d)", D);
+    RF_CHECK_ARG(Q > 0 && n_rows > 0, "rf_knn_l2_topk: empty bank or query set");
+    RF_CHECK_ARG(k >= 1 && k <= 32 && k <= n_rows, "rf_knn_l2_topk: k=%d out of range (1..min(32, n_rows=%ld))", k, n_rows);
+    RF_CHECK_ARG(row_offset >= 0 && row_offset + n_rows < (1L << 31), "rf_knn_l2_topk: row ids exceed int32");
+    RF_CHECK_ARG(((uintptr_t)bank & 15) == 0 && ((uintptr_t)q & 15) == 0, "rf_knn_l2_topk: bank / q must be 16-byte aligned");
+    RF_CHECK_ARG(method >= 0 && method <= 2, "rf_knn_l2_topk: bad method %d", method);
+    if (method == 0) method = (Q >= 1024 && n_rows >= 4096 && k <= 16) ? 2 : 1;
+    if (method == 2)
+        return rf_knn_tc_launch(bank, n_rows, row_offset, q, Q, k, out_idx, out_d, workspace, workspace_bytes, (cudaStream_t)stream);
+    return rf_knn_exact_launch(bank, n_rows, row_offset, q, Q, k, out_idx, out_d, workspace, workspace_bytes, (cudaStream_t)stream);
+}

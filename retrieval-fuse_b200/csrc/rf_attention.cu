@@ -1,0 +1,213 @@
+// Patch attention (model/attention.py:49-157) on the GPU.
+//
+// Rows: one row per (chunk b, sub-patch r) with r in [0, (S/E)^3); a row's
+// vector is the nf*E^3 values of that sub-patch in (c, ex, ey, ez) order -
+// exactly Unfold3D(E, nf)'s row layout.  The K retrieved candidates of a row
+// are kept in (b, k, r) order (the order Unfold3D produces on x_retr), the
+// reference's permute to (b, r, k) is only an indexing change.
+//
+// Stage plan (round 1): unfold -> theta / phi MLPs through the implicit-GEMM
+// kernel -> one warp-per-row epilogue (normalise, scores, ReLU-max switch,
+// softmax(1024 s) or hard Gumbel arg-max, weighted sum of the raw candidate
+// vectors, blend) -> fold.
+#include <float.h>
+
+#include "rf_common.cuh"
+
+namespace {
+
+constexpr int FEAT = 32;    // cf_feat, model/attention.py:54
+constexpr int HIDDEN = 128; // model/attention.py:35-41
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// xf [R,32], pf [(b,k,r),32], xu [R,V], pu [(b,k,r),V] -> orows [R,V]
+__global__ void __launch_bounds__(256) attention_epilogue_kernel(const float* __restrict__ xf, const float* __restrict__ pf,
+                                                                 const float* __restrict__ xu, const float* __restrict__ pu,
+                                                                 const float* __restrict__ noise, float* __restrict__ orows,
+                                                                 long R, int rp3, int K, int V, int normalize, int mode,
+                                                                 int blend, float sharp) {
+    const long row = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= R) return;
+    const long b = row / rp3, rr = row % rp3;
+    const long prow0 = b * K * rp3 + rr;  // candidate k lives at prow0 + k * rp3
+
+    float xv = xf[row * FEAT + lane];
+    if (normalize) {
+        const float n = fmaxf(sqrtf(warp_sum(xv * xv)), 1e-12f);  // F.normalize eps
+        xv = xv / n;
+    }
+    float my_s = -FLT_MAX;  // lane k holds score k
+    for (int k = 0; k < K; ++k) {
+        float pv = pf[(prow0 + (long)k * rp3) * FEAT + lane];
+        if (normalize) {
+            const float n = fmaxf(sqrtf(warp_sum(pv * pv)), 1e-12f);
+            pv = pv / n;
+        }
+        const float s = warp_sum(xv * pv);
+        if (lane == k) my_s = s;
+    }
+    const float smax = warp_max(my_s);
+    const float sw = fmaxf(smax, 0.f);  // relu(max_k s), model/attention.py:99
+    float w = 0.f;                      // lane k holds weight k
+    if (mode == 0) {
+        const float z = lane < K ? sharp * my_s : -FLT_MAX;
+        const float zmax = warp_max(z);
+        const float e = lane < K ? expf(z - zmax) : 0.f;
+        const float den = warp_sum(e);
+        w = e / den;
+    } else {
+        // gumbel_softmax(25 s, tau=1, hard=True): y_hard - y_soft + y_soft
+        const float z = lane < K ? (25.f * my_s + noise[row * K + lane]) : -FLT_MAX;
+        const float zmax = warp_max(z);
+        const float e = lane < K ? expf(z - zmax) : 0.f;
+        const float den = warp_sum(e);
+        const float y = e / den;
+        // arg-max of y_soft, first index on ties
+        const float ymax = warp_max(lane < K ? y : -FLT_MAX);
+        const unsigned mm = __ballot_sync(0xffffffffu, lane < K && y == ymax);
+        const int arg = __ffs(mm) - 1;
+        const float hard = lane == arg ? 1.f : 0.f;
+        w = lane < K ? (hard - y) + y : 0.f;
+    }
+    const float* xrow = xu + row * V;
+    float* orow = orows + row * V;
+    for (int v = lane; v < V; v += 32) {
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float wk = __shfl_sync(0xffffffffu, w, k);
+            acc = fmaf(wk, pu[(prow0 + (long)k * rp3) * V + v], acc);
+        }
+        const float x = xrow[v];
+        orow[v] = blend ? (x * (1.f - sw) + acc * sw) : (x + acc * sw);
+    }
+}
+
+__global__ void __launch_bounds__(256) occ_any_kernel(const uint8_t* __restrict__ occ, uint8_t* __restrict__ out, int B, int S,
+                                                      int E) {
+    const int Rp = S / E;
+    const long total = (long)B * Rp * Rp * Rp;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long t = i;
+        const int pz = (int)(t % Rp); t /= Rp;
+        const int py = (int)(t % Rp); t /= Rp;
+        const int px = (int)(t % Rp); t /= Rp;
+        uint8_t any = 0;
+        for (int ex = 0; ex < E; ++ex)
+            for (int ey = 0; ey < E; ++ey)
+                for (int ez = 0; ez < E; ++ez)
+                    any |= occ[((t * S + px * E + ex) * S + py * E + ey) * (long)S + pz * E + ez] != 0;
+        out[i] = any;
+    }
+}
+
+struct AttnWs {
+    float *xu, *pu, *ha, *hb, *xf, *pf, *orows;
+};
+
+size_t attn_ws_layout(int B, int nf, int S, int E, int K, AttnWs* ws, char* base) {
+    const size_t Rp = S / E, R = (size_t)B * Rp * Rp * Rp, V = (size_t)nf * E * E * E;
+    const size_t Kc = K > 1 ? K : 1;
+    size_t off = 0;
+    auto take = [&](size_t n_floats) {
+        float* p = (float*)(base + off);
+        off += (n_floats * sizeof(float) + 255) / 256 * 256;
+        return p;
+    };
+    float* xu = take(R * V);
+    float* pu = take(R * Kc * V);
+    float* ha = take(R * Kc * HIDDEN);
+    float* hb = take(R * Kc * HIDDEN);
+    float* xf = take(R * FEAT);
+    float* pf = take(R * Kc * FEAT);
+    float* orows = take(R * V);
+    if (ws) { ws->xu = xu; ws->pu = pu; ws->ha = ha; ws->hb = hb; ws->xf = xf; ws->pf = pf; ws->orows = orows; }
+    return off;
+}
+
+// theta / phi: Linear(V,128) LeakyReLU Linear(128,128) LeakyReLU Linear(128,128) LeakyReLU Linear(128,32)
+int run_mlp(const float* in, long rows, int V, const float* const* wt, const float* const* b, float* ha, float* hb, float* out,
+            void* stream) {
+    RF_CHECK_ARG(rows < (1L << 31), "attention: too many rows");
+    const float slope = 0.01f;  // nn.LeakyReLU() default
+    int rc;
+    if ((rc = rf_linear_fwd(in, wt[0], b[0], ha, (int)rows, V, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;
+    if ((rc = rf_linear_fwd(ha, wt[1], b[1], hb, (int)rows, HIDDEN, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;
+    if ((rc = rf_linear_fwd(hb, wt[2], b[2], ha, (int)rows, HIDDEN, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;
+    return rf_linear_fwd(ha, wt[3], b[3], out, (int)rows, HIDDEN, FEAT, RF_ACT_NONE, 0.f, stream);
+}
+
+}  // namespace
+
+extern "C" size_t rf_attention_workspace_bytes(int B, int nf, int S, int E, int K) {
+    if (B <= 0 || nf <= 0 || S <= 0 || E <= 0 || K <= 0 || S % E) return 0;
+    return attn_ws_layout(B, nf, S, E, K, nullptr, nullptr);
+}
+
+extern "C" int rf_attention_fuse_fwd(const float* x_back, const float* x_retr, const float* const* theta_wt_host,
+                                     const float* const* theta_b_host, const float* const* phi_wt_host,
+                                     const float* const* phi_b_host, const float* gumbel_noise, float* out, int B, int nf,
+                                     int S, int E, int K, int normalize, int mode, int blend, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+    RF_CHECK_ARG(x_back && x_retr && out && theta_wt_host && theta_b_host && phi_wt_host && phi_b_host && workspace,
+                 "rf_attention_fuse_fwd: null pointer");
+    RF_CHECK_ARG(B > 0 && nf > 0 && S > 0 && E > 0 && S % E == 0, "rf_attention_fuse_fwd: bad shape");
+    RF_CHECK_ARG(K >= 1 && K <= 32, "rf_attention_fuse_fwd: K=%d unsupported (1..32)", K);
+    RF_CHECK_ARG(mode == 0 || (mode == 1 && gumbel_noise), "rf_attention_fuse_fwd: retrieval mode needs the Gumbel noise");
+    RF_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "rf_attention_fuse_fwd: workspace must be 256-byte aligned");
+    AttnWs ws;
+    const size_t need = attn_ws_layout(B, nf, S, E, K, &ws, (char*)workspace);
+    RF_CHECK_ARG(workspace_bytes >= need, "rf_attention_fuse_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+    const int Rp = S / E, rp3 = Rp * Rp * Rp, V = nf * E * E * E;
+    const long R = (long)B * rp3;
+    int rc;
+    if ((rc = rf_unfold3d(x_back, ws.xu, B, nf, S, E, stream))) return rc;
+    if ((rc = rf_unfold3d(x_retr, ws.pu, B * K, nf, S, E, stream))) return rc;
+    if ((rc = run_mlp(ws.xu, R, V, theta_wt_host, theta_b_host, ws.ha, ws.hb, ws.xf, stream))) return rc;
+    if ((rc = run_mlp(ws.pu, R * K, V, phi_wt_host, phi_b_host, ws.ha, ws.hb, ws.pf, stream))) return rc;
+    const float sharp = (float)(FEAT * E * E * E * 4);  // model/attention.py:105
+    attention_epilogue_kernel<<<(unsigned)rf_cdivl(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        ws.xf, ws.pf, ws.xu, ws.pu, gumbel_noise, ws.orows, R, rp3, K, V, normalize, mode, blend, sharp);
+    RF_LAUNCH_OK("attention_epilogue_kernel");
+    return rf_fold3d(ws.orows, out, B, nf, Rp, E, stream);
+}
+
+extern "C" int rf_attention_features(const float* x, const float* t, const uint8_t* occ, const float* const* theta_wt_host,
+                                     const float* const* theta_b_host, const float* const* phi_wt_host,
+                                     const float* const* phi_b_host, float* x_feat, float* p_feat, uint8_t* occ_any, int B,
+                                     int nf, int S, int E, int normalize, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    RF_CHECK_ARG(x && t && x_feat && p_feat && theta_wt_host && theta_b_host && phi_wt_host && phi_b_host && workspace,
+                 "rf_attention_features: null pointer");
+    RF_CHECK_ARG(B > 0 && nf > 0 && S > 0 && E > 0 && S % E == 0, "rf_attention_features: bad shape");
+    RF_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "rf_attention_features: workspace must be 256-byte aligned");
+    AttnWs ws;
+    const size_t need = attn_ws_layout(B, nf, S, E, 1, &ws, (char*)workspace);
+    RF_CHECK_ARG(workspace_bytes >= need, "rf_attention_features: workspace too small (%zu < %zu)", workspace_bytes, need);
+    const int Rp = S / E, V = nf * E * E * E;
+    const long R = (long)B * Rp * Rp * Rp;
+    int rc;
+    if ((rc = rf_unfold3d(x, ws.xu, B, nf, S, E, stream))) return rc;
+    if ((rc = rf_unfold3d(t, ws.pu, B, nf, S, E, stream))) return rc;
+    if ((rc = run_mlp(ws.xu, R, V, theta_wt_host, theta_b_host, ws.ha, ws.hb, normalize ? ws.xf : x_feat, stream))) return rc;
+    if ((rc = run_mlp(ws.pu, R, V, phi_wt_host, phi_b_host, ws.ha, ws.hb, normalize ? ws.pf : p_feat, stream))) return rc;
+    if (normalize) {
+        if ((rc = rf_l2_normalize_rows(ws.xf, x_feat, R, FEAT, 1e-12f, stream))) return rc;
+        if ((rc = rf_l2_normalize_rows(ws.pf, p_feat, R, FEAT, 1e-12f, stream))) return rc;
+    }
+    if (occ && occ_any) {
+        occ_any_kernel<<<rf_grid_1d(R, 256), 256, 0, (cudaStream_t)stream>>>(occ, occ_any, B, S, E);
+        RF_LAUNCH_OK("occ_any_kernel");
+    }
+    return 0;
+}

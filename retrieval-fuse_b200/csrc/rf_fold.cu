@@ -1,0 +1,260 @@
+// Patch fold / unfold / pad-unfold / recompose / compose / pool / upsample:
+// pure re-indexing kernels, HBM-bound.  Each thread moves one contiguous run
+// of the innermost axis so that both the read and the write side coalesce as
+// far as the permutation allows; grids are sized in multiples of the SM count
+// (rf_grid_1d) and walk the output with a grid-stride loop.
+#include "rf_common.cuh"
+
+// ---------------------------------------------------------------------------
+// Unfold3D / Fold3D (model/attention.py:160-188).  One index space for both:
+// element (b, px,py,pz, c, ex,ey,ez) of the patch tensor <-> element
+// (b, c, px*E+ex, py*E+ey, pz*E+ez) of the volume.
+// ---------------------------------------------------------------------------
+template <bool kFold>
+__global__ void __launch_bounds__(256) fold_unfold_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
+                                                          int C, int R, int E) {
+    const long total = (long)B * C * R * R * R * E * E * E;
+    const int S = R * E;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        // decompose the PATCH-side linear index
+        long t = i;
+        const int ez = (int)(t % E); t /= E;
+        const int ey = (int)(t % E); t /= E;
+        const int ex = (int)(t % E); t /= E;
+        const int c = (int)(t % C); t /= C;
+        const int pz = (int)(t % R); t /= R;
+        const int py = (int)(t % R); t /= R;
+        const int px = (int)(t % R); t /= R;
+        const int b = (int)t;
+        const long v = ((((long)b * C + c) * S + (px * E + ex)) * S + (py * E + ey)) * S + (pz * E + ez);
+        if (kFold) out[v] = in[i];
+        else out[i] = in[v];
+    }
+}
+
+extern "C" int rf_unfold3d(const float* x, float* out, int B, int C, int S, int E, void* stream) {
+    RF_CHECK_ARG(x && out, "rf_unfold3d: null pointer");
+    RF_CHECK_ARG(B > 0 && C > 0 && S > 0 && E > 0 && S % E == 0, "rf_unfold3d: bad shape B=%d C=%d S=%d E=%d", B, C, S, E);
+    const long total = (long)B * C * S * S * S;
+    fold_unfold_kernel<false><<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, C, S / E, E);
+    RF_LAUNCH_OK("fold_unfold_kernel<unfold>");
+    return 0;
+}
+
+extern "C" int rf_fold3d(const float* x, float* out, int B, int C, int R, int E, void* stream) {
+    RF_CHECK_ARG(x && out, "rf_fold3d: null pointer");
+    RF_CHECK_ARG(B > 0 && C > 0 && R > 0 && E > 0, "rf_fold3d: bad shape B=%d C=%d R=%d E=%d", B, C, R, E);
+    const long total = (long)B * C * R * R * R * E * E * E;
+    fold_unfold_kernel<true><<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, C, R, E);
+    RF_LAUNCH_OK("fold_unfold_kernel<fold>");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Unfold3DPadStride / Patcher.__call__ with optional fused normalisation.
+// ---------------------------------------------------------------------------
+struct Int3 { int v[3]; };
+
+__global__ void __launch_bounds__(256) pad_unfold_kernel(const float* __restrict__ x, float* __restrict__ out, int B,
+                                                         int C, Int3 size, Int3 kernel, Int3 pad, Int3 stride, Int3 cnt,
+                                                         float pad_val, float norm_sub, float norm_div) {
+    const long total = (long)B * cnt.v[0] * cnt.v[1] * cnt.v[2] * C * kernel.v[0] * kernel.v[1] * kernel.v[2];
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long t = i;
+        const int kz = (int)(t % kernel.v[2]); t /= kernel.v[2];
+        const int ky = (int)(t % kernel.v[1]); t /= kernel.v[1];
+        const int kx = (int)(t % kernel.v[0]); t /= kernel.v[0];
+        const int c = (int)(t % C); t /= C;
+        const int iz = (int)(t % cnt.v[2]); t /= cnt.v[2];
+        const int iy = (int)(t % cnt.v[1]); t /= cnt.v[1];
+        const int ix = (int)(t % cnt.v[0]); t /= cnt.v[0];
+        const int b = (int)t;
+        const int sx = ix * stride.v[0] + kx - pad.v[0];
+        const int sy = iy * stride.v[1] + ky - pad.v[1];
+        const int sz = iz * stride.v[2] + kz - pad.v[2];
+        float v = pad_val;
+        if (sx >= 0 && sx < size.v[0] && sy >= 0 && sy < size.v[1] && sz >= 0 && sz < size.v[2])
+            v = x[((((long)b * C + c) * size.v[0] + sx) * size.v[1] + sy) * size.v[2] + sz];
+        if (norm_div != 0.f) v = __fdiv_rn(__fsub_rn(v, norm_sub), norm_div);  // two rounded fp32 ops, as numpy does
+        out[i] = v;
+    }
+}
+
+extern "C" int rf_unfold3d_pad_stride(const float* x, float* out, int B, int C, const int size[3], const int kernel[3],
+                                      const int pad[3], const int stride[3], float pad_val, float norm_sub,
+                                      float norm_div, void* stream) {
+    RF_CHECK_ARG(x && out && size && kernel && pad && stride, "rf_unfold3d_pad_stride: null pointer");
+    Int3 s, k, p, st, cnt;
+    long total = (long)B * C;
+    for (int a = 0; a < 3; ++a) {
+        s.v[a] = size[a]; k.v[a] = kernel[a]; p.v[a] = pad[a]; st.v[a] = stride[a];
+        RF_CHECK_ARG(size[a] > 0 && kernel[a] > 0 && pad[a] >= 0 && stride[a] > 0, "rf_unfold3d_pad_stride: bad axis %d", a);
+        RF_CHECK_ARG(size[a] + 2 * pad[a] >= kernel[a], "rf_unfold3d_pad_stride: kernel larger than padded input");
+        cnt.v[a] = (size[a] + 2 * pad[a] - kernel[a]) / stride[a] + 1;  // Tensor.unfold count
+        total *= (long)cnt.v[a] * kernel[a];
+    }
+    RF_CHECK_ARG(B > 0 && C > 0, "rf_unfold3d_pad_stride: bad B/C");
+    pad_unfold_kernel<<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, C, s, k, p, st, cnt, pad_val,
+                                                                               norm_sub, norm_div);
+    RF_LAUNCH_OK("pad_unfold_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Patcher.recompose_patches as a gather: the reference writes patches in scan
+// order (x outer, z inner) so the last writer of a voxel is the patch with the
+// largest covering index along every axis.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) recompose_kernel(const float* __restrict__ patches, float* __restrict__ out,
+                                                        int B, int C, Int3 size, Int3 kernel, Int3 pad, Int3 stride,
+                                                        Int3 cnt, float pad_val) {
+    const long total = (long)B * C * size.v[0] * size.v[1] * size.v[2];
+    const long n_patches = (long)cnt.v[0] * cnt.v[1] * cnt.v[2];
+    const long kvol = (long)kernel.v[0] * kernel.v[1] * kernel.v[2];
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long t = i;
+        int co[3];
+        co[2] = (int)(t % size.v[2]); t /= size.v[2];
+        co[1] = (int)(t % size.v[1]); t /= size.v[1];
+        co[0] = (int)(t % size.v[0]); t /= size.v[0];
+        t /= C;  // channel: every channel receives the same patch data (broadcast assignment)
+        const int b = (int)t;
+        int pi[3], off[3];
+        bool covered = true;
+        for (int a = 0; a < 3; ++a) {
+            const int pc = co[a] + pad.v[a];  // coordinate in the padded volume
+            int idx = pc / stride.v[a];
+            if (idx > cnt.v[a] - 1) idx = cnt.v[a] - 1;
+            const int o = pc - idx * stride.v[a];
+            if (o >= kernel.v[a]) covered = false;
+            pi[a] = idx; off[a] = o;
+        }
+        float v = pad_val;
+        if (covered) {
+            const long p = ((long)pi[0] * cnt.v[1] + pi[1]) * cnt.v[2] + pi[2];
+            v = patches[((long)b * n_patches + p) * kvol + ((long)off[0] * kernel.v[1] + off[1]) * kernel.v[2] + off[2]];
+        }
+        out[i] = v;
+    }
+}
+
+extern "C" int rf_recompose_patches(const float* patches, float* out, int B, int C, const int size[3],
+                                    const int kernel[3], const int pad[3], const int stride[3], const int count[3],
+                                    float pad_val, void* stream) {
+    RF_CHECK_ARG(patches && out && size && kernel && pad && stride && count, "rf_recompose_patches: null pointer");
+    Int3 s, k, p, st, cnt;
+    long total = (long)B * C;
+    for (int a = 0; a < 3; ++a) {
+        s.v[a] = size[a]; k.v[a] = kernel[a]; p.v[a] = pad[a]; st.v[a] = stride[a]; cnt.v[a] = count[a];
+        RF_CHECK_ARG(size[a] > 0 && kernel[a] > 0 && pad[a] >= 0 && stride[a] > 0 && count[a] > 0,
+                     "rf_recompose_patches: bad axis %d", a);
+        RF_CHECK_ARG((count[a] - 1) * stride[a] + kernel[a] <= size[a] + 2 * pad[a],
+                     "rf_recompose_patches: patches exceed the padded volume on axis %d", a);
+        total *= size[a];
+    }
+    recompose_kernel<<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(patches, out, B, C, s, k, p, st, cnt,
+                                                                              pad_val);
+    RF_LAUNCH_OK("recompose_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// compose: out[c,k,dst block] = store[scene][src block] * ratio
+// (util/retrieval.py:145-164).  One CTA per (chunk, k, patch).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ rows, const int* __restrict__ dst_ext,
+                                                      const float* __restrict__ store, float* __restrict__ out, int P,
+                                                      int K, int n_scenes, Int3 ssz, Int3 csz, float trunc, float ratio) {
+    const int p = blockIdx.x, k = blockIdx.y, c = blockIdx.z;
+    const float* row = rows + (((long)c * P + p) * K + k) * 8;
+    const int scene = (int)row[0];
+    // .astype(np.int32) on fp32 extents (util/retrieval.py:153)
+    const int X0 = (int)row[1], X1 = (int)row[2], Y0 = (int)row[3], Y1 = (int)row[4], Z0 = (int)row[5], Z1 = (int)row[6];
+    const int* de = dst_ext + p * 6;
+    const int ex = de[1] - de[0], ey = de[3] - de[2], ez = de[5] - de[4];
+    // the sentinel block is a float64 numpy array in the reference (:161), so the
+    // product is rounded to fp32 only once, on assignment
+    const float fill = (float)((double)trunc * (double)ratio);
+    float* o = out + ((long)c * K + k) * csz.v[0] * csz.v[1] * csz.v[2];
+    const float* s = store + (long)(scene < 0 ? 0 : scene) * ssz.v[0] * ssz.v[1] * ssz.v[2];
+    const int n = ex * ey * ez;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int z = i % ez, y = (i / ez) % ey, x = i / (ez * ey);
+        float v = fill;
+        const int sx = X0 + x, sy = Y0 + y, sz = Z0 + z;
+        // numpy slicing clips at the array end; a block that is narrower than
+        // the destination would raise in the reference, so only in-range
+        // voxels are defined - anything else keeps the truncation value.
+        if (scene >= 0 && scene < n_scenes && sx < X1 && sy < Y1 && sz < Z1 && sx >= 0 && sy >= 0 && sz >= 0 &&
+            sx < ssz.v[0] && sy < ssz.v[1] && sz < ssz.v[2])
+            v = __fmul_rn(s[((long)sx * ssz.v[1] + sy) * ssz.v[2] + sz], ratio);
+        o[((long)(de[0] + x) * csz.v[1] + (de[2] + y)) * csz.v[2] + (de[4] + z)] = v;
+    }
+}
+
+extern "C" int rf_compose_gather(const float* rows, const int* dst_extents, const float* scene_store, float* out,
+                                 int n_chunks, int P, int K, int n_scenes, const int scene_size[3],
+                                 const int chunk_size[3], float trunc, float ratio, void* stream) {
+    RF_CHECK_ARG(rows && dst_extents && scene_store && out && scene_size && chunk_size, "rf_compose_gather: null pointer");
+    RF_CHECK_ARG(n_chunks > 0 && P > 0 && K > 0 && n_scenes > 0 && K <= 65535 && n_chunks <= 65535,
+                 "rf_compose_gather: bad sizes");
+    Int3 s, c;
+    for (int a = 0; a < 3; ++a) { s.v[a] = scene_size[a]; c.v[a] = chunk_size[a]; }
+    dim3 grid(P, K, n_chunks);
+    compose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, dst_extents, scene_store, out, P, K, n_scenes, s, c,
+                                                          trunc, ratio);
+    RF_LAUNCH_OK("compose_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// MaxPool3d(2) and nearest 2x upsample
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__ x, float* __restrict__ y, long NC, int D,
+                                                       int H, int W) {
+    const int Do = D / 2, Ho = H / 2, Wo = W / 2;
+    const long total = NC * Do * Ho * Wo;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long t = i;
+        const int w = (int)(t % Wo); t /= Wo;
+        const int h = (int)(t % Ho); t /= Ho;
+        const int d = (int)(t % Do); t /= Do;
+        const float* p = x + ((t * D + 2 * d) * H + 2 * h) * (long)W + 2 * w;
+        float m = p[0];
+        m = fmaxf(m, p[1]);
+        m = fmaxf(m, p[W]); m = fmaxf(m, p[W + 1]);
+        const float* p2 = p + (long)H * W;
+        m = fmaxf(m, p2[0]); m = fmaxf(m, p2[1]);
+        m = fmaxf(m, p2[W]); m = fmaxf(m, p2[W + 1]);
+        y[i] = m;
+    }
+}
+
+extern "C" int rf_maxpool3d_2(const float* x, float* y, int N, int C, int D, int H, int W, void* stream) {
+    RF_CHECK_ARG(x && y && N > 0 && C > 0 && D >= 2 && H >= 2 && W >= 2, "rf_maxpool3d_2: bad arguments");
+    const long total = (long)N * C * (D / 2) * (H / 2) * (W / 2);
+    maxpool2_kernel<<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, (long)N * C, D, H, W);
+    RF_LAUNCH_OK("maxpool2_kernel");
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) upsample2_kernel(const float* __restrict__ x, float* __restrict__ y, long NC, int D,
+                                                        int H, int W) {
+    const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
+    const long total = NC * Do * Ho * Wo;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long t = i;
+        const int w = (int)(t % Wo); t /= Wo;
+        const int h = (int)(t % Ho); t /= Ho;
+        const int d = (int)(t % Do); t /= Do;
+        y[i] = x[((t * D + d / 2) * H + h / 2) * (long)W + w / 2];
+    }
+}
+
+extern "C" int rf_upsample_nearest_2(const float* x, float* y, int N, int C, int D, int H, int W, void* stream) {
+    RF_CHECK_ARG(x && y && N > 0 && C > 0 && D > 0 && H > 0 && W > 0, "rf_upsample_nearest_2: bad arguments");
+    const long total = (long)N * C * D * H * W * 8;
+    upsample2_kernel<<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, (long)N * C, D, H, W);
+    RF_LAUNCH_OK("upsample2_kernel");
+    return 0;
+}

@@ -1,0 +1,138 @@
+"""model/attention.py: 3-D fold / unfold modules and the patch attention block
+with the reference's names, signatures and state_dict keys."""
+import torch
+from torch import nn
+
+from .. import ops
+from ._base import RfModule
+
+
+class AttentionFeatureEncoder(nn.Module):
+    """model/attention.py:29-46 (parameter container; the MLP runs inside
+    rf_attention_fuse_fwd / rf_attention_features)."""
+
+    def __init__(self, n_in, n_out, e):
+        super().__init__()
+        self.n_in = n_in * (e ** 3)
+        self.n_out = n_out
+        self.encoder = nn.Sequential(nn.Linear(self.n_in, 128), nn.LeakyReLU(), nn.Linear(128, 128), nn.LeakyReLU(),
+                                     nn.Linear(128, 128), nn.LeakyReLU(), nn.Linear(128, self.n_out))
+
+    def linears(self):
+        return [m for m in self.encoder if isinstance(m, nn.Linear)]
+
+
+class AttentionBlock(RfModule):
+    """model/attention.py:49-116."""
+
+    def __init__(self, num_output_channels, patch_extent, K, normalize, use_switching, retrieval_mode,
+                 no_output_mapping, blend):
+        super().__init__()
+        if not no_output_mapping:
+            raise NotImplementedError("attn_no_output_mapping=False (1x1x1 g/o convs) is not used by any shipped "
+                                      "config and is not implemented by the rf_b200 kernels")
+        self.cf_op = num_output_channels
+        self.cf_feat = 32
+        self.patch_extent = patch_extent
+        self.K = K
+        self.theta = AttentionFeatureEncoder(num_output_channels, self.cf_feat, patch_extent)
+        self.phi = AttentionFeatureEncoder(num_output_channels, self.cf_feat, patch_extent)
+        self.g = nn.Identity()
+        self.o = nn.Identity()
+        self.init_scale = 35
+        self.init_shift = -27
+        # unused in the reference's forward (:97-99) but part of its state_dict
+        self.sig_scale = nn.Parameter(torch.ones(1) * self.init_scale)
+        self.sig_shift = nn.Parameter(torch.ones(1) * self.init_shift)
+        self.retrieval_mode = retrieval_mode
+        self.blend_mode = blend
+        self.use_switching = use_switching
+        self.normalize = normalize
+
+    def _branch(self, enc):
+        lin = enc.linears()
+        return [self._wt(m.weight) for m in lin], [m.bias for m in lin]
+
+    def get_regularization_losses(self):
+        return ((self.sig_scale - self.init_scale) ** 2 + (self.sig_shift - self.init_shift) ** 2) if self.use_switching else 0
+
+
+class PatchedAttentionBlock(nn.Module):
+    """model/attention.py:119-157."""
+
+    def __init__(self, nf, num_patch_x, patch_extent, num_nearest_neighbors, attention_block):
+        super().__init__()
+        self.num_patch_x = num_patch_x
+        self.patch_extent = patch_extent
+        self.num_nearest_neighbors = num_nearest_neighbors
+        self.nf = nf
+        self.attention_blocks_layer = attention_block
+        self.fold_3d = Fold3D(num_patch_x, patch_extent, self.nf)
+        self.unfold_3d = Unfold3D(patch_extent, self.nf)
+        self.unfold_3d_occ = Unfold3D(patch_extent, 1)
+
+    def get_features(self, x_predicted, x_target, occupancy):
+        ab = self.attention_blocks_layer
+        ops._forward_only(x_predicted, x_target, *ab.parameters())
+        return ops.attention_features(x_predicted, x_target, occupancy, ab._branch(ab.theta), ab._branch(ab.phi),
+                                      self.patch_extent, normalize=ab.normalize)
+
+    def forward(self, x_predicted, x_retrieved, gumbel_noise=None):
+        """x_predicted [B,F,S,S,S], x_retrieved [B*K,F,S,S,S] -> [B,F,S,S,S].
+        In retrieval (Gumbel) mode the noise [B*R^3, K] may be injected; when it
+        is not, it is drawn on the device as torch's gumbel_softmax does."""
+        ab = self.attention_blocks_layer
+        ops._forward_only(x_predicted, x_retrieved, *ab.parameters())
+        K = self.num_nearest_neighbors
+        if x_retrieved.shape[0] != x_predicted.shape[0] * K:
+            raise ValueError(f"x_retrieved has {x_retrieved.shape[0]} volumes, expected B*K = {x_predicted.shape[0] * K}")
+        if x_predicted.shape[2] != self.num_patch_x * self.patch_extent:
+            raise ValueError("feature volume edge must equal attn_num_patch * patch_extent")
+        mode = 1 if ab.retrieval_mode else 0
+        if mode == 1 and gumbel_noise is None:
+            rows = x_predicted.shape[0] * self.num_patch_x ** 3
+            gumbel_noise = -torch.empty(rows, K, device=x_predicted.device, dtype=torch.float32).exponential_().log()
+        return ops.attention_fuse(x_predicted, x_retrieved.reshape(-1, self.nf, *x_retrieved.shape[2:]),
+                                  ab._branch(ab.theta), ab._branch(ab.phi), self.patch_extent, K,
+                                  normalize=ab.normalize, mode=mode, blend=ab.blend_mode, gumbel_noise=gumbel_noise)
+
+
+class Fold3D(nn.Module):
+    """model/attention.py:160-176."""
+
+    def __init__(self, num_patch_x, patch_extent, nf):
+        super().__init__()
+        self.nf = nf
+        self.num_patch_x = num_patch_x
+        self.patch_extent = patch_extent
+
+    def forward(self, x):
+        return ops.fold3d(x, self.num_patch_x, self.patch_extent, self.nf)
+
+
+class Unfold3D(nn.Module):
+    """model/attention.py:179-188."""
+
+    def __init__(self, patch_extent, nf):
+        super().__init__()
+        self.patch_extent = patch_extent
+        self.nf = nf
+
+    def forward(self, x):
+        if x.shape[1] != self.nf:
+            raise ValueError(f"Unfold3D was built for nf={self.nf}, input has {x.shape[1]} channels")
+        return ops.unfold3d(x, self.patch_extent)
+
+
+class Unfold3DPadStride(nn.Module):
+    """model/attention.py:191-203."""
+
+    def __init__(self, patch_extent, pad_size, pad_val, stride):
+        super().__init__()
+        self.patch_extent = patch_extent
+        self.pad_size = pad_size
+        self.pad_val = pad_val
+        self.stride = stride
+
+    def forward(self, x):
+        return ops.unfold3d_pad_stride(x, self.patch_extent, self.pad_size, self.stride, self.pad_val)

@@ -1,0 +1,87 @@
+"""model/refinement.py:6-73 - the task-specific U-Net wirings."""
+import torch
+from torch import nn
+
+from .. import ops
+from ._base import RfModule
+from .unet import UNet3D, DecoderNoJoining
+
+
+class _Chain(nn.Module):
+    def forward(self, x):
+        for net in self.network:
+            x = net(x)
+        return x
+
+
+class Superresolution08UNetBackbone(_Chain):
+    """model/refinement.py:6-19: [B,1,8^3] -> [B,nf,32^3]."""
+
+    def __init__(self, nf, num_levels, layer_order):
+        super().__init__()
+        self.network = nn.ModuleList([
+            UNet3D(in_channels=1, out_channels=2 * nf, final_sigmoid=False, final_conv=False, f_maps=nf,
+                   num_groups=nf // 2, layer_order=layer_order, num_levels=num_levels, is_segmentation=False),
+            DecoderNoJoining(2 * nf, 2 * nf, conv_layer_order=layer_order, num_groups=nf // 2),
+            DecoderNoJoining(2 * nf, nf, conv_layer_order=layer_order, num_groups=nf // 2),
+        ])
+
+
+class Superresolution16UNetBackbone(_Chain):
+    """model/refinement.py:22-34: [B,1,16^3] -> [B,nf,32^3]."""
+
+    def __init__(self, nf, num_levels, layer_order):
+        super().__init__()
+        self.network = nn.ModuleList([
+            UNet3D(in_channels=1, out_channels=2 * nf, final_sigmoid=False, final_conv=False, f_maps=nf,
+                   num_groups=nf // 2, layer_order=layer_order, num_levels=num_levels, is_segmentation=False),
+            DecoderNoJoining(2 * nf, nf, conv_layer_order=layer_order, num_groups=nf // 2),
+        ])
+
+
+class SurfaceReconstructionUNetBackbone(nn.Module):
+    """model/refinement.py:37-45: [B,1,128^3] -> [B,nf,32^3]."""
+
+    def __init__(self, nf, num_levels, layer_order):
+        super().__init__()
+        self.network = UNet3D(in_channels=1, out_channels=nf, final_sigmoid=False, final_conv=False,
+                              remove_n_final_layers=2, f_maps=nf, layer_order=layer_order, num_groups=nf // 2,
+                              num_levels=num_levels, is_segmentation=False)
+
+    def forward(self, x):
+        return self.network(x)
+
+
+class Superresolution08FinalDecoder(RfModule):
+    """model/refinement.py:48-61: nearest x2 + DoubleConv, 1x1x1 conv + bias, tanh
+    (bias and tanh are fused into the conv epilogue)."""
+
+    def __init__(self, nf, layer_order):
+        super().__init__()
+        self.network = nn.ModuleList([
+            DecoderNoJoining(nf, nf, conv_layer_order=layer_order, num_groups=nf // 2),
+            nn.Conv3d(nf, 1, 1, padding=0),
+            nn.Tanh(),
+        ])
+
+    def forward(self, x):
+        ops._forward_only(x, *self.parameters())
+        x = self.network[0](x)
+        head = self.network[1]
+        return ops.conv3d(x, self._wt(head.weight), head.bias, cout=1, ks=1, stride=1, pad=0, act=ops.ACT_TANH)
+
+
+class RetrievalUNetBackbone(nn.Module):
+    """model/refinement.py:64-73: per 16^3 patch [N,1,16^3] -> [N,nf,8^3].
+    (positional order is (f_maps, nf, ...) as in the reference; the factory
+    passes keywords.)"""
+
+    def __init__(self, f_maps, nf, num_levels, layer_order):
+        super().__init__()
+        self.nf = nf
+        self.network = UNet3D(in_channels=1, out_channels=nf, num_groups=nf // 2, final_sigmoid=False,
+                              final_conv=False, remove_n_final_layers=1, f_maps=f_maps, layer_order=layer_order,
+                              num_levels=num_levels, is_segmentation=False)
+
+    def forward(self, x):
+        return self.network(x)

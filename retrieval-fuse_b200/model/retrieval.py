@@ -1,0 +1,123 @@
+"""Patch encoders with the reference's class names, constructor signatures and
+state_dict keys (model/retrieval.py:4-388), executed by rf_conv3d_fwd /
+rf_mlp_encode_fwd.  The architectures come from one table instead of thirteen
+hand-written classes; `layers` keeps the reference's ModuleList indices so
+checkpoints load unchanged."""
+import torch
+from torch import nn
+
+from .. import ops
+from ._base import RfModule
+
+# (channel multiple of nf, kernel, stride) per Conv3d; LeakyReLU(0.2) after each.
+_CONV_SPECS = {
+    "Patch32": [(1, 5, 1), (2, 3, 1), (4, 3, 2), (8, 3, 1), (8, 3, 2), (8, 4, 1)],        # :4
+    "Patch08": [(1, 3, 1), (4, 3, 1), (4, 3, 1), (8, 2, 1)],                              # :136
+    "PCPatch32": [(1, 3, 1), (2, 3, 1), (4, 3, 2), (4, 3, 1), (8, 3, 2), (8, 3, 1), (8, 3, 1)],  # :187
+    "PCPatch48": [(1, 5, 1), (2, 3, 1), (4, 3, 2), (4, 3, 2), (8, 3, 2), (8, 3, 1), (8, 2, 1)],  # :217
+    "PCPatch64": [(1, 5, 1), (2, 3, 1), (4, 3, 2), (4, 3, 2), (8, 3, 2), (8, 3, 1), (8, 4, 1)],  # :247
+    "Patch16": [(1, 3, 1), (2, 3, 1), (2, 3, 1), (4, 3, 1), (4, 3, 1), (8, 3, 1), (8, 4, 1)],    # :277
+    "Patch24": [(1, 5, 1), (2, 3, 1), (2, 3, 2), (4, 3, 1), (8, 3, 1), (8, 3, 1), (8, 2, 1)],    # :306
+    "Patch24V2": [(1, 3, 1), (2, 3, 1), (2, 3, 2), (4, 3, 1), (8, 3, 1), (8, 3, 1), (8, 3, 1)],  # :335
+    "Patch12": [(1, 3, 1), (2, 3, 1), (4, 3, 1), (4, 3, 1), (8, 3, 1), (8, 2, 1)],               # :364
+}
+_CONV_SPECS["PatchNorm32"] = _CONV_SPECS["Patch32"]  # :31 (+BatchNorm3d after every conv)
+_CONV_SPECS["PatchNorm08"] = _CONV_SPECS["Patch08"]  # :160
+_MLP_SPECS = {  # (input patch edge, hidden widths as multiples of nf)
+    "Patch04": (4, [4, 8, 16, 8]),       # :64
+    "Patch05": (5, [4, 8, 16, 8]),       # :87
+    "Patch04V2": (4, [4, 8, 16, 16, 8]),  # :110
+}
+
+
+class _ConvPatchEncoder(RfModule):
+    _spec = None
+    _batchnorm = False
+
+    def __init__(self, nf, z_dim):
+        super().__init__()
+        mods, cin = [], 1
+        for mult, k, s in self._spec:
+            mods.append(nn.Conv3d(cin, mult * nf, kernel_size=k, stride=s, padding=0))
+            if self._batchnorm:
+                mods.append(nn.BatchNorm3d(mult * nf))
+            mods.append(nn.LeakyReLU(0.2, inplace=True))
+            cin = mult * nf
+        self.layers = nn.ModuleList(mods)  # parameter containers; never called
+        self.final_layer = nn.Linear(cin, z_dim)
+
+    def forward(self, x):
+        ops._forward_only(x, *self.parameters())
+        if self._batchnorm and self.training:
+            raise NotImplementedError("PatchNorm* encoders run in eval mode only (running statistics)")
+        h = x
+        i = 0
+        for _mult, k, s in self._spec:
+            conv = self.layers[i]
+            i += 1
+            oscale = oshift = None
+            if self._batchnorm:
+                bn = self.layers[i]
+                i += 1
+                oscale, oshift = self._wcache.derived(
+                    ("bn", i), [bn.weight, bn.bias, bn.running_mean, bn.running_var],
+                    lambda w, b, m, v, eps=bn.eps: ((w / torch.sqrt(v + eps)).contiguous(),
+                                                    (b - m * w / torch.sqrt(v + eps)).contiguous()))
+            i += 1  # LeakyReLU slot
+            h = ops.conv3d(h, self._wt(conv.weight), conv.bias, cout=conv.out_channels, ks=k, stride=s, pad=0,
+                           act=ops.ACT_LEAKY, slope=0.2, oscale=oscale, oshift=oshift)
+        h = h.reshape(h.shape[0], -1)  # spatial is 1^3 here (squeeze x3 in the reference)
+        z = ops.linear(h, self._wt(self.final_layer.weight), self.final_layer.bias)
+        return z.reshape(z.shape[0], z.shape[1], 1, 1, 1)
+
+
+class _MlpPatchEncoder(RfModule):
+    _spec = None
+
+    def __init__(self, nf, z_dim):
+        super().__init__()
+        edge, hidden = self._spec
+        widths = [edge ** 3] + [h * nf for h in hidden] + [z_dim]
+        mods = []
+        for j in range(len(widths) - 1):
+            mods.append(nn.Linear(widths[j], widths[j + 1]))
+            if j < len(widths) - 2:
+                mods.append(nn.ReLU())
+        self.layers = nn.ModuleList(mods)
+
+    def _linears(self):
+        return [m for m in self.layers if isinstance(m, nn.Linear)]
+
+    def forward(self, x):
+        return self.encode(x, l2_normalize=False)
+
+    def encode(self, x, l2_normalize):
+        """forward (+ optionally util/retrieval.py:66 row normalisation fused)."""
+        ops._forward_only(x, *self.parameters())
+        lin = self._linears()
+        h = x.reshape(x.shape[0], -1)
+        z = ops.mlp_encode(h, [self._wt(m.weight) for m in lin], [m.bias for m in lin], l2_normalize=l2_normalize)
+        return z.reshape(z.shape[0], z.shape[1], 1, 1, 1)
+
+
+def _make(name):
+    if name in _MLP_SPECS:
+        return type(name, (_MlpPatchEncoder,), {"_spec": _MLP_SPECS[name], "__doc__": f"model/retrieval.py {name}"})
+    return type(name, (_ConvPatchEncoder,), {"_spec": _CONV_SPECS[name], "_batchnorm": name.startswith("PatchNorm"),
+                                             "__doc__": f"model/retrieval.py {name}"})
+
+
+Patch32 = _make("Patch32")
+PatchNorm32 = _make("PatchNorm32")
+Patch04 = _make("Patch04")
+Patch05 = _make("Patch05")
+Patch04V2 = _make("Patch04V2")
+Patch08 = _make("Patch08")
+PatchNorm08 = _make("PatchNorm08")
+PCPatch32 = _make("PCPatch32")
+PCPatch48 = _make("PCPatch48")
+PCPatch64 = _make("PCPatch64")
+Patch16 = _make("Patch16")
+Patch24 = _make("Patch24")
+Patch24V2 = _make("Patch24V2")
+Patch12 = _make("Patch12")

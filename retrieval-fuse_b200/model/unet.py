@@ -1,0 +1,198 @@
+"""3D U-Net building blocks with the reference's module tree and state_dict
+keys (model/unet.py, itself derived from wolny/pytorch-3dunet), executed by
+the rf_b200 kernels: GroupNorm statistics -> implicit-GEMM conv with the
+normalisation fused into the operand load and ReLU fused into the epilogue;
+nearest upsampling and the skip concat are never materialised (the conv and
+the statistics kernels read the two sources directly)."""
+import torch
+from torch import nn
+
+from .. import ops
+from ._base import RfModule
+
+
+def number_of_features_per_level(init_channel_number, num_levels):
+    return [init_channel_number * 2 ** k for k in range(num_levels)]  # model/unet.py:11-12
+
+
+class SingleConv(RfModule):
+    """model/unet.py:79-100 + create_conv :19-76.  Supported orders: any
+    combination of one 'c', an optional 'g' BEFORE it and one of 'r' / 'l'
+    after it ('gcr' in every shipped config; also 'cr', 'cl', 'gcl', 'c', 'gc')."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, order="crg", num_groups=8, padding=1):
+        super().__init__()
+        assert "c" in order, "Conv layer MUST be present"
+        assert order[0] not in "rle", "Non-linearity cannot be the first operation in the layer"
+        if any(ch not in "gcrl" for ch in order) or ("g" in order and order.index("g") > order.index("c")):
+            raise NotImplementedError(f"layer order '{order}' is not supported by the rf_b200 kernels "
+                                      "(supported: [g]c[r|l]); every reference config uses 'gcr'")
+        self.order = order
+        self.kernel_size, self.padding = kernel_size, padding
+        self.in_channels, self.out_channels = in_channels, out_channels
+        for ch in order:  # registration order == the reference's add_module order
+            if ch == "g":
+                g = num_groups if in_channels >= num_groups else 1  # :60-62
+                assert in_channels % g == 0, (f"Expected number of channels in input to be divisible by num_groups. "
+                                              f"num_channels={in_channels}, num_groups={g}")
+                self.groupnorm = nn.GroupNorm(num_groups=g, num_channels=in_channels)
+            elif ch == "c":
+                bias = not ("g" in order or "b" in order)  # :52
+                self.conv = nn.Conv3d(in_channels, out_channels, kernel_size, padding=padding, bias=bias)
+        self.act = ops.ACT_RELU if "r" in order else (ops.ACT_LEAKY if "l" in order else ops.ACT_NONE)
+
+    def forward(self, x, x2=None):
+        """x2: optional half-resolution tensor, virtually upsampled x2 and
+        concatenated after x's channels (Decoder joining)."""
+        gn = None
+        if "g" in self.order:
+            g = self.groupnorm
+            if x is None:  # statistics of an upsampled volume == statistics of the volume
+                mu, a = ops.groupnorm_stats(x2, g.weight, g.num_groups, g.eps)
+            else:
+                mu, a = ops.groupnorm_stats(x, g.weight, g.num_groups, g.eps, x2=x2)
+            gn = (mu, a, g.bias)
+        return ops.conv3d(x, self._wt(self.conv.weight), self.conv.bias, cout=self.out_channels, ks=self.kernel_size,
+                          stride=1, pad=self.padding, act=self.act, slope=0.1, x2=x2, gn=gn)
+
+
+class DoubleConv(nn.Module):
+    """model/unet.py:103-144."""
+
+    def __init__(self, in_channels, out_channels, encoder, kernel_size=3, order="crg", num_groups=8):
+        super().__init__()
+        if encoder:
+            c1_in, c1_out = in_channels, out_channels // 2
+            if c1_out < in_channels:
+                c1_out = in_channels
+            c2_in, c2_out = c1_out, out_channels
+        else:
+            c1_in, c1_out = in_channels, out_channels
+            c2_in, c2_out = out_channels, out_channels
+        self.SingleConv1 = SingleConv(c1_in, c1_out, kernel_size, order, num_groups)
+        self.SingleConv2 = SingleConv(c2_in, c2_out, kernel_size, order, num_groups)
+
+    def forward(self, x, x2=None):
+        return self.SingleConv2(self.SingleConv1(x, x2))
+
+
+class StepDownDoubleConv(nn.Module):
+    """model/unet.py:147-159."""
+
+    def __init__(self, in_channels, out_channels, encoder, kernel_size=3, order="crg", num_groups=8):
+        super().__init__()
+        self.encoder = encoder
+        mid = (in_channels + out_channels) // 2
+        self.SingleConv1 = SingleConv(in_channels, mid, kernel_size, order, num_groups)
+        self.SingleConv2 = SingleConv(mid, out_channels, kernel_size, order, num_groups)
+
+    def forward(self, x, x2=None):
+        return self.SingleConv2(self.SingleConv1(x, x2))
+
+
+class Encoder(nn.Module):
+    """model/unet.py:210-253: optional MaxPool3d(2) then the basic module."""
+
+    def __init__(self, in_channels, out_channels, conv_kernel_size=3, apply_pooling=True, pool_kernel_size=(2, 2, 2),
+                 pool_type="max", basic_module=DoubleConv, conv_layer_order="crg", num_groups=8):
+        super().__init__()
+        assert pool_type in ["max", "avg"]
+        if apply_pooling and (pool_type != "max" or tuple(pool_kernel_size) != (2, 2, 2)):
+            raise NotImplementedError("only MaxPool3d(2) is used by the reference configs")
+        self.pooling = nn.MaxPool3d(kernel_size=pool_kernel_size) if apply_pooling else None  # marker only
+        self.basic_module = basic_module(in_channels, out_channels, encoder=True, kernel_size=conv_kernel_size,
+                                         order=conv_layer_order, num_groups=num_groups)
+
+    def forward(self, x):
+        if self.pooling is not None:
+            x = ops.maxpool3d_2(x)
+        return self.basic_module(x)
+
+
+class Decoder(nn.Module):
+    """model/unet.py:256-308 with nearest upsampling + concat joining (the
+    DoubleConv / StepDownDoubleConv case; ExtResNetBlock is unused by the reference)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, scale_factor=(2, 2, 2), basic_module=DoubleConv,
+                 conv_layer_order="crg", num_groups=8, mode="nearest"):
+        super().__init__()
+        if basic_module not in (DoubleConv, StepDownDoubleConv) or mode != "nearest" or tuple(scale_factor) != (2, 2, 2):
+            raise NotImplementedError("only nearest x2 upsampling with concat joining is implemented")
+        self.basic_module = basic_module(in_channels, out_channels, encoder=False, kernel_size=kernel_size,
+                                         order=conv_layer_order, num_groups=num_groups)
+
+    def forward(self, encoder_features, x):
+        if tuple(encoder_features.shape[2:]) != tuple(2 * s for s in x.shape[2:]):
+            raise NotImplementedError("encoder features must be exactly 2x the decoder input (even extents)")
+        return self.basic_module(encoder_features, x)  # concat(enc, up2(x)) is read in place
+
+
+class DecoderNoJoining(Decoder):
+    """model/unet.py:311-322: nearest x2 then DoubleConv (no skip connection).
+    The reference draws a torch.randn just to carry the target size; that RNG
+    side effect is not reproduced (it does not influence any output)."""
+
+    def forward(self, x):
+        return self.basic_module(None, x)
+
+
+class Abstract3DUNet(nn.Module):
+    """model/unet.py:392-520 (final_conv / segmentation heads are unused by the
+    reference's hot path and rejected here)."""
+
+    def __init__(self, in_channels, out_channels, final_sigmoid, basic_module, f_maps=64, layer_order="gcr",
+                 num_groups=8, num_levels=4, remove_n_final_layers=0, is_segmentation=False, final_conv=False,
+                 testing=False, **kwargs):
+        super().__init__()
+        if final_conv or is_segmentation or basic_module is not DoubleConv:
+            raise NotImplementedError("only UNet3D(final_conv=False, is_segmentation=False) is on the hot path")
+        self.testing = testing
+        if isinstance(f_maps, int):
+            f_maps = number_of_features_per_level(f_maps, num_levels=num_levels)
+        encoders = []
+        for i, out_feature_num in enumerate(f_maps):
+            if i == 0:
+                encoders.append(Encoder(in_channels, out_feature_num, apply_pooling=False, basic_module=basic_module,
+                                        conv_layer_order=layer_order, num_groups=num_groups))
+            else:
+                encoders.append(Encoder(f_maps[i - 1], out_feature_num, basic_module=basic_module,
+                                        conv_layer_order=layer_order, num_groups=num_groups))
+        self.encoders = nn.ModuleList(encoders)
+        rev = list(reversed(f_maps))
+        if remove_n_final_layers > 0:
+            rev = rev[:-remove_n_final_layers]
+        rev_mod = list(rev)
+        rev_mod[-1] = out_channels
+        decoders = []
+        for i in range(len(rev) - 1):
+            in_feature_num = rev[i] + rev[i + 1]
+            out_feature_num = rev_mod[i + 1]
+            step_down = i == (len(rev) - 2) and remove_n_final_layers > 0
+            decoders.append(Decoder(in_feature_num, out_feature_num,
+                                    basic_module=StepDownDoubleConv if step_down else basic_module,
+                                    conv_layer_order=layer_order, num_groups=num_groups))
+        self.decoders = nn.ModuleList(decoders)
+        self.final_conv = nn.Identity()
+        self.final_activation = None
+
+    def forward(self, x):
+        ops._forward_only(x, *self.parameters())
+        feats = []
+        for encoder in self.encoders:
+            x = encoder(x)
+            feats.insert(0, x)
+        feats = feats[1:]
+        for decoder, ef in zip(self.decoders, feats):
+            x = decoder(ef, x)
+        return x
+
+
+class UNet3D(Abstract3DUNet):
+    """model/unet.py:523-537."""
+
+    def __init__(self, in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order="gcr", num_groups=8,
+                 num_levels=4, is_segmentation=True, remove_n_final_layers=0, final_conv=False, **kwargs):
+        super().__init__(in_channels=in_channels, out_channels=out_channels, final_sigmoid=final_sigmoid,
+                         basic_module=DoubleConv, f_maps=f_maps, layer_order=layer_order, num_groups=num_groups,
+                         num_levels=num_levels, is_segmentation=is_segmentation, final_conv=final_conv,
+                         remove_n_final_layers=remove_n_final_layers, **kwargs)

@@ -1,0 +1,377 @@
+"""Tensor-level wrappers over the C ABI (include/rf_b200.h).
+
+torch is plumbing here: device memory, the current stream, dtype/shape checks.
+Every function launches the hand-written sm_100a kernels through ctypes on
+`torch.cuda.current_stream()`; CPU tensors are rejected (no fallback).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, int3, ptr_array
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
+
+# launches issued through this module since the last reset (bench.py's gpu_launches)
+_launches = 0
+_LAUNCHES_PER_CALL = {}
+
+
+def launches() -> int:
+    return _launches
+
+
+def reset_launches() -> None:
+    global _launches
+    _launches = 0
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _dev(t: torch.Tensor, dtype=torch.float32, name="tensor") -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.RfError(f"{name} must be a CUDA tensor: the rf_b200 ops have no CPU path")
+    if t.dtype != dtype:
+        raise _lib.RfError(f"{name} must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _forward_only(*tensors):
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            "rf_b200 kernels are forward-only in this round: call under torch.no_grad() "
+            "(the reference's --sanity_steps -1 inference mode)")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------------------
+# a2-a4
+# ---------------------------------------------------------------------------
+
+def unfold3d(x: torch.Tensor, E: int) -> torch.Tensor:
+    """model/attention.py:186-188."""
+    _forward_only(x)
+    x = _dev(x, name="x")
+    B, C, S = x.shape[0], x.shape[1], x.shape[2]
+    assert x.dim() == 5 and x.shape[3] == S and x.shape[4] == S, "Unfold3D expects a cubic [B,C,S,S,S] volume"
+    R = S // E
+    out = torch.empty((B * R * R * R, C, E, E, E), device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_unfold3d(x.data_ptr(), out.data_ptr(), B, C, S, E, _stream(x)), "rf_unfold3d")
+    _count()
+    return out
+
+
+def fold3d(x: torch.Tensor, R: int, E: int, nf: int) -> torch.Tensor:
+    """model/attention.py:170-176 (returns a contiguous tensor with the same values)."""
+    _forward_only(x)
+    x = _dev(x, name="x")
+    per = R * R * R * nf * E * E * E
+    assert x.numel() % per == 0, "Fold3D: input size does not match num_patch_x / patch_extent / nf"
+    B = x.numel() // per
+    out = torch.empty((B, nf, R * E, R * E, R * E), device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_fold3d(x.data_ptr(), out.data_ptr(), B, nf, R, E, _stream(x)), "rf_fold3d")
+    _count()
+    return out
+
+
+def unfold3d_pad_stride(x, kernel, pad, stride, pad_val, norm_sub=0.0, norm_div=0.0, keep_channels=False):
+    """model/attention.py:200-203 / util/patcher.py:14-19. kernel/pad/stride: int or 3-sequence."""
+    _forward_only(x)
+    x = _dev(x, name="x")
+    B, C = x.shape[0], x.shape[1]
+    size = tuple(x.shape[2:])
+    k, p, s = int3(kernel), int3(pad), int3(stride)
+    cnt = [(size[a] + 2 * p[a] - k[a]) // s[a] + 1 for a in range(3)]
+    rows = B * cnt[0] * cnt[1] * cnt[2]
+    shape = (rows, C, k[0], k[1], k[2]) if keep_channels else (rows * C, 1, k[0], k[1], k[2])
+    out = torch.empty(shape, device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_unfold3d_pad_stride(x.data_ptr(), out.data_ptr(), B, C, int3(size), k, p, s, float(pad_val),
+                                                float(norm_sub), float(norm_div), _stream(x)), "rf_unfold3d_pad_stride")
+    _count()
+    return out
+
+
+def recompose_patches(patches, out_shape, kernel, pad, stride, count, pad_val):
+    """util/patcher.py:21-30."""
+    _forward_only(patches)
+    patches = _dev(patches, name="patches")
+    B, C = int(out_shape[0]), int(out_shape[1])
+    size = tuple(int(v) for v in out_shape[2:])
+    out = torch.empty((B, C) + size, device=patches.device, dtype=patches.dtype)
+    with torch.cuda.device(patches.device):
+        check(_lib.lib().rf_recompose_patches(patches.data_ptr(), out.data_ptr(), B, C, int3(size), int3(kernel),
+                                              int3(pad), int3(stride), int3(count), float(pad_val), _stream(patches)),
+              "rf_recompose_patches")
+    _count()
+    return out
+
+
+# ---------------------------------------------------------------------------
+# conv / linear / norm building blocks
+# ---------------------------------------------------------------------------
+
+def conv3d(x, wt, bias=None, *, cout, ks, stride=1, pad=0, act=ACT_NONE, slope=0.0, x2=None, gn=None, oscale=None,
+           oshift=None):
+    """rf_conv3d_fwd. x [N,C1,D,H,W] (or None when everything comes from x2),
+    x2 optional [N,C2,D/2,H/2,W/2] (virtually upsampled + concatenated),
+    wt [Cin*ks^3, cout]; gn = (gn_mu, gn_a, gn_beta) or None."""
+    ref = x if x is not None else x2
+    if x is not None:
+        x = _dev(x, name="x")
+        N, C1, D, H, W = x.shape
+    else:
+        C1 = 0
+    C2 = 0
+    if x2 is not None:
+        x2 = _dev(x2, name="x2")
+        C2 = x2.shape[1]
+        if x is None:
+            N, D, H, W = x2.shape[0], 2 * x2.shape[2], 2 * x2.shape[3], 2 * x2.shape[4]
+        else:
+            assert x2.shape[0] == N and tuple(x2.shape[2:]) == (D // 2, H // 2, W // 2), "x2 must be half resolution"
+    cin = C1 + C2
+    wt = _dev(wt, name="wt")
+    assert tuple(wt.shape) == (cin * ks ** 3, cout), f"wt shape {tuple(wt.shape)} != {(cin * ks ** 3, cout)}"
+    Do, Ho, Wo = [(v + 2 * pad - ks) // stride + 1 for v in (D, H, W)]
+    y = torch.empty((N, cout, Do, Ho, Wo), device=ref.device, dtype=torch.float32)
+    g = gn if gn is not None else (None, None, None)
+    with torch.cuda.device(ref.device):
+        check(_lib.lib().rf_conv3d_fwd(_ptr(x), _ptr(x2), C2, wt.data_ptr(), _ptr(bias), _ptr(oscale), _ptr(oshift),
+                                       _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), y.data_ptr(), N, cin, D, H, W, cout, ks,
+                                       stride, pad, act, float(slope), _stream(ref)), "rf_conv3d_fwd")
+    _count()
+    return y
+
+
+def linear(x, wt, bias=None, act=ACT_NONE, slope=0.0):
+    """y = act(x @ wt + bias); wt [K, N] (= nn.Linear.weight.T)."""
+    x = _dev(x, name="x")
+    wt = _dev(wt, name="wt")
+    M, K = x.shape
+    assert wt.shape[0] == K
+    N = wt.shape[1]
+    y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_linear_fwd(x.data_ptr(), wt.data_ptr(), _ptr(bias), y.data_ptr(), M, K, N, act, float(slope),
+                                       _stream(x)), "rf_linear_fwd")
+    _count()
+    return y
+
+
+def groupnorm_stats(x, gamma, groups, eps=1e-5, x2=None):
+    """Returns (gn_mu [N,C], gn_a [N,C]) for the virtual input concat(x, up2(x2))."""
+    ref = x if x is not None else x2
+    C1 = 0
+    if x is not None:
+        x = _dev(x, name="x")
+        N, C1, D, H, W = x.shape
+    C2 = 0
+    if x2 is not None:
+        x2 = _dev(x2, name="x2")
+        C2 = x2.shape[1]
+        if x is None:
+            N, D, H, W = x2.shape[0], 2 * x2.shape[2], 2 * x2.shape[3], 2 * x2.shape[4]
+    C = C1 + C2
+    mu = torch.empty((N, C), device=ref.device, dtype=torch.float32)
+    a = torch.empty((N, C), device=ref.device, dtype=torch.float32)
+    with torch.cuda.device(ref.device):
+        check(_lib.lib().rf_groupnorm_stats(_ptr(x), _ptr(x2), C2, gamma.data_ptr(), mu.data_ptr(), a.data_ptr(), N, C,
+                                            D, H, W, groups, float(eps), _stream(ref)), "rf_groupnorm_stats")
+    _count()
+    return mu, a
+
+
+def maxpool3d_2(x):
+    x = _dev(x, name="x")
+    N, C, D, H, W = x.shape
+    y = torch.empty((N, C, D // 2, H // 2, W // 2), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_maxpool3d_2(x.data_ptr(), y.data_ptr(), N, C, D, H, W, _stream(x)), "rf_maxpool3d_2")
+    _count()
+    return y
+
+
+def upsample_nearest_2(x):
+    x = _dev(x, name="x")
+    N, C, D, H, W = x.shape
+    y = torch.empty((N, C, 2 * D, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_upsample_nearest_2(x.data_ptr(), y.data_ptr(), N, C, D, H, W, _stream(x)),
+              "rf_upsample_nearest_2")
+    _count()
+    return y
+
+
+def l2_normalize_rows(x, eps=1e-12):
+    """F.normalize(x, dim=1) for a [M, D] matrix."""
+    x = _dev(x, name="x")
+    M, D = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_l2_normalize_rows(x.data_ptr(), y.data_ptr(), M, D, float(eps), _stream(x)),
+              "rf_l2_normalize_rows")
+    _count()
+    return y
+
+
+def mlp_encode(x, wts, biases, l2_normalize=True):
+    """rf_mlp_encode_fwd: ReLU MLP (Patch04 family) + optional row normalisation."""
+    x = _dev(x, name="x")
+    M = x.shape[0]
+    n = len(wts)
+    widths = [x.shape[1]] + [int(w.shape[1]) for w in wts]
+    import ctypes
+    warr = (ctypes.c_int * 9)(*(widths + [0] * (9 - len(widths))))
+    L = _lib.lib()
+    ws_bytes = L.rf_mlp_encode_workspace_bytes(M, warr, n)
+    ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+    out = torch.empty((M, widths[-1]), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(L.rf_mlp_encode_fwd(x.data_ptr(), ptr_array([w.data_ptr() for w in wts]),
+                                  ptr_array([b.data_ptr() for b in biases]), warr, n, int(bool(l2_normalize)),
+                                  out.data_ptr(), M, ws.data_ptr(), ws_bytes, _stream(x)), "rf_mlp_encode_fwd")
+    _count(n + (1 if l2_normalize else 0))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# kNN
+# ---------------------------------------------------------------------------
+
+def knn_topk(bank, q, k, row_offset=0, method=0):
+    """Exact top-k under the canonical (fp64 d, row id) rule.
+    bank [n,64] fp32, q [Q,64] fp32 -> (idx int32 [Q,k] global ids, d fp64 [Q,k])."""
+    bank = _dev(bank, name="bank")
+    q = _dev(q, name="q")
+    n, D = bank.shape
+    Q = q.shape[0]
+    L = _lib.lib()
+    idx = torch.empty((Q, k), device=q.device, dtype=torch.int32)
+    d = torch.empty((Q, k), device=q.device, dtype=torch.float64)
+    ws_bytes = L.rf_knn_workspace_bytes(Q, n, k, method)
+    ws = torch.empty(max(ws_bytes, 256), device=q.device, dtype=torch.uint8)
+    with torch.cuda.device(q.device):
+        check(L.rf_knn_l2_topk(bank.data_ptr(), n, int(row_offset), q.data_ptr(), Q, D, k, method, idx.data_ptr(),
+                               d.data_ptr(), ws.data_ptr(), ws.numel(), _stream(q)), "rf_knn_l2_topk")
+    _count(2)
+    return idx, d
+
+
+def knn_merge(parts_idx, parts_d):
+    """parts_idx int32 [S,Q,k], parts_d fp64 [S,Q,k] -> merged ([Q,k], [Q,k])."""
+    parts_idx = _dev(parts_idx, torch.int32, "parts_idx")
+    parts_d = _dev(parts_d, torch.float64, "parts_d")
+    S, Q, k = parts_idx.shape
+    idx = torch.empty((Q, k), device=parts_idx.device, dtype=torch.int32)
+    d = torch.empty((Q, k), device=parts_idx.device, dtype=torch.float64)
+    with torch.cuda.device(parts_idx.device):
+        check(_lib.lib().rf_knn_merge(parts_idx.data_ptr(), parts_d.data_ptr(), S, Q, k, idx.data_ptr(), d.data_ptr(),
+                                      _stream(parts_idx)), "rf_knn_merge")
+    _count()
+    return idx, d
+
+
+def knn_demote_rows(idx2k, d2k, meta, query_scene, K):
+    """util/retrieval.py:93-100 -> (rows fp32 [Q,K,8], idx int32 [Q,K])."""
+    idx2k = _dev(idx2k, torch.int32, "idx2k")
+    d2k = _dev(d2k, torch.float64, "d2k")
+    meta = _dev(meta, name="meta")
+    Q, K2 = idx2k.shape
+    if query_scene is not None:
+        query_scene = _dev(query_scene, torch.int32, "query_scene")
+    rows = torch.empty((Q, K, 8), device=idx2k.device, dtype=torch.float32)
+    idx = torch.empty((Q, K), device=idx2k.device, dtype=torch.int32)
+    with torch.cuda.device(idx2k.device):
+        check(_lib.lib().rf_knn_demote_rows(idx2k.data_ptr(), d2k.data_ptr(), meta.data_ptr(), _ptr(query_scene), Q, K2,
+                                            K, rows.data_ptr(), idx.data_ptr(), _stream(idx2k)), "rf_knn_demote_rows")
+    _count()
+    return rows, idx
+
+
+def compose_gather(rows, dst_extents, scene_store, n_chunks, chunk_size, trunc, ratio):
+    """util/retrieval.py:145-164 for non-overlapping patches.
+    rows [n_chunks*P,K,8]; dst_extents int32 [P,6]; scene_store [S,sx,sy,sz] -> [n_chunks,K,cx,cy,cz]."""
+    rows = _dev(rows, name="rows")
+    dst_extents = _dev(dst_extents, torch.int32, "dst_extents")
+    scene_store = _dev(scene_store, name="scene_store")
+    P = dst_extents.shape[0]
+    K = rows.shape[1]
+    assert rows.shape[0] == n_chunks * P
+    out = torch.empty((n_chunks, K) + tuple(chunk_size), device=rows.device, dtype=torch.float32)
+    with torch.cuda.device(rows.device):
+        check(_lib.lib().rf_compose_gather(rows.data_ptr(), dst_extents.data_ptr(), scene_store.data_ptr(),
+                                           out.data_ptr(), n_chunks, P, K, scene_store.shape[0],
+                                           int3(scene_store.shape[1:]), int3(chunk_size), float(trunc), float(ratio),
+                                           _stream(rows)), "rf_compose_gather")
+    _count()
+    return out
+
+
+# ---------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------
+
+def attention_fuse(x_back, x_retr, theta, phi, E, K, normalize=True, mode=0, blend=True, gumbel_noise=None):
+    """model/attention.py:141-157. theta/phi: (list of 4 wt [in,out], list of 4 biases)."""
+    _forward_only(x_back, x_retr)
+    x_back = _dev(x_back, name="x_predicted")
+    x_retr = _dev(x_retr, name="x_retrieved")
+    B, nf, S = x_back.shape[0], x_back.shape[1], x_back.shape[2]
+    assert x_retr.shape[0] == B * K and x_retr.shape[1] == nf and x_retr.shape[2] == S
+    L = _lib.lib()
+    ws_bytes = L.rf_attention_workspace_bytes(B, nf, S, E, K)
+    ws = torch.empty(ws_bytes, device=x_back.device, dtype=torch.uint8)
+    out = torch.empty_like(x_back)
+    if gumbel_noise is not None:
+        gumbel_noise = _dev(gumbel_noise, name="gumbel_noise")
+    with torch.cuda.device(x_back.device):
+        check(L.rf_attention_fuse_fwd(x_back.data_ptr(), x_retr.data_ptr(),
+                                      ptr_array([w.data_ptr() for w in theta[0]]),
+                                      ptr_array([b.data_ptr() for b in theta[1]]),
+                                      ptr_array([w.data_ptr() for w in phi[0]]),
+                                      ptr_array([b.data_ptr() for b in phi[1]]), _ptr(gumbel_noise), out.data_ptr(), B,
+                                      nf, S, E, K, int(bool(normalize)), int(mode), int(bool(blend)), ws.data_ptr(),
+                                      ws_bytes, _stream(x_back)), "rf_attention_fuse_fwd")
+    _count(12)
+    return out
+
+
+def attention_features(x, t, occ, theta, phi, E, normalize=True):
+    """model/attention.py:132-139 -> (x_feat [R,32], p_feat [R,32], occ_any bool [R])."""
+    _forward_only(x, t)
+    x = _dev(x, name="x_predicted")
+    t = _dev(t, name="x_target")
+    B, nf, S = x.shape[0], x.shape[1], x.shape[2]
+    Rp = S // E
+    R = B * Rp ** 3
+    occ_u8 = occ.to(torch.uint8).contiguous()
+    L = _lib.lib()
+    ws_bytes = L.rf_attention_workspace_bytes(B, nf, S, E, 1)
+    ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+    xf = torch.empty((R, 32), device=x.device, dtype=torch.float32)
+    pf = torch.empty((R, 32), device=x.device, dtype=torch.float32)
+    oa = torch.empty((R,), device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device):
+        check(L.rf_attention_features(x.data_ptr(), t.data_ptr(), occ_u8.data_ptr(),
+                                      ptr_array([w.data_ptr() for w in theta[0]]),
+                                      ptr_array([b.data_ptr() for b in theta[1]]),
+                                      ptr_array([w.data_ptr() for w in phi[0]]),
+                                      ptr_array([b.data_ptr() for b in phi[1]]), xf.data_ptr(), pf.data_ptr(),
+                                      oa.data_ptr(), B, nf, S, E, int(bool(normalize)), ws.data_ptr(), ws_bytes,
+                                      _stream(x)), "rf_attention_features")
+    _count(13)
+    return xf, pf, oa.bool()

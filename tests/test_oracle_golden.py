@@ -1,0 +1,140 @@
+"""Pins the CPU oracle (oracle/rf_oracle.py) against the golden vectors that
+tests/golden/make_golden.py produced by running the reference's own modules."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+from oracle import rf_oracle as O
+
+torch.set_grad_enabled(False)
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+INDEX = json.load(open(os.path.join(GOLD, "index.json")))
+TOL = 1e-4  # north_star: fp32 values within 1e-4
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def synth(shapes):
+    return O.synth_state_dict(shapes, C.SEED)
+
+
+def test_fold_unfold_hashes():
+    f = INDEX["fold"]
+    x = C.rnd("unfold.x1", (3, 1, 64, 64, 64)).numpy()
+    assert sha(O.unfold3d(x, 16)) == f["unfold_16_1"]
+    x = C.rnd("unfold.x2", (2, 16, 32, 32, 32)).numpy()
+    assert sha(O.unfold3d(x, 8)) == f["unfold_8_16"]
+    assert sha(O.unfold3d(x, 2)) == f["unfold_2_16"]
+    x = C.rnd("unfold.x3", (2, 12, 32, 32, 32)).numpy()
+    assert sha(O.unfold3d(x, 2)) == f["unfold_2_12"]
+    assert sha(O.fold3d(C.rnd("fold.x1", (128, 16, 8, 8, 8)).numpy(), 4, 8, 16)) == f["fold_4_8_16"]
+    assert sha(O.fold3d(C.rnd("fold.x2", (4096, 16, 2, 2, 2)).numpy(), 16, 2, 16)) == f["fold_16_2_16"]
+    assert sha(O.fold3d(C.rnd("fold.x3", (128, 1, 16, 16, 16)).numpy(), 4, 16, 1)) == f["fold_4_16_1"]
+    x = C.rnd("ups.x1", (3, 1, 8, 8, 8)).numpy()
+    assert sha(O.unfold3d_pad_stride(x, 4, 1, np.float32(0.37), 2)) == f["padstride_4_1_2"]
+    x = C.rnd("ups.x2", (2, 1, 16, 16, 16)).numpy()
+    assert sha(O.unfold3d_pad_stride(x, 8, 2, np.float32(-1.5), 4)) == f["padstride_8_2_4"]
+    x = C.rnd("ups.x3", (2, 1, 64, 64, 64)).numpy()
+    assert sha(O.unfold3d_pad_stride(x, 32, 8, np.float32(2.25), 16)) == f["padstride_32_8_16"]
+    assert sha(O.unfold3d_pad_stride(x, 24, 4, np.float32(2.25), 16)) == f["padstride_24_4_16"]
+    p = O.PatcherOracle([16] * 3, [8] * 3, [16] * 3, 2.25, [64] * 3)
+    pat = p(x)
+    assert sha(pat) == f["patcher_16_8_16"]
+    assert p.get_patch_counts() == f["patcher_counts"]
+    assert sha(p.recompose_patches(x.shape, pat.reshape(2, 64, 32, 32, 32))) == f["patcher_recompose"]
+    p2 = O.PatcherOracle([2] * 3, [1] * 3, [2] * 3, 0.5, [8] * 3)
+    assert sha(p2(C.rnd("ups.x1", (3, 1, 8, 8, 8)).numpy())) == f["patcher_2_1_2"]
+
+
+def test_fold_is_inverse_of_unfold():
+    x = C.rnd("inv.x", (2, 6, 16, 16, 16)).numpy()
+    for E in (2, 4, 8):
+        assert np.array_equal(O.fold3d(O.unfold3d(x, E), 16 // E, E, 6), x)
+
+
+def test_chunk_patches_equals_pad_unfold():
+    """a1: dataset patch extraction == Unfold3DPadStride on the normalised chunk."""
+    chunk = O.synthetic_tsdf(3, 8, 0.43334)
+    trunc = float(np.float16(0.43334 * 3))
+    m, s = 0.81, 0.51
+    a = O.chunk_patches(chunk, 2, 1, 2, trunc, m, s)
+    norm = ((chunk - m) / s).astype(np.float32)
+    b = O.unfold3d_pad_stride(norm[None, None], 4, 1, np.float32((np.float32(trunc) - m) / s), 2)
+    assert a.shape == (64, 1, 4, 4, 4)
+    np.testing.assert_allclose(a, b, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("cls,nf,n", C.ENC_CASES)
+def test_encoders(cls, nf, n):
+    gold = np.load(os.path.join(GOLD, "encoders.npz"))[f"{cls}.{nf}"]
+    sd = synth(O.encoder_param_shapes(cls, nf, 64))
+    y = O.encoder_forward(cls, sd, C.encoder_input(cls, n)).reshape(n, 64).numpy()
+    np.testing.assert_allclose(y, gold, rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("nf", [16, 12])
+def test_retrieval_backbone(nf):
+    gold = np.load(os.path.join(GOLD, "unets.npz"))[f"retrieval_backbone.{nf}"]
+    sd = synth(O.retrieval_backbone_shapes(nf, nf, 4))
+    y = O.retrieval_backbone_forward(C.retrieval_backbone_input(nf), sd, nf, nf, 4).numpy()
+    np.testing.assert_allclose(y, gold, rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("kind,cls,nf,lv,S", C.UNET_CASES)
+def test_unet_backbone(kind, cls, nf, lv, S):
+    gold = np.load(os.path.join(GOLD, "unets.npz"))[f"unet_backbone.{kind}"]
+    sd = synth(O.unet_backbone_shapes(kind, nf, lv))
+    y = O.unet_backbone_forward(kind, C.unet_backbone_input(kind, S), sd, nf, lv)
+    np.testing.assert_allclose(y[:, :, ::3, ::3, ::3].numpy(), gold, rtol=0, atol=TOL)
+    st = INDEX[f"unet_backbone.{kind}.stats"]
+    assert abs(float(y.double().abs().sum()) - st[1]) <= 1e-5 * st[1]
+
+
+@pytest.mark.parametrize("nf", [16, 12])
+def test_final_decoder(nf):
+    gold = np.load(os.path.join(GOLD, "unets.npz"))[f"decoder.{nf}"]
+    sd = synth(O.final_decoder_shapes(nf))
+    y = O.final_decoder_forward(C.rnd(f"dec.{nf}.x", (1, nf, 32, 32, 32)), sd, nf)
+    np.testing.assert_allclose(y[:, :, ::2, ::2, ::2].numpy(), gold, rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("nf,K,mode", C.ATTN_CASES)
+def test_attention(nf, K, mode):
+    g = np.load(os.path.join(GOLD, "attention.npz"))
+    tag = C.attention_tag(nf, K, mode)
+    sd = synth(O.attention_shapes(nf, 2))
+    xb, xr, occ = C.attention_inputs(nf, K, mode)
+    noise = torch.from_numpy(g[tag + ".noise"]) if mode else None
+    y = O.patched_attention_forward(xb, xr, sd, nf, 16, 2, K, retrieval_mode=mode, gumbel_noise=noise)
+    np.testing.assert_allclose(y[:, :, ::2, ::2, ::2].numpy(), g[tag], rtol=0, atol=TOL)
+    if not mode and K == 4:
+        xf, pf, of = O.attention_get_features(xb, xr[:1], occ, sd, nf, 2)
+        np.testing.assert_allclose(xf[::16].numpy(), g[tag + ".feat_x"], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(pf[::16].numpy(), g[tag + ".feat_p"], rtol=0, atol=1e-5)
+        assert np.array_equal(of.numpy(), g[tag + ".feat_occ"])
+
+
+def test_refine_full_forward():
+    """BASELINE config 1: the parity anchor."""
+    g = np.load(os.path.join(GOLD, "refine_full.npz"))
+    x_in, x_re = C.refine_full_inputs()
+    assert sha(x_in.numpy()) == INDEX["refine_full.input_sha"]
+    assert sha(x_re.numpy()) == INDEX["refine_full.retrieval_sha"]
+    sds = dict(unet_backbone=synth(O.unet_backbone_shapes("sr08", 16, 4)),
+               retrieval_backbone=synth(O.retrieval_backbone_shapes(16, 16, 4)),
+               attention=synth(O.attention_shapes(16, 2)), decoder=synth(O.final_decoder_shapes(16)))
+    cfg = dict(kind="sr08", nf=16, unet_num_level=4, retrieval_fmaps=16, retrieval_num_level=4, K=4, E=2)
+    pred, x_back, x_retr, xa = O.refine_forward(x_in, x_re, sds, cfg)
+    np.testing.assert_allclose(x_back[:, :, ::4, ::4, ::4].numpy(), g["x_back"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(x_retr[:, :, ::4, ::4, ::4].numpy(), g["x_retr"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(xa[:, :, ::4, ::4, ::4].numpy(), g["x_attn"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(pred.numpy(), g["pred"], rtol=0, atol=TOL)
+    # the output must not be degenerate, or 1e-4 would be vacuous
+    assert float(np.abs(g["pred"]).max()) > 0.2 and float(g["pred"].std()) > 0.05
