@@ -781,3 +781,70 @@ def refine_forward(inp, retrieval, sds, cfg):
 def network_pred_to_df(pred, trunc):
     """trainer/train_refinement.py:242-243."""
     return (pred + 1) * trunc / 2
+
+
+# ---------------------------------------------------------------------------
+# whole hot path on the CPU (used by smoke(), the tests and bench.py's
+# cpu_baseline / --impl reference legs)
+# ---------------------------------------------------------------------------
+
+_INPUT_ENCODER = {"2+1": "Patch04", "2+1V2": "Patch04V2", "4+2": "Patch08", "4+2N": "PatchNorm08", "16+4": "Patch24",
+                  "pc_16+8": "PCPatch32", "pc_32+8": "PCPatch48", "pc_32+16": "PCPatch64"}  # model/__init__.py:8-23
+_TARGET_ENCODER = {"pc_32+16": "PCPatch64", "8+2": "Patch12", "8+4": "Patch16", "16+4": "Patch24", "16+4V2": "Patch24V2",
+                   "16+8": "Patch32", "16+8N": "PatchNorm32"}  # model/__init__.py:24-37
+
+
+def f16_trunc(voxel_size):
+    return float(np.float16(voxel_size * 3).astype(np.float32))  # dataset/scene.py:32-33
+
+
+def encode_chunk_queries(config, sd_fenc_input, chunks: np.ndarray) -> np.ndarray:
+    """chunks [B,1,s,s,s] raw low-res SDF -> unit queries [B*P, D]: the dataloader's
+    patch extraction + normalisation (a1), the input encoder (a5/a6), F.normalize (a9)."""
+    d = config["dataset"]
+    stride_in = int(d["patch_stride"] * d["patch_size_input"] / d["patch_size_target"])
+    pats = np.concatenate([chunk_patches(c[0], d["patch_size_input"], d["patch_context_input"], stride_in,
+                                         f16_trunc(d["voxel_size_input"]), d["input_mean"], d["input_std"])
+                           for c in chunks])
+    name = _INPUT_ENCODER[config["retrieval_model"]["network_input"]]
+    feat = encoder_forward(name, sd_fenc_input, torch.from_numpy(pats))
+    return normalize_features(feat, config["retrieval_model"]["latent_dim"]).numpy()
+
+
+def lookup_rows(bank_emb, bank_meta, q, K, query_scene=None, threads=0):
+    """util/retrieval.py:92-100 with the exact kNN: -> (rows [Q,K,8], idx [Q,K])."""
+    k2 = min(2 * K, bank_emb.shape[0])
+    idx2k, d2k = knn_exact(bank_emb, q, k2, threads=threads)
+    qs = np.full(q.shape[0], -1, dtype=np.int64) if query_scene is None else np.asarray(query_scene)
+    idx, dist = demote_same_scene(idx2k, d2k, bank_meta[:, 0].astype(np.int64), qs, K)
+    return mapping_rows(bank_meta, idx, dist), idx
+
+
+def chunk_dst_extents(config) -> np.ndarray:
+    d = config["dataset"]
+    ext = get_extents_for_size([d["target_chunk_size"]] * 3, d["patch_size_target"], d["patch_context_target"], d["patch_stride"])
+    ext = ext.copy()
+    ext[:, 1::2] -= 2 * d["patch_context_target"]  # unpad
+    return ext
+
+
+def compose_chunks(config, rows, scene_store, n_chunks) -> np.ndarray:
+    d = config["dataset"]
+    P = rows.shape[0] // n_chunks
+    trunc = np.float32(f16_trunc(d["voxel_size_target"]))
+    dst = chunk_dst_extents(config)
+    c = d["target_chunk_size"]
+    return np.stack([compose_from_mapping(rows[i * P:(i + 1) * P], dst, scene_store, (c, c, c), trunc, trunc)
+                     for i in range(n_chunks)])
+
+
+def refine_chunks(config, sds, chunks, retrieval_raw):
+    """dataloader normalisation (patched_scene_dataset.py:127-133) + forward_full's inference part."""
+    d = config["dataset"]
+    x_in = torch.from_numpy(((chunks - d["input_mean"]) / d["input_std"]).astype(np.float32))
+    x_re = torch.from_numpy(((retrieval_raw - d["target_mean"]) / d["target_std"]).astype(np.float32))
+    kind = {8: "sr08", 16: "sr16", 128: "surface"}[d["input_chunk_size"]]
+    cfg = dict(kind=kind, nf=config["nf"], unet_num_level=config["unet_num_level"], retrieval_fmaps=config["retrieval_fmaps"],
+               retrieval_num_level=config["retrieval_num_level"], K=config["K"], E=config["attn_patch_extent"] // 2,
+               retrieval_mode=config["attn_retrieval_mode"])
+    return refine_forward(x_in, x_re, sds, cfg)

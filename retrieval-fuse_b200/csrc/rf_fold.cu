@@ -164,7 +164,8 @@ extern "C" int rf_recompose_patches(const float* patches, float* out, int B, int
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ rows, const int* __restrict__ dst_ext,
                                                       const float* __restrict__ store, float* __restrict__ out, int P,
-                                                      int K, int n_scenes, Int3 ssz, Int3 csz, float trunc, float ratio) {
+                                                      int K, int n_scenes, Int3 ssz, Int3 csz, float trunc, float ratio,
+                                                      float norm_sub, float norm_div) {
     const int p = blockIdx.x, k = blockIdx.y, c = blockIdx.z;
     const float* row = rows + (((long)c * P + p) * K + k) * 8;
     const int scene = (int)row[0];
@@ -188,13 +189,15 @@ __global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ 
         if (scene >= 0 && scene < n_scenes && sx < X1 && sy < Y1 && sz < Z1 && sx >= 0 && sy >= 0 && sz >= 0 &&
             sx < ssz.v[0] && sy < ssz.v[1] && sz < ssz.v[2])
             v = __fmul_rn(s[((long)sx * ssz.v[1] + sy) * ssz.v[2] + sz], ratio);
+        if (norm_div != 0.f) v = __fdiv_rn(__fsub_rn(v, norm_sub), norm_div);
         o[((long)(de[0] + x) * csz.v[1] + (de[2] + y)) * csz.v[2] + (de[4] + z)] = v;
     }
 }
 
 extern "C" int rf_compose_gather(const float* rows, const int* dst_extents, const float* scene_store, float* out,
                                  int n_chunks, int P, int K, int n_scenes, const int scene_size[3],
-                                 const int chunk_size[3], float trunc, float ratio, void* stream) {
+                                 const int chunk_size[3], float trunc, float ratio, float norm_sub,
+                                 float norm_div, void* stream) {
     RF_CHECK_ARG(rows && dst_extents && scene_store && out && scene_size && chunk_size, "rf_compose_gather: null pointer");
     RF_CHECK_ARG(n_chunks > 0 && P > 0 && K > 0 && n_scenes > 0 && K <= 65535 && n_chunks <= 65535,
                  "rf_compose_gather: bad sizes");
@@ -202,7 +205,7 @@ extern "C" int rf_compose_gather(const float* rows, const int* dst_extents, cons
     for (int a = 0; a < 3; ++a) { s.v[a] = scene_size[a]; c.v[a] = chunk_size[a]; }
     dim3 grid(P, K, n_chunks);
     compose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, dst_extents, scene_store, out, P, K, n_scenes, s, c,
-                                                          trunc, ratio);
+                                                          trunc, ratio, norm_sub, norm_div);
     RF_LAUNCH_OK("compose_kernel");
     return 0;
 }

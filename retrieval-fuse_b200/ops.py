@@ -111,6 +111,9 @@ def recompose_patches(patches, out_shape, kernel, pad, stride, count, pad_val):
     patches = _dev(patches, name="patches")
     B, C = int(out_shape[0]), int(out_shape[1])
     size = tuple(int(v) for v in out_shape[2:])
+    n = int(count[0]) * int(count[1]) * int(count[2])
+    if patches.shape[1] != n:  # extra trailing patches are never read by the reference either
+        patches = patches[:, :n].contiguous()
     out = torch.empty((B, C) + size, device=patches.device, dtype=patches.dtype)
     with torch.cuda.device(patches.device):
         check(_lib.lib().rf_recompose_patches(patches.data_ptr(), out.data_ptr(), B, C, int3(size), int3(kernel),
@@ -302,21 +305,25 @@ def knn_demote_rows(idx2k, d2k, meta, query_scene, K):
     return rows, idx
 
 
-def compose_gather(rows, dst_extents, scene_store, n_chunks, chunk_size, trunc, ratio):
+def compose_gather(rows, dst_extents, scene_store, n_chunks, chunk_size, trunc, ratio, prefill=False, norm_sub=0.0,
+                   norm_div=0.0):
     """util/retrieval.py:145-164 for non-overlapping patches.
-    rows [n_chunks*P,K,8]; dst_extents int32 [P,6]; scene_store [S,sx,sy,sz] -> [n_chunks,K,cx,cy,cz]."""
+    rows [n_chunks*P,K,8]; dst_extents int32 [P,6]; scene_store [S,sx,sy,sz] -> [n_chunks,K,cx,cy,cz].
+    prefill=True initialises the output with `trunc` (:148) for scenes whose patch list does not tile the chunk."""
     rows = _dev(rows, name="rows")
     dst_extents = _dev(dst_extents, torch.int32, "dst_extents")
     scene_store = _dev(scene_store, name="scene_store")
     P = dst_extents.shape[0]
     K = rows.shape[1]
     assert rows.shape[0] == n_chunks * P
-    out = torch.empty((n_chunks, K) + tuple(chunk_size), device=rows.device, dtype=torch.float32)
+    shape = (n_chunks, K) + tuple(int(v) for v in chunk_size)
+    out = (torch.full(shape, float(trunc), device=rows.device, dtype=torch.float32) if prefill
+           else torch.empty(shape, device=rows.device, dtype=torch.float32))
     with torch.cuda.device(rows.device):
         check(_lib.lib().rf_compose_gather(rows.data_ptr(), dst_extents.data_ptr(), scene_store.data_ptr(),
                                            out.data_ptr(), n_chunks, P, K, scene_store.shape[0],
                                            int3(scene_store.shape[1:]), int3(chunk_size), float(trunc), float(ratio),
-                                           _stream(rows)), "rf_compose_gather")
+                                           float(norm_sub), float(norm_div), _stream(rows)), "rf_compose_gather")
     _count()
     return out
 

@@ -1,0 +1,391 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the
+golden vectors produced by the reference's own modules.  Needs a B200.
+
+Tolerances (north_star): bit-exact for index work (fold/unfold/patcher, kNN
+ids, demotion, compose); fp32 values within 1e-4.  For feature tensors whose
+magnitude exceeds 1 the 1e-4 is taken relative to the tensor's max-abs (the
+reference's own fp32 result sits 1.2e-4 away from an fp64 evaluation of the
+same network at |x|max = 7, see DESIGN.md "Numerics"); TSDF outputs are
+checked at 1e-4 absolute in TSDF units (network_pred_to_df).
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+from oracle import rf_oracle as O
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+INDEX = json.load(open(os.path.join(GOLD, "index.json")))
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need CUDA"
+    from retrieval_fuse_b200 import _lib
+    _lib.lib()  # fails loudly when the extension is missing
+    return torch.device("cuda:0")
+
+
+def sha(a):
+    if isinstance(a, torch.Tensor):
+        a = a.cpu().numpy()
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def synth(shapes):
+    return O.synth_state_dict(shapes, C.SEED)
+
+
+def load(module, shapes, dev):
+    sd = synth(shapes)
+    module.load_state_dict(sd)
+    return module.to(dev).eval(), sd
+
+
+def close(a, b, tol=TOL, rel_to_max=False, what=""):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else b
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = max(1.0, float(np.abs(b).max())) if rel_to_max else 1.0
+    err = float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max())
+    assert err <= tol * scale, f"{what}: max abs err {err:.3e} > {tol * scale:.3e}"
+    return err
+
+
+# --------------------------------------------------------------------------- a2-a4
+
+def test_fold_unfold_bit_exact(dev):
+    from retrieval_fuse_b200.model.attention import Fold3D, Unfold3D, Unfold3DPadStride
+    f = INDEX["fold"]
+    x = C.rnd("unfold.x1", (3, 1, 64, 64, 64)).to(dev)
+    assert sha(Unfold3D(16, 1)(x)) == f["unfold_16_1"]
+    x = C.rnd("unfold.x2", (2, 16, 32, 32, 32)).to(dev)
+    assert sha(Unfold3D(8, 16)(x)) == f["unfold_8_16"]
+    assert sha(Unfold3D(2, 16)(x)) == f["unfold_2_16"]
+    assert sha(Unfold3D(2, 12)(C.rnd("unfold.x3", (2, 12, 32, 32, 32)).to(dev))) == f["unfold_2_12"]
+    assert sha(Fold3D(4, 8, 16)(C.rnd("fold.x1", (128, 16, 8, 8, 8)).to(dev))) == f["fold_4_8_16"]
+    assert sha(Fold3D(16, 2, 16)(C.rnd("fold.x2", (4096, 16, 2, 2, 2)).to(dev))) == f["fold_16_2_16"]
+    assert sha(Fold3D(4, 16, 1)(C.rnd("fold.x3", (128, 1, 16, 16, 16)).to(dev))) == f["fold_4_16_1"]
+    assert sha(Unfold3DPadStride(4, 1, 0.37, 2)(C.rnd("ups.x1", (3, 1, 8, 8, 8)).to(dev))) == f["padstride_4_1_2"]
+    assert sha(Unfold3DPadStride(8, 2, -1.5, 4)(C.rnd("ups.x2", (2, 1, 16, 16, 16)).to(dev))) == f["padstride_8_2_4"]
+    x = C.rnd("ups.x3", (2, 1, 64, 64, 64)).to(dev)
+    assert sha(Unfold3DPadStride(32, 8, 2.25, 16)(x)) == f["padstride_32_8_16"]
+    assert sha(Unfold3DPadStride(24, 4, 2.25, 16)(x)) == f["padstride_24_4_16"]
+    # round trip at a larger, non-golden size
+    y = torch.randn(3, 5, 24, 24, 24, device=dev)
+    for E in (2, 3, 4, 8):
+        assert torch.equal(Fold3D(24 // E, E, 5)(Unfold3D(E, 5)(y)), y)
+
+
+def test_patcher_bit_exact(dev):
+    from retrieval_fuse_b200.util.patcher import Patcher
+    f = INDEX["fold"]
+    x = C.rnd("ups.x3", (2, 1, 64, 64, 64)).to(dev)
+    p = Patcher([16] * 3, [8] * 3, [16] * 3, 2.25, [64] * 3)
+    pat = p(x)
+    assert sha(pat) == f["patcher_16_8_16"]
+    assert p.get_patch_counts() == f["patcher_counts"]
+    assert sha(p.recompose_patches(x.shape, pat.reshape(2, 64, 32, 32, 32))) == f["patcher_recompose"]
+    p2 = Patcher([2] * 3, [1] * 3, [2] * 3, 0.5, [8] * 3)
+    assert sha(p2(C.rnd("ups.x1", (3, 1, 8, 8, 8)).to(dev))) == f["patcher_2_1_2"]
+    # ragged / overlapping case against the oracle (stride < patch, size not a multiple)
+    xr = torch.randn(2, 3, 13, 10, 9, device=dev)
+    po = O.PatcherOracle([4, 3, 3], [1, 2, 0], [3, 2, 3], -0.25, [13, 10, 9])
+    pg = Patcher([4, 3, 3], [1, 2, 0], [3, 2, 3], -0.25, [13, 10, 9])
+    assert np.array_equal(pg(xr).cpu().numpy(), po(xr.cpu().numpy()))
+
+
+def test_fused_patch_normalisation(dev):
+    """a1: pad + patch extraction + (x-mean)/std in one kernel == the dataloader's arithmetic."""
+    from retrieval_fuse_b200 import ops
+    chunk = O.synthetic_tsdf(3, 8, 0.43334)
+    trunc = O.f16_trunc(0.43334)
+    m, s = 0.8112343966484424, 0.5094238937427482
+    want = O.chunk_patches(chunk, 2, 1, 2, trunc, m, s)
+    got = ops.unfold3d_pad_stride(torch.from_numpy(chunk)[None, None].to(dev), 4, 1, 2, trunc, norm_sub=m, norm_div=s)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+# --------------------------------------------------------------------------- a5-a9
+
+@pytest.mark.parametrize("cls,nf,n", C.ENC_CASES)
+def test_encoders(dev, cls, nf, n):
+    from retrieval_fuse_b200.model import retrieval as R
+    gold = np.load(os.path.join(GOLD, "encoders.npz"))[f"{cls}.{nf}"]
+    m, sd = load(getattr(R, cls)(nf, 64), O.encoder_param_shapes(cls, nf, 64), dev)
+    x = C.encoder_input(cls, n)
+    y = m(x.to(dev))
+    assert y.shape == (n, 64, 1, 1, 1)
+    close(y.reshape(n, 64), gold, what=f"{cls} vs reference golden")
+    close(y.reshape(n, 64), O.encoder_forward(cls, sd, x).reshape(n, 64), what=f"{cls} vs oracle")
+
+
+def test_encoder_batch_and_normalise(dev):
+    """64 patches x several chunks through Patch04 + F.normalize (util/retrieval.py:66)."""
+    from retrieval_fuse_b200.model import retrieval as R
+    from retrieval_fuse_b200.util.retrieval import _encode_normalized
+    m, sd = load(R.Patch04(32, 64), O.encoder_param_shapes("Patch04", 32, 64), dev)
+    x = torch.randn(64 * 5 + 3, 1, 4, 4, 4, generator=torch.Generator().manual_seed(5))
+    got = _encode_normalized(m, x.to(dev), 64)
+    want = O.normalize_features(O.encoder_forward("Patch04", sd, x), 64)
+    close(got, want, tol=1e-5, what="Patch04 + normalise")
+    m8, sd8 = load(R.Patch08(16, 64), O.encoder_param_shapes("Patch08", 16, 64), dev)
+    x8 = torch.randn(70, 1, 8, 8, 8, generator=torch.Generator().manual_seed(6))
+    close(_encode_normalized(m8, x8.to(dev), 64), O.normalize_features(O.encoder_forward("Patch08", sd8, x8), 64), tol=1e-5,
+          what="Patch08 + normalise")
+
+
+# --------------------------------------------------------------------------- a13, a15, a16
+
+@pytest.mark.parametrize("nf", [16, 12])
+def test_retrieval_backbone(dev, nf):
+    from retrieval_fuse_b200.model import get_retrieval_backbone
+    gold = np.load(os.path.join(GOLD, "unets.npz"))[f"retrieval_backbone.{nf}"]
+    m, _ = load(get_retrieval_backbone(dict(nf=nf, retrieval_fmaps=nf, retrieval_num_level=4, layer_order="gcr")),
+                O.retrieval_backbone_shapes(nf, nf, 4), dev)
+    assert m.nf == nf
+    y = m(C.retrieval_backbone_input(nf).to(dev))
+    close(y, gold, rel_to_max=True, what=f"retrieval backbone nf={nf}")
+
+
+@pytest.mark.parametrize("kind,cls,nf,lv,S", C.UNET_CASES)
+def test_unet_backbone(dev, kind, cls, nf, lv, S):
+    from retrieval_fuse_b200.model import refinement as RF
+    gold = np.load(os.path.join(GOLD, "unets.npz"))[f"unet_backbone.{kind}"]
+    m, _ = load(getattr(RF, cls)(nf, num_levels=lv, layer_order="gcr"), O.unet_backbone_shapes(kind, nf, lv), dev)
+    y = m(C.unet_backbone_input(kind, S).to(dev))
+    close(y[:, :, ::3, ::3, ::3], gold, rel_to_max=True, what=f"unet backbone {kind}")
+    st = INDEX[f"unet_backbone.{kind}.stats"]
+    assert abs(float(y.double().abs().sum()) - st[1]) <= 1e-5 * st[1]
+
+
+@pytest.mark.parametrize("nf", [16, 12])
+def test_final_decoder(dev, nf):
+    from retrieval_fuse_b200.model import refinement as RF
+    gold = np.load(os.path.join(GOLD, "unets.npz"))[f"decoder.{nf}"]
+    m, _ = load(RF.Superresolution08FinalDecoder(nf, layer_order="gcr"), O.final_decoder_shapes(nf), dev)
+    y = m(C.rnd(f"dec.{nf}.x", (1, nf, 32, 32, 32)).to(dev))
+    close(y[:, :, ::2, ::2, ::2], gold, what=f"final decoder nf={nf}")
+
+
+# --------------------------------------------------------------------------- a14
+
+@pytest.mark.parametrize("nf,K,mode", C.ATTN_CASES)
+def test_attention(dev, nf, K, mode):
+    from retrieval_fuse_b200.model import get_attention_block
+    g = np.load(os.path.join(GOLD, "attention.npz"))
+    tag = C.attention_tag(nf, K, mode)
+    cfg = dict(nf=nf, attn_patch_extent=4, K=K, attn_normalize=True, attn_use_switching=True, attn_retrieval_mode=mode,
+               attn_no_output_mapping=True, attn_blend=True, attn_num_patch=16)
+    m, sd = load(get_attention_block(cfg), O.attention_shapes(nf, 2), dev)
+    xb, xr, occ = C.attention_inputs(nf, K, mode)
+    noise = torch.from_numpy(g[tag + ".noise"]).to(dev) if mode else None
+    y = m(xb.to(dev), xr.to(dev), noise) if mode else m(xb.to(dev), xr.to(dev))
+    # softmax(1024 s) amplifies fp32 rounding of s by 1024: compare against an
+    # fp64 evaluation and require to be as close to it as the reference's fp32 is
+    sd64 = {k: v.double() for k, v in sd.items()}
+    y64 = O.patched_attention_forward(xb.double(), xr.double(), sd64, nf, 16, 2, K, retrieval_mode=mode,
+                                      gumbel_noise=None if noise is None else noise.cpu().double())
+    y32 = O.patched_attention_forward(xb, xr, sd, nf, 16, 2, K, retrieval_mode=mode,
+                                      gumbel_noise=None if noise is None else noise.cpu())
+    ref_noise = float((y32.double() - y64).abs().max())
+    ours = float((y.cpu().double() - y64).abs().max())
+    assert ours <= max(2 * ref_noise, TOL), f"{tag}: |ours-fp64| {ours:.3e} vs reference fp32 noise {ref_noise:.3e}"
+    # and against the reference's golden output: all but a vanishing fraction within 1e-4
+    diff = np.abs(y[:, :, ::2, ::2, ::2].cpu().numpy() - g[tag])
+    assert float(np.mean(diff > TOL)) <= 1e-4 and float(diff.max()) <= max(10 * ref_noise, 1e-3), (tag, diff.max())
+    if not mode and K == 4:
+        xf, pf, of = m.get_features(xb.to(dev), xr[:1].to(dev), occ.to(dev))
+        close(xf[::16], g[tag + ".feat_x"], tol=1e-5, what="theta features")
+        close(pf[::16], g[tag + ".feat_p"], tol=1e-5, what="phi features")
+        assert np.array_equal(of.cpu().numpy(), g[tag + ".feat_occ"])
+
+
+# --------------------------------------------------------------------------- a17
+
+def test_refine_full_forward(dev):
+    """BASELINE config 1 (one SR 8^3 -> 64^3 chunk, K=4): the parity anchor."""
+    from retrieval_fuse_b200.pipeline import FRONT3D_SR, RefinementPipeline
+    g = np.load(os.path.join(GOLD, "refine_full.npz"))
+    x_in, x_re = C.refine_full_inputs()
+    pipe = RefinementPipeline(FRONT3D_SR, bank=None, device=dev)
+    sds = dict(unet_backbone=synth(O.unet_backbone_shapes("sr08", 16, 4)),
+               retrieval_backbone=synth(O.retrieval_backbone_shapes(16, 16, 4)),
+               attention=synth(O.attention_shapes(16, 2)), decoder=synth(O.final_decoder_shapes(16)))
+    pipe.unet_backbone.load_state_dict(sds["unet_backbone"])
+    pipe.retrieval_backbone.load_state_dict(sds["retrieval_backbone"])
+    pipe.patched_attention_block.load_state_dict(sds["attention"])
+    pipe.decoder.load_state_dict(sds["decoder"])
+    pred, x_back, x_retr, xa = pipe.refine(x_in.to(dev), x_re.to(dev))
+    close(x_back[:, :, ::4, ::4, ::4], g["x_back"], rel_to_max=True, what="x_back")
+    close(x_retr[:, :, ::4, ::4, ::4], g["x_retr"], rel_to_max=True, what="x_retr")
+    # TSDF units (network_pred_to_df, trunc = float16(3 * 0.054167)): 1e-4 absolute
+    trunc = O.f16_trunc(C.SR_3DFRONT["voxel_size_target"])
+    df_err = close(pipe.pred_to_df(pred), O.network_pred_to_df(torch.from_numpy(g["pred"]), trunc), what="TSDF (df units)")
+    # tanh domain: as close to the fp64 truth as the reference's own fp32 arithmetic
+    cfg = dict(kind="sr08", nf=16, unet_num_level=4, retrieval_fmaps=16, retrieval_num_level=4, K=4, E=2)
+    sd64 = {k: {n: v.double() for n, v in d.items()} for k, d in sds.items()}
+    p64 = O.refine_forward(x_in.double(), x_re.double(), sd64, cfg)[0]
+    ref_noise = float((torch.from_numpy(g["pred"]).double() - p64).abs().max())
+    ours = float((pred.cpu().double() - p64).abs().max())
+    assert ours <= 2 * ref_noise + 1e-5, f"|ours-fp64| {ours:.3e} vs reference's fp32 noise {ref_noise:.3e}"
+    print(f"refine_full: df err {df_err:.2e}, tanh-domain |ours-fp64| {ours:.2e}, reference fp32 noise {ref_noise:.2e}")
+
+
+# --------------------------------------------------------------------------- a10-a12
+
+def _unit(rng, n, d=64):
+    x = rng.normal(size=(n, d)).astype(np.float32)
+    return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+
+@pytest.mark.parametrize("N,Q,k,method", [(5000, 200, 8, 1), (2048, 40000, 8, 1), (70, 33, 32, 1), (131, 1, 1, 1),
+                                          (5000, 2000, 8, 2), (20000, 4096, 16, 2), (4096, 1500, 2, 2)])
+def test_knn_bit_exact(dev, N, Q, k, method):
+    from retrieval_fuse_b200 import ops
+    rng = np.random.default_rng(N * 7 + Q)
+    db, q = _unit(rng, N), _unit(rng, Q)
+    # collisions: duplicated rows, a query equal to a row, near-duplicates
+    db[N // 2] = db[3]
+    db[N - 1] = db[3]
+    q[0] = db[3]
+    if N > 100:
+        db[50:60] = db[40] + rng.normal(size=(10, 64)).astype(np.float32) * 1e-7
+    want_i, want_d = O.knn_exact(db, q, k)
+    got_i, got_d = ops.knn_topk(torch.from_numpy(db).to(dev), torch.from_numpy(q).to(dev), k, method=method)
+    assert np.array_equal(got_i.cpu().numpy(), want_i)
+    assert np.array_equal(got_d.cpu().numpy().astype(np.float32), want_d)
+    # row_offset shifts the ids only
+    off_i, _ = ops.knn_topk(torch.from_numpy(db).to(dev), torch.from_numpy(q).to(dev), k, row_offset=1000, method=method)
+    assert np.array_equal(off_i.cpu().numpy(), want_i + 1000)
+
+
+def test_knn_merge_and_sharding(dev):
+    from retrieval_fuse_b200 import ops
+    rng = np.random.default_rng(11)
+    db, q = _unit(rng, 3001), _unit(rng, 257)
+    db[2999] = db[5]
+    k = 8
+    want_i, want_d = O.knn_exact(db, q, k)
+    parts_i, parts_d = [], []
+    bounds = [0, 700, 1500, 1501, 3001]  # ragged shards, one with a single row (k > rows)
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        kk = min(k, hi - lo)
+        i, d = ops.knn_topk(torch.from_numpy(db[lo:hi]).to(dev), torch.from_numpy(q).to(dev), kk, row_offset=lo)
+        if kk < k:
+            i = torch.cat([i, torch.full((q.shape[0], k - kk), 2 ** 31 - 1, dtype=torch.int32, device=dev)], 1)
+            d = torch.cat([d, torch.full((q.shape[0], k - kk), torch.finfo(torch.float64).max, dtype=torch.float64, device=dev)], 1)
+        parts_i.append(i)
+        parts_d.append(d)
+    mi, md = ops.knn_merge(torch.stack(parts_i), torch.stack(parts_d))
+    assert np.array_equal(mi.cpu().numpy(), want_i)
+    assert np.array_equal(md.cpu().numpy().astype(np.float32), want_d)
+
+
+def test_demotion_and_rows(dev):
+    from retrieval_fuse_b200.util.retrieval import EmbeddingBank
+    rng = np.random.default_rng(3)
+    N, Q, K = 4000, 300, 4
+    emb, q = _unit(rng, N), _unit(rng, Q)
+    meta = np.zeros((N, 7), dtype=np.float32)
+    meta[:, 0] = rng.integers(0, 12, size=N)
+    meta[:, 1:] = rng.integers(0, 64, size=(N, 6))
+    meta[N - 1] = [-1, 0, 16, 0, 16, 0, 16]
+    qs = rng.integers(-1, 12, size=Q)
+    bank = EmbeddingBank(torch.from_numpy(emb).to(dev), torch.from_numpy(meta).to(dev), [f"s{i}" for i in range(12)])
+    rows, idx = bank.query(torch.from_numpy(q).to(dev), K, torch.from_numpy(qs.astype(np.int32)))
+    want_rows, want_idx = O.lookup_rows(emb, meta, q, K, qs)
+    assert np.array_equal(idx.cpu().numpy(), want_idx)
+    assert np.array_equal(rows.cpu().numpy(), want_rows)
+    # queries whose 2K hits ALL come from their own scene keep the original order
+    meta2 = meta.copy()
+    meta2[:, 0] = 5
+    bank2 = EmbeddingBank(torch.from_numpy(emb).to(dev), torch.from_numpy(meta2).to(dev), ["s"] * 6)
+    rows2, idx2 = bank2.query(torch.from_numpy(q).to(dev), K, torch.full((Q,), 5, dtype=torch.int32))
+    w2 = O.lookup_rows(emb, meta2, q, K, np.full(Q, 5))
+    assert np.array_equal(idx2.cpu().numpy(), w2[1]) and np.array_equal(rows2.cpu().numpy(), w2[0])
+
+
+def test_compose_bit_exact(dev):
+    from retrieval_fuse_b200.pipeline import FRONT3D_SR, RetrievalPipeline
+    rng = np.random.default_rng(9)
+    S, B, K = 5, 3, 4
+    store = rng.random((S, 64, 64, 64)).astype(np.float32)
+    rows = np.zeros((B * 64, K, 8), dtype=np.float32)
+    rows[:, :, 0] = rng.integers(-1, S, size=(B * 64, K))
+    st = rng.integers(0, 4, size=(B * 64, K, 3)) * 16
+    rows[:, :, 1], rows[:, :, 3], rows[:, :, 5] = st[..., 0], st[..., 1], st[..., 2]
+    rows[:, :, 2], rows[:, :, 4], rows[:, :, 6] = st[..., 0] + 16, st[..., 1] + 16, st[..., 2] + 16
+    rows[:, :, 7] = rng.random((B * 64, K))
+    pipe = RetrievalPipeline(FRONT3D_SR, bank=None, scene_store=torch.from_numpy(store).to(dev), device=dev)
+    got = pipe.compose(torch.from_numpy(rows).to(dev), B)
+    want = O.compose_chunks(FRONT3D_SR, rows, store, B)
+    assert np.array_equal(got.cpu().numpy(), want)
+    d = FRONT3D_SR["dataset"]
+    gotn = pipe.compose(torch.from_numpy(rows).to(dev), B, normalize=True)
+    assert np.array_equal(gotn.cpu().numpy(), ((want - d["target_mean"]) / d["target_std"]).astype(np.float32))
+
+
+# --------------------------------------------------------------------------- end to end
+
+def test_hot_path_end_to_end_small(dev):
+    """encode -> kNN -> compose -> refine on synthetic chunks vs the oracle (same as smoke())."""
+    import __graft_entry__ as G
+    G.smoke()
+
+
+def test_retrieval_interface_roundtrip(dev, tmp_path):
+    """create_dictionary -> database.npy/index.json -> query -> compose through the
+    reference-shaped API (RetrievalInterface, SceneHandler access, PatchedSceneDataset)."""
+    from retrieval_fuse_b200.dataset.patched_scene_dataset import PatchedSceneDataset
+    from retrieval_fuse_b200.dataset.scene import InMemorySceneHandler
+    from retrieval_fuse_b200.model import get_retrieval_networks
+    from retrieval_fuse_b200.pipeline import FRONT3D_SR, init_unit_gain_
+    from retrieval_fuse_b200.util import retrieval as UR
+    cfg = FRONT3D_SR
+    dc = dict(cfg["dataset"], occupancy_threshold=-1, train_multiplier=1)
+    tg = {f"sc{i}": O.synthetic_tsdf(i, 64, dc["voxel_size_target"]) for i in range(3)}
+    inp = {k: O.downsample_tsdf(v / dc["voxel_size_target"] * dc["voxel_size_input"], 8, dc["voxel_size_input"]) for k, v in tg.items()}
+    sh = InMemorySceneHandler("superresolution", dc, inp, tg)
+    ds = PatchedSceneDataset("train", dc, sh)
+    assert len(ds) == 3 * 64
+    fi, ft = get_retrieval_networks(cfg["retrieval_model"])
+    init_unit_gain_(fi, 1)
+    init_unit_gain_(ft, 2)
+    fi, ft = fi.to(dev).eval(), ft.to(dev).eval()
+    tree = tmp_path / "tree"
+    UR.create_dictionary(ft, dict(batch_size=64, num_workers=0), 64, ds, tree)
+    db = np.load(tree / "database.npy")
+    assert db.shape == (3 * 64 + 1, 71) and db[-1, 0] == -1 and json.loads((tree / "index.json").read_text()) == ds.scenes
+    # the rows follow the oracle's restatement of create_dictionary
+    sd_t = {k: v.cpu() for k, v in ft.state_dict().items()}
+    tgt = torch.from_numpy(np.stack([ds[i]["target"] for i in range(len(ds))]).astype(np.float32))
+    emb_ref = O.normalize_features(O.encoder_forward("Patch32", sd_t, tgt), 64).numpy()
+    ext = np.stack([ds[i]["extent"] for i in range(len(ds))])
+    rows_ref = O.database_rows(ds.get_scene_indices([ds[i]["scene"] for i in range(len(ds))]), ext, 8, emb_ref)
+    assert np.array_equal(db[:-1, :7], rows_ref[:, :7])
+    np.testing.assert_allclose(db[:-1, 7:], emb_ref, rtol=0, atol=1e-5)
+    zero_ref = O.zero_patch_row(lambda x: O.encoder_forward("Patch32", sd_t, x), 16, 8, 64)
+    np.testing.assert_allclose(db[-1], zero_ref[0], rtol=0, atol=1e-5)
+    ri = UR.RetrievalInterface(dict(batch_size=64, num_workers=0, K=4, flann_num_workers=0), 64)
+    mapping = ri.get_retrieval_mapping(fi, UR.extract_input_features, tree, ds, True)
+    names, feats = UR.extract_input_features(fi, ri.config, 64, ds)
+    assert sorted(mapping.keys()) == sorted(names)
+    qs = np.array([ds.scenes.index(n.split("--")[0]) for n in names])
+    want_rows, _ = O.lookup_rows(db[:, 7:], db[:, :7], feats, 4, qs)
+    for i, n in enumerate(names):
+        assert mapping[n].shape == (4, 8) and np.array_equal(mapping[n], want_rows[i])
+        assert not np.any(mapping[n][:, 0] == qs[i])  # own scene demoted out of the top 4 (3 scenes x 64 patches)
+    vol = ri.retrieve_nearest_scenes(mapping, "sc1", 4, tree, ds, ds)
+    P = ds.patch_from_scene_lookup["sc1"]
+    rows = np.stack([mapping[p] for p in P])
+    want = O.compose_chunks(cfg, rows, np.stack([tg[s] for s in ds.scenes]), 1)[0]
+    assert np.array_equal(vol.numpy(), want)
