@@ -110,12 +110,19 @@ int rf_mlp_encode_fwd(const float* x, const float* const* wt_host, const float* 
  *   once (no fma); result = k smallest under ascending (d, global row id).
  * bank [n_rows, D] is one shard whose first row has global id row_offset.
  * out_idx [Q,k] int32 global ids, out_d [Q,k] fp64.  D must be 64.
- * method: 0 = auto, 1 = exact fp64 sweep, 2 = tcgen05 candidate pass (bf16x3
- * split, fp32 accumulate in TMEM) + fp64 re-rank + proof check + fp64 sweep of
- * the queries whose candidate set could not be proven complete. */
+ * method: 0 = auto, 1 = exact fp64 sweep, 2 / 3 = tcgen05 candidate pass (2:
+ * one fp16 GEMM; 3: bf16 hi/lo split, K = 192; fp32 accumulators in TMEM) that
+ * keeps 16 candidates per query, then the canonical fp64 re-rank, a proof that
+ * no rejected row can enter or tie the top-k, and the fp64 sweep for the queries
+ * whose proof fails.  All methods return identical results (k <= 16 for 2 / 3).
+ * Methods 2 / 3 synchronise `stream` once (to read the unproven-query count). */
 size_t rf_knn_workspace_bytes(long Q, long n_rows, int k, int method);
 int rf_knn_l2_topk(const float* bank, long n_rows, long row_offset, const float* q, long Q, int D, int k, int method,
                    int* out_idx, double* out_d, void* workspace, size_t workspace_bytes, void* stream);
+/* Diagnostics of the last method-2/3 call that used `workspace`: number of
+ * queries that needed the exact re-check and the largest observed error of the
+ * tensor-core score over all re-ranked candidates (validates the bound). */
+int rf_knn_tc_stats(const void* workspace, int* n_unproven, float* max_score_err, void* stream);
 /* Merge S sorted candidate lists per query (shards of one GPU sweep or the
  * all-gathered per-rank lists): parts_idx/parts_d [S,Q,k] -> [Q,k]
  * under the same (d, id) order. */

@@ -26,11 +26,11 @@ extern "C" int rf_device_info(int device, int* sm_count, int* cc_major, int* cc_
     return 0;
 }
 
-int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, int* out_idx,
-                        double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s);
+int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, const int* q_sel,
+                        int* out_idx, double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s);
 int rf_knn_exact_nsplit(long Q, long n_rows);
-size_t rf_knn_tc_workspace_bytes(long Q, long n_rows, int k);
-int rf_knn_tc_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, int* out_idx,
+size_t rf_knn_tc_workspace_bytes(long Q, long n_rows, int k, int kblk);
+int rf_knn_tc_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, int kblk, int* out_idx,
                      double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
 static size_t exact_ws(long Q, long n_rows, int k) {
@@ -38,14 +38,20 @@ static size_t exact_ws(long Q, long n_rows, int k) {
     return ns == 1 ? 256 : (size_t)ns * Q * k * (sizeof(int) + sizeof(double)) + 256;
 }
 
+// 0 = auto: the tensor-core candidate pass whenever it applies (k <= 16, enough
+// work to amortise the operand images); fp16 single pass up to 400k rows, the
+// bf16 split above (denser banks need the tighter error bound).
+static int resolve_method(int method, long Q, long n_rows, int k) {
+    if (method != 0) return method;
+    if (k > 16 || n_rows < 1024 || Q * n_rows < (1L << 24)) return 1;
+    return n_rows <= 400000 ? 2 : 3;
+}
+
 extern "C" size_t rf_knn_workspace_bytes(long Q, long n_rows, int k, int method) {
     if (Q <= 0 || n_rows <= 0 || k <= 0) return 0;
-    size_t a = exact_ws(Q, n_rows, k);
-    if (method != 1) {
-        const size_t b = rf_knn_tc_workspace_bytes(Q, n_rows, k);
-        if (b > a) a = b;
-    }
-    return a;
+    method = resolve_method(method, Q, n_rows, k);
+    if (method == 1) return exact_ws(Q, n_rows, k);
+    return rf_knn_tc_workspace_bytes(Q, n_rows, k, method == 2 ? 1 : 3);
 }
 
 extern "C" int rf_knn_l2_topk(const float* bank, long n_rows, long row_offset, const float* q, long Q, int D, int k,
@@ -57,9 +63,10 @@ extern "C" int rf_knn_l2_topk(const float* bank, long n_rows, long row_offset, c
     RF_CHECK_ARG(k >= 1 && k <= 32 && k <= n_rows, "rf_knn_l2_topk: k=%d out of range (1..min(32, n_rows=%ld))", k, n_rows);
     RF_CHECK_ARG(row_offset >= 0 && row_offset + n_rows < (1L << 31), "rf_knn_l2_topk: row ids exceed int32");
     RF_CHECK_ARG(((uintptr_t)bank & 15) == 0 && ((uintptr_t)q & 15) == 0, "rf_knn_l2_topk: bank / q must be 16-byte aligned");
-    RF_CHECK_ARG(method >= 0 && method <= 2, "rf_knn_l2_topk: bad method %d", method);
-    if (method == 0) method = (Q >= 1024 && n_rows >= 4096 && k <= 16) ? 2 : 1;
-    if (method == 2)
-        return rf_knn_tc_launch(bank, n_rows, row_offset, q, Q, k, out_idx, out_d, workspace, workspace_bytes, (cudaStream_t)stream);
-    return rf_knn_exact_launch(bank, n_rows, row_offset, q, Q, k, out_idx, out_d, workspace, workspace_bytes, (cudaStream_t)stream);
+    RF_CHECK_ARG(method >= 0 && method <= 3, "rf_knn_l2_topk: bad method %d", method);
+    method = resolve_method(method, Q, n_rows, k);
+    if (method >= 2)
+        return rf_knn_tc_launch(bank, n_rows, row_offset, q, Q, k, method == 2 ? 1 : 3, out_idx, out_d, workspace,
+                                workspace_bytes, (cudaStream_t)stream);
+    return rf_knn_exact_launch(bank, n_rows, row_offset, q, Q, k, nullptr, out_idx, out_d, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -43,6 +43,7 @@ __device__ __forceinline__ void warp_list_insert(double& ld, int& li, double cd,
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) knn_exact_f64_kernel(const float* __restrict__ bank, long n_rows,
                                                                            long row_offset, const float* __restrict__ q,
                                                                            long Q, int k, int nsplit,
+                                                                           const int* __restrict__ q_sel,
                                                                            int* __restrict__ out_idx,
                                                                            double* __restrict__ out_d) {
     __shared__ double qs[QB][D64];
@@ -50,7 +51,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) knn_exact_f64_kernel(const
     const long q_cta = (long)blockIdx.x * QB;
     for (int i = threadIdx.x; i < QB * D64; i += blockDim.x) {
         const long qi = q_cta + i / D64;
-        qs[i / D64][i % D64] = qi < Q ? (double)q[qi * D64 + (i % D64)] : 0.0;
+        // q_sel (optional) selects a subset of the query matrix: the re-check of unproven queries
+        qs[i / D64][i % D64] = qi < Q ? (double)q[(q_sel ? (long)q_sel[qi] : qi) * D64 + (i % D64)] : 0.0;
     }
     __syncthreads();
 
@@ -107,7 +109,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) knn_exact_f64_kernel(const
     for (int j = 0; j < QW; ++j) {
         const long qi = q_cta + warp * QW + j;
         if (qi < Q && lane < k) {
-            const long o = ((long)split * Q + qi) * k + lane;
+            // single-slice sweeps write the final rows directly (through q_sel when given)
+            const long oq = (nsplit == 1 && q_sel) ? (long)q_sel[qi] : qi;
+            const long o = ((long)split * Q + oq) * k + lane;
             out_idx[o] = li[j];
             out_d[o] = ld[j];
         }
@@ -117,7 +121,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) knn_exact_f64_kernel(const
 // One warp per query: fold S sorted k-lists into one under (d, id).
 __global__ void __launch_bounds__(128) knn_merge_kernel(const int* __restrict__ parts_idx,
                                                         const double* __restrict__ parts_d, int S, long Q, int k,
-                                                        int* __restrict__ out_idx, double* __restrict__ out_d) {
+                                                        const int* __restrict__ q_sel, int* __restrict__ out_idx,
+                                                        double* __restrict__ out_d) {
     const long qi = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (qi >= Q) return;
@@ -136,7 +141,8 @@ __global__ void __launch_bounds__(128) knn_merge_kernel(const int* __restrict__ 
             tau_i = __shfl_sync(0xffffffffu, li, k - 1);
         }
     }
-    if (lane < k) { out_idx[qi * k + lane] = li; out_d[qi * k + lane] = ld; }
+    const long oq = q_sel ? (long)q_sel[qi] : qi;
+    if (lane < k) { out_idx[oq * k + lane] = li; out_d[oq * k + lane] = ld; }
 }
 
 // util/retrieval.py:93-100 per query: stable partition by "same scene as the
@@ -168,8 +174,8 @@ __global__ void __launch_bounds__(256) knn_demote_rows_kernel(const int* __restr
 
 }  // namespace
 
-int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, int* out_idx,
-                        double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s);
+int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, const int* q_sel,
+                        int* out_idx, double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s);
 int rf_knn_exact_nsplit(long Q, long n_rows);
 
 // Number of bank slices for the exact sweep: enough warps to fill the chip.
@@ -183,12 +189,13 @@ int rf_knn_exact_nsplit(long Q, long n_rows) {
     return (int)want;
 }
 
-int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, int* out_idx,
-                        double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+// q_sel == NULL: queries 0..Q-1 of q.  q_sel != NULL: the Q queries q[q_sel[i]], results written to rows q_sel[i].
+int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, const int* q_sel,
+                        int* out_idx, double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s) {
     const int nsplit = rf_knn_exact_nsplit(Q, n_rows);
     dim3 grid((unsigned)((Q + QB - 1) / QB), nsplit);
     if (nsplit == 1) {
-        knn_exact_f64_kernel<<<grid, WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, k, 1, out_idx, out_d);
+        knn_exact_f64_kernel<<<grid, WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, k, 1, q_sel, out_idx, out_d);
         RF_LAUNCH_OK("knn_exact_f64_kernel");
         return 0;
     }
@@ -196,9 +203,9 @@ int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const f
     RF_CHECK_ARG(workspace && workspace_bytes >= need, "rf_knn_l2_topk: workspace too small (%zu < %zu)", workspace_bytes, need);
     double* pd = (double*)workspace;
     int* pi = (int*)(pd + (size_t)nsplit * Q * k);
-    knn_exact_f64_kernel<<<grid, WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, k, nsplit, pi, pd);
+    knn_exact_f64_kernel<<<grid, WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, k, nsplit, q_sel, pi, pd);
     RF_LAUNCH_OK("knn_exact_f64_kernel");
-    knn_merge_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, s>>>(pi, pd, nsplit, Q, k, out_idx, out_d);
+    knn_merge_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, s>>>(pi, pd, nsplit, Q, k, q_sel, out_idx, out_d);
     RF_LAUNCH_OK("knn_merge_kernel");
     return 0;
 }
@@ -207,7 +214,7 @@ extern "C" int rf_knn_merge(const int* parts_idx, const double* parts_d, int S, 
                             double* out_d, void* stream) {
     RF_CHECK_ARG(parts_idx && parts_d && out_idx && out_d, "rf_knn_merge: null pointer");
     RF_CHECK_ARG(S > 0 && Q > 0 && k > 0 && k <= 32, "rf_knn_merge: bad sizes S=%d Q=%ld k=%d", S, Q, k);
-    knn_merge_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, (cudaStream_t)stream>>>(parts_idx, parts_d, S, Q, k, out_idx, out_d);
+    knn_merge_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, (cudaStream_t)stream>>>(parts_idx, parts_d, S, Q, k, nullptr, out_idx, out_d);
     RF_LAUNCH_OK("knn_merge_kernel");
     return 0;
 }

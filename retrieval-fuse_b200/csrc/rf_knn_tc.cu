@@ -1,13 +1,589 @@
-// tcgen05 candidate pass for the kNN (placeholder until the TMEM kernel lands:
-// method 2 currently routes to the exact fp64 sweep so that the ABI is stable).
+// tcgen05 candidate pass for the exact kNN (methods 2 and 3 of rf_knn_l2_topk).
+//
+// Idea: the canonical ranking is by the fp64 distance, but almost all of the
+// 2*Q*N*64 flops are only needed to REJECT rows.  So:
+//   1. evaluate an approximate score s~ ~ q.x on the 5th-gen tensor cores
+//      (tcgen05.mma, fp32 accumulators in TMEM) with a proven error bound
+//      |s~ - q.x| <= eps_rel |q| |x|:
+//        method 2: one fp16 GEMM, K = 64          (eps_rel = 1.0e-3)
+//        method 3: bf16 hi/lo split, K = 3*64: q_hi.x_hi + q_hi.x_lo + q_lo.x_hi
+//                  (x = hi + lo + r, |r| <= 2^-18 |x|; eps_rel = 4e-5)
+//   2. each query keeps its CAND = 16 best s~ (a register-resident sorted list
+//      owned by the epilogue thread that reads the query's TMEM lane).
+//   3. re-rank the 16 candidates with the canonical fp64 arithmetic, and PROVE
+//      completeness: every rejected row has s~ <= tau (the 16th best), hence
+//      d >= |q|^2 + min|x|^2 - 2 (tau + eps); if the k-th best candidate's exact
+//      d is strictly below that bound, no rejected row can enter or tie the
+//      top-k.  Queries that cannot be proven (dense ties, duplicates beyond the
+//      slack) are re-done by the exact fp64 sweep (rf_knn.cu).
+// The result is therefore bit-identical to method 1 by construction.
+//
+// Operand staging: both operands are pre-arranged in HBM as byte images of
+// the shared-memory tiles the MMA reads - [tile][kb][128 rows][128 B], K-major,
+// 128-byte swizzle (16-byte chunk index XOR row%8) - so that one
+// cp.async.bulk (TMA bulk copy, 16 KiB) per K-block lands a ready-to-use
+// SWIZZLE_128B operand; no tensor map, no register staging.
+//
+// CTA = 256 queries (two M=128 sub-tiles, so every bank byte pulled from L2
+// feeds 2x128 rows of MMA) x a slice of bank tiles; 12 warps:
+//   warp 0  producer   : bulk copies into a ring of bank-tile stages
+//   warp 1  MMA issuer : one thread, 2 x KBLK x 4 tcgen05.mma (M128 N128 K16) per tile
+//   warp 2  TMEM alloc : 512 columns = 2 buffers x 2 sub-tiles x 128 columns
+//   warps 4-11 epilogue: tcgen05.ld 32 columns at a time, running top-16
+// smem<->MMA and MMA<->epilogue hand-offs are mbarriers (full/empty rings).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <float.h>
+#include <string.h>
+#include <limits.h>
+
 #include "rf_common.cuh"
 
-int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, int* out_idx,
-                        double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s);
+int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, const int* q_sel,
+                        int* out_idx, double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s);
+int rf_knn_exact_nsplit(long Q, long n_rows);
 
-size_t rf_knn_tc_workspace_bytes(long Q, long n_rows, int k) { (void)Q; (void)n_rows; (void)k; return 256; }
+namespace {
 
-int rf_knn_tc_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, int* out_idx,
+constexpr int TILE = 128;              // rows per operand tile (UMMA M and N)
+constexpr int MQ = 2;                  // query sub-tiles per CTA
+constexpr int KB_BYTES = TILE * 128;   // one K block: 64 x 16-bit per row, 16 KiB
+constexpr int NACC = 2;                // TMEM accumulator buffers (MQ x 128 columns each)
+constexpr int CAND = 16;               // candidates kept per query and bank slice
+constexpr int MAX_SPLIT = 8;
+constexpr int NTHREADS = 128 + MQ * 128;
+
+template <int KBLK> struct Cfg {
+    static constexpr int TILE_BYTES = KBLK * KB_BYTES;
+    static constexpr int NSTAGE = KBLK == 1 ? 6 : 2;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + TILE_BYTES * (MQ + NSTAGE) + 256 /*barriers*/;
+};
+// bound on |s~ - q.x| / (|q| |x|), see DESIGN.md "kNN proof"
+// (+4e-6: the epilogue tags scores with their column in the low 5 mantissa bits)
+__host__ __device__ constexpr float eps_rel(int kblk) { return kblk == 1 ? 1.004e-3f : 4.4e-5f; }
+
+struct Stats {            // first 256 bytes of the workspace
+    int n_flagged;        // queries whose top-k could not be proven
+    unsigned max_err_bits;  // max observed |s~ - s| over candidates (float bits)
+    unsigned nmin_bits;   // min |x|^2 over the bank (float bits)
+    unsigned nmax_bits;   // max |x|^2
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// try_wait suspends the thread for a hardware time slice per attempt; a
+// pipeline bug must never hang the GPU, so give up (trap) after ~seconds.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 26)) {
+            printf("rf_knn_tc: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
+                   threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// Issue a 32-lane x 32-column TMEM load; the registers are valid after tc_ld_wait().
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, float (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+        "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+          "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+          "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory operand descriptor (sm_100 UMMA):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for
+//   swizzled K-major; 1) | [32,46) stride byte offset >> 4 = 1024 B between
+//   8-row groups | [46,48) version = 1 | [61,64) layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A = B = bf16 (bits
+// 7-9, 10-12 = 1), both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24
+// (A/B format 0 = f16, 1 = bf16)
+__host__ __device__ constexpr uint32_t idesc(int ab_format) {
+    return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) | ((uint32_t)(TILE >> 3) << 17) |
+           ((uint32_t)(TILE >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ prep
+// src [n_rows, 64] fp32 -> swizzled 16-bit tile images [(n_tiles), KBLK, 128 rows, 128 B].
+// KBLK = 1: fp16(x).  KBLK = 3: bf16 split, bank K blocks = (hi, lo, hi), queries (hi, hi, lo).
+// For the bank the range of |x|^2 is recorded.
+template <int KBLK>
+__global__ void __launch_bounds__(256) knn_tc_prep_kernel(const float* __restrict__ src, long n_rows, long n_rows_padded,
+                                                          int is_bank, uint8_t* __restrict__ img, Stats* stats) {
+    const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;  // one thread per (row, 16-byte chunk)
+    const long row = gid >> 3;
+    const int c = (int)(gid & 7);
+    float nrm = 0.f;
+    if (row < n_rows_padded) {
+        float x[8];
+        if (row < n_rows) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + row * 64 + c * 8));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src + row * 64 + c * 8 + 4));
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = 0.f;
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (KBLK == 1) {
+                hi[i] = (uint32_t)__half_as_ushort(__float2half_rn(x[2 * i])) |
+                        ((uint32_t)__half_as_ushort(__float2half_rn(x[2 * i + 1])) << 16);
+                lo[i] = 0u;
+            } else {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+                hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            nrm = fmaf(x[2 * i], x[2 * i], nrm);
+            nrm = fmaf(x[2 * i + 1], x[2 * i + 1], nrm);
+        }
+        const long tile = row / TILE;
+        const int r = (int)(row % TILE);
+        const uint4 vhi = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        uint8_t* base = img + tile * (long)(KBLK * KB_BYTES) + (long)r * 128 + ((c ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(base) = vhi;
+        if (KBLK == 3) {
+            const uint4 vlo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(base + KB_BYTES) = is_bank ? vlo : vhi;
+            *reinterpret_cast<uint4*>(base + 2 * KB_BYTES) = is_bank ? vhi : vlo;
+        }
+    }
+    if (is_bank) {  // |x|^2 per row: reduce over the row's 8 chunk threads (consecutive lanes)
+        nrm += __shfl_xor_sync(0xffffffffu, nrm, 1);
+        nrm += __shfl_xor_sync(0xffffffffu, nrm, 2);
+        nrm += __shfl_xor_sync(0xffffffffu, nrm, 4);
+        if (c == 0 && row < n_rows) {  // non-negative floats order like their bit patterns
+            atomicMin(&stats->nmin_bits, __float_as_uint(nrm));
+            atomicMax(&stats->nmax_bits, __float_as_uint(nrm));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ main kernel
+template <int KBLK>
+__global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const uint8_t* __restrict__ q_img,
+                                                                        const uint8_t* __restrict__ bank_img, long Q,
+                                                                        long n_rows, int n_qtiles, int n_btiles,
+                                                                        int tiles_per_split, float* __restrict__ cand_s,
+                                                                        int* __restrict__ cand_i) {
+    constexpr int TILE_BYTES = Cfg<KBLK>::TILE_BYTES;
+    constexpr int NSTAGE = Cfg<KBLK>::NSTAGE;
+    constexpr uint32_t IDESC = idesc(KBLK == 1 ? 0 : 1);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+    const uint32_t sA = smem_base;                          // MQ query sub-tiles
+    const uint32_t sB = smem_base + MQ * TILE_BYTES;        // NSTAGE bank tiles
+    const uint32_t bars = smem_base + TILE_BYTES * (MQ + NSTAGE);
+    const uint32_t bar_full = bars;                     // NSTAGE x 8 B
+    const uint32_t bar_empty = bars + 8 * NSTAGE;       // NSTAGE x 8 B
+    const uint32_t bar_a = bars + 16 * NSTAGE;          // 8 B
+    const uint32_t bar_tfull = bar_a + 8;               // NACC x 8 B
+    const uint32_t bar_tempty = bar_tfull + 8 * NACC;   // NACC x 8 B
+    const uint32_t tmem_slot = bar_tempty + 8 * NACC;   // 4 B
+    volatile uint32_t* tmem_slot_gen =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qpair = blockIdx.x, split = blockIdx.y;
+    const int t_begin = split * tiles_per_split;
+    int t_end = t_begin + tiles_per_split;
+    if (t_end > n_btiles) t_end = n_btiles;
+    const int n_iter = t_end > t_begin ? t_end - t_begin : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_a, 1);
+        for (int b = 0; b < NACC; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, MQ * 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {  // TMEM: all 512 columns (one CTA per SM by launch bounds)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---------------- producer
+            // the query pair: sub-tile m of this CTA is query tile 2*qpair+m (the image is padded to an even tile count)
+            mbar_arrive_expect_tx(bar_a, MQ * TILE_BYTES);
+            for (int j = 0; j < MQ * KBLK; ++j)
+                bulk_g2s(sA + j * KB_BYTES, q_img + (long)qpair * MQ * TILE_BYTES + (long)j * KB_BYTES, KB_BYTES, bar_a);
+            for (int it = 0; it < n_iter; ++it) {
+                const int s = it % NSTAGE;
+                const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1u);  // a fresh barrier passes the parity-1 wait
+                mbar_arrive_expect_tx(bar_full + 8 * s, TILE_BYTES);
+                const uint8_t* src = bank_img + (long)(t_begin + it) * TILE_BYTES;
+                for (int kb = 0; kb < KBLK; ++kb)
+                    bulk_g2s(sB + s * TILE_BYTES + kb * KB_BYTES, src + (long)kb * KB_BYTES, KB_BYTES, bar_full + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---------------- MMA issuer
+            mbar_wait(bar_a, 0);
+            for (int it = 0; it < n_iter; ++it) {
+                const int s = it % NSTAGE, b = it % NACC;
+                const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u, bph = (uint32_t)(it / NACC) & 1u;
+                mbar_wait(bar_tempty + 8 * b, bph ^ 1u);  // epilogue has drained this accumulator buffer
+                mbar_wait(bar_full + 8 * s, ph);          // bank tile landed
+                tc_fence_after();
+#pragma unroll
+                for (int m = 0; m < MQ; ++m) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((b * MQ + m) * TILE);
+#pragma unroll
+                    for (int kb = 0; kb < KBLK; ++kb) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {  // 4 x K=16 (32 B) steps inside one 128 B swizzle atom
+                            const uint64_t ad = umma_desc(sA + m * TILE_BYTES + kb * KB_BYTES + k * 32);
+                            const uint64_t bd = umma_desc(sB + s * TILE_BYTES + kb * KB_BYTES + k * 32);
+                            tc_mma_bf16(d_tmem, ad, bd, IDESC, (kb | k) ? 1u : 0u);
+                        }
+                    }
+                }
+                tc_commit(bar_empty + 8 * s);   // smem stage reusable once these MMAs retire
+                tc_commit(bar_tfull + 8 * b);   // accumulators ready for the epilogue
+            }
+        }
+    } else if (warp >= 4) {  // ---------------- epilogue: thread <-> query row (TMEM lane)
+        const int ew = warp - 4;          // 0..7
+        const int quad = ew & 3;          // a warp may only touch TMEM lanes [32*(warp%4), +32); warp%4 == ew%4
+        const int m = ew >> 2;            // query sub-tile
+        float ls[CAND];
+        int li[CAND];
+#pragma unroll
+        for (int i = 0; i < CAND; ++i) { ls[i] = -FLT_MAX; li[i] = -1; }
+        float tau = -FLT_MAX;
+        // Software pipeline over the tile's four 32-column chunks: the TMEM load of
+        // chunk c+1 is in flight while chunk c is scanned (two register buffers).
+        float va[32], vb[32];
+        for (int it = 0; it < n_iter; ++it) {
+            const int b = it % NACC;
+            const uint32_t bph = (uint32_t)(it / NACC) & 1u;
+            mbar_wait(bar_tfull + 8 * b, bph);
+            tc_fence_after();
+            const long col_tile = (long)(t_begin + it) * TILE;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((b * MQ + m) * TILE);
+            tc_ld32_issue(taddr, va);
+#pragma unroll
+            for (int c = 0; c < TILE / 32; ++c) {
+                float(&v)[32] = (c & 1) ? vb : va;
+                float(&vn)[32] = (c & 1) ? va : vb;
+                tc_ld_wait();
+                if (c + 1 < TILE / 32) tc_ld32_issue(taddr + (uint32_t)((c + 1) * 32), vn);
+                const long col0 = col_tile + c * 32;
+                if (col0 + 32 > n_rows) {  // padded rows of the last tile never compete
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j >= n_rows) v[j] = -FLT_MAX;
+                }
+                float mx = fmaxf(v[0], v[1]);
+#pragma unroll
+                for (int j = 2; j < 32; j += 2) mx = fmaxf(mx, fmaxf(v[j], v[j + 1]));
+                if (mx > tau) {
+                    // Rare path, ONE code site: tag every score with its column (low 5
+                    // mantissa bits; costs 2^-18 relative, covered by the proof's eps),
+                    // then repeatedly pull the maximum while it beats tau.
+                    float key[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) key[j] = __uint_as_float((__float_as_uint(v[j]) & ~31u) | (uint32_t)j);
+#pragma unroll 1
+                    for (int guard = 0; guard < 32; ++guard) {
+                        float km = fmaxf(key[0], key[1]);
+#pragma unroll
+                        for (int j = 2; j < 32; j += 2) km = fmaxf(km, fmaxf(key[j], key[j + 1]));
+                        if (!(km > tau)) break;
+                        float cs = km;
+                        int ci = (int)(col0 + (long)(__float_as_uint(km) & 31u));
+#pragma unroll
+                        for (int i = 0; i < CAND; ++i) {  // insert into the descending list, dropping the last
+                            const bool gt = cs > ls[i];
+                            const float ts = gt ? ls[i] : cs;
+                            const int ti = gt ? li[i] : ci;
+                            ls[i] = gt ? cs : ls[i];
+                            li[i] = gt ? ci : li[i];
+                            cs = ts;
+                            ci = ti;
+                        }
+                        tau = ls[CAND - 1];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) key[j] = (key[j] == km) ? -FLT_MAX : key[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * b);
+        }
+        const long q = ((long)qpair * MQ + m) * TILE + quad * 32 + lane;
+        if (q < Q) {
+            float* os = cand_s + ((long)split * Q + q) * CAND;
+            int* oi = cand_i + ((long)split * Q + q) * CAND;
+#pragma unroll
+            for (int i = 0; i < CAND; ++i) { os[i] = ls[i]; oi[i] = li[i]; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ re-rank + proof
+__device__ __forceinline__ bool cand_less(double d, int i, double d2, int i2) { return d < d2 || (d == d2 && i < i2); }
+
+__device__ __forceinline__ void warp_list_insert(double& ld, int& li, double cd, int ci, int lane) {
+    const bool before = cand_less(ld, li, cd, ci);
+    const int pos = __popc(__ballot_sync(0xffffffffu, before));
+    const double ud = __shfl_up_sync(0xffffffffu, ld, 1);
+    const int ui = __shfl_up_sync(0xffffffffu, li, 1);
+    if (lane == pos) { ld = cd; li = ci; }
+    else if (lane > pos) { ld = ud; li = ui; }
+}
+
+// One warp per query.  Candidate c of slice s: (cand_s, cand_i)[s][q][c].
+__global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restrict__ bank, long row_offset,
+                                                            const float* __restrict__ q, long Q, int k, int S,
+                                                            const float* __restrict__ cand_s, const int* __restrict__ cand_i,
+                                                            int* __restrict__ out_idx, double* __restrict__ out_d,
+                                                            int* __restrict__ flagged, Stats* stats, float eps_r) {
+    const long qi = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (qi >= Q) return;
+    // the query in fp64, two elements per lane; |q|^2
+    const float* qr = q + qi * 64;
+    const double q0 = (double)qr[lane], q1 = (double)qr[lane + 32];
+    double qn = q0 * q0 + q1 * q1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
+
+    double ld = DBL_MAX;
+    int li = INT_MAX;
+    float tau = -FLT_MAX;       // max over slices of the slice's 16th best approximate score
+    float err = 0.f;
+    const int total = S * CAND;
+    for (int base = 0; base < total; base += 32) {
+        const int c = base + lane;
+        int id = -1;
+        float sc = -FLT_MAX;
+        if (c < total) {
+            const long o = ((long)(c / CAND) * Q + qi) * CAND + (c % CAND);
+            id = cand_i[o];
+            sc = cand_s[o];
+            if ((c % CAND) == CAND - 1 && id >= 0) tau = fmaxf(tau, sc);  // a full list: its tail bounds the rejected rows
+        }
+        double d = DBL_MAX;
+        if (id >= 0) {  // canonical fp64 distance, same arithmetic as the exact sweep
+            const float4* xr = reinterpret_cast<const float4*>(bank + (long)id * 64);
+            double acc = 0.0, xn = 0.0;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const float4 x4 = __ldg(xr + i);
+                const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double qv = (double)qr[4 * i + j];
+                    const double diff = __dsub_rn(qv, (double)xv[j]);
+                    acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+                    xn = fma((double)xv[j], (double)xv[j], xn);
+                }
+            }
+            d = acc;
+            // observed approximation error of the tensor-core score (diagnostic for EPS_REL)
+            const double s_exact = 0.5 * (qn + xn - acc);
+            err = fmaxf(err, (float)fabs((double)sc - s_exact));
+        }
+        // insert this round's candidates one by one (warp-uniform loop)
+        unsigned m = __ballot_sync(0xffffffffu, id >= 0);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const double cd = __shfl_sync(0xffffffffu, d, src);
+            const int ci = __shfl_sync(0xffffffffu, id, src) + (int)row_offset;
+            warp_list_insert(ld, li, cd, ci, lane);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
+        err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
+    }
+    if (lane < k) { out_idx[qi * k + lane] = li; out_d[qi * k + lane] = ld; }
+    // proof: rejected rows have s~ <= tau  =>  d >= |q|^2 + min|x|^2 - 2 (tau + eps)
+    const double dk = __shfl_sync(0xffffffffu, ld, k - 1);
+    bool proven = true;
+    if (tau > -FLT_MAX) {
+        const double nmin = (double)__uint_as_float(stats->nmin_bits);
+        const double nmax = (double)__uint_as_float(stats->nmax_bits);
+        const double eps = (double)eps_r * sqrt(qn * nmax) + 2e-6;
+        const double d_lb = qn + nmin * (1.0 - 1e-6) - 2.0 * ((double)tau + eps);
+        proven = dk < d_lb - 1e-9;
+    }
+    if (lane == 0) {
+        if (!proven) flagged[atomicAdd(&stats->n_flagged, 1)] = (int)qi;
+        atomicMax(&stats->max_err_bits, __float_as_uint(err));
+    }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct TcLayout {
+    size_t stats, bank_img, q_img, cand_s, cand_i, flagged, exact_ws, total;
+    int n_btiles, n_qtiles, n_qpairs, nsplit, tiles_per_split;
+    size_t exact_ws_bytes;
+};
+
+TcLayout tc_layout(long Q, long n_rows, int k, int kblk) {
+    TcLayout L;
+    const size_t tile_bytes = (size_t)kblk * KB_BYTES;
+    L.n_btiles = (int)((n_rows + TILE - 1) / TILE);
+    L.n_qpairs = (int)((Q + MQ * TILE - 1) / (MQ * TILE));
+    L.n_qtiles = L.n_qpairs * MQ;
+    int ns = (148 + L.n_qpairs - 1) / L.n_qpairs;  // fill the chip when there are few query tiles
+    if (ns > MAX_SPLIT) ns = MAX_SPLIT;
+    if (ns > L.n_btiles) ns = L.n_btiles;
+    if (ns < 1) ns = 1;
+    L.tiles_per_split = (L.n_btiles + ns - 1) / ns;
+    L.nsplit = (L.n_btiles + L.tiles_per_split - 1) / L.tiles_per_split;
+    size_t off = 0;
+    L.stats = off; off += 256;
+    off = align_up(off, 1024);
+    L.bank_img = off; off += (size_t)L.n_btiles * tile_bytes;
+    L.q_img = off; off += (size_t)L.n_qtiles * tile_bytes;
+    L.cand_s = off; off += align_up((size_t)L.nsplit * Q * CAND * sizeof(float), 256);
+    L.cand_i = off; off += align_up((size_t)L.nsplit * Q * CAND * sizeof(int), 256);
+    L.flagged = off; off += align_up((size_t)Q * sizeof(int), 256);
+    // the exact re-check of unproven queries: worst case every query, see rf_knn_exact_nsplit
+    L.exact_ws_bytes = ((size_t)148 * 8 * 32 + (size_t)Q) * k * (sizeof(int) + sizeof(double)) + 256;
+    L.exact_ws = off; off += L.exact_ws_bytes;
+    L.total = off;
+    return L;
+}
+
+template <int KBLK>
+int tc_run(const TcLayout& L, const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, int* out_idx,
+           double* out_d, char* ws, cudaStream_t s) {
+    Stats* stats = (Stats*)(ws + L.stats);
+    uint8_t* bank_img = (uint8_t*)(ws + L.bank_img);
+    uint8_t* q_img = (uint8_t*)(ws + L.q_img);
+    float* cand_s = (float*)(ws + L.cand_s);
+    int* cand_i = (int*)(ws + L.cand_i);
+    int* flagged = (int*)(ws + L.flagged);
+    static bool attr_set = false;
+    if (!attr_set) {
+        RF_CUDA_OK(cudaFuncSetAttribute(knn_tc_candidates_kernel<KBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg<KBLK>::SMEM_BYTES));
+        attr_set = true;
+    }
+    const Stats init = {0, 0u, 0x7f7fffffu /*FLT_MAX*/, 0u};
+    RF_CUDA_OK(cudaMemcpyAsync(stats, &init, sizeof(Stats), cudaMemcpyHostToDevice, s));
+    const long bpad = (long)L.n_btiles * TILE, qpad = (long)L.n_qtiles * TILE;
+    knn_tc_prep_kernel<KBLK><<<(unsigned)rf_cdivl(bpad * 8, 256), 256, 0, s>>>(bank, n_rows, bpad, 1, bank_img, stats);
+    RF_LAUNCH_OK("knn_tc_prep_kernel(bank)");
+    knn_tc_prep_kernel<KBLK><<<(unsigned)rf_cdivl(qpad * 8, 256), 256, 0, s>>>(q, Q, qpad, 0, q_img, stats);
+    RF_LAUNCH_OK("knn_tc_prep_kernel(queries)");
+    dim3 grid(L.n_qpairs, L.nsplit);
+    knn_tc_candidates_kernel<KBLK><<<grid, NTHREADS, Cfg<KBLK>::SMEM_BYTES, s>>>(q_img, bank_img, Q, n_rows, L.n_qtiles,
+                                                                               L.n_btiles, L.tiles_per_split, cand_s, cand_i);
+    RF_LAUNCH_OK("knn_tc_candidates_kernel");
+    knn_tc_rerank_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, s>>>(bank, row_offset, q, Q, k, L.nsplit, cand_s, cand_i,
+                                                                        out_idx, out_d, flagged, stats, eps_rel(KBLK));
+    RF_LAUNCH_OK("knn_tc_rerank_kernel");
+    return 0;
+}
+
+}  // namespace
+
+size_t rf_knn_tc_workspace_bytes(long Q, long n_rows, int k, int kblk) { return tc_layout(Q, n_rows, k, kblk).total + 1024; }
+
+// kblk = 1: fp16 single pass (method 2); kblk = 3: bf16 hi/lo split (method 3)
+int rf_knn_tc_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, int kblk, int* out_idx,
                      double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s) {
-    return rf_knn_exact_launch(bank, n_rows, row_offset, q, Q, k, out_idx, out_d, workspace, workspace_bytes, s);
+    RF_CHECK_ARG(k <= CAND, "rf_knn_l2_topk(tensor-core methods): k=%d exceeds the candidate list (%d)", k, CAND);
+    RF_CHECK_ARG(n_rows >= k, "rf_knn_l2_topk(tensor-core methods): fewer bank rows than k");
+    const TcLayout L = tc_layout(Q, n_rows, k, kblk);
+    char* ws = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);  // swizzled tile images need 1024-byte alignment
+    RF_CHECK_ARG(workspace && workspace_bytes >= L.total + (size_t)(ws - (char*)workspace),
+                 "rf_knn_l2_topk(tensor-core methods): workspace too small (%zu < %zu)", workspace_bytes, L.total + 1024);
+    int rc = kblk == 1 ? tc_run<1>(L, bank, n_rows, row_offset, q, Q, k, out_idx, out_d, ws, s)
+                       : tc_run<3>(L, bank, n_rows, row_offset, q, Q, k, out_idx, out_d, ws, s);
+    if (rc) return rc;
+    // unproven queries (normally none): exact fp64 sweep, results scattered through `flagged`
+    int n_flagged = 0;
+    RF_CUDA_OK(cudaMemcpyAsync(&n_flagged, &((Stats*)(ws + L.stats))->n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
+    RF_CUDA_OK(cudaStreamSynchronize(s));
+    if (n_flagged > 0)
+        return rf_knn_exact_launch(bank, n_rows, row_offset, q, n_flagged, k, (const int*)(ws + L.flagged), out_idx, out_d,
+                                   ws + L.exact_ws, L.exact_ws_bytes, s);
+    return 0;
+}
+
+// Diagnostics of the last tensor-core call that used `workspace` (synchronises the stream).
+extern "C" int rf_knn_tc_stats(const void* workspace, int* n_unproven, float* max_score_err, void* stream) {
+    RF_CHECK_ARG(workspace, "rf_knn_tc_stats: null workspace");
+    Stats h;
+    const void* ws = (const void*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    RF_CUDA_OK(cudaMemcpyAsync(&h, ws, sizeof(Stats), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    RF_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (n_unproven) *n_unproven = h.n_flagged;
+    if (max_score_err) memcpy(max_score_err, &h.max_err_bits, sizeof(float));
+    return 0;
 }

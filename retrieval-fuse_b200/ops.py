@@ -255,9 +255,13 @@ def mlp_encode(x, wts, biases, l2_normalize=True):
 # kNN
 # ---------------------------------------------------------------------------
 
-def knn_topk(bank, q, k, row_offset=0, method=0):
+last_knn_stats = {}
+
+
+def knn_topk(bank, q, k, row_offset=0, method=0, stats=False):
     """Exact top-k under the canonical (fp64 d, row id) rule.
-    bank [n,64] fp32, q [Q,64] fp32 -> (idx int32 [Q,k] global ids, d fp64 [Q,k])."""
+    bank [n,64] fp32, q [Q,64] fp32 -> (idx int32 [Q,k] global ids, d fp64 [Q,k]).
+    stats=True also fills ops.last_knn_stats for the tensor-core methods."""
     bank = _dev(bank, name="bank")
     q = _dev(q, name="q")
     n, D = bank.shape
@@ -270,7 +274,13 @@ def knn_topk(bank, q, k, row_offset=0, method=0):
     with torch.cuda.device(q.device):
         check(L.rf_knn_l2_topk(bank.data_ptr(), n, int(row_offset), q.data_ptr(), Q, D, k, method, idx.data_ptr(),
                                d.data_ptr(), ws.data_ptr(), ws.numel(), _stream(q)), "rf_knn_l2_topk")
-    _count(2)
+        if stats:
+            import ctypes
+            nu, err = ctypes.c_int(-1), ctypes.c_float(-1.0)
+            if method != 1:
+                check(L.rf_knn_tc_stats(ws.data_ptr(), ctypes.byref(nu), ctypes.byref(err), _stream(q)), "rf_knn_tc_stats")
+            last_knn_stats.update(n_unproven=nu.value, max_score_err=err.value)
+    _count(4)
     return idx, d
 
 

@@ -239,30 +239,31 @@ class RefinementPipeline(RetrievalPipeline):
 # synthetic data on the device (setup only; not part of any timed region)
 # ---------------------------------------------------------------------------
 
-def synthetic_tsdf_batch(n, size, voxel_size, seed, device, n_prims=5):
+def synthetic_tsdf_batch(n, size, voxel_size, seed, device, n_prims=5, batch=128):
     """n random TSDF chunks [n, size,size,size]: unsigned distance to a union of
     sphere shells and planes, in voxel units * voxel_size, clamped to the
-    float16 truncation.  Generated with torch ops on the device."""
+    float16 truncation.  Generated with torch ops on the device,
+    `batch` chunks at a time (setup only)."""
     g = torch.Generator(device="cpu").manual_seed(int(seed))
     trunc = f16_trunc(voxel_size)
     ax = (torch.arange(size, dtype=torch.float32, device=device) + 0.5)
-    X, Y, Z = torch.meshgrid(ax, ax, ax, indexing="ij")
+    X, Y, Z = [t[None] for t in torch.meshgrid(ax, ax, ax, indexing="ij")]
     out = torch.empty((n, size, size, size), dtype=torch.float32, device=device)
     par = torch.rand((n, n_prims, 8), generator=g).to(device)
-    for i in range(n):
-        d = torch.full((size, size, size), 1e9, dtype=torch.float32, device=device)
+    for lo in range(0, n, batch):
+        p = par[lo: lo + batch]
+        d = torch.full((p.shape[0], size, size, size), 1e9, dtype=torch.float32, device=device)
         for j in range(n_prims):
-            p = par[i, j]
-            cx, cy, cz = p[0] * size, p[1] * size, p[2] * size
-            if p[3] < 0.6:
-                r = (0.08 + 0.25 * p[4]) * size
-                dd = (torch.sqrt((X - cx) ** 2 + (Y - cy) ** 2 + (Z - cz) ** 2) - r).abs()
-            else:
-                nrm = p[5:8] * 2 - 1
-                nrm = nrm / nrm.norm().clamp_min(1e-6)
-                dd = ((X - cx) * nrm[0] + (Y - cy) * nrm[1] + (Z - cz) * nrm[2]).abs()
-            d = torch.minimum(d, dd)
-        out[i] = torch.clamp(d * voxel_size, max=trunc)
+            v = lambda c: p[:, j, c].reshape(-1, 1, 1, 1)
+            cx, cy, cz = v(0) * size, v(1) * size, v(2) * size
+            r = (0.08 + 0.25 * v(4)) * size
+            sphere = (torch.sqrt((X - cx) ** 2 + (Y - cy) ** 2 + (Z - cz) ** 2) - r).abs()
+            nrm = p[:, j, 5:8] * 2 - 1
+            nrm = nrm / nrm.norm(dim=1, keepdim=True).clamp_min(1e-6)
+            w = lambda c: nrm[:, c].reshape(-1, 1, 1, 1)
+            plane = ((X - cx) * w(0) + (Y - cy) * w(1) + (Z - cz) * w(2)).abs()
+            d = torch.minimum(d, torch.where(v(3) < 0.6, sphere, plane))
+        out[lo: lo + batch] = torch.clamp(d * voxel_size, max=trunc)
     return out
 
 
@@ -275,9 +276,13 @@ def downsample_tsdf_batch(target, factor, voxel_size_target, voxel_size_input):
     return torch.clamp(v, max=f16_trunc(voxel_size_input)).unsqueeze(1).contiguous()
 
 
-def build_bank_from_targets(config, targets, device, fenc_target=None, weight_seed=None, batch_patches=512):
+def build_bank_from_targets(config, targets, device, fenc_target=None, weight_seed=None, batch_patches=512,
+                            scene_offset=0, n_scenes_total=None):
     """create_dictionary (util/retrieval.py:29-55) for GPU-resident scenes:
-    targets [S,64,64,64] raw TSDF -> EmbeddingBank with S*64 rows + the sentinel."""
+    targets [S,64,64,64] raw TSDF -> EmbeddingBank with S*64 rows + the sentinel.
+    With scene_offset / n_scenes_total the result is the row shard of a larger
+    bank (scenes [scene_offset, scene_offset+S) of n_scenes_total; the sentinel
+    row belongs to the last shard; meta is always the full table)."""
     d = config["dataset"]
     lat = config["retrieval_model"]["latent_dim"]
     if fenc_target is None:
@@ -289,23 +294,28 @@ def build_bank_from_targets(config, targets, device, fenc_target=None, weight_se
     n = d["target_chunk_size"] // d["patch_stride"]
     P = n ** 3
     S = targets.shape[0]
+    S_tot = n_scenes_total if n_scenes_total is not None else S
+    last = scene_offset + S == S_tot
     trunc = f16_trunc(d["voxel_size_target"])
-    emb = torch.empty((S * P + 1, lat), dtype=torch.float32, device=device)
+    emb = torch.empty((S * P + (1 if last else 0), lat), dtype=torch.float32, device=device)
     per = max(1, batch_patches // P)
     for lo in range(0, S, per):
         hi = min(lo + per, S)
         patches = ops.unfold3d_pad_stride(targets[lo:hi].unsqueeze(1), ps + 2 * ctx, ctx, d["patch_stride"], trunc,
                                           norm_sub=d["target_mean"], norm_div=d["target_std"])
         emb[lo * P: hi * P] = _encode_normalized(fenc_target, patches, lat)
-    ones = torch.ones((1, 1) + (ps + 2 * ctx,) * 3, dtype=torch.float32, device=device)
-    emb[S * P] = _encode_normalized(fenc_target, ones, lat)[0]  # get_zero_patch_entry
+    if last:
+        ones = torch.ones((1, 1) + (ps + 2 * ctx,) * 3, dtype=torch.float32, device=device)
+        emb[S * P] = _encode_normalized(fenc_target, ones, lat)[0]  # get_zero_patch_entry
     ext = torch.tensor([[x * ps, x * ps + ps, y * ps, y * ps + ps, z * ps, z * ps + ps]
                         for x in range(n) for y in range(n) for z in range(n)], dtype=torch.float32, device=device)
-    meta = torch.empty((S * P + 1, 7), dtype=torch.float32, device=device)
-    meta[:S * P, 0] = torch.arange(S, device=device, dtype=torch.float32).repeat_interleave(P)
-    meta[:S * P, 1:] = ext.repeat(S, 1)
-    meta[S * P] = torch.tensor([-1, 0, ps, 0, ps, 0, ps], dtype=torch.float32, device=device)
-    return EmbeddingBank(emb, meta, [f"scene{i:05d}" for i in range(S)]), fenc_target
+    meta = torch.empty((S_tot * P + 1, 7), dtype=torch.float32, device=device)
+    meta[:S_tot * P, 0] = torch.arange(S_tot, device=device, dtype=torch.float32).repeat_interleave(P)
+    meta[:S_tot * P, 1:] = ext.repeat(S_tot, 1)
+    meta[S_tot * P] = torch.tensor([-1, 0, ps, 0, ps, 0, ps], dtype=torch.float32, device=device)
+    bank = EmbeddingBank(emb, meta, [f"scene{i:05d}" for i in range(S_tot)], row_offset=scene_offset * P,
+                         n_total=S_tot * P + 1)
+    return bank, fenc_target
 
 
 def build_synthetic_world(n_bank_scenes, n_query_chunks, seed, device, config=None):
