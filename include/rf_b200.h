@@ -91,6 +91,17 @@ int rf_upsample_nearest_2(const float* x, float* y, int N, int C, int D, int H, 
 /* F.normalize(x, dim=1) on rows (util/retrieval.py:38,66): y = x / max(||x||_2, eps) */
 int rf_l2_normalize_rows(const float* x, float* y, long M, int D, float eps, void* stream);
 
+/* Tensor-core linear layer (tcgen05, bf16 hi/lo split: Xh.Wh + Xh.Wl + Xl.Wh,
+ * fp32 accumulators in TMEM; ~1e-5 relative accuracy).  The weight
+ * [N, K] (nn.Linear.weight, row-major) is staged once as a pre-split,
+ * pre-swizzled operand image (rf_tc_weight_image, 1024-byte aligned buffer of
+ * rf_tc_weight_image_bytes); then y[M,N] = act(x[M,K] (row stride ldx) @ W^T + bias).
+ * N in {32, 64, 96, 128, 256, 384, 512}; x, y 16-byte aligned, ldx % 4 == 0. */
+size_t rf_tc_weight_image_bytes(int N, int K);
+int rf_tc_weight_image(const float* w, int N, int K, void* image, void* stream);
+int rf_tc_linear_fwd(const float* x, int ldx, const void* weight_image, const float* bias, float* y, long M, int K, int N,
+                     int act, float slope, void* stream);
+
 /* ---- a5 + a9  fused query encoder --------------------------------------- */
 
 /* model/retrieval.py:64-84 Patch04.forward (+Patch05/Patch04V2: any ReLU MLP)

@@ -35,6 +35,10 @@ PROTOTYPES = {
     "rf_maxpool3d_2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "rf_upsample_nearest_2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "rf_l2_normalize_rows": (c_int, [c_void_p, c_void_p, c_long, c_int, c_float, c_void_p]),
+    "rf_tc_weight_image_bytes": (c_size_t, [c_int, c_int]),
+    "rf_tc_weight_image": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "rf_tc_linear_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_float,
+                                 c_void_p]),
     "rf_mlp_encode_workspace_bytes": (c_size_t, [c_long, c_int * 9, c_int]),
     "rf_mlp_encode_fwd": (c_int, [c_void_p, _ptr4, _ptr4, c_int * 9, c_int, c_int, c_void_p, c_long, c_void_p, c_size_t,
                                   c_void_p]),

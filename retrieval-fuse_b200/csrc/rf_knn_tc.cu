@@ -343,7 +343,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
                     // then repeatedly pull the maximum while it beats tau.
                     float key[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) key[j] = __uint_as_float((__float_as_uint(v[j]) & ~31u) | (uint32_t)j);
+                    for (int j = 0; j < 32; ++j)  // masked (padded) columns stay at -FLT_MAX and can never beat tau
+                        key[j] = v[j] == -FLT_MAX ? -FLT_MAX : __uint_as_float((__float_as_uint(v[j]) & ~31u) | (uint32_t)j);
 #pragma unroll 1
                     for (int guard = 0; guard < 32; ++guard) {
                         float km = fmaxf(key[0], key[1]);

@@ -1,0 +1,329 @@
+// Tensor-core linear layer: Y[M,N] = act(X[M,K] @ W[N,K]^T + bias) with fp32
+// inputs/outputs and near-fp32 accuracy from a bf16 hi/lo split
+//   x = x_hi + x_lo + r (|r| <= 2^-18 |x|),  X.W ~= Xh.Wh + Xh.Wl + Xl.Wh
+// evaluated by tcgen05.mma (M128, kind::f16 bf16 inputs, fp32 accumulators in
+// TMEM).  Used for the query encoder MLP (model/retrieval.py:64-84) and the
+// attention feature MLPs (model/attention.py:29-46).
+//
+// CTA = 128 rows x all N (N <= 512 accumulator columns).  K runs in blocks of
+// 64 (one 128-byte swizzle atom of bf16):
+//   warps 4-7  A producers: coalesced fp32 loads of the row block, hi/lo split,
+//              swizzled st.shared into a double-buffered [hi|lo] operand image,
+//              fence.proxy.async, mbarrier arrive; afterwards the same warps run
+//              the epilogue (tcgen05.ld -> bias/activation -> fp32 stores).
+//   warp 0     B producer: one cp.async.bulk per (K block, N tile) of the
+//              pre-split, pre-swizzled weight image (32 KiB for 128 rows).
+//   warp 1     MMA issuer (one thread): 3 products x 4 K-steps per stage.
+//   warp 2     TMEM allocation.
+#include <cuda_bf16.h>
+
+#include "rf_common.cuh"
+
+namespace {
+
+constexpr int TM = 128;               // rows per CTA
+constexpr int KBE = 64;               // K elements per block
+constexpr int IMG = TM * 128;         // bytes of one 128-row x 64-bf16 operand image (16 KiB)
+constexpr int MAX_A_STAGES = 2, MAX_B_STAGES = 3;
+constexpr int NTHREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 26)) {  // a pipeline bug must never hang the GPU
+            printf("rf_tc_linear: mbarrier wait timed out (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+        "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+          "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+          "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+// K-major SWIZZLE_128B operand descriptor (see rf_knn_tc.cu)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16: D f32, A/B bf16, K-major, N >> 3 at bit 17, M = 128 (>> 4) at bit 24
+__device__ __forceinline__ uint32_t idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void split_bf16(float x, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
+}
+
+// W [N, K] fp32 row-major -> image [K/64][N/nt][hi|lo][nt rows][128 B], rows swizzled.
+__global__ void __launch_bounds__(256) tc_weight_image_kernel(const float* __restrict__ w, int N, int K, int Kp, int nt,
+                                                              uint8_t* __restrict__ img) {
+    const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;  // one thread per (row n, 16-byte chunk of 8 k)
+    const int chunks = Kp / 8;
+    if (gid >= (long)N * chunks) return;
+    const int n = (int)(gid / chunks), ck = (int)(gid % chunks);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t h0, l0, h1, l1;
+        const int k0 = ck * 8 + 2 * i;
+        split_bf16(k0 < K ? w[(long)n * K + k0] : 0.f, h0, l0);
+        split_bf16(k0 + 1 < K ? w[(long)n * K + k0 + 1] : 0.f, h1, l1);
+        hi[i] = h0 | (h1 << 16);
+        lo[i] = l0 | (l1 << 16);
+    }
+    const int kb = ck / 8, c = ck % 8;
+    const int tile = n / nt, r = n % nt;
+    const long stage = ((long)kb * (N / nt) + tile) * (2L * nt * 128);
+    uint8_t* base = img + stage + (long)r * 128 + ((c ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + (long)nt * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+struct LinArgs {
+    const float* x;        // [M, K] row-major, leading dimension ldx
+    const uint8_t* wimg;
+    const float* bias;
+    float* y;              // [M, N]
+    long M;
+    int K, Kp, N, nt, ldx, act;
+    float slope;
+    int a_stages, b_stages;  // ring depths: (1, 2) keeps 2 CTAs per SM when N <= 256, (2, 3) otherwise
+};
+
+__global__ void __launch_bounds__(NTHREADS, 2) tc_linear_kernel(const LinArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int A_STAGES = a.a_stages, B_STAGES = a.b_stages;
+    const uint32_t sA = base;                               // A_STAGES x [hi 16K | lo 16K]
+    const uint32_t sB = base + A_STAGES * 2 * IMG;          // B_STAGES x [hi | lo] (2 * nt * 128 B, <= 32 KiB)
+    const uint32_t bars = sB + B_STAGES * 2 * IMG;
+    const uint32_t bar_afull = bars, bar_aempty = bars + 8 * MAX_A_STAGES;
+    const uint32_t bar_bfull = bars + 16 * MAX_A_STAGES, bar_bempty = bar_bfull + 8 * MAX_B_STAGES;
+    const uint32_t bar_dfull = bar_bempty + 8 * MAX_B_STAGES;
+    const uint32_t tmem_slot = bar_dfull + 8;
+    uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long m0 = (long)blockIdx.x * TM;
+    const int n_kb = a.Kp / KBE, n_nt = a.N / a.nt;
+    const uint32_t b_bytes = 2u * (uint32_t)a.nt * 128u;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < a.N) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < A_STAGES; ++s) { mbar_init(bar_afull + 8 * s, 128); mbar_init(bar_aempty + 8 * s, 1); }
+        for (int s = 0; s < B_STAGES; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+        mbar_init(bar_dfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- weight producer
+            int it = 0;
+            for (int kb = 0; kb < n_kb; ++kb)
+                for (int t = 0; t < n_nt; ++t, ++it) {
+                    const int s = it % B_STAGES;
+                    mbar_wait(bar_bempty + 8 * s, ((uint32_t)(it / B_STAGES) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(bar_bfull + 8 * s, b_bytes);
+                    bulk_g2s(sB + s * 2 * IMG, a.wimg + ((long)kb * n_nt + t) * b_bytes, b_bytes, bar_bfull + 8 * s);
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issuer
+            const uint32_t idesc = idesc_bf16(a.nt);
+            int it = 0;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int sa = kb % A_STAGES;
+                mbar_wait(bar_afull + 8 * sa, (uint32_t)(kb / A_STAGES) & 1u);
+                tc_fence_after();
+                const uint32_t a_hi = sA + sa * 2 * IMG, a_lo = a_hi + IMG;
+                for (int t = 0; t < n_nt; ++t, ++it) {
+                    const int s = it % B_STAGES;
+                    mbar_wait(bar_bfull + 8 * s, (uint32_t)(it / B_STAGES) & 1u);
+                    tc_fence_after();
+                    const uint32_t b_hi = sB + s * 2 * IMG, b_lo = b_hi + (uint32_t)a.nt * 128u;
+                    const uint32_t d = tmem_base + (uint32_t)(t * a.nt);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        tc_mma(d, umma_desc(a_hi + k * 32), umma_desc(b_hi + k * 32), idesc, (kb | k) ? 1u : 0u);
+                        tc_mma(d, umma_desc(a_hi + k * 32), umma_desc(b_lo + k * 32), idesc, 1u);
+                        tc_mma(d, umma_desc(a_lo + k * 32), umma_desc(b_hi + k * 32), idesc, 1u);
+                    }
+                    tc_commit(bar_bempty + 8 * s);
+                }
+                tc_commit(bar_aempty + 8 * sa);
+            }
+            tc_commit(bar_dfull);
+        }
+    } else if (warp >= 4) {
+        const int pw = warp - 4;  // rows [32 pw, 32 pw + 32) of the tile; also this warp's TMEM lane quadrant
+        // ---- A producer: two rows per iteration, 16 lanes x float4 = one 64-element row segment
+        for (int kb = 0; kb < n_kb; ++kb) {
+            const int sa = kb % A_STAGES;
+            mbar_wait(bar_aempty + 8 * sa, ((uint32_t)(kb / A_STAGES) & 1u) ^ 1u);
+            uint8_t* img_hi = smem_al + (sA - base) + sa * 2 * IMG;
+            const int f4 = lane & 15;
+            const int kcol = kb * KBE + f4 * 4;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int r = pw * 32 + i * 2 + (lane >> 4);
+                const long row = m0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < a.M) {
+                    const float* src = a.x + row * a.ldx + kcol;
+                    if (kcol + 3 < a.K) v = __ldg(reinterpret_cast<const float4*>(src));
+                    else {
+                        if (kcol < a.K) v.x = __ldg(src);
+                        if (kcol + 1 < a.K) v.y = __ldg(src + 1);
+                        if (kcol + 2 < a.K) v.z = __ldg(src + 2);
+                    }
+                }
+                uint32_t h0, l0, h1, l1, h2, l2, h3, l3;
+                split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+                const uint32_t off = (uint32_t)r * 128u + ((uint32_t)((f4 >> 1) ^ (r & 7)) << 4) + (uint32_t)(f4 & 1) * 8u;
+                *reinterpret_cast<uint2*>(img_hi + off) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+                *reinterpret_cast<uint2*>(img_hi + IMG + off) = make_uint2(l0 | (l1 << 16), l2 | (l3 << 16));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
+            mbar_arrive(bar_afull + 8 * sa);
+        }
+        // ---- epilogue: thread <-> output row
+        mbar_wait(bar_dfull, 0);
+        tc_fence_after();
+        const long row = m0 + pw * 32 + lane;
+        for (int c0 = 0; c0 < a.N; c0 += 32) {
+            float v[32];
+            tc_ld32(tmem_base + ((uint32_t)(pw * 32) << 16) + (uint32_t)c0, v);
+            if (row < a.M) {
+                float* dst = a.y + row * a.N + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    o.x = rf_act(v[j] + (a.bias ? __ldg(a.bias + c0 + j) : 0.f), a.act, a.slope);
+                    o.y = rf_act(v[j + 1] + (a.bias ? __ldg(a.bias + c0 + j + 1) : 0.f), a.act, a.slope);
+                    o.z = rf_act(v[j + 2] + (a.bias ? __ldg(a.bias + c0 + j + 2) : 0.f), a.act, a.slope);
+                    o.w = rf_act(v[j + 3] + (a.bias ? __ldg(a.bias + c0 + j + 3) : 0.f), a.act, a.slope);
+                    *reinterpret_cast<float4*>(dst + j) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+constexpr int lin_smem(int a_stages, int b_stages) { return 1024 + (a_stages + b_stages) * 2 * IMG + 256; }
+
+int pick_nt(int N) { return N >= 128 ? 128 : N; }
+bool tc_shape_ok(int K, int N) {
+    if (N < 32 || N > 512 || K < 1 || K > 4096) return false;
+    const int nt = pick_nt(N);
+    return N % nt == 0 && nt % 16 == 0 && N % 32 == 0;
+}
+
+}  // namespace
+
+extern "C" size_t rf_tc_weight_image_bytes(int N, int K) {
+    if (!tc_shape_ok(K, N)) return 0;
+    const int Kp = (K + KBE - 1) / KBE * KBE;
+    return (size_t)(Kp / KBE) * N * 128 * 2;
+}
+
+extern "C" int rf_tc_weight_image(const float* w, int N, int K, void* image, void* stream) {
+    RF_CHECK_ARG(w && image, "rf_tc_weight_image: null pointer");
+    RF_CHECK_ARG(tc_shape_ok(K, N), "rf_tc_weight_image: unsupported shape N=%d K=%d (N in {32,64,96,128,256,384,512})", N, K);
+    RF_CHECK_ARG(((uintptr_t)image & 1023) == 0, "rf_tc_weight_image: image must be 1024-byte aligned");
+    const int Kp = (K + KBE - 1) / KBE * KBE;
+    const long threads = (long)N * (Kp / 8);
+    tc_weight_image_kernel<<<(unsigned)rf_cdivl(threads, 256), 256, 0, (cudaStream_t)stream>>>(w, N, K, Kp, pick_nt(N), (uint8_t*)image);
+    RF_LAUNCH_OK("tc_weight_image_kernel");
+    return 0;
+}
+
+extern "C" int rf_tc_linear_fwd(const float* x, int ldx, const void* weight_image, const float* bias, float* y, long M, int K,
+                                int N, int act, float slope, void* stream) {
+    RF_CHECK_ARG(x && weight_image && y, "rf_tc_linear_fwd: null pointer");
+    RF_CHECK_ARG(tc_shape_ok(K, N) && M > 0 && ldx >= K, "rf_tc_linear_fwd: unsupported shape M=%ld K=%d N=%d ldx=%d", M, K, N, ldx);
+    RF_CHECK_ARG(((uintptr_t)x & 15) == 0 && (ldx % 4) == 0 && ((uintptr_t)y & 15) == 0, "rf_tc_linear_fwd: x / y must be 16-byte aligned, ldx % 4 == 0");
+    RF_CHECK_ARG(((uintptr_t)weight_image & 1023) == 0, "rf_tc_linear_fwd: weight image must be 1024-byte aligned");
+    static bool attr_set = false;
+    if (!attr_set) {
+        RF_CUDA_OK(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        lin_smem(MAX_A_STAGES, MAX_B_STAGES)));
+        attr_set = true;
+    }
+    LinArgs a;
+    a.x = x; a.wimg = (const uint8_t*)weight_image; a.bias = bias; a.y = y; a.M = M; a.K = K;
+    a.Kp = (K + KBE - 1) / KBE * KBE; a.N = N; a.nt = pick_nt(N); a.ldx = ldx; a.act = act; a.slope = slope;
+    // N <= 256 accumulator columns: two CTAs fit one SM's TMEM, so keep shared memory under half an SM
+    // (one CTA's operand production / epilogue then overlaps the other's MMAs)
+    a.a_stages = N <= 256 ? 1 : MAX_A_STAGES;
+    a.b_stages = N <= 256 ? 2 : MAX_B_STAGES;
+    tc_linear_kernel<<<(unsigned)rf_cdivl(M, TM), NTHREADS, lin_smem(a.a_stages, a.b_stages), (cudaStream_t)stream>>>(a);
+    RF_LAUNCH_OK("tc_linear_kernel");
+    return 0;
+}

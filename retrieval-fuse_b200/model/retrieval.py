@@ -91,12 +91,20 @@ class _MlpPatchEncoder(RfModule):
     def forward(self, x):
         return self.encode(x, l2_normalize=False)
 
+    use_tensor_cores = True  # tcgen05 bf16-split GEMMs (~1e-5 relative); False -> fp32 FMA kernels
+
     def encode(self, x, l2_normalize):
         """forward (+ optionally util/retrieval.py:66 row normalisation fused)."""
         ops._forward_only(x, *self.parameters())
         lin = self._linears()
         h = x.reshape(x.shape[0], -1)
-        z = ops.mlp_encode(h, [self._wt(m.weight) for m in lin], [m.bias for m in lin], l2_normalize=l2_normalize)
+        if self.use_tensor_cores and h.shape[0] >= 128 and all(ops.tc_supported(*m.weight.shape) for m in lin):
+            for j, m in enumerate(lin):
+                img = self._wcache.derived(("tcimg", j), [m.weight], ops.tc_weight_image)
+                h = ops.tc_linear(h, img, m.bias, m.out_features, act=ops.ACT_RELU if j < len(lin) - 1 else ops.ACT_NONE)
+            z = ops.l2_normalize_rows(h) if l2_normalize else h
+        else:
+            z = ops.mlp_encode(h, [self._wt(m.weight) for m in lin], [m.bias for m in lin], l2_normalize=l2_normalize)
         return z.reshape(z.shape[0], z.shape[1], 1, 1, 1)
 
 

@@ -175,6 +175,40 @@ def linear(x, wt, bias=None, act=ACT_NONE, slope=0.0):
     return y
 
 
+def tc_supported(N, K):
+    """True when the tensor-core linear kernel handles an [N, K] weight."""
+    return _lib.lib().rf_tc_weight_image_bytes(int(N), int(K)) > 0 and K % 4 == 0
+
+
+def tc_weight_image(weight):
+    """nn.Linear.weight [N, K] -> the pre-split, pre-swizzled bf16 operand image (uint8 tensor view, 1024-aligned)."""
+    weight = _dev(weight.detach(), name="weight")
+    N, K = weight.shape
+    L = _lib.lib()
+    nbytes = L.rf_tc_weight_image_bytes(N, K)
+    if nbytes == 0:
+        raise _lib.RfError(f"tensor-core linear does not support a weight of shape {(N, K)}")
+    buf = torch.empty(nbytes + 1024, device=weight.device, dtype=torch.uint8)
+    off = (-buf.data_ptr()) % 1024
+    img = buf[off: off + nbytes]
+    with torch.cuda.device(weight.device):
+        check(L.rf_tc_weight_image(weight.data_ptr(), N, K, img.data_ptr(), _stream(weight)), "rf_tc_weight_image")
+    _count()
+    return img
+
+
+def tc_linear(x, weight_image, bias, N, act=ACT_NONE, slope=0.0):
+    """y = act(x @ W^T + bias) on the tensor cores (bf16 hi/lo split, fp32 accumulate)."""
+    x = _dev(x, name="x")
+    M, K = x.shape
+    y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_tc_linear_fwd(x.data_ptr(), K, weight_image.data_ptr(), _ptr(bias), y.data_ptr(), M, K, N, act,
+                                          float(slope), _stream(x)), "rf_tc_linear_fwd")
+    _count()
+    return y
+
+
 def groupnorm_stats(x, gamma, groups, eps=1e-5, x2=None):
     """Returns (gn_mu [N,C], gn_a [N,C]) for the virtual input concat(x, up2(x2))."""
     ref = x if x is not None else x2

@@ -128,6 +128,26 @@ def test_encoders(dev, cls, nf, n):
     close(y.reshape(n, 64), O.encoder_forward(cls, sd, x).reshape(n, 64), what=f"{cls} vs oracle")
 
 
+@pytest.mark.parametrize("M,K,N,act", [(300, 64, 128, 1), (1000, 128, 256, 1), (257, 256, 512, 0), (128, 512, 256, 2),
+                                       (4097, 256, 64, 0), (513, 96, 128, 2), (200, 128, 32, 0)])
+def test_tc_linear(dev, M, K, N, act):
+    """tcgen05 bf16-split linear layer against an fp64 evaluation: error ~1e-5 of the row's |x||w| scale."""
+    from retrieval_fuse_b200 import ops
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.1
+    img = ops.tc_weight_image(w.to(dev))
+    y = ops.tc_linear(x.to(dev), img, b.to(dev), N, act=act, slope=0.2)
+    ref = x.double() @ w.double().t() + b.double()
+    ref = torch.relu(ref) if act == 1 else (torch.nn.functional.leaky_relu(ref, 0.2) if act == 2 else ref)
+    scale = (x.double().norm(dim=1, keepdim=True) * w.double().norm(dim=1)[None]).clamp_min(1.0)
+    err = ((y.cpu().double() - ref).abs() / scale).max().item()
+    assert err <= 2e-5, f"relative error {err:.2e}"
+    y32 = ops.linear(x.to(dev), w.t().contiguous().to(dev), b.to(dev), act=act, slope=0.2)
+    assert (y - y32).abs().max().item() <= 1e-4 * max(1.0, float(ref.abs().max()))
+
+
 def test_encoder_batch_and_normalise(dev):
     """64 patches x several chunks through Patch04 + F.normalize (util/retrieval.py:66)."""
     from retrieval_fuse_b200.model import retrieval as R
@@ -136,7 +156,9 @@ def test_encoder_batch_and_normalise(dev):
     x = torch.randn(64 * 5 + 3, 1, 4, 4, 4, generator=torch.Generator().manual_seed(5))
     got = _encode_normalized(m, x.to(dev), 64)
     want = O.normalize_features(O.encoder_forward("Patch04", sd, x), 64)
-    close(got, want, tol=1e-5, what="Patch04 + normalise")
+    close(got, want, tol=2e-5, what="Patch04 + normalise (tensor-core path)")
+    m.use_tensor_cores = False
+    close(_encode_normalized(m, x.to(dev), 64), want, tol=1e-5, what="Patch04 + normalise (fp32 path)")
     m8, sd8 = load(R.Patch08(16, 64), O.encoder_param_shapes("Patch08", 16, 64), dev)
     x8 = torch.randn(70, 1, 8, 8, 8, generator=torch.Generator().manual_seed(6))
     close(_encode_normalized(m8, x8.to(dev), 64), O.normalize_features(O.encoder_forward("Patch08", sd8, x8), 64), tol=1e-5,
