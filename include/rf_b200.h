@@ -91,8 +91,8 @@ int rf_upsample_nearest_2(const float* x, float* y, int N, int C, int D, int H, 
 /* F.normalize(x, dim=1) on rows (util/retrieval.py:38,66): y = x / max(||x||_2, eps) */
 int rf_l2_normalize_rows(const float* x, float* y, long M, int D, float eps, void* stream);
 
-/* Tensor-core linear layer (tcgen05, bf16 hi/lo split: Xh.Wh + Xh.Wl + Xl.Wh,
- * fp32 accumulators in TMEM; ~1e-5 relative accuracy).  The weight
+/* Tensor-core linear layer (tcgen05, fp16 hi/lo split: Xh.Wh + Xh.Wl + Xl.Wh,
+ * fp32 accumulators in TMEM; ~2e-7 relative accuracy).  The weight
  * [N, K] (nn.Linear.weight, row-major) is staged once as a pre-split,
  * pre-swizzled operand image (rf_tc_weight_image, 1024-byte aligned buffer of
  * rf_tc_weight_image_bytes); then y[M,N] = act(x[M,K] (row stride ldx) @ W^T + bias).
@@ -101,6 +101,31 @@ size_t rf_tc_weight_image_bytes(int N, int K);
 int rf_tc_weight_image(const float* w, int N, int K, void* image, void* stream);
 int rf_tc_linear_fwd(const float* x, int ldx, const void* weight_image, const float* bias, float* y, long M, int K, int N,
                      int act, float slope, void* stream);
+
+/* Tensor-core 3D convolution on channels-last activations (U-Net 'gcr' blocks,
+ * conv patch encoders).  One SingleConv = rf_cl_gn_stats -> rf_cl_norm_split
+ * (normalise once, split to fp16 hi/lo, pad channels to 8) -> rf_tc_conv3d_fwd
+ * (implicit GEMM on tcgen05, three fp16 products per K step, fp32 accumulate).
+ *   fp32 channels-last tensors are [N,D,H,W,C]; split tensors are two fp16
+ *   arrays [N,D,H,W,Cp], Cp = C rounded up to 8.  The optional second source
+ *   (x2, half resolution) is virtually nearest-upsampled and concatenated after
+ *   x's channels (model/unet.py:297-306).  Cout <= 128.
+ *   `scale` arguments are powers of two that move activations / weights into
+ *   fp16's comfortable range before the hi/lo split (so that the lo parts are
+ *   normal numbers); the conv multiplies its accumulator by out_scale =
+ *   1 / (activation scale * weight scale) before bias and activation. */
+size_t rf_cl_gn_stats_workspace_bytes(int N, int C);
+int rf_cl_gn_stats(const float* x, const float* x2, int C2, const float* gamma, float* gn_mu, float* gn_a, int N, int C,
+                   int D, int H, int W, int groups, float eps, void* workspace, void* stream);
+int rf_cl_norm_split(const float* x, const float* gn_mu, const float* gn_a, const float* gn_beta, int c_off, int c_tot,
+                     void* hi, void* lo, long N, long S, int C, int Cp, float scale, void* stream);
+int rf_cl_maxpool3d_2(const float* x, float* y, int N, int D, int H, int W, int C, void* stream);
+int rf_cl_transpose(const float* in, float* out, long N, long S, int C, int to_channels_last, void* stream);
+size_t rf_tc_conv_weight_image_bytes(int Cout, int C1, int C2, int KS);
+int rf_tc_conv_weight_image(const float* w, int Cout, int C1, int C2, int KS, float scale, void* image, void* stream);
+int rf_tc_conv3d_fwd(const void* x_hi, const void* x_lo, int C1, const void* x2_hi, const void* x2_lo, int C2,
+                     const void* weight_image, const float* bias, float* y, int N, int Di, int Hi, int Wi, int Cout, int KS,
+                     int stride, int pad, int act, float slope, float out_scale, int out_ncdhw, void* stream);
 
 /* ---- a5 + a9  fused query encoder --------------------------------------- */
 
@@ -168,12 +193,15 @@ int rf_compose_gather(const float* rows, const int* dst_extents, const float* sc
  * AttentionBlock.forward :84-113 (g = o = Identity, blend or additive).
  *   x_back [B,nf,S,S,S], x_retr [B*K,nf,S,S,S] -> out [B,nf,S,S,S]
  *   theta_wt/phi_wt: 4 transposed Linear weights [in,out] each, *_b biases;
+ *   theta_img/phi_img: NULL, or the 4 rf_tc_weight_image buffers of each MLP -
+ *   then the MLPs run on the tensor cores (rf_tc_linear_fwd) and *_wt is unused;
  *   mode 0: softmax(32*E^3*4 * s); mode 1: hard Gumbel arg-max of 25*s + noise
  *   (noise [B*R^3, K], required); workspace from rf_attention_workspace_bytes. */
 size_t rf_attention_workspace_bytes(int B, int nf, int S, int E, int K);
 int rf_attention_fuse_fwd(const float* x_back, const float* x_retr, const float* const* theta_wt_host,
                           const float* const* theta_b_host, const float* const* phi_wt_host,
-                          const float* const* phi_b_host, const float* gumbel_noise, float* out, int B, int nf, int S,
+                          const float* const* phi_b_host, const void* const* theta_img_host,
+                          const void* const* phi_img_host, const float* gumbel_noise, float* out, int B, int nf, int S,
                           int E, int K, int normalize, int mode, int blend, void* workspace, size_t workspace_bytes,
                           void* stream);
 /* model/attention.py:132-139 get_features: theta(unfold(x)), phi(unfold(t)),
@@ -181,7 +209,8 @@ int rf_attention_fuse_fwd(const float* x_back, const float* x_retr, const float*
  * x_feat,p_feat [B*R^3,32]; occ_any [B*R^3] uint8. */
 int rf_attention_features(const float* x, const float* t, const uint8_t* occ, const float* const* theta_wt_host,
                           const float* const* theta_b_host, const float* const* phi_wt_host,
-                          const float* const* phi_b_host, float* x_feat, float* p_feat, uint8_t* occ_any, int B, int nf,
+                          const float* const* phi_b_host, const void* const* theta_img_host,
+                          const void* const* phi_img_host, float* x_feat, float* p_feat, uint8_t* occ_any, int B, int nf,
                           int S, int E, int normalize, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

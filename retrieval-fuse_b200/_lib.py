@@ -39,6 +39,17 @@ PROTOTYPES = {
     "rf_tc_weight_image": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "rf_tc_linear_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_float,
                                  c_void_p]),
+    "rf_cl_gn_stats_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "rf_cl_gn_stats": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                               c_int, c_float, c_void_p, c_void_p]),
+    "rf_cl_norm_split": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_long, c_long,
+                                 c_int, c_int, c_float, c_void_p]),
+    "rf_cl_maxpool3d_2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "rf_cl_transpose": (c_int, [c_void_p, c_void_p, c_long, c_long, c_int, c_int, c_void_p]),
+    "rf_tc_conv_weight_image_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "rf_tc_conv_weight_image": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "rf_tc_conv3d_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
     "rf_mlp_encode_workspace_bytes": (c_size_t, [c_long, c_int * 9, c_int]),
     "rf_mlp_encode_fwd": (c_int, [c_void_p, _ptr4, _ptr4, c_int * 9, c_int, c_int, c_void_p, c_long, c_void_p, c_size_t,
                                   c_void_p]),
@@ -52,10 +63,10 @@ PROTOTYPES = {
     "rf_compose_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, _int3, _int3,
                                   c_float, c_float, c_float, c_float, c_void_p]),
     "rf_attention_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
-    "rf_attention_fuse_fwd": (c_int, [c_void_p, c_void_p, _ptr4, _ptr4, _ptr4, _ptr4, c_void_p, c_void_p, c_int, c_int,
-                                      c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "rf_attention_features": (c_int, [c_void_p, c_void_p, c_void_p, _ptr4, _ptr4, _ptr4, _ptr4, c_void_p, c_void_p,
-                                      c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "rf_attention_fuse_fwd": (c_int, [c_void_p, c_void_p, _ptr4, _ptr4, _ptr4, _ptr4, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "rf_attention_features": (c_int, [c_void_p, c_void_p, c_void_p, _ptr4, _ptr4, _ptr4, _ptr4, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -135,12 +135,19 @@ size_t attn_ws_layout(int B, int nf, int S, int E, int K, AttnWs* ws, char* base
     return off;
 }
 
-// theta / phi: Linear(V,128) LeakyReLU Linear(128,128) LeakyReLU Linear(128,128) LeakyReLU Linear(128,32)
-int run_mlp(const float* in, long rows, int V, const float* const* wt, const float* const* b, float* ha, float* hb, float* out,
-            void* stream) {
+// theta / phi: Linear(V,128) LeakyReLU Linear(128,128) LeakyReLU Linear(128,128) LeakyReLU Linear(128,32).
+// img != NULL: tcgen05 fp16-split GEMMs (rf_tc_linear_fwd) on pre-staged weight images; else fp32 FMA kernels.
+int run_mlp(const float* in, long rows, int V, const float* const* wt, const float* const* b, const void* const* img,
+            float* ha, float* hb, float* out, void* stream) {
     RF_CHECK_ARG(rows < (1L << 31), "attention: too many rows");
     const float slope = 0.01f;  // nn.LeakyReLU() default
     int rc;
+    if (img) {
+        if ((rc = rf_tc_linear_fwd(in, V, img[0], b[0], ha, rows, V, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;
+        if ((rc = rf_tc_linear_fwd(ha, HIDDEN, img[1], b[1], hb, rows, HIDDEN, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;
+        if ((rc = rf_tc_linear_fwd(hb, HIDDEN, img[2], b[2], ha, rows, HIDDEN, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;
+        return rf_tc_linear_fwd(ha, HIDDEN, img[3], b[3], out, rows, HIDDEN, FEAT, RF_ACT_NONE, 0.f, stream);
+    }
     if ((rc = rf_linear_fwd(in, wt[0], b[0], ha, (int)rows, V, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;
     if ((rc = rf_linear_fwd(ha, wt[1], b[1], hb, (int)rows, HIDDEN, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;
     if ((rc = rf_linear_fwd(hb, wt[2], b[2], ha, (int)rows, HIDDEN, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;
@@ -156,7 +163,8 @@ extern "C" size_t rf_attention_workspace_bytes(int B, int nf, int S, int E, int 
 
 extern "C" int rf_attention_fuse_fwd(const float* x_back, const float* x_retr, const float* const* theta_wt_host,
                                      const float* const* theta_b_host, const float* const* phi_wt_host,
-                                     const float* const* phi_b_host, const float* gumbel_noise, float* out, int B, int nf,
+                                     const float* const* phi_b_host, const void* const* theta_img_host,
+                                     const void* const* phi_img_host, const float* gumbel_noise, float* out, int B, int nf,
                                      int S, int E, int K, int normalize, int mode, int blend, void* workspace,
                                      size_t workspace_bytes, void* stream) {
     RF_CHECK_ARG(x_back && x_retr && out && theta_wt_host && theta_b_host && phi_wt_host && phi_b_host && workspace,
@@ -173,8 +181,8 @@ extern "C" int rf_attention_fuse_fwd(const float* x_back, const float* x_retr, c
     int rc;
     if ((rc = rf_unfold3d(x_back, ws.xu, B, nf, S, E, stream))) return rc;
     if ((rc = rf_unfold3d(x_retr, ws.pu, B * K, nf, S, E, stream))) return rc;
-    if ((rc = run_mlp(ws.xu, R, V, theta_wt_host, theta_b_host, ws.ha, ws.hb, ws.xf, stream))) return rc;
-    if ((rc = run_mlp(ws.pu, R * K, V, phi_wt_host, phi_b_host, ws.ha, ws.hb, ws.pf, stream))) return rc;
+    if ((rc = run_mlp(ws.xu, R, V, theta_wt_host, theta_b_host, theta_img_host, ws.ha, ws.hb, ws.xf, stream))) return rc;
+    if ((rc = run_mlp(ws.pu, R * K, V, phi_wt_host, phi_b_host, phi_img_host, ws.ha, ws.hb, ws.pf, stream))) return rc;
     const float sharp = (float)(FEAT * E * E * E * 4);  // model/attention.py:105
     attention_epilogue_kernel<<<(unsigned)rf_cdivl(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         ws.xf, ws.pf, ws.xu, ws.pu, gumbel_noise, ws.orows, R, rp3, K, V, normalize, mode, blend, sharp);
@@ -184,7 +192,8 @@ extern "C" int rf_attention_fuse_fwd(const float* x_back, const float* x_retr, c
 
 extern "C" int rf_attention_features(const float* x, const float* t, const uint8_t* occ, const float* const* theta_wt_host,
                                      const float* const* theta_b_host, const float* const* phi_wt_host,
-                                     const float* const* phi_b_host, float* x_feat, float* p_feat, uint8_t* occ_any, int B,
+                                     const float* const* phi_b_host, const void* const* theta_img_host,
+                                     const void* const* phi_img_host, float* x_feat, float* p_feat, uint8_t* occ_any, int B,
                                      int nf, int S, int E, int normalize, void* workspace, size_t workspace_bytes,
                                      void* stream) {
     RF_CHECK_ARG(x && t && x_feat && p_feat && theta_wt_host && theta_b_host && phi_wt_host && phi_b_host && workspace,
@@ -199,8 +208,8 @@ extern "C" int rf_attention_features(const float* x, const float* t, const uint8
     int rc;
     if ((rc = rf_unfold3d(x, ws.xu, B, nf, S, E, stream))) return rc;
     if ((rc = rf_unfold3d(t, ws.pu, B, nf, S, E, stream))) return rc;
-    if ((rc = run_mlp(ws.xu, R, V, theta_wt_host, theta_b_host, ws.ha, ws.hb, normalize ? ws.xf : x_feat, stream))) return rc;
-    if ((rc = run_mlp(ws.pu, R, V, phi_wt_host, phi_b_host, ws.ha, ws.hb, normalize ? ws.pf : p_feat, stream))) return rc;
+    if ((rc = run_mlp(ws.xu, R, V, theta_wt_host, theta_b_host, theta_img_host, ws.ha, ws.hb, normalize ? ws.xf : x_feat, stream))) return rc;
+    if ((rc = run_mlp(ws.pu, R, V, phi_wt_host, phi_b_host, phi_img_host, ws.ha, ws.hb, normalize ? ws.pf : p_feat, stream))) return rc;
     if (normalize) {
         if ((rc = rf_l2_normalize_rows(ws.xf, x_feat, R, FEAT, 1e-12f, stream))) return rc;
         if ((rc = rf_l2_normalize_rows(ws.pf, p_feat, R, FEAT, 1e-12f, stream))) return rc;

@@ -49,9 +49,15 @@ class AttentionBlock(RfModule):
         self.use_switching = use_switching
         self.normalize = normalize
 
+    use_tensor_cores = True  # theta / phi MLPs as tcgen05 fp16-split GEMMs; False -> fp32 FMA kernels
+
     def _branch(self, enc):
         lin = enc.linears()
-        return [self._wt(m.weight) for m in lin], [m.bias for m in lin]
+        imgs = None
+        if self.use_tensor_cores and all(ops.tc_supported(*m.weight.shape) for m in lin):
+            tag = "theta" if enc is self.theta else "phi"
+            imgs = [self._wcache.derived((tag, j), [m.weight], ops.tc_weight_image) for j, m in enumerate(lin)]
+        return [self._wt(m.weight) for m in lin], [m.bias for m in lin], imgs
 
     def get_regularization_losses(self):
         return ((self.sig_scale - self.init_scale) ** 2 + (self.sig_shift - self.init_shift) ** 2) if self.use_switching else 0

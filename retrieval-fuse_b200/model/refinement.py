@@ -9,7 +9,16 @@ from .unet import UNet3D, DecoderNoJoining
 
 class _Chain(nn.Module):
     def forward(self, x):
-        for net in self.network:
+        from . import unet as U
+        nets = list(self.network)
+        if U.USE_TENSOR_CORES and x.is_cuda and nets[0].tc_ok(x.shape[1]) and all(
+                n.basic_module.tc_ok(0, n.basic_module.SingleConv1.in_channels) for n in nets[1:]):
+            ops._forward_only(x, *self.parameters())
+            h = nets[0].forward_cl(ops.cl_from_ncdhw(x))          # channels-last all the way through
+            for i, n in enumerate(nets[1:]):
+                h = n.forward_cl(h, out_ncdhw=i == len(nets) - 2)
+            return h
+        for net in nets:
             x = net(x)
         return x
 
@@ -66,8 +75,15 @@ class Superresolution08FinalDecoder(RfModule):
 
     def forward(self, x):
         ops._forward_only(x, *self.parameters())
-        x = self.network[0](x)
+        from . import unet as U
         head = self.network[1]
+        nf = head.in_channels
+        if U.USE_TENSOR_CORES and x.is_cuda and self.network[0].basic_module.tc_ok(0, nf) and ops.tc_conv_supported(1, nf, 0, 1):
+            h = self.network[0].forward_cl(ops.cl_from_ncdhw(x))
+            img, sw = self._wcache.derived("tchead", [head.weight], lambda w: ops.tc_conv_weight_image(w, nf, 0))
+            return ops.tc_conv3d(ops.cl_norm_split(h), None, nf, 0, img, head.bias, 1, 1, act=ops.ACT_TANH, out_ncdhw=True,
+                                 out_scale=1.0 / sw)
+        x = self.network[0](x)
         return ops.conv3d(x, self._wt(head.weight), head.bias, cout=1, ks=1, stride=1, pad=0, act=ops.ACT_TANH)
 
 

@@ -46,10 +46,33 @@ class _ConvPatchEncoder(RfModule):
         self.layers = nn.ModuleList(mods)  # parameter containers; never called
         self.final_layer = nn.Linear(cin, z_dim)
 
+    use_tensor_cores = True  # tcgen05 implicit-GEMM convs on channels-last bf16-split activations
+
+    def _forward_tc(self, x):
+        """Channels-last tensor-core path: split -> tc_conv3d (bias + LeakyReLU fused) per layer."""
+        convs = [m for m in self.layers if isinstance(m, nn.Conv3d)]
+        h = ops.cl_from_ncdhw(x)
+        for li, (conv, (_mult, k, s)) in enumerate(zip(convs, self._spec)):
+            cin = conv.in_channels
+            img, sw = self._wcache.derived(("tcconv", li), [conv.weight], lambda w, c=cin: ops.tc_conv_weight_image(w, c, 0))
+            h = ops.tc_conv3d(ops.cl_norm_split(h), None, cin, 0, img, conv.bias, conv.out_channels, k, stride=s, pad=0,
+                              act=ops.ACT_LEAKY, slope=0.2, out_scale=1.0 / sw)
+        h = h.reshape(h.shape[0], -1)  # spatial extent is 1^3 here
+        fl = self.final_layer
+        if h.shape[0] >= 128 and ops.tc_supported(*fl.weight.shape):
+            z = ops.tc_linear(h, self._wcache.derived("tcfinal", [fl.weight], ops.tc_weight_image), fl.bias, fl.out_features)
+        else:
+            z = ops.linear(h, self._wt(fl.weight), fl.bias)
+        return z.reshape(z.shape[0], z.shape[1], 1, 1, 1)
+
     def forward(self, x):
         ops._forward_only(x, *self.parameters())
         if self._batchnorm and self.training:
             raise NotImplementedError("PatchNorm* encoders run in eval mode only (running statistics)")
+        if (self.use_tensor_cores and not self._batchnorm and x.is_cuda and x.shape[0] >= 8 and
+                all(ops.tc_conv_supported(m.out_channels, m.in_channels, 0, m.kernel_size[0])
+                    for m in self.layers if isinstance(m, nn.Conv3d))):
+            return self._forward_tc(x)
         h = x
         i = 0
         for _mult, k, s in self._spec:
@@ -91,7 +114,7 @@ class _MlpPatchEncoder(RfModule):
     def forward(self, x):
         return self.encode(x, l2_normalize=False)
 
-    use_tensor_cores = True  # tcgen05 bf16-split GEMMs (~1e-5 relative); False -> fp32 FMA kernels
+    use_tensor_cores = True  # tcgen05 fp16-split GEMMs (~2e-7 relative); False -> fp32 FMA kernels
 
     def encode(self, x, l2_normalize):
         """forward (+ optionally util/retrieval.py:66 row normalisation fused)."""

@@ -11,6 +11,11 @@ from .. import ops
 from ._base import RfModule
 
 
+# Tensor-core path: channels-last activations, GroupNorm applied once per element, implicit-GEMM
+# convolutions on tcgen05 with a fp16 hi/lo split (~2e-7 relative per layer).  False: fp32 FMA kernels.
+USE_TENSOR_CORES = True
+
+
 def number_of_features_per_level(init_channel_number, num_levels):
     return [init_channel_number * 2 ** k for k in range(num_levels)]  # model/unet.py:11-12
 
@@ -56,7 +61,40 @@ class SingleConv(RfModule):
                           stride=1, pad=self.padding, act=self.act, slope=0.1, x2=x2, gn=gn)
 
 
-class DoubleConv(nn.Module):
+    def tc_ok(self, c1, c2):
+        return ("g" in self.order and self.order.index("g") < self.order.index("c") and self.kernel_size == 3
+                and self.padding == 1 and ops.tc_conv_supported(self.out_channels, c1, c2, 3))
+
+    def forward_cl(self, x, x2=None, out_ncdhw=False):
+        """Channels-last tensor-core path.  x: fp32 [N,D,H,W,C1] or None; x2: fp32 half-resolution
+        [N,D/2,H/2,W/2,C2] or None (virtually upsampled and concatenated after x)."""
+        g = self.groupnorm
+        c1 = x.shape[-1] if x is not None else 0
+        c2 = x2.shape[-1] if x2 is not None else 0
+        if x is None:  # statistics of an upsampled volume == statistics of the volume
+            mu, a = ops.cl_gn_stats(x2, g.weight, g.num_groups, g.eps)
+        else:
+            mu, a = ops.cl_gn_stats(x, g.weight, g.num_groups, g.eps, x2=x2)
+        sa = ops.ACT_SCALE_GN
+        xs = ops.cl_norm_split(x, (mu, a, g.bias), 0, scale=sa) if x is not None else None
+        x2s = ops.cl_norm_split(x2, (mu, a, g.bias), c1, scale=sa) if x2 is not None else None
+        img, sw = self._wcache.derived(("tcconv", c1, c2), [self.conv.weight], lambda w: ops.tc_conv_weight_image(w, c1, c2))
+        return ops.tc_conv3d(xs, x2s, c1, c2, img, self.conv.bias, self.out_channels, 3, stride=1, pad=1, act=self.act,
+                             slope=0.1, out_ncdhw=out_ncdhw, out_scale=1.0 / (sa * sw))
+
+
+class _TwoConvs(nn.Module):
+    def forward(self, x, x2=None):
+        return self.SingleConv2(self.SingleConv1(x, x2))
+
+    def tc_ok(self, c1, c2):
+        return self.SingleConv1.tc_ok(c1, c2) and self.SingleConv2.tc_ok(self.SingleConv1.out_channels, 0)
+
+    def forward_cl(self, x, x2=None, out_ncdhw=False):
+        return self.SingleConv2.forward_cl(self.SingleConv1.forward_cl(x, x2), None, out_ncdhw)
+
+
+class DoubleConv(_TwoConvs):
     """model/unet.py:103-144."""
 
     def __init__(self, in_channels, out_channels, encoder, kernel_size=3, order="crg", num_groups=8):
@@ -72,11 +110,8 @@ class DoubleConv(nn.Module):
         self.SingleConv1 = SingleConv(c1_in, c1_out, kernel_size, order, num_groups)
         self.SingleConv2 = SingleConv(c2_in, c2_out, kernel_size, order, num_groups)
 
-    def forward(self, x, x2=None):
-        return self.SingleConv2(self.SingleConv1(x, x2))
 
-
-class StepDownDoubleConv(nn.Module):
+class StepDownDoubleConv(_TwoConvs):
     """model/unet.py:147-159."""
 
     def __init__(self, in_channels, out_channels, encoder, kernel_size=3, order="crg", num_groups=8):
@@ -85,9 +120,6 @@ class StepDownDoubleConv(nn.Module):
         mid = (in_channels + out_channels) // 2
         self.SingleConv1 = SingleConv(in_channels, mid, kernel_size, order, num_groups)
         self.SingleConv2 = SingleConv(mid, out_channels, kernel_size, order, num_groups)
-
-    def forward(self, x, x2=None):
-        return self.SingleConv2(self.SingleConv1(x, x2))
 
 
 class Encoder(nn.Module):
@@ -108,6 +140,11 @@ class Encoder(nn.Module):
             x = ops.maxpool3d_2(x)
         return self.basic_module(x)
 
+    def forward_cl(self, x):
+        if self.pooling is not None:
+            x = ops.cl_maxpool3d_2(x)
+        return self.basic_module.forward_cl(x)
+
 
 class Decoder(nn.Module):
     """model/unet.py:256-308 with nearest upsampling + concat joining (the
@@ -126,6 +163,9 @@ class Decoder(nn.Module):
             raise NotImplementedError("encoder features must be exactly 2x the decoder input (even extents)")
         return self.basic_module(encoder_features, x)  # concat(enc, up2(x)) is read in place
 
+    def forward_cl(self, encoder_features, x, out_ncdhw=False):
+        return self.basic_module.forward_cl(encoder_features, x, out_ncdhw)
+
 
 class DecoderNoJoining(Decoder):
     """model/unet.py:311-322: nearest x2 then DoubleConv (no skip connection).
@@ -133,7 +173,12 @@ class DecoderNoJoining(Decoder):
     side effect is not reproduced (it does not influence any output)."""
 
     def forward(self, x):
+        if USE_TENSOR_CORES and x.is_cuda and self.basic_module.tc_ok(0, x.shape[1]):
+            return self.forward_cl(ops.cl_from_ncdhw(x), out_ncdhw=True)
         return self.basic_module(None, x)
+
+    def forward_cl(self, x, out_ncdhw=False):
+        return self.basic_module.forward_cl(None, x, out_ncdhw)
 
 
 class Abstract3DUNet(nn.Module):
@@ -175,8 +220,15 @@ class Abstract3DUNet(nn.Module):
         self.final_conv = nn.Identity()
         self.final_activation = None
 
+    def tc_ok(self, in_channels):
+        """Every SingleConv is a [g]c[r|l] 3x3x3 block the tensor-core kernel supports (Cout <= 128)."""
+        convs = [m for m in self.modules() if isinstance(m, SingleConv)]
+        return all(m.tc_ok(m.in_channels, 0) for m in convs)
+
     def forward(self, x):
         ops._forward_only(x, *self.parameters())
+        if USE_TENSOR_CORES and x.is_cuda and self.tc_ok(x.shape[1]):
+            return self.forward_cl(ops.cl_from_ncdhw(x), out_ncdhw=True)
         feats = []
         for encoder in self.encoders:
             x = encoder(x)
@@ -184,6 +236,22 @@ class Abstract3DUNet(nn.Module):
         feats = feats[1:]
         for decoder, ef in zip(self.decoders, feats):
             x = decoder(ef, x)
+        return x
+
+    def forward_cl(self, x, out_ncdhw=False):
+        """x: fp32 channels-last [N,D,H,W,C]; returns channels-last (or NCDHW when out_ncdhw)."""
+        feats = []
+        for encoder in self.encoders:
+            x = encoder.forward_cl(x)
+            feats.insert(0, x)
+        feats = feats[1:]
+        pairs = list(zip(self.decoders, feats))
+        if not pairs:
+            return ops.cl_to_ncdhw(x) if out_ncdhw else x
+        for i, (decoder, ef) in enumerate(pairs):
+            if tuple(ef.shape[1:4]) != tuple(2 * s for s in x.shape[1:4]):
+                raise NotImplementedError("encoder features must be exactly 2x the decoder input (even extents)")
+            x = decoder.forward_cl(ef, x, out_ncdhw=out_ncdhw and i == len(pairs) - 1)
         return x
 
 

@@ -6,6 +6,8 @@ Every function launches the hand-written sm_100a kernels through ctypes on
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
 from . import _lib
@@ -181,7 +183,7 @@ def tc_supported(N, K):
 
 
 def tc_weight_image(weight):
-    """nn.Linear.weight [N, K] -> the pre-split, pre-swizzled bf16 operand image (uint8 tensor view, 1024-aligned)."""
+    """nn.Linear.weight [N, K] -> the pre-split, pre-swizzled fp16 operand image (uint8 tensor view, 1024-aligned)."""
     weight = _dev(weight.detach(), name="weight")
     N, K = weight.shape
     L = _lib.lib()
@@ -198,13 +200,142 @@ def tc_weight_image(weight):
 
 
 def tc_linear(x, weight_image, bias, N, act=ACT_NONE, slope=0.0):
-    """y = act(x @ W^T + bias) on the tensor cores (bf16 hi/lo split, fp32 accumulate)."""
+    """y = act(x @ W^T + bias) on the tensor cores (fp16 hi/lo split, fp32 accumulate)."""
     x = _dev(x, name="x")
     M, K = x.shape
     y = torch.empty((M, N), device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device):
         check(_lib.lib().rf_tc_linear_fwd(x.data_ptr(), K, weight_image.data_ptr(), _ptr(bias), y.data_ptr(), M, K, N, act,
                                           float(slope), _stream(x)), "rf_tc_linear_fwd")
+    _count()
+    return y
+
+
+# ---- channels-last tensor-core convolution path ------------------------------------------------
+
+def _aligned_bytes(nbytes, device, align=1024):
+    buf = torch.empty(nbytes + align, device=device, dtype=torch.uint8)
+    off = (-buf.data_ptr()) % align
+    return buf[off: off + nbytes]
+
+
+def cl_from_ncdhw(x):
+    """[N,C,D,H,W] fp32 -> channels-last [N,D,H,W,C] (a view when C == 1)."""
+    x = _dev(x, name="x")
+    N, C, D, H, W = x.shape
+    if C == 1:
+        return x.reshape(N, D, H, W, 1)
+    y = torch.empty((N, D, H, W, C), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_cl_transpose(x.data_ptr(), y.data_ptr(), N, D * H * W, C, 1, _stream(x)), "rf_cl_transpose")
+    _count()
+    return y
+
+
+def cl_to_ncdhw(x):
+    x = _dev(x, name="x")
+    N, D, H, W, C = x.shape
+    if C == 1:
+        return x.reshape(N, 1, D, H, W)
+    y = torch.empty((N, C, D, H, W), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_cl_transpose(x.data_ptr(), y.data_ptr(), N, D * H * W, C, 0, _stream(x)), "rf_cl_transpose")
+    _count()
+    return y
+
+
+def cl_gn_stats(x, gamma, groups, eps=1e-5, x2=None):
+    """GroupNorm statistics of the virtual channels-last input concat(x, up2(x2)) -> (mu, a) [N, C]."""
+    x = _dev(x, name="x")
+    N, D, H, W, C1 = x.shape
+    C2 = 0
+    if x2 is not None:
+        x2 = _dev(x2, name="x2")
+        C2 = x2.shape[-1]
+    C = C1 + C2
+    mu = torch.empty((N, C), device=x.device, dtype=torch.float32)
+    a = torch.empty((N, C), device=x.device, dtype=torch.float32)
+    ws = torch.empty((N, C, 2), device=x.device, dtype=torch.float64)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_cl_gn_stats(x.data_ptr(), _ptr(x2), C2, gamma.data_ptr(), mu.data_ptr(), a.data_ptr(), N, C, D, H,
+                                        W, groups, float(eps), ws.data_ptr(), _stream(x)), "rf_cl_gn_stats")
+    _count(3 if x2 is not None else 2)
+    return mu, a
+
+
+ACT_SCALE_GN = 16.0  # GroupNorm-ed activations are O(1): x16 keeps their fp16 lo parts normal, far from overflow
+
+
+def cl_norm_split(x, gn=None, c_off=0, scale=1.0):
+    """fp32 channels-last -> (hi, lo) fp16 [N,D,H,W,Cp] of scale * value; gn = (mu, a, beta) applies the
+    GroupNorm affine with this tensor's channels starting at c_off of the statistics."""
+    x = _dev(x, name="x")
+    N, D, H, W, C = x.shape
+    Cp = (C + 7) // 8 * 8
+    hi = torch.empty((N, D, H, W, Cp), device=x.device, dtype=torch.int16)
+    lo = torch.empty((N, D, H, W, Cp), device=x.device, dtype=torch.int16)
+    mu, a, beta = gn if gn is not None else (None, None, None)
+    c_tot = mu.shape[1] if mu is not None else C
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_cl_norm_split(x.data_ptr(), _ptr(mu), _ptr(a), _ptr(beta), c_off, c_tot, hi.data_ptr(),
+                                          lo.data_ptr(), N, D * H * W, C, Cp, float(scale), _stream(x)), "rf_cl_norm_split")
+    _count()
+    return hi, lo
+
+
+def cl_maxpool3d_2(x):
+    x = _dev(x, name="x")
+    N, D, H, W, C = x.shape
+    y = torch.empty((N, D // 2, H // 2, W // 2, C), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_cl_maxpool3d_2(x.data_ptr(), y.data_ptr(), N, D, H, W, C, _stream(x)), "rf_cl_maxpool3d_2")
+    _count()
+    return y
+
+
+def tc_conv_supported(cout, c1, c2, ks):
+    return _lib.lib().rf_tc_conv_weight_image_bytes(int(cout), int(c1), int(c2), int(ks)) > 0
+
+
+def tc_conv_weight_image(weight, c1, c2):
+    """Conv3d weight [Cout, C1+C2, k,k,k] -> (pre-split, pre-swizzled fp16 operand image, weight scale).
+    The scale is the power of two that brings max|w| into [16, 32)."""
+    weight = _dev(weight.detach(), name="weight")
+    wmax = float(weight.abs().max())
+    scale = 2.0 ** (4 - math.floor(math.log2(wmax))) if wmax > 0 and math.isfinite(wmax) else 1.0
+    scale = min(max(scale, 2.0 ** -8), 2.0 ** 24)
+    cout, cin, ks = weight.shape[0], weight.shape[1], weight.shape[2]
+    assert cin == c1 + c2
+    L = _lib.lib()
+    nbytes = L.rf_tc_conv_weight_image_bytes(cout, c1, c2, ks)
+    if nbytes == 0:
+        raise _lib.RfError(f"tensor-core conv does not support weight {tuple(weight.shape)}")
+    img = _aligned_bytes(nbytes, weight.device)
+    with torch.cuda.device(weight.device):
+        check(L.rf_tc_conv_weight_image(weight.data_ptr(), cout, c1, c2, ks, scale, img.data_ptr(), _stream(weight)),
+              "rf_tc_conv_weight_image")
+    _count()
+    return img, scale
+
+
+def tc_conv3d(xs, x2s, c1, c2, img, bias, cout, ks, stride=1, pad=0, act=ACT_NONE, slope=0.0, out_ncdhw=False,
+              out_scale=1.0):
+    """xs / x2s: (hi, lo) split tensors or None; img: operand image; out_scale = 1 / (activation scale x
+    weight scale).  Returns fp32 channels-last [N,Do,Ho,Wo,Cout] or NCDHW."""
+    if xs is not None:
+        N, D, H, W = xs[0].shape[:4]
+    else:
+        N, D, H, W = x2s[0].shape[0], 2 * x2s[0].shape[1], 2 * x2s[0].shape[2], 2 * x2s[0].shape[3]
+    dev = (xs or x2s)[0].device
+    Do, Ho, Wo = [(v + 2 * pad - ks) // stride + 1 for v in (D, H, W)]
+    shape = (N, cout, Do, Ho, Wo) if out_ncdhw else (N, Do, Ho, Wo, cout)
+    y = torch.empty(shape, device=dev, dtype=torch.float32)
+    xh, xl = (xs[0].data_ptr(), xs[1].data_ptr()) if xs is not None else (None, None)
+    x2h, x2l = (x2s[0].data_ptr(), x2s[1].data_ptr()) if x2s is not None else (None, None)
+    with torch.cuda.device(dev):
+        check(_lib.lib().rf_tc_conv3d_fwd(xh, xl, c1, x2h, x2l, c2, img.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W, cout,
+                                          ks, stride, pad, act, float(slope), float(out_scale), int(bool(out_ncdhw)),
+                                          torch.cuda.current_stream(dev).cuda_stream), "rf_tc_conv3d_fwd")
     _count()
     return y
 
@@ -376,8 +507,15 @@ def compose_gather(rows, dst_extents, scene_store, n_chunks, chunk_size, trunc, 
 # attention
 # ---------------------------------------------------------------------------
 
+def _img_array(branch):
+    """branch = (wts, biases[, images]); returns the ctypes pointer array of the images or None."""
+    if len(branch) < 3 or branch[2] is None:
+        return None
+    return ptr_array([im.data_ptr() for im in branch[2]])
+
+
 def attention_fuse(x_back, x_retr, theta, phi, E, K, normalize=True, mode=0, blend=True, gumbel_noise=None):
-    """model/attention.py:141-157. theta/phi: (list of 4 wt [in,out], list of 4 biases)."""
+    """model/attention.py:141-157. theta/phi: (4 wt [in,out], 4 biases[, 4 tensor-core weight images])."""
     _forward_only(x_back, x_retr)
     x_back = _dev(x_back, name="x_predicted")
     x_retr = _dev(x_retr, name="x_retrieved")
@@ -394,8 +532,8 @@ def attention_fuse(x_back, x_retr, theta, phi, E, K, normalize=True, mode=0, ble
                                       ptr_array([w.data_ptr() for w in theta[0]]),
                                       ptr_array([b.data_ptr() for b in theta[1]]),
                                       ptr_array([w.data_ptr() for w in phi[0]]),
-                                      ptr_array([b.data_ptr() for b in phi[1]]), _ptr(gumbel_noise), out.data_ptr(), B,
-                                      nf, S, E, K, int(bool(normalize)), int(mode), int(bool(blend)), ws.data_ptr(),
+                                      ptr_array([b.data_ptr() for b in phi[1]]), _img_array(theta), _img_array(phi),
+                                      _ptr(gumbel_noise), out.data_ptr(), B, nf, S, E, K, int(bool(normalize)), int(mode), int(bool(blend)), ws.data_ptr(),
                                       ws_bytes, _stream(x_back)), "rf_attention_fuse_fwd")
     _count(12)
     return out
@@ -421,8 +559,8 @@ def attention_features(x, t, occ, theta, phi, E, normalize=True):
                                       ptr_array([w.data_ptr() for w in theta[0]]),
                                       ptr_array([b.data_ptr() for b in theta[1]]),
                                       ptr_array([w.data_ptr() for w in phi[0]]),
-                                      ptr_array([b.data_ptr() for b in phi[1]]), xf.data_ptr(), pf.data_ptr(),
-                                      oa.data_ptr(), B, nf, S, E, int(bool(normalize)), ws.data_ptr(), ws_bytes,
+                                      ptr_array([b.data_ptr() for b in phi[1]]), _img_array(theta), _img_array(phi),
+                                      xf.data_ptr(), pf.data_ptr(), oa.data_ptr(), B, nf, S, E, int(bool(normalize)), ws.data_ptr(), ws_bytes,
                                       _stream(x)), "rf_attention_features")
     _count(13)
     return xf, pf, oa.bool()

@@ -131,7 +131,7 @@ def test_encoders(dev, cls, nf, n):
 @pytest.mark.parametrize("M,K,N,act", [(300, 64, 128, 1), (1000, 128, 256, 1), (257, 256, 512, 0), (128, 512, 256, 2),
                                        (4097, 256, 64, 0), (513, 96, 128, 2), (200, 128, 32, 0)])
 def test_tc_linear(dev, M, K, N, act):
-    """tcgen05 bf16-split linear layer against an fp64 evaluation: error ~1e-5 of the row's |x||w| scale."""
+    """tcgen05 fp16-split linear layer against an fp64 evaluation: error <= 2e-6 of the row's |x||w| scale."""
     from retrieval_fuse_b200 import ops
     g = torch.Generator().manual_seed(M + K + N)
     x = torch.randn(M, K, generator=g)
@@ -143,9 +143,24 @@ def test_tc_linear(dev, M, K, N, act):
     ref = torch.relu(ref) if act == 1 else (torch.nn.functional.leaky_relu(ref, 0.2) if act == 2 else ref)
     scale = (x.double().norm(dim=1, keepdim=True) * w.double().norm(dim=1)[None]).clamp_min(1.0)
     err = ((y.cpu().double() - ref).abs() / scale).max().item()
-    assert err <= 2e-5, f"relative error {err:.2e}"
+    assert err <= 2e-6, f"relative error {err:.2e}"
     y32 = ops.linear(x.to(dev), w.t().contiguous().to(dev), b.to(dev), act=act, slope=0.2)
     assert (y - y32).abs().max().item() <= 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("cls,nf,n", [("Patch32", 8, 40), ("Patch08", 16, 300), ("Patch24", 12, 17), ("PCPatch48", 10, 9)])
+def test_conv_encoders_tensor_core_path(dev, cls, nf, n):
+    """Batches large enough for the tcgen05 implicit-GEMM path, against the oracle and the fp32 FMA path."""
+    from retrieval_fuse_b200.model import retrieval as R
+    m, sd = load(getattr(R, cls)(nf, 64), O.encoder_param_shapes(cls, nf, 64), dev)
+    P = O.ENCODER_SPECS[cls]["patch"]
+    x = torch.randn(n, 1, P, P, P, generator=torch.Generator().manual_seed(n))
+    x[0] = 1.0
+    want = O.encoder_forward(cls, sd, x).reshape(n, 64)
+    got = m(x.to(dev)).reshape(n, 64)
+    close(got, want, rel_to_max=True, what=f"{cls} tensor-core path vs oracle")
+    m.use_tensor_cores = False
+    close(m(x.to(dev)).reshape(n, 64), want, rel_to_max=True, what=f"{cls} fp32 path vs oracle")
 
 
 def test_encoder_batch_and_normalise(dev):
@@ -252,14 +267,27 @@ def test_refine_full_forward(dev):
     # TSDF units (network_pred_to_df, trunc = float16(3 * 0.054167)): 1e-4 absolute
     trunc = O.f16_trunc(C.SR_3DFRONT["voxel_size_target"])
     df_err = close(pipe.pred_to_df(pred), O.network_pred_to_df(torch.from_numpy(g["pred"]), trunc), what="TSDF (df units)")
-    # tanh domain: as close to the fp64 truth as the reference's own fp32 arithmetic
+    # tanh domain: the random-weight network amplifies fp32 rounding ~1000x (the reference's own fp32
+    # result is 2.9e-4 away from an fp64 evaluation), so "parity" is measured against that noise floor:
+    # the fp32 FMA path must stay within 2x of it, the tensor-core (fp16 hi/lo split) path within 4x.
     cfg = dict(kind="sr08", nf=16, unet_num_level=4, retrieval_fmaps=16, retrieval_num_level=4, K=4, E=2)
     sd64 = {k: {n: v.double() for n, v in d.items()} for k, d in sds.items()}
     p64 = O.refine_forward(x_in.double(), x_re.double(), sd64, cfg)[0]
     ref_noise = float((torch.from_numpy(g["pred"]).double() - p64).abs().max())
     ours = float((pred.cpu().double() - p64).abs().max())
-    assert ours <= 2 * ref_noise + 1e-5, f"|ours-fp64| {ours:.3e} vs reference's fp32 noise {ref_noise:.3e}"
-    print(f"refine_full: df err {df_err:.2e}, tanh-domain |ours-fp64| {ours:.2e}, reference fp32 noise {ref_noise:.2e}")
+    assert ours <= 4 * ref_noise + 1e-5, f"|ours-fp64| {ours:.3e} vs reference's fp32 noise {ref_noise:.3e}"
+    from retrieval_fuse_b200.model import unet as U
+    U.USE_TENSOR_CORES = False
+    pipe.patched_attention_block.attention_blocks_layer.use_tensor_cores = False
+    try:
+        pred32 = pipe.refine(x_in.to(dev), x_re.to(dev))[0]
+    finally:
+        U.USE_TENSOR_CORES = True
+        pipe.patched_attention_block.attention_blocks_layer.use_tensor_cores = True
+    ours32 = float((pred32.cpu().double() - p64).abs().max())
+    assert ours32 <= 2 * ref_noise + 1e-5, f"fp32 path |ours-fp64| {ours32:.3e} vs reference's fp32 noise {ref_noise:.3e}"
+    close(pipe.pred_to_df(pred32), O.network_pred_to_df(torch.from_numpy(g["pred"]), trunc), what="TSDF (df units), fp32 path")
+    print(f"refine_full: df err {df_err:.2e}, tanh-domain |ours-fp64| tc {ours:.2e} / fp32 {ours32:.2e}, reference fp32 noise {ref_noise:.2e}")
 
 
 # --------------------------------------------------------------------------- a10-a12
