@@ -53,6 +53,7 @@ def parse():
                     help="encoded: Patch32 embeddings of synthetic 64^3 targets (the workload); random: unit Gaussian "
                          "bank AND queries (profiling aid, BASELINE config 5 style)")
     ap.add_argument("--refine-batch", type=int, default=8)
+    ap.add_argument("--no-cuda-graph", action="store_true", help="refine workload: launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample-chunks", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -222,6 +223,8 @@ def run_ours(args, rank, local, world):
     dev = torch.device("cuda", local)
     torch.set_grad_enabled(False)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     peaks = {}
     try:
@@ -288,6 +291,16 @@ def run_ours(args, rank, local, world):
 
         h2d = chunks_host.numel() * 4
         d2h = Q * cfg["K"] * 8 * 4
+        # the same workload with the bank REPLICATED on every rank (33.5 MB): no data-path collective at all
+        pipe_repl = None
+        if world > 1:
+            parts = [torch.empty((min((r + 1) * per, S_tot) - min(r * per, S_tot)) * 64 + (1 if min((r + 1) * per, S_tot) == S_tot else 0),
+                                 64, device=dev) for r in range(world)]
+            dist.all_gather(parts, bank.emb)
+            from retrieval_fuse_b200.util.retrieval import EmbeddingBank
+            full = EmbeddingBank(torch.cat(parts), bank.meta, bank.scenes)
+            pipe_repl = RetrievalPipeline(cfg, full, device=dev, fenc_input=pipe.fenc_input)
+            del parts
         workload = f"ShapeNetV2 SR retrieval_008_064: Patch04 encode + exact kNN (fetch 8, demote, keep 4), {B} chunks x 64 queries vs {n_rows} rows"
         config = {"workload": workload, "chunks_per_step_per_gpu": B, "bank_rows": n_rows, "K": cfg["K"],
                   "bank": "sharded by rows" if world > 1 else "single GPU", "l2": "flushed between timed steps (256 MiB write)",
@@ -306,16 +319,28 @@ def run_ours(args, rank, local, world):
         out_host = torch.empty((B, 1, 64, 64, 64), dtype=torch.float32).pin_memory()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
+        use_graph = not args.no_cuda_graph
+        if use_graph:
+            try:
+                pipe.refine_graphed(x_in, retr)
+            except Exception as e:  # same kernels either way; say so instead of failing the measurement
+                log(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); launching eagerly")
+                use_graph = False
+        fwd = (lambda a, b: pipe.refine_graphed(a, b)) if use_graph else (lambda a, b: pipe.refine(a, b)[0])
+        ops.reset_launches()
+        pipe.refine(x_in, retr)
+        launches_per_forward = ops.launches()
+
         def step(timed):
             if timed:
                 ev[0].record(); ev[1].record()
-            pred = pipe.refine(x_in, retr)[0]
+            pred = fwd(x_in, retr)
             if timed:
                 ev[2].record()
             return pred
 
         def e2e_step():
-            p = pipe.refine(x_in_host.to(dev, non_blocking=True), retr_host.to(dev, non_blocking=True))[0]
+            p = fwd(x_in_host.to(dev, non_blocking=True), retr_host.to(dev, non_blocking=True))
             out_host.copy_(p, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
             return out_host
@@ -323,7 +348,8 @@ def run_ours(args, rank, local, world):
         h2d = (x_in.numel() + retr.numel()) * 4
         d2h = out_host.numel() * 4
         config = {"workload": f"3DFront SR 008->064 refine forward, batch {B}, K=4 (unet + retrieval unet + attention + decoder)",
-                  "chunks_per_step_per_gpu": B, "l2": "flushed between timed steps (256 MiB write)"}
+                  "chunks_per_step_per_gpu": B, "l2": "flushed between timed steps (256 MiB write)",
+                  "launch": "CUDA graph replay" if use_graph else "eager", "kernels_per_forward": launches_per_forward}
         algo_flops = 87.4e9 * B
         units_per_step = B
 
@@ -339,7 +365,8 @@ def run_ours(args, rank, local, world):
     ops.reset_launches()
     barrier()
     wall0 = time.perf_counter()
-    t_step, t_enc, t_knn = [], [], []
+    t_step, t_enc, t_knn, t_cand = [], [], [], []
+    from retrieval_fuse_b200 import _lib as rf_lib
     ev_end = torch.cuda.Event(enable_timing=True)
     for _ in range(args.steps):
         flush_buf.fill_(1)
@@ -349,9 +376,12 @@ def run_ours(args, rank, local, world):
         t_step.append(ev[0].elapsed_time(ev_end))
         t_enc.append(ev[0].elapsed_time(ev[1]))
         t_knn.append(ev[1].elapsed_time(ev[2]))
+        t_cand.append(float(rf_lib.lib().rf_knn_last_candidates_ms()))  # CUDA-event time of the tcgen05 candidates kernel
     barrier()
     wall = time.perf_counter() - wall0
     launches = ops.launches()
+    if args.workload == "refine" and launches == 0:  # graph replays bypass the Python-side counter
+        launches = launches_per_forward * args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     dev_ms = torch.tensor([sum(t_step)], dtype=torch.float64, device=dev)
@@ -373,24 +403,61 @@ def run_ours(args, rank, local, world):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = units_per_step * world * args.steps / float(e2e_s.item())
 
+    replicated = None
+    if args.workload == "retrieval" and world > 1 and pipe_repl is not None:
+        for _ in range(2):
+            pipe_repl.retrieve(chunks, None, args.knn_method)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for _ in range(args.steps):
+            flush_buf.fill_(1)
+            e0.record()
+            pipe_repl.retrieve(chunks, None, args.knn_method)
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([tot], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        replicated = {"value": units_per_step * world * args.steps / (float(t.item()) / 1e3), "unit": UNIT,
+                      "ms_per_step": float(t.item()) / args.steps,
+                      "note": "bank replicated on every rank, queries data parallel, no collective on the data path"}
+
     if rank == 0:
         knn_ms = float(np.mean(t_knn))
         peak = peaks.get("bf16_tflops_sustained") or 1400.0
-        roof = {"bound": "tensor", "kernel": "kNN distance + top-k (rf_knn_l2_topk)" if args.workload == "retrieval" else "refine forward (all kernels)",
-                "achieved": algo_flops / (knn_ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                "frac": algo_flops / (knn_ms / 1e3) / 1e12 / peak, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
-                "avg_launch_ms": knn_ms, "algorithmic_flops_per_launch": algo_flops,
-                "hbm_view": {"algorithmic_bytes": (bank.emb.numel() * 4 + Q * world * 256 + Q * world * 8 * 12) if args.workload == "retrieval" else None,
-                             "peak_gbs": peaks.get("hbm_gbs")}}
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)"
+        if args.workload == "retrieval":
+            cand_ms = float(np.mean(t_cand)) if t_cand and min(t_cand) > 0 else None
+            k_ms = cand_ms if cand_ms else knn_ms
+            # dram bytes per launch of knn_tc_candidates_kernel<1> from the ncu --set full capture of this workload
+            # (profiles/r01_knn_tc_candidates_fp16_full.txt: 99.6 MB read + 47.1 MB write); null for other shapes
+            traffic = 146.7e6 if (cand_ms and world == 1 and B == 10000 and n_rows == 131073 and args.bank == "encoded") else None
+            roof = {"bound": "tensor", "kernel": "knn_tc_candidates_kernel (tcgen05 score GEMM + running top-16)" if cand_ms
+                    else "rf_knn_l2_topk (whole call)",
+                    "achieved": algo_flops / (k_ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                    "frac": algo_flops / (k_ms / 1e3) / 1e12 / peak, "traffic": traffic, "peak_source": peak_src,
+                    "avg_launch_ms": k_ms, "algorithmic_flops_per_launch": algo_flops,
+                    "note": "algorithmic flops = 2*Q*N*64 (one fp16 pass here; the epilogue must read every one of the Q*N "
+                            "fp32 scores from TMEM, 16 per clock per SM, which bounds this K=64 GEMM below the MMA rate)",
+                    "hbm_view": {"algorithmic_bytes": bank.emb.numel() * 4 + Q * world * 256 + Q * world * 8 * 12,
+                                 "peak_gbs": peaks.get("hbm_gbs")}}
+        else:
+            roof = {"bound": "tensor", "kernel": "refine forward (all kernels)", "achieved": algo_flops / (knn_ms / 1e3) / 1e12,
+                    "peak": peak, "unit": "TFLOP/s", "frac": algo_flops / (knn_ms / 1e3) / 1e12 / peak, "traffic": None,
+                    "peak_source": peak_src, "avg_launch_ms": knn_ms, "algorithmic_flops_per_launch": algo_flops}
         line = {"metric": METRIC if args.workload == "retrieval" else "64^3 TSDF chunks/sec (refine forward)", "value": value,
                 "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 encode / f64 distance ranking", "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roof, "clocks": clocks,
-                "breakdown_ms": {"encode": float(np.mean(t_enc)), "knn": knn_ms, "step": total_ms / args.steps,
+                "breakdown_ms": {"encode": float(np.mean(t_enc)), "knn": knn_ms,
+                                 "knn_candidates_kernel": float(np.mean(t_cand)) if t_cand else None, "step": total_ms / args.steps,
                                  "wall_per_step_incl_flush": 1e3 * wall / args.steps}}
+        if replicated is not None:
+            line["replicated_bank"] = replicated
         if args.workload == "retrieval" and world == 1:
             # proof statistics of the tensor-core kNN on this workload (one extra, untimed call)
             qq = pipe.encode_queries(chunks) if q_rand is None else q_rand

@@ -127,6 +127,15 @@ int rf_tc_conv3d_fwd(const void* x_hi, const void* x_lo, int C1, const void* x2_
                      const void* weight_image, const float* bias, float* y, int N, int Di, int Hi, int Wi, int Cout, int KS,
                      int stride, int pad, int act, float slope, float out_scale, int out_ncdhw, void* stream);
 
+/* First layers (single input channel: the TSDF / occupancy volume): direct
+ * convolution, one thread per output voxel, filter bank in shared memory,
+ * optional GroupNorm(1 group) on the input (gn_mu/gn_a per sample, gn_beta
+ * scalar), bias + activation fused.  x [N,Di,Hi,Wi] fp32, w [Cout,1,KS,KS,KS]
+ * (the Conv3d weight as is), y fp32 channels-last [N,Do,Ho,Wo,Cout], Cout <= 32. */
+int rf_conv3d_cin1_cl_fwd(const float* x, const float* w, const float* bias, const float* gn_mu, const float* gn_a,
+                          const float* gn_beta, float* y, int N, int Di, int Hi, int Wi, int Cout, int KS, int stride, int pad,
+                          int act, float slope, void* stream);
+
 /* ---- a5 + a9  fused query encoder --------------------------------------- */
 
 /* model/retrieval.py:64-84 Patch04.forward (+Patch05/Patch04V2: any ReLU MLP)
@@ -157,8 +166,12 @@ int rf_knn_l2_topk(const float* bank, long n_rows, long row_offset, const float*
                    int* out_idx, double* out_d, void* workspace, size_t workspace_bytes, void* stream);
 /* Diagnostics of the last method-2/3 call that used `workspace`: number of
  * queries that needed the exact re-check and the largest observed error of the
- * tensor-core score over all re-ranked candidates (validates the bound). */
-int rf_knn_tc_stats(const void* workspace, int* n_unproven, float* max_score_err, void* stream);
+ * tensor-core score over all re-ranked candidates (validates the bound), and
+ * the CUDA-event duration of the last candidates kernel launched by this
+ * process (the kernel the roofline is quoted on). */
+int rf_knn_tc_stats(const void* workspace, int* n_unproven, float* max_score_err, float* candidates_ms, void* stream);
+/* CUDA-event duration (ms) of the candidates kernel of the last method-2/3 call in this process; -1 if none. */
+float rf_knn_last_candidates_ms(void);
 /* Merge S sorted candidate lists per query (shards of one GPU sweep or the
  * all-gathered per-rank lists): parts_idx/parts_d [S,Q,k] -> [Q,k]
  * under the same (d, id) order. */

@@ -50,13 +50,16 @@ PROTOTYPES = {
     "rf_tc_conv_weight_image": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "rf_tc_conv3d_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
+    "rf_conv3d_cin1_cl_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                      c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "rf_mlp_encode_workspace_bytes": (c_size_t, [c_long, c_int * 9, c_int]),
     "rf_mlp_encode_fwd": (c_int, [c_void_p, _ptr4, _ptr4, c_int * 9, c_int, c_int, c_void_p, c_long, c_void_p, c_size_t,
                                   c_void_p]),
     "rf_knn_workspace_bytes": (c_size_t, [c_long, c_long, c_int, c_int]),
     "rf_knn_l2_topk": (c_int, [c_void_p, c_long, c_long, c_void_p, c_long, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_size_t, c_void_p]),
-    "rf_knn_tc_stats": (c_int, [c_void_p, POINTER(c_int), POINTER(c_float), c_void_p]),
+    "rf_knn_tc_stats": (c_int, [c_void_p, POINTER(c_int), POINTER(c_float), POINTER(c_float), c_void_p]),
+    "rf_knn_last_candidates_ms": (c_float, []),
     "rf_knn_merge": (c_int, [c_void_p, c_void_p, c_int, c_long, c_int, c_void_p, c_void_p, c_void_p]),
     "rf_knn_demote_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p]),

@@ -231,6 +231,100 @@ extern "C" int rf_groupnorm_stats(const float* x, const float* x2, int C2, const
 }
 
 // ---------------------------------------------------------------------------
+// First layers: single input channel (the TSDF / occupancy volume itself).
+// With Cin = 1 a conv is 27 or 125 MACs per output channel - nothing for a GEMM
+// to chew on - so this is a direct convolution: one thread per output voxel,
+// the filter bank transposed in shared memory ([tap][CO], broadcast reads),
+// CO accumulators in registers, GroupNorm(1 group) applied to in-bounds taps on
+// the fly, bias + activation fused, fp32 channels-last output (what the
+// tensor-core layers consume).
+// ---------------------------------------------------------------------------
+namespace {
+template <int CO>
+__global__ void __launch_bounds__(256) conv_cin1_direct_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, const float* __restrict__ gn_mu,
+                                                               const float* __restrict__ gn_a, const float* __restrict__ gn_beta,
+                                                               float* __restrict__ y, int Di, int Hi, int Wi, int Do, int Ho,
+                                                               int Wo, int KS, int stride, int pad, int Cout, int act,
+                                                               float slope, long M) {
+    extern __shared__ float wsm[];  // [taps][CO]
+    const int taps = KS * KS * KS;
+    for (int i = threadIdx.x; i < taps * CO; i += blockDim.x) {
+        const int t = i / CO, co = i % CO;
+        wsm[i] = co < Cout ? __ldg(w + (long)co * taps + t) : 0.f;
+    }
+    __syncthreads();
+    const float beta = gn_mu ? __ldg(gn_beta) : 0.f;
+    for (long m = blockIdx.x * (long)blockDim.x + threadIdx.x; m < M; m += (long)gridDim.x * blockDim.x) {
+        long t = m;
+        const int ow = (int)(t % Wo); t /= Wo;
+        const int oh = (int)(t % Ho); t /= Ho;
+        const int od = (int)(t % Do); t /= Do;
+        const long n = t;
+        const float mu = gn_mu ? __ldg(gn_mu + n) : 0.f, ga = gn_mu ? __ldg(gn_a + n) : 1.f;
+        const float* xn = x + n * (long)Di * Hi * Wi;
+        float acc[CO];
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+        const int d0 = od * stride - pad, h0 = oh * stride - pad, w0 = ow * stride - pad;
+        int tap = 0;
+        for (int kd = 0; kd < KS; ++kd) {
+            const int id = d0 + kd;
+            for (int kh = 0; kh < KS; ++kh) {
+                const int ih = h0 + kh;
+                const bool row_ok = id >= 0 && id < Di && ih >= 0 && ih < Hi;
+                const float* xr = xn + ((long)id * Hi + ih) * Wi;
+                for (int kw = 0; kw < KS; ++kw, ++tap) {
+                    const int iw = w0 + kw;
+                    float v = 0.f;
+                    if (row_ok && iw >= 0 && iw < Wi) {
+                        v = __ldg(xr + iw);
+                        if (gn_mu) v = fmaf(v - mu, ga, beta);
+                    }
+                    const float4* wr = reinterpret_cast<const float4*>(wsm + tap * CO);
+#pragma unroll
+                    for (int c4 = 0; c4 < CO / 4; ++c4) {
+                        const float4 w4 = wr[c4];
+                        acc[4 * c4] = fmaf(v, w4.x, acc[4 * c4]);
+                        acc[4 * c4 + 1] = fmaf(v, w4.y, acc[4 * c4 + 1]);
+                        acc[4 * c4 + 2] = fmaf(v, w4.z, acc[4 * c4 + 2]);
+                        acc[4 * c4 + 3] = fmaf(v, w4.w, acc[4 * c4 + 3]);
+                    }
+                }
+            }
+        }
+        float* out = y + m * Cout;
+#pragma unroll
+        for (int c = 0; c < CO; ++c)
+            if (c < Cout) out[c] = rf_act(acc[c] + (bias ? __ldg(bias + c) : 0.f), act, slope);
+    }
+}
+}  // namespace
+
+extern "C" int rf_conv3d_cin1_cl_fwd(const float* x, const float* w, const float* bias, const float* gn_mu, const float* gn_a,
+                                     const float* gn_beta, float* y, int N, int Di, int Hi, int Wi, int Cout, int KS,
+                                     int stride, int pad, int act, float slope, void* stream) {
+    RF_CHECK_ARG(x && w && y, "rf_conv3d_cin1_cl_fwd: null pointer");
+    RF_CHECK_ARG(N > 0 && Di > 0 && Hi > 0 && Wi > 0 && Cout >= 1 && Cout <= 32 && KS >= 1 && KS <= 5 && stride >= 1 && pad >= 0,
+                 "rf_conv3d_cin1_cl_fwd: unsupported shape (Cout <= 32, kernel <= 5)");
+    RF_CHECK_ARG((gn_mu == nullptr) == (gn_a == nullptr) && (gn_mu == nullptr) == (gn_beta == nullptr), "rf_conv3d_cin1_cl_fwd: partial GroupNorm arguments");
+    const int Do = (Di + 2 * pad - KS) / stride + 1, Ho = (Hi + 2 * pad - KS) / stride + 1, Wo = (Wi + 2 * pad - KS) / stride + 1;
+    RF_CHECK_ARG(Do > 0 && Ho > 0 && Wo > 0, "rf_conv3d_cin1_cl_fwd: empty output");
+    const long M = (long)N * Do * Ho * Wo;
+    const int taps = KS * KS * KS;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = rf_grid_1d(M, 256, 148 * 32);
+    if (Cout <= 8)
+        conv_cin1_direct_kernel<8><<<grid, 256, taps * 8 * sizeof(float), s>>>(x, w, bias, gn_mu, gn_a, gn_beta, y, Di, Hi, Wi, Do, Ho, Wo, KS, stride, pad, Cout, act, slope, M);
+    else if (Cout <= 16)
+        conv_cin1_direct_kernel<16><<<grid, 256, taps * 16 * sizeof(float), s>>>(x, w, bias, gn_mu, gn_a, gn_beta, y, Di, Hi, Wi, Do, Ho, Wo, KS, stride, pad, Cout, act, slope, M);
+    else
+        conv_cin1_direct_kernel<32><<<grid, 256, taps * 32 * sizeof(float), s>>>(x, w, bias, gn_mu, gn_a, gn_beta, y, Di, Hi, Wi, Do, Ho, Wo, KS, stride, pad, Cout, act, slope, M);
+    RF_LAUNCH_OK("conv_cin1_direct_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // F.normalize(x, dim=1): one warp per row.
 // ---------------------------------------------------------------------------
 namespace {

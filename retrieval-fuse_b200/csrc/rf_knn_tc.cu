@@ -68,6 +68,9 @@ struct Stats {            // first 256 bytes of the workspace
     unsigned nmin_bits;   // min |x|^2 over the bank (float bits)
     unsigned nmax_bits;   // max |x|^2
 };
+// host-side record of the last call (per process): device time of the candidates kernel
+static float g_last_candidates_ms = -1.f;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -542,9 +545,15 @@ int tc_run(const TcLayout& L, const float* bank, long n_rows, long row_offset, c
     knn_tc_prep_kernel<KBLK><<<(unsigned)rf_cdivl(qpad * 8, 256), 256, 0, s>>>(q, Q, qpad, 0, q_img, stats);
     RF_LAUNCH_OK("knn_tc_prep_kernel(queries)");
     dim3 grid(L.n_qpairs, L.nsplit);
+    if (!g_ev0) {
+        RF_CUDA_OK(cudaEventCreate(&g_ev0));
+        RF_CUDA_OK(cudaEventCreate(&g_ev1));
+    }
+    RF_CUDA_OK(cudaEventRecord(g_ev0, s));  // device time of the dominant kernel, read back by rf_knn_tc_stats
     knn_tc_candidates_kernel<KBLK><<<grid, NTHREADS, Cfg<KBLK>::SMEM_BYTES, s>>>(q_img, bank_img, Q, n_rows, L.n_qtiles,
                                                                                L.n_btiles, L.tiles_per_split, cand_s, cand_i);
     RF_LAUNCH_OK("knn_tc_candidates_kernel");
+    RF_CUDA_OK(cudaEventRecord(g_ev1, s));
     knn_tc_rerank_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, s>>>(bank, row_offset, q, Q, k, L.nsplit, cand_s, cand_i,
                                                                         out_idx, out_d, flagged, stats, eps_rel(KBLK));
     RF_LAUNCH_OK("knn_tc_rerank_kernel");
@@ -571,14 +580,18 @@ int rf_knn_tc_launch(const float* bank, long n_rows, long row_offset, const floa
     int n_flagged = 0;
     RF_CUDA_OK(cudaMemcpyAsync(&n_flagged, &((Stats*)(ws + L.stats))->n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
     RF_CUDA_OK(cudaStreamSynchronize(s));
+    if (g_ev0 && cudaEventElapsedTime(&g_last_candidates_ms, g_ev0, g_ev1) != cudaSuccess) g_last_candidates_ms = -1.f;
     if (n_flagged > 0)
         return rf_knn_exact_launch(bank, n_rows, row_offset, q, n_flagged, k, (const int*)(ws + L.flagged), out_idx, out_d,
                                    ws + L.exact_ws, L.exact_ws_bytes, s);
     return 0;
 }
 
+extern "C" float rf_knn_last_candidates_ms(void) { return g_last_candidates_ms; }
+
 // Diagnostics of the last tensor-core call that used `workspace` (synchronises the stream).
-extern "C" int rf_knn_tc_stats(const void* workspace, int* n_unproven, float* max_score_err, void* stream) {
+extern "C" int rf_knn_tc_stats(const void* workspace, int* n_unproven, float* max_score_err, float* candidates_ms,
+                               void* stream) {
     RF_CHECK_ARG(workspace, "rf_knn_tc_stats: null workspace");
     Stats h;
     const void* ws = (const void*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
@@ -586,5 +599,6 @@ extern "C" int rf_knn_tc_stats(const void* workspace, int* n_unproven, float* ma
     RF_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
     if (n_unproven) *n_unproven = h.n_flagged;
     if (max_score_err) memcpy(max_score_err, &h.max_err_bits, sizeof(float));
+    if (candidates_ms) *candidates_ms = g_last_candidates_ms;  // CUDA-event time of the last candidates kernel (this process)
     return 0;
 }

@@ -212,6 +212,24 @@ __global__ void __launch_bounds__(256) cl_norm_split_kernel(const float* __restr
     }
 }
 
+// Single-channel tensors (the 1-channel TSDF inputs) stay unpadded: [N,S] fp16 hi / lo.
+__global__ void __launch_bounds__(256) cl_norm_split_c1_kernel(const float* __restrict__ x, const float* __restrict__ mu,
+                                                               const float* __restrict__ a, const float* __restrict__ beta,
+                                                               uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, long NS, long S,
+                                                               float scale) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < NS; i += (long)gridDim.x * blockDim.x) {
+        float val = __ldg(x + i);
+        if (mu) {
+            const long n = i / S;
+            val = fmaf(val - __ldg(mu + n), __ldg(a + n), __ldg(beta));
+        }
+        uint32_t h, l;
+        split_f16(val * scale, h, l);
+        hi[i] = (uint16_t)h;
+        lo[i] = (uint16_t)l;
+    }
+}
+
 __global__ void __launch_bounds__(256) cl_maxpool2_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int D,
                                                           int H, int W, int C) {
     const int Do = D / 2, Ho = H / 2, Wo = W / 2;
@@ -265,7 +283,18 @@ __global__ void __launch_bounds__(256) tc_conv_weight_image_kernel(const float* 
     if (gid >= total) return;
     const int n = (int)(gid / (n_kb * 8)), q = (int)(gid % (n_kb * 8));
     uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
-    if (n < Cout && q < taps * CC) {
+    if (Cin == 1) {  // tap-major mode: K index = tap (no channel padding)
+        if (n < Cout) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int tap = q * 8 + e;
+                uint32_t h, l;
+                split_f16(tap < taps ? w[(long)n * taps + tap] * scale : 0.f, h, l);
+                hi[e / 2] |= h << (16 * (e & 1));
+                lo[e / 2] |= l << (16 * (e & 1));
+            }
+        }
+    } else if (n < Cout && q < taps * CC) {
         const int tap = q / CC, cc = q % CC;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -293,7 +322,7 @@ struct ConvArgs {
     float* y;
     int N, Di, Hi, Wi, Do, Ho, Wo, KS, stride, pad, Cp1, Cp2, Cout, Npad, act, out_ncdhw;
     float slope, out_scale;  // out_scale = 1 / (activation scale * weight scale), applied to the accumulator
-    int M, n_kb, total_chunks, a_stages, b_stages;
+    int M, n_kb, total_chunks, a_stages, b_stages, cin1;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_kernel(const ConvArgs a) {
@@ -381,6 +410,40 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_kernel(const ConvArgs a
         }
         const int CC1 = a.Cp1 >> 3, CC = (a.Cp1 + a.Cp2) >> 3;
         const int D2 = a.Di >> 1, H2 = a.Hi >> 1, W2 = a.Wi >> 1;
+        if (a.cin1) {
+            // Single input channel: K index = tap.  x_hi / x_lo are unpadded [N,D,H,W] fp16; chunk q of a row holds
+            // taps 8q .. 8q+7 of that output voxel's receptive field (scalar gathers, 27 / 125 taps in total).
+            const int taps = a.KS * a.KS * a.KS;
+            for (int kb = 0; kb < a.n_kb; ++kb) {
+                const int sa = kb % A_STAGES;
+                const int q = kb * 8 + j;
+                mbar_wait(bar_aempty + 8 * sa, ((uint32_t)(kb / A_STAGES) & 1u) ^ 1u);
+                uint8_t* img_hi = smem_al + (sA - base) + sa * 2 * IMG;
+#pragma unroll 2
+                for (int p = 0; p < 8; ++p) {
+                    uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+                    if (r_n[p] >= 0) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int tap = q * 8 + e;
+                            const int kw = tap % a.KS, kh = (tap / a.KS) % a.KS, kd = tap / (a.KS * a.KS);
+                            const int id = r_d[p] + kd, ih = r_h[p] + kh, iw = r_w[p] + kw;
+                            if (tap < taps && id >= 0 && id < a.Di && ih >= 0 && ih < a.Hi && iw >= 0 && iw < a.Wi) {
+                                const long off = (((long)r_n[p] * a.Di + id) * a.Hi + ih) * a.Wi + iw;
+                                h[e >> 1] |= (uint32_t)__ldg(a.x_hi + off) << (16 * (e & 1));
+                                l[e >> 1] |= (uint32_t)__ldg(a.x_lo + off) << (16 * (e & 1));
+                            }
+                        }
+                    }
+                    const int r = pw * 32 + p * 4 + (lane >> 3);
+                    const uint32_t off = (uint32_t)r * 128u + ((uint32_t)(j ^ (r & 7)) << 4);
+                    *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4*>(img_hi + IMG + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(bar_afull + 8 * sa);
+            }
+        } else
         for (int kb = 0; kb < a.n_kb; ++kb) {
             const int sa = kb % A_STAGES;
             const int q = kb * 8 + j;
@@ -449,6 +512,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_kernel(const ConvArgs a
     }
 }
 
+// K blocks of 64: (taps x padded channel chunks) / 8, or taps / 64 in the single-channel tap-major mode
+int conv_total_chunks(int C1, int C2, int KS) {
+    const int taps = KS * KS * KS;
+    if (C1 + C2 == 1) return (taps + 7) / 8;
+    return taps * ((C1 + 7) / 8 + (C2 + 7) / 8);
+}
 int conv_smem(int a_stages, int b_stages, int npad) { return 1024 + a_stages * 2 * IMG + b_stages * 2 * npad * 128 + 256; }
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 int conv_npad(int cout) { return round_up(cout, 16) < 32 ? 32 : round_up(cout, 16); }
@@ -486,6 +555,13 @@ extern "C" int rf_cl_gn_stats(const float* x, const float* x2, int C2, const flo
 
 extern "C" int rf_cl_norm_split(const float* x, const float* gn_mu, const float* gn_a, const float* gn_beta, int c_off,
                                 int c_tot, void* hi, void* lo, long N, long S, int C, int Cp, float scale, void* stream) {
+    if (C == 1 && Cp == 1) {  // single-channel input: unpadded fp16 hi / lo, consumed by the conv's tap-major mode
+        RF_CHECK_ARG(x && hi && lo && N > 0 && S > 0 && c_off == 0 && c_tot == 1, "rf_cl_norm_split: bad arguments (C = 1)");
+        cl_norm_split_c1_kernel<<<rf_grid_1d(N * S, 256), 256, 0, (cudaStream_t)stream>>>(x, gn_mu, gn_a, gn_beta, (uint16_t*)hi,
+                                                                                         (uint16_t*)lo, N * S, S, scale);
+        RF_LAUNCH_OK("cl_norm_split_c1_kernel");
+        return 0;
+    }
     RF_CHECK_ARG(x && hi && lo && N > 0 && S > 0 && C > 0 && Cp >= C && Cp % 8 == 0, "rf_cl_norm_split: bad arguments");
     RF_CHECK_ARG((gn_mu == nullptr) == (gn_a == nullptr) && (gn_mu == nullptr) == (gn_beta == nullptr), "rf_cl_norm_split: partial GroupNorm arguments");
     RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0, "rf_cl_norm_split: outputs must be 16-byte aligned");
@@ -513,8 +589,7 @@ extern "C" int rf_cl_transpose(const float* in, float* out, long N, long S, int 
 
 extern "C" size_t rf_tc_conv_weight_image_bytes(int Cout, int C1, int C2, int KS) {
     if (Cout < 1 || Cout > 128 || C1 < 0 || C2 < 0 || C1 + C2 < 1 || KS < 1 || KS > 5) return 0;
-    const int CC = (round_up(C1, 8) + round_up(C2, 8)) / 8;
-    const int n_kb = (KS * KS * KS * CC + 7) / 8;
+    const int n_kb = (conv_total_chunks(C1, C2, KS) + 7) / 8;
     return (size_t)n_kb * 2 * conv_npad(Cout) * 128;
 }
 
@@ -523,8 +598,8 @@ extern "C" int rf_tc_conv_weight_image(const float* w, int Cout, int C1, int C2,
     RF_CHECK_ARG(w && image, "rf_tc_conv_weight_image: null pointer");
     RF_CHECK_ARG(rf_tc_conv_weight_image_bytes(Cout, C1, C2, KS) > 0, "rf_tc_conv_weight_image: unsupported shape Cout=%d C1=%d C2=%d KS=%d", Cout, C1, C2, KS);
     RF_CHECK_ARG(((uintptr_t)image & 1023) == 0, "rf_tc_conv_weight_image: image must be 1024-byte aligned");
-    const int Cp1 = round_up(C1, 8), Cp2 = round_up(C2, 8), CC = (Cp1 + Cp2) / 8;
-    const int n_kb = (KS * KS * KS * CC + 7) / 8, npad = conv_npad(Cout);
+    const int Cp1 = round_up(C1, 8), Cp2 = round_up(C2, 8);
+    const int n_kb = (conv_total_chunks(C1, C2, KS) + 7) / 8, npad = conv_npad(Cout);
     const long threads = (long)npad * n_kb * 8;
     tc_conv_weight_image_kernel<<<(unsigned)rf_cdivl(threads, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, C1, C2, Cp1, Cp2, KS, npad, n_kb,
                                                                                                    scale, (uint8_t*)image);
@@ -551,8 +626,10 @@ extern "C" int rf_tc_conv3d_fwd(const void* x_hi, const void* x_lo, int C1, cons
     const long M = (long)N * a.Do * a.Ho * a.Wo;
     RF_CHECK_ARG(M < (1L << 31) - TM, "rf_tc_conv3d_fwd: too many output voxels");
     a.M = (int)M;
-    a.total_chunks = KS * KS * KS * ((a.Cp1 + a.Cp2) / 8);
+    a.total_chunks = conv_total_chunks(C1, C2, KS);
     a.n_kb = (a.total_chunks + 7) / 8;
+    a.cin1 = (C1 + C2 == 1) ? 1 : 0;
+    RF_CHECK_ARG(!a.cin1 || C1 == 1, "rf_tc_conv3d_fwd: a single input channel must come from x");
     a.a_stages = MAX_A_STAGES;
     a.b_stages = 2;  // Npad <= 64: 97 KiB per CTA -> two CTAs per SM; Npad = 128: 129 KiB, one CTA
     static bool attr_set = false;

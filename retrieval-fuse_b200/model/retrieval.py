@@ -54,6 +54,9 @@ class _ConvPatchEncoder(RfModule):
         h = ops.cl_from_ncdhw(x)
         for li, (conv, (_mult, k, s)) in enumerate(zip(convs, self._spec)):
             cin = conv.in_channels
+            if cin == 1 and conv.out_channels <= 32:  # first layer: direct convolution on the raw single-channel patch
+                h = ops.conv3d_cin1_cl(h, conv.weight, conv.bias, None, ks=k, stride=s, pad=0, act=ops.ACT_LEAKY, slope=0.2)
+                continue
             img, sw = self._wcache.derived(("tcconv", li), [conv.weight], lambda w, c=cin: ops.tc_conv_weight_image(w, c, 0))
             h = ops.tc_conv3d(ops.cl_norm_split(h), None, cin, 0, img, conv.bias, conv.out_channels, k, stride=s, pad=0,
                               act=ops.ACT_LEAKY, slope=0.2, out_scale=1.0 / sw)

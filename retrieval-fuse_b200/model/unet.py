@@ -75,6 +75,10 @@ class SingleConv(RfModule):
             mu, a = ops.cl_gn_stats(x2, g.weight, g.num_groups, g.eps)
         else:
             mu, a = ops.cl_gn_stats(x, g.weight, g.num_groups, g.eps, x2=x2)
+        if c1 == 1 and c2 == 0 and self.out_channels <= 32 and not out_ncdhw:
+            # first layer (single input channel): direct convolution with the normalisation on the fly
+            return ops.conv3d_cin1_cl(x, self.conv.weight, self.conv.bias, (mu, a, g.bias), ks=3, stride=1, pad=1,
+                                      act=self.act, slope=0.1)
         sa = ops.ACT_SCALE_GN
         xs = ops.cl_norm_split(x, (mu, a, g.bias), 0, scale=sa) if x is not None else None
         x2s = ops.cl_norm_split(x2, (mu, a, g.bias), c1, scale=sa) if x2 is not None else None

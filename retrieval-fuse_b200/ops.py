@@ -271,7 +271,7 @@ def cl_norm_split(x, gn=None, c_off=0, scale=1.0):
     GroupNorm affine with this tensor's channels starting at c_off of the statistics."""
     x = _dev(x, name="x")
     N, D, H, W, C = x.shape
-    Cp = (C + 7) // 8 * 8
+    Cp = 1 if C == 1 else (C + 7) // 8 * 8  # single-channel inputs stay unpadded (tap-major conv mode)
     hi = torch.empty((N, D, H, W, Cp), device=x.device, dtype=torch.int16)
     lo = torch.empty((N, D, H, W, Cp), device=x.device, dtype=torch.int16)
     mu, a, beta = gn if gn is not None else (None, None, None)
@@ -289,6 +289,23 @@ def cl_maxpool3d_2(x):
     y = torch.empty((N, D // 2, H // 2, W // 2, C), device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device):
         check(_lib.lib().rf_cl_maxpool3d_2(x.data_ptr(), y.data_ptr(), N, D, H, W, C, _stream(x)), "rf_cl_maxpool3d_2")
+    _count()
+    return y
+
+
+def conv3d_cin1_cl(x, weight, bias, gn=None, ks=3, stride=1, pad=0, act=ACT_NONE, slope=0.0):
+    """Direct convolution of a single-channel channels-last volume x [N,D,H,W,1] -> fp32 [N,Do,Ho,Wo,Cout]."""
+    x = _dev(x, name="x")
+    N, D, H, W = x.shape[:4]
+    weight = _dev(weight.detach(), name="weight")
+    cout = weight.shape[0]
+    Do, Ho, Wo = [(v + 2 * pad - ks) // stride + 1 for v in (D, H, W)]
+    y = torch.empty((N, Do, Ho, Wo, cout), device=x.device, dtype=torch.float32)
+    mu, a, beta = gn if gn is not None else (None, None, None)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_conv3d_cin1_cl_fwd(x.data_ptr(), weight.data_ptr(), _ptr(bias), _ptr(mu), _ptr(a), _ptr(beta),
+                                               y.data_ptr(), N, D, H, W, cout, ks, stride, pad, act, float(slope), _stream(x)),
+              "rf_conv3d_cin1_cl_fwd")
     _count()
     return y
 
@@ -441,10 +458,11 @@ def knn_topk(bank, q, k, row_offset=0, method=0, stats=False):
                                d.data_ptr(), ws.data_ptr(), ws.numel(), _stream(q)), "rf_knn_l2_topk")
         if stats:
             import ctypes
-            nu, err = ctypes.c_int(-1), ctypes.c_float(-1.0)
+            nu, err, ms = ctypes.c_int(-1), ctypes.c_float(-1.0), ctypes.c_float(-1.0)
             if method != 1:
-                check(L.rf_knn_tc_stats(ws.data_ptr(), ctypes.byref(nu), ctypes.byref(err), _stream(q)), "rf_knn_tc_stats")
-            last_knn_stats.update(n_unproven=nu.value, max_score_err=err.value)
+                check(L.rf_knn_tc_stats(ws.data_ptr(), ctypes.byref(nu), ctypes.byref(err), ctypes.byref(ms), _stream(q)),
+                      "rf_knn_tc_stats")
+            last_knn_stats.update(n_unproven=nu.value, max_score_err=err.value, candidates_kernel_ms=ms.value)
     _count(4)
     return idx, d
 
