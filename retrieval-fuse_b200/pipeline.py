@@ -55,6 +55,18 @@ MATTERPORT_SR16 = dict(
     retrieval_model=dict(network_input="4+2", network_target="16+8", nf_input=16, nf_target=8, latent_dim=64),
     dictionary=dict(batch_size=512), query=dict(batch_size=1024, K=4),
 )
+# config/surface_reconstruction/Matterport3D/{retrieval,refinement}_128_064.yaml: 128^3 occupancy grid of a point
+# cloud (util/misc.py:73-78) -> 64^3 TSDF; K = 8 as in BASELINE config 4 (the yaml default is 4)
+MATTERPORT_SURFACE = dict(
+    task="surface_reconstruction", K=8, nf=12, unet_num_level=5, layer_order="gcr", retrieval_fmaps=12, retrieval_num_level=4,
+    attn_patch_extent=4, attn_normalize=True, attn_use_switching=True, attn_retrieval_mode=False,
+    attn_no_output_mapping=True, attn_blend=True, attn_num_patch=16,
+    dataset=dict(input_chunk_size=128, target_chunk_size=64, patch_size_input=32, patch_context_input=8,
+                 patch_size_target=16, patch_context_target=4, patch_stride=16, voxel_size_input=0, voxel_size_target=3.75,
+                 input_mean=0, input_std=1, target_mean=10.502049923464249, target_std=2.3319665041587627, num_points=1000),
+    retrieval_model=dict(network_input="pc_32+8", network_target="16+4", nf_input=10, nf_target=12, latent_dim=64),
+    dictionary=dict(batch_size=256), query=dict(batch_size=128, K=8),
+)
 
 
 def f16_trunc(voxel_size):

@@ -422,6 +422,38 @@ def test_hot_path_end_to_end_small(dev):
     G.smoke()
 
 
+def test_surface_reconstruction_config_end_to_end(dev):
+    """BASELINE config 4 shapes: 128^3 occupancy grid of a point cloud -> PCPatch48 queries -> kNN against a
+    Patch24 bank -> compose -> 5-level U-Net (nf 12) + retrieval U-Net + attention (K = 8) + decoder, vs the oracle."""
+    from retrieval_fuse_b200.pipeline import MATTERPORT_SURFACE as CFG, RefinementPipeline, build_bank_from_targets, init_unit_gain_
+    d = CFG["dataset"]
+    rng = np.random.default_rng(4)
+    targets = np.stack([O.synthetic_tsdf(20 + i, 64, d["voxel_size_target"]) for i in range(3)])
+    bank, fenc_t = build_bank_from_targets(CFG, torch.from_numpy(targets).to(dev), dev, weight_seed=3)
+    assert bank.emb.shape == (3 * 64 + 1, 64)
+    pipe = RefinementPipeline(CFG, bank, torch.from_numpy(targets).to(dev), device=dev, weight_seed=5)
+    pts = rng.random((1000, 3)) * 64
+    grid = O.point_cloud_to_grid(pts, 128, 2.0, 0)[None, None]            # dataset/scene.py:81-90 with pad 0
+    chunks = torch.from_numpy(grid).to(dev)
+    q = pipe.encode_queries(chunks)
+    sds = pipe.state_dicts()
+    q_ref = O.encode_chunk_queries(CFG, sds["fenc_input"], grid)
+    assert q.shape == (64, 64)
+    close(q, q_ref, tol=2e-5, what="PCPatch48 queries")
+    rows, idx = pipe.lookup(q)
+    rows_ref, idx_ref = O.lookup_rows(bank.emb.cpu().numpy(), bank.meta.cpu().numpy(), q.cpu().numpy(), CFG["K"])
+    assert np.array_equal(idx.cpu().numpy(), idx_ref) and np.array_equal(rows.cpu().numpy(), rows_ref)
+    retr = pipe.compose(rows, 1)
+    retr_ref = O.compose_chunks(CFG, rows_ref, targets, 1)
+    assert retr.shape == (1, 8, 64, 64, 64) and np.array_equal(retr.cpu().numpy(), retr_ref)
+    pred = pipe.refine(pipe.normalize_input(chunks), pipe.compose(rows, 1, normalize=True))[0]
+    pred_ref = O.refine_chunks(CFG, {k: v for k, v in sds.items() if k != "fenc_input"}, grid, retr_ref)[0]
+    # TSDF units here are centimetres-scale (trunc = 11.25): compare in the network's tanh domain against
+    # the fp32 noise of this 5-level network instead
+    err = float((pred.cpu() - pred_ref).abs().max())
+    assert err <= 2e-3, f"surface-reconstruction refine forward differs by {err:.2e}"
+
+
 def test_retrieval_interface_roundtrip(dev, tmp_path):
     """create_dictionary -> database.npy/index.json -> query -> compose through the
     reference-shaped API (RetrievalInterface, SceneHandler access, PatchedSceneDataset)."""
