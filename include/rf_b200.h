@@ -127,6 +127,29 @@ int rf_tc_conv3d_fwd(const void* x_hi, const void* x_lo, int C1, const void* x2_
                      const void* weight_image, const float* bias, float* y, int N, int Di, int Hi, int Wi, int Cout, int KS,
                      int stride, int pad, int act, float slope, float out_scale, int out_ncdhw, void* stream);
 
+/* "Shifted window" variant of the tensor-core convolution for the 3x3x3 / stride 1 /
+ * pad 1 layers of the U-Nets (model/unet.py:19-100 create_conv 'gcr'): the
+ * normalised activations are written once as fp16 hi / lo slot planes with a zero
+ * halo, [channel chunk][N][D+2][H+2][W+2] x 16 B (one slot = 8 channels of a voxel;
+ * x2, when given, is nearest-upsampled and concatenated after x's channels, each
+ * source padded to 8 channels; the chunk count is padded to an even number unless
+ * it is 1), and the convolution kernel stages a patch / slab of those planes in
+ * shared memory once, addressing all 27 taps in place through no-swizzle UMMA
+ * descriptors (no im2col).  rf_halo_act_bytes = size of ONE of hi / lo.
+ * rf_tc_conv3d_halo_supported tells whether an item shape fits shared memory and
+ * TMEM for this layer; callers use rf_tc_conv3d_fwd otherwise.  y is fp32
+ * channels-last [N,D,H,W,Cout] or NCDHW. */
+size_t rf_halo_act_bytes(int N, int D, int H, int W, int C1, int C2);
+int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a,
+                          const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, float scale, void* stream);
+size_t rf_tc_conv_halo_weight_image_bytes(int Cout, int C1, int C2);
+int rf_tc_conv_halo_weight_image(const float* w, int Cout, int C1, int C2, float scale, void* image, void* stream);
+int rf_tc_conv3d_halo_supported(int N, int D, int H, int W, int Cout, int C1, int C2);
+int rf_tc_conv3d_halo_geometry(int N, int D, int H, int W, int Cout, int C1, int C2, int* out8);
+int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D,
+                          int H, int W, int Cout, int C1, int C2, int act, float slope, float out_scale, int out_ncdhw,
+                          void* stream);
+
 /* First layers (single input channel: the TSDF / occupancy volume): direct
  * convolution, one thread per output voxel, filter bank in shared memory,
  * optional GroupNorm(1 group) on the input (gn_mu/gn_a per sample, gn_beta

@@ -1,0 +1,700 @@
+// "Shifted window" tensor-core convolution for the U-Net 'gcr' blocks
+// (model/unet.py:19-100: GroupNorm -> Conv3d k3 p1 -> ReLU), 3x3x3, stride 1,
+// zero padding 1.
+//
+// rf_tc_conv3d_fwd (rf_tc_conv.cu) gathers every tap's operand rows from L2 again:
+// 27x the activation bytes per layer, which bounds that kernel far below the MMA
+// rate.  Here the activation block is staged in shared memory ONCE and the tensor
+// core reads all 27 shifted windows of it in place:
+//
+//   * rf_cl_norm_split_halo writes the normalised activations (virtual concat of x and
+//     the nearest-upsampled x2 included) as fp16 hi / lo "slot planes"
+//         [channel chunk][sample][D+2][H+2][W+2] x 16 B   (slot = 8 channels of one voxel)
+//     with a zero halo, so that a patch / slab of one chunk plane is contiguous and one
+//     cp.async.bulk moves it to shared memory.
+//   * UMMA operand descriptors in the NO-swizzle K-major layout address core matrices
+//     of 8 rows x 16 B at arbitrary 16-byte granularity: 8 consecutive slots are the 8
+//     rows of a core matrix, the next 8-row group sits SBO bytes further, the second
+//     K chunk (channels 8..15 of the K = 16 step) LBO bytes further (the other chunk
+//     plane).  Tap (kd,kh,kw) of the convolution is therefore the SAME staged block
+//     with the start address advanced by ((kd*Hs + kh)*Wp + kw) slots: no im2col, no
+//     copies, one descriptor add per MMA.
+//   * GEMM rows are positions of the HALOED block ("linear" mode: 128 consecutive
+//     slots per M tile; "lines" mode when W % 8 == 0: 16 lines x 8 slots, SBO = one
+//     line), rows that fall on halo positions are computed and dropped (64-94 % of
+//     the rows are real outputs, depending on the extent).
+//   * fp16 hi/lo split with three products per step (hi*hi + hi*lo + lo*hi), fp32
+//     accumulators for the whole item in TMEM (n_tiles x Npad columns <= 512).
+//   * Single-chunk inputs (C <= 8) pair two taps into one K = 16 step: LBO = 16 B makes
+//     the second K chunk the neighbouring slot, i.e. tap kw+1.
+#include <cuda_fp16.h>
+
+#include "rf_common.cuh"
+
+namespace {
+
+constexpr int TM = 128, NTHREADS = 256, NB = 4, MAX_ABUF = 2;
+constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in maximum per CTA on sm_100
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 26)) {  // a pipeline bug must never hang the GPU
+            printf("rf_tc_conv_halo: mbarrier wait timed out (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
+            __trap();
+        }
+    }
+}
+// Whole-warp wait with a warp-uniform loop condition (a vote): the code after it stays provably convergent, which
+// the compiler needs in order to keep the MMA issue loop on the uniform datapath (uniform registers feed
+// tcgen05.mma directly; otherwise every MMA pays vector -> uniform register moves).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if (++spins > (1u << 26)) __trap();  // a pipeline bug must never hang the GPU
+    }
+}
+// Producer-side wait: these threads wait for a long time (a whole stage of MMAs); polling at full speed would
+// take shared-memory cycles away from the tensor core's operand reads.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        __nanosleep(200);
+        if (spins > (1u << 22)) {
+            printf("rf_tc_conv_halo: mbarrier wait timed out (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// Same, with the descriptors passed as (low, high) words: the low word carries start address and LBO and is the
+// only part that changes between MMAs.
+// `issue` (1 on the elected lane) predicates the instruction INSIDE the asm block: with a C++ `if (leader)` around
+// it the compiler sinks the descriptor arithmetic into the divergent region, computes it in vector registers and
+// pays two R2UR moves per MMA; unconditional arithmetic stays on the uniform datapath.
+__device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t acc, uint32_t issue) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc), "r"(issue)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 B stored as 128 contiguous bytes; LBO = byte distance
+// between the two K chunks of one K = 16 step, SBO = byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc_ns(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo & 0x3FFFFu) >> 4) << 16) |
+           ((uint64_t)((sbo & 0x3FFFFu) >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t idesc_f16(int n) {  // D f32, A/B f16, both K-major, N>>3 @17, M>>4 @24
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void split_f16(float x, uint32_t& hi, uint32_t& lo) {
+    const __half h = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+    const __half l = __float2half_rn(x - __half2float(h));
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
+}
+
+// ------------------------------------------------------------------ activations -> haloed slot planes
+struct SplitArgs {
+    const float *x, *x2, *mu, *a, *beta;
+    uint4 *hi, *lo;
+    int N, D, H, W, C1, C2, CC1, CC, CCe;
+    float scale;
+};
+
+__global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs s) {
+    const int Dp = s.D + 2, Hp = s.H + 2, Wp = s.W + 2;
+    const long V = (long)Dp * Hp * Wp;
+    const long total = (long)s.CCe * s.N * V;
+    const int c_tot = s.C1 + s.C2;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long t = i;
+        const int ww = (int)(t % Wp); t /= Wp;
+        const int hh = (int)(t % Hp); t /= Hp;
+        const int dd = (int)(t % Dp); t /= Dp;
+        const int n = (int)(t % s.N);
+        const int cc = (int)(t / s.N);
+        uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+        if (cc < s.CC && ww >= 1 && ww <= s.W && hh >= 1 && hh <= s.H && dd >= 1 && dd <= s.D) {
+            const int d = dd - 1, hq = hh - 1, w = ww - 1;
+            const float* src;
+            int C, c0, goff;
+            if (cc < s.CC1) {
+                C = s.C1; c0 = cc * 8; goff = 0;
+                src = s.x + ((((long)n * s.D + d) * s.H + hq) * s.W + w) * C;
+            } else {
+                C = s.C2; c0 = (cc - s.CC1) * 8; goff = s.C1;
+                src = s.x2 + ((((long)n * (s.D >> 1) + (d >> 1)) * (s.H >> 1) + (hq >> 1)) * (s.W >> 1) + (w >> 1)) * C;
+            }
+            float f[8];
+            if ((C & 3) == 0 && c0 + 8 <= C) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + c0));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + c0 + 4));
+                f[0] = v0.x; f[1] = v0.y; f[2] = v0.z; f[3] = v0.w; f[4] = v1.x; f[5] = v1.y; f[6] = v1.z; f[7] = v1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = c0 + e < C ? __ldg(src + c0 + e) : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float val = f[e];
+                if (c0 + e < C) {
+                    if (s.mu) {
+                        const long si = (long)n * c_tot + goff + c0 + e;
+                        val = fmaf(val - __ldg(s.mu + si), __ldg(s.a + si), __ldg(s.beta + goff + c0 + e));
+                    }
+                    val *= s.scale;
+                } else {
+                    val = 0.f;
+                }
+                uint32_t hv, lv;
+                split_f16(val, hv, lv);
+                h[e >> 1] |= hv << (16 * (e & 1));
+                l[e >> 1] |= lv << (16 * (e & 1));
+            }
+        }
+        s.hi[i] = make_uint4(h[0], h[1], h[2], h[3]);
+        s.lo[i] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// ------------------------------------------------------------------ weight image
+// [stage][(kd,kh) group][k step][hi|lo][K chunk][Npad rows][16 B]; a ring slot of the conv kernel = one group.
+// normal: k step = kw, K chunk c <-> channel chunk 2*stage + c.   pair (one channel chunk): k step 0 = taps
+// kw 0 (chunk 0) and kw 1 (chunk 1); k step 1 = tap kw 2 (chunk 0) and zeros.
+__global__ void __launch_bounds__(256) halo_weight_image_kernel(const float* __restrict__ w, int Cout, int C1, int C2, int Cp1,
+                                                                int Cp2, int Npad, int n_stages, int pair, float scale,
+                                                                uint8_t* __restrict__ img) {
+    const int kpg = pair ? 2 : 3, Cin = C1 + C2;
+    const long total = (long)n_stages * 9 * kpg * 2 * Npad;
+    const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    long t = gid;
+    const int n = (int)(t % Npad); t /= Npad;
+    const int kc = (int)(t % 2); t /= 2;
+    const int ks = (int)(t % kpg); t /= kpg;
+    const int g = (int)(t % 9);
+    const int st = (int)(t / 9);
+    int kw, cc;
+    if (pair) { kw = ks * 2 + kc; cc = 0; } else { kw = ks; cc = st * 2 + kc; }
+    uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+    if (n < Cout && kw < 3 && cc * 8 < Cp1 + Cp2) {
+        const int tap = g * 3 + kw;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int cs = cc * 8 + e;
+            int ci = -1;
+            if (cs < Cp1) { if (cs < C1) ci = cs; }
+            else if (cs - Cp1 < C2) ci = C1 + (cs - Cp1);
+            const float val = ci >= 0 ? w[((long)n * Cin + ci) * 27 + tap] * scale : 0.f;
+            uint32_t hv, lv;
+            split_f16(val, hv, lv);
+            hi[e >> 1] |= hv << (16 * (e & 1));
+            lo[e >> 1] |= lv << (16 * (e & 1));
+        }
+    }
+    const long blk = (long)Npad * 32;  // one (k step, hi|lo) operand block
+    uint8_t* base = img + (((long)(st * 9 + g) * kpg + ks) * 2) * blk + (long)kc * Npad * 16 + (long)n * 16;
+    *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + blk) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ------------------------------------------------------------------ the convolution
+struct HaloArgs {
+    const uint8_t *hi, *lo, *wimg;
+    const float* bias;
+    float* y;
+    int N, D, H, W, Hp, Wp;
+    long V, plane_slots;          // slots per haloed sample volume, slots per channel-chunk plane (N * V)
+    int Dt, Ht, Hs, G, stacked;   // item = G stacked whole samples, or a Dt x Ht x W slab of one sample
+    int n_dt, n_ht, Ls;           // slabs per sample; lines per stacked sample (Dp * Hp)
+    int lines, n_wblk, n_tiles, P;  // P = slots per staged plane (incl. over-read slack)
+    int S_st;                     // staged slots per plane that the bulk copies fill
+    int pair, n_stages, nbuf, ck, kpg;
+    int Cout, Npad, act, out_ncdhw, n_acc, n_iss;
+    float slope, out_scale;
+    uint32_t bslot_bytes, tmem_cols;
+    uint16_t tile_off[32];        // first slot of M tile t within the staged block (uniform-indexed constant loads)
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
+    const int planes = 2 * a.ck;
+    const uint32_t abuf_bytes = (uint32_t)planes * (uint32_t)a.P * 16u;
+    const uint32_t sA = base;
+    const uint32_t sB = sA + (uint32_t)a.nbuf * abuf_bytes;
+    const uint32_t bars = sB + NB * a.bslot_bytes;
+    const uint32_t bar_afull = bars, bar_aempty = bars + 8 * MAX_ABUF;
+    const uint32_t bar_bfull = bars + 16 * MAX_ABUF, bar_bempty = bar_bfull + 8 * NB;
+    const uint32_t bar_dfull = bar_bempty + 8 * NB;
+    const uint32_t tmem_slot = bar_dfull + 8;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp: uniform register
+
+    // ---- item geometry
+    int n0, gact, d0, h0;
+    if (a.stacked) {
+        n0 = blockIdx.x * a.G; gact = min(a.G, a.N - n0); d0 = 0; h0 = 0;
+    } else {
+        const int per = a.n_dt * a.n_ht;
+        n0 = blockIdx.x / per; gact = 1;
+        const int r = blockIdx.x % per;
+        d0 = (r / a.n_ht) * a.Dt; h0 = (r % a.n_ht) * a.Ht;
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.nbuf; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, a.n_iss); }
+        for (int s = 0; s < NB; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, a.n_iss); }
+        mbar_init(bar_dfull, a.n_iss);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // Zero what the bulk copies never fill (over-read slack, missing samples of a ragged last item): operand rows
+    // that touch it are dropped, but in pair mode a REAL row multiplies one such slot by a zero weight, and
+    // 0 * NaN would poison it.
+    {
+        const int filled = a.stacked ? gact * (int)a.V : a.S_st;
+        const int per_plane = a.P - filled;
+        const int total = a.nbuf * planes * per_plane;
+        for (int i = threadIdx.x; i < total; i += NTHREADS) {
+            const int pl = i / per_plane, o = i % per_plane;
+            *reinterpret_cast<uint4*>(smem_al + ((size_t)pl * a.P + filled + o) * 16) = make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+      if (lane == 0) {
+        // ---- activation producer: one stage = ck channel chunks x (hi, lo) planes of the item's haloed block
+        const long slab = (long)a.Hp * a.Wp;
+        // Two passes over the channel stages (cross products first, then hi * hi; see the issuers).  With a single
+        // stage the block stays resident and is loaded once.
+        const int n_loads = a.n_stages == 1 ? 1 : 2 * a.n_stages;
+        for (int l = 0; l < n_loads; ++l) {
+            const int s = l >= a.n_stages ? l - a.n_stages : l;
+            const int b = l % a.nbuf;
+            mbar_wait_relaxed(bar_aempty + 8 * b, ((uint32_t)(l / a.nbuf) & 1u) ^ 1u);
+            const bool one_copy = a.stacked || a.Ht == a.H;
+            const uint32_t plane_bytes = a.stacked ? (uint32_t)(gact * a.V) * 16u : (uint32_t)a.S_st * 16u;
+            mbar_arrive_expect_tx(bar_afull + 8 * b, plane_bytes * planes);
+            for (int pl = 0; pl < planes; ++pl) {
+                const int hl = pl / a.ck, c = pl % a.ck;
+                const long cc = (long)s * a.ck + c;
+                const uint8_t* src = (hl ? a.lo : a.hi) + (cc * a.plane_slots + (long)n0 * a.V) * 16;
+                const uint32_t dst = sA + b * abuf_bytes + (uint32_t)pl * (uint32_t)a.P * 16u;
+                if (one_copy) {
+                    bulk_g2s(dst, src + (long)d0 * slab * 16, plane_bytes, bar_afull + 8 * b);
+                } else {
+                    const uint32_t row_bytes = (uint32_t)(a.Hs * a.Wp) * 16u;
+                    for (int dd = 0; dd < a.Dt + 2; ++dd)
+                        bulk_g2s(dst + dd * row_bytes, src + ((long)(d0 + dd) * slab + (long)h0 * a.Wp) * 16, row_bytes,
+                                 bar_afull + 8 * b);
+                }
+            }
+        }
+      }
+    } else if (warp == 3) {
+      if (lane == 0) {
+        // ---- weight producer: ring of (kd,kh) groups
+        const int per_pass = a.n_stages * 9, total = 2 * per_pass;
+        for (int gi = 0; gi < total; ++gi) {
+            const int sl = gi % NB;
+            const int img = gi >= per_pass ? gi - per_pass : gi;  // second pass streams the same groups again
+            mbar_wait_relaxed(bar_bempty + 8 * sl, ((uint32_t)(gi / NB) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(bar_bfull + 8 * sl, a.bslot_bytes);
+            bulk_g2s(sB + sl * a.bslot_bytes, a.wimg + (long)img * a.bslot_bytes, a.bslot_bytes, bar_bfull + 8 * sl);
+        }
+      }
+    } else {
+        // ---- MMA issuers: warps 1, 2, 4, 5, 6, 7 -> issuer 0..5; issuer i owns the M tiles t = i (mod n_iss).
+        // One warp cannot feed the tensor pipe here: every tcgen05.mma needs its descriptors moved from vector to
+        // uniform registers (R2UR) under an elected lane, ~150 cycles per MMA measured, while the pipe needs 39-48
+        // cycles for an M128 K16 step with N <= 64.  Tiles are independent accumulators, so several warps issue
+        // concurrently (each warp's own MMAs stay ordered, which is all one accumulator needs); every issuer
+        // commits to the stage / ring / accumulator barriers, which count n_iss arrivals.
+        const int iss = warp <= 2 ? warp - 1 : warp - 2;
+        if (iss < a.n_iss) {
+            const uint32_t leader = elect_one();
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t idesc = idesc_f16(a.Npad);
+            // descriptor = {lo: start >> 4 | (LBO >> 4) << 16, hi: SBO >> 4 | version 1 << 14}; addresses advance in
+            // 16-byte units = slots, so "+ slots" on the low word moves the window.
+            const uint32_t a_hi32 = (a.lines ? (uint32_t)a.Wp : 8u) | (1u << 14);
+            const uint32_t a_lbo = (a.pair ? 1u : (uint32_t)a.P) << 16;
+            const uint32_t b_hi32 = 8u | (1u << 14);
+            const uint32_t b_lbo = (uint32_t)a.Npad << 16;
+            const uint32_t blk_u = (uint32_t)a.Npad * 2u;       // one (k step, hi|lo) weight block, in 16-byte units
+            const uint32_t lo_off = (uint32_t)(a.ck * a.P);     // hi -> lo plane, in slots
+            const uint32_t npad = (uint32_t)a.Npad;
+            // The tensor core truncates when it aligns the 16 products of a K step with the fp32 accumulator, a
+            // bias that grows with the number of accumulations at full magnitude (measured: error linear in the
+            // MMA count).  So the two small cross products (hi*lo, lo*hi: 2^-11 of the result) of ALL taps and
+            // stages are accumulated first, while the accumulator is tiny, and the hi*hi products in a second pass
+            // over the stages: a third of the accumulations happen at full magnitude.
+            const bool resident = a.n_stages == 1;
+            for (int vs = 0; vs < 2 * a.n_stages; ++vs) {
+                const int pass = vs >= a.n_stages ? 1 : 0;
+                const int b = resident ? 0 : vs % a.nbuf;
+                if (!resident || vs == 0) mbar_wait_warp(bar_afull + 8 * b, (uint32_t)(vs / a.nbuf) & 1u);
+                tc_fence_after();
+                const uint32_t abase = (((sA + b * abuf_bytes) & 0x3FFFFu) >> 4) | a_lbo;
+                for (int g = 0; g < 9; ++g) {
+                    const int gi = vs * 9 + g, sl = gi % NB;
+                    mbar_wait_warp(bar_bfull + 8 * sl, (uint32_t)(gi / NB) & 1u);
+                    tc_fence_after();
+                    const int kd = g / 3, kh = g % 3;
+                    const uint32_t bbase = (((sB + sl * a.bslot_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+                    for (int ks = 0; ks < a.kpg; ++ks) {
+                        const uint32_t koff = (uint32_t)((kd * a.Hs + kh) * a.Wp + (a.pair ? 2 * ks : ks));
+                        const uint32_t b_hi = bbase + (uint32_t)ks * 2u * blk_u, b_lo = b_hi + blk_u;
+                        const uint32_t acc = (vs | g | ks) ? 1u : 0u;  // the very first MMA of a tile overwrites its accumulator
+                        for (int t = iss; t < a.n_tiles; t += a.n_iss) {
+                            const uint32_t d = tmem_u + (uint32_t)t * npad;
+                            const uint32_t da = abase + koff + a.tile_off[t];
+                            if (pass == 0) {
+                                tc_mma2(d, da, a_hi32, b_lo, b_hi32, idesc, acc, leader);          // hi * lo
+                                tc_mma2(d, da + lo_off, a_hi32, b_hi, b_hi32, idesc, 1u, leader);  // lo * hi
+                            } else {
+                                tc_mma2(d, da, a_hi32, b_hi, b_hi32, idesc, 1u, leader);           // hi * hi
+                            }
+                        }
+                    }
+                    if (leader) tc_commit(bar_bempty + 8 * sl);
+                }
+                if (!resident && leader) tc_commit(bar_aempty + 8 * b);
+            }
+            if (leader) tc_commit(bar_dfull);
+            __syncwarp();
+            if (iss == 0) mbar_wait_warp(bar_dfull, 0);  // the only warp that polls; all others sleep in the barrier below
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ---- epilogue (all 8 warps): warp % 4 = TMEM lane quadrant, warp / 4 = tile parity
+    tc_fence_after();
+    {
+        const int q = warp & 3;
+        const long So = (long)a.D * a.H * a.W;
+        const bool vec4 = !a.out_ncdhw && (a.Cout & 3) == 0;
+        for (int t = warp >> 2; t < a.n_tiles; t += 2) {
+            const int r = q * 32 + lane;
+            int line, w;
+            if (a.lines) {
+                line = (t / a.n_wblk) * 16 + (r >> 3);
+                w = (t % a.n_wblk) * 8 + (r & 7);
+            } else {
+                const int R = t * 128 + r;
+                line = R / a.Wp; w = R % a.Wp;
+            }
+            const int g = a.stacked ? line / a.Ls : 0;
+            const int rem = a.stacked ? line % a.Ls : line;
+            const int dd = rem / a.Hs, hh = rem % a.Hs;
+            const bool valid = g < gact && dd < a.Dt && hh < a.Ht && w < a.W;
+            const long vox = valid ? ((((long)(n0 + g) * a.D + d0 + dd) * a.H + h0 + hh) * a.W + w) : 0;
+            for (int c0 = 0; c0 < a.Npad; c0 += 16) {
+                float v[16];
+                tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * a.Npad + c0), v);
+                for (int set = 1; set < a.n_acc; ++set) {
+                    float u[16];
+                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((set * a.n_tiles + t) * a.Npad + c0), u);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] += u[e];
+                }
+                if (!valid) continue;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int co = c0 + e;
+                    const float bb = (a.bias && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
+                    v[e] = rf_act(fmaf(v[e], a.out_scale, bb), a.act, a.slope);
+                }
+                if (vec4) {
+                    float* dst = a.y + vox * a.Cout + c0;
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4)
+                        if (c0 + e < a.Cout) *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                } else if (a.out_ncdhw) {
+                    const long nn = vox / So, sp = vox % So;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (c0 + e < a.Cout) a.y[(nn * a.Cout + c0 + e) * So + sp] = v[e];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (c0 + e < a.Cout) a.y[vox * a.Cout + c0 + e] = v[e];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+    }
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct Geo {
+    int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, n_acc;
+    uint32_t tmem_cols, bslot;
+    size_t smem;
+    double score;
+};
+
+// Chooses the item shape: maximise (real outputs / computed GEMM rows), penalise grids that leave SMs idle.
+bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, Geo& best) {
+    const int Dp = D + 2, Hp = H + 2, Wp = W + 2;
+    const long V = (long)Dp * Hp * Wp;
+    const int ck = pair ? 1 : 2, planes = 2 * ck, kpg = pair ? 2 : 3;
+    const int n_stages = pair ? 1 : CCe / 2, nbuf = n_stages < 2 ? 1 : 2;
+    const uint32_t bslot = (uint32_t)kpg * 2u * (uint32_t)Npad * 32u;
+    const long avail = (long)SMEM_LIMIT - 1024 - 256 - (long)NB * bslot;
+    best.score = -1.0;
+    auto consider = [&](int stacked, int G, int Dt, int Ht, int lines) {
+        if (lines && W % 8 != 0) return;
+        const int Hs = stacked ? Hp : Ht + 2;
+        const long S_st = stacked ? (long)G * V : (long)(Dt + 2) * Hs * Wp;
+        const long lines_needed = stacked ? (long)(G - 1) * Dp * Hp + (long)(D - 1) * Hp + H : (long)(Dt - 1) * Hs + Ht;
+        long n_tiles, max_slot;
+        const int n_wblk = lines ? W / 8 : 1;
+        if (lines) {
+            const long lb = (lines_needed + 15) / 16;
+            n_tiles = lb * n_wblk;
+            max_slot = (lb * 16 - 1 + 2L * Hs + 2) * Wp + (W - 1) + 2 + 1;
+        } else {
+            const long rows = (lines_needed - 1) * Wp + W;
+            n_tiles = (rows + 127) / 128;
+            max_slot = n_tiles * 128 - 1 + 2L * Hs * Wp + 2L * Wp + 2 + 1;
+        }
+        long P = max_slot + 1 > S_st ? max_slot + 1 : S_st;
+        P = (P + 7) / 8 * 8;
+        if (n_tiles * Npad > 512 || P * 16 >= (1L << 18)) return;
+        const long smemA = (long)nbuf * planes * P * 16;
+        if (smemA > avail || S_st * 16 * planes >= (1L << 20)) return;
+        const long outputs = stacked ? (long)G * D * H * W : (long)Dt * Ht * W;
+        const long n_items = stacked ? (N + G - 1) / G : (long)N * (D / Dt) * (H / Ht);
+        // cost model: ~34 cycles per 128-row MMA (operand reads from shared memory bound it, not N) plus a
+        // per-item prologue / epilogue that only overlaps with another CTA's MMAs when two CTAs fit on an SM
+        const int n_acc = 1;  // accumulator sets per tile (summed in the epilogue); one is enough, see mma_pattern.cu
+        uint32_t cols_needed = 32;
+        while ((long)cols_needed < n_tiles * Npad * n_acc) cols_needed <<= 1;
+        const long smem_total = 1024 + smemA + (long)NB * bslot + 256;
+        const bool two_resident = smem_total <= 113 * 1024 && cols_needed <= 256;
+        const double n_mma = (double)n_stages * 9 * kpg * (double)n_tiles * 3.0;
+        const double t_item = n_mma * 34.0 + (two_resident ? 1500.0 : 5000.0);
+        const double fill = n_items >= 148 ? 1.0 : (double)n_items / 148.0;
+        const double score = (double)outputs / t_item * fill;
+        if (score > best.score) {
+            best.Dt = stacked ? D : Dt; best.Ht = stacked ? H : Ht; best.Hs = Hs; best.G = stacked ? G : 1; best.stacked = stacked;
+            best.lines = lines; best.n_wblk = n_wblk; best.n_tiles = (int)n_tiles; best.P = (int)P; best.S_st = (int)S_st;
+            best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot;
+            best.tmem_cols = cols_needed;
+            best.n_acc = n_acc;
+            best.smem = (size_t)(1024 + smemA + (long)NB * bslot + 256);
+            best.score = score;
+        }
+    };
+    for (int lines = 0; lines < 2; ++lines) {
+        for (int G = 1; G <= 64 && G <= N; ++G) consider(1, G, D, H, lines);
+        for (int Dt = 1; Dt <= D; ++Dt) {
+            if (D % Dt) continue;
+            for (int Ht = 1; Ht <= H; ++Ht) {
+                if (H % Ht) continue;
+                consider(0, 1, Dt, Ht, lines);
+            }
+        }
+    }
+    return best.score > 0.0;
+}
+
+bool halo_shape(int Cout, int C1, int C2, int& Cp1, int& Cp2, int& CC, int& CCe, int& pair, int& Npad) {
+    if (Cout < 1 || Cout > 256 || C1 < 0 || C2 < 0 || C1 + C2 < 1) return false;
+    Cp1 = round_up(C1, 8); Cp2 = round_up(C2, 8);
+    CC = (Cp1 + Cp2) / 8;
+    pair = CC == 1;
+    CCe = pair ? 1 : round_up(CC, 2);
+    Npad = round_up(Cout, 16);
+    return true;
+}
+
+}  // namespace
+
+extern "C" size_t rf_halo_act_bytes(int N, int D, int H, int W, int C1, int C2) {
+    int Cp1, Cp2, CC, CCe, pair, Npad;
+    if (!halo_shape(16, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad) || N < 1 || D < 1 || H < 1 || W < 1) return 0;
+    return (size_t)CCe * N * (size_t)(D + 2) * (H + 2) * (W + 2) * 16;
+}
+
+extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a,
+                                     const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, float scale,
+                                     void* stream) {
+    int Cp1, Cp2, CC, CCe, pair, Npad;
+    RF_CHECK_ARG(halo_shape(16, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad), "rf_cl_norm_split_halo: bad channel counts");
+    RF_CHECK_ARG(hi && lo && (C1 == 0 || x) && (C2 == 0 || x2) && N > 0 && D > 0 && H > 0 && W > 0, "rf_cl_norm_split_halo: bad arguments");
+    RF_CHECK_ARG(C2 == 0 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "rf_cl_norm_split_halo: upsampled input needs even extents");
+    RF_CHECK_ARG((gn_mu == nullptr) == (gn_a == nullptr) && (gn_mu == nullptr) == (gn_beta == nullptr), "rf_cl_norm_split_halo: partial GroupNorm arguments");
+    RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)x2 & 15) == 0,
+                 "rf_cl_norm_split_halo: pointers must be 16-byte aligned");
+    SplitArgs s;
+    s.x = x; s.x2 = x2; s.mu = gn_mu; s.a = gn_a; s.beta = gn_beta; s.hi = (uint4*)hi; s.lo = (uint4*)lo;
+    s.N = N; s.D = D; s.H = H; s.W = W; s.C1 = C1; s.C2 = C2; s.CC1 = Cp1 / 8; s.CC = CC; s.CCe = CCe; s.scale = scale;
+    const long total = (long)CCe * N * (long)(D + 2) * (H + 2) * (W + 2);
+    cl_norm_split_halo_kernel<<<rf_grid_1d(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(s);
+    RF_LAUNCH_OK("cl_norm_split_halo_kernel");
+    return 0;
+}
+
+extern "C" size_t rf_tc_conv_halo_weight_image_bytes(int Cout, int C1, int C2) {
+    int Cp1, Cp2, CC, CCe, pair, Npad;
+    if (!halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad)) return 0;
+    const int n_stages = pair ? 1 : CCe / 2, kpg = pair ? 2 : 3;
+    return (size_t)n_stages * 9 * kpg * 2 * Npad * 32;
+}
+
+extern "C" int rf_tc_conv_halo_weight_image(const float* w, int Cout, int C1, int C2, float scale, void* image, void* stream) {
+    int Cp1, Cp2, CC, CCe, pair, Npad;
+    RF_CHECK_ARG(w && image, "rf_tc_conv_halo_weight_image: null pointer");
+    RF_CHECK_ARG(halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad), "rf_tc_conv_halo_weight_image: unsupported shape");
+    RF_CHECK_ARG(((uintptr_t)image & 15) == 0, "rf_tc_conv_halo_weight_image: image must be 16-byte aligned");
+    const int n_stages = pair ? 1 : CCe / 2, kpg = pair ? 2 : 3;
+    const long threads = (long)n_stages * 9 * kpg * 2 * Npad;
+    halo_weight_image_kernel<<<(unsigned)rf_cdivl(threads, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, C1, C2, Cp1, Cp2, Npad, n_stages,
+                                                                                                pair, scale, (uint8_t*)image);
+    RF_LAUNCH_OK("halo_weight_image_kernel");
+    return 0;
+}
+
+/* 1 when rf_tc_conv3d_halo_fwd can run this layer (an item shape fits shared memory and TMEM). */
+extern "C" int rf_tc_conv3d_halo_supported(int N, int D, int H, int W, int Cout, int C1, int C2) {
+    int Cp1, Cp2, CC, CCe, pair, Npad;
+    if (!halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad) || N < 1 || D < 1 || H < 1 || W < 1) return 0;
+    if ((long)N * (D + 2) * (H + 2) * (W + 2) * CCe >= (1L << 31)) return 0;
+    Geo g;
+    return choose_geometry(N, D, H, W, CCe, pair, Npad, g) ? 1 : 0;
+}
+
+extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y,
+                                     int N, int D, int H, int W, int Cout, int C1, int C2, int act, float slope,
+                                     float out_scale, int out_ncdhw, void* stream) {
+    RF_CHECK_ARG(hi && lo && weight_image && y, "rf_tc_conv3d_halo_fwd: null pointer");
+    int Cp1, Cp2, CC, CCe, pair, Npad;
+    RF_CHECK_ARG(halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad) && N > 0 && D > 0 && H > 0 && W > 0,
+                 "rf_tc_conv3d_halo_fwd: unsupported shape Cout=%d C1=%d C2=%d", Cout, C1, C2);
+    RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)weight_image & 15) == 0 && ((uintptr_t)y & 15) == 0,
+                 "rf_tc_conv3d_halo_fwd: pointers must be 16-byte aligned");
+    Geo g;
+    RF_CHECK_ARG(choose_geometry(N, D, H, W, CCe, pair, Npad, g), "rf_tc_conv3d_halo_fwd: no item shape fits (N=%d D=%d H=%d W=%d Cout=%d C=%d+%d)",
+                 N, D, H, W, Cout, C1, C2);
+    HaloArgs a;
+    a.hi = (const uint8_t*)hi; a.lo = (const uint8_t*)lo; a.wimg = (const uint8_t*)weight_image; a.bias = bias; a.y = y;
+    a.N = N; a.D = D; a.H = H; a.W = W; a.Hp = H + 2; a.Wp = W + 2;
+    a.V = (long)(D + 2) * (H + 2) * (W + 2); a.plane_slots = (long)N * a.V;
+    a.Dt = g.Dt; a.Ht = g.Ht; a.Hs = g.Hs; a.G = g.G; a.stacked = g.stacked;
+    a.n_dt = D / g.Dt; a.n_ht = H / g.Ht; a.Ls = (D + 2) * (H + 2);
+    a.lines = g.lines; a.n_wblk = g.n_wblk; a.n_tiles = g.n_tiles; a.P = g.P; a.S_st = g.S_st;
+    a.pair = pair; a.n_stages = pair ? 1 : CCe / 2; a.nbuf = g.nbuf; a.ck = pair ? 1 : 2; a.kpg = pair ? 2 : 3;
+    a.Cout = Cout; a.Npad = Npad; a.act = act; a.out_ncdhw = out_ncdhw; a.slope = slope; a.out_scale = out_scale;
+    a.bslot_bytes = g.bslot; a.tmem_cols = g.tmem_cols; a.n_acc = g.n_acc;
+    a.n_iss = g.n_tiles < 6 ? g.n_tiles : 6;
+    // tile t = lb * n_wblk + wb starts at slot lb * (16 lines) + wb * 8 (linear mode: n_wblk = 1, 128 slots per tile)
+    RF_CHECK_ARG(g.n_tiles <= 32, "rf_tc_conv3d_halo_fwd: internal: more than 32 M tiles");
+    for (int t = 0; t < 32; ++t) {
+        const long off = g.lines ? (long)(t / g.n_wblk) * 16 * a.Wp + (t % g.n_wblk) * 8 : (long)t * 128;
+        a.tile_off[t] = (uint16_t)(t < g.n_tiles ? off : 0);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        RF_CUDA_OK(cudaFuncSetAttribute(tc_conv3d_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        attr_set = true;
+    }
+    tc_conv3d_halo_kernel<<<(unsigned)g.n_items, NTHREADS, g.smem, (cudaStream_t)stream>>>(a);
+    RF_LAUNCH_OK("tc_conv3d_halo_kernel");
+    return 0;
+}
+
+/* Debug / test aid: the item shape the chooser picks (returns 0 when unsupported). */
+extern "C" int rf_tc_conv3d_halo_geometry(int N, int D, int H, int W, int Cout, int C1, int C2, int* out8) {
+    int Cp1, Cp2, CC, CCe, pair, Npad;
+    if (!halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad)) return 0;
+    Geo g;
+    if (!choose_geometry(N, D, H, W, CCe, pair, Npad, g)) return 0;
+    out8[0] = g.stacked; out8[1] = g.G; out8[2] = g.Dt; out8[3] = g.Ht; out8[4] = g.lines; out8[5] = g.n_tiles;
+    out8[6] = g.n_items; out8[7] = (int)g.smem;
+    return 1;
+}

@@ -14,6 +14,8 @@ from ._base import RfModule
 # Tensor-core path: channels-last activations, GroupNorm applied once per element, implicit-GEMM
 # convolutions on tcgen05 with a fp16 hi/lo split (~2e-7 relative per layer).  False: fp32 FMA kernels.
 USE_TENSOR_CORES = True
+# 3x3x3 layers: shifted-window kernel (rf_tc_conv_halo.cu) instead of the gathering implicit GEMM (rf_tc_conv.cu)
+USE_HALO_CONV = True
 
 
 def number_of_features_per_level(init_channel_number, num_levels):
@@ -80,6 +82,14 @@ class SingleConv(RfModule):
             return ops.conv3d_cin1_cl(x, self.conv.weight, self.conv.bias, (mu, a, g.bias), ks=3, stride=1, pad=1,
                                       act=self.act, slope=0.1)
         sa = ops.ACT_SCALE_GN
+        N, D, H, W = x.shape[:4] if x is not None else (x2.shape[0], 2 * x2.shape[1], 2 * x2.shape[2], 2 * x2.shape[3])
+        if USE_HALO_CONV and ops.tc_conv_halo_supported(N, D, H, W, self.out_channels, c1, c2):
+            # shifted-window kernel: activations staged in shared memory once, all 27 taps addressed in place
+            split = ops.cl_norm_split_halo(x, x2, (mu, a, g.bias), scale=sa)
+            img, sw = self._wcache.derived(("halo", c1, c2), [self.conv.weight],
+                                           lambda w: ops.tc_conv_halo_weight_image(w, c1, c2))
+            return ops.tc_conv3d_halo(split, img, self.conv.bias, self.out_channels, act=self.act, slope=0.1,
+                                      out_ncdhw=out_ncdhw, out_scale=1.0 / (sa * sw))
         xs = ops.cl_norm_split(x, (mu, a, g.bias), 0, scale=sa) if x is not None else None
         x2s = ops.cl_norm_split(x2, (mu, a, g.bias), c1, scale=sa) if x2 is not None else None
         img, sw = self._wcache.derived(("tcconv", c1, c2), [self.conv.weight], lambda w: ops.tc_conv_weight_image(w, c1, c2))

@@ -6,6 +6,7 @@ Every function launches the hand-written sm_100a kernels through ctypes on
 """
 from __future__ import annotations
 
+import ctypes
 import math
 
 import torch
@@ -353,6 +354,78 @@ def tc_conv3d(xs, x2s, c1, c2, img, bias, cout, ks, stride=1, pad=0, act=ACT_NON
         check(_lib.lib().rf_tc_conv3d_fwd(xh, xl, c1, x2h, x2l, c2, img.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W, cout,
                                           ks, stride, pad, act, float(slope), float(out_scale), int(bool(out_ncdhw)),
                                           torch.cuda.current_stream(dev).cuda_stream), "rf_tc_conv3d_fwd")
+    _count()
+    return y
+
+
+# ---- shifted-window ("halo") tensor-core convolution: 3x3x3, stride 1, pad 1 -------------------
+
+def tc_conv_halo_supported(N, D, H, W, cout, c1, c2):
+    return bool(_lib.lib().rf_tc_conv3d_halo_supported(int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2)))
+
+
+def tc_conv_halo_geometry(N, D, H, W, cout, c1, c2):
+    """Item shape the kernel picks: dict(stacked, G, Dt, Ht, lines, n_tiles, n_items, smem) or None."""
+    out = (ctypes.c_int * 8)()
+    if not _lib.lib().rf_tc_conv3d_halo_geometry(int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2), out):
+        return None
+    return dict(zip(["stacked", "G", "Dt", "Ht", "lines", "n_tiles", "n_items", "smem"], list(out)))
+
+
+def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0):
+    """fp32 channels-last x [N,D,H,W,C1] (or None) and half-resolution x2 [N,D/2,H/2,W/2,C2] (or None) ->
+    (hi, lo) fp16 slot planes [chunk][N][D+2][H+2][W+2][8] of scale * GroupNorm(concat(x, up2(x2))), zero halo."""
+    src = x if x is not None else x2
+    src = _dev(src, name="x")
+    c1 = x.shape[-1] if x is not None else 0
+    c2 = x2.shape[-1] if x2 is not None else 0
+    if x is not None:
+        N, D, H, W = x.shape[:4]
+    else:
+        N, D, H, W = x2.shape[0], 2 * x2.shape[1], 2 * x2.shape[2], 2 * x2.shape[3]
+    L = _lib.lib()
+    nbytes = L.rf_halo_act_bytes(N, D, H, W, c1, c2)
+    if nbytes == 0:
+        raise _lib.RfError(f"halo layout does not support C={c1}+{c2}")
+    hi = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
+    lo = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
+    mu, a, beta = gn if gn is not None else (None, None, None)
+    with torch.cuda.device(src.device):
+        check(L.rf_cl_norm_split_halo(_ptr(x), c1, _ptr(x2), c2, _ptr(mu), _ptr(a), _ptr(beta), hi.data_ptr(), lo.data_ptr(),
+                                      N, D, H, W, float(scale), _stream(src)), "rf_cl_norm_split_halo")
+    _count()
+    return hi, lo, (N, D, H, W, c1, c2)
+
+
+def tc_conv_halo_weight_image(weight, c1, c2):
+    """Conv3d weight [Cout, C1+C2, 3,3,3] -> (pre-split fp16 operand image for rf_tc_conv3d_halo_fwd, weight scale)."""
+    weight = _dev(weight.detach(), name="weight")
+    assert tuple(weight.shape[2:]) == (3, 3, 3) and weight.shape[1] == c1 + c2
+    wmax = float(weight.abs().max())
+    scale = 2.0 ** (4 - math.floor(math.log2(wmax))) if wmax > 0 and math.isfinite(wmax) else 1.0
+    scale = min(max(scale, 2.0 ** -8), 2.0 ** 24)
+    cout = weight.shape[0]
+    L = _lib.lib()
+    nbytes = L.rf_tc_conv_halo_weight_image_bytes(cout, c1, c2)
+    if nbytes == 0:
+        raise _lib.RfError(f"halo conv does not support weight {tuple(weight.shape)}")
+    img = _aligned_bytes(nbytes, weight.device)
+    with torch.cuda.device(weight.device):
+        check(L.rf_tc_conv_halo_weight_image(weight.data_ptr(), cout, c1, c2, scale, img.data_ptr(), _stream(weight)),
+              "rf_tc_conv_halo_weight_image")
+    _count()
+    return img, scale
+
+
+def tc_conv3d_halo(split, img, bias, cout, act=ACT_NONE, slope=0.0, out_ncdhw=False, out_scale=1.0):
+    """split = cl_norm_split_halo(...) result.  Returns fp32 channels-last [N,D,H,W,Cout] or NCDHW."""
+    hi, lo, (N, D, H, W, c1, c2) = split
+    shape = (N, cout, D, H, W) if out_ncdhw else (N, D, H, W, cout)
+    y = torch.empty(shape, device=hi.device, dtype=torch.float32)
+    with torch.cuda.device(hi.device):
+        check(_lib.lib().rf_tc_conv3d_halo_fwd(hi.data_ptr(), lo.data_ptr(), img.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W,
+                                               cout, c1, c2, act, float(slope), float(out_scale), int(bool(out_ncdhw)),
+                                               torch.cuda.current_stream(hi.device).cuda_stream), "rf_tc_conv3d_halo_fwd")
     _count()
     return y
 
