@@ -54,7 +54,7 @@ def full(rep, out):
             d = dict(zip(hdr, vals))
             f.write(f"## {d.get('Kernel Name', '?')}\n")
             for i, h in enumerate(hdr):
-                if h in KEYS:
+                if h in KEYS or 'pipe_tensor_cycles_active' in h or 'subpipe_hmma_cycles_active' in h:
                     f.write(f"{h:80s} {vals[i]:>18s} {units[i]}\n")
             f.write("\n")
         srows = list(csv.reader(src.splitlines()))

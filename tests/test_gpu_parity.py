@@ -148,6 +148,49 @@ def test_tc_linear(dev, M, K, N, act):
     assert (y - y32).abs().max().item() <= 1e-4 * max(1.0, float(ref.abs().max()))
 
 
+# (N, S, C1, C2, Cout, out_ncdhw): every item geometry of rf_tc_conv_halo.cu - "lines" and "linear" row modes, whole
+# stacked samples (ragged last item), d/h slabs, the single-chunk tap-pairing mode, odd chunk counts, Npad 128
+HALO_CASES = [(5, 8, 16, 0, 32, 0), (3, 8, 32, 64, 56, 0), (7, 4, 64, 128, 64, 0), (3, 16, 8, 0, 16, 0), (2, 8, 56, 0, 16, 1),
+              (9, 2, 64, 0, 128, 0), (1, 32, 0, 16, 16, 1), (2, 16, 12, 24, 24, 0), (300, 8, 16, 0, 32, 0), (301, 4, 32, 0, 32, 0)]
+
+
+@pytest.mark.parametrize("N,S,C1,C2,Cout,ncdhw", HALO_CASES)
+def test_shifted_window_conv(dev, N, S, C1, C2, Cout, ncdhw):
+    """model/unet.py:79-100 SingleConv 'gcr' (GroupNorm -> Conv3d k3 p1 -> ReLU) on concat(x, up2(x2)) through the
+    shifted-window tcgen05 kernel, against the oracle's restatement (torch CPU fp32) and an fp64 evaluation of it."""
+    from retrieval_fuse_b200 import ops
+    g = torch.Generator().manual_seed(N + 7 * S + C1 + C2 + Cout)
+    C = C1 + C2
+    x = torch.randn(N, C1, S, S, S, generator=g) * 1.5 + 0.3 if C1 else None
+    x2 = torch.randn(N, C2, S // 2, S // 2, S // 2, generator=g) * 0.7 - 0.2 if C2 else None
+    if N > 1 and C1:
+        x[1] = 0.25  # a constant sample: GroupNorm variance 0 (the all-trunc patch / database sentinel case)
+    sd = {"c.groupnorm.weight": torch.rand(C, generator=g) + 0.5, "c.groupnorm.bias": torch.randn(C, generator=g) * 0.1,
+          "c.conv.weight": torch.randn(Cout, C, 3, 3, 3, generator=g) / (27 * C) ** 0.5}
+    parts = ([x] if C1 else []) + ([torch.nn.functional.interpolate(x2, scale_factor=2, mode="nearest")] if C2 else [])
+    xc = torch.cat(parts, 1)
+    groups = 8 if C % 8 == 0 else 1
+    n_ref = min(N, 6)  # the oracle is a CPU conv: check the first samples and the last (ragged) item
+    sel = list(range(n_ref)) + ([N - 1] if N > n_ref else [])
+    ref32 = O._single_conv(xc[sel], sd, "c", "gcr", groups)
+    ref64 = O._single_conv(xc[sel].double(), {k: v.double() for k, v in sd.items()}, "c", "gcr", groups)
+    assert ops.tc_conv_halo_supported(N, S, S, S, Cout, C1, C2)
+    xd = x.permute(0, 2, 3, 4, 1).contiguous().to(dev) if C1 else None
+    x2d = x2.permute(0, 2, 3, 4, 1).contiguous().to(dev) if C2 else None
+    gamma, beta, w = sd["c.groupnorm.weight"].to(dev), sd["c.groupnorm.bias"].to(dev), sd["c.conv.weight"].to(dev)
+    mu, a = ops.cl_gn_stats(xd, gamma, groups, 1e-5, x2=x2d) if C1 else ops.cl_gn_stats(x2d, gamma, groups, 1e-5)
+    sa = ops.ACT_SCALE_GN
+    img, sw = ops.tc_conv_halo_weight_image(w, C1, C2)
+    y = ops.tc_conv3d_halo(ops.cl_norm_split_halo(xd, x2d, (mu, a, beta), scale=sa), img, None, Cout, act=ops.ACT_RELU,
+                           out_ncdhw=bool(ncdhw), out_scale=1.0 / (sa * sw))
+    y = (y if ncdhw else y.permute(0, 4, 1, 2, 3)).cpu()[sel]
+    scale = max(1.0, float(ref64.abs().max()))
+    err64 = float((y.double() - ref64).abs().max())
+    noise = float((ref32.double() - ref64).abs().max())
+    assert err64 <= 2e-5 * scale, f"|ours - fp64| {err64:.2e} (reference fp32 noise {noise:.2e}, scale {scale:.1f})"
+    close(y, ref32, rel_to_max=True, what="shifted-window conv vs oracle")
+
+
 @pytest.mark.parametrize("cls,nf,n", [("Patch32", 8, 40), ("Patch08", 16, 300), ("Patch24", 12, 17), ("PCPatch48", 10, 9)])
 def test_conv_encoders_tensor_core_path(dev, cls, nf, n):
     """Batches large enough for the tcgen05 implicit-GEMM path, against the oracle and the fp32 FMA path."""

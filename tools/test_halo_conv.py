@@ -130,6 +130,9 @@ def run(case, check=True, old=True):
 
 
 if __name__ == "__main__":
+    if "--case" in sys.argv:  # one shape, no checks: the ncu target (profiles/*_halo_conv_*.txt)
+        run(tuple(int(v) for v in sys.argv[sys.argv.index("--case") + 1].split(",")), check=False, old=False)
+        sys.exit(0)
     quick = "--quick" in sys.argv
     t0 = time.time()
     for c in CASES:
