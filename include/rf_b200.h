@@ -102,6 +102,20 @@ int rf_tc_weight_image(const float* w, int N, int K, void* image, void* stream);
 int rf_tc_linear_fwd(const float* x, int ldx, const void* weight_image, const float* bias, float* y, long M, int K, int N,
                      int act, float slope, void* stream);
 
+/* Fused MLP chain on tcgen05 (model/retrieval.py:64-133 Patch04 / Patch05 / Patch04V2 forward +
+ * util/retrieval.py:66 normalisation; model/attention.py:29-46 AttentionFeatureEncoder): all layers of
+ * y = L_n(act(... act(L_1 x))) in ONE launch, hidden activations never leave the SM (fp16 hi/lo operand
+ * planes in shared memory, fp32 accumulators in TMEM).  widths_host[0..n_layers] are the layer widths
+ * (each <= 512, widths[0] <= 256, no two consecutive hidden widths above 256); images_host[l] is the operand
+ * image of layer l's nn.Linear weight [widths[l+1], widths[l]] (rf_tc_mlp_weight_image); `act`/`slope` apply
+ * between layers (not after the last); l2_normalize divides output rows by max(|row|, eps). */
+int rf_tc_mlp_supported(const int* widths_host, int n_layers);
+size_t rf_tc_mlp_weight_image_bytes(int N, int K);
+int rf_tc_mlp_weight_image(const float* w, int N, int K, void* image, void* stream);
+int rf_tc_mlp_fwd(const float* x, int ldx, const void* const* images_host, const float* const* bias_host,
+                  const int* widths_host, int n_layers, int act, float slope, int l2_normalize, float eps, float* y, int ldy,
+                  long M, void* stream);
+
 /* Tensor-core 3D convolution on channels-last activations (U-Net 'gcr' blocks,
  * conv patch encoders).  One SingleConv = rf_cl_gn_stats -> rf_cl_norm_split
  * (normalise once, split to fp16 hi/lo, pad channels to 8) -> rf_tc_conv3d_fwd

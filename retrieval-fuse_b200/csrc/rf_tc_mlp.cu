@@ -1,0 +1,490 @@
+// Fused MLP chain on tcgen05: y = L_n(act(... act(L_1(x)))) for 128-row tiles with every hidden activation
+// kept on chip (model/retrieval.py:64-133 Patch04 / Patch05 / Patch04V2 query encoders + util/retrieval.py:66
+// normalisation; model/attention.py:29-46 AttentionFeatureEncoder theta / phi).
+//
+// rf_tc_linear_fwd runs one layer per launch: every hidden activation makes an HBM round trip as fp32, each
+// launch is a serial load -> MMA -> store pipeline per CTA, and its single-thread MMA issue costs more than the
+// MMAs.  Here one persistent CTA per SM walks over row tiles:
+//   * the layer input lives in shared memory as fp16 hi / lo planes in the no-swizzle K-major UMMA layout
+//     [8-channel chunk][row 0..127][16 B] (LBO = one chunk plane = 2 KiB, SBO = 128 B), at most 256 channels at
+//     a time; wider inputs (the 512-wide hidden layer of Patch04) are consumed in slabs of 256 channels, converted
+//     from TMEM slab by slab while the next layer accumulates into the columns already freed;
+//   * weights stream through a ring of [k step] blocks ([hi|lo][2 chunks][Np rows][16 B], one cp.async.bulk
+//     each) issued by a dedicated producer warp that runs ahead across layers and tiles;
+//   * up to four issuer warps own 128 accumulator columns each (several warps must issue: one warp cannot feed
+//     the tensor pipe, see rf_tc_conv_halo.cu); fp16 hi/lo split, three products per k step, cross products
+//     first, fp32 accumulators in TMEM (512 columns = one layer's full output);
+//   * the layer epilogue (all 8 worker warps) reads TMEM, adds bias, applies the activation, splits to fp16
+//     hi / lo and writes the next layer's operand planes; the last layer optionally L2-normalises rows and
+//     writes fp32 output.
+#include <cuda_fp16.h>
+
+#include "rf_common.cuh"
+
+namespace {
+
+constexpr int TM = 128, WORKERS = 256, NTHREADS = 288, MAX_LAYERS = 8, MAX_SLOTS = 8;
+constexpr int PLANE = TM * 16;             // one 8-channel chunk plane: 128 rows x 16 B
+constexpr int ACT_CHUNKS = 32;             // 256 channels resident
+constexpr int ACT_BYTES = ACT_CHUNKS * PLANE;  // 64 KiB per hi / lo
+constexpr int SMEM_LIMIT = 232448;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// whole-warp wait with a warp-uniform loop condition (keeps the issue loop on the uniform datapath)
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if (++spins > (1u << 26)) __trap();  // a pipeline bug must never hang the GPU
+    }
+}
+// same, polling gently: used while MMAs run (hundreds to thousands of cycles), by all worker warps at once
+__device__ __forceinline__ void mbar_wait_warp_sleepy(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        __nanosleep(40);
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        __nanosleep(100);
+        if (spins > (1u << 23)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// descriptors as (low, high) words; `issue` predicates the MMA inside the asm block (see rf_tc_conv_halo.cu)
+__device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t acc, uint32_t issue) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc), "r"(issue)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t idesc_f16(int n) {  // D f32, A/B f16, both K-major, N>>3 @17, M>>4 @24
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void split_f16(float x, uint32_t& hi, uint32_t& lo) {
+    const __half h = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+    const __half l = __float2half_rn(x - __half2float(h));
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
+}
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// W [N, K] fp32 row-major (nn.Linear.weight) -> [k step][hi|lo][chunk 0|1][Np rows][16 B]
+__global__ void __launch_bounds__(256) mlp_weight_image_kernel(const float* __restrict__ w, int N, int K, int Np, int Kp,
+                                                               uint8_t* __restrict__ img) {
+    const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const long total = (long)(Kp / 16) * 2 * Np;
+    if (gid >= total) return;
+    const int n = (int)(gid % Np);
+    const int kc = (int)((gid / Np) % 2);
+    const int j = (int)(gid / (2L * Np));
+    uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+    if (n < N) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = j * 16 + kc * 8 + e;
+            uint32_t hv, lv;
+            split_f16(k < K ? w[(long)n * K + k] : 0.f, hv, lv);
+            hi[e >> 1] |= hv << (16 * (e & 1));
+            lo[e >> 1] |= lv << (16 * (e & 1));
+        }
+    }
+    uint8_t* base = img + (long)j * (64L * Np) + (long)kc * Np * 16 + (long)n * 16;
+    *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + 32L * Np) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+struct MlpArgs {
+    const float* x;
+    float* y;
+    long M;
+    int ldx, ldy, n_layers, K0, K0p;
+    int N[MAX_LAYERS], Np[MAX_LAYERS];
+    const uint8_t* wimg[MAX_LAYERS];
+    const float* bias[MAX_LAYERS];
+    int act, l2norm;
+    float slope, eps;
+    uint32_t slot_bytes;
+    int nbw, n_tiles;
+};
+
+// TMEM columns [c0, c1) of the finished layer (bias, activation) -> operand planes, chunks from 0
+__device__ __forceinline__ void convert_slab(const MlpArgs& a, int l, int c0, int c1, uint32_t tmem_base, uint8_t* act_hi, int tid) {
+    const int row = tid & 127, half = tid >> 7, q = (tid >> 5) & 3;
+    const float* bias = a.bias[l];
+    const int N = a.N[l];
+    const int n_groups = (c1 - c0) >> 4;
+    for (int g = half; g < n_groups; g += 2) {
+        float v[16];
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 16 * g), v);
+        uint32_t h[8], lw[8];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+            float f[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int c = c0 + 16 * g + e + t;
+                f[t] = c < N ? rf_act(v[e + t] + (bias ? __ldg(bias + c) : 0.f), a.act, a.slope) : 0.f;
+            }
+            uint32_t h0, l0, h1, l1;
+            split_f16(f[0], h0, l0);
+            split_f16(f[1], h1, l1);
+            h[e >> 1] = h0 | (h1 << 16);
+            lw[e >> 1] = l0 | (l1 << 16);
+        }
+        uint8_t* p = act_hi + (size_t)(2 * g) * PLANE + row * 16;
+        *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(p + PLANE) = make_uint4(h[4], h[5], h[6], h[7]);
+        *reinterpret_cast<uint4*>(p + ACT_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        *reinterpret_cast<uint4*>(p + ACT_BYTES + PLANE) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sACT = base;                       // hi planes, then lo planes
+    const uint32_t sW = base + 2 * ACT_BYTES;
+    const uint32_t bars = sW + (uint32_t)a.nbw * a.slot_bytes;
+    const uint32_t bar_wfull = bars, bar_wempty = bars + 8 * MAX_SLOTS, bar_mma = bars + 16 * MAX_SLOTS;
+    const uint32_t tmem_slot = bar_mma + 8;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
+    float* ssq = reinterpret_cast<float*>(smem_al + (tmem_slot + 8 - base));  // [256] row partial sums (l2norm)
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < a.nbw; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 4); }
+        mbar_init(bar_mma, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 8) {
+        // ---- weight producer: runs ahead over tiles, layers and k steps
+        if ((tid & 31) == 0) {
+            uint32_t kt = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
+                for (int l = 0; l < a.n_layers; ++l) {
+                    const int nks = (l == 0 ? a.K0p : a.Np[l - 1]) >> 4;
+                    const uint32_t bytes = 64u * (uint32_t)a.Np[l];
+                    for (int ks = 0; ks < nks; ++ks, ++kt) {
+                        const uint32_t sl = kt % (uint32_t)a.nbw;
+                        mbar_wait_relaxed(bar_wempty + 8 * sl, ((kt / (uint32_t)a.nbw) & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(bar_wfull + 8 * sl, bytes);
+                        bulk_g2s(sW + sl * a.slot_bytes, a.wimg[l] + (size_t)ks * bytes, bytes, bar_wfull + 8 * sl);
+                    }
+                }
+        }
+    } else {
+        // ---- 8 worker warps: loaders / epilogue; warps 1..4 are also the MMA issuers (128 accumulator columns each)
+        const int iss = warp - 1;
+        const bool issuer = iss >= 0 && iss < 4;
+        const uint32_t leader = elect_one();
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        uint8_t* act_hi = smem_al;  // sACT == base
+        uint32_t kt = 0, mma_phase = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            // ---- phase A: x rows -> operand planes.  item = (row, 8-channel chunk); a quarter warp covers 8
+            // consecutive rows of one chunk (128 contiguous bytes of a plane: conflict-free 16-byte stores)
+            {
+                const int nch = a.K0p >> 3;
+                const bool vec = (a.ldx & 3) == 0;
+                for (int i = tid; i < TM * nch; i += WORKERS) {
+                    const int r_lo = i & 7, c = (i >> 3) % nch, r_hi = i / (8 * nch);
+                    const int row = r_hi * 8 + r_lo;
+                    const long grow = (long)tile * TM + row;
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = 0.f;
+                    if (grow < a.M) {
+                        const float* src = a.x + grow * a.ldx + c * 8;
+                        if (vec && c * 8 + 8 <= a.K0) {
+                            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+                            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                            f[0] = v0.x; f[1] = v0.y; f[2] = v0.z; f[3] = v0.w; f[4] = v1.x; f[5] = v1.y; f[6] = v1.z; f[7] = v1.w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (c * 8 + e < a.K0) f[e] = __ldg(src + e);
+                        }
+                    }
+                    uint32_t h[4], lw[4];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        uint32_t h0, l0, h1, l1;
+                        split_f16(f[e], h0, l0);
+                        split_f16(f[e + 1], h1, l1);
+                        h[e >> 1] = h0 | (h1 << 16);
+                        lw[e >> 1] = l0 | (l1 << 16);
+                    }
+                    uint8_t* p = act_hi + (size_t)c * PLANE + row * 16;
+                    *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4*>(p + ACT_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            tc_fence_before();
+            workers_sync();
+            tc_fence_after();
+
+            for (int l = 0; l < a.n_layers; ++l) {
+                const int Kp = l == 0 ? a.K0p : a.Np[l - 1];
+                const int nks = Kp >> 4, Np = a.Np[l];
+                for (int ks0 = 0; ks0 < nks; ks0 += ACT_CHUNKS / 2) {  // slabs of 16 k steps = 256 input channels
+                    const int ks1 = min(nks, ks0 + ACT_CHUNKS / 2);
+                    if (ks0 > 0) {  // next 256 input channels: still in TMEM as the previous layer's columns
+                        convert_slab(a, l - 1, ks0 * 16, ks1 * 16, tmem_base, act_hi, tid);
+                        tc_fence_before();
+                        workers_sync();
+                        tc_fence_after();
+                    }
+                    if (issuer) {
+                        const bool active = iss * 128 < Np;
+                        const int n_mma = min(128, Np - iss * 128);
+                        const uint32_t idesc = idesc_f16(active ? n_mma : 16);
+                        const uint32_t a_hi32 = 8u | (1u << 14);                      // SBO 128 B
+                        const uint32_t b_hi32 = 8u | (1u << 14);
+                        const uint32_t a0 = ((sACT & 0x3FFFFu) >> 4) | ((uint32_t)(PLANE >> 4) << 16);   // LBO = one chunk plane
+                        const uint32_t b_lbo = (uint32_t)Np << 16;                    // LBO = Np rows x 16 B
+                        const uint32_t d = tmem_u + (uint32_t)(iss * 128);
+                        for (int ks = ks0; ks < ks1; ++ks, ++kt) {
+                            const uint32_t sl = kt % (uint32_t)a.nbw;
+                            mbar_wait_warp(bar_wfull + 8 * sl, (kt / (uint32_t)a.nbw) & 1u);
+                            tc_fence_after();
+                            if (active) {
+                                const uint32_t da = a0 + (uint32_t)(ks - ks0) * (2u * PLANE >> 4);
+                                const uint32_t db = ((((sW + sl * a.slot_bytes) & 0x3FFFFu) >> 4) | b_lbo) + (uint32_t)(iss * 128);
+                                const uint32_t db_lo = db + (uint32_t)(2 * Np);       // lo block: 2 * Np * 16 bytes further
+                                tc_mma2(d, da, a_hi32, db_lo, b_hi32, idesc, ks > 0 ? 1u : 0u, leader);            // hi * lo
+                                tc_mma2(d, da + (ACT_BYTES >> 4), a_hi32, db, b_hi32, idesc, 1u, leader);          // lo * hi
+                                tc_mma2(d, da, a_hi32, db, b_hi32, idesc, 1u, leader);                             // hi * hi
+                                if (leader) tc_commit(bar_wempty + 8 * sl);
+                            } else if (leader) {
+                                mbar_arrive(bar_wempty + 8 * sl);
+                            }
+                        }
+                        if (leader) {
+                            if (active) tc_commit(bar_mma);
+                            else mbar_arrive(bar_mma);
+                        }
+                        __syncwarp();
+                    } else {
+                        kt += (uint32_t)(ks1 - ks0);
+                    }
+                    mbar_wait_warp_sleepy(bar_mma, mma_phase & 1u);
+                    ++mma_phase;
+                    tc_fence_after();
+                }
+                // ---- layer epilogue
+                if (l + 1 < a.n_layers) {
+                    convert_slab(a, l, 0, min(Np, 16 * 16), tmem_base, act_hi, tid);
+                    tc_fence_before();
+                    workers_sync();
+                    tc_fence_after();
+                } else {
+                    const int row = tid & 127, half = tid >> 7, q = (tid >> 5) & 3;
+                    const long grow = (long)tile * TM + row;
+                    const int N = a.N[l];
+                    const float* bias = a.bias[l];
+                    const int n_groups = Np >> 4;
+                    float scale = 1.f;
+                    if (a.l2norm) {  // util/retrieval.py:66 F.normalize: x / max(|x|, eps)
+                        float ss = 0.f;
+                        for (int g = half; g < n_groups; g += 2) {
+                            float v[16];
+                            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * g), v);
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                const int c = 16 * g + e;
+                                const float o = c < N ? v[e] + (bias ? __ldg(bias + c) : 0.f) : 0.f;
+                                ss = fmaf(o, o, ss);
+                            }
+                        }
+                        ssq[tid] = ss;
+                        workers_sync();
+                        scale = 1.f / fmaxf(sqrtf(ssq[row] + ssq[row + 128]), a.eps);
+                    }
+                    for (int g = half; g < n_groups; g += 2) {
+                        float v[16];
+                        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * g), v);
+                        if (grow < a.M) {
+                            float* dst = a.y + grow * a.ldy + 16 * g;
+#pragma unroll
+                            for (int e = 0; e < 16; e += 4) {
+                                float o[4];
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const int c = 16 * g + e + t;
+                                    o[t] = (c < N ? v[e + t] + (bias ? __ldg(bias + c) : 0.f) : 0.f) * scale;
+                                }
+                                if (16 * g + e + 4 <= N && (a.ldy & 3) == 0) {
+                                    *reinterpret_cast<float4*>(dst + e) = make_float4(o[0], o[1], o[2], o[3]);
+                                } else {
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t)
+                                        if (16 * g + e + t < N) dst[e + t] = o[t];
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    workers_sync();  // TMEM and the operand planes are free for the next tile
+                    tc_fence_after();
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+bool mlp_shape_ok(const int* widths, int n_layers) {
+    if (n_layers < 1 || n_layers > MAX_LAYERS || widths[0] < 1 || widths[0] > 512) return false;
+    for (int l = 1; l <= n_layers; ++l) {
+        if (widths[l] < 1 || widths[l] > 512) return false;
+        // a layer wider than 256 is consumed slab by slab while the next one accumulates into the freed columns
+        if (l < n_layers && round_up(widths[l], 16) > 256 && round_up(widths[l + 1], 16) > 256) return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" int rf_tc_mlp_supported(const int* widths_host, int n_layers) { return mlp_shape_ok(widths_host, n_layers) ? 1 : 0; }
+
+/* bytes of the operand image of one layer (weight [N, K]) */
+extern "C" size_t rf_tc_mlp_weight_image_bytes(int N, int K) {
+    if (N < 1 || N > 512 || K < 1 || K > 512) return 0;
+    return (size_t)(round_up(K, 16) / 16) * 64 * round_up(N, 16);
+}
+
+extern "C" int rf_tc_mlp_weight_image(const float* w, int N, int K, void* image, void* stream) {
+    RF_CHECK_ARG(w && image && rf_tc_mlp_weight_image_bytes(N, K) > 0, "rf_tc_mlp_weight_image: bad arguments N=%d K=%d", N, K);
+    RF_CHECK_ARG(((uintptr_t)image & 15) == 0, "rf_tc_mlp_weight_image: image must be 16-byte aligned");
+    const int Np = round_up(N, 16), Kp = round_up(K, 16);
+    const long threads = (long)(Kp / 16) * 2 * Np;
+    mlp_weight_image_kernel<<<(unsigned)rf_cdivl(threads, 256), 256, 0, (cudaStream_t)stream>>>(w, N, K, Np, Kp, (uint8_t*)image);
+    RF_LAUNCH_OK("mlp_weight_image_kernel");
+    return 0;
+}
+
+extern "C" int rf_tc_mlp_fwd(const float* x, int ldx, const void* const* images_host, const float* const* bias_host,
+                             const int* widths_host, int n_layers, int act, float slope, int l2_normalize, float eps, float* y,
+                             int ldy, long M, void* stream) {
+    RF_CHECK_ARG(x && y && images_host && widths_host && M > 0, "rf_tc_mlp_fwd: bad arguments");
+    RF_CHECK_ARG(mlp_shape_ok(widths_host, n_layers), "rf_tc_mlp_fwd: unsupported layer widths");
+    RF_CHECK_ARG(ldx >= widths_host[0] && ldy >= widths_host[n_layers], "rf_tc_mlp_fwd: leading dimensions too small");
+    RF_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "rf_tc_mlp_fwd: x / y must be 16-byte aligned");
+    MlpArgs a;
+    a.x = x; a.y = y; a.M = M; a.ldx = ldx; a.ldy = ldy; a.n_layers = n_layers; a.K0 = widths_host[0]; a.K0p = round_up(widths_host[0], 16);
+    int max_np = 16;
+    for (int l = 0; l < MAX_LAYERS; ++l) {
+        a.N[l] = l < n_layers ? widths_host[l + 1] : 0;
+        a.Np[l] = l < n_layers ? round_up(widths_host[l + 1], 16) : 0;
+        a.wimg[l] = l < n_layers ? (const uint8_t*)images_host[l] : nullptr;
+        a.bias[l] = (l < n_layers && bias_host) ? bias_host[l] : nullptr;
+        if (l < n_layers) {
+            RF_CHECK_ARG(a.wimg[l] && ((uintptr_t)a.wimg[l] & 15) == 0, "rf_tc_mlp_fwd: weight image %d missing or misaligned", l);
+            if (a.Np[l] > max_np) max_np = a.Np[l];
+        }
+    }
+    RF_CHECK_ARG(a.K0p <= 8 * ACT_CHUNKS, "rf_tc_mlp_fwd: input wider than 256 channels");
+    a.act = act; a.slope = slope; a.l2norm = l2_normalize; a.eps = eps;
+    a.slot_bytes = 64u * (uint32_t)max_np;
+    const long avail = (long)SMEM_LIMIT - 1024 - 2L * ACT_BYTES - (16 * MAX_SLOTS + 32 + 1024 + 64);
+    long nbw = avail / a.slot_bytes;
+    if (nbw > MAX_SLOTS) nbw = MAX_SLOTS;
+    RF_CHECK_ARG(nbw >= 2, "rf_tc_mlp_fwd: weight ring does not fit");
+    a.nbw = (int)nbw;
+    a.n_tiles = (int)rf_cdivl(M, TM);
+    const size_t smem = 1024 + 2 * (size_t)ACT_BYTES + (size_t)a.nbw * a.slot_bytes + 16 * MAX_SLOTS + 32 + 1024 + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RF_CUDA_OK(cudaFuncSetAttribute(tc_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = a.n_tiles < sms ? a.n_tiles : sms;
+    tc_mlp_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+    RF_LAUNCH_OK("tc_mlp_kernel");
+    return 0;
+}

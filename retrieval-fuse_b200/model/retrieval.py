@@ -118,13 +118,19 @@ class _MlpPatchEncoder(RfModule):
         return self.encode(x, l2_normalize=False)
 
     use_tensor_cores = True  # tcgen05 fp16-split GEMMs (~2e-7 relative); False -> fp32 FMA kernels
+    use_fused_chain = True   # one launch for the whole MLP (rf_tc_mlp_fwd) instead of one rf_tc_linear_fwd per layer
 
     def encode(self, x, l2_normalize):
         """forward (+ optionally util/retrieval.py:66 row normalisation fused)."""
         ops._forward_only(x, *self.parameters())
         lin = self._linears()
         h = x.reshape(x.shape[0], -1)
-        if self.use_tensor_cores and h.shape[0] >= 128 and all(ops.tc_supported(*m.weight.shape) for m in lin):
+        widths = [lin[0].in_features] + [m.out_features for m in lin]
+        if self.use_tensor_cores and self.use_fused_chain and h.shape[0] >= 128 and ops.tc_mlp_supported(widths):
+            # all layers in one launch: hidden activations stay in shared memory / TMEM (rf_tc_mlp.cu)
+            imgs = [self._wcache.derived(("mlpimg", j), [m.weight], ops.tc_mlp_weight_image) for j, m in enumerate(lin)]
+            z = ops.tc_mlp(h, imgs, [m.bias for m in lin], widths, act=ops.ACT_RELU, l2_normalize=l2_normalize)
+        elif self.use_tensor_cores and h.shape[0] >= 128 and all(ops.tc_supported(*m.weight.shape) for m in lin):
             for j, m in enumerate(lin):
                 img = self._wcache.derived(("tcimg", j), [m.weight], ops.tc_weight_image)
                 h = ops.tc_linear(h, img, m.bias, m.out_features, act=ops.ACT_RELU if j < len(lin) - 1 else ops.ACT_NONE)

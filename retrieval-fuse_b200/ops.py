@@ -214,6 +214,46 @@ def tc_linear(x, weight_image, bias, N, act=ACT_NONE, slope=0.0):
 
 # ---- channels-last tensor-core convolution path ------------------------------------------------
 
+def _widths_arr(widths):
+    return (ctypes.c_int * 9)(*(list(widths) + [0] * (9 - len(widths))))
+
+
+def tc_mlp_supported(widths):
+    """widths = [in, hidden..., out]: can the fused tcgen05 MLP chain run these layers?"""
+    return len(widths) <= 9 and bool(_lib.lib().rf_tc_mlp_supported(_widths_arr(widths), len(widths) - 1))
+
+
+def tc_mlp_weight_image(weight):
+    """nn.Linear weight [N, K] -> operand image of rf_tc_mlp_fwd."""
+    weight = _dev(weight.detach(), name="weight")
+    N, K = weight.shape
+    L = _lib.lib()
+    nbytes = L.rf_tc_mlp_weight_image_bytes(N, K)
+    if nbytes == 0:
+        raise _lib.RfError(f"fused MLP does not support a weight of shape {tuple(weight.shape)}")
+    img = _aligned_bytes(nbytes, weight.device)
+    with torch.cuda.device(weight.device):
+        check(L.rf_tc_mlp_weight_image(weight.data_ptr(), N, K, img.data_ptr(), _stream(weight)), "rf_tc_mlp_weight_image")
+    _count()
+    return img
+
+
+def tc_mlp(x, images, biases, widths, act=ACT_RELU, slope=0.0, l2_normalize=False, eps=1e-12):
+    """All layers of an MLP in one launch (hidden activations stay on chip).  x [M, widths[0]] fp32 (row stride = its
+    leading dimension), images[l] = tc_mlp_weight_image(layer l weight) -> [M, widths[-1]]."""
+    x = _dev(x, name="x")
+    M = x.shape[0]
+    assert x.shape[1] == widths[0] and len(images) == len(widths) - 1
+    y = torch.empty((M, widths[-1]), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_tc_mlp_fwd(x.data_ptr(), x.shape[1], ptr_array([i.data_ptr() for i in images]),
+                                       ptr_array([_ptr(b) for b in biases]), _widths_arr(widths), len(widths) - 1, act,
+                                       float(slope), int(bool(l2_normalize)), float(eps), y.data_ptr(), widths[-1], M,
+                                       _stream(x)), "rf_tc_mlp_fwd")
+    _count()
+    return y
+
+
 def _aligned_bytes(nbytes, device, align=1024):
     buf = torch.empty(nbytes + align, device=device, dtype=torch.uint8)
     off = (-buf.data_ptr()) % align

@@ -191,6 +191,32 @@ def test_shifted_window_conv(dev, N, S, C1, C2, Cout, ncdhw):
     close(y, ref32, rel_to_max=True, what="shifted-window conv vs oracle")
 
 
+@pytest.mark.parametrize("M,widths,act,l2", [(1000, [64, 128, 256, 512, 256, 64], 1, True), (129, [64, 128, 256, 512, 256, 64], 1, False),
+                                             (4097, [128, 128, 128, 128, 32], 2, False), (300, [96, 128, 128, 128, 32], 2, False),
+                                             (640, [40, 72, 24], 1, True), (20000, [125, 128, 256, 512, 256, 64], 1, True)])
+def test_tc_mlp_chain(dev, M, widths, act, l2):
+    """Fused tcgen05 MLP chain (Patch04 family / attention theta, phi shapes) against an fp64 evaluation and against
+    the per-layer fp32 FMA kernels."""
+    from retrieval_fuse_b200 import ops
+    g = torch.Generator().manual_seed(M + sum(widths))
+    x = torch.randn(M, widths[0], generator=g)
+    ws = [torch.randn(widths[i + 1], widths[i], generator=g) / widths[i] ** 0.5 for i in range(len(widths) - 1)]
+    bs = [torch.randn(widths[i + 1], generator=g) * 0.1 for i in range(len(widths) - 1)]
+    assert ops.tc_mlp_supported(widths)
+    imgs = [ops.tc_mlp_weight_image(w.to(dev)) for w in ws]
+    y = ops.tc_mlp(x.to(dev), imgs, [b.to(dev) for b in bs], widths, act=act, slope=0.01, l2_normalize=l2)
+    h = x.double()
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        h = h @ w.double().t() + b.double()
+        if i < len(ws) - 1:
+            h = torch.relu(h) if act == 1 else torch.nn.functional.leaky_relu(h, 0.01)
+    if l2:
+        h = h / h.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    err = float((y.cpu().double() - h).abs().max())
+    scale = max(1.0, float(h.abs().max()))
+    assert err <= 1e-5 * scale, f"max abs err {err:.2e} (scale {scale:.2f})"
+
+
 @pytest.mark.parametrize("cls,nf,n", [("Patch32", 8, 40), ("Patch08", 16, 300), ("Patch24", 12, 17), ("PCPatch48", 10, 9)])
 def test_conv_encoders_tensor_core_path(dev, cls, nf, n):
     """Batches large enough for the tcgen05 implicit-GEMM path, against the oracle and the fp32 FMA path."""
