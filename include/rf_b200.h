@@ -243,8 +243,8 @@ int rf_compose_gather(const float* rows, const int* dst_extents, const float* sc
  * AttentionBlock.forward :84-113 (g = o = Identity, blend or additive).
  *   x_back [B,nf,S,S,S], x_retr [B*K,nf,S,S,S] -> out [B,nf,S,S,S]
  *   theta_wt/phi_wt: 4 transposed Linear weights [in,out] each, *_b biases;
- *   theta_img/phi_img: NULL, or the 4 rf_tc_weight_image buffers of each MLP -
- *   then the MLPs run on the tensor cores (rf_tc_linear_fwd) and *_wt is unused;
+ *   theta_img/phi_img: NULL, or the 4 rf_tc_mlp_weight_image buffers of each MLP -
+ *   then each MLP is ONE fused tensor-core launch (rf_tc_mlp_fwd) and *_wt is unused;
  *   mode 0: softmax(32*E^3*4 * s); mode 1: hard Gumbel arg-max of 25*s + noise
  *   (noise [B*R^3, K], required); workspace from rf_attention_workspace_bytes. */
 size_t rf_attention_workspace_bytes(int B, int nf, int S, int E, int K);

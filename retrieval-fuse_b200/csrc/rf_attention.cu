@@ -136,17 +136,15 @@ size_t attn_ws_layout(int B, int nf, int S, int E, int K, AttnWs* ws, char* base
 }
 
 // theta / phi: Linear(V,128) LeakyReLU Linear(128,128) LeakyReLU Linear(128,128) LeakyReLU Linear(128,32).
-// img != NULL: tcgen05 fp16-split GEMMs (rf_tc_linear_fwd) on pre-staged weight images; else fp32 FMA kernels.
+// img != NULL: the fused tcgen05 chain (rf_tc_mlp_fwd) on rf_tc_mlp_weight_image operand images; else fp32 FMA kernels.
 int run_mlp(const float* in, long rows, int V, const float* const* wt, const float* const* b, const void* const* img,
             float* ha, float* hb, float* out, void* stream) {
     RF_CHECK_ARG(rows < (1L << 31), "attention: too many rows");
     const float slope = 0.01f;  // nn.LeakyReLU() default
     int rc;
-    if (img) {
-        if ((rc = rf_tc_linear_fwd(in, V, img[0], b[0], ha, rows, V, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;
-        if ((rc = rf_tc_linear_fwd(ha, HIDDEN, img[1], b[1], hb, rows, HIDDEN, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;
-        if ((rc = rf_tc_linear_fwd(hb, HIDDEN, img[2], b[2], ha, rows, HIDDEN, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;
-        return rf_tc_linear_fwd(ha, HIDDEN, img[3], b[3], out, rows, HIDDEN, FEAT, RF_ACT_NONE, 0.f, stream);
+    if (img) {  // all four layers in one launch, hidden activations on chip (rf_tc_mlp.cu)
+        const int widths[5] = {V, HIDDEN, HIDDEN, HIDDEN, FEAT};
+        return rf_tc_mlp_fwd(in, V, img, b, widths, 4, RF_ACT_LEAKY, slope, 0, 0.f, out, FEAT, rows, stream);
     }
     if ((rc = rf_linear_fwd(in, wt[0], b[0], ha, (int)rows, V, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;
     if ((rc = rf_linear_fwd(ha, wt[1], b[1], hb, (int)rows, HIDDEN, HIDDEN, RF_ACT_LEAKY, slope, stream))) return rc;

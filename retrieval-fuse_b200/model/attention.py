@@ -54,9 +54,10 @@ class AttentionBlock(RfModule):
     def _branch(self, enc):
         lin = enc.linears()
         imgs = None
-        if self.use_tensor_cores and all(ops.tc_supported(*m.weight.shape) for m in lin):
+        widths = [lin[0].in_features] + [m.out_features for m in lin]
+        if self.use_tensor_cores and len(lin) == 4 and ops.tc_mlp_supported(widths):
             tag = "theta" if enc is self.theta else "phi"
-            imgs = [self._wcache.derived((tag, j), [m.weight], ops.tc_weight_image) for j, m in enumerate(lin)]
+            imgs = [self._wcache.derived((tag, j), [m.weight], ops.tc_mlp_weight_image) for j, m in enumerate(lin)]
         return [self._wt(m.weight) for m in lin], [m.bias for m in lin], imgs
 
     def get_regularization_losses(self):
