@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="retrieval", choices=["retrieval", "refine"])
+    ap.add_argument("--workload", default="retrieval", choices=["retrieval", "refine", "stages"])
     ap.add_argument("--chunks", type=int, default=10000, help="chunks per step per GPU")
     ap.add_argument("--bank-scenes", type=int, default=2048, help="64^3 scenes encoded into the bank (x64 rows)")
     ap.add_argument("--knn-method", type=int, default=0, help="0 auto, 1 exact fp64 sweep, 2 tcgen05 fp16, 3 tcgen05 bf16x3")
@@ -54,7 +54,7 @@ def parse():
                          "bank AND queries (profiling aid, BASELINE config 5 style)")
     ap.add_argument("--refine-batch", type=int, default=8)
     ap.add_argument("--no-cuda-graph", action="store_true", help="refine workload: launch kernels eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--cpu-sample-chunks", type=int, default=128)
+    ap.add_argument("--cpu-sample-chunks", type=int, default=2048, help="chunks of the workload the CPU arm runs per step (~10-15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -209,6 +209,124 @@ def dist_setup(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     return rank, local, world
+
+
+def run_stages(args, local):
+    """--workload stages: every SURVEY 8(d) stage of the path timed alone (CUDA events, L2 flushed before each
+    timed launch) against the roofline that bounds it.  One JSON line: {"stages": {name: {...}}}.  A report next to
+    the headline metric, not a replacement for it."""
+    from retrieval_fuse_b200 import ops
+    from retrieval_fuse_b200.pipeline import (FRONT3D_SR, SHAPENET_SR_RETRIEVAL, RefinementPipeline, RetrievalPipeline,
+                                              build_bank_from_targets, synthetic_tsdf_batch)
+    from retrieval_fuse_b200.model import get_retrieval_networks
+    from retrieval_fuse_b200.pipeline import init_unit_gain_
+    assert torch.cuda.is_available(), "bench.py needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.set_grad_enabled(False)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs") or 6500.0
+    tens = peaks.get("bf16_tflops_sustained") or 1400.0
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, iters=args.steps):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        tot = 0.0
+        for _ in range(iters):
+            flush_buf.fill_(1)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / iters
+
+    stages = {}
+
+    def add(name, ms, bytes_=None, flops=None, note=None):
+        d = {"ms": ms}
+        if bytes_ is not None:
+            d.update(bound="hbm", algorithmic_bytes=bytes_, achieved_gbs=bytes_ / ms / 1e6, frac=bytes_ / ms / 1e6 / hbm)
+        if flops is not None:
+            d.update(bound="tensor" if bytes_ is None else "hbm+tensor", algorithmic_flops=flops,
+                     achieved_tflops=flops / ms / 1e9, frac_tensor=flops / ms / 1e9 / tens)
+        if note:
+            d["note"] = note
+        stages[name] = d
+        log(f"[stages] {name}: {d}")
+
+    cfg = FRONT3D_SR
+    d = cfg["dataset"]
+    B, K, nf = args.refine_batch, cfg["K"], 16
+    # ---- a2 / a3 fold, unfold (pure permutations: 2 x numel x 4 B)
+    x = torch.randn(B * (K + 1), nf, 32, 32, 32, device=dev)
+    u = ops.unfold3d(x, 8)
+    add("a2 Unfold3D(8, nf) [40,16,32^3]", timed(lambda: ops.unfold3d(x, 8)), bytes_=2 * x.numel() * 4)
+    add("a3 Fold3D(4, 8, nf)", timed(lambda: ops.fold3d(u, 4, 8, nf)), bytes_=2 * x.numel() * 4)
+    del x, u
+    # ---- a1/a4 pad + unfold + normalise of the query chunks and of target scenes
+    rcfg = SHAPENET_SR_RETRIEVAL
+    rd = rcfg["dataset"]
+    chunks = synthetic_tsdf_batch(args.chunks, 8, rd["voxel_size_input"], seed=7, device=dev, batch=2048).unsqueeze(1).contiguous()
+    pipe_r = RetrievalPipeline(rcfg, bank=None, device=dev, weight_seed=1234)
+    pu = lambda: ops.unfold3d_pad_stride(chunks, pipe_r.in_kernel, rd["patch_context_input"], pipe_r.in_stride, pipe_r.input_trunc,
+                                         norm_sub=rd["input_mean"], norm_div=rd["input_std"])
+    patches = pu()
+    add("a1/a4 pad+unfold+normalise, 8^3 chunks -> 64 x 4^3", timed(pu), bytes_=(chunks.numel() + patches.numel()) * 4)
+    # ---- a5 + a9 query encoder (Patch04) + row normalisation, one fused launch
+    from retrieval_fuse_b200.pipeline import _encode_normalized
+    enc = lambda: _encode_normalized(pipe_r.fenc_input, patches, 64)
+    n_par = sum(p.numel() for n_, p in pipe_r.fenc_input.named_parameters() if n_.endswith("weight"))
+    add("a5+a9 Patch04 MLP + normalise (fused chain)", timed(enc), flops=2.0 * n_par * patches.shape[0],
+        note="weights (1.28 MB fp16 hi+lo) are re-streamed from L2 for every 128-row tile")
+    del patches
+    # ---- a7 dictionary encoder (Patch32) incl. pad-unfold of 64^3 targets
+    n_sc = 64
+    targets = synthetic_tsdf_batch(n_sc, 64, rd["voxel_size_target"], seed=100, device=dev)
+    _, fenc_t = get_retrieval_networks(rcfg["retrieval_model"])
+    init_unit_gain_(fenc_t, 11)
+    fenc_t = fenc_t.to(dev).eval()
+    ps, ctx = rd["patch_size_target"], rd["patch_context_target"]
+    tp = lambda: ops.unfold3d_pad_stride(targets.unsqueeze(1), ps + 2 * ctx, ctx, rd["patch_stride"], pipe_r.target_trunc,
+                                         norm_sub=rd["target_mean"], norm_div=rd["target_std"])
+    tpatches = tp()
+    add("a4 pad+unfold of 64^3 targets -> 64 x 32^3", timed(tp), bytes_=(targets.numel() + tpatches.numel()) * 4)
+    add("a7 Patch32 dictionary encoder, 4096 x 32^3", timed(lambda: _encode_normalized(fenc_t, tpatches, 64)),
+        flops=338.5e6 * tpatches.shape[0])
+    del tpatches
+    # ---- a12 compose
+    bank, _ = build_bank_from_targets(cfg, targets, dev, weight_seed=11)
+    pipe = RefinementPipeline(cfg, bank, targets, device=dev, weight_seed=1234)
+    rchunks = synthetic_tsdf_batch(B, 8, d["voxel_size_input"], seed=3, device=dev).unsqueeze(1).contiguous()
+    rows, _ = pipe.retrieve(rchunks)
+    add("a12 compose gather (K=4)", timed(lambda: pipe.compose(rows, B, normalize=True)), bytes_=2.0 * K * 64 ** 3 * 4 * B)
+    retr = pipe.compose(rows, B, normalize=True)
+    x_in = pipe.normalize_input(rchunks)
+    # ---- a13 retrieval U-Net, a15 input U-Net, a14 attention, a16 decoder
+    rp = ops.unfold3d(retr.reshape(B * K, 1, 64, 64, 64), 16)
+    add("a13 RetrievalUNetBackbone, 2048 x 16^3 patches", timed(lambda: pipe.retrieval_backbone(rp)), flops=19.03e9 * B * K)
+    feats = pipe.retrieval_backbone(rp)
+    x_retr = ops.fold3d(feats, 4, 8, nf)
+    add("a15 Superresolution08UNetBackbone", timed(lambda: pipe.unet_backbone(x_in)), flops=1.91e9 * B)
+    x_back = pipe.unet_backbone(x_in)
+    add("a14 PatchedAttentionBlock (K=4)", timed(lambda: pipe.patched_attention_block(x_back, x_retr)),
+        bytes_=(K + 2.0) * nf * 32 ** 3 * 4 * B, flops=2.18e9 * B)
+    xa = pipe.patched_attention_block(x_back, x_retr)
+    add("a16 Superresolution08FinalDecoder", timed(lambda: pipe.decoder(xa)), flops=7.26e9 * B)
+    line = {"metric": "per-stage rooflines (SURVEY 8d)", "unit": "ms", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "config": {"workload": f"stages: 3DFront SR 008->064 batch {B} K={K}; ShapeNetV2 retrieval {args.chunks} chunks",
+                       "l2": "flushed before every timed launch (256 MiB write)"},
+            "peaks": {"hbm_gbs": hbm, "bf16_tflops_sustained": tens, "source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            "tensor_note": "tensor fractions are ALGORITHMIC flops / bf16 dense peak; the kernels spend 3 fp16 MMAs per product "
+                           "(hi/lo split for fp32-level accuracy), so 1/3 is the ceiling of this column",
+            "stages": stages}
+    print(json.dumps(line), flush=True)
 
 
 def run_ours(args, rank, local, world):
@@ -492,6 +610,10 @@ def main():
     rank, local, world = dist_setup(args)
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "stages":
+        if rank == 0:
+            run_stages(args, local)
         return
     run_ours(args, rank, local, world)
 

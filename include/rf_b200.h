@@ -151,18 +151,22 @@ int rf_tc_conv3d_fwd(const void* x_hi, const void* x_lo, int C1, const void* x2_
  * shared memory once, addressing all 27 taps in place through no-swizzle UMMA
  * descriptors (no im2col).  rf_halo_act_bytes = size of ONE of hi / lo.
  * rf_tc_conv3d_halo_supported tells whether an item shape fits shared memory and
- * TMEM for this layer; callers use rf_tc_conv3d_fwd otherwise.  y is fp32
- * channels-last [N,D,H,W,Cout] or NCDHW. */
-size_t rf_halo_act_bytes(int N, int D, int H, int W, int C1, int C2);
+ * TMEM for this layer; callers use rf_tc_conv3d_fwd otherwise.  D, H, W are the
+ * INPUT extents; pad = 1 ('same', the U-Nets; zero halo written by the split kernel)
+ * or 0 ('valid', the conv patch encoders of model/retrieval.py: no halo, output
+ * extents D-2).  y is fp32 channels-last [N,Do,Ho,Wo,Cout] or NCDHW. */
+size_t rf_halo_act_bytes(int N, int D, int H, int W, int C1, int C2, int pad);
 int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a,
-                          const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, float scale, void* stream);
+                          const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, int pad, float scale,
+                          void* stream);
 size_t rf_tc_conv_halo_weight_image_bytes(int Cout, int C1, int C2);
 int rf_tc_conv_halo_weight_image(const float* w, int Cout, int C1, int C2, float scale, void* image, void* stream);
-int rf_tc_conv3d_halo_supported(int N, int D, int H, int W, int Cout, int C1, int C2);
-int rf_tc_conv3d_halo_geometry(int N, int D, int H, int W, int Cout, int C1, int C2, int* out8);
+int rf_tc_conv3d_halo_supported(int N, int D, int H, int W, int Cout, int C1, int C2, int pad);
+int rf_tc_conv3d_halo_geometry(int N, int D, int H, int W, int Cout, int C1, int C2, int pad, int* out8);
+int rf_tc_conv3d_halo_debug_read(long long* out64); /* tuning aid: phase timestamps of CTA 0's first items */
 int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D,
-                          int H, int W, int Cout, int C1, int C2, int act, float slope, float out_scale, int out_ncdhw,
-                          void* stream);
+                          int H, int W, int pad, int Cout, int C1, int C2, int act, float slope, float out_scale,
+                          int out_ncdhw, void* stream);
 
 /* First layers (single input channel: the TSDF / occupancy volume): direct
  * convolution, one thread per output voxel, filter bank in shared memory,

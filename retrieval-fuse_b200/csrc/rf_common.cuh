@@ -56,3 +56,20 @@ __device__ __forceinline__ float rf_act(float v, int act, float slope) {
     if (act == RF_ACT_TANH) return tanhf(v);
     return v;
 }
+
+// Activation of a register vector with ONE switch on the (runtime) activation kind: rf_act per element makes
+// the compiler expand the tanh path next to every element and branch around it 16 times per group, which
+// turned the tensor-core epilogues into ~900 instructions per 16 columns.
+template <int N>
+__device__ __forceinline__ void rf_act_vec(float (&v)[N], int act, float slope) {
+    if (act == RF_ACT_RELU) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) v[e] = fmaxf(v[e], 0.f);
+    } else if (act == RF_ACT_LEAKY) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
+    } else if (act == RF_ACT_TANH) {
+#pragma unroll 1
+        for (int e = 0; e < N; ++e) v[e] = tanhf(v[e]);
+    }
+}

@@ -294,9 +294,19 @@ __global__ void __launch_bounds__(256) conv_cin1_direct_kernel(const float* __re
             }
         }
         float* out = y + m * Cout;
+        if (bias) {
 #pragma unroll
-        for (int c = 0; c < CO; ++c)
-            if (c < Cout) out[c] = rf_act(acc[c] + (bias ? __ldg(bias + c) : 0.f), act, slope);
+            for (int c = 0; c < CO; ++c) acc[c] += c < Cout ? __ldg(bias + c) : 0.f;
+        }
+        rf_act_vec(acc, act, slope);
+        if (Cout == CO && (CO & 3) == 0) {  // one voxel = CO contiguous floats (16-byte aligned: m * CO * 4)
+#pragma unroll
+            for (int c = 0; c < CO; c += 4) *reinterpret_cast<float4*>(out + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CO; ++c)
+                if (c < Cout) out[c] = acc[c];
+        }
     }
 }
 }  // namespace

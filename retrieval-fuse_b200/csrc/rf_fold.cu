@@ -32,11 +32,85 @@ __global__ void __launch_bounds__(256) fold_unfold_kernel(const float* __restric
     }
 }
 
+// Vectorised variant for E in {4, 8, 16}: one thread moves one z-run of E floats (E/4 float4s).  The patch side is
+// fully contiguous across threads, the volume side is written / read in whole 32-byte sectors; index arithmetic is
+// 32-bit with compile-time E and happens once per run instead of once per element.
+template <int E, bool kFold>
+__global__ void __launch_bounds__(256) fold_unfold_vec_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int R,
+                                                              int total_runs) {
+    const int S = R * E;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total_runs; r += gridDim.x * blockDim.x) {
+        int t = r;
+        const int ey = t % E; t /= E;
+        const int ex = t % E; t /= E;
+        const int c = t % C; t /= C;
+        const int pz = t % R; t /= R;
+        const int py = t % R; t /= R;
+        const int px = t % R;
+        const int b = t / R;
+        const long v = ((((long)b * C + c) * S + (px * E + ex)) * S + (py * E + ey)) * S + pz * E;
+        const float4* src = reinterpret_cast<const float4*>(kFold ? in + (long)r * E : in + v);
+        float4* dst = reinterpret_cast<float4*>(kFold ? out + v : out + (long)r * E);
+#pragma unroll
+        for (int j = 0; j < E / 4; ++j) dst[j] = __ldg(src + j);
+    }
+}
+
+// E = 2 (the attention's Unfold3D(2, nf) / Fold3D(16, 2, nf)): one thread moves one (patch, channel) block of
+// 2 x 2 x 2 floats: two float4s on the patch side, four float2s on the volume side.
+template <bool kFold>
+__global__ void __launch_bounds__(256) fold_unfold_e2_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int R,
+                                                             int total_blocks) {
+    const int S = R * 2;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total_blocks; r += gridDim.x * blockDim.x) {
+        int t = r;
+        const int c = t % C; t /= C;
+        const int pz = t % R; t /= R;
+        const int py = t % R; t /= R;
+        const int px = t % R;
+        const int b = t / R;
+        const long v = ((((long)b * C + c) * S + px * 2) * S + py * 2) * S + pz * 2;
+        if (kFold) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(in + (long)r * 8));
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(in + (long)r * 8 + 4));
+            *reinterpret_cast<float2*>(out + v) = make_float2(a.x, a.y);
+            *reinterpret_cast<float2*>(out + v + S) = make_float2(a.z, a.w);
+            *reinterpret_cast<float2*>(out + v + (long)S * S) = make_float2(bq.x, bq.y);
+            *reinterpret_cast<float2*>(out + v + (long)S * S + S) = make_float2(bq.z, bq.w);
+        } else {
+            const float2 p00 = __ldg(reinterpret_cast<const float2*>(in + v));
+            const float2 p01 = __ldg(reinterpret_cast<const float2*>(in + v + S));
+            const float2 p10 = __ldg(reinterpret_cast<const float2*>(in + v + (long)S * S));
+            const float2 p11 = __ldg(reinterpret_cast<const float2*>(in + v + (long)S * S + S));
+            *reinterpret_cast<float4*>(out + (long)r * 8) = make_float4(p00.x, p00.y, p01.x, p01.y);
+            *reinterpret_cast<float4*>(out + (long)r * 8 + 4) = make_float4(p10.x, p10.y, p11.x, p11.y);
+        }
+    }
+}
+
+template <bool kFold>
+static int launch_fold_unfold(const float* in, float* out, int B, int C, int R, int E, cudaStream_t s) {
+    const long total = (long)B * C * R * R * R * E * E * E;
+    const bool aligned = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+    if (aligned && total < (1L << 31) && (E == 2 || E == 4 || E == 8 || E == 16)) {
+        const int units = (int)(E == 2 ? total / 8 : total / E);
+        const int grid = rf_grid_1d(units, 256, 148 * 64);
+        switch (E) {
+            case 2: fold_unfold_e2_kernel<kFold><<<grid, 256, 0, s>>>(in, out, C, R, units); break;
+            case 4: fold_unfold_vec_kernel<4, kFold><<<grid, 256, 0, s>>>(in, out, C, R, units); break;
+            case 8: fold_unfold_vec_kernel<8, kFold><<<grid, 256, 0, s>>>(in, out, C, R, units); break;
+            default: fold_unfold_vec_kernel<16, kFold><<<grid, 256, 0, s>>>(in, out, C, R, units); break;
+        }
+    } else {
+        fold_unfold_kernel<kFold><<<rf_grid_1d(total, 256), 256, 0, s>>>(in, out, B, C, R, E);
+    }
+    return 0;
+}
+
 extern "C" int rf_unfold3d(const float* x, float* out, int B, int C, int S, int E, void* stream) {
     RF_CHECK_ARG(x && out, "rf_unfold3d: null pointer");
     RF_CHECK_ARG(B > 0 && C > 0 && S > 0 && E > 0 && S % E == 0, "rf_unfold3d: bad shape B=%d C=%d S=%d E=%d", B, C, S, E);
-    const long total = (long)B * C * S * S * S;
-    fold_unfold_kernel<false><<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, C, S / E, E);
+    launch_fold_unfold<false>(x, out, B, C, S / E, E, (cudaStream_t)stream);
     RF_LAUNCH_OK("fold_unfold_kernel<unfold>");
     return 0;
 }
@@ -44,8 +118,7 @@ extern "C" int rf_unfold3d(const float* x, float* out, int B, int C, int S, int 
 extern "C" int rf_fold3d(const float* x, float* out, int B, int C, int R, int E, void* stream) {
     RF_CHECK_ARG(x && out, "rf_fold3d: null pointer");
     RF_CHECK_ARG(B > 0 && C > 0 && R > 0 && E > 0, "rf_fold3d: bad shape B=%d C=%d R=%d E=%d", B, C, R, E);
-    const long total = (long)B * C * R * R * R * E * E * E;
-    fold_unfold_kernel<true><<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, C, R, E);
+    launch_fold_unfold<true>(x, out, B, C, R, E, (cudaStream_t)stream);
     RF_LAUNCH_OK("fold_unfold_kernel<fold>");
     return 0;
 }
@@ -80,6 +153,42 @@ __global__ void __launch_bounds__(256) pad_unfold_kernel(const float* __restrict
     }
 }
 
+// Same, one thread per z-run of the patch (kernel z extent a multiple of 4, 16-byte aligned output): the index
+// decomposition happens once per run, stores are float4, and 32-bit arithmetic suffices.
+__global__ void __launch_bounds__(256) pad_unfold_rows_kernel(const float* __restrict__ x, float* __restrict__ out, int C,
+                                                              Int3 size, Int3 kernel, Int3 pad, Int3 stride, Int3 cnt,
+                                                              float pad_val, float norm_sub, float norm_div, int total_runs) {
+    const int KZ = kernel.v[2];
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total_runs; r += gridDim.x * blockDim.x) {
+        int t = r;
+        const int ky = t % kernel.v[1]; t /= kernel.v[1];
+        const int kx = t % kernel.v[0]; t /= kernel.v[0];
+        const int c = t % C; t /= C;
+        const int iz = t % cnt.v[2]; t /= cnt.v[2];
+        const int iy = t % cnt.v[1]; t /= cnt.v[1];
+        const int ix = t % cnt.v[0];
+        const int b = t / cnt.v[0];
+        const int sx = ix * stride.v[0] + kx - pad.v[0];
+        const int sy = iy * stride.v[1] + ky - pad.v[1];
+        const int sz0 = iz * stride.v[2] - pad.v[2];
+        const bool row_in = sx >= 0 && sx < size.v[0] && sy >= 0 && sy < size.v[1];
+        const float* src = x + ((((long)b * C + c) * size.v[0] + sx) * size.v[1] + sy) * size.v[2];
+        float4* dst = reinterpret_cast<float4*>(out + (long)r * KZ);
+        for (int k0 = 0; k0 < KZ; k0 += 4) {
+            float f[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int sz = sz0 + k0 + e;
+                float v = pad_val;
+                if (row_in && sz >= 0 && sz < size.v[2]) v = __ldg(src + sz);
+                if (norm_div != 0.f) v = __fdiv_rn(__fsub_rn(v, norm_sub), norm_div);
+                f[e] = v;
+            }
+            dst[k0 >> 2] = make_float4(f[0], f[1], f[2], f[3]);
+        }
+    }
+}
+
 extern "C" int rf_unfold3d_pad_stride(const float* x, float* out, int B, int C, const int size[3], const int kernel[3],
                                       const int pad[3], const int stride[3], float pad_val, float norm_sub,
                                       float norm_div, void* stream) {
@@ -94,8 +203,14 @@ extern "C" int rf_unfold3d_pad_stride(const float* x, float* out, int B, int C, 
         total *= (long)cnt.v[a] * kernel[a];
     }
     RF_CHECK_ARG(B > 0 && C > 0, "rf_unfold3d_pad_stride: bad B/C");
-    pad_unfold_kernel<<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, C, s, k, p, st, cnt, pad_val,
-                                                                               norm_sub, norm_div);
+    if (kernel[2] % 4 == 0 && ((uintptr_t)out & 15) == 0 && total / kernel[2] < (1L << 31)) {
+        const int runs = (int)(total / kernel[2]);
+        pad_unfold_rows_kernel<<<rf_grid_1d(runs, 256, 148 * 64), 256, 0, (cudaStream_t)stream>>>(x, out, C, s, k, p, st, cnt, pad_val,
+                                                                                                 norm_sub, norm_div, runs);
+    } else {
+        pad_unfold_kernel<<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, C, s, k, p, st, cnt, pad_val,
+                                                                                   norm_sub, norm_div);
+    }
     RF_LAUNCH_OK("pad_unfold_kernel");
     return 0;
 }
@@ -179,6 +294,24 @@ __global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ 
     float* o = out + ((long)c * K + k) * csz.v[0] * csz.v[1] * csz.v[2];
     const float* s = store + (long)(scene < 0 ? 0 : scene) * ssz.v[0] * ssz.v[1] * ssz.v[2];
     const int n = ex * ey * ez;
+    // fast path: the whole block lies inside the scene and every z-run is 16-byte aligned on both sides -> float4 moves
+    const bool inside = scene >= 0 && scene < n_scenes && X0 >= 0 && Y0 >= 0 && Z0 >= 0 && X0 + ex <= X1 && Y0 + ey <= Y1 &&
+                        Z0 + ez <= Z1 && X1 <= ssz.v[0] && Y1 <= ssz.v[1] && Z1 <= ssz.v[2];
+    if (inside && (ez & 3) == 0 && (Z0 & 3) == 0 && (de[4] & 3) == 0 && (ssz.v[2] & 3) == 0 && (csz.v[2] & 3) == 0 &&
+        (((uintptr_t)store | (uintptr_t)out) & 15) == 0) {
+        const int ez4 = ez >> 2;
+        for (int i = threadIdx.x; i < ex * ey * ez4; i += blockDim.x) {
+            const int z = (i % ez4) << 2, y = (i / ez4) % ey, x = i / (ez4 * ey);
+            float4 v = __ldg(reinterpret_cast<const float4*>(s + ((long)(X0 + x) * ssz.v[1] + (Y0 + y)) * ssz.v[2] + Z0 + z));
+            v.x = __fmul_rn(v.x, ratio); v.y = __fmul_rn(v.y, ratio); v.z = __fmul_rn(v.z, ratio); v.w = __fmul_rn(v.w, ratio);
+            if (norm_div != 0.f) {
+                v.x = __fdiv_rn(__fsub_rn(v.x, norm_sub), norm_div); v.y = __fdiv_rn(__fsub_rn(v.y, norm_sub), norm_div);
+                v.z = __fdiv_rn(__fsub_rn(v.z, norm_sub), norm_div); v.w = __fdiv_rn(__fsub_rn(v.w, norm_sub), norm_div);
+            }
+            *reinterpret_cast<float4*>(o + ((long)(de[0] + x) * csz.v[1] + (de[2] + y)) * csz.v[2] + (de[4] + z)) = v;
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int z = i % ez, y = (i / ez) % ey, x = i / (ez * ey);
         float v = fill;

@@ -493,12 +493,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_kernel(const ConvArgs a
             tc_ld32(tmem_base + ((uint32_t)(pw * 32) << 16) + (uint32_t)c0, v);
             if (m < a.M) {
 #pragma unroll
+                for (int t = 0; t < 32; ++t) v[t] = fmaf(v[t], a.out_scale, (a.bias && c0 + t < a.Cout) ? __ldg(a.bias + c0 + t) : 0.f);
+                rf_act_vec(v, a.act, a.slope);
+#pragma unroll
                 for (int t = 0; t < 32; ++t) {
                     const int co = c0 + t;
                     if (co < a.Cout) {
-                        const float o = rf_act(fmaf(v[t], a.out_scale, a.bias ? __ldg(a.bias + co) : 0.f), a.act, a.slope);
-                        if (a.out_ncdhw) a.y[((long)(m / So) * a.Cout + co) * So + (m % So)] = o;
-                        else a.y[(long)m * a.Cout + co] = o;
+                        if (a.out_ncdhw) a.y[((long)(m / So) * a.Cout + co) * So + (m % So)] = v[t];
+                        else a.y[(long)m * a.Cout + co] = v[t];
                     }
                 }
             }

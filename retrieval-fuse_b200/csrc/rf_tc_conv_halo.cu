@@ -28,12 +28,13 @@
 //   * Single-chunk inputs (C <= 8) pair two taps into one K = 16 step: LBO = 16 B makes
 //     the second K chunk the neighbouring slot, i.e. tap kw+1.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "rf_common.cuh"
 
 namespace {
 
-constexpr int TM = 128, NTHREADS = 256, NB = 4, MAX_ABUF = 2;
+constexpr int TM = 128, NTHREADS = 384, NB = 4, MAX_ABUF = 2;
 constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in maximum per CTA on sm_100
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,6 +72,17 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
         if (++spins > (1u << 26)) __trap();  // a pipeline bug must never hang the GPU
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// same, polling gently: the epilogue warps wait for a whole item's MMAs
+__device__ __forceinline__ void mbar_wait_warp_sleepy(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        __nanosleep(100);
+        if (++spins > (1u << 24)) __trap();
     }
 }
 // Producer-side wait: these threads wait for a long time (a whole stage of MMAs); polling at full speed would
@@ -163,12 +175,12 @@ __device__ __forceinline__ void split_f16(float x, uint32_t& hi, uint32_t& lo) {
 struct SplitArgs {
     const float *x, *x2, *mu, *a, *beta;
     uint4 *hi, *lo;
-    int N, D, H, W, C1, C2, CC1, CC, CCe;
+    int N, D, H, W, C1, C2, CC1, CC, CCe, pad;
     float scale;
 };
 
 __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs s) {
-    const int Dp = s.D + 2, Hp = s.H + 2, Wp = s.W + 2;
+    const int Dp = s.D + 2 * s.pad, Hp = s.H + 2 * s.pad, Wp = s.W + 2 * s.pad;
     const long V = (long)Dp * Hp * Wp;
     const long total = (long)s.CCe * s.N * V;
     const int c_tot = s.C1 + s.C2;
@@ -180,8 +192,8 @@ __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs
         const int n = (int)(t % s.N);
         const int cc = (int)(t / s.N);
         uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
-        if (cc < s.CC && ww >= 1 && ww <= s.W && hh >= 1 && hh <= s.H && dd >= 1 && dd <= s.D) {
-            const int d = dd - 1, hq = hh - 1, w = ww - 1;
+        if (cc < s.CC && ww >= s.pad && ww < s.W + s.pad && hh >= s.pad && hh < s.H + s.pad && dd >= s.pad && dd < s.D + s.pad) {
+            const int d = dd - s.pad, hq = hh - s.pad, w = ww - s.pad;
             const float* src;
             int C, c0, goff;
             if (cc < s.CC1) {
@@ -265,6 +277,9 @@ __global__ void __launch_bounds__(256) halo_weight_image_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------ the convolution
+// phase timestamps of CTA 0's first items (tuning aid, read back by rf_tc_conv3d_halo_debug_read)
+__device__ long long g_halo_dbg[64];
+
 struct HaloArgs {
     const uint8_t *hi, *lo, *wimg;
     const float* bias;
@@ -276,12 +291,17 @@ struct HaloArgs {
     int lines, n_wblk, n_tiles, P;  // P = slots per staged plane (incl. over-read slack)
     int S_st;                     // staged slots per plane that the bulk copies fill
     int pair, n_stages, nbuf, ck, kpg;
-    int Cout, Npad, act, out_ncdhw, n_acc, n_iss;
+    int Cout, Npad, act, out_ncdhw, n_acc, n_iss, n_items;
     float slope, out_scale;
     uint32_t bslot_bytes, tmem_cols;
     uint16_t tile_off[32];        // first slot of M tile t within the staged block (uniform-indexed constant loads)
 };
 
+// Persistent: CTA c walks over items c, c + gridDim.x, ...  Barriers, TMEM and the zeroed staging buffers are set
+// up once; the producers run ahead into the next item while the epilogue warps drain the accumulators, so launch,
+// allocation and first-load latency (10-30 thousand cycles per item when every item was its own CTA) are paid once
+// per CTA instead of once per item.
+//   warp 0: activation producer   warp 3: weight producer   warps 1,2,4-7: MMA issuers   warps 8-11: epilogue
 __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -293,94 +313,88 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloA
     const uint32_t bars = sB + NB * a.bslot_bytes;
     const uint32_t bar_afull = bars, bar_aempty = bars + 8 * MAX_ABUF;
     const uint32_t bar_bfull = bars + 16 * MAX_ABUF, bar_bempty = bar_bfull + 8 * NB;
-    const uint32_t bar_dfull = bar_bempty + 8 * NB;
-    const uint32_t tmem_slot = bar_dfull + 8;
+    const uint32_t bar_dfull = bar_bempty + 8 * NB, bar_dempty = bar_dfull + 8;
+    const uint32_t tmem_slot = bar_dempty + 8;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp: uniform register
-
-    // ---- item geometry
-    int n0, gact, d0, h0;
-    if (a.stacked) {
-        n0 = blockIdx.x * a.G; gact = min(a.G, a.N - n0); d0 = 0; h0 = 0;
-    } else {
-        const int per = a.n_dt * a.n_ht;
-        n0 = blockIdx.x / per; gact = 1;
-        const int r = blockIdx.x % per;
-        d0 = (r / a.n_ht) * a.Dt; h0 = (r % a.n_ht) * a.Ht;
-    }
+    const bool resident = a.n_stages == 1;  // one stage per item: loaded once, used by both accumulation passes
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nbuf; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, a.n_iss); }
         for (int s = 0; s < NB; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, a.n_iss); }
         mbar_init(bar_dfull, a.n_iss);
+        mbar_init(bar_dempty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(a.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // Zero what the bulk copies never fill (over-read slack, missing samples of a ragged last item): operand rows
-    // that touch it are dropped, but in pair mode a REAL row multiplies one such slot by a zero weight, and
-    // 0 * NaN would poison it.
+    // Zero the staging buffers once: the bulk copies never fill the over-read slack (nor the missing samples of a
+    // ragged last item).  Operand rows that touch it are dropped, but in pair mode a REAL row multiplies one such
+    // slot by a zero weight, and 0 * NaN would poison it; later items leave finite values there.
     {
-        const int filled = a.stacked ? gact * (int)a.V : a.S_st;
-        const int per_plane = a.P - filled;
-        const int total = a.nbuf * planes * per_plane;
-        for (int i = threadIdx.x; i < total; i += NTHREADS) {
-            const int pl = i / per_plane, o = i % per_plane;
-            *reinterpret_cast<uint4*>(smem_al + ((size_t)pl * a.P + filled + o) * 16) = make_uint4(0, 0, 0, 0);
-        }
+        const int total = a.nbuf * planes * a.P;
+        for (int i = threadIdx.x; i < total; i += NTHREADS) *reinterpret_cast<uint4*>(smem_al + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    const int per_sample = a.n_dt * a.n_ht;
 
     if (warp == 0) {
       if (lane == 0) {
-        // ---- activation producer: one stage = ck channel chunks x (hi, lo) planes of the item's haloed block
+        // ---- activation producer: one stage = ck channel chunks x (hi, lo) planes of the item's haloed block; two
+        // passes over the channel stages (cross products first, then hi * hi; see the issuers)
         const long slab = (long)a.Hp * a.Wp;
-        // Two passes over the channel stages (cross products first, then hi * hi; see the issuers).  With a single
-        // stage the block stays resident and is loaded once.
-        const int n_loads = a.n_stages == 1 ? 1 : 2 * a.n_stages;
-        for (int l = 0; l < n_loads; ++l) {
-            const int s = l >= a.n_stages ? l - a.n_stages : l;
-            const int b = l % a.nbuf;
-            mbar_wait_relaxed(bar_aempty + 8 * b, ((uint32_t)(l / a.nbuf) & 1u) ^ 1u);
+        const int n_loads = resident ? 1 : 2 * a.n_stages;
+        uint32_t lc = 0;
+        for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+            int n0, gact = 1, d0 = 0, h0 = 0;
+            if (a.stacked) { n0 = item * a.G; gact = min(a.G, a.N - n0); }
+            else { n0 = item / per_sample; const int r = item % per_sample; d0 = (r / a.n_ht) * a.Dt; h0 = (r % a.n_ht) * a.Ht; }
             const bool one_copy = a.stacked || a.Ht == a.H;
             const uint32_t plane_bytes = a.stacked ? (uint32_t)(gact * a.V) * 16u : (uint32_t)a.S_st * 16u;
-            mbar_arrive_expect_tx(bar_afull + 8 * b, plane_bytes * planes);
-            for (int pl = 0; pl < planes; ++pl) {
-                const int hl = pl / a.ck, c = pl % a.ck;
-                const long cc = (long)s * a.ck + c;
-                const uint8_t* src = (hl ? a.lo : a.hi) + (cc * a.plane_slots + (long)n0 * a.V) * 16;
-                const uint32_t dst = sA + b * abuf_bytes + (uint32_t)pl * (uint32_t)a.P * 16u;
-                if (one_copy) {
-                    bulk_g2s(dst, src + (long)d0 * slab * 16, plane_bytes, bar_afull + 8 * b);
-                } else {
-                    const uint32_t row_bytes = (uint32_t)(a.Hs * a.Wp) * 16u;
-                    for (int dd = 0; dd < a.Dt + 2; ++dd)
-                        bulk_g2s(dst + dd * row_bytes, src + ((long)(d0 + dd) * slab + (long)h0 * a.Wp) * 16, row_bytes,
-                                 bar_afull + 8 * b);
+            for (int l = 0; l < n_loads; ++l, ++lc) {
+                const int s = l >= a.n_stages ? l - a.n_stages : l;
+                const uint32_t b = lc % (uint32_t)a.nbuf;
+                mbar_wait_relaxed(bar_aempty + 8 * b, ((lc / (uint32_t)a.nbuf) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(bar_afull + 8 * b, plane_bytes * planes);
+                for (int pl = 0; pl < planes; ++pl) {
+                    const int hl = pl / a.ck, c = pl % a.ck;
+                    const long cc = (long)s * a.ck + c;
+                    const uint8_t* src = (hl ? a.lo : a.hi) + (cc * a.plane_slots + (long)n0 * a.V) * 16;
+                    const uint32_t dst = sA + b * abuf_bytes + (uint32_t)pl * (uint32_t)a.P * 16u;
+                    if (one_copy) {
+                        bulk_g2s(dst, src + (long)d0 * slab * 16, plane_bytes, bar_afull + 8 * b);
+                    } else {
+                        const uint32_t row_bytes = (uint32_t)(a.Hs * a.Wp) * 16u;
+                        for (int dd = 0; dd < a.Dt + 2; ++dd)
+                            bulk_g2s(dst + dd * row_bytes, src + ((long)(d0 + dd) * slab + (long)h0 * a.Wp) * 16, row_bytes,
+                                     bar_afull + 8 * b);
+                    }
                 }
             }
         }
       }
     } else if (warp == 3) {
       if (lane == 0) {
-        // ---- weight producer: ring of (kd,kh) groups
-        const int per_pass = a.n_stages * 9, total = 2 * per_pass;
-        for (int gi = 0; gi < total; ++gi) {
-            const int sl = gi % NB;
-            const int img = gi >= per_pass ? gi - per_pass : gi;  // second pass streams the same groups again
-            mbar_wait_relaxed(bar_bempty + 8 * sl, ((uint32_t)(gi / NB) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(bar_bfull + 8 * sl, a.bslot_bytes);
-            bulk_g2s(sB + sl * a.bslot_bytes, a.wimg + (long)img * a.bslot_bytes, a.bslot_bytes, bar_bfull + 8 * sl);
-        }
+        // ---- weight producer: ring of (kd,kh) groups; the second pass of every item streams the same groups again
+        const int per_pass = a.n_stages * 9;
+        uint32_t gc = 0;
+        for (int item = blockIdx.x; item < a.n_items; item += gridDim.x)
+            for (int gi = 0; gi < 2 * per_pass; ++gi, ++gc) {
+                const uint32_t sl = gc % NB;
+                const int img = gi >= per_pass ? gi - per_pass : gi;
+                mbar_wait_relaxed(bar_bempty + 8 * sl, ((gc / NB) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(bar_bfull + 8 * sl, a.bslot_bytes);
+                bulk_g2s(sB + sl * a.bslot_bytes, a.wimg + (long)img * a.bslot_bytes, a.bslot_bytes, bar_bfull + 8 * sl);
+            }
       }
-    } else {
+    } else if (warp < 8) {
         // ---- MMA issuers: warps 1, 2, 4, 5, 6, 7 -> issuer 0..5; issuer i owns the M tiles t = i (mod n_iss).
         // One warp cannot feed the tensor pipe here: every tcgen05.mma needs its descriptors moved from vector to
         // uniform registers (R2UR) under an elected lane, ~150 cycles per MMA measured, while the pipe needs 39-48
@@ -406,98 +420,119 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloA
             // MMA count).  So the two small cross products (hi*lo, lo*hi: 2^-11 of the result) of ALL taps and
             // stages are accumulated first, while the accumulator is tiny, and the hi*hi products in a second pass
             // over the stages: a third of the accumulations happen at full magnitude.
-            const bool resident = a.n_stages == 1;
-            for (int vs = 0; vs < 2 * a.n_stages; ++vs) {
-                const int pass = vs >= a.n_stages ? 1 : 0;
-                const int b = resident ? 0 : vs % a.nbuf;
-                if (!resident || vs == 0) mbar_wait_warp(bar_afull + 8 * b, (uint32_t)(vs / a.nbuf) & 1u);
+            uint32_t lc = 0, gc = 0, it = 0;
+            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
+                const bool dbg = blockIdx.x == 0 && iss == 0 && leader && it < 6;
+                if (dbg) g_halo_dbg[it * 8 + 0] = clock64();
+                mbar_wait_warp(bar_dempty, (it & 1u) ^ 1u);  // the epilogue has drained the previous item's accumulators
                 tc_fence_after();
-                const uint32_t abase = (((sA + b * abuf_bytes) & 0x3FFFFu) >> 4) | a_lbo;
-                for (int g = 0; g < 9; ++g) {
-                    const int gi = vs * 9 + g, sl = gi % NB;
-                    mbar_wait_warp(bar_bfull + 8 * sl, (uint32_t)(gi / NB) & 1u);
-                    tc_fence_after();
-                    const int kd = g / 3, kh = g % 3;
-                    const uint32_t bbase = (((sB + sl * a.bslot_bytes) & 0x3FFFFu) >> 4) | b_lbo;
-                    for (int ks = 0; ks < a.kpg; ++ks) {
-                        const uint32_t koff = (uint32_t)((kd * a.Hs + kh) * a.Wp + (a.pair ? 2 * ks : ks));
-                        const uint32_t b_hi = bbase + (uint32_t)ks * 2u * blk_u, b_lo = b_hi + blk_u;
-                        const uint32_t acc = (vs | g | ks) ? 1u : 0u;  // the very first MMA of a tile overwrites its accumulator
-                        for (int t = iss; t < a.n_tiles; t += a.n_iss) {
-                            const uint32_t d = tmem_u + (uint32_t)t * npad;
-                            const uint32_t da = abase + koff + a.tile_off[t];
-                            if (pass == 0) {
-                                tc_mma2(d, da, a_hi32, b_lo, b_hi32, idesc, acc, leader);          // hi * lo
-                                tc_mma2(d, da + lo_off, a_hi32, b_hi, b_hi32, idesc, 1u, leader);  // lo * hi
-                            } else {
-                                tc_mma2(d, da, a_hi32, b_hi, b_hi32, idesc, 1u, leader);           // hi * hi
+                if (dbg) g_halo_dbg[it * 8 + 1] = clock64();
+                uint32_t b = 0;
+                for (int vs = 0; vs < 2 * a.n_stages; ++vs) {
+                    const int pass = vs >= a.n_stages ? 1 : 0;
+                    if (!resident || vs == 0) {
+                        b = lc % (uint32_t)a.nbuf;
+                        mbar_wait_warp(bar_afull + 8 * b, (lc / (uint32_t)a.nbuf) & 1u);
+                        tc_fence_after();
+                        if (dbg && vs == 0) g_halo_dbg[it * 8 + 2] = clock64();
+                    }
+                    const uint32_t abase = (((sA + b * abuf_bytes) & 0x3FFFFu) >> 4) | a_lbo;
+                    for (int g = 0; g < 9; ++g, ++gc) {
+                        const uint32_t sl = gc % NB;
+                        mbar_wait_warp(bar_bfull + 8 * sl, (gc / NB) & 1u);
+                        tc_fence_after();
+                        const int kd = g / 3, kh = g % 3;
+                        const uint32_t bbase = (((sB + sl * a.bslot_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+                        for (int ks = 0; ks < a.kpg; ++ks) {
+                            const uint32_t koff = (uint32_t)((kd * a.Hs + kh) * a.Wp + (a.pair ? 2 * ks : ks));
+                            const uint32_t b_hi = bbase + (uint32_t)ks * 2u * blk_u, b_lo = b_hi + blk_u;
+                            const uint32_t acc = (vs | g | ks) ? 1u : 0u;  // the very first MMA of a tile overwrites its accumulator
+                            for (int t = iss; t < a.n_tiles; t += a.n_iss) {
+                                const uint32_t d = tmem_u + (uint32_t)t * npad;
+                                const uint32_t da = abase + koff + a.tile_off[t];
+                                if (pass == 0) {
+                                    tc_mma2(d, da, a_hi32, b_lo, b_hi32, idesc, acc, leader);          // hi * lo
+                                    tc_mma2(d, da + lo_off, a_hi32, b_hi, b_hi32, idesc, 1u, leader);  // lo * hi
+                                } else {
+                                    tc_mma2(d, da, a_hi32, b_hi, b_hi32, idesc, 1u, leader);           // hi * hi
+                                }
                             }
                         }
+                        if (leader) tc_commit(bar_bempty + 8 * sl);
                     }
-                    if (leader) tc_commit(bar_bempty + 8 * sl);
+                    if (!resident || vs == 2 * a.n_stages - 1) {
+                        if (leader) tc_commit(bar_aempty + 8 * b);
+                        ++lc;
+                    }
                 }
-                if (!resident && leader) tc_commit(bar_aempty + 8 * b);
+                if (leader) tc_commit(bar_dfull);
+                if (dbg) g_halo_dbg[it * 8 + 3] = clock64();
+                __syncwarp();
             }
-            if (leader) tc_commit(bar_dfull);
-            __syncwarp();
-            if (iss == 0) mbar_wait_warp(bar_dfull, 0);  // the only warp that polls; all others sleep in the barrier below
         }
-    }
-    tc_fence_before();
-    __syncthreads();
-    // ---- epilogue (all 8 warps): warp % 4 = TMEM lane quadrant, warp / 4 = tile parity
-    tc_fence_after();
-    {
+    } else {
+        // ---- epilogue warps 8..11: warp % 4 = TMEM lane quadrant; one thread <-> one GEMM row of every tile
         const int q = warp & 3;
         const long So = (long)a.D * a.H * a.W;
         const bool vec4 = !a.out_ncdhw && (a.Cout & 3) == 0;
-        for (int t = warp >> 2; t < a.n_tiles; t += 2) {
-            const int r = q * 32 + lane;
-            int line, w;
-            if (a.lines) {
-                line = (t / a.n_wblk) * 16 + (r >> 3);
-                w = (t % a.n_wblk) * 8 + (r & 7);
-            } else {
-                const int R = t * 128 + r;
-                line = R / a.Wp; w = R % a.Wp;
-            }
-            const int g = a.stacked ? line / a.Ls : 0;
-            const int rem = a.stacked ? line % a.Ls : line;
-            const int dd = rem / a.Hs, hh = rem % a.Hs;
-            const bool valid = g < gact && dd < a.Dt && hh < a.Ht && w < a.W;
-            const long vox = valid ? ((((long)(n0 + g) * a.D + d0 + dd) * a.H + h0 + hh) * a.W + w) : 0;
-            for (int c0 = 0; c0 < a.Npad; c0 += 16) {
-                float v[16];
-                tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * a.Npad + c0), v);
-                for (int set = 1; set < a.n_acc; ++set) {
-                    float u[16];
-                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((set * a.n_tiles + t) * a.Npad + c0), u);
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] += u[e];
-                }
-                if (!valid) continue;
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int co = c0 + e;
-                    const float bb = (a.bias && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
-                    v[e] = rf_act(fmaf(v[e], a.out_scale, bb), a.act, a.slope);
-                }
-                if (vec4) {
-                    float* dst = a.y + vox * a.Cout + c0;
-#pragma unroll
-                    for (int e = 0; e < 16; e += 4)
-                        if (c0 + e < a.Cout) *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-                } else if (a.out_ncdhw) {
-                    const long nn = vox / So, sp = vox % So;
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        if (c0 + e < a.Cout) a.y[(nn * a.Cout + c0 + e) * So + sp] = v[e];
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
+            int n0, gact = 1, d0 = 0, h0 = 0;
+            if (a.stacked) { n0 = item * a.G; gact = min(a.G, a.N - n0); }
+            else { n0 = item / per_sample; const int r = item % per_sample; d0 = (r / a.n_ht) * a.Dt; h0 = (r % a.n_ht) * a.Ht; }
+            const bool dbg = blockIdx.x == 0 && threadIdx.x == 256 && it < 6;
+            if (dbg) g_halo_dbg[it * 8 + 4] = clock64();
+            mbar_wait_warp_sleepy(bar_dfull, it & 1u);
+            tc_fence_after();
+            if (dbg) g_halo_dbg[it * 8 + 5] = clock64();
+            for (int t = 0; t < a.n_tiles; ++t) {
+                const int r = q * 32 + lane;
+                int line, w;
+                if (a.lines) {
+                    line = (t / a.n_wblk) * 16 + (r >> 3);
+                    w = (t % a.n_wblk) * 8 + (r & 7);
                 } else {
+                    const int R = t * 128 + r;
+                    line = R / a.Wp; w = R % a.Wp;
+                }
+                const int g = a.stacked ? line / a.Ls : 0;
+                const int rem = a.stacked ? line % a.Ls : line;
+                const int dd = rem / a.Hs, hh = rem % a.Hs;
+                const bool valid = g < gact && dd < a.Dt && hh < a.Ht && w < a.W;
+                const long vox = valid ? ((((long)(n0 + g) * a.D + d0 + dd) * a.H + h0 + hh) * a.W + w) : 0;
+                for (int c0 = 0; c0 < a.Npad; c0 += 16) {
+                    float v[16];
+                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * a.Npad + c0), v);
+                    if (!valid) continue;
+                    if (a.bias) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        if (c0 + e < a.Cout) a.y[vox * a.Cout + c0 + e] = v[e];
+                        for (int e = 0; e < 16; ++e) v[e] = fmaf(v[e], a.out_scale, c0 + e < a.Cout ? __ldg(a.bias + c0 + e) : 0.f);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] *= a.out_scale;
+                    }
+                    rf_act_vec(v, a.act, a.slope);
+                    if (vec4) {
+                        float* dst = a.y + vox * a.Cout + c0;
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4)
+                            if (c0 + e < a.Cout) *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                    } else if (a.out_ncdhw) {
+                        const long nn = vox / So, sp = vox % So;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e)
+                            if (c0 + e < a.Cout) a.y[(nn * a.Cout + c0 + e) * So + sp] = v[e];
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e)
+                            if (c0 + e < a.Cout) a.y[vox * a.Cout + c0 + e] = v[e];
+                    }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_dempty);  // 4 arrivals: the accumulators may be overwritten
+            if (dbg) g_halo_dbg[it * 8 + 6] = clock64();
         }
     }
     tc_fence_before();
@@ -511,7 +546,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloA
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct Geo {
-    int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, n_acc;
+    int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, n_acc, two_resident;
     uint32_t tmem_cols, bslot;
     size_t smem;
     double score;
@@ -522,21 +557,20 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, Ge
     const int Dp = D + 2, Hp = H + 2, Wp = W + 2;
     const long V = (long)Dp * Hp * Wp;
     const int ck = pair ? 1 : 2, planes = 2 * ck, kpg = pair ? 2 : 3;
-    const int n_stages = pair ? 1 : CCe / 2, nbuf = n_stages < 2 ? 1 : 2;
+    const int n_stages = pair ? 1 : CCe / 2;
     const uint32_t bslot = (uint32_t)kpg * 2u * (uint32_t)Npad * 32u;
     const long avail = (long)SMEM_LIMIT - 1024 - 256 - (long)NB * bslot;
     best.score = -1.0;
     auto consider = [&](int stacked, int G, int Dt, int Ht, int lines) {
-        if (lines && W % 8 != 0) return;
         const int Hs = stacked ? Hp : Ht + 2;
         const long S_st = stacked ? (long)G * V : (long)(Dt + 2) * Hs * Wp;
         const long lines_needed = stacked ? (long)(G - 1) * Dp * Hp + (long)(D - 1) * Hp + H : (long)(Dt - 1) * Hs + Ht;
         long n_tiles, max_slot;
-        const int n_wblk = lines ? W / 8 : 1;
+        const int n_wblk = lines ? (W + 7) / 8 : 1;
         if (lines) {
             const long lb = (lines_needed + 15) / 16;
             n_tiles = lb * n_wblk;
-            max_slot = (lb * 16 - 1 + 2L * Hs + 2) * Wp + (W - 1) + 2 + 1;
+            max_slot = (lb * 16 - 1 + 2L * Hs + 2) * Wp + (n_wblk * 8 - 1) + 2 + 1;
         } else {
             const long rows = (lines_needed - 1) * Wp + W;
             n_tiles = (rows + 127) / 128;
@@ -544,32 +578,44 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, Ge
         }
         long P = max_slot + 1 > S_st ? max_slot + 1 : S_st;
         P = (P + 7) / 8 * 8;
-        if (n_tiles * Npad > 512 || P * 16 >= (1L << 18)) return;
-        const long smemA = (long)nbuf * planes * P * 16;
+        if (n_tiles * Npad > 512 || n_tiles > 32 || P * 16 >= (1L << 18)) return;
+        // two staging buffers whenever they fit: the next stage (or the next item's block) loads during the MMAs
+        const long smemA1 = (long)planes * P * 16;
+        const int nbuf = 2 * smemA1 <= avail ? 2 : 1;
+        if (nbuf == 1 && n_stages > 1) return;
+        const long smemA = nbuf * smemA1;
         if (smemA > avail || S_st * 16 * planes >= (1L << 20)) return;
         const long outputs = stacked ? (long)G * D * H * W : (long)Dt * Ht * W;
         const long n_items = stacked ? (N + G - 1) / G : (long)N * (D / Dt) * (H / Ht);
-        // cost model: ~34 cycles per 128-row MMA (operand reads from shared memory bound it, not N) plus a
-        // per-item prologue / epilogue that only overlaps with another CTA's MMAs when two CTAs fit on an SM
+        // cost model (persistent CTAs): ~34-48 cycles per 128-row MMA (operand reads from shared memory bound it,
+        // not N) plus the epilogue, which only overlaps with MMAs when a second CTA shares the SM
         const int n_acc = 1;  // accumulator sets per tile (summed in the epilogue); one is enough, see mma_pattern.cu
         uint32_t cols_needed = 32;
         while ((long)cols_needed < n_tiles * Npad * n_acc) cols_needed <<= 1;
         const long smem_total = 1024 + smemA + (long)NB * bslot + 256;
         const bool two_resident = smem_total <= 113 * 1024 && cols_needed <= 256;
         const double n_mma = (double)n_stages * 9 * kpg * (double)n_tiles * 3.0;
-        const double t_item = n_mma * 34.0 + (two_resident ? 1500.0 : 5000.0);
-        const double fill = n_items >= 148 ? 1.0 : (double)n_items / 148.0;
-        const double score = (double)outputs / t_item * fill;
+        const double t_epi = 1500.0 + (double)n_tiles * (Npad / 16) * 250.0 + (nbuf == 1 ? 4000.0 : 0.0);
+        const double t_item = n_mma * (Npad > 32 ? 48.0 : 40.0) + (two_resident ? 0.3 : 1.0) * t_epi;
+        const double waves = (double)((n_items + 147) / 148);   // items every SM walks through (the tensor pipe is per SM)
+        const double score = (double)outputs * (double)n_items / (waves * t_item);
         if (score > best.score) {
             best.Dt = stacked ? D : Dt; best.Ht = stacked ? H : Ht; best.Hs = Hs; best.G = stacked ? G : 1; best.stacked = stacked;
             best.lines = lines; best.n_wblk = n_wblk; best.n_tiles = (int)n_tiles; best.P = (int)P; best.S_st = (int)S_st;
-            best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot;
+            best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot; best.two_resident = two_resident ? 1 : 0;
             best.tmem_cols = cols_needed;
             best.n_acc = n_acc;
             best.smem = (size_t)(1024 + smemA + (long)NB * bslot + 256);
             best.score = score;
         }
     };
+    if (const char* e = getenv("RF_HALO_GEO")) {  // tuning aid: "stacked,G,Dt,Ht,lines" forces the item shape
+        int st, G, Dt, Ht, ln;
+        if (sscanf(e, "%d,%d,%d,%d,%d", &st, &G, &Dt, &Ht, &ln) == 5) {
+            consider(st, G, st ? D : Dt, st ? H : Ht, ln);
+            return best.score > 0.0;
+        }
+    }
     for (int lines = 0; lines < 2; ++lines) {
         for (int G = 1; G <= 64 && G <= N; ++G) consider(1, G, D, H, lines);
         for (int Dt = 1; Dt <= D; ++Dt) {
@@ -595,26 +641,27 @@ bool halo_shape(int Cout, int C1, int C2, int& Cp1, int& Cp2, int& CC, int& CCe,
 
 }  // namespace
 
-extern "C" size_t rf_halo_act_bytes(int N, int D, int H, int W, int C1, int C2) {
+extern "C" size_t rf_halo_act_bytes(int N, int D, int H, int W, int C1, int C2, int pad) {
     int Cp1, Cp2, CC, CCe, pair, Npad;
-    if (!halo_shape(16, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad) || N < 1 || D < 1 || H < 1 || W < 1) return 0;
-    return (size_t)CCe * N * (size_t)(D + 2) * (H + 2) * (W + 2) * 16;
+    if (!halo_shape(16, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad) || N < 1 || D < 1 || H < 1 || W < 1 || pad < 0 || pad > 1) return 0;
+    return (size_t)CCe * N * (size_t)(D + 2 * pad) * (H + 2 * pad) * (W + 2 * pad) * 16;
 }
 
 extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a,
-                                     const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, float scale,
+                                     const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, int pad, float scale,
                                      void* stream) {
     int Cp1, Cp2, CC, CCe, pair, Npad;
     RF_CHECK_ARG(halo_shape(16, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad), "rf_cl_norm_split_halo: bad channel counts");
-    RF_CHECK_ARG(hi && lo && (C1 == 0 || x) && (C2 == 0 || x2) && N > 0 && D > 0 && H > 0 && W > 0, "rf_cl_norm_split_halo: bad arguments");
+    RF_CHECK_ARG(hi && lo && (C1 == 0 || x) && (C2 == 0 || x2) && N > 0 && D > 0 && H > 0 && W > 0 && (pad == 0 || pad == 1),
+                 "rf_cl_norm_split_halo: bad arguments");
     RF_CHECK_ARG(C2 == 0 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "rf_cl_norm_split_halo: upsampled input needs even extents");
     RF_CHECK_ARG((gn_mu == nullptr) == (gn_a == nullptr) && (gn_mu == nullptr) == (gn_beta == nullptr), "rf_cl_norm_split_halo: partial GroupNorm arguments");
     RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)x2 & 15) == 0,
                  "rf_cl_norm_split_halo: pointers must be 16-byte aligned");
     SplitArgs s;
     s.x = x; s.x2 = x2; s.mu = gn_mu; s.a = gn_a; s.beta = gn_beta; s.hi = (uint4*)hi; s.lo = (uint4*)lo;
-    s.N = N; s.D = D; s.H = H; s.W = W; s.C1 = C1; s.C2 = C2; s.CC1 = Cp1 / 8; s.CC = CC; s.CCe = CCe; s.scale = scale;
-    const long total = (long)CCe * N * (long)(D + 2) * (H + 2) * (W + 2);
+    s.N = N; s.D = D; s.H = H; s.W = W; s.C1 = C1; s.C2 = C2; s.CC1 = Cp1 / 8; s.CC = CC; s.CCe = CCe; s.pad = pad; s.scale = scale;
+    const long total = (long)CCe * N * (long)(D + 2 * pad) * (H + 2 * pad) * (W + 2 * pad);
     cl_norm_split_halo_kernel<<<rf_grid_1d(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(s);
     RF_LAUNCH_OK("cl_norm_split_halo_kernel");
     return 0;
@@ -640,26 +687,32 @@ extern "C" int rf_tc_conv_halo_weight_image(const float* w, int Cout, int C1, in
     return 0;
 }
 
-/* 1 when rf_tc_conv3d_halo_fwd can run this layer (an item shape fits shared memory and TMEM). */
-extern "C" int rf_tc_conv3d_halo_supported(int N, int D, int H, int W, int Cout, int C1, int C2) {
+/* 1 when rf_tc_conv3d_halo_fwd can run this layer (an item shape fits shared memory and TMEM).  D, H, W are the
+ * INPUT extents; the output extents are D + 2 pad - 2 (pad 1: 'same', pad 0: 'valid'). */
+extern "C" int rf_tc_conv3d_halo_supported(int N, int D, int H, int W, int Cout, int C1, int C2, int pad) {
     int Cp1, Cp2, CC, CCe, pair, Npad;
-    if (!halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad) || N < 1 || D < 1 || H < 1 || W < 1) return 0;
-    if ((long)N * (D + 2) * (H + 2) * (W + 2) * CCe >= (1L << 31)) return 0;
+    if (!halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad) || N < 1 || pad < 0 || pad > 1) return 0;
+    const int Do = D + 2 * pad - 2, Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+    if (Do < 1 || Ho < 1 || Wo < 1) return 0;
+    if ((long)N * (Do + 2) * (Ho + 2) * (Wo + 2) * CCe >= (1L << 31)) return 0;
     Geo g;
-    return choose_geometry(N, D, H, W, CCe, pair, Npad, g) ? 1 : 0;
+    return choose_geometry(N, Do, Ho, Wo, CCe, pair, Npad, g) && g.n_tiles <= 32 ? 1 : 0;
 }
 
 extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y,
-                                     int N, int D, int H, int W, int Cout, int C1, int C2, int act, float slope,
+                                     int N, int D, int H, int W, int pad, int Cout, int C1, int C2, int act, float slope,
                                      float out_scale, int out_ncdhw, void* stream) {
     RF_CHECK_ARG(hi && lo && weight_image && y, "rf_tc_conv3d_halo_fwd: null pointer");
     int Cp1, Cp2, CC, CCe, pair, Npad;
-    RF_CHECK_ARG(halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad) && N > 0 && D > 0 && H > 0 && W > 0,
-                 "rf_tc_conv3d_halo_fwd: unsupported shape Cout=%d C1=%d C2=%d", Cout, C1, C2);
+    RF_CHECK_ARG(halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad) && N > 0 && (pad == 0 || pad == 1),
+                 "rf_tc_conv3d_halo_fwd: unsupported shape Cout=%d C1=%d C2=%d pad=%d", Cout, C1, C2, pad);
     RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)weight_image & 15) == 0 && ((uintptr_t)y & 15) == 0,
                  "rf_tc_conv3d_halo_fwd: pointers must be 16-byte aligned");
+    // from here on D, H, W are the OUTPUT extents; the stored block is (D+2) x (H+2) x (W+2) either way
+    D += 2 * pad - 2; H += 2 * pad - 2; W += 2 * pad - 2;
+    RF_CHECK_ARG(D > 0 && H > 0 && W > 0, "rf_tc_conv3d_halo_fwd: empty output");
     Geo g;
-    RF_CHECK_ARG(choose_geometry(N, D, H, W, CCe, pair, Npad, g), "rf_tc_conv3d_halo_fwd: no item shape fits (N=%d D=%d H=%d W=%d Cout=%d C=%d+%d)",
+    RF_CHECK_ARG(choose_geometry(N, D, H, W, CCe, pair, Npad, g), "rf_tc_conv3d_halo_fwd: no item shape fits (N=%d out %dx%dx%d Cout=%d C=%d+%d)",
                  N, D, H, W, Cout, C1, C2);
     HaloArgs a;
     a.hi = (const uint8_t*)hi; a.lo = (const uint8_t*)lo; a.wimg = (const uint8_t*)weight_image; a.bias = bias; a.y = y;
@@ -683,18 +736,32 @@ extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void*
         RF_CUDA_OK(cudaFuncSetAttribute(tc_conv3d_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
-    tc_conv3d_halo_kernel<<<(unsigned)g.n_items, NTHREADS, g.smem, (cudaStream_t)stream>>>(a);
+    a.n_items = g.n_items;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int slots = sms * (g.two_resident ? 2 : 1);
+    tc_conv3d_halo_kernel<<<(unsigned)(g.n_items < slots ? g.n_items : slots), NTHREADS, g.smem, (cudaStream_t)stream>>>(a);
     RF_LAUNCH_OK("tc_conv3d_halo_kernel");
     return 0;
 }
 
 /* Debug / test aid: the item shape the chooser picks (returns 0 when unsupported). */
-extern "C" int rf_tc_conv3d_halo_geometry(int N, int D, int H, int W, int Cout, int C1, int C2, int* out8) {
+extern "C" int rf_tc_conv3d_halo_geometry(int N, int D, int H, int W, int Cout, int C1, int C2, int pad, int* out8) {
     int Cp1, Cp2, CC, CCe, pair, Npad;
     if (!halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad)) return 0;
     Geo g;
-    if (!choose_geometry(N, D, H, W, CCe, pair, Npad, g)) return 0;
+    if (!choose_geometry(N, D + 2 * pad - 2, H + 2 * pad - 2, W + 2 * pad - 2, CCe, pair, Npad, g)) return 0;
     out8[0] = g.stacked; out8[1] = g.G; out8[2] = g.Dt; out8[3] = g.Ht; out8[4] = g.lines; out8[5] = g.n_tiles;
     out8[6] = g.n_items; out8[7] = (int)g.smem;
     return 1;
+}
+
+/* Tuning aid: phase timestamps (clock64) of CTA 0's first six items of the last rf_tc_conv3d_halo_fwd launch:
+ * per item [issuer: start, accumulators free, first stage landed, all MMAs issued; epilogue: start waiting,
+ * accumulators complete, stores done, -]. */
+extern "C" int rf_tc_conv3d_halo_debug_read(long long* out64) {
+    RF_CUDA_OK(cudaDeviceSynchronize());
+    RF_CUDA_OK(cudaMemcpyFromSymbol(out64, g_halo_dbg, sizeof(long long) * 64));
+    return 0;
 }

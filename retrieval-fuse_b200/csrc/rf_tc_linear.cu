@@ -264,15 +264,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_linear_kernel(const LinArgs a)
             tc_ld32(tmem_base + ((uint32_t)(pw * 32) << 16) + (uint32_t)c0, v);
             if (row < a.M) {
                 float* dst = a.y + row * a.N + c0;
+                if (a.bias) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    o.x = rf_act(v[j] + (a.bias ? __ldg(a.bias + c0 + j) : 0.f), a.act, a.slope);
-                    o.y = rf_act(v[j + 1] + (a.bias ? __ldg(a.bias + c0 + j + 1) : 0.f), a.act, a.slope);
-                    o.z = rf_act(v[j + 2] + (a.bias ? __ldg(a.bias + c0 + j + 2) : 0.f), a.act, a.slope);
-                    o.w = rf_act(v[j + 3] + (a.bias ? __ldg(a.bias + c0 + j + 3) : 0.f), a.act, a.slope);
-                    *reinterpret_cast<float4*>(dst + j) = o;
+                    for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + c0 + j);
                 }
+                rf_act_vec(v, a.act, a.slope);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
         }
     }

@@ -179,17 +179,19 @@ __device__ __forceinline__ void convert_slab(const MlpArgs& a, int l, int c0, in
         float v[16];
         tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 16 * g), v);
         uint32_t h[8], lw[8];
+        if (bias) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] += c0 + 16 * g + e < N ? __ldg(bias + c0 + 16 * g + e) : 0.f;
+        }
+        rf_act_vec(v, a.act, a.slope);
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+            if (c0 + 16 * g + e >= N) v[e] = 0.f;  // padded output channels feed zero weights, keep them finite and zero
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
-            float f[2];
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int c = c0 + 16 * g + e + t;
-                f[t] = c < N ? rf_act(v[e + t] + (bias ? __ldg(bias + c) : 0.f), a.act, a.slope) : 0.f;
-            }
             uint32_t h0, l0, h1, l1;
-            split_f16(f[0], h0, l0);
-            split_f16(f[1], h1, l1);
+            split_f16(v[e], h0, l0);
+            split_f16(v[e + 1], h1, l1);
             h[e >> 1] = h0 | (h1 << 16);
             lw[e >> 1] = l0 | (l1 << 16);
         }

@@ -46,7 +46,8 @@ class _ConvPatchEncoder(RfModule):
         self.layers = nn.ModuleList(mods)  # parameter containers; never called
         self.final_layer = nn.Linear(cin, z_dim)
 
-    use_tensor_cores = True  # tcgen05 implicit-GEMM convs on channels-last bf16-split activations
+    use_tensor_cores = True  # tcgen05 implicit-GEMM convs on channels-last fp16-split activations
+    use_halo_conv = True     # stride-1 3x3x3 layers through the shifted-window kernel (rf_tc_conv_halo.cu)
 
     def _forward_tc(self, x):
         """Channels-last tensor-core path: split -> tc_conv3d (bias + LeakyReLU fused) per layer."""
@@ -56,6 +57,13 @@ class _ConvPatchEncoder(RfModule):
             cin = conv.in_channels
             if cin == 1 and conv.out_channels <= 32:  # first layer: direct convolution on the raw single-channel patch
                 h = ops.conv3d_cin1_cl(h, conv.weight, conv.bias, None, ks=k, stride=s, pad=0, act=ops.ACT_LEAKY, slope=0.2)
+                continue
+            if (self.use_halo_conv and k == 3 and s == 1 and
+                    ops.tc_conv_halo_supported(h.shape[0], h.shape[1], h.shape[2], h.shape[3], conv.out_channels, cin, 0, pad=0)):
+                # 'valid' 3x3x3 layers: shifted-window kernel, the patch block staged in shared memory once
+                img, sw = self._wcache.derived(("halo", li), [conv.weight], lambda w, c=cin: ops.tc_conv_halo_weight_image(w, c, 0))
+                h = ops.tc_conv3d_halo(ops.cl_norm_split_halo(h, None, None, scale=1.0, pad=0), img, conv.bias, conv.out_channels,
+                                       act=ops.ACT_LEAKY, slope=0.2, out_scale=1.0 / sw)
                 continue
             img, sw = self._wcache.derived(("tcconv", li), [conv.weight], lambda w, c=cin: ops.tc_conv_weight_image(w, c, 0))
             h = ops.tc_conv3d(ops.cl_norm_split(h), None, cin, 0, img, conv.bias, conv.out_channels, k, stride=s, pad=0,

@@ -400,21 +400,23 @@ def tc_conv3d(xs, x2s, c1, c2, img, bias, cout, ks, stride=1, pad=0, act=ACT_NON
 
 # ---- shifted-window ("halo") tensor-core convolution: 3x3x3, stride 1, pad 1 -------------------
 
-def tc_conv_halo_supported(N, D, H, W, cout, c1, c2):
-    return bool(_lib.lib().rf_tc_conv3d_halo_supported(int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2)))
+def tc_conv_halo_supported(N, D, H, W, cout, c1, c2, pad=1):
+    """D, H, W: input extents; pad 1 = 'same' (U-Nets), pad 0 = 'valid' (conv patch encoders)."""
+    return bool(_lib.lib().rf_tc_conv3d_halo_supported(int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2), int(pad)))
 
 
-def tc_conv_halo_geometry(N, D, H, W, cout, c1, c2):
+def tc_conv_halo_geometry(N, D, H, W, cout, c1, c2, pad=1):
     """Item shape the kernel picks: dict(stacked, G, Dt, Ht, lines, n_tiles, n_items, smem) or None."""
     out = (ctypes.c_int * 8)()
-    if not _lib.lib().rf_tc_conv3d_halo_geometry(int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2), out):
+    if not _lib.lib().rf_tc_conv3d_halo_geometry(int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2), int(pad), out):
         return None
     return dict(zip(["stacked", "G", "Dt", "Ht", "lines", "n_tiles", "n_items", "smem"], list(out)))
 
 
-def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0):
+def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0, pad=1):
     """fp32 channels-last x [N,D,H,W,C1] (or None) and half-resolution x2 [N,D/2,H/2,W/2,C2] (or None) ->
-    (hi, lo) fp16 slot planes [chunk][N][D+2][H+2][W+2][8] of scale * GroupNorm(concat(x, up2(x2))), zero halo."""
+    (hi, lo) fp16 slot planes [chunk][N][D+2p][H+2p][W+2p][8] of scale * GroupNorm(concat(x, up2(x2))), zero halo of
+    width p = pad."""
     src = x if x is not None else x2
     src = _dev(src, name="x")
     c1 = x.shape[-1] if x is not None else 0
@@ -424,7 +426,7 @@ def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0):
     else:
         N, D, H, W = x2.shape[0], 2 * x2.shape[1], 2 * x2.shape[2], 2 * x2.shape[3]
     L = _lib.lib()
-    nbytes = L.rf_halo_act_bytes(N, D, H, W, c1, c2)
+    nbytes = L.rf_halo_act_bytes(N, D, H, W, c1, c2, int(pad))
     if nbytes == 0:
         raise _lib.RfError(f"halo layout does not support C={c1}+{c2}")
     hi = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
@@ -432,9 +434,9 @@ def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0):
     mu, a, beta = gn if gn is not None else (None, None, None)
     with torch.cuda.device(src.device):
         check(L.rf_cl_norm_split_halo(_ptr(x), c1, _ptr(x2), c2, _ptr(mu), _ptr(a), _ptr(beta), hi.data_ptr(), lo.data_ptr(),
-                                      N, D, H, W, float(scale), _stream(src)), "rf_cl_norm_split_halo")
+                                      N, D, H, W, int(pad), float(scale), _stream(src)), "rf_cl_norm_split_halo")
     _count()
-    return hi, lo, (N, D, H, W, c1, c2)
+    return hi, lo, (N, D, H, W, c1, c2, int(pad))
 
 
 def tc_conv_halo_weight_image(weight, c1, c2):
@@ -458,13 +460,15 @@ def tc_conv_halo_weight_image(weight, c1, c2):
 
 
 def tc_conv3d_halo(split, img, bias, cout, act=ACT_NONE, slope=0.0, out_ncdhw=False, out_scale=1.0):
-    """split = cl_norm_split_halo(...) result.  Returns fp32 channels-last [N,D,H,W,Cout] or NCDHW."""
-    hi, lo, (N, D, H, W, c1, c2) = split
-    shape = (N, cout, D, H, W) if out_ncdhw else (N, D, H, W, cout)
+    """split = cl_norm_split_halo(...) result.  Returns fp32 channels-last [N,Do,Ho,Wo,Cout] or NCDHW
+    (output extents = input + 2 pad - 2)."""
+    hi, lo, (N, D, H, W, c1, c2, pad) = split
+    Do, Ho, Wo = D + 2 * pad - 2, H + 2 * pad - 2, W + 2 * pad - 2
+    shape = (N, cout, Do, Ho, Wo) if out_ncdhw else (N, Do, Ho, Wo, cout)
     y = torch.empty(shape, device=hi.device, dtype=torch.float32)
     with torch.cuda.device(hi.device):
         check(_lib.lib().rf_tc_conv3d_halo_fwd(hi.data_ptr(), lo.data_ptr(), img.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W,
-                                               cout, c1, c2, act, float(slope), float(out_scale), int(bool(out_ncdhw)),
+                                               pad, cout, c1, c2, act, float(slope), float(out_scale), int(bool(out_ncdhw)),
                                                torch.cuda.current_stream(hi.device).cuda_stream), "rf_tc_conv3d_halo_fwd")
     _count()
     return y

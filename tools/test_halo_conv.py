@@ -132,6 +132,15 @@ def run(case, check=True, old=True):
 if __name__ == "__main__":
     if "--case" in sys.argv:  # one shape, no checks: the ncu target (profiles/*_halo_conv_*.txt)
         run(tuple(int(v) for v in sys.argv[sys.argv.index("--case") + 1].split(",")), check=False, old=False)
+        if "--phases" in sys.argv:  # phase timestamps of CTA 0's first items (cycles relative to the first)
+            import ctypes
+            from retrieval_fuse_b200 import _lib
+            buf = (ctypes.c_longlong * 64)()
+            _lib.lib().rf_tc_conv3d_halo_debug_read(ctypes.cast(buf, ctypes.c_void_p))
+            t0 = buf[0]
+            for it in range(6):
+                v = [buf[it * 8 + k] - t0 for k in range(7)]
+                print(f"item {it}: issuer start {v[0]} acc-free {v[1]} stage0 {v[2]} issued {v[3]} | epi wait {v[4]} acc-done {v[5]} stored {v[6]}")
         sys.exit(0)
     quick = "--quick" in sys.argv
     t0 = time.time()
