@@ -34,7 +34,7 @@
 
 namespace {
 
-constexpr int TM = 128, NTHREADS = 384, NB = 4, MAX_ABUF = 2;
+constexpr int TM = 128, NTHREADS = 512, NB = 4, MAX_ABUF = 2;
 constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in maximum per CTA on sm_100
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -291,7 +291,7 @@ struct HaloArgs {
     int lines, n_wblk, n_tiles, P;  // P = slots per staged plane (incl. over-read slack)
     int S_st;                     // staged slots per plane that the bulk copies fill
     int pair, n_stages, nbuf, ck, kpg;
-    int Cout, Npad, act, out_ncdhw, n_acc, n_iss, n_items;
+    int Cout, Npad, act, out_ncdhw, n_acc, n_iss, n_items, n_sets;
     float slope, out_scale;
     uint32_t bslot_bytes, tmem_cols;
     uint16_t tile_off[32];        // first slot of M tile t within the staged block (uniform-indexed constant loads)
@@ -301,8 +301,8 @@ struct HaloArgs {
 // up once; the producers run ahead into the next item while the epilogue warps drain the accumulators, so launch,
 // allocation and first-load latency (10-30 thousand cycles per item when every item was its own CTA) are paid once
 // per CTA instead of once per item.
-//   warp 0: activation producer   warp 3: weight producer   warps 1,2,4-7: MMA issuers   warps 8-11: epilogue
-__global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloArgs a) {
+//   warp 0: activation producer   warp 3: weight producer   warps 1,2,4-7: MMA issuers   warps 8-15: epilogue
+__global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
@@ -313,9 +313,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloA
     const uint32_t bars = sB + NB * a.bslot_bytes;
     const uint32_t bar_afull = bars, bar_aempty = bars + 8 * MAX_ABUF;
     const uint32_t bar_bfull = bars + 16 * MAX_ABUF, bar_bempty = bar_bfull + 8 * NB;
-    const uint32_t bar_dfull = bar_bempty + 8 * NB, bar_dempty = bar_dfull + 8;
-    const uint32_t tmem_slot = bar_dempty + 8;
+    const uint32_t bar_dfull = bar_bempty + 8 * NB, bar_dempty = bar_dfull + 16;  // one pair per accumulator set
+    const uint32_t tmem_slot = bar_dempty + 16;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
+    // row table: GEMM row (tile, r) -> output voxel offset relative to the item's first voxel, stacked sample index in
+    // the top 6 bits; -1 = halo row.  Built once per CTA: the decode costs several integer divisions per row, which a
+    // lone epilogue warp per scheduler cannot hide.
+    int* row_tab = reinterpret_cast<int*>(smem_al + (tmem_slot + 16 - base));
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp: uniform register
     const bool resident = a.n_stages == 1;  // one stage per item: loaded once, used by both accumulation passes
@@ -323,8 +327,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloA
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nbuf; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, a.n_iss); }
         for (int s = 0; s < NB; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, a.n_iss); }
-        mbar_init(bar_dfull, a.n_iss);
-        mbar_init(bar_dempty, 4);
+        for (int k = 0; k < 2; ++k) { mbar_init(bar_dfull + 8 * k, a.n_iss); mbar_init(bar_dempty + 8 * k, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -338,6 +341,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloA
         const int total = a.nbuf * planes * a.P;
         for (int i = threadIdx.x; i < total; i += NTHREADS) *reinterpret_cast<uint4*>(smem_al + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < a.n_tiles * TM; i += NTHREADS) {
+        const int t = i >> 7, r = i & 127;
+        int line, w;
+        if (a.lines) {
+            line = (t / a.n_wblk) * 16 + (r >> 3);
+            w = (t % a.n_wblk) * 8 + (r & 7);
+        } else {
+            line = i / a.Wp; w = i % a.Wp;
+        }
+        const int g = a.stacked ? line / a.Ls : 0;
+        const int rem = a.stacked ? line % a.Ls : line;
+        const int dd = rem / a.Hs, hh = rem % a.Hs;
+        const bool valid = g < a.G && dd < a.Dt && hh < a.Ht && w < a.W;
+        row_tab[i] = valid ? ((((g * a.D + dd) * a.H + hh) * a.W + w) | (g << 26)) : -1;
     }
     tc_fence_before();
     __syncthreads();
@@ -414,7 +432,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloA
             const uint32_t b_lbo = (uint32_t)a.Npad << 16;
             const uint32_t blk_u = (uint32_t)a.Npad * 2u;       // one (k step, hi|lo) weight block, in 16-byte units
             const uint32_t lo_off = (uint32_t)(a.ck * a.P);     // hi -> lo plane, in slots
-            const uint32_t npad = (uint32_t)a.Npad;
+            const uint32_t npad = (uint32_t)a.Npad, set_cols = (uint32_t)(a.n_tiles * a.Npad);
             // The tensor core truncates when it aligns the 16 products of a K step with the fp32 accumulator, a
             // bias that grows with the number of accumulations at full magnitude (measured: error linear in the
             // MMA count).  So the two small cross products (hi*lo, lo*hi: 2^-11 of the result) of ALL taps and
@@ -424,7 +442,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloA
             for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
                 const bool dbg = blockIdx.x == 0 && iss == 0 && leader && it < 6;
                 if (dbg) g_halo_dbg[it * 8 + 0] = clock64();
-                mbar_wait_warp(bar_dempty, (it & 1u) ^ 1u);  // the epilogue has drained the previous item's accumulators
+                // accumulator set of this item (two sets when they fit TMEM: the epilogue of item i overlaps the MMAs of
+                // item i+1); wait until the epilogue has drained the set's previous item
+                const uint32_t set = a.n_sets == 2 ? (it & 1u) : 0u, use = a.n_sets == 2 ? (it >> 1) : it;
+                mbar_wait_warp(bar_dempty + 8 * set, (use & 1u) ^ 1u);
                 tc_fence_after();
                 if (dbg) g_halo_dbg[it * 8 + 1] = clock64();
                 uint32_t b = 0;
@@ -448,7 +469,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloA
                             const uint32_t b_hi = bbase + (uint32_t)ks * 2u * blk_u, b_lo = b_hi + blk_u;
                             const uint32_t acc = (vs | g | ks) ? 1u : 0u;  // the very first MMA of a tile overwrites its accumulator
                             for (int t = iss; t < a.n_tiles; t += a.n_iss) {
-                                const uint32_t d = tmem_u + (uint32_t)t * npad;
+                                const uint32_t d = tmem_u + set * set_cols + (uint32_t)t * npad;
                                 const uint32_t da = abase + koff + a.tile_off[t];
                                 if (pass == 0) {
                                     tc_mma2(d, da, a_hi32, b_lo, b_hi32, idesc, acc, leader);          // hi * lo
@@ -465,14 +486,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloA
                         ++lc;
                     }
                 }
-                if (leader) tc_commit(bar_dfull);
+                if (leader) tc_commit(bar_dfull + 8 * set);
                 if (dbg) g_halo_dbg[it * 8 + 3] = clock64();
                 __syncwarp();
             }
         }
     } else {
-        // ---- epilogue warps 8..11: warp % 4 = TMEM lane quadrant; one thread <-> one GEMM row of every tile
-        const int q = warp & 3;
+        // ---- epilogue warps 8..15: warp % 4 = TMEM lane quadrant, (warp - 8) / 4 = tile parity; one thread <-> one
+        // GEMM row of its tiles
+        const int q = warp & 3, half = (warp - 8) >> 2;
         const long So = (long)a.D * a.H * a.W;
         const bool vec4 = !a.out_ncdhw && (a.Cout & 3) == 0;
         uint32_t it = 0;
@@ -480,29 +502,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloA
             int n0, gact = 1, d0 = 0, h0 = 0;
             if (a.stacked) { n0 = item * a.G; gact = min(a.G, a.N - n0); }
             else { n0 = item / per_sample; const int r = item % per_sample; d0 = (r / a.n_ht) * a.Dt; h0 = (r % a.n_ht) * a.Ht; }
+            const long vox0 = (((long)n0 * a.D + d0) * a.H + h0) * a.W;
             const bool dbg = blockIdx.x == 0 && threadIdx.x == 256 && it < 6;
             if (dbg) g_halo_dbg[it * 8 + 4] = clock64();
-            mbar_wait_warp_sleepy(bar_dfull, it & 1u);
+            const uint32_t set = a.n_sets == 2 ? (it & 1u) : 0u, use = a.n_sets == 2 ? (it >> 1) : it;
+            const uint32_t tm_set = tmem_base + set * (uint32_t)(a.n_tiles * a.Npad);
+            mbar_wait_warp_sleepy(bar_dfull + 8 * set, use & 1u);
             tc_fence_after();
             if (dbg) g_halo_dbg[it * 8 + 5] = clock64();
-            for (int t = 0; t < a.n_tiles; ++t) {
-                const int r = q * 32 + lane;
-                int line, w;
-                if (a.lines) {
-                    line = (t / a.n_wblk) * 16 + (r >> 3);
-                    w = (t % a.n_wblk) * 8 + (r & 7);
-                } else {
-                    const int R = t * 128 + r;
-                    line = R / a.Wp; w = R % a.Wp;
-                }
-                const int g = a.stacked ? line / a.Ls : 0;
-                const int rem = a.stacked ? line % a.Ls : line;
-                const int dd = rem / a.Hs, hh = rem % a.Hs;
-                const bool valid = g < gact && dd < a.Dt && hh < a.Ht && w < a.W;
-                const long vox = valid ? ((((long)(n0 + g) * a.D + d0 + dd) * a.H + h0 + hh) * a.W + w) : 0;
+            for (int t = half; t < a.n_tiles; t += 2) {
+                const int rt = row_tab[t * TM + q * 32 + lane];
+                const bool valid = rt >= 0 && (rt >> 26) < gact;
+                const long vox = vox0 + (rt & 0x3FFFFFF);
                 for (int c0 = 0; c0 < a.Npad; c0 += 16) {
                     float v[16];
-                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * a.Npad + c0), v);
+                    tc_ld16(tm_set + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * a.Npad + c0), v);
+                    if (dbg && t == 0 && c0 == 0) g_halo_dbg[it * 8 + 7] = clock64();
+                    if (dbg && t == 2 && c0 == 0) g_halo_dbg[48 + it] = clock64();
                     if (!valid) continue;
                     if (a.bias) {
 #pragma unroll
@@ -531,7 +547,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloA
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_dempty);  // 4 arrivals: the accumulators may be overwritten
+            if (lane == 0) mbar_arrive(bar_dempty + 8 * set);  // 8 arrivals: the set may be overwritten
             if (dbg) g_halo_dbg[it * 8 + 6] = clock64();
         }
     }
@@ -546,7 +562,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3d_halo_kernel(const HaloA
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct Geo {
-    int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, n_acc, two_resident;
+    int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, n_acc, two_resident, n_sets;
     uint32_t tmem_cols, bslot;
     size_t smem;
     double score;
@@ -559,7 +575,7 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, Ge
     const int ck = pair ? 1 : 2, planes = 2 * ck, kpg = pair ? 2 : 3;
     const int n_stages = pair ? 1 : CCe / 2;
     const uint32_t bslot = (uint32_t)kpg * 2u * (uint32_t)Npad * 32u;
-    const long avail = (long)SMEM_LIMIT - 1024 - 256 - (long)NB * bslot;
+    const long avail_all = (long)SMEM_LIMIT - 1024 - 256 - (long)NB * bslot;
     best.score = -1.0;
     auto consider = [&](int stacked, int G, int Dt, int Ht, int lines) {
         const int Hs = stacked ? Hp : Ht + 2;
@@ -579,6 +595,7 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, Ge
         long P = max_slot + 1 > S_st ? max_slot + 1 : S_st;
         P = (P + 7) / 8 * 8;
         if (n_tiles * Npad > 512 || n_tiles > 32 || P * 16 >= (1L << 18)) return;
+        const long avail = avail_all - n_tiles * 512;  // the row table: n_tiles x 128 ints
         // two staging buffers whenever they fit: the next stage (or the next item's block) loads during the MMAs
         const long smemA1 = (long)planes * P * 16;
         const int nbuf = 2 * smemA1 <= avail ? 2 : 1;
@@ -587,26 +604,35 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, Ge
         if (smemA > avail || S_st * 16 * planes >= (1L << 20)) return;
         const long outputs = stacked ? (long)G * D * H * W : (long)Dt * Ht * W;
         const long n_items = stacked ? (N + G - 1) / G : (long)N * (D / Dt) * (H / Ht);
-        // cost model (persistent CTAs): ~34-48 cycles per 128-row MMA (operand reads from shared memory bound it,
-        // not N) plus the epilogue, which only overlaps with MMAs when a second CTA shares the SM
-        const int n_acc = 1;  // accumulator sets per tile (summed in the epilogue); one is enough, see mma_pattern.cu
-        uint32_t cols_needed = 32;
-        while ((long)cols_needed < n_tiles * Npad * n_acc) cols_needed <<= 1;
-        const long smem_total = 1024 + smemA + (long)NB * bslot + 256;
-        const bool two_resident = smem_total <= 113 * 1024 && cols_needed <= 256;
+        // Cost model, calibrated on B200 (tools/halo_geo_sweep.sh): an M128 K16 MMA occupies the tensor pipe for ~40
+        // (N <= 32) to 48 (N = 64) cycles, one issuer warp sustains one MMA per ~150 cycles, the epilogue costs ~2000
+        // cycles per (tile pair, 16 columns), and every item pays ~3000 cycles of pipeline fill.  Accumulators are
+        // double-buffered (epilogue of item i under the MMAs of item i+1) when two sets fit TMEM; otherwise a second
+        // resident CTA hides part of the epilogue.
+        const int n_acc = 1;  // accumulator sets per tile summed in the epilogue; one is enough, see mma_pattern.cu
         const double n_mma = (double)n_stages * 9 * kpg * (double)n_tiles * 3.0;
-        const double t_epi = 1500.0 + (double)n_tiles * (Npad / 16) * 250.0 + (nbuf == 1 ? 4000.0 : 0.0);
-        const double t_item = n_mma * (Npad > 32 ? 48.0 : 40.0) + (two_resident ? 0.3 : 1.0) * t_epi;
+        const int n_iss = n_tiles < 6 ? (int)n_tiles : 6;
+        const double t_epi = 1000.0 + (double)((n_tiles + 1) / 2) * (Npad / 16) * 2000.0 + (nbuf == 1 ? 4000.0 : 0.0);
         const double waves = (double)((n_items + 147) / 148);   // items every SM walks through (the tensor pipe is per SM)
-        const double score = (double)outputs * (double)n_items / (waves * t_item);
-        if (score > best.score) {
-            best.Dt = stacked ? D : Dt; best.Ht = stacked ? H : Ht; best.Hs = Hs; best.G = stacked ? G : 1; best.stacked = stacked;
-            best.lines = lines; best.n_wblk = n_wblk; best.n_tiles = (int)n_tiles; best.P = (int)P; best.S_st = (int)S_st;
-            best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot; best.two_resident = two_resident ? 1 : 0;
-            best.tmem_cols = cols_needed;
-            best.n_acc = n_acc;
-            best.smem = (size_t)(1024 + smemA + (long)NB * bslot + 256);
-            best.score = score;
+        for (int n_sets = 1; n_sets <= 2; ++n_sets) {
+            if (n_sets * n_tiles * Npad > 512) break;
+            uint32_t cols_needed = 32;
+            while ((long)cols_needed < n_tiles * Npad * n_sets) cols_needed <<= 1;
+            const long smem_total = 1024 + smemA + (long)NB * bslot + 256 + n_tiles * 512;
+            const bool two_resident = smem_total <= 113 * 1024 && cols_needed <= 256;
+            const double pipe = Npad > 32 ? 48.0 : 40.0, issue = 150.0 / (n_iss * (two_resident ? 2 : 1));
+            const double t_mma = n_mma * (pipe > issue ? pipe : issue);
+            const double t_item = 3000.0 + (n_sets == 2 ? (t_mma > t_epi ? t_mma : t_epi) : t_mma + (two_resident ? 0.3 : 1.0) * t_epi);
+            const double score = (double)outputs * (double)n_items / (waves * t_item);
+            if (score > best.score) {
+                best.Dt = stacked ? D : Dt; best.Ht = stacked ? H : Ht; best.Hs = Hs; best.G = stacked ? G : 1; best.stacked = stacked;
+                best.lines = lines; best.n_wblk = n_wblk; best.n_tiles = (int)n_tiles; best.P = (int)P; best.S_st = (int)S_st;
+                best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot; best.two_resident = two_resident ? 1 : 0;
+                best.tmem_cols = cols_needed;
+                best.n_acc = n_acc; best.n_sets = n_sets;
+                best.smem = (size_t)smem_total;
+                best.score = score;
+            }
         }
     };
     if (const char* e = getenv("RF_HALO_GEO")) {  // tuning aid: "stacked,G,Dt,Ht,lines" forces the item shape
@@ -736,7 +762,7 @@ extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void*
         RF_CUDA_OK(cudaFuncSetAttribute(tc_conv3d_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
-    a.n_items = g.n_items;
+    a.n_items = g.n_items; a.n_sets = g.n_sets;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

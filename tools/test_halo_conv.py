@@ -139,8 +139,9 @@ if __name__ == "__main__":
             _lib.lib().rf_tc_conv3d_halo_debug_read(ctypes.cast(buf, ctypes.c_void_p))
             t0 = buf[0]
             for it in range(6):
-                v = [buf[it * 8 + k] - t0 for k in range(7)]
-                print(f"item {it}: issuer start {v[0]} acc-free {v[1]} stage0 {v[2]} issued {v[3]} | epi wait {v[4]} acc-done {v[5]} stored {v[6]}")
+                v = [buf[it * 8 + k] - t0 for k in range(8)]
+                print(f"item {it}: issuer start {v[0]} acc-free {v[1]} stage0 {v[2]} issued {v[3]} | epi wait {v[4]} acc-done {v[5]} "
+                      f"first-ld {v[7]} tile1-ld {buf[48 + it] - t0} stored {v[6]}")
         sys.exit(0)
     quick = "--quick" in sys.argv
     t0 = time.time()
