@@ -177,6 +177,11 @@ int rf_conv3d_cin1_cl_fwd(const float* x, const float* w, const float* bias, con
                           const float* gn_beta, float* y, int N, int Di, int Hi, int Wi, int Cout, int KS, int stride, int pad,
                           int act, float slope, void* stream);
 
+/* Pointwise head (model/refinement.py:55-57: the decoder's final Conv3d(nf, 1, 1) + bias + Tanh) on a channels-last
+ * volume x [n_voxels, C] -> y [n_voxels] (= NCDHW with one channel); w [C] is the Conv3d weight, bias one float. */
+int rf_cl_pointwise_head(const float* x, const float* w, const float* bias, float* y, long n_voxels, int C, int act, float slope,
+                         void* stream);
+
 /* ---- a5 + a9  fused query encoder --------------------------------------- */
 
 /* model/retrieval.py:64-84 Patch04.forward (+Patch05/Patch04V2: any ReLU MLP)

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "rf_tc_conv3d_halo_debug_read": (c_int, [c_void_p]),
     "rf_tc_conv3d_halo_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
+    "rf_cl_pointwise_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_float, c_void_p]),
     "rf_conv3d_cin1_cl_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "rf_mlp_encode_workspace_bytes": (c_size_t, [c_long, c_int * 9, c_int]),

@@ -392,3 +392,40 @@ extern "C" int rf_mlp_encode_fwd(const float* x, const float* const* wt_host, co
     if (l2_normalize) return rf_l2_normalize_rows(cur, out, M, widths_host[n_layers], 1e-12f, stream);
     return 0;
 }
+
+// ---------------------------------------------------------------------------
+// Pointwise head: Conv3d(C, 1, 1) + bias + activation on a channels-last volume (model/refinement.py:55-57, the
+// final 1x1x1 conv + Tanh of the decoder).  Memory-bound: one thread per voxel reads its C contiguous floats as
+// float4s and writes one float; fp32 FMA in channel order.
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) cl_pointwise_head_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float* __restrict__ y, long total,
+                                                                int C, int act, float slope) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const float* src = x + i * C;
+        float acc = 0.f;
+        if ((C & 3) == 0) {
+            for (int c = 0; c < C; c += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+                acc = fmaf(v.x, __ldg(w + c), acc);
+                acc = fmaf(v.y, __ldg(w + c + 1), acc);
+                acc = fmaf(v.z, __ldg(w + c + 2), acc);
+                acc = fmaf(v.w, __ldg(w + c + 3), acc);
+            }
+        } else {
+            for (int c = 0; c < C; ++c) acc = fmaf(__ldg(src + c), __ldg(w + c), acc);
+        }
+        y[i] = rf_act(acc + (bias ? __ldg(bias) : 0.f), act, slope);
+    }
+}
+}  // namespace
+
+extern "C" int rf_cl_pointwise_head(const float* x, const float* w, const float* bias, float* y, long n_voxels, int C, int act,
+                                    float slope, void* stream) {
+    RF_CHECK_ARG(x && w && y && n_voxels > 0 && C > 0, "rf_cl_pointwise_head: bad arguments");
+    RF_CHECK_ARG(((uintptr_t)x & 15) == 0, "rf_cl_pointwise_head: x must be 16-byte aligned");
+    cl_pointwise_head_kernel<<<rf_grid_1d(n_voxels, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, n_voxels, C, act, slope);
+    RF_LAUNCH_OK("cl_pointwise_head_kernel");
+    return 0;
+}

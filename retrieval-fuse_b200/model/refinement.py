@@ -78,11 +78,10 @@ class Superresolution08FinalDecoder(RfModule):
         from . import unet as U
         head = self.network[1]
         nf = head.in_channels
-        if U.USE_TENSOR_CORES and x.is_cuda and self.network[0].basic_module.tc_ok(0, nf) and ops.tc_conv_supported(1, nf, 0, 1):
+        if U.USE_TENSOR_CORES and x.is_cuda and self.network[0].basic_module.tc_ok(0, nf):
             h = self.network[0].forward_cl(ops.cl_from_ncdhw(x))
-            img, sw = self._wcache.derived("tchead", [head.weight], lambda w: ops.tc_conv_weight_image(w, nf, 0))
-            return ops.tc_conv3d(ops.cl_norm_split(h), None, nf, 0, img, head.bias, 1, 1, act=ops.ACT_TANH, out_ncdhw=True,
-                                 out_scale=1.0 / sw)
+            # the 1x1x1 head is memory-bound: one fp32 FMA pass over the channels-last volume, bias + tanh fused
+            return ops.cl_pointwise_head(h, head.weight, head.bias, act=ops.ACT_TANH)
         x = self.network[0](x)
         return ops.conv3d(x, self._wt(head.weight), head.bias, cout=1, ks=1, stride=1, pad=0, act=ops.ACT_TANH)
 

@@ -351,6 +351,20 @@ def conv3d_cin1_cl(x, weight, bias, gn=None, ks=3, stride=1, pad=0, act=ACT_NONE
     return y
 
 
+def cl_pointwise_head(x, weight, bias, act=ACT_NONE, slope=0.0):
+    """Conv3d(C, 1, 1) + bias + activation of a channels-last volume x [N,D,H,W,C] -> NCDHW [N,1,D,H,W]."""
+    x = _dev(x, name="x")
+    N, D, H, W, C = x.shape
+    weight = _dev(weight.detach().reshape(-1), name="weight")
+    assert weight.numel() == C
+    y = torch.empty((N, 1, D, H, W), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().rf_cl_pointwise_head(x.data_ptr(), weight.data_ptr(), _ptr(bias), y.data_ptr(), N * D * H * W, C, act,
+                                              float(slope), _stream(x)), "rf_cl_pointwise_head")
+    _count()
+    return y
+
+
 def tc_conv_supported(cout, c1, c2, ks):
     return _lib.lib().rf_tc_conv_weight_image_bytes(int(cout), int(c1), int(c2), int(ks)) > 0
 

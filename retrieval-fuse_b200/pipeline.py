@@ -225,11 +225,22 @@ class RefinementPipeline(RetrievalPipeline):
         """x_in [B,1,s,s,s] normalised, retrieval [B,K',64,64,64] normalised -> pred [B,1,64,64,64] in [-1,1]."""
         nf = self.retrieval_backbone.nf
         B, S = retrieval.shape[0], retrieval.shape[2]
-        x_back = self.unet_backbone(x_in)
+        # the input U-Net (a few dozen tiny launches on B chunks) and the retrieval U-Net are independent until the
+        # attention: fork the former onto a side stream so that it hides under the latter (also inside a CUDA graph)
+        cur = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_side_stream"):
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        side = self._side_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            x_in.record_stream(side)
+            x_back = self.unet_backbone(x_in)
         retr = retrieval[:, :self.K].reshape(B * self.K, 1, S, S, S)   # get_retrievals (:255-257)
         patches = ops.unfold3d(retr, 16)                                # Unfold3D(16, 1) (:34)
         feats = self.retrieval_backbone(patches)                        # [B*K*64, nf, 8,8,8]
         x_retr = ops.fold3d(feats, 4, 8, nf)                            # Fold3D(4, 8, nf) (:37)
+        cur.wait_stream(side)
+        x_back.record_stream(cur)
         x = self.patched_attention_block(x_back, x_retr, gumbel_noise)
         return self.decoder(x), x_back, x_retr, x
 
