@@ -69,7 +69,7 @@ __device__ __forceinline__ void rf_act_vec(float (&v)[N], int act, float slope) 
 #pragma unroll
         for (int e = 0; e < N; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
     } else if (act == RF_ACT_TANH) {
-#pragma unroll 1
+#pragma unroll  // (a rolled loop would index v dynamically and push the whole vector to local memory)
         for (int e = 0; e < N; ++e) v[e] = tanhf(v[e]);
     }
 }

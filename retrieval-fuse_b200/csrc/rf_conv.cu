@@ -309,6 +309,99 @@ __global__ void __launch_bounds__(256) conv_cin1_direct_kernel(const float* __re
         }
     }
 }
+
+// Register-tiled variant for stride 1: one thread computes WT consecutive outputs along w for all CO channels.  Per
+// (kd, kh) it loads one row segment of WT + KS - 1 inputs and then needs only the two float4 weight loads per tap for
+// WT x CO FMAs (the one-voxel kernel above issues three loads per eight FMAs and is load-issue bound: 13 TFLOP/s on the
+// 5^3 first layer of Patch32).  Same tap order per output, hence bit-identical results.
+template <int CO, int KS, int WT>
+__global__ void __launch_bounds__(128) conv_cin1_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, const float* __restrict__ gn_mu,
+                                                              const float* __restrict__ gn_a, const float* __restrict__ gn_beta,
+                                                              float* __restrict__ y, int Di, int Hi, int Wi, int Do, int Ho,
+                                                              int Wo, int pad, int Cout, int act, float slope, long M4) {
+    __shared__ float wsm[KS * KS * KS * CO];  // [taps][CO]
+    constexpr int taps = KS * KS * KS;
+    for (int i = threadIdx.x; i < taps * CO; i += blockDim.x) {
+        const int t = i / CO, co = i % CO;
+        wsm[i] = co < Cout ? __ldg(w + (long)co * taps + t) : 0.f;
+    }
+    __syncthreads();
+    const float beta = gn_mu ? __ldg(gn_beta) : 0.f;
+    const int Wo4 = (Wo + WT - 1) / WT;
+    for (long m4 = blockIdx.x * (long)blockDim.x + threadIdx.x; m4 < M4; m4 += (long)gridDim.x * blockDim.x) {
+        long t = m4;
+        const int ow0 = (int)(t % Wo4) * WT; t /= Wo4;
+        const int oh = (int)(t % Ho); t /= Ho;
+        const int od = (int)(t % Do); t /= Do;
+        const long n = t;
+        const float mu = gn_mu ? __ldg(gn_mu + n) : 0.f, ga = gn_mu ? __ldg(gn_a + n) : 1.f;
+        const float* xn = x + n * (long)Di * Hi * Wi;
+        float acc[WT][CO];
+#pragma unroll
+        for (int j = 0; j < WT; ++j)
+#pragma unroll
+            for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
+        const int d0 = od - pad, h0 = oh - pad, w0 = ow0 - pad;
+#pragma unroll 1
+        for (int kd = 0; kd < KS; ++kd) {
+            const int id = d0 + kd;
+#pragma unroll 1
+            for (int kh = 0; kh < KS; ++kh) {
+                const int ih = h0 + kh;
+                const bool row_ok = id >= 0 && id < Di && ih >= 0 && ih < Hi;
+                const float* xr = xn + ((long)id * Hi + ih) * Wi;
+                float xv[WT + KS - 1];
+#pragma unroll
+                for (int i = 0; i < WT + KS - 1; ++i) {
+                    const int iw = w0 + i;
+                    float v = 0.f;
+                    if (row_ok && iw >= 0 && iw < Wi) {
+                        v = __ldg(xr + iw);
+                        if (gn_mu) v = fmaf(v - mu, ga, beta);
+                    }
+                    xv[i] = v;
+                }
+                const float* wrow = wsm + (kd * KS + kh) * KS * CO;
+#pragma unroll
+                for (int kw = 0; kw < KS; ++kw) {
+                    const float4* wr = reinterpret_cast<const float4*>(wrow + kw * CO);
+#pragma unroll
+                    for (int c4 = 0; c4 < CO / 4; ++c4) {
+                        const float4 w4 = wr[c4];
+#pragma unroll
+                        for (int j = 0; j < WT; ++j) {
+                            acc[j][4 * c4] = fmaf(xv[j + kw], w4.x, acc[j][4 * c4]);
+                            acc[j][4 * c4 + 1] = fmaf(xv[j + kw], w4.y, acc[j][4 * c4 + 1]);
+                            acc[j][4 * c4 + 2] = fmaf(xv[j + kw], w4.z, acc[j][4 * c4 + 2]);
+                            acc[j][4 * c4 + 3] = fmaf(xv[j + kw], w4.w, acc[j][4 * c4 + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        const long m0 = ((n * Do + od) * Ho + oh) * (long)Wo + ow0;
+#pragma unroll
+        for (int j = 0; j < WT; ++j) {
+            if (ow0 + j < Wo) {
+                float* out = y + (m0 + j) * Cout;
+                if (bias) {
+#pragma unroll
+                    for (int c = 0; c < CO; ++c) acc[j][c] += c < Cout ? __ldg(bias + c) : 0.f;
+                }
+                rf_act_vec(acc[j], act, slope);
+                if (Cout == CO) {
+#pragma unroll
+                    for (int c = 0; c < CO; c += 4) *reinterpret_cast<float4*>(out + c) = make_float4(acc[j][c], acc[j][c + 1], acc[j][c + 2], acc[j][c + 3]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CO; ++c)
+                        if (c < Cout) out[c] = acc[j][c];
+                }
+            }
+        }
+    }
+}
 }  // namespace
 
 extern "C" int rf_conv3d_cin1_cl_fwd(const float* x, const float* w, const float* bias, const float* gn_mu, const float* gn_a,
@@ -324,6 +417,17 @@ extern "C" int rf_conv3d_cin1_cl_fwd(const float* x, const float* w, const float
     const int taps = KS * KS * KS;
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = rf_grid_1d(M, 256, 148 * 32);
+    if (stride == 1 && (KS == 3 || KS == 5) && Cout <= 16) {
+        constexpr int WT = 4;
+        const long M4 = (long)N * Do * Ho * ((Wo + WT - 1) / WT);
+        const int g4 = rf_grid_1d(M4, 128, 148 * 64);
+        if (Cout <= 8 && KS == 3) conv_cin1_tiled_kernel<8, 3, WT><<<g4, 128, 0, s>>>(x, w, bias, gn_mu, gn_a, gn_beta, y, Di, Hi, Wi, Do, Ho, Wo, pad, Cout, act, slope, M4);
+        else if (Cout <= 8) conv_cin1_tiled_kernel<8, 5, WT><<<g4, 128, 0, s>>>(x, w, bias, gn_mu, gn_a, gn_beta, y, Di, Hi, Wi, Do, Ho, Wo, pad, Cout, act, slope, M4);
+        else if (KS == 3) conv_cin1_tiled_kernel<16, 3, WT><<<g4, 128, 0, s>>>(x, w, bias, gn_mu, gn_a, gn_beta, y, Di, Hi, Wi, Do, Ho, Wo, pad, Cout, act, slope, M4);
+        else conv_cin1_tiled_kernel<16, 5, WT><<<g4, 128, 0, s>>>(x, w, bias, gn_mu, gn_a, gn_beta, y, Di, Hi, Wi, Do, Ho, Wo, pad, Cout, act, slope, M4);
+        RF_LAUNCH_OK("conv_cin1_tiled_kernel");
+        return 0;
+    }
     if (Cout <= 8)
         conv_cin1_direct_kernel<8><<<grid, 256, taps * 8 * sizeof(float), s>>>(x, w, bias, gn_mu, gn_a, gn_beta, y, Di, Hi, Wi, Do, Ho, Wo, KS, stride, pad, Cout, act, slope, M);
     else if (Cout <= 16)
