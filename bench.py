@@ -557,8 +557,11 @@ def run_ours(args, rank, local, world):
                     "achieved": algo_flops / (k_ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                     "frac": algo_flops / (k_ms / 1e3) / 1e12 / peak, "traffic": traffic, "peak_source": peak_src,
                     "avg_launch_ms": k_ms, "algorithmic_flops_per_launch": algo_flops,
-                    "note": "algorithmic flops = 2*Q*N*64 (one fp16 pass here; the epilogue must read every one of the Q*N "
-                            "fp32 scores from TMEM, 16 per clock per SM, which bounds this K=64 GEMM below the MMA rate)",
+                    "note": "algorithmic flops = 2*Q*N*64, one fp16 tcgen05 pass; every one of the Q*N fp32 scores is read back "
+                            "from TMEM by the epilogue (K = 64 is too short to amortise that), which bounds this GEMM far below "
+                            "the MMA rate; bank rows are scanned in descending projection on the mean query so that the "
+                            "running top-16 thresholds tighten early (exactness unaffected)",
+                    "scores_per_clk_per_sm": (Q * world * float(bank.emb.shape[0])) / (k_ms / 1e3) / 148.0 / 1.965e9,
                     "hbm_view": {"algorithmic_bytes": bank.emb.numel() * 4 + Q * world * 256 + Q * world * 8 * 12,
                                  "peak_gbs": peaks.get("hbm_gbs")}}
         else:

@@ -37,6 +37,8 @@
 #include <string.h>
 #include <limits.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "rf_common.cuh"
 
 int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, const int* q_sel,
@@ -157,22 +159,66 @@ __host__ __device__ constexpr uint32_t idesc(int ab_format) {
            ((uint32_t)(TILE >> 4) << 24);
 }
 
+// ------------------------------------------------------------------ scan order
+// The epilogue's running top-16 pays for every row that beats the current 16th best score (insertion path, taken
+// by the whole warp when any of its 32 queries inserts).  Scanning the rows that score high for a TYPICAL query
+// first makes the thresholds tight after a few tiles, so later insertions become rare.  The order is the bank
+// rows' projection on the mean query direction, descending; it changes nothing in the result (the candidate
+// lists carry scan positions, the re-rank maps them back through perm[] and ranks by the canonical fp64 rule).
+__global__ void __launch_bounds__(256) knn_mean_query_kernel(const float* __restrict__ q, long Q, float* __restrict__ mean64) {
+    __shared__ float sh[64];
+    if (threadIdx.x < 64) sh[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int c = threadIdx.x & 63;
+    float acc = 0.f;
+    for (long r = blockIdx.x * 4L + (threadIdx.x >> 6); r < Q; r += gridDim.x * 4L) acc += __ldg(q + r * 64 + c);
+    atomicAdd(&sh[c], acc);
+    __syncthreads();
+    if (threadIdx.x < 64) atomicAdd(mean64 + threadIdx.x, sh[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) knn_scan_key_kernel(const float* __restrict__ bank, long n_rows, long n_padded,
+                                                           const float* __restrict__ mean64, float* __restrict__ key,
+                                                           int* __restrict__ idx) {
+    const long row = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (row >= n_padded) return;
+    float k = -FLT_MAX;  // padding rows sort last
+    if (row < n_rows) {
+        k = 0.f;
+        const float4* xr = reinterpret_cast<const float4*>(bank + row * 64);
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const float4 x = __ldg(xr + i);
+            k = fmaf(x.x, __ldg(mean64 + 4 * i), k);
+            k = fmaf(x.y, __ldg(mean64 + 4 * i + 1), k);
+            k = fmaf(x.z, __ldg(mean64 + 4 * i + 2), k);
+            k = fmaf(x.w, __ldg(mean64 + 4 * i + 3), k);
+        }
+    }
+    key[row] = k;
+    idx[row] = (int)row;
+}
+
 // ------------------------------------------------------------------ prep
 // src [n_rows, 64] fp32 -> swizzled 16-bit tile images [(n_tiles), KBLK, 128 rows, 128 B].
 // KBLK = 1: fp16(x).  KBLK = 3: bf16 split, bank K blocks = (hi, lo, hi), queries (hi, hi, lo).
 // For the bank the range of |x|^2 is recorded.
 template <int KBLK>
 __global__ void __launch_bounds__(256) knn_tc_prep_kernel(const float* __restrict__ src, long n_rows, long n_rows_padded,
-                                                          int is_bank, uint8_t* __restrict__ img, Stats* stats) {
+                                                          int is_bank, uint8_t* __restrict__ img, Stats* stats,
+                                                          const int* __restrict__ perm) {
     const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;  // one thread per (row, 16-byte chunk)
     const long row = gid >> 3;
     const int c = (int)(gid & 7);
     float nrm = 0.f;
+    bool valid = false;
     if (row < n_rows_padded) {
         float x[8];
-        if (row < n_rows) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(src + row * 64 + c * 8));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(src + row * 64 + c * 8 + 4));
+        const long srow = perm ? (long)perm[row] : row;  // image position `row` holds bank row perm[row] (scan order)
+        valid = srow < n_rows;
+        if (valid) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + srow * 64 + c * 8));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src + srow * 64 + c * 8 + 4));
             x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
         } else {
 #pragma unroll
@@ -210,7 +256,7 @@ __global__ void __launch_bounds__(256) knn_tc_prep_kernel(const float* __restric
         nrm += __shfl_xor_sync(0xffffffffu, nrm, 1);
         nrm += __shfl_xor_sync(0xffffffffu, nrm, 2);
         nrm += __shfl_xor_sync(0xffffffffu, nrm, 4);
-        if (c == 0 && row < n_rows) {  // non-negative floats order like their bit patterns
+        if (c == 0 && valid) {  // non-negative floats order like their bit patterns
             atomicMin(&stats->nmin_bits, __float_as_uint(nrm));
             atomicMax(&stats->nmax_bits, __float_as_uint(nrm));
         }
@@ -408,7 +454,8 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restr
                                                             const float* __restrict__ q, long Q, int k, int S,
                                                             const float* __restrict__ cand_s, const int* __restrict__ cand_i,
                                                             int* __restrict__ out_idx, double* __restrict__ out_d,
-                                                            int* __restrict__ flagged, Stats* stats, float eps_r) {
+                                                            int* __restrict__ flagged, Stats* stats, float eps_r,
+                                                            const int* __restrict__ perm) {
     const long qi = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (qi >= Q) return;
@@ -431,6 +478,7 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restr
         if (c < total) {
             const long o = ((long)(c / CAND) * Q + qi) * CAND + (c % CAND);
             id = cand_i[o];
+            if (perm && id >= 0) id = perm[id];  // scan position -> bank row
             sc = cand_s[o];
             if ((c % CAND) == CAND - 1 && id >= 0) tau = fmaxf(tau, sc);  // a full list: its tail bounds the rejected rows
         }
@@ -490,7 +538,7 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restr
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct TcLayout {
-    size_t stats, bank_img, q_img, cand_s, cand_i, flagged, exact_ws, total;
+    size_t stats, bank_img, q_img, cand_s, cand_i, flagged, exact_ws, total, mean, key_in, key_out, idx_in, perm, sort_tmp, sort_tmp_bytes;
     int n_btiles, n_qtiles, n_qpairs, nsplit, tiles_per_split;
     size_t exact_ws_bytes;
 };
@@ -515,6 +563,19 @@ TcLayout tc_layout(long Q, long n_rows, int k, int kblk) {
     L.cand_s = off; off += align_up((size_t)L.nsplit * Q * CAND * sizeof(float), 256);
     L.cand_i = off; off += align_up((size_t)L.nsplit * Q * CAND * sizeof(int), 256);
     L.flagged = off; off += align_up((size_t)Q * sizeof(int), 256);
+    {   // scan order: mean query, projection keys, radix-sort buffers
+        const size_t bpad = (size_t)L.n_btiles * TILE;
+        L.mean = off; off += 256;
+        L.key_in = off; off += align_up(bpad * sizeof(float), 256);
+        L.key_out = off; off += align_up(bpad * sizeof(float), 256);
+        L.idx_in = off; off += align_up(bpad * sizeof(int), 256);
+        L.perm = off; off += align_up(bpad * sizeof(int), 256);
+        size_t tmp = 0;
+        cub::DeviceRadixSort::SortPairsDescending((void*)nullptr, tmp, (const float*)nullptr, (float*)nullptr, (const int*)nullptr,
+                                                  (int*)nullptr, (int)bpad);
+        L.sort_tmp_bytes = tmp;
+        L.sort_tmp = off; off += align_up(tmp, 256);
+    }
     // the exact re-check of unproven queries: worst case every query, see rf_knn_exact_nsplit
     L.exact_ws_bytes = ((size_t)148 * 8 * 32 + (size_t)Q) * k * (sizeof(int) + sizeof(double)) + 256;
     L.exact_ws = off; off += L.exact_ws_bytes;
@@ -540,9 +601,27 @@ int tc_run(const TcLayout& L, const float* bank, long n_rows, long row_offset, c
     const Stats init = {0, 0u, 0x7f7fffffu /*FLT_MAX*/, 0u};
     RF_CUDA_OK(cudaMemcpyAsync(stats, &init, sizeof(Stats), cudaMemcpyHostToDevice, s));
     const long bpad = (long)L.n_btiles * TILE, qpad = (long)L.n_qtiles * TILE;
-    knn_tc_prep_kernel<KBLK><<<(unsigned)rf_cdivl(bpad * 8, 256), 256, 0, s>>>(bank, n_rows, bpad, 1, bank_img, stats);
+    const int* perm = nullptr;
+    if (n_rows >= 16 * TILE && L.nsplit == 1) {  // scan order (see knn_scan_key_kernel); pointless for tiny banks
+        float* mean = (float*)(ws + L.mean);
+        float* key_in = (float*)(ws + L.key_in);
+        float* key_out = (float*)(ws + L.key_out);
+        int* idx_in = (int*)(ws + L.idx_in);
+        int* perm_w = (int*)(ws + L.perm);
+        RF_CUDA_OK(cudaMemsetAsync(mean, 0, 64 * sizeof(float), s));
+        const long q_sample = Q < 65536 ? Q : 65536;
+        knn_mean_query_kernel<<<(unsigned)(q_sample / 4 < 592 ? (q_sample + 3) / 4 : 592), 256, 0, s>>>(q, q_sample, mean);
+        RF_LAUNCH_OK("knn_mean_query_kernel");
+        knn_scan_key_kernel<<<(unsigned)rf_cdivl(bpad, 256), 256, 0, s>>>(bank, n_rows, bpad, mean, key_in, idx_in);
+        RF_LAUNCH_OK("knn_scan_key_kernel");
+        size_t tmp = L.sort_tmp_bytes;
+        RF_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending((void*)(ws + L.sort_tmp), tmp, (const float*)key_in, key_out,
+                                                             (const int*)idx_in, perm_w, (int)bpad, 0, 32, s));
+        perm = perm_w;
+    }
+    knn_tc_prep_kernel<KBLK><<<(unsigned)rf_cdivl(bpad * 8, 256), 256, 0, s>>>(bank, n_rows, bpad, 1, bank_img, stats, perm);
     RF_LAUNCH_OK("knn_tc_prep_kernel(bank)");
-    knn_tc_prep_kernel<KBLK><<<(unsigned)rf_cdivl(qpad * 8, 256), 256, 0, s>>>(q, Q, qpad, 0, q_img, stats);
+    knn_tc_prep_kernel<KBLK><<<(unsigned)rf_cdivl(qpad * 8, 256), 256, 0, s>>>(q, Q, qpad, 0, q_img, stats, nullptr);
     RF_LAUNCH_OK("knn_tc_prep_kernel(queries)");
     dim3 grid(L.n_qpairs, L.nsplit);
     if (!g_ev0) {
@@ -555,7 +634,7 @@ int tc_run(const TcLayout& L, const float* bank, long n_rows, long row_offset, c
     RF_LAUNCH_OK("knn_tc_candidates_kernel");
     RF_CUDA_OK(cudaEventRecord(g_ev1, s));
     knn_tc_rerank_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, s>>>(bank, row_offset, q, Q, k, L.nsplit, cand_s, cand_i,
-                                                                        out_idx, out_d, flagged, stats, eps_rel(KBLK));
+                                                                        out_idx, out_d, flagged, stats, eps_rel(KBLK), perm);
     RF_LAUNCH_OK("knn_tc_rerank_kernel");
     return 0;
 }
