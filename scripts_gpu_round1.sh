@@ -1,9 +1,16 @@
 #!/bin/bash
+# Round-1 measurement run: GPU parity tests, the three bench workloads, ncu launch lists and full captures.
 mkdir -p gpurun_out
-echo "== pytest -m gpu" ; timeout 1200 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider --durations=6 2>&1 | grep -E "passed|failed|FAILED|max abs err|ours-fp64|AssertionError|relative error|refine_full:|s call|s setup|Error" | cut -c1-300 | tee gpurun_out/pytest_gpu.log
-echo "== ncu full: halo conv 96->56 @ 8^3 x 2048 patches"
+echo "== pytest -m gpu" ; timeout 1200 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider 2>&1 | tail -3 | tee gpurun_out/pytest_gpu.log
+echo "== bench retrieval"; timeout 600 python bench.py 2> gpurun_out/bench_n1.err | tee gpurun_out/bench_n1.json | cut -c1-250; tail -1 gpurun_out/bench_n1.err
+echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tee gpurun_out/bench_ref.json | cut -c1-250
+echo "== bench refine"; timeout 600 python bench.py --workload refine 2> gpurun_out/bench_refine.err | tee gpurun_out/bench_refine.json | cut -c1-250
+echo "== bench stages"; timeout 600 python bench.py --workload stages 2>/dev/null > gpurun_out/stages.json; wc -c gpurun_out/stages.json
+echo "== ncu launch lists"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_retrieval.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_refine.csv python bench.py --workload refine --steps 1 --warmup 1 --no-cpu-baseline --no-cuda-graph > /dev/null 2>&1
+echo "== ncu full captures"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn_tc_candidates -c 1 -o gpurun_out/knn_cand python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_mlp_kernel -s 1 -c 1 -o gpurun_out/tc_mlp python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_conv3d_halo -c 1 -o gpurun_out/halo_conv_96_56 python tools/test_halo_conv.py --case 2048,8,32,64,56,0 > /dev/null 2>&1
-timeout 300 ncu --set full --clock-control none -k regex:tc_conv3d_halo -c 1 -o gpurun_out/halo_conv_dec16 python tools/test_halo_conv.py --case 8,64,16,0,16,0 > /dev/null 2>&1
-echo "== ncu launch list (refine)"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_refine.csv python bench.py --workload refine --steps 1 --warmup 1 --no-cpu-baseline --no-cuda-graph > gpurun_out/ncu_refine.log 2>&1; tail -1 gpurun_out/ncu_refine.log | cut -c1-200
-echo "== bench refine (graph)" ; timeout 600 python bench.py --workload refine --steps 5 --warmup 3 2> gpurun_out/bench_refine.err | tee gpurun_out/bench_refine.json | cut -c1-300 ; tail -2 gpurun_out/bench_refine.err
-ls -la gpurun_out
+ls -la gpurun_out | head -30
