@@ -389,6 +389,32 @@ def test_knn_bit_exact(dev, N, Q, k, method):
     assert np.array_equal(off_i.cpu().numpy(), want_i + 1000)
 
 
+@pytest.mark.parametrize("N,Q,k,method,clustered", [(5000, 40000, 8, 2, False), (4099, 38001, 8, 0, True), (20000, 40960, 16, 3, True)])
+def test_knn_scan_order_bit_exact(dev, N, Q, k, method, clustered):
+    """Many queries (one bank slice per CTA): the tensor-core pass scans the bank in descending projection on the
+    mean query (rf_knn_tc.cu scan order).  Results must still be the canonical exact top-k, on isotropic data and on
+    a clustered bank (rows and queries inside a narrow cone, many near-ties, duplicated rows)."""
+    from retrieval_fuse_b200 import ops
+    rng = np.random.default_rng(N + Q)
+    if clustered:
+        centre = _unit(rng, 1)
+        db = centre + 0.05 * rng.normal(size=(N, 64)).astype(np.float32)
+        q = centre + 0.05 * rng.normal(size=(Q, 64)).astype(np.float32)
+        db /= np.linalg.norm(db, axis=1, keepdims=True)
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        db, q = db.astype(np.float32), q.astype(np.float32)
+    else:
+        db, q = _unit(rng, N), _unit(rng, Q)
+    db[N // 2] = db[3]
+    db[N - 1] = db[3]
+    q[0] = db[3]
+    db[50:60] = db[40] + rng.normal(size=(10, 64)).astype(np.float32) * 1e-7
+    want_i, want_d = O.knn_exact(db, q, k)
+    got_i, got_d = ops.knn_topk(torch.from_numpy(db).to(dev), torch.from_numpy(q).to(dev), k, row_offset=7, method=method)
+    assert np.array_equal(got_i.cpu().numpy(), want_i + 7)
+    assert np.array_equal(got_d.cpu().numpy().astype(np.float32), want_d)
+
+
 def test_knn_tensor_core_proof_and_fallback(dev):
     """Methods 2/3: the observed tensor-core score error stays far below the proven
     bound, random banks need no re-check, and a bank with more exact duplicates than
