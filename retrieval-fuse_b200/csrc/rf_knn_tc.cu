@@ -440,39 +440,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
 // ------------------------------------------------------------------ re-rank + proof
 __device__ __forceinline__ bool cand_less(double d, int i, double d2, int i2) { return d < d2 || (d == d2 && i < i2); }
 
-__device__ __forceinline__ void warp_list_insert(double& ld, int& li, double cd, int ci, int lane) {
+// Sorted list of 16 (d, id) entries, one per lane of a HALF warp; inserts (cd, ci) if it ranks before an entry.
+__device__ __forceinline__ void half_list_insert(double& ld, int& li, double cd, int ci, int lane16, int half, bool doit) {
     const bool before = cand_less(ld, li, cd, ci);
-    const int pos = __popc(__ballot_sync(0xffffffffu, before));
-    const double ud = __shfl_up_sync(0xffffffffu, ld, 1);
-    const int ui = __shfl_up_sync(0xffffffffu, li, 1);
-    if (lane == pos) { ld = cd; li = ci; }
-    else if (lane > pos) { ld = ud; li = ui; }
+    const unsigned b = (__ballot_sync(0xffffffffu, before) >> (16 * half)) & 0xFFFFu;
+    const int pos = __popc(b);
+    const double ud = __shfl_up_sync(0xffffffffu, ld, 1, 16);
+    const int ui = __shfl_up_sync(0xffffffffu, li, 1, 16);
+    if (doit) {
+        if (lane16 == pos) { ld = cd; li = ci; }
+        else if (lane16 > pos) { ld = ud; li = ui; }
+    }
 }
 
-// One warp per query.  Candidate c of slice s: (cand_s, cand_i)[s][q][c].
+// Half a warp per query (the candidate lists hold 16 entries per slice, so 16 lanes cover one slice at a time and
+// the fp64 pipe is not fed half-empty warps).  Candidate c of slice s: (cand_s, cand_i)[s][q][c].
 __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restrict__ bank, long row_offset,
                                                             const float* __restrict__ q, long Q, int k, int S,
                                                             const float* __restrict__ cand_s, const int* __restrict__ cand_i,
                                                             int* __restrict__ out_idx, double* __restrict__ out_d,
                                                             int* __restrict__ flagged, Stats* stats, float eps_r,
                                                             const int* __restrict__ perm) {
-    const long qi = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (qi >= Q) return;
-    // the query in fp64, two elements per lane; |q|^2
+    const long hw = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 4;  // half-warp index = query
+    const int lane16 = threadIdx.x & 15, half = (threadIdx.x >> 4) & 1;
+    const bool live = hw < Q;
+    const long qi = live ? hw : Q - 1;  // a dead half warp shadows the last query (shuffles need all lanes), writes nothing
+    // the query in fp64, four elements per lane; |q|^2
     const float* qr = q + qi * 64;
-    const double q0 = (double)qr[lane], q1 = (double)qr[lane + 32];
-    double qn = q0 * q0 + q1 * q1;
+    double qn = 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
+    for (int j = 0; j < 4; ++j) { const double v = (double)qr[lane16 + 16 * j]; qn += v * v; }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o, 16);
 
     double ld = DBL_MAX;
     int li = INT_MAX;
     float tau = -FLT_MAX;       // max over slices of the slice's 16th best approximate score
     float err = 0.f;
     const int total = S * CAND;
-    for (int base = 0; base < total; base += 32) {
-        const int c = base + lane;
+    for (int base = 0; base < total; base += 16) {
+        const int c = base + lane16;
         int id = -1;
         float sc = -FLT_MAX;
         if (c < total) {
@@ -485,7 +492,8 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restr
         double d = DBL_MAX;
         if (id >= 0) {  // canonical fp64 distance, same arithmetic as the exact sweep
             const float4* xr = reinterpret_cast<const float4*>(bank + (long)id * 64);
-            double acc = 0.0, xn = 0.0;
+            double acc = 0.0;
+            float xn = 0.f;  // |x|^2 only feeds the error diagnostic: fp32 is plenty
 #pragma unroll 4
             for (int i = 0; i < 16; ++i) {
                 const float4 x4 = __ldg(xr + i);
@@ -495,32 +503,33 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restr
                     const double qv = (double)qr[4 * i + j];
                     const double diff = __dsub_rn(qv, (double)xv[j]);
                     acc = __dadd_rn(acc, __dmul_rn(diff, diff));
-                    xn = fma((double)xv[j], (double)xv[j], xn);
+                    xn = fmaf(xv[j], xv[j], xn);
                 }
             }
             d = acc;
             // observed approximation error of the tensor-core score (diagnostic for EPS_REL)
-            const double s_exact = 0.5 * (qn + xn - acc);
-            err = fmaxf(err, (float)fabs((double)sc - s_exact));
+            const float s_exact = 0.5f * (float)(qn + (double)xn - acc);
+            err = fmaxf(err, fabsf(sc - s_exact));
         }
-        // insert this round's candidates one by one (warp-uniform loop)
-        unsigned m = __ballot_sync(0xffffffffu, id >= 0);
-        while (m) {
-            const int src = __ffs(m) - 1;
+        // insert this round's candidates one by one (both half warps step together)
+        unsigned m = (__ballot_sync(0xffffffffu, id >= 0) >> (16 * half)) & 0xFFFFu;
+        while (__any_sync(0xffffffffu, m != 0)) {
+            const bool doit = m != 0;
+            const int src = doit ? __ffs(m) - 1 : 0;
             m &= m - 1;
-            const double cd = __shfl_sync(0xffffffffu, d, src);
-            const int ci = __shfl_sync(0xffffffffu, id, src) + (int)row_offset;
-            warp_list_insert(ld, li, cd, ci, lane);
+            const double cd = __shfl_sync(0xffffffffu, d, src, 16);
+            const int ci = __shfl_sync(0xffffffffu, id, src, 16) + (int)row_offset;
+            half_list_insert(ld, li, cd, ci, lane16, half, doit);
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
-        err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
+    for (int o = 8; o > 0; o >>= 1) {
+        tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, o, 16));
+        err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o, 16));
     }
-    if (lane < k) { out_idx[qi * k + lane] = li; out_d[qi * k + lane] = ld; }
+    if (live && lane16 < k) { out_idx[qi * k + lane16] = li; out_d[qi * k + lane16] = ld; }
     // proof: rejected rows have s~ <= tau  =>  d >= |q|^2 + min|x|^2 - 2 (tau + eps)
-    const double dk = __shfl_sync(0xffffffffu, ld, k - 1);
+    const double dk = __shfl_sync(0xffffffffu, ld, k - 1, 16);
     bool proven = true;
     if (tau > -FLT_MAX) {
         const double nmin = (double)__uint_as_float(stats->nmin_bits);
@@ -529,11 +538,12 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restr
         const double d_lb = qn + nmin * (1.0 - 1e-6) - 2.0 * ((double)tau + eps);
         proven = dk < d_lb - 1e-9;
     }
-    if (lane == 0) {
+    if (live && lane16 == 0) {
         if (!proven) flagged[atomicAdd(&stats->n_flagged, 1)] = (int)qi;
         atomicMax(&stats->max_err_bits, __float_as_uint(err));
     }
 }
+
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -633,7 +643,7 @@ int tc_run(const TcLayout& L, const float* bank, long n_rows, long row_offset, c
                                                                                L.n_btiles, L.tiles_per_split, cand_s, cand_i);
     RF_LAUNCH_OK("knn_tc_candidates_kernel");
     RF_CUDA_OK(cudaEventRecord(g_ev1, s));
-    knn_tc_rerank_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, s>>>(bank, row_offset, q, Q, k, L.nsplit, cand_s, cand_i,
+    knn_tc_rerank_kernel<<<(unsigned)rf_cdivl(Q * 16, 128), 128, 0, s>>>(bank, row_offset, q, Q, k, L.nsplit, cand_s, cand_i,
                                                                         out_idx, out_d, flagged, stats, eps_rel(KBLK), perm);
     RF_LAUNCH_OK("knn_tc_rerank_kernel");
     return 0;
