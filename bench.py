@@ -286,6 +286,19 @@ def run_stages(args, local):
     add("a5+a9 Patch04 MLP + normalise (fused chain)", timed(enc), flops=2.0 * n_par * patches.shape[0],
         note="weights (1.28 MB fp16 hi+lo) are re-streamed from L2 for every 128-row tile")
     del patches
+    # ---- a6 conv query encoder (Patch08, Matterport SR 16^3 -> 64^3): 64 x 8^3 patches per chunk
+    from retrieval_fuse_b200.pipeline import MATTERPORT_SR16
+    mcfg = MATTERPORT_SR16
+    md = mcfg["dataset"]
+    pipe_m = RetrievalPipeline(mcfg, bank=None, device=dev, weight_seed=1234)
+    mchunks = synthetic_tsdf_batch(args.chunks // 4, 16, md["voxel_size_input"], seed=9, device=dev, batch=1024).unsqueeze(1).contiguous()
+    mpu = lambda: ops.unfold3d_pad_stride(mchunks, pipe_m.in_kernel, md["patch_context_input"], pipe_m.in_stride, pipe_m.input_trunc,
+                                          norm_sub=md["input_mean"], norm_div=md["input_std"])
+    mpatches = mpu()
+    add("a1/a4 pad+unfold+normalise, 16^3 chunks -> 64 x 8^3", timed(mpu), bytes_=(mchunks.numel() + mpatches.numel()) * 4)
+    add(f"a6 Patch08 conv query encoder, {mpatches.shape[0]} x 8^3", timed(lambda: _encode_normalized(pipe_m.fenc_input, mpatches, 64)),
+        flops=361e6 / 64 * mpatches.shape[0])
+    del mpatches, mchunks
     # ---- a7 dictionary encoder (Patch32) incl. pad-unfold of 64^3 targets
     n_sc = 64
     targets = synthetic_tsdf_batch(n_sc, 64, rd["voxel_size_target"], seed=100, device=dev)

@@ -27,149 +27,15 @@
 //     accumulators for the whole item in TMEM (n_tiles x Npad columns <= 512).
 //   * Single-chunk inputs (C <= 8) pair two taps into one K = 16 step: LBO = 16 B makes
 //     the second K chunk the neighbouring slot, i.e. tap kw+1.
-#include <cuda_fp16.h>
 #include <stdlib.h>
 
-#include "rf_common.cuh"
+#include "rf_tc_common.cuh"
 
 namespace {
+using namespace rf_tc;
 
 constexpr int TM = 128, NTHREADS = 512, NB = 4, MAX_ABUF = 2;
 constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in maximum per CTA on sm_100
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        if (spins > (1u << 26)) {  // a pipeline bug must never hang the GPU
-            printf("rf_tc_conv_halo: mbarrier wait timed out (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
-            __trap();
-        }
-    }
-}
-// Whole-warp wait with a warp-uniform loop condition (a vote): the code after it stays provably convergent, which
-// the compiler needs in order to keep the MMA issue loop on the uniform datapath (uniform registers feed
-// tcgen05.mma directly; otherwise every MMA pays vector -> uniform register moves).
-__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
-        if (++spins > (1u << 26)) __trap();  // a pipeline bug must never hang the GPU
-    }
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// same, polling gently: the epilogue warps wait for a whole item's MMAs
-__device__ __forceinline__ void mbar_wait_warp_sleepy(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
-        __nanosleep(100);
-        if (++spins > (1u << 24)) __trap();
-    }
-}
-// Producer-side wait: these threads wait for a long time (a whole stage of MMAs); polling at full speed would
-// take shared-memory cycles away from the tensor core's operand reads.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        __nanosleep(200);
-        if (spins > (1u << 22)) {
-            printf("rf_tc_conv_halo: mbarrier wait timed out (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// Same, with the descriptors passed as (low, high) words: the low word carries start address and LBO and is the
-// only part that changes between MMAs.
-// `issue` (1 on the elected lane) predicates the instruction INSIDE the asm block: with a C++ `if (leader)` around
-// it the compiler sinks the descriptor arithmetic into the divergent region, computes it in vector registers and
-// pays two R2UR moves per MMA; unconditional arithmetic stays on the uniform datapath.
-__device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                        uint32_t idesc, uint32_t acc, uint32_t issue) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, q;\n\t"
-        ".reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "setp.ne.b32 q, %7, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc), "r"(issue)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(pred));
-    return pred;
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
-          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-// K-major, no swizzle: core matrix = 8 rows x 16 B stored as 128 contiguous bytes; LBO = byte distance
-// between the two K chunks of one K = 16 step, SBO = byte distance between consecutive 8-row groups.
-__device__ __forceinline__ uint64_t umma_desc_ns(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo & 0x3FFFFu) >> 4) << 16) |
-           ((uint64_t)((sbo & 0x3FFFFu) >> 4) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ uint32_t idesc_f16(int n) {  // D f32, A/B f16, both K-major, N>>3 @17, M>>4 @24
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-}
-__device__ __forceinline__ void split_f16(float x, uint32_t& hi, uint32_t& lo) {
-    const __half h = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
-    const __half l = __float2half_rn(x - __half2float(h));
-    hi = __half_as_ushort(h);
-    lo = __half_as_ushort(l);
-}
 
 // ------------------------------------------------------------------ activations -> haloed slot planes
 struct SplitArgs {
@@ -291,7 +157,7 @@ struct HaloArgs {
     int lines, n_wblk, n_tiles, P;  // P = slots per staged plane (incl. over-read slack)
     int S_st;                     // staged slots per plane that the bulk copies fill
     int pair, n_stages, nbuf, ck, kpg;
-    int Cout, Npad, act, out_ncdhw, n_acc, n_iss, n_items, n_sets;
+    int Cout, Npad, act, out_ncdhw, n_iss, n_items, n_sets;
     float slope, out_scale;
     uint32_t bslot_bytes, tmem_cols;
     uint16_t tile_off[32];        // first slot of M tile t within the staged block (uniform-indexed constant loads)
@@ -562,7 +428,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct Geo {
-    int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, n_acc, two_resident, n_sets;
+    int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, two_resident, n_sets;
     uint32_t tmem_cols, bslot;
     size_t smem;
     double score;
@@ -609,7 +475,6 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, Ge
         // cycles per (tile pair, 16 columns), and every item pays ~3000 cycles of pipeline fill.  Accumulators are
         // double-buffered (epilogue of item i under the MMAs of item i+1) when two sets fit TMEM; otherwise a second
         // resident CTA hides part of the epilogue.
-        const int n_acc = 1;  // accumulator sets per tile summed in the epilogue; one is enough, see mma_pattern.cu
         const double n_mma = (double)n_stages * 9 * kpg * (double)n_tiles * 3.0;
         const int n_iss = n_tiles < 6 ? (int)n_tiles : 6;
         const double t_epi = 1000.0 + (double)((n_tiles + 1) / 2) * (Npad / 16) * 2000.0 + (nbuf == 1 ? 4000.0 : 0.0);
@@ -629,7 +494,7 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, Ge
                 best.lines = lines; best.n_wblk = n_wblk; best.n_tiles = (int)n_tiles; best.P = (int)P; best.S_st = (int)S_st;
                 best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot; best.two_resident = two_resident ? 1 : 0;
                 best.tmem_cols = cols_needed;
-                best.n_acc = n_acc; best.n_sets = n_sets;
+                best.n_sets = n_sets;
                 best.smem = (size_t)smem_total;
                 best.score = score;
             }
@@ -749,7 +614,7 @@ extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void*
     a.lines = g.lines; a.n_wblk = g.n_wblk; a.n_tiles = g.n_tiles; a.P = g.P; a.S_st = g.S_st;
     a.pair = pair; a.n_stages = pair ? 1 : CCe / 2; a.nbuf = g.nbuf; a.ck = pair ? 1 : 2; a.kpg = pair ? 2 : 3;
     a.Cout = Cout; a.Npad = Npad; a.act = act; a.out_ncdhw = out_ncdhw; a.slope = slope; a.out_scale = out_scale;
-    a.bslot_bytes = g.bslot; a.tmem_cols = g.tmem_cols; a.n_acc = g.n_acc;
+    a.bslot_bytes = g.bslot; a.tmem_cols = g.tmem_cols;
     a.n_iss = g.n_tiles < 6 ? g.n_tiles : 6;
     // tile t = lb * n_wblk + wb starts at slot lb * (16 lines) + wb * 8 (linear mode: n_wblk = 1, 128 slots per tile)
     RF_CHECK_ARG(g.n_tiles <= 32, "rf_tc_conv3d_halo_fwd: internal: more than 32 M tiles");

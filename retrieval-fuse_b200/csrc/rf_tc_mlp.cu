@@ -17,11 +17,10 @@
 //   * the layer epilogue (all 8 worker warps) reads TMEM, adds bias, applies the activation, splits to fp16
 //     hi / lo and writes the next layer's operand planes; the last layer optionally L2-normalises rows and
 //     writes fp32 output.
-#include <cuda_fp16.h>
-
-#include "rf_common.cuh"
+#include "rf_tc_common.cuh"
 
 namespace {
+using namespace rf_tc;
 
 constexpr int TM = 128, WORKERS = 256, NTHREADS = 288, MAX_LAYERS = 8, MAX_SLOTS = 8;
 constexpr int PLANE = TM * 16;             // one 8-channel chunk plane: 128 rows x 16 B
@@ -29,105 +28,6 @@ constexpr int ACT_CHUNKS = 32;             // 256 channels resident
 constexpr int ACT_BYTES = ACT_CHUNKS * PLANE;  // 64 KiB per hi / lo
 constexpr int SMEM_LIMIT = 232448;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// whole-warp wait with a warp-uniform loop condition (keeps the issue loop on the uniform datapath)
-__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
-        if (++spins > (1u << 26)) __trap();  // a pipeline bug must never hang the GPU
-    }
-}
-// same, polling gently: used while MMAs run (hundreds to thousands of cycles), by all worker warps at once
-__device__ __forceinline__ void mbar_wait_warp_sleepy(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
-        __nanosleep(40);
-        if (++spins > (1u << 24)) __trap();
-    }
-}
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        __nanosleep(100);
-        if (spins > (1u << 23)) __trap();
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// descriptors as (low, high) words; `issue` predicates the MMA inside the asm block (see rf_tc_conv_halo.cu)
-__device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                        uint32_t idesc, uint32_t acc, uint32_t issue) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, q;\n\t"
-        ".reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "setp.ne.b32 q, %7, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc), "r"(issue)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(pred));
-    return pred;
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
-          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t idesc_f16(int n) {  // D f32, A/B f16, both K-major, N>>3 @17, M>>4 @24
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-}
-__device__ __forceinline__ void split_f16(float x, uint32_t& hi, uint32_t& lo) {
-    const __half h = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
-    const __half l = __float2half_rn(x - __half2float(h));
-    hi = __half_as_ushort(h);
-    lo = __half_as_ushort(l);
-}
 __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // W [N, K] fp32 row-major (nn.Linear.weight) -> [k step][hi|lo][chunk 0|1][Np rows][16 B]
@@ -242,7 +142,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
                     const uint32_t bytes = 64u * (uint32_t)a.Np[l];
                     for (int ks = 0; ks < nks; ++ks, ++kt) {
                         const uint32_t sl = kt % (uint32_t)a.nbw;
-                        mbar_wait_relaxed(bar_wempty + 8 * sl, ((kt / (uint32_t)a.nbw) & 1u) ^ 1u);
+                        mbar_wait_relaxed(bar_wempty + 8 * sl, ((kt / (uint32_t)a.nbw) & 1u) ^ 1u, 100);
                         mbar_arrive_expect_tx(bar_wfull + 8 * sl, bytes);
                         bulk_g2s(sW + sl * a.slot_bytes, a.wimg[l] + (size_t)ks * bytes, bytes, bar_wfull + 8 * sl);
                     }
@@ -344,7 +244,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
                     } else {
                         kt += (uint32_t)(ks1 - ks0);
                     }
-                    mbar_wait_warp_sleepy(bar_mma, mma_phase & 1u);
+                    mbar_wait_warp_sleepy(bar_mma, mma_phase & 1u, 40);
                     ++mma_phase;
                     tc_fence_after();
                 }
