@@ -8,10 +8,13 @@ Workload at N = 1 (BASELINE.json configs[1]): ShapeNetV2 super_resolution
 retrieval_008_064 - query encoder (Patch04) + exact kNN (fetch 2K = 8, demote,
 keep K = 4) for 10 000 synthetic 8^3 chunks (640 000 queries) per step against
 a bank of 2 048 encoded synthetic 64^3 targets (131 072 rows + the sentinel).
-At N > 1 the bank is sharded by rows and every rank brings its own 10 000
-chunks (weak scaling): queries are all-gathered, every rank ranks
-all queries against its shard, the per-shard top-2K lists are exchanged and
-merged.  `--workload refine` times the full refinement forward (config 3
+At N > 1 every rank brings its own 10 000 chunks (weak scaling) and the
+bank is sharded by rows into `--bank-shards` shards (default 2): the ranks form
+N / shards groups, each group holds one full copy of the bank, queries are
+all-gathered inside the group, every rank ranks its group's queries against its
+shard, the per-shard top-2K lists are exchanged (all-to-all) and merged.
+`--bank-shards N` is the fully sharded layout; the line also carries the fully
+replicated variant (no collective on the data path) as `replicated_bank`.  `--workload refine` times the full refinement forward (config 3
 shapes) instead; it is reported, not the headline.
 
 One JSON line on stdout (rank 0); everything else goes to stderr.
@@ -39,6 +42,19 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None  # set when fd 1 has been redirected to stderr (multi-rank runs)
+
+
+def emit(line: dict):
+    """The one JSON line of the contract, on the real stdout."""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text.encode())
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -52,6 +68,10 @@ def parse():
     ap.add_argument("--bank", default="encoded", choices=["encoded", "random"],
                     help="encoded: Patch32 embeddings of synthetic 64^3 targets (the workload); random: unit Gaussian "
                          "bank AND queries (profiling aid, BASELINE config 5 style)")
+    ap.add_argument("--bank-shards", type=int, default=0,
+                    help="N > 1: row shards of the bank (0 = auto: 2, the smallest sharding that keeps the NCCL exchange "
+                         "on the data path; the N / shards groups of ranks each hold one full copy and exchange "
+                         "inside the group).  --bank-shards N = one shard per rank")
     ap.add_argument("--refine-batch", type=int, default=8)
     ap.add_argument("--no-cuda-graph", action="store_true", help="refine workload: launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample-chunks", type=int, default=2048, help="chunks of the workload the CPU arm runs per step (~10-15 s)")
@@ -354,8 +374,12 @@ def run_ours(args, rank, local, world):
     dev = torch.device("cuda", local)
     torch.set_grad_enabled(False)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: stdout carries exactly one JSON line
+        # stdout carries exactly ONE JSON line, but NCCL writes its version banner there from C: point fd 1 at stderr
+        # for the whole run and keep the real stdout for the result line (emit())
+        global _REAL_STDOUT
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     peaks = {}
     try:
@@ -374,17 +398,30 @@ def run_ours(args, rank, local, world):
         cfg = SHAPENET_SR_RETRIEVAL
         d = cfg["dataset"]
         S_tot = args.bank_scenes
-        per = (S_tot + world - 1) // world
-        lo, hi = min(rank * per, S_tot), min((rank + 1) * per, S_tot)
+        # Bank placement: the bank is sharded by rows only as far as asked (default 2 shards: a 33.5 MB
+        # bank needs no sharding for memory, and every additional shard makes every rank rank ALL of a group's
+        # queries); the world is world / shards groups of ranks, each group holds one full copy of the bank and runs
+        # the all-gather / all-to-all exchange among its own ranks.
+        S_b = args.bank_shards if args.bank_shards > 0 else min(world, 2)
+        if S_b > world or world % S_b:
+            S_b = world
+        shard, gidx, my_group = rank % S_b, rank // S_b, None
+        if world > 1:
+            for gi in range(world // S_b):  # every rank creates every group (collective call)
+                grp = dist.new_group(list(range(gi * S_b, (gi + 1) * S_b)))
+                if gi == gidx:
+                    my_group = grp
+        per = (S_tot + S_b - 1) // S_b
+        lo, hi = min(shard * per, S_tot), min((shard + 1) * per, S_tot)
         t0 = time.time()
         if args.bank == "encoded":
-            targets = synthetic_tsdf_batch(hi - lo, 64, d["voxel_size_target"], seed=100 + rank, device=dev)
+            targets = synthetic_tsdf_batch(hi - lo, 64, d["voxel_size_target"], seed=100 + shard, device=dev)
             bank, _ = build_bank_from_targets(cfg, targets, dev, weight_seed=11, scene_offset=lo, n_scenes_total=S_tot,
                                               batch_patches=4096)
             del targets
         else:
             from retrieval_fuse_b200.util.retrieval import EmbeddingBank
-            g = torch.Generator(device=dev).manual_seed(1 + rank)
+            g = torch.Generator(device=dev).manual_seed(1 + shard)
             n_loc = (hi - lo) * 64 + (1 if hi == S_tot else 0)
             emb = torch.nn.functional.normalize(torch.randn(n_loc, 64, generator=g, device=dev), dim=1)
             meta = torch.zeros((S_tot * 64 + 1, 7), device=dev)
@@ -392,7 +429,7 @@ def run_ours(args, rank, local, world):
             bank = EmbeddingBank(emb, meta, [f"scene{i:05d}" for i in range(S_tot)], row_offset=lo * 64, n_total=S_tot * 64 + 1)
         torch.cuda.synchronize(dev)
         log(f"[rank {rank}] bank shard rows {bank.emb.shape[0]} of {bank.n_total} built in {time.time() - t0:.1f}s")
-        sq = ShardedBankQuery(bank) if world > 1 else None
+        sq = ShardedBankQuery(bank, group=my_group) if world > 1 else None
         pipe = RetrievalPipeline(cfg, bank, device=dev, weight_seed=1234, sharded_query=sq)
         B = args.chunks
         chunks = synthetic_tsdf_batch(B, 8, d["voxel_size_input"], seed=7 + rank, device=dev, batch=2048).unsqueeze(1).contiguous()
@@ -426,17 +463,18 @@ def run_ours(args, rank, local, world):
         pipe_repl = None
         if world > 1:
             parts = [torch.empty((min((r + 1) * per, S_tot) - min(r * per, S_tot)) * 64 + (1 if min((r + 1) * per, S_tot) == S_tot else 0),
-                                 64, device=dev) for r in range(world)]
-            dist.all_gather(parts, bank.emb)
+                                 64, device=dev) for r in range(S_b)]
+            dist.all_gather(parts, bank.emb, group=my_group)
             from retrieval_fuse_b200.util.retrieval import EmbeddingBank
             full = EmbeddingBank(torch.cat(parts), bank.meta, bank.scenes)
             pipe_repl = RetrievalPipeline(cfg, full, device=dev, fenc_input=pipe.fenc_input)
             del parts
         workload = f"ShapeNetV2 SR retrieval_008_064: Patch04 encode + exact kNN (fetch 8, demote, keep 4), {B} chunks x 64 queries vs {n_rows} rows"
         config = {"workload": workload, "chunks_per_step_per_gpu": B, "bank_rows": n_rows, "K": cfg["K"],
-                  "bank": "sharded by rows" if world > 1 else "single GPU", "l2": "flushed between timed steps (256 MiB write)",
+                  "bank": (f"{S_b} row shards x {world // S_b} replica groups, exchange (all-gather queries, all-to-all "
+                           f"top-2K lists) inside a group") if world > 1 else "single GPU", "bank_shards": S_b if world > 1 else 1, "l2": "flushed between timed steps (256 MiB write)",
                   "knn_method": args.knn_method, "embeddings": args.bank}
-        algo_flops = 2.0 * Q * world * bank.emb.shape[0] * 64  # per rank: all ranks' queries x its shard
+        algo_flops = 2.0 * Q * (S_b if world > 1 else 1) * bank.emb.shape[0] * 64  # per rank: its group's queries x its shard
         units_per_step = B
     else:
         cfg = FRONT3D_SR
@@ -574,8 +612,8 @@ def run_ours(args, rank, local, world):
                             "from TMEM by the epilogue (K = 64 is too short to amortise that), which bounds this GEMM far below "
                             "the MMA rate; bank rows are scanned in descending projection on the mean query so that the "
                             "running top-16 thresholds tighten early (exactness unaffected)",
-                    "scores_per_clk_per_sm": (Q * world * float(bank.emb.shape[0])) / (k_ms / 1e3) / 148.0 / 1.965e9,
-                    "hbm_view": {"algorithmic_bytes": bank.emb.numel() * 4 + Q * world * 256 + Q * world * 8 * 12,
+                    "scores_per_clk_per_sm": algo_flops / 128.0 / (k_ms / 1e3) / 148.0 / 1.965e9,
+                    "hbm_view": {"algorithmic_bytes": bank.emb.numel() * 4 + algo_flops / (128.0 * bank.emb.shape[0]) * (256 + 8 * 12),
                                  "peak_gbs": peaks.get("hbm_gbs")}}
         else:
             roof = {"bound": "tensor", "kernel": "refine forward (all kernels)", "achieved": algo_flops / (knn_ms / 1e3) / 1e12,
@@ -616,7 +654,7 @@ def run_ours(args, rank, local, world):
             except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {type(e).__name__}: {e}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
