@@ -39,6 +39,16 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 26)) __trap();
     }
 }
+// same with back-off: a few fast polls (the common short wait), then sleep between polls so that a warp that waits
+// for thousands of cycles (an issuer waiting for the epilogue, a weight block in flight) does not take issue slots
+// and mbarrier bandwidth from the warps that are working
+__device__ __forceinline__ void mbar_wait_warp_backoff(uint32_t bar, uint32_t parity, unsigned ns = 64) {
+    uint32_t spins = 0;
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if (++spins > 8) __nanosleep(ns);
+        if (spins > (1u << 24)) __trap();
+    }
+}
 // same, polling gently: for warps that wait for a whole phase of MMAs
 __device__ __forceinline__ void mbar_wait_warp_sleepy(uint32_t bar, uint32_t parity, unsigned ns = 100) {
     uint32_t spins = 0;

@@ -27,6 +27,7 @@
 //     accumulators for the whole item in TMEM (n_tiles x Npad columns <= 512).
 //   * Single-chunk inputs (C <= 8) pair two taps into one K = 16 step: LBO = 16 B makes
 //     the second K chunk the neighbouring slot, i.e. tap kw+1.
+#include <math.h>
 #include <stdlib.h>
 
 #include "rf_tc_common.cuh"
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs
 }
 
 // ------------------------------------------------------------------ weight image
-// [stage][(kd,kh) group][k step][hi|lo][K chunk][Npad rows][16 B]; a ring slot of the conv kernel = one group.
+// [stage][(kd,kh) group][k step][K chunk][hi rows | lo rows (Npad each)][16 B]; a ring slot of the conv kernel = one group.
 // normal: k step = kw, K chunk c <-> channel chunk 2*stage + c.   pair (one channel chunk): k step 0 = taps
 // kw 0 (chunk 0) and kw 1 (chunk 1); k step 1 = tap kw 2 (chunk 0) and zeros.
 __global__ void __launch_bounds__(256) halo_weight_image_kernel(const float* __restrict__ w, int Cout, int C1, int C2, int Cp1,
@@ -136,10 +137,12 @@ __global__ void __launch_bounds__(256) halo_weight_image_kernel(const float* __r
             lo[e >> 1] |= lv << (16 * (e & 1));
         }
     }
-    const long blk = (long)Npad * 32;  // one (k step, hi|lo) operand block
-    uint8_t* base = img + (((long)(st * 9 + g) * kpg + ks) * 2) * blk + (long)kc * Npad * 16 + (long)n * 16;
+    // one k step = a K-major operand of 2*Npad rows: rows [0, Npad) the hi parts, rows [Npad, 2 Npad) the lo parts, so
+    // that [W_hi; W_lo] can be ONE N = 2 Npad operand (LBO = 2 Npad * 16 B between the two K chunks)
+    const long step = (long)Npad * 64;
+    uint8_t* base = img + ((long)(st * 9 + g) * kpg + ks) * step + (long)kc * (2L * Npad * 16) + (long)n * 16;
     *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(base + blk) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(base + (long)Npad * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // ------------------------------------------------------------------ the convolution
@@ -157,7 +160,7 @@ struct HaloArgs {
     int lines, n_wblk, n_tiles, P;  // P = slots per staged plane (incl. over-read slack)
     int S_st;                     // staged slots per plane that the bulk copies fill
     int pair, n_stages, nbuf, ck, kpg;
-    int Cout, Npad, act, out_ncdhw, n_iss, n_items, n_sets;
+    int Cout, Npad, act, out_ncdhw, n_iss, n_items, n_sets, fused;
     float slope, out_scale;
     uint32_t bslot_bytes, tmem_cols;
     uint16_t tile_off[32];        // first slot of M tile t within the staged block (uniform-indexed constant loads)
@@ -234,7 +237,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
         // ---- activation producer: one stage = ck channel chunks x (hi, lo) planes of the item's haloed block; two
         // passes over the channel stages (cross products first, then hi * hi; see the issuers)
         const long slab = (long)a.Hp * a.Wp;
-        const int n_loads = resident ? 1 : 2 * a.n_stages;
+        const int n_pass = a.fused ? 1 : 2;
+        const int n_loads = resident ? 1 : n_pass * a.n_stages;
         uint32_t lc = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
             int n0, gact = 1, d0 = 0, h0 = 0;
@@ -267,10 +271,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
     } else if (warp == 3) {
       if (lane == 0) {
         // ---- weight producer: ring of (kd,kh) groups; the second pass of every item streams the same groups again
-        const int per_pass = a.n_stages * 9;
+        const int per_pass = a.n_stages * 9, n_pass = a.fused ? 1 : 2;
         uint32_t gc = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x)
-            for (int gi = 0; gi < 2 * per_pass; ++gi, ++gc) {
+            for (int gi = 0; gi < n_pass * per_pass; ++gi, ++gc) {
                 const uint32_t sl = gc % NB;
                 const int img = gi >= per_pass ? gi - per_pass : gi;
                 mbar_wait_relaxed(bar_bempty + 8 * sl, ((gc / NB) & 1u) ^ 1u);
@@ -289,16 +293,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
         if (iss < a.n_iss) {
             const uint32_t leader = elect_one();
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-            const uint32_t idesc = idesc_f16(a.Npad);
+            const uint32_t idesc = idesc_f16(a.Npad), idesc2 = idesc_f16(2 * a.Npad);
             // descriptor = {lo: start >> 4 | (LBO >> 4) << 16, hi: SBO >> 4 | version 1 << 14}; addresses advance in
             // 16-byte units = slots, so "+ slots" on the low word moves the window.
             const uint32_t a_hi32 = (a.lines ? (uint32_t)a.Wp : 8u) | (1u << 14);
             const uint32_t a_lbo = (a.pair ? 1u : (uint32_t)a.P) << 16;
             const uint32_t b_hi32 = 8u | (1u << 14);
-            const uint32_t b_lbo = (uint32_t)a.Npad << 16;
-            const uint32_t blk_u = (uint32_t)a.Npad * 2u;       // one (k step, hi|lo) weight block, in 16-byte units
+            const uint32_t b_lbo = (uint32_t)(2 * a.Npad) << 16;  // K chunks of a k step are 2 Npad rows apart
+            const uint32_t step_u = (uint32_t)a.Npad * 4u;        // one k step of weights, in 16-byte units
             const uint32_t lo_off = (uint32_t)(a.ck * a.P);     // hi -> lo plane, in slots
-            const uint32_t npad = (uint32_t)a.Npad, set_cols = (uint32_t)(a.n_tiles * a.Npad);
+            const uint32_t npad = (uint32_t)a.Npad, tile_cols = a.fused ? 2u * npad : npad, set_cols = (uint32_t)a.n_tiles * tile_cols;
+            const int n_vs = (a.fused ? 1 : 2) * a.n_stages;
             // The tensor core truncates when it aligns the 16 products of a K step with the fp32 accumulator, a
             // bias that grows with the number of accumulations at full magnitude (measured: error linear in the
             // MMA count).  So the two small cross products (hi*lo, lo*hi: 2^-11 of the result) of ALL taps and
@@ -311,33 +316,40 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
                 // accumulator set of this item (two sets when they fit TMEM: the epilogue of item i overlaps the MMAs of
                 // item i+1); wait until the epilogue has drained the set's previous item
                 const uint32_t set = a.n_sets == 2 ? (it & 1u) : 0u, use = a.n_sets == 2 ? (it >> 1) : it;
-                mbar_wait_warp(bar_dempty + 8 * set, (use & 1u) ^ 1u);
+                mbar_wait_warp_backoff(bar_dempty + 8 * set, (use & 1u) ^ 1u, 200);
                 tc_fence_after();
                 if (dbg) g_halo_dbg[it * 8 + 1] = clock64();
                 uint32_t b = 0;
-                for (int vs = 0; vs < 2 * a.n_stages; ++vs) {
+                for (int vs = 0; vs < n_vs; ++vs) {
                     const int pass = vs >= a.n_stages ? 1 : 0;
                     if (!resident || vs == 0) {
                         b = lc % (uint32_t)a.nbuf;
-                        mbar_wait_warp(bar_afull + 8 * b, (lc / (uint32_t)a.nbuf) & 1u);
+                        mbar_wait_warp_backoff(bar_afull + 8 * b, (lc / (uint32_t)a.nbuf) & 1u, 100);
                         tc_fence_after();
                         if (dbg && vs == 0) g_halo_dbg[it * 8 + 2] = clock64();
                     }
                     const uint32_t abase = (((sA + b * abuf_bytes) & 0x3FFFFu) >> 4) | a_lbo;
                     for (int g = 0; g < 9; ++g, ++gc) {
                         const uint32_t sl = gc % NB;
-                        mbar_wait_warp(bar_bfull + 8 * sl, (gc / NB) & 1u);
+                        mbar_wait_warp_backoff(bar_bfull + 8 * sl, (gc / NB) & 1u, 40);
                         tc_fence_after();
                         const int kd = g / 3, kh = g % 3;
                         const uint32_t bbase = (((sB + sl * a.bslot_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                         for (int ks = 0; ks < a.kpg; ++ks) {
                             const uint32_t koff = (uint32_t)((kd * a.Hs + kh) * a.Wp + (a.pair ? 2 * ks : ks));
-                            const uint32_t b_hi = bbase + (uint32_t)ks * 2u * blk_u, b_lo = b_hi + blk_u;
+                            const uint32_t b_hi = bbase + (uint32_t)ks * step_u, b_lo = b_hi + npad;  // lo rows follow the hi rows
                             const uint32_t acc = (vs | g | ks) ? 1u : 0u;  // the very first MMA of a tile overwrites its accumulator
                             for (int t = iss; t < a.n_tiles; t += a.n_iss) {
-                                const uint32_t d = tmem_u + set * set_cols + (uint32_t)t * npad;
+                                const uint32_t d = tmem_u + set * set_cols + (uint32_t)t * tile_cols;
                                 const uint32_t da = abase + koff + a.tile_off[t];
-                                if (pass == 0) {
+                                if (a.fused) {
+                                    // A_hi x [W_hi; W_lo] as ONE N = 2 Npad MMA -> columns [main | cross]; A_lo x W_hi into
+                                    // the cross block.  For N <= 64 the pipe time is set by reading the A operand, so
+                                    // the doubled N is almost free: two MMAs instead of three, one pass over the stages,
+                                    // and the main block still sees only the hi*hi accumulations.
+                                    tc_mma2(d, da, a_hi32, b_hi, b_hi32, idesc2, acc, leader);                 // hi * [hi | lo]
+                                    tc_mma2(d + npad, da + lo_off, a_hi32, b_hi, b_hi32, idesc, 1u, leader);   // lo * hi -> cross
+                                } else if (pass == 0) {
                                     tc_mma2(d, da, a_hi32, b_lo, b_hi32, idesc, acc, leader);          // hi * lo
                                     tc_mma2(d, da + lo_off, a_hi32, b_hi, b_hi32, idesc, 1u, leader);  // lo * hi
                                 } else {
@@ -347,7 +359,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
                         }
                         if (leader) tc_commit(bar_bempty + 8 * sl);
                     }
-                    if (!resident || vs == 2 * a.n_stages - 1) {
+                    if (!resident || vs == n_vs - 1) {
                         if (leader) tc_commit(bar_aempty + 8 * b);
                         ++lc;
                     }
@@ -372,7 +384,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
             const bool dbg = blockIdx.x == 0 && threadIdx.x == 256 && it < 6;
             if (dbg) g_halo_dbg[it * 8 + 4] = clock64();
             const uint32_t set = a.n_sets == 2 ? (it & 1u) : 0u, use = a.n_sets == 2 ? (it >> 1) : it;
-            const uint32_t tm_set = tmem_base + set * (uint32_t)(a.n_tiles * a.Npad);
+            const uint32_t tile_cols = a.fused ? 2u * (uint32_t)a.Npad : (uint32_t)a.Npad;
+            const uint32_t tm_set = tmem_base + set * (uint32_t)a.n_tiles * tile_cols;
             mbar_wait_warp_sleepy(bar_dfull + 8 * set, use & 1u);
             tc_fence_after();
             if (dbg) g_halo_dbg[it * 8 + 5] = clock64();
@@ -382,7 +395,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
                 const long vox = vox0 + (rt & 0x3FFFFFF);
                 for (int c0 = 0; c0 < a.Npad; c0 += 16) {
                     float v[16];
-                    tc_ld16(tm_set + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * a.Npad + c0), v);
+                    tc_ld16(tm_set + ((uint32_t)(q * 32) << 16) + (uint32_t)t * tile_cols + (uint32_t)c0, v);
+                    if (a.fused) {  // main + cross blocks
+                        float u[16];
+                        tc_ld16(tm_set + ((uint32_t)(q * 32) << 16) + (uint32_t)t * tile_cols + (uint32_t)(a.Npad + c0), u);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] += u[e];
+                    }
                     if (dbg && t == 0 && c0 == 0) g_halo_dbg[it * 8 + 7] = clock64();
                     if (dbg && t == 2 && c0 == 0) g_halo_dbg[48 + it] = clock64();
                     if (!valid) continue;
@@ -428,7 +447,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct Geo {
-    int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, two_resident, n_sets;
+    int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, two_resident, n_sets, fused;
     uint32_t tmem_cols, bslot;
     size_t smem;
     double score;
@@ -460,7 +479,7 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, Ge
         }
         long P = max_slot + 1 > S_st ? max_slot + 1 : S_st;
         P = (P + 7) / 8 * 8;
-        if (n_tiles * Npad > 512 || n_tiles > 32 || P * 16 >= (1L << 18)) return;
+        if (n_tiles * Npad > 512 || n_tiles > 32 || P * 16 >= (1L << 18)) return;  // (the fused scheme needs twice the columns: checked below)
         const long avail = avail_all - n_tiles * 512;  // the row table: n_tiles x 128 ints
         // two staging buffers whenever they fit: the next stage (or the next item's block) loads during the MMAs
         const long smemA1 = (long)planes * P * 16;
@@ -471,32 +490,44 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, Ge
         const long outputs = stacked ? (long)G * D * H * W : (long)Dt * Ht * W;
         const long n_items = stacked ? (N + G - 1) / G : (long)N * (D / Dt) * (H / Ht);
         // Cost model, calibrated on B200 (tools/halo_geo_sweep.sh): an M128 K16 MMA occupies the tensor pipe for ~40
-        // (N <= 32) to 48 (N = 64) cycles, one issuer warp sustains one MMA per ~150 cycles, the epilogue costs ~2000
+        // (N <= 32) to 48 (N = 64) cycles, one issuer warp sustains one MMA per ~150 cycles, the epilogue costs ~1200
         // cycles per (tile pair, 16 columns), and every item pays ~3000 cycles of pipeline fill.  Accumulators are
         // double-buffered (epilogue of item i under the MMAs of item i+1) when two sets fit TMEM; otherwise a second
         // resident CTA hides part of the epilogue.
-        const double n_mma = (double)n_stages * 9 * kpg * (double)n_tiles * 3.0;
+        const double k_steps = (double)n_stages * 9 * kpg * (double)n_tiles;  // (k step, tile) pairs of one item
         const int n_iss = n_tiles < 6 ? (int)n_tiles : 6;
-        const double t_epi = 1000.0 + (double)((n_tiles + 1) / 2) * (Npad / 16) * 2000.0 + (nbuf == 1 ? 4000.0 : 0.0);
         const double waves = (double)((n_items + 147) / 148);   // items every SM walks through (the tensor pipe is per SM)
-        for (int n_sets = 1; n_sets <= 2; ++n_sets) {
-            if (n_sets * n_tiles * Npad > 512) break;
-            uint32_t cols_needed = 32;
-            while ((long)cols_needed < n_tiles * Npad * n_sets) cols_needed <<= 1;
-            const long smem_total = 1024 + smemA + (long)NB * bslot + 256 + n_tiles * 512;
-            const bool two_resident = smem_total <= 113 * 1024 && cols_needed <= 256;
-            const double pipe = Npad > 32 ? 48.0 : 40.0, issue = 150.0 / (n_iss * (two_resident ? 2 : 1));
-            const double t_mma = n_mma * (pipe > issue ? pipe : issue);
-            const double t_item = 3000.0 + (n_sets == 2 ? (t_mma > t_epi ? t_mma : t_epi) : t_mma + (two_resident ? 0.3 : 1.0) * t_epi);
-            const double score = (double)outputs * (double)n_items / (waves * t_item);
-            if (score > best.score) {
-                best.Dt = stacked ? D : Dt; best.Ht = stacked ? H : Ht; best.Hs = Hs; best.G = stacked ? G : 1; best.stacked = stacked;
-                best.lines = lines; best.n_wblk = n_wblk; best.n_tiles = (int)n_tiles; best.P = (int)P; best.S_st = (int)S_st;
-                best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot; best.two_resident = two_resident ? 1 : 0;
-                best.tmem_cols = cols_needed;
-                best.n_sets = n_sets;
-                best.smem = (size_t)smem_total;
-                best.score = score;
+        auto pipe_cycles = [](int n) { return n <= 32 ? 40.0 : n <= 64 ? 48.0 : n <= 128 ? 64.0 : 128.0; };
+        const char* force = getenv("RF_HALO_FUSED");  // tuning aid: "0" / "1" forces the MMA scheme
+        // fused = 1: two MMAs per step, A_hi x [W_hi; W_lo] (N = 2 Npad) and A_lo x W_hi, accumulators [main | cross]
+        // of 2 Npad columns per tile, one pass over the stages; fused = 0: three N = Npad MMAs in two passes.
+        for (int fused = 0; fused < 2; ++fused) {
+            if (force && atoi(force) != fused) continue;
+            const int tile_cols = fused ? 2 * Npad : Npad;
+            if (fused && 2 * Npad > 256) continue;
+            for (int n_sets = 1; n_sets <= 2; ++n_sets) {
+                if ((long)n_sets * n_tiles * tile_cols > 512) break;
+                uint32_t cols_needed = 32;
+                while ((long)cols_needed < n_tiles * tile_cols * n_sets) cols_needed <<= 1;
+                const long smem_total = 1024 + smemA + (long)NB * bslot + 256 + n_tiles * 512;
+                const bool two_resident = smem_total <= 113 * 1024 && cols_needed <= 256;
+                const double issue = 150.0 / (n_iss * (two_resident ? 2 : 1));
+                const double per_step = fused ? fmax(pipe_cycles(2 * Npad), issue) + fmax(pipe_cycles(Npad), issue)
+                                              : 3.0 * fmax(pipe_cycles(Npad), issue);
+                const double t_mma = k_steps * per_step;
+                const double t_epi = 1000.0 + (double)((n_tiles + 1) / 2) * (tile_cols / 16) * 1200.0 + (nbuf == 1 ? 4000.0 : 0.0);
+                const double t_item = (fused ? 2000.0 : 3000.0) +
+                                      (n_sets == 2 ? fmax(t_mma, t_epi) : t_mma + (two_resident ? 0.3 : 1.0) * t_epi);
+                const double score = (double)outputs * (double)n_items / (waves * t_item);
+                if (score > best.score) {
+                    best.Dt = stacked ? D : Dt; best.Ht = stacked ? H : Ht; best.Hs = Hs; best.G = stacked ? G : 1; best.stacked = stacked;
+                    best.lines = lines; best.n_wblk = n_wblk; best.n_tiles = (int)n_tiles; best.P = (int)P; best.S_st = (int)S_st;
+                    best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot; best.two_resident = two_resident ? 1 : 0;
+                    best.tmem_cols = cols_needed;
+                    best.n_sets = n_sets; best.fused = fused;
+                    best.smem = (size_t)smem_total;
+                    best.score = score;
+                }
             }
         }
     };
@@ -627,7 +658,7 @@ extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void*
         RF_CUDA_OK(cudaFuncSetAttribute(tc_conv3d_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
-    a.n_items = g.n_items; a.n_sets = g.n_sets;
+    a.n_items = g.n_items; a.n_sets = g.n_sets; a.fused = g.fused;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -643,7 +674,7 @@ extern "C" int rf_tc_conv3d_halo_geometry(int N, int D, int H, int W, int Cout, 
     if (!halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad)) return 0;
     Geo g;
     if (!choose_geometry(N, D + 2 * pad - 2, H + 2 * pad - 2, W + 2 * pad - 2, CCe, pair, Npad, g)) return 0;
-    out8[0] = g.stacked; out8[1] = g.G; out8[2] = g.Dt; out8[3] = g.Ht; out8[4] = g.lines; out8[5] = g.n_tiles;
+    out8[0] = g.stacked; out8[1] = g.G; out8[2] = g.Dt; out8[3] = g.Ht; out8[4] = g.lines + 2 * g.fused; out8[5] = g.n_tiles;
     out8[6] = g.n_items; out8[7] = (int)g.smem;
     return 1;
 }
