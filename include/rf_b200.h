@@ -154,11 +154,13 @@ int rf_tc_conv3d_fwd(const void* x_hi, const void* x_lo, int C1, const void* x2_
  * TMEM for this layer; callers use rf_tc_conv3d_fwd otherwise.  D, H, W are the
  * INPUT extents; pad = 1 ('same', the U-Nets; zero halo written by the split kernel)
  * or 0 ('valid', the conv patch encoders of model/retrieval.py: no halo, output
- * extents D-2).  y is fp32 channels-last [N,Do,Ho,Wo,Cout] or NCDHW. */
+ * extents D-2).  interior_only = 1: hi / lo are caller-owned buffers that were zeroed once and whose halo
+ * nobody writes; only the interior slots are written (the halo is half of an 8^3 patch's slots).
+ * y is fp32 channels-last [N,Do,Ho,Wo,Cout] or NCDHW. */
 size_t rf_halo_act_bytes(int N, int D, int H, int W, int C1, int C2, int pad);
 int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a,
                           const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, int pad, float scale,
-                          void* stream);
+                          int interior_only, void* stream);
 size_t rf_tc_conv_halo_weight_image_bytes(int Cout, int C1, int C2);
 int rf_tc_conv_halo_weight_image(const float* w, int Cout, int C1, int C2, float scale, void* image, void* stream);
 int rf_tc_conv3d_halo_supported(int N, int D, int H, int W, int Cout, int C1, int C2, int pad);

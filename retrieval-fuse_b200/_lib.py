@@ -57,7 +57,7 @@ PROTOTYPES = {
                                  c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
     "rf_halo_act_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "rf_cl_norm_split_halo": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                      c_int, c_int, c_int, c_int, c_float, c_void_p]),
+                                      c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "rf_tc_conv_halo_weight_image_bytes": (c_size_t, [c_int, c_int, c_int]),
     "rf_tc_conv_halo_weight_image": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "rf_tc_conv3d_halo_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),

@@ -42,22 +42,27 @@ constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in maximum per CTA on sm_100
 struct SplitArgs {
     const float *x, *x2, *mu, *a, *beta;
     uint4 *hi, *lo;
-    int N, D, H, W, C1, C2, CC1, CC, CCe, pad;
+    int N, D, H, W, C1, C2, CC1, CC, CCe, pad, interior_only;
     float scale;
 };
 
 __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs s) {
     const int Dp = s.D + 2 * s.pad, Hp = s.H + 2 * s.pad, Wp = s.W + 2 * s.pad;
     const long V = (long)Dp * Hp * Wp;
-    const long total = (long)s.CCe * s.N * V;
+    // interior_only: the caller owns a zero-initialised buffer whose halo (and padding chunk planes) nobody ever
+    // writes, so only the D x H x W interior of the real chunks is visited (half the slots of an 8^3 patch are halo)
+    const int Dv = s.interior_only ? s.D : Dp, Hv = s.interior_only ? s.H : Hp, Wv = s.interior_only ? s.W : Wp;
+    const int off = s.interior_only ? s.pad : 0;
+    const long total = (long)(s.interior_only ? s.CC : s.CCe) * s.N * Dv * Hv * Wv;
     const int c_tot = s.C1 + s.C2;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        long t = i;
-        const int ww = (int)(t % Wp); t /= Wp;
-        const int hh = (int)(t % Hp); t /= Hp;
-        const int dd = (int)(t % Dp); t /= Dp;
+    for (long j = blockIdx.x * (long)blockDim.x + threadIdx.x; j < total; j += (long)gridDim.x * blockDim.x) {
+        long t = j;
+        const int ww = (int)(t % Wv) + off; t /= Wv;
+        const int hh = (int)(t % Hv) + off; t /= Hv;
+        const int dd = (int)(t % Dv) + off; t /= Dv;
         const int n = (int)(t % s.N);
         const int cc = (int)(t / s.N);
+        const long i = (((long)cc * s.N + n) * Dp + dd) * Hp * Wp + (long)hh * Wp + ww;  // slot index in the haloed planes
         uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
         if (cc < s.CC && ww >= s.pad && ww < s.W + s.pad && hh >= s.pad && hh < s.H + s.pad && dd >= s.pad && dd < s.D + s.pad) {
             const int d = dd - s.pad, hq = hh - s.pad, w = ww - s.pad;
@@ -571,7 +576,7 @@ extern "C" size_t rf_halo_act_bytes(int N, int D, int H, int W, int C1, int C2, 
 
 extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a,
                                      const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, int pad, float scale,
-                                     void* stream) {
+                                     int interior_only, void* stream) {
     int Cp1, Cp2, CC, CCe, pair, Npad;
     RF_CHECK_ARG(halo_shape(16, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad), "rf_cl_norm_split_halo: bad channel counts");
     RF_CHECK_ARG(hi && lo && (C1 == 0 || x) && (C2 == 0 || x2) && N > 0 && D > 0 && H > 0 && W > 0 && (pad == 0 || pad == 1),
@@ -582,8 +587,8 @@ extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, in
                  "rf_cl_norm_split_halo: pointers must be 16-byte aligned");
     SplitArgs s;
     s.x = x; s.x2 = x2; s.mu = gn_mu; s.a = gn_a; s.beta = gn_beta; s.hi = (uint4*)hi; s.lo = (uint4*)lo;
-    s.N = N; s.D = D; s.H = H; s.W = W; s.C1 = C1; s.C2 = C2; s.CC1 = Cp1 / 8; s.CC = CC; s.CCe = CCe; s.pad = pad; s.scale = scale;
-    const long total = (long)CCe * N * (long)(D + 2 * pad) * (H + 2 * pad) * (W + 2 * pad);
+    s.N = N; s.D = D; s.H = H; s.W = W; s.C1 = C1; s.C2 = C2; s.CC1 = Cp1 / 8; s.CC = CC; s.CCe = CCe; s.pad = pad; s.scale = scale; s.interior_only = interior_only ? 1 : 0;
+    const long total = interior_only ? (long)CC * N * (long)D * H * W : (long)CCe * N * (long)(D + 2 * pad) * (H + 2 * pad) * (W + 2 * pad);
     cl_norm_split_halo_kernel<<<rf_grid_1d(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(s);
     RF_LAUNCH_OK("cl_norm_split_halo_kernel");
     return 0;

@@ -85,7 +85,9 @@ class SingleConv(RfModule):
         N, D, H, W = x.shape[:4] if x is not None else (x2.shape[0], 2 * x2.shape[1], 2 * x2.shape[2], 2 * x2.shape[3])
         if USE_HALO_CONV and ops.tc_conv_halo_supported(N, D, H, W, self.out_channels, c1, c2):
             # shifted-window kernel: activations staged in shared memory once, all 27 taps addressed in place
-            split = ops.cl_norm_split_halo(x, x2, (mu, a, g.bias), scale=sa)
+            if not hasattr(self, "_halo_planes"):
+                object.__setattr__(self, "_halo_planes", {})  # zeroed operand planes of this layer, reused across calls
+            split = ops.cl_norm_split_halo(x, x2, (mu, a, g.bias), scale=sa, buffers=self._halo_planes)
             img, sw = self._wcache.derived(("halo", c1, c2), [self.conv.weight],
                                            lambda w: ops.tc_conv_halo_weight_image(w, c1, c2))
             return ops.tc_conv3d_halo(split, img, self.conv.bias, self.out_channels, act=self.act, slope=0.1,

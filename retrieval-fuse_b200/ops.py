@@ -427,7 +427,7 @@ def tc_conv_halo_geometry(N, D, H, W, cout, c1, c2, pad=1):
     return dict(zip(["stacked", "G", "Dt", "Ht", "lines", "n_tiles", "n_items", "smem"], list(out)))
 
 
-def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0, pad=1):
+def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0, pad=1, buffers=None):
     """fp32 channels-last x [N,D,H,W,C1] (or None) and half-resolution x2 [N,D/2,H/2,W/2,C2] (or None) ->
     (hi, lo) fp16 slot planes [chunk][N][D+2p][H+2p][W+2p][8] of scale * GroupNorm(concat(x, up2(x2))), zero halo of
     width p = pad."""
@@ -443,12 +443,24 @@ def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0, pad=1):
     nbytes = L.rf_halo_act_bytes(N, D, H, W, c1, c2, int(pad))
     if nbytes == 0:
         raise _lib.RfError(f"halo layout does not support C={c1}+{c2}")
-    hi = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
-    lo = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
+    # buffers: a dict owned by the caller (one per layer).  The planes for this shape are allocated zeroed once and
+    # reused; nobody ever writes their halo, so later calls only write the interior slots.
+    interior_only = 0
+    if buffers is not None:
+        key = (N, D, H, W, c1, c2, int(pad), src.device)
+        if key not in buffers:
+            buffers.clear()  # one shape at a time per layer: a new batch size replaces the old planes
+            buffers[key] = (torch.zeros(nbytes, device=src.device, dtype=torch.uint8),
+                            torch.zeros(nbytes, device=src.device, dtype=torch.uint8))
+        hi, lo = buffers[key]
+        interior_only = 1
+    else:
+        hi = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
+        lo = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
     mu, a, beta = gn if gn is not None else (None, None, None)
     with torch.cuda.device(src.device):
         check(L.rf_cl_norm_split_halo(_ptr(x), c1, _ptr(x2), c2, _ptr(mu), _ptr(a), _ptr(beta), hi.data_ptr(), lo.data_ptr(),
-                                      N, D, H, W, int(pad), float(scale), _stream(src)), "rf_cl_norm_split_halo")
+                                      N, D, H, W, int(pad), float(scale), interior_only, _stream(src)), "rf_cl_norm_split_halo")
     _count()
     return hi, lo, (N, D, H, W, c1, c2, int(pad))
 
