@@ -74,32 +74,49 @@ __device__ __forceinline__ void convert_slab(const MlpArgs& a, int l, int c0, in
     const int row = tid & 127, half = tid >> 7, q = (tid >> 5) & 3;
     const float* bias = a.bias[l];
     const int N = a.N[l];
-    const int n_groups = (c1 - c0) >> 4;
-    for (int g = half; g < n_groups; g += 2) {
-        float v[16];
-        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 16 * g), v);
-        uint32_t h[8], lw[8];
-        if (bias) {
+    // 64 columns per step: four TMEM loads in flight and the block's biases (float4 loads) issued before the one
+    // wait, so that both latencies overlap (one 16-column load per wait plus 16 scalar bias loads after it made the
+    // conversions the longest stall of this kernel)
+    const int n_blocks = (c1 - c0 + 63) >> 6;
+    for (int b = half; b < n_blocks; b += 2) {
+        const int cb = c0 + 64 * b;
+        float v[64], bv[64];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] += c0 + 16 * g + e < N ? __ldg(bias + c0 + 16 * g + e) : 0.f;
+        for (int j = 0; j < 4; ++j) tc_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb + 16 * j), v + 16 * j);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int c = cb + 4 * j;
+            if (bias && c + 4 <= N) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
+                bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) bv[4 * j + t] = (bias && c + t < N) ? __ldg(bias + c + t) : 0.f;
+            }
         }
+        tc_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 64; ++e) v[e] += bv[e];
         rf_act_vec(v, a.act, a.slope);
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-            if (c0 + 16 * g + e >= N) v[e] = 0.f;  // padded output channels feed zero weights, keep them finite and zero
+        for (int e = 0; e < 64; ++e)
+            if (cb + e >= N) v[e] = 0.f;  // padded output channels feed zero weights, keep them finite and zero
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-            uint32_t h0, l0, h1, l1;
-            split_f16(v[e], h0, l0);
-            split_f16(v[e + 1], h1, l1);
-            h[e >> 1] = h0 | (h1 << 16);
-            lw[e >> 1] = l0 | (l1 << 16);
+        for (int c = 0; c < 8; ++c) {  // eight 8-channel chunks
+            if (cb + 8 * c >= c1) break;
+            uint32_t h[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                uint32_t h0, l0, h1, l1;
+                split_f16(v[8 * c + e], h0, l0);
+                split_f16(v[8 * c + e + 1], h1, l1);
+                h[e >> 1] = h0 | (h1 << 16);
+                lw[e >> 1] = l0 | (l1 << 16);
+            }
+            uint8_t* p = act_hi + (size_t)(((cb - c0) >> 3) + c) * PLANE + row * 16;
+            *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(p + ACT_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
-        uint8_t* p = act_hi + (size_t)(2 * g) * PLANE + row * 16;
-        *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(p + PLANE) = make_uint4(h[4], h[5], h[6], h[7]);
-        *reinterpret_cast<uint4*>(p + ACT_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        *reinterpret_cast<uint4*>(p + ACT_BYTES + PLANE) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
