@@ -112,6 +112,7 @@ int rf_tc_linear_fwd(const float* x, int ldx, const void* weight_image, const fl
 int rf_tc_mlp_supported(const int* widths_host, int n_layers);
 size_t rf_tc_mlp_weight_image_bytes(int N, int K);
 int rf_tc_mlp_weight_image(const float* w, int N, int K, void* image, void* stream);
+int rf_tc_mlp_debug_read(long long* out64); /* tuning aid: phase timestamps of CTA 0's second tile */
 int rf_tc_mlp_fwd(const float* x, int ldx, const void* const* images_host, const float* const* bias_host,
                   const int* widths_host, int n_layers, int act, float slope, int l2_normalize, float eps, float* y, int ldy,
                   long M, void* stream);

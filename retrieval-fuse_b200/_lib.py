@@ -42,6 +42,7 @@ PROTOTYPES = {
     "rf_tc_mlp_supported": (c_int, [c_int * 9, c_int]),
     "rf_tc_mlp_weight_image_bytes": (c_size_t, [c_int, c_int]),
     "rf_tc_mlp_weight_image": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "rf_tc_mlp_debug_read": (c_int, [c_void_p]),
     "rf_tc_mlp_fwd": (c_int, [c_void_p, c_int, _ptr4, _ptr4, c_int * 9, c_int, c_int, c_float, c_int, c_float, c_void_p, c_int,
                               c_long, c_void_p]),
     "rf_cl_gn_stats_workspace_bytes": (c_size_t, [c_int, c_int]),

@@ -139,4 +139,16 @@ __device__ __forceinline__ void split_f16(float x, uint32_t& hi, uint32_t& lo) {
     lo = __half_as_ushort(l);
 }
 
+// Two values at once with the packed converts (F2FP.PACK_AB / HADD2.F32): ~5 instructions per value instead of ~8.
+// Same result as split_f16 on each element.
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    x0 = fminf(fmaxf(x0, -65504.f), 65504.f);
+    x1 = fminf(fmaxf(x1, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 }  // namespace rf_tc

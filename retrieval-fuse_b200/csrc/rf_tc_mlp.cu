@@ -55,6 +55,9 @@ __global__ void __launch_bounds__(256) mlp_weight_image_kernel(const float* __re
     *reinterpret_cast<uint4*>(base + 32L * Np) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// phase timestamps of CTA 0's second tile (tuning aid, rf_tc_mlp_debug_read)
+__device__ long long g_mlp_dbg[64];
+
 struct MlpArgs {
     const float* x;
     float* y;
@@ -106,13 +109,7 @@ __device__ __forceinline__ void convert_slab(const MlpArgs& a, int l, int c0, in
             if (cb + 8 * c >= c1) break;
             uint32_t h[4], lw[4];
 #pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-                uint32_t h0, l0, h1, l1;
-                split_f16(v[8 * c + e], h0, l0);
-                split_f16(v[8 * c + e + 1], h1, l1);
-                h[e >> 1] = h0 | (h1 << 16);
-                lw[e >> 1] = l0 | (l1 << 16);
-            }
+            for (int e = 0; e < 8; e += 2) split_f16x2(v[8 * c + e], v[8 * c + e + 1], h[e >> 1], lw[e >> 1]);
             uint8_t* p = act_hi + (size_t)(((cb - c0) >> 3) + c) * PLANE + row * 16;
             *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(p + ACT_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -173,13 +170,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         uint8_t* act_hi = smem_al;  // sACT == base
         uint32_t kt = 0, mma_phase = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        int tile_no = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tile_no) {
+            const bool dbg = blockIdx.x == 0 && tid == 0 && tile_no == 1;
+            if (dbg) g_mlp_dbg[0] = clock64();
             // ---- phase A: x rows -> operand planes.  item = (row, 8-channel chunk); a quarter warp covers 8
             // consecutive rows of one chunk (128 contiguous bytes of a plane: conflict-free 16-byte stores)
             {
                 const int nch = a.K0p >> 3;
                 const bool vec = (a.ldx & 3) == 0;
-                for (int i = tid; i < TM * nch; i += WORKERS) {
+#pragma unroll 4
+                for (int i = tid; i < TM * nch; i += WORKERS) {  // (unrolled: the rows' loads are issued together)
                     const int r_lo = i & 7, c = (i >> 3) % nch, r_hi = i / (8 * nch);
                     const int row = r_hi * 8 + r_lo;
                     const long grow = (long)tile * TM + row;
@@ -200,13 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
                     }
                     uint32_t h[4], lw[4];
 #pragma unroll
-                    for (int e = 0; e < 8; e += 2) {
-                        uint32_t h0, l0, h1, l1;
-                        split_f16(f[e], h0, l0);
-                        split_f16(f[e + 1], h1, l1);
-                        h[e >> 1] = h0 | (h1 << 16);
-                        lw[e >> 1] = l0 | (l1 << 16);
-                    }
+                    for (int e = 0; e < 8; e += 2) split_f16x2(f[e], f[e + 1], h[e >> 1], lw[e >> 1]);
                     uint8_t* p = act_hi + (size_t)c * PLANE + row * 16;
                     *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
                     *reinterpret_cast<uint4*>(p + ACT_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -217,7 +212,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
             workers_sync();
             tc_fence_after();
 
+            if (dbg) g_mlp_dbg[1] = clock64();
             for (int l = 0; l < a.n_layers; ++l) {
+                if (dbg) g_mlp_dbg[2 + 3 * l] = clock64();
                 const int Kp = l == 0 ? a.K0p : a.Np[l - 1];
                 const int nks = Kp >> 4, Np = a.Np[l];
                 for (int ks0 = 0; ks0 < nks; ks0 += ACT_CHUNKS / 2) {  // slabs of 16 k steps = 256 input channels
@@ -265,6 +262,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
                     ++mma_phase;
                     tc_fence_after();
                 }
+                if (dbg) g_mlp_dbg[3 + 3 * l] = clock64();
                 // ---- layer epilogue
                 if (l + 1 < a.n_layers) {
                     convert_slab(a, l, 0, min(Np, 16 * 16), tmem_base, act_hi, tid);
@@ -278,6 +276,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
                     const float* bias = a.bias[l];
                     const int n_groups = Np >> 4;
                     float scale = 1.f;
+                    if (Np <= 64) {
+                        // narrow output (the 64-d embedding, the 32-d attention features): each half of the workers keeps
+                        // its 32 columns in registers - one round of TMEM loads with the biases prefetched, the row norm
+                        // through shared memory, one store pass
+                        const int cb = 32 * half;
+                        float v[32], bv[32];
+                        const bool mine = cb < Np;
+                        if (mine) {
+                            tc_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+                            tc_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb + 16), v + 16);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) bv[e] = (bias && cb + e < N) ? __ldg(bias + cb + e) : 0.f;
+                        tc_ld_wait();
+                        float ss = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            v[e] = (mine && cb + e < N) ? v[e] + bv[e] : 0.f;
+                            ss = fmaf(v[e], v[e], ss);
+                        }
+                        if (a.l2norm) {  // util/retrieval.py:66 F.normalize: x / max(|x|, eps)
+                            ssq[tid] = ss;
+                            workers_sync();
+                            scale = 1.f / fmaxf(sqrtf(ssq[row] + ssq[row + 128]), a.eps);
+                        }
+                        if (mine && grow < a.M) {
+                            float* dst = a.y + grow * a.ldy + cb;
+#pragma unroll
+                            for (int e = 0; e < 32; e += 4) {
+                                if (cb + e + 4 <= N && (a.ldy & 3) == 0) {
+                                    *reinterpret_cast<float4*>(dst + e) = make_float4(v[e] * scale, v[e + 1] * scale, v[e + 2] * scale, v[e + 3] * scale);
+                                } else {
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t)
+                                        if (cb + e + t < N) dst[e + t] = v[e + t] * scale;
+                                }
+                            }
+                        }
+                    } else {
                     if (a.l2norm) {  // util/retrieval.py:66 F.normalize: x / max(|x|, eps)
                         float ss = 0.f;
                         for (int g = half; g < n_groups; g += 2) {
@@ -317,10 +354,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
                             }
                         }
                     }
+                    }
                     tc_fence_before();
                     workers_sync();  // TMEM and the operand planes are free for the next tile
                     tc_fence_after();
                 }
+                if (dbg) g_mlp_dbg[4 + 3 * l] = clock64();
             }
         }
     }
@@ -405,5 +444,13 @@ extern "C" int rf_tc_mlp_fwd(const float* x, int ldx, const void* const* images_
     const int grid = a.n_tiles < sms ? a.n_tiles : sms;
     tc_mlp_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
     RF_LAUNCH_OK("tc_mlp_kernel");
+    return 0;
+}
+
+/* Tuning aid: clock64 timestamps of CTA 0's second row tile in the last rf_tc_mlp_fwd launch:
+ * [0] tile start, [1] input planes ready, then per layer l: [2+3l] layer start, [3+3l] MMAs complete, [4+3l] epilogue done. */
+extern "C" int rf_tc_mlp_debug_read(long long* out64) {
+    RF_CUDA_OK(cudaDeviceSynchronize());
+    RF_CUDA_OK(cudaMemcpyFromSymbol(out64, g_mlp_dbg, sizeof(long long) * 64));
     return 0;
 }
