@@ -188,6 +188,25 @@ class RetrievalPipeline:
         return out
 
 
+    def retrieve_host_async(self, chunks_host, chunk_scene_host=None, method=0, slot=0):
+        """retrieve_host without the final wait, for a two-deep pipeline over batches: the host->device copy, the
+        lookup and the device->host copy of batch i are enqueued on stream `slot` (0 / 1, alternate them) so that
+        the copies of one batch overlap the kernels of the next.  Returns (rows in pinned host memory, event); the
+        rows are valid after event.synchronize(), and slot s may be reused once its previous event was waited for."""
+        if not hasattr(self, "_pipe_streams"):
+            self._pipe_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        st = self._pipe_streams[slot & 1]
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(st):
+            x = chunks_host.to(self.device, non_blocking=True)
+            rows, _ = self.retrieve(x, chunk_scene_host, method)
+            out = self._pin(("rows", slot & 1), rows.shape, rows.dtype)
+            out.copy_(rows, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        return out, ev
+
+
 class RefinementPipeline(RetrievalPipeline):
     """+ U-Net backbone, retrieval U-Net, patch attention, decoder
     (trainer/train_refinement.py:108-120, inference part)."""

@@ -517,6 +517,29 @@ def test_hot_path_end_to_end_small(dev):
     G.smoke()
 
 
+def test_host_pipeline_matches_synchronous_call(dev):
+    """retrieve_host_async (two batches in flight on alternating streams) returns exactly what retrieve_host does."""
+    from retrieval_fuse_b200.pipeline import FRONT3D_SR, RetrievalPipeline, build_bank_from_targets, synthetic_tsdf_batch
+    d = FRONT3D_SR["dataset"]
+    targets = synthetic_tsdf_batch(6, 64, d["voxel_size_target"], seed=31, device=dev)
+    bank, _ = build_bank_from_targets(FRONT3D_SR, targets, dev, weight_seed=3)
+    pipe = RetrievalPipeline(FRONT3D_SR, bank, targets, device=dev, weight_seed=5)
+    batches = [synthetic_tsdf_batch(40, 8, d["voxel_size_input"], seed=50 + i, device=dev).unsqueeze(1).cpu().pin_memory() for i in range(5)]
+    want = [pipe.retrieve_host(b).clone() for b in batches]
+    got, pending = [], []
+    for i, b in enumerate(batches):
+        pending.append(pipe.retrieve_host_async(b, slot=i))
+        if len(pending) > 1:
+            out, ev = pending.pop(0)
+            ev.synchronize()
+            got.append(out.clone())
+    out, ev = pending.pop(0)
+    ev.synchronize()
+    got.append(out.clone())
+    for w, g in zip(want, got):
+        assert torch.equal(w, g)
+
+
 def test_surface_reconstruction_config_end_to_end(dev):
     """BASELINE config 4 shapes: 128^3 occupancy grid of a point cloud -> PCPatch48 queries -> kNN against a
     Patch24 bank -> compose -> 5-level U-Net (nf 12) + retrieval U-Net + attention (K = 8) + decoder, vs the oracle."""
