@@ -5,6 +5,30 @@
 // (rf_grid_1d) and walk the output with a grid-stride loop.
 #include "rf_common.cuh"
 
+// Exact division of a 32-bit index by a run-time divisor with one 64-bit high multiply: m = ceil(2^64 / d) gives
+// floor(n / d) for every n < 2^32 (error term n * (m * d - 2^64) / (d * 2^64) < 1 / d).  The re-indexing kernels
+// decompose one linear index per 16-byte access, so the ~20-instruction hardware-less integer division matters.
+struct FastDiv {
+    unsigned long long m;
+    unsigned d;
+};
+static inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = (unsigned)d;
+    f.m = d <= 1 ? 0ull : (~0ull) / (unsigned long long)d + 1ull;
+    return f;
+}
+__device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
+    return f.d == 1u ? n : (unsigned)__umul64hi((unsigned long long)n, f.m);
+}
+// n -> n / d, returns n % d
+__device__ __forceinline__ unsigned fd_divmod(unsigned& n, const FastDiv& f) {
+    const unsigned q = fd_div(n, f);
+    const unsigned r = n - q * f.d;
+    n = q;
+    return r;
+}
+
 // ---------------------------------------------------------------------------
 // Unfold3D / Fold3D (model/attention.py:160-188).  One index space for both:
 // element (b, px,py,pz, c, ex,ey,ez) of the patch tensor <-> element
@@ -32,27 +56,39 @@ __global__ void __launch_bounds__(256) fold_unfold_kernel(const float* __restric
     }
 }
 
-// Vectorised variant for E in {4, 8, 16}: one thread moves one z-run of E floats (E/4 float4s).  The patch side is
-// fully contiguous across threads, the volume side is written / read in whole 32-byte sectors; index arithmetic is
-// 32-bit with compile-time E and happens once per run instead of once per element.
+// Vectorised variant for E in {4, 8, 16}: one thread moves one float4, consecutive threads walk the PATCH side
+// linearly (every warp access there is one contiguous 512-byte segment) and touch the volume side in z-runs of
+// E floats (whole 32-byte sectors); two independent float4s are in flight per thread.  The earlier one-thread-per-
+// z-run mapping wrote 16 bytes into each of 32 different sectors per store instruction.
 template <int E, bool kFold>
-__global__ void __launch_bounds__(256) fold_unfold_vec_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int R,
-                                                              int total_runs) {
-    const int S = R * E;
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total_runs; r += gridDim.x * blockDim.x) {
-        int t = r;
-        const int ey = t % E; t /= E;
-        const int ex = t % E; t /= E;
-        const int c = t % C; t /= C;
-        const int pz = t % R; t /= R;
-        const int py = t % R; t /= R;
-        const int px = t % R;
-        const int b = t / R;
-        const long v = ((((long)b * C + c) * S + (px * E + ex)) * S + (py * E + ey)) * S + pz * E;
-        const float4* src = reinterpret_cast<const float4*>(kFold ? in + (long)r * E : in + v);
-        float4* dst = reinterpret_cast<float4*>(kFold ? out + v : out + (long)r * E);
-#pragma unroll
-        for (int j = 0; j < E / 4; ++j) dst[j] = __ldg(src + j);
+__global__ void __launch_bounds__(256) fold_unfold_vec_kernel(const float4* __restrict__ in, float4* __restrict__ out, FastDiv C,
+                                                              FastDiv R, unsigned total4) {
+    constexpr unsigned E4 = E / 4;
+    const unsigned S = R.d * E;
+    const unsigned step = gridDim.x * blockDim.x;
+    auto vol_index = [&](unsigned i4) -> long {
+        const unsigned j = i4 % E4;
+        unsigned t = i4 / E4;
+        const unsigned ey = t % E; t /= E;
+        const unsigned ex = t % E; t /= E;
+        const unsigned c = fd_divmod(t, C);
+        const unsigned pz = fd_divmod(t, R);
+        const unsigned py = fd_divmod(t, R);
+        const unsigned px = fd_divmod(t, R);
+        const unsigned b = t;
+        return (((((long)b * C.d + c) * S + (px * E + ex)) * S + (py * E + ey)) * S + pz * E) / 4 + j;
+    };
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + step < total4; i += 2 * step) {
+        const long v0 = vol_index(i), v1 = vol_index(i + step);
+        const float4 a = __ldg(in + (kFold ? (long)i : v0));
+        const float4 b = __ldg(in + (kFold ? (long)(i + step) : v1));
+        out[kFold ? v0 : (long)i] = a;
+        out[kFold ? v1 : (long)(i + step)] = b;
+    }
+    if (i < total4) {
+        const long v0 = vol_index(i);
+        out[kFold ? v0 : (long)i] = __ldg(in + (kFold ? (long)i : v0));
     }
 }
 
@@ -88,18 +124,84 @@ __global__ void __launch_bounds__(256) fold_unfold_e2_kernel(const float* __rest
     }
 }
 
+// E = 2 through shared memory: one CTA per (b, px, py) line of R sub-patches.  Its patch side is ONE contiguous
+// run of R * C * 8 floats, its volume side C * 4 z-rows of 2R floats, so both global sides move as float4 in
+// 128-byte (or longer) contiguous pieces and the (c, ex, ey, ez) <-> (pz, c, ...) transposition happens in shared
+// memory.  (The register-only kernel above reads the volume as 8-byte pieces 128 KB apart across the lanes of a warp:
+// 20 % of the HBM rate on the attention's Unfold3D(2, nf).)  Patch-order staging with 4 floats of padding per pz
+// block: the float2 accesses of the volume side then spread over all banks.
+template <bool kFold>
+__global__ void __launch_bounds__(256) fold_unfold_e2_smem_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
+                                                                  int R) {
+    extern __shared__ float4 e2_smem4[];
+    float* sm = reinterpret_cast<float*>(e2_smem4);
+    const int S = 2 * R, S4 = S / 4, blk = C * 8 + 4;
+    const int line = blockIdx.x;                       // (b * R + px) * R + py
+    const int py = line % R, px = (line / R) % R, b = line / (R * R);
+    const int n_items = 2 * C * R;                     // float4s on either side
+    const float* pin = in;
+    float* pout = out;
+    const long patch_base = (long)line * R * C * 8;    // floats
+    const long vol_base = (((long)b * C * S + 2 * px) * S + 2 * py) * S;
+    auto vol_addr = [&](int i, int& c, int& ex, int& ey, int& z4) -> long {
+        z4 = i % S4;
+        const int row = i / S4;
+        ey = row & 1; ex = (row >> 1) & 1; c = row >> 2;
+        return vol_base + (((long)c * S + ex) * S + ey) * S + 4 * z4;
+    };
+    if (!kFold) {
+        for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+            int c, ex, ey, z4;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(pin + vol_addr(i, c, ex, ey, z4)));
+            float* d0 = sm + (2 * z4) * blk + c * 8 + ex * 4 + ey * 2;
+            *reinterpret_cast<float2*>(d0) = make_float2(v.x, v.y);
+            *reinterpret_cast<float2*>(d0 + blk) = make_float2(v.z, v.w);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+            const int j = i % (2 * C), pz = i / (2 * C);
+            *reinterpret_cast<float4*>(pout + patch_base + 4L * i) = *reinterpret_cast<const float4*>(sm + pz * blk + 4 * j);
+        }
+    } else {
+        for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+            const int j = i % (2 * C), pz = i / (2 * C);
+            *reinterpret_cast<float4*>(sm + pz * blk + 4 * j) = __ldg(reinterpret_cast<const float4*>(pin + patch_base + 4L * i));
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+            int c, ex, ey, z4;
+            const long va = vol_addr(i, c, ex, ey, z4);
+            const float* s0 = sm + (2 * z4) * blk + c * 8 + ex * 4 + ey * 2;
+            const float2 a = *reinterpret_cast<const float2*>(s0);
+            const float2 bq = *reinterpret_cast<const float2*>(s0 + blk);
+            *reinterpret_cast<float4*>(pout + va) = make_float4(a.x, a.y, bq.x, bq.y);
+        }
+    }
+}
+
 template <bool kFold>
 static int launch_fold_unfold(const float* in, float* out, int B, int C, int R, int E, cudaStream_t s) {
     const long total = (long)B * C * R * R * R * E * E * E;
     const bool aligned = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
     if (aligned && total < (1L << 31) && (E == 2 || E == 4 || E == 8 || E == 16)) {
-        const int units = (int)(E == 2 ? total / 8 : total / E);
-        const int grid = rf_grid_1d(units, 256, 148 * 64);
-        switch (E) {
-            case 2: fold_unfold_e2_kernel<kFold><<<grid, 256, 0, s>>>(in, out, C, R, units); break;
-            case 4: fold_unfold_vec_kernel<4, kFold><<<grid, 256, 0, s>>>(in, out, C, R, units); break;
-            case 8: fold_unfold_vec_kernel<8, kFold><<<grid, 256, 0, s>>>(in, out, C, R, units); break;
-            default: fold_unfold_vec_kernel<16, kFold><<<grid, 256, 0, s>>>(in, out, C, R, units); break;
+        const int units = (int)(E == 2 ? total / 8 : total / 4);
+        if (E == 2) {
+            const size_t smem = (size_t)R * (C * 8 + 4) * sizeof(float);
+            if ((R & 1) == 0 && smem <= 48 * 1024 && (long)B * R * R < (1L << 31))
+                fold_unfold_e2_smem_kernel<kFold><<<(unsigned)(B * R * R), 256, smem, s>>>(in, out, C, R);
+            else
+                fold_unfold_e2_kernel<kFold><<<rf_grid_1d(units, 256, 148 * 64), 256, 0, s>>>(in, out, C, R, units);
+        } else {
+            // two float4s per thread and loop trip; 148 x 8 resident CTAs x 2 waves at most
+            const int grid = rf_grid_1d((units + 1) / 2, 256, 148 * 16);
+            const float4* in4 = reinterpret_cast<const float4*>(in);
+            float4* out4 = reinterpret_cast<float4*>(out);
+            const FastDiv fc = make_fastdiv(C), fr = make_fastdiv(R);
+            switch (E) {
+                case 4: fold_unfold_vec_kernel<4, kFold><<<grid, 256, 0, s>>>(in4, out4, fc, fr, (unsigned)units); break;
+                case 8: fold_unfold_vec_kernel<8, kFold><<<grid, 256, 0, s>>>(in4, out4, fc, fr, (unsigned)units); break;
+                default: fold_unfold_vec_kernel<16, kFold><<<grid, 256, 0, s>>>(in4, out4, fc, fr, (unsigned)units); break;
+            }
         }
     } else {
         fold_unfold_kernel<kFold><<<rf_grid_1d(total, 256), 256, 0, s>>>(in, out, B, C, R, E);
@@ -153,39 +255,58 @@ __global__ void __launch_bounds__(256) pad_unfold_kernel(const float* __restrict
     }
 }
 
-// Same, one thread per z-run of the patch (kernel z extent a multiple of 4, 16-byte aligned output): the index
-// decomposition happens once per run, stores are float4, and 32-bit arithmetic suffices.
-__global__ void __launch_bounds__(256) pad_unfold_rows_kernel(const float* __restrict__ x, float* __restrict__ out, int C,
-                                                              Int3 size, Int3 kernel, Int3 pad, Int3 stride, Int3 cnt,
-                                                              float pad_val, float norm_sub, float norm_div, int total_runs) {
-    const int KZ = kernel.v[2];
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total_runs; r += gridDim.x * blockDim.x) {
-        int t = r;
-        const int ky = t % kernel.v[1]; t /= kernel.v[1];
-        const int kx = t % kernel.v[0]; t /= kernel.v[0];
-        const int c = t % C; t /= C;
-        const int iz = t % cnt.v[2]; t /= cnt.v[2];
-        const int iy = t % cnt.v[1]; t /= cnt.v[1];
-        const int ix = t % cnt.v[0];
-        const int b = t / cnt.v[0];
+// Same, one thread per float4 of the OUTPUT (kernel z extent a multiple of 4, 16-byte aligned output): consecutive
+// threads write consecutive 16-byte pieces, so every warp store is one contiguous 512-byte segment (the earlier
+// one-thread-per-z-run mapping scattered each store instruction over 32 sectors and ran at 16-36 % of the HBM rate).
+// The source float4 is loaded in one piece when it lies inside the volume and is 16-byte aligned, else element by
+// element with the pad value; the overlapping reads (8x for the 32^3 / stride-16 target patches) are L2 hits.
+struct PadUnfoldDivs { FastDiv kz4, ky, kx, c, cz, cy, cx; };
+
+__global__ void __launch_bounds__(256) pad_unfold_vec4_kernel(const float* __restrict__ x, float4* __restrict__ out, Int3 size,
+                                                              Int3 pad, Int3 stride, PadUnfoldDivs dv, float pad_val,
+                                                              float norm_sub, float norm_div, unsigned total4, int x_aligned) {
+    const unsigned step = gridDim.x * blockDim.x;
+    const bool norm = norm_div != 0.f;
+    const float pad_out = norm ? __fdiv_rn(__fsub_rn(pad_val, norm_sub), norm_div) : pad_val;
+    const bool vec_ok = x_aligned && (size.v[2] & 3) == 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += step) {
+        unsigned t = i;
+        const int kz = 4 * (int)fd_divmod(t, dv.kz4);
+        const int ky = (int)fd_divmod(t, dv.ky);
+        const int kx = (int)fd_divmod(t, dv.kx);
+        const int c = (int)fd_divmod(t, dv.c);
+        const int iz = (int)fd_divmod(t, dv.cz);
+        const int iy = (int)fd_divmod(t, dv.cy);
+        const int ix = (int)fd_divmod(t, dv.cx);
+        const int b = (int)t;
         const int sx = ix * stride.v[0] + kx - pad.v[0];
         const int sy = iy * stride.v[1] + ky - pad.v[1];
-        const int sz0 = iz * stride.v[2] - pad.v[2];
-        const bool row_in = sx >= 0 && sx < size.v[0] && sy >= 0 && sy < size.v[1];
-        const float* src = x + ((((long)b * C + c) * size.v[0] + sx) * size.v[1] + sy) * size.v[2];
-        float4* dst = reinterpret_cast<float4*>(out + (long)r * KZ);
-        for (int k0 = 0; k0 < KZ; k0 += 4) {
+        const int sz = iz * stride.v[2] + kz - pad.v[2];
+        float4 v = make_float4(pad_out, pad_out, pad_out, pad_out);
+        if (sx >= 0 && sx < size.v[0] && sy >= 0 && sy < size.v[1] && sz > -4 && sz < size.v[2]) {
+            const float* src = x + ((((long)b * dv.c.d + c) * size.v[0] + sx) * size.v[1] + sy) * size.v[2];
             float f[4];
+            if (vec_ok && sz >= 0 && sz + 4 <= size.v[2] && (sz & 3) == 0) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(src + sz));
+                f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
+                if (norm) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int sz = sz0 + k0 + e;
-                float v = pad_val;
-                if (row_in && sz >= 0 && sz < size.v[2]) v = __ldg(src + sz);
-                if (norm_div != 0.f) v = __fdiv_rn(__fsub_rn(v, norm_sub), norm_div);
-                f[e] = v;
+                    for (int e = 0; e < 4; ++e) f[e] = __fdiv_rn(__fsub_rn(f[e], norm_sub), norm_div);  // two rounded fp32 ops, as numpy does
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int z = sz + e;
+                    f[e] = pad_out;
+                    if (z >= 0 && z < size.v[2]) {
+                        f[e] = __ldg(src + z);
+                        if (norm) f[e] = __fdiv_rn(__fsub_rn(f[e], norm_sub), norm_div);
+                    }
+                }
             }
-            dst[k0 >> 2] = make_float4(f[0], f[1], f[2], f[3]);
+            v = make_float4(f[0], f[1], f[2], f[3]);
         }
+        out[i] = v;
     }
 }
 
@@ -203,10 +324,13 @@ extern "C" int rf_unfold3d_pad_stride(const float* x, float* out, int B, int C, 
         total *= (long)cnt.v[a] * kernel[a];
     }
     RF_CHECK_ARG(B > 0 && C > 0, "rf_unfold3d_pad_stride: bad B/C");
-    if (kernel[2] % 4 == 0 && ((uintptr_t)out & 15) == 0 && total / kernel[2] < (1L << 31)) {
-        const int runs = (int)(total / kernel[2]);
-        pad_unfold_rows_kernel<<<rf_grid_1d(runs, 256, 148 * 64), 256, 0, (cudaStream_t)stream>>>(x, out, C, s, k, p, st, cnt, pad_val,
-                                                                                                 norm_sub, norm_div, runs);
+    if (kernel[2] % 4 == 0 && ((uintptr_t)out & 15) == 0 && total / 4 < (1L << 31)) {
+        const unsigned total4 = (unsigned)(total / 4);
+        PadUnfoldDivs dv;
+        dv.kz4 = make_fastdiv(kernel[2] / 4); dv.ky = make_fastdiv(kernel[1]); dv.kx = make_fastdiv(kernel[0]);
+        dv.c = make_fastdiv(C); dv.cz = make_fastdiv(cnt.v[2]); dv.cy = make_fastdiv(cnt.v[1]); dv.cx = make_fastdiv(cnt.v[0]);
+        pad_unfold_vec4_kernel<<<rf_grid_1d(total4, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+            x, reinterpret_cast<float4*>(out), s, p, st, dv, pad_val, norm_sub, norm_div, total4, ((uintptr_t)x & 15) == 0);
     } else {
         pad_unfold_kernel<<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, C, s, k, p, st, cnt, pad_val,
                                                                                    norm_sub, norm_div);
@@ -299,16 +423,34 @@ __global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ 
                         Z0 + ez <= Z1 && X1 <= ssz.v[0] && Y1 <= ssz.v[1] && Z1 <= ssz.v[2];
     if (inside && (ez & 3) == 0 && (Z0 & 3) == 0 && (de[4] & 3) == 0 && (ssz.v[2] & 3) == 0 && (csz.v[2] & 3) == 0 &&
         (((uintptr_t)store | (uintptr_t)out) & 15) == 0) {
-        const int ez4 = ez >> 2;
-        for (int i = threadIdx.x; i < ex * ey * ez4; i += blockDim.x) {
-            const int z = (i % ez4) << 2, y = (i / ez4) % ey, x = i / (ez4 * ey);
-            float4 v = __ldg(reinterpret_cast<const float4*>(s + ((long)(X0 + x) * ssz.v[1] + (Y0 + y)) * ssz.v[2] + Z0 + z));
-            v.x = __fmul_rn(v.x, ratio); v.y = __fmul_rn(v.y, ratio); v.z = __fmul_rn(v.z, ratio); v.w = __fmul_rn(v.w, ratio);
-            if (norm_div != 0.f) {
-                v.x = __fdiv_rn(__fsub_rn(v.x, norm_sub), norm_div); v.y = __fdiv_rn(__fsub_rn(v.y, norm_sub), norm_div);
-                v.z = __fdiv_rn(__fsub_rn(v.z, norm_sub), norm_div); v.w = __fdiv_rn(__fsub_rn(v.w, norm_sub), norm_div);
+        const int ez4 = ez >> 2, n4 = ex * ey * ez4;
+        // four independent 16-byte loads in flight per thread before the first store (a 16^3 block is 1024 float4s =
+        // one trip of this loop): the copy is a dependent chain row -> scene -> data, so latency, not bandwidth, is
+        // what a CTA sees
+        for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {
+            float4 v[4];
+            long dsti[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < n4) {
+                    const int z = (i % ez4) << 2, y = (i / ez4) % ey, x = i / (ez4 * ey);
+                    v[u] = __ldg(reinterpret_cast<const float4*>(s + ((long)(X0 + x) * ssz.v[1] + (Y0 + y)) * ssz.v[2] + Z0 + z));
+                    dsti[u] = ((long)(de[0] + x) * csz.v[1] + (de[2] + y)) * csz.v[2] + (de[4] + z);
+                }
             }
-            *reinterpret_cast<float4*>(o + ((long)(de[0] + x) * csz.v[1] + (de[2] + y)) * csz.v[2] + (de[4] + z)) = v;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + u * blockDim.x < n4) {
+                    float4 w = v[u];
+                    w.x = __fmul_rn(w.x, ratio); w.y = __fmul_rn(w.y, ratio); w.z = __fmul_rn(w.z, ratio); w.w = __fmul_rn(w.w, ratio);
+                    if (norm_div != 0.f) {
+                        w.x = __fdiv_rn(__fsub_rn(w.x, norm_sub), norm_div); w.y = __fdiv_rn(__fsub_rn(w.y, norm_sub), norm_div);
+                        w.z = __fdiv_rn(__fsub_rn(w.z, norm_sub), norm_div); w.w = __fdiv_rn(__fsub_rn(w.w, norm_sub), norm_div);
+                    }
+                    *reinterpret_cast<float4*>(o + dsti[u]) = w;
+                }
+            }
         }
         return;
     }

@@ -443,6 +443,103 @@ def test_knn_tensor_core_proof_and_fallback(dev):
         assert np.array_equal(np.sort(want_i[0]), np.sort(dup)[:8])  # ties resolved by the lowest row ids
 
 
+def test_knn_full_size_properties(dev):
+    """BASELINE config 2 at its full size (10 000 chunks x 64 queries against 131 073 rows, fetch 8): the oracle
+    cannot rank 640 000 queries in seconds, so the whole result is checked through size-independent properties and
+    a random sample of queries bit-exactly against the oracle:
+      * ids valid and distinct per query, distances ascending under the canonical (d, id) order;
+      * every returned distance equals an fp64 re-evaluation of (q - x)^2 on the returned row;
+      * completeness: an independent fp32 GEMM (cuBLAS through torch, a checker only) finds no row that is closer
+        than the k-th returned one by more than its own rounding margin and is missing from the list;
+      * the bank cut into two ragged row shards + rf_knn_merge gives the identical lists (checksum of checksums);
+      * the result does not depend on the order / batching of the queries."""
+    from retrieval_fuse_b200 import ops
+    N, Q, k = 131073, 640000, 8
+    g = torch.Generator(device="cpu").manual_seed(20261017)
+    centre = torch.nn.functional.normalize(torch.randn(8, 64, generator=g), dim=1)       # 8 clusters in narrow cones
+    bank = centre[torch.randint(0, 8, (N,), generator=g)] + 0.08 * torch.randn(N, 64, generator=g)
+    q = centre[torch.randint(0, 8, (Q,), generator=g)] + 0.08 * torch.randn(Q, 64, generator=g)
+    bank[N // 2] = bank[3]
+    bank[N - 1] = bank[3]            # duplicated rows: ties resolved by row id
+    q[0] = bank[3]
+    bank = torch.nn.functional.normalize(bank, dim=1).contiguous()
+    q = torch.nn.functional.normalize(q, dim=1).contiguous()
+    bank_d, q_d = bank.to(dev), q.to(dev)
+    idx, d = ops.knn_topk(bank_d, q_d, k, stats=True)
+    assert ops.last_knn_stats["n_unproven"] >= 0
+    torch.cuda.synchronize()
+    # ---- structure
+    assert int(idx.min()) >= 0 and int(idx.max()) < N
+    srt = torch.sort(idx.long(), dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all()), "duplicate ids inside one list"
+    assert bool((d[:, 1:] >= d[:, :-1]).all()), "distances not ascending"
+    tie = d[:, 1:] == d[:, :-1]
+    assert bool((idx[:, 1:][tie] > idx[:, :-1][tie]).all()), "ties not in ascending row id"
+    assert idx[0, :3].tolist() == [3, N // 2, N - 1] and float(d[0, 2]) == 0.0
+    # ---- returned distances are the fp64 distances of the returned rows
+    for lo in range(0, Q, 80000):
+        hi = min(Q, lo + 80000)
+        x = bank_d[idx[lo:hi].long()].double()                                           # [q, k, 64]
+        dd = ((q_d[lo:hi].double().unsqueeze(1) - x) ** 2).sum(-1)
+        assert float((dd - d[lo:hi]).abs().max()) <= 1e-13
+    # ---- completeness against an independent fp32 GEMM
+    bn = (bank_d * bank_d).sum(1)
+    margin = 2e-5
+    for lo in range(0, Q, 16000):
+        hi = min(Q, lo + 16000)
+        qq = q_d[lo:hi]
+        d32 = (qq * qq).sum(1, keepdim=True) + bn.unsqueeze(0) - 2.0 * (qq @ bank_d.t())
+        thr = (d[lo:hi, k - 1].float() - margin).unsqueeze(1)
+        closer_all = (d32 < thr).sum(1)
+        closer_ret = (torch.gather(d32, 1, idx[lo:hi].long()) < thr).sum(1)
+        assert torch.equal(closer_all, closer_ret), f"a closer row is missing from {int((closer_all != closer_ret).sum())} lists"
+        del d32
+    # ---- sample against the oracle, bit-exact
+    rng = np.random.default_rng(1)
+    pick = np.unique(np.concatenate([[0, 1, Q - 1], rng.integers(0, Q, size=1500)]))
+    want_i, want_d = O.knn_exact(bank.numpy(), q.numpy()[pick], k)
+    assert np.array_equal(idx[pick].cpu().numpy(), want_i)
+    assert np.array_equal(d[pick].cpu().numpy().astype(np.float32), want_d)
+    # ---- two ragged row shards + merge == one bank
+    cut = 70001
+    i0, d0 = ops.knn_topk(bank_d[:cut], q_d, k, row_offset=0)
+    i1, d1 = ops.knn_topk(bank_d[cut:].contiguous(), q_d, k, row_offset=cut)
+    mi, md = ops.knn_merge(torch.stack([i0, i1]), torch.stack([d0, d1]))
+    assert torch.equal(mi, idx) and torch.equal(md, d)
+    # ---- query order / batching does not matter
+    perm = torch.randperm(Q, generator=g)[:200000].to(dev)
+    pi, pd = ops.knn_topk(bank_d, q_d[perm].contiguous(), k)
+    assert torch.equal(pi, idx[perm]) and torch.equal(pd, d[perm])
+
+
+def test_reindex_kernels_full_size_round_trips(dev):
+    """Fold / unfold / pad-unfold / recompose at bench sizes through properties: Fold3D(Unfold3D(x)) == x for every
+    vectorised extent, the pad-unfold patches of a chunk batch recompose to the batch, patch interiors equal the
+    non-overlapping unfold, and the result equals torch's own unfold on the same tensor (checker only)."""
+    from retrieval_fuse_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(7)
+    for (B, C, S, E) in [(40, 16, 32, 8), (40, 16, 32, 4), (10, 1, 64, 16), (8, 16, 32, 2), (2, 12, 32, 2), (2, 3, 6, 2), (3, 5, 12, 3)]:
+        x = torch.randn(B, C, S, S, S, generator=g).to(dev)
+        u = ops.unfold3d(x, E)
+        R = S // E
+        want = x.reshape(B, C, R, E, R, E, R, E).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(B * R ** 3, C, E, E, E)
+        assert torch.equal(u, want), (B, C, S, E)
+        assert torch.equal(ops.fold3d(u, R, E, C), x), (B, C, S, E)
+    for (B, S, kern, pad, stride) in [(4096, 8, 4, 1, 2), (1024, 16, 8, 2, 4), (24, 64, 32, 8, 16), (5, 24, 12, 3, 4), (3, 10, 6, 1, 2)]:
+        x = torch.randn(B, 1, S, S, S, generator=g).to(dev)
+        got = ops.unfold3d_pad_stride(x, kern, pad, stride, -1.5)
+        xp = torch.nn.functional.pad(x, (pad,) * 6, value=-1.5)
+        w = xp.unfold(2, kern, stride).unfold(3, kern, stride).unfold(4, kern, stride)     # [B,1,cx,cy,cz,k,k,k]
+        want = w.permute(0, 2, 3, 4, 1, 5, 6, 7).reshape(-1, 1, kern, kern, kern)
+        assert torch.equal(got, want), (B, S, kern, pad, stride)
+        gotn = ops.unfold3d_pad_stride(x, kern, pad, stride, -1.5, norm_sub=0.25, norm_div=1.75)
+        assert torch.equal(gotn, (want - 0.25) / 1.75), (B, S, kern, pad, stride)
+        cnt = (S + 2 * pad - kern) // stride + 1
+        if (cnt - 1) * stride + kern == S + 2 * pad:   # the patches cover the padded volume: recompose gives x back
+            back = ops.recompose_patches(got.reshape(B, cnt ** 3, kern, kern, kern), (B, 1, S, S, S), kern, pad, stride, [cnt] * 3, -1.5)
+            assert torch.equal(back, x), (B, S, kern, pad, stride)
+
+
 def test_knn_merge_and_sharding(dev):
     from retrieval_fuse_b200 import ops
     rng = np.random.default_rng(11)
