@@ -260,6 +260,9 @@ def run_stages(args, local):
         tot = 0.0
         for _ in range(iters):
             flush_buf.fill_(1)
+            # keep the GPU busy (~0.15 ms spin) while the host enqueues e0, the stage and e1: otherwise the host-side
+            # launch latency of the Python wrapper (20-30 us) is inside the event pair of a 25 us kernel
+            torch.cuda._sleep(300000)
             e0.record()
             fn()
             e1.record()

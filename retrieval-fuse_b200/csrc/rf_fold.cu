@@ -255,58 +255,83 @@ __global__ void __launch_bounds__(256) pad_unfold_kernel(const float* __restrict
     }
 }
 
-// Same, one thread per float4 of the OUTPUT (kernel z extent a multiple of 4, 16-byte aligned output): consecutive
-// threads write consecutive 16-byte pieces, so every warp store is one contiguous 512-byte segment (the earlier
-// one-thread-per-z-run mapping scattered each store instruction over 32 sectors and ran at 16-36 % of the HBM rate).
-// The source float4 is loaded in one piece when it lies inside the volume and is 16-byte aligned, else element by
-// element with the pad value; the overlapping reads (8x for the 32^3 / stride-16 target patches) are L2 hits.
-struct PadUnfoldDivs { FastDiv kz4, ky, kx, c, cz, cy, cx; };
+// Same, one thread per float4 of ONE batch item's output, looping over batch items (kernel z extent a multiple of
+// 4, 16-byte aligned output).  Consecutive threads write consecutive 16-byte pieces, so every warp store is one
+// contiguous 512-byte segment (the first version - one thread per z-run - scattered each store instruction over 32
+// sectors and ran at 16-36 % of the HBM rate).  The position of a float4 inside its item fixes everything but the
+// batch index: the index decomposition, the bounds tests and the source offset are computed ONCE per thread, and an
+// iteration is load / normalise / store plus two pointer increments.  (The second version decomposed the flat index
+// per float4: ~350 instructions each, issue-bound at 1.5-2.9 TB/s.)  The source float4 is loaded in one piece when it
+// lies inside the volume and is 16-byte aligned, else element by element with the pad value; the overlapping reads
+// (8x for the 32^3 / stride-16 target patches) are L1 / L2 hits.
+struct PadUnfoldDivs { FastDiv kz4, ky, kx, c, cz, cy; };
 
-__global__ void __launch_bounds__(256) pad_unfold_vec4_kernel(const float* __restrict__ x, float4* __restrict__ out, Int3 size,
+__global__ void __launch_bounds__(256) pad_unfold_item_kernel(const float* __restrict__ x, float4* __restrict__ out, Int3 size,
                                                               Int3 pad, Int3 stride, PadUnfoldDivs dv, float pad_val,
-                                                              float norm_sub, float norm_div, unsigned total4, int x_aligned) {
-    const unsigned step = gridDim.x * blockDim.x;
+                                                              float norm_sub, float norm_div, unsigned item4, long item_in,
+                                                              int B, int x_aligned) {
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index inside one item's patches
+    if (w >= item4) return;
     const bool norm = norm_div != 0.f;
     const float pad_out = norm ? __fdiv_rn(__fsub_rn(pad_val, norm_sub), norm_div) : pad_val;
-    const bool vec_ok = x_aligned && (size.v[2] & 3) == 0;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += step) {
-        unsigned t = i;
-        const int kz = 4 * (int)fd_divmod(t, dv.kz4);
-        const int ky = (int)fd_divmod(t, dv.ky);
-        const int kx = (int)fd_divmod(t, dv.kx);
-        const int c = (int)fd_divmod(t, dv.c);
-        const int iz = (int)fd_divmod(t, dv.cz);
-        const int iy = (int)fd_divmod(t, dv.cy);
-        const int ix = (int)fd_divmod(t, dv.cx);
-        const int b = (int)t;
-        const int sx = ix * stride.v[0] + kx - pad.v[0];
-        const int sy = iy * stride.v[1] + ky - pad.v[1];
-        const int sz = iz * stride.v[2] + kz - pad.v[2];
-        float4 v = make_float4(pad_out, pad_out, pad_out, pad_out);
-        if (sx >= 0 && sx < size.v[0] && sy >= 0 && sy < size.v[1] && sz > -4 && sz < size.v[2]) {
-            const float* src = x + ((((long)b * dv.c.d + c) * size.v[0] + sx) * size.v[1] + sy) * size.v[2];
+    unsigned t = w;
+    const int kz = 4 * (int)fd_divmod(t, dv.kz4);
+    const int ky = (int)fd_divmod(t, dv.ky);
+    const int kx = (int)fd_divmod(t, dv.kx);
+    const int c = (int)fd_divmod(t, dv.c);
+    const int iz = (int)fd_divmod(t, dv.cz);
+    const int iy = (int)fd_divmod(t, dv.cy);
+    const int ix = (int)t;
+    const int sx = ix * stride.v[0] + kx - pad.v[0];
+    const int sy = iy * stride.v[1] + ky - pad.v[1];
+    const int sz = iz * stride.v[2] + kz - pad.v[2];
+    const bool row_in = sx >= 0 && sx < size.v[0] && sy >= 0 && sy < size.v[1] && sz > -4 && sz < size.v[2];
+    const bool vec = row_in && x_aligned && (size.v[2] & 3) == 0 && (item_in & 3) == 0 && sz >= 0 && sz + 4 <= size.v[2] && (sz & 3) == 0;
+    bool in_e[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) in_e[e] = row_in && sz + e >= 0 && sz + e < size.v[2];
+    const long off = (((long)c * size.v[0] + (row_in ? sx : 0)) * size.v[1] + (row_in ? sy : 0)) * size.v[2] + sz;
+    const float* src = x + (long)blockIdx.y * item_in + off;
+    float4* dst = out + (long)blockIdx.y * item4 + w;
+    const long src_step = (long)gridDim.y * item_in, dst_step = (long)gridDim.y * item4;
+    const float4 padv = make_float4(pad_out, pad_out, pad_out, pad_out);
+    if (!row_in) {
+        for (int b = blockIdx.y; b < B; b += gridDim.y, dst += dst_step) *dst = padv;
+    } else if (vec) {
+        int b = blockIdx.y;
+        for (; b + (int)gridDim.y < B; b += 2 * gridDim.y, src += 2 * src_step, dst += 2 * dst_step) {  // two loads in flight
+            float4 q0 = __ldg(reinterpret_cast<const float4*>(src));
+            float4 q1 = __ldg(reinterpret_cast<const float4*>(src + src_step));
+            if (norm) {  // two rounded fp32 ops per element, as numpy does
+                q0.x = __fdiv_rn(__fsub_rn(q0.x, norm_sub), norm_div); q0.y = __fdiv_rn(__fsub_rn(q0.y, norm_sub), norm_div);
+                q0.z = __fdiv_rn(__fsub_rn(q0.z, norm_sub), norm_div); q0.w = __fdiv_rn(__fsub_rn(q0.w, norm_sub), norm_div);
+                q1.x = __fdiv_rn(__fsub_rn(q1.x, norm_sub), norm_div); q1.y = __fdiv_rn(__fsub_rn(q1.y, norm_sub), norm_div);
+                q1.z = __fdiv_rn(__fsub_rn(q1.z, norm_sub), norm_div); q1.w = __fdiv_rn(__fsub_rn(q1.w, norm_sub), norm_div);
+            }
+            dst[0] = q0;
+            dst[dst_step] = q1;
+        }
+        if (b < B) {
+            float4 q0 = __ldg(reinterpret_cast<const float4*>(src));
+            if (norm) {
+                q0.x = __fdiv_rn(__fsub_rn(q0.x, norm_sub), norm_div); q0.y = __fdiv_rn(__fsub_rn(q0.y, norm_sub), norm_div);
+                q0.z = __fdiv_rn(__fsub_rn(q0.z, norm_sub), norm_div); q0.w = __fdiv_rn(__fsub_rn(q0.w, norm_sub), norm_div);
+            }
+            dst[0] = q0;
+        }
+    } else {
+        for (int b = blockIdx.y; b < B; b += gridDim.y, src += src_step, dst += dst_step) {
             float f[4];
-            if (vec_ok && sz >= 0 && sz + 4 <= size.v[2] && (sz & 3) == 0) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(src + sz));
-                f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
-                if (norm) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) f[e] = __fdiv_rn(__fsub_rn(f[e], norm_sub), norm_div);  // two rounded fp32 ops, as numpy does
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int z = sz + e;
-                    f[e] = pad_out;
-                    if (z >= 0 && z < size.v[2]) {
-                        f[e] = __ldg(src + z);
-                        if (norm) f[e] = __fdiv_rn(__fsub_rn(f[e], norm_sub), norm_div);
-                    }
+            for (int e = 0; e < 4; ++e) {
+                f[e] = pad_out;
+                if (in_e[e]) {
+                    f[e] = __ldg(src + e);
+                    if (norm) f[e] = __fdiv_rn(__fsub_rn(f[e], norm_sub), norm_div);
                 }
             }
-            v = make_float4(f[0], f[1], f[2], f[3]);
+            *dst = make_float4(f[0], f[1], f[2], f[3]);
         }
-        out[i] = v;
     }
 }
 
@@ -324,13 +349,20 @@ extern "C" int rf_unfold3d_pad_stride(const float* x, float* out, int B, int C, 
         total *= (long)cnt.v[a] * kernel[a];
     }
     RF_CHECK_ARG(B > 0 && C > 0, "rf_unfold3d_pad_stride: bad B/C");
-    if (kernel[2] % 4 == 0 && ((uintptr_t)out & 15) == 0 && total / 4 < (1L << 31)) {
-        const unsigned total4 = (unsigned)(total / 4);
+    const long item4 = total / B / 4;  // float4s of one batch item's patches
+    if (kernel[2] % 4 == 0 && ((uintptr_t)out & 15) == 0 && item4 < (1L << 31)) {
         PadUnfoldDivs dv;
         dv.kz4 = make_fastdiv(kernel[2] / 4); dv.ky = make_fastdiv(kernel[1]); dv.kx = make_fastdiv(kernel[0]);
-        dv.c = make_fastdiv(C); dv.cz = make_fastdiv(cnt.v[2]); dv.cy = make_fastdiv(cnt.v[1]); dv.cx = make_fastdiv(cnt.v[0]);
-        pad_unfold_vec4_kernel<<<rf_grid_1d(total4, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
-            x, reinterpret_cast<float4*>(out), s, p, st, dv, pad_val, norm_sub, norm_div, total4, ((uintptr_t)x & 15) == 0);
+        dv.c = make_fastdiv(C); dv.cz = make_fastdiv(cnt.v[2]); dv.cy = make_fastdiv(cnt.v[1]);
+        // grid.x covers one item, grid.y strides over the batch: ~148 x 16 CTAs in total, at least 2 items per thread
+        const unsigned gx = (unsigned)rf_cdivl(item4, 256);
+        long gy = rf_cdivl(148L * 16, gx);
+        if (gy > (B + 1) / 2) gy = (B + 1) / 2;
+        if (gy < 1) gy = 1;
+        if (gy > 65535) gy = 65535;
+        pad_unfold_item_kernel<<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(
+            x, reinterpret_cast<float4*>(out), s, p, st, dv, pad_val, norm_sub, norm_div, (unsigned)item4,
+            (long)C * size[0] * size[1] * size[2], B, ((uintptr_t)x & 15) == 0);
     } else {
         pad_unfold_kernel<<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, C, s, k, p, st, cnt, pad_val,
                                                                                    norm_sub, norm_div);
@@ -424,6 +456,8 @@ __global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ 
     if (inside && (ez & 3) == 0 && (Z0 & 3) == 0 && (de[4] & 3) == 0 && (ssz.v[2] & 3) == 0 && (csz.v[2] & 3) == 0 &&
         (((uintptr_t)store | (uintptr_t)out) & 15) == 0) {
         const int ez4 = ez >> 2, n4 = ex * ey * ez4;
+        const bool pow2 = (ez4 & (ez4 - 1)) == 0 && (ey & (ey - 1)) == 0;
+        const int sh_z = 31 - __clz(ez4), sh_zy = sh_z + 31 - __clz(ey);
         // four independent 16-byte loads in flight per thread before the first store (a 16^3 block is 1024 float4s =
         // one trip of this loop): the copy is a dependent chain row -> scene -> data, so latency, not bandwidth, is
         // what a CTA sees
@@ -434,7 +468,9 @@ __global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ 
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u * blockDim.x;
                 if (i < n4) {
-                    const int z = (i % ez4) << 2, y = (i / ez4) % ey, x = i / (ez4 * ey);
+                    int z, y, x;
+                    if (pow2) { z = (i & (ez4 - 1)) << 2; y = (i >> sh_z) & (ey - 1); x = i >> sh_zy; }   // 16^3 blocks: no divisions
+                    else { z = (i % ez4) << 2; y = (i / ez4) % ey; x = i / (ez4 * ey); }
                     v[u] = __ldg(reinterpret_cast<const float4*>(s + ((long)(X0 + x) * ssz.v[1] + (Y0 + y)) * ssz.v[2] + Z0 + z));
                     dsti[u] = ((long)(de[0] + x) * csz.v[1] + (de[2] + y)) * csz.v[2] + (de[4] + z);
                 }

@@ -525,7 +525,7 @@ def test_reindex_kernels_full_size_round_trips(dev):
         want = x.reshape(B, C, R, E, R, E, R, E).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(B * R ** 3, C, E, E, E)
         assert torch.equal(u, want), (B, C, S, E)
         assert torch.equal(ops.fold3d(u, R, E, C), x), (B, C, S, E)
-    for (B, S, kern, pad, stride) in [(4096, 8, 4, 1, 2), (1024, 16, 8, 2, 4), (24, 64, 32, 8, 16), (5, 24, 12, 3, 4), (3, 10, 6, 1, 2)]:
+    for (B, S, kern, pad, stride) in [(4097, 8, 4, 1, 2), (1024, 16, 8, 2, 4), (23, 64, 32, 8, 16), (1, 64, 32, 8, 16), (5, 24, 12, 3, 4), (3, 10, 6, 1, 2), (2, 128, 48, 8, 32)]:
         x = torch.randn(B, 1, S, S, S, generator=g).to(dev)
         got = ops.unfold3d_pad_stride(x, kern, pad, stride, -1.5)
         xp = torch.nn.functional.pad(x, (pad,) * 6, value=-1.5)
@@ -533,7 +533,8 @@ def test_reindex_kernels_full_size_round_trips(dev):
         want = w.permute(0, 2, 3, 4, 1, 5, 6, 7).reshape(-1, 1, kern, kern, kern)
         assert torch.equal(got, want), (B, S, kern, pad, stride)
         gotn = ops.unfold3d_pad_stride(x, kern, pad, stride, -1.5, norm_sub=0.25, norm_div=1.75)
-        assert torch.equal(gotn, (want - 0.25) / 1.75), (B, S, kern, pad, stride)
+        wantn = (want.cpu().numpy() - np.float32(0.25)) / np.float32(1.75)   # numpy: a true fp32 division (torch multiplies by 1/s)
+        assert np.array_equal(gotn.cpu().numpy(), wantn), (B, S, kern, pad, stride)
         cnt = (S + 2 * pad - kern) // stride + 1
         if (cnt - 1) * stride + kern == S + 2 * pad:   # the patches cover the padded volume: recompose gives x back
             back = ops.recompose_patches(got.reshape(B, cnt ** 3, kern, kern, kern), (B, 1, S, S, S), kern, pad, stride, [cnt] * 3, -1.5)

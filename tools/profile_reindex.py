@@ -14,12 +14,19 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
+ONCE = "--once" in sys.argv  # one launch per kernel (for ncu)
+
+
 def timed(name, fn, nbytes, iters=5):
+    if ONCE:
+        fn()
+        return
     for _ in range(2):
         fn()
     tot = 0.0
     for _ in range(iters):
         flush.fill_(1)
+        torch.cuda._sleep(300000)  # the host enqueues e0 / kernel / e1 while the GPU spins: no launch latency in the pair
         e0.record()
         fn()
         e1.record()
