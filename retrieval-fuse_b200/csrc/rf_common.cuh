@@ -50,6 +50,29 @@ static inline int rf_grid_1d(long n, int block, int max_ctas = 148 * 16) {
     return (int)g;
 }
 
+// Correctly rounded a / b for a divisor that is fixed per launch (the (x - mean) / std normalisation must be the
+// same two rounded fp32 operations numpy performs).  __fdiv_rn costs ~20 instructions per element and made the
+// re-indexing kernels issue-bound; with y = RN(1 / b) from the host, two Newton steps on the quotient give a
+// faithful q1 and Markstein's theorem (q faithful, r = a - b q exact by FMA, y = RN(1/b)  =>  RN(q + r y) = RN(a / b))
+// makes the third rounding exact: 5 FMA-class instructions.  Guarded ranges keep every intermediate normal
+// (|a| in [2^-20, 2^20], |b| in [2^-10, 2^10], checked on the host: y == 0 means "use __fdiv_rn"); zeros, tiny and
+// huge values take the IEEE division.
+static inline float rf_host_rcp_for_div(float b) {
+    const float ab = b < 0.f ? -b : b;
+    return (ab >= 0.0009765625f && ab <= 1024.f) ? 1.0f / b : 0.f;
+}
+__device__ __forceinline__ float rf_div_rn_fixed(float a, float b, float y) {
+    const float aa = fabsf(a);
+    if (y != 0.f && aa >= 9.5367431640625e-07f && aa <= 1048576.f) {
+        const float q0 = __fmul_rn(a, y);
+        const float r0 = __fmaf_rn(-b, q0, a);
+        const float q1 = __fmaf_rn(r0, y, q0);
+        const float r1 = __fmaf_rn(-b, q1, a);
+        return __fmaf_rn(r1, y, q1);
+    }
+    return __fdiv_rn(a, b);
+}
+
 __device__ __forceinline__ float rf_act(float v, int act, float slope) {
     if (act == RF_ACT_RELU) return v > 0.f ? v : 0.f;
     if (act == RF_ACT_LEAKY) return v > 0.f ? v : v * slope;

@@ -268,12 +268,12 @@ struct PadUnfoldDivs { FastDiv kz4, ky, kx, c, cz, cy; };
 
 __global__ void __launch_bounds__(256) pad_unfold_item_kernel(const float* __restrict__ x, float4* __restrict__ out, Int3 size,
                                                               Int3 pad, Int3 stride, PadUnfoldDivs dv, float pad_val,
-                                                              float norm_sub, float norm_div, unsigned item4, long item_in,
-                                                              int B, int x_aligned) {
+                                                              float norm_sub, float norm_div, float norm_rcp, unsigned item4,
+                                                              long item_in, int B, int x_aligned) {
     const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index inside one item's patches
     if (w >= item4) return;
     const bool norm = norm_div != 0.f;
-    const float pad_out = norm ? __fdiv_rn(__fsub_rn(pad_val, norm_sub), norm_div) : pad_val;
+    const float pad_out = norm ? rf_div_rn_fixed(__fsub_rn(pad_val, norm_sub), norm_div, norm_rcp) : pad_val;
     unsigned t = w;
     const int kz = 4 * (int)fd_divmod(t, dv.kz4);
     const int ky = (int)fd_divmod(t, dv.ky);
@@ -303,10 +303,10 @@ __global__ void __launch_bounds__(256) pad_unfold_item_kernel(const float* __res
             float4 q0 = __ldg(reinterpret_cast<const float4*>(src));
             float4 q1 = __ldg(reinterpret_cast<const float4*>(src + src_step));
             if (norm) {  // two rounded fp32 ops per element, as numpy does
-                q0.x = __fdiv_rn(__fsub_rn(q0.x, norm_sub), norm_div); q0.y = __fdiv_rn(__fsub_rn(q0.y, norm_sub), norm_div);
-                q0.z = __fdiv_rn(__fsub_rn(q0.z, norm_sub), norm_div); q0.w = __fdiv_rn(__fsub_rn(q0.w, norm_sub), norm_div);
-                q1.x = __fdiv_rn(__fsub_rn(q1.x, norm_sub), norm_div); q1.y = __fdiv_rn(__fsub_rn(q1.y, norm_sub), norm_div);
-                q1.z = __fdiv_rn(__fsub_rn(q1.z, norm_sub), norm_div); q1.w = __fdiv_rn(__fsub_rn(q1.w, norm_sub), norm_div);
+                q0.x = rf_div_rn_fixed(__fsub_rn(q0.x, norm_sub), norm_div, norm_rcp); q0.y = rf_div_rn_fixed(__fsub_rn(q0.y, norm_sub), norm_div, norm_rcp);
+                q0.z = rf_div_rn_fixed(__fsub_rn(q0.z, norm_sub), norm_div, norm_rcp); q0.w = rf_div_rn_fixed(__fsub_rn(q0.w, norm_sub), norm_div, norm_rcp);
+                q1.x = rf_div_rn_fixed(__fsub_rn(q1.x, norm_sub), norm_div, norm_rcp); q1.y = rf_div_rn_fixed(__fsub_rn(q1.y, norm_sub), norm_div, norm_rcp);
+                q1.z = rf_div_rn_fixed(__fsub_rn(q1.z, norm_sub), norm_div, norm_rcp); q1.w = rf_div_rn_fixed(__fsub_rn(q1.w, norm_sub), norm_div, norm_rcp);
             }
             dst[0] = q0;
             dst[dst_step] = q1;
@@ -314,20 +314,40 @@ __global__ void __launch_bounds__(256) pad_unfold_item_kernel(const float* __res
         if (b < B) {
             float4 q0 = __ldg(reinterpret_cast<const float4*>(src));
             if (norm) {
-                q0.x = __fdiv_rn(__fsub_rn(q0.x, norm_sub), norm_div); q0.y = __fdiv_rn(__fsub_rn(q0.y, norm_sub), norm_div);
-                q0.z = __fdiv_rn(__fsub_rn(q0.z, norm_sub), norm_div); q0.w = __fdiv_rn(__fsub_rn(q0.w, norm_sub), norm_div);
+                q0.x = rf_div_rn_fixed(__fsub_rn(q0.x, norm_sub), norm_div, norm_rcp); q0.y = rf_div_rn_fixed(__fsub_rn(q0.y, norm_sub), norm_div, norm_rcp);
+                q0.z = rf_div_rn_fixed(__fsub_rn(q0.z, norm_sub), norm_div, norm_rcp); q0.w = rf_div_rn_fixed(__fsub_rn(q0.w, norm_sub), norm_div, norm_rcp);
             }
             dst[0] = q0;
         }
     } else {
-        for (int b = blockIdx.y; b < B; b += gridDim.y, src += src_step, dst += dst_step) {
+        // partly outside or not 16-byte aligned: element loads under per-thread constant predicates, two items in flight
+        int b = blockIdx.y;
+        for (; b + (int)gridDim.y < B; b += 2 * gridDim.y, src += 2 * src_step, dst += 2 * dst_step) {
+            float f[4], g[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                f[e] = in_e[e] ? __ldg(src + e) : 0.f;
+                g[e] = in_e[e] ? __ldg(src + src_step + e) : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (norm) {
+                    f[e] = rf_div_rn_fixed(__fsub_rn(f[e], norm_sub), norm_div, norm_rcp);
+                    g[e] = rf_div_rn_fixed(__fsub_rn(g[e], norm_sub), norm_div, norm_rcp);
+                }
+                if (!in_e[e]) { f[e] = pad_out; g[e] = pad_out; }
+            }
+            dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+            dst[dst_step] = make_float4(g[0], g[1], g[2], g[3]);
+        }
+        if (b < B) {
             float f[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 f[e] = pad_out;
                 if (in_e[e]) {
                     f[e] = __ldg(src + e);
-                    if (norm) f[e] = __fdiv_rn(__fsub_rn(f[e], norm_sub), norm_div);
+                    if (norm) f[e] = rf_div_rn_fixed(__fsub_rn(f[e], norm_sub), norm_div, norm_rcp);
                 }
             }
             *dst = make_float4(f[0], f[1], f[2], f[3]);
@@ -361,7 +381,7 @@ extern "C" int rf_unfold3d_pad_stride(const float* x, float* out, int B, int C, 
         if (gy < 1) gy = 1;
         if (gy > 65535) gy = 65535;
         pad_unfold_item_kernel<<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(
-            x, reinterpret_cast<float4*>(out), s, p, st, dv, pad_val, norm_sub, norm_div, (unsigned)item4,
+            x, reinterpret_cast<float4*>(out), s, p, st, dv, pad_val, norm_sub, norm_div, rf_host_rcp_for_div(norm_div), (unsigned)item4,
             (long)C * size[0] * size[1] * size[2], B, ((uintptr_t)x & 15) == 0);
     } else {
         pad_unfold_kernel<<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, C, s, k, p, st, cnt, pad_val,
@@ -436,7 +456,7 @@ extern "C" int rf_recompose_patches(const float* patches, float* out, int B, int
 __global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ rows, const int* __restrict__ dst_ext,
                                                       const float* __restrict__ store, float* __restrict__ out, int P,
                                                       int K, int n_scenes, Int3 ssz, Int3 csz, float trunc, float ratio,
-                                                      float norm_sub, float norm_div) {
+                                                      float norm_sub, float norm_div, float norm_rcp) {
     const int p = blockIdx.x, k = blockIdx.y, c = blockIdx.z;
     const float* row = rows + (((long)c * P + p) * K + k) * 8;
     const int scene = (int)row[0];
@@ -481,8 +501,8 @@ __global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ 
                     float4 w = v[u];
                     w.x = __fmul_rn(w.x, ratio); w.y = __fmul_rn(w.y, ratio); w.z = __fmul_rn(w.z, ratio); w.w = __fmul_rn(w.w, ratio);
                     if (norm_div != 0.f) {
-                        w.x = __fdiv_rn(__fsub_rn(w.x, norm_sub), norm_div); w.y = __fdiv_rn(__fsub_rn(w.y, norm_sub), norm_div);
-                        w.z = __fdiv_rn(__fsub_rn(w.z, norm_sub), norm_div); w.w = __fdiv_rn(__fsub_rn(w.w, norm_sub), norm_div);
+                        w.x = rf_div_rn_fixed(__fsub_rn(w.x, norm_sub), norm_div, norm_rcp); w.y = rf_div_rn_fixed(__fsub_rn(w.y, norm_sub), norm_div, norm_rcp);
+                        w.z = rf_div_rn_fixed(__fsub_rn(w.z, norm_sub), norm_div, norm_rcp); w.w = rf_div_rn_fixed(__fsub_rn(w.w, norm_sub), norm_div, norm_rcp);
                     }
                     *reinterpret_cast<float4*>(o + dsti[u]) = w;
                 }
@@ -516,7 +536,7 @@ extern "C" int rf_compose_gather(const float* rows, const int* dst_extents, cons
     for (int a = 0; a < 3; ++a) { s.v[a] = scene_size[a]; c.v[a] = chunk_size[a]; }
     dim3 grid(P, K, n_chunks);
     compose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, dst_extents, scene_store, out, P, K, n_scenes, s, c,
-                                                          trunc, ratio, norm_sub, norm_div);
+                                                          trunc, ratio, norm_sub, norm_div, rf_host_rcp_for_div(norm_div));
     RF_LAUNCH_OK("compose_kernel");
     return 0;
 }

@@ -70,6 +70,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) knn_exact_f64_kernel(const
     for (int j = 0; j < QW; ++j) { ld[j] = DBL_MAX; li[j] = INT_MAX; tau_d[j] = DBL_MAX; tau_i[j] = INT_MAX; }
 
     const double(*qw)[D64] = &qs[warp * QW];
+    // queries past the end of the list (the re-check of a handful of unproven queries fills a fraction of one CTA):
+    // a warp without queries leaves, the others skip their empty slots - the fp64 pipe is the bound of this kernel
+    const long nq_l = Q - q_cta - (long)warp * QW;
+    const int nq = nq_l >= QW ? QW : (int)nq_l;  // warp-uniform
+    if (nq <= 0) return;                         // (no block-level synchronisation follows)
     for (long base = r_begin; base < r_end; base += 32) {
         const long r = base + lane;
         const bool valid = r < r_end;
@@ -84,6 +89,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) knn_exact_f64_kernel(const
         const int gid = (int)(row_offset + r);
 #pragma unroll
         for (int j = 0; j < QW; ++j) {
+            if (j >= nq) break;
             double acc = 0.0;
 #pragma unroll
             for (int i = 0; i < D64; ++i) {

@@ -473,6 +473,19 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restr
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o, 16);
 
+    // Staging (per warp: 2 queries x 16 candidate rows).  A lane needs its candidate's whole 256-byte row in index
+    // order (the canonical sum is sequential), so reading rows straight from the bank makes every load instruction
+    // touch 32 different lines; instead each half warp fetches its 16 rows with one contiguous 256-byte access per
+    // row into shared memory (row pitch 272 B: the per-lane float4 reads are conflict-free per quarter warp), and the
+    // query sits there once as fp64 (no per-candidate re-conversion).
+    __shared__ __align__(16) float xs[4][32][68];
+    __shared__ double qsd[8][64];
+    const int warp_l = threadIdx.x >> 5, hw_l = threadIdx.x >> 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) qsd[hw_l][lane16 + 16 * j] = (double)qr[lane16 + 16 * j];
+    __syncwarp();
+    const double* qd = qsd[hw_l];
+
     double ld = DBL_MAX;
     int li = INT_MAX;
     float tau = -FLT_MAX;       // max over slices of the slice's 16th best approximate score
@@ -489,18 +502,27 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restr
             sc = cand_s[o];
             if ((c % CAND) == CAND - 1 && id >= 0) tau = fmaxf(tau, sc);  // a full list: its tail bounds the rejected rows
         }
+        __syncwarp();  // the previous round's rows have been consumed
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) {
+            const int idc = __shfl_sync(0xffffffffu, id, cc, 16);
+            if (idc >= 0)
+                *reinterpret_cast<float4*>(&xs[warp_l][half * 16 + cc][lane16 * 4]) =
+                    __ldg(reinterpret_cast<const float4*>(bank + (long)idc * 64) + lane16);
+        }
+        __syncwarp();
         double d = DBL_MAX;
         if (id >= 0) {  // canonical fp64 distance, same arithmetic as the exact sweep
-            const float4* xr = reinterpret_cast<const float4*>(bank + (long)id * 64);
+            const float4* xr = reinterpret_cast<const float4*>(&xs[warp_l][half * 16 + lane16][0]);
             double acc = 0.0;
             float xn = 0.f;  // |x|^2 only feeds the error diagnostic: fp32 is plenty
 #pragma unroll 4
             for (int i = 0; i < 16; ++i) {
-                const float4 x4 = __ldg(xr + i);
+                const float4 x4 = xr[i];
                 const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const double qv = (double)qr[4 * i + j];
+                    const double qv = qd[4 * i + j];
                     const double diff = __dsub_rn(qv, (double)xv[j]);
                     acc = __dadd_rn(acc, __dmul_rn(diff, diff));
                     xn = fmaf(xv[j], xv[j], xn);

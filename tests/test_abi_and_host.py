@@ -158,3 +158,20 @@ def test_oracle_demotion_rule():
     assert list(oi[0]) == [4, 9, 2]
     oi, _ = O.demote_same_scene(idx[:, :4], d[:, :4], np.full(10, 3), np.array([3]), 2)  # everything same-scene: order kept
     assert list(oi[0]) == [4, 9]
+
+
+def test_fixed_divisor_division_is_ieee(tmp_path):
+    """rf_div_rn_fixed (the normalisation's division in the re-indexing kernels) against the host's IEEE division:
+    tools/check_fixed_div.c runs the same 5-step FMA sequence on 5e7 random (a, b) pairs of the guarded ranges."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "check_fixed_div.c")
+    exe = str(tmp_path / "check_fixed_div")
+    flags = ["-O2", "-ffp-contract=off"]
+    if "fma" in open("/proc/cpuinfo").read():
+        flags.append("-mfma")  # hardware fmaf; glibc's software fmaf is correctly rounded as well, only slower
+    subprocess.check_call(["gcc"] + flags + ["-o", exe, src, "-lm"])
+    out = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and " bad 0" in out.stdout, out.stdout
