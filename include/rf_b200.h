@@ -275,6 +275,28 @@ int rf_attention_features(const float* x, const float* t, const uint8_t* occ, co
                           const void* const* phi_img_host, float* x_feat, float* p_feat, uint8_t* occ_any, int B, int nf,
                           int S, int E, int normalize, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- callers either side of the path ------------------ */
+
+/* dataset/patched_scene_dataset.py:139-146 compute_normals: pad by 1 with pad_val (the target truncation), the
+ * three 3x3x3 Sobel cross-correlations (:194-196), n / sqrt(|n|^2 + 1e-5).  x [B,1,D,H,W] -> out [B,3,D,H,W]. */
+int rf_sobel_normals(const float* x, float* out, int B, int D, int H, int W, float pad_val, void* stream);
+/* util/metrics.py:15-16 (IoU), :66 (Precision), :83 (Recall): per sample the integer sums
+ * counts[b] = {sum(pred & target), sum(pred | target), sum(pred), sum(target)} of two bool volumes
+ * (one byte per voxel, non-zero = True); counts [B,4] uint64 (zeroed by the call). */
+int rf_occupancy_counts(const uint8_t* pred, const uint8_t* target, int B, long voxels_per_sample, unsigned long long* counts,
+                        void* stream);
+/* external/ChamferDistancePytorch chamfer3D (un-vendored submodule; call site util/metrics.py:46
+ * `dist1, dist2, _, _ = cham_loss(points_target, points_pred)`): for every point of a [na,3] the squared distance
+ * to its nearest neighbour in b [nb,3] and that neighbour's index (first minimal index).  Call twice for both
+ * directions.  d = fma(dz,dz, fma(dy,dy, dx*dx)) in fp32. */
+int rf_chamfer_nn(const float* a, int na, const float* b, int nb, float* dist, int* idx, void* stream);
+/* model/loss.py:48-69 NTXentLoss.forward(zis, zjs, iou_matrix=None): zis, zjs [N,C] (C <= 128), iou_matrix NULL or
+ * [2N,2N]; cosine != 0 selects the cosine similarity (eps 1e-8), else the dot product; loss [1].
+ * workspace: rf_ntxent_workspace_bytes(N). */
+size_t rf_ntxent_workspace_bytes(int N);
+int rf_ntxent_fwd(const float* zis, const float* zjs, int N, int C, const float* iou_matrix, float temperature, float sig_scale,
+                  float sig_shift, int cosine, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

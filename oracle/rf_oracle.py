@@ -848,3 +848,119 @@ def refine_chunks(config, sds, chunks, retrieval_raw):
                retrieval_num_level=config["retrieval_num_level"], K=config["K"], E=config["attn_patch_extent"] // 2,
                retrieval_mode=config["attn_retrieval_mode"])
     return refine_forward(x_in, x_re, sds, cfg)
+
+
+# ---------------------------------------------------------------------------
+# callers either side of the path (training-side loss and
+# normals, evaluation metrics)
+# ---------------------------------------------------------------------------
+
+# dataset/patched_scene_dataset.py:194-196 (class attributes of PatchedSceneDataset)
+SOBEL_3D_X = np.array([[[+1, +2, +1], [+2, +4, +2], [+1, +2, +1]], [[0, 0, 0], [0, 0, 0], [0, 0, 0]],
+                       [[-1, -2, -1], [-2, -4, -2], [-1, -2, -1]]], dtype=np.float32)
+SOBEL_3D_Y = np.array([[[+1, +2, +1], [0, 0, 0], [-1, -2, -1]], [[+2, +4, +2], [0, 0, 0], [-2, -4, -2]],
+                       [[+1, +2, +1], [0, 0, 0], [-1, -2, -1]]], dtype=np.float32)
+SOBEL_3D_Z = np.array([[[-1, 0, +1], [-2, 0, +2], [-1, 0, +1]], [[-2, 0, +2], [-4, 0, +4], [-2, 0, +2]],
+                       [[-1, 0, +1], [-2, 0, +2], [-1, 0, +1]]], dtype=np.float32)
+
+
+def compute_normals(target: torch.Tensor, target_trunc: float) -> torch.Tensor:
+    """dataset/patched_scene_dataset.py:139-146 compute_normals, line by line."""
+    padded = F.pad(target, [1, 1, 1, 1, 1, 1], mode="constant", value=float(target_trunc))
+    k = [torch.from_numpy(a)[None, None] for a in (SOBEL_3D_X, SOBEL_3D_Y, SOBEL_3D_Z)]
+    normals = torch.cat([F.conv3d(padded, kk) for kk in k], dim=1)
+    normalizer = torch.sqrt(torch.square(normals).sum(dim=1, keepdim=True) + 1e-5)
+    return torch.div(normals, normalizer)
+
+
+def ntxent_loss(zis: torch.Tensor, zjs: torch.Tensor, temperature: float, use_cosine: bool = True, iou_matrix=None,
+                sig_scale: float = 80, sig_shift: float = -65) -> torch.Tensor:
+    """model/loss.py:48-69 NTXentLoss.forward (CPU restatement: `.cuda()` calls dropped, nothing else changed)."""
+    n = zis.shape[0]
+    rep = torch.cat([zjs, zis], dim=0)
+    if use_cosine:
+        sim = torch.nn.CosineSimilarity(dim=-1)(rep.unsqueeze(1), rep.unsqueeze(0))          # :44
+    else:
+        sim = torch.tensordot(rep.unsqueeze(1), rep.T.unsqueeze(0), dims=2)                  # :35
+    l_pos = torch.diag(sim, n)
+    r_pos = torch.diag(sim, -n)
+    positives = torch.cat([l_pos, r_pos]).view(2 * n, 1)
+    mask = torch.from_numpy(1 - (np.eye(2 * n) + np.eye(2 * n, 2 * n, k=-n) + np.eye(2 * n, 2 * n, k=n))).type(torch.bool)  # :25-31
+    negatives = sim[mask].view(2 * n, -1)
+    logits = torch.cat((positives, negatives), dim=1)
+    if iou_matrix is None:
+        logits = logits / temperature
+    else:
+        neg_iou = iou_matrix[mask].view(2 * n, -1)
+        logits[:, 0] /= temperature
+        logits[:, 1:] /= (temperature + (1 - temperature) * torch.sigmoid(neg_iou * sig_scale + sig_shift))
+    labels = torch.zeros(2 * n).long()
+    return torch.nn.CrossEntropyLoss(reduction="sum")(logits, labels) / (2 * n)
+
+
+def sliced_attn_nt_xent(temperature, batch_size, x_fpred, x_ftgt, occupancy, budget=1280):
+    """trainer/train_refinement.py:208-221 compute_sliced_attn_nt_xent_loss."""
+    split = x_fpred.shape[0] // batch_size
+    total = 0
+    loss = torch.zeros(1)
+    for b in range(batch_size):
+        occ = occupancy[b * split:(b + 1) * split] > 0
+        if occ.sum() > 0 and total + int(occ.sum()) <= budget:
+            loss = ntxent_loss(x_fpred[b * split:(b + 1) * split][occ], x_ftgt[b * split:(b + 1) * split][occ], temperature) + loss
+            total += int(occ.sum())
+    return loss
+
+
+def occupancy_metrics(pred: np.ndarray, target: np.ndarray):
+    """util/metrics.py:15-24 (IoU), :66-67 (Precision), :83-84 (Recall) for ONE update call on bool [B,1,S,S,S]:
+    returns (iou_sum, iou_total, precision_sum, recall_sum, n) exactly as the metric states accumulate them
+    (torch float32 arithmetic on the integer sums)."""
+    p, t = torch.from_numpy(pred), torch.from_numpy(target)
+    inter = (p & t).sum(-1).sum(-1).sum(-1).squeeze(1)
+    union = (p | t).sum(-1).sum(-1).sum(-1).squeeze(1)
+    valid = union > 0
+    iou_sum, iou_total = 0.0, 0
+    if union[valid].sum() > 0:
+        iou_sum = float((inter[valid] / (union[valid] + 1e-5)).sum())
+        iou_total = int(valid.sum())
+    prec = float((inter / (p.sum(-1).sum(-1).sum(-1).squeeze(1) + 1e-5)).sum())
+    rec = float((inter / (t.sum(-1).sum(-1).sum(-1).squeeze(1) + 1e-5)).sum())
+    counts = np.stack([inter.numpy(), union.numpy(), p.sum((-1, -2, -3)).squeeze(1).numpy(), t.sum((-1, -2, -3)).squeeze(1).numpy()], 1)
+    return iou_sum, iou_total, prec, rec, counts.astype(np.int64)
+
+
+def chamfer_nn(a: np.ndarray, b: np.ndarray):
+    """Nearest neighbour in b of every point of a, the arithmetic of the (un-vendored) ChamferDistancePytorch
+    chamfer3D NmDistanceKernel as nvcc contracts it: d = fma(dz,dz, fma(dy,dy, dx*dx)) in fp32, first minimal index.
+    fp32 FMAs are emulated in float64 (exact products; exact for the integer voxel coordinates util/metrics.py:43-44
+    feeds it).  Parity unpinned for non-integer clouds (the submodule is absent): tests use a tolerance there."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    dist = np.empty(a.shape[0], dtype=np.float32)
+    idx = np.empty(a.shape[0], dtype=np.int32)
+    for lo in range(0, a.shape[0], 1024):
+        aa = a[lo:lo + 1024, None, :]
+        df = (b[None, :, :] - aa).astype(np.float32)                      # fp32 differences
+        dd = df.astype(np.float64)
+        t = (dd[..., 0] * dd[..., 0]).astype(np.float32)                  # __fmul_rn
+        t = (dd[..., 1] * dd[..., 1] + t.astype(np.float64)).astype(np.float32)
+        t = (dd[..., 2] * dd[..., 2] + t.astype(np.float64)).astype(np.float32)
+        j = np.argmin(t, axis=1)                                          # first minimal index
+        idx[lo:lo + 1024] = j
+        dist[lo:lo + 1024] = t[np.arange(t.shape[0]), j]
+    return dist, idx
+
+
+def chamfer_metric(pred: np.ndarray, target: np.ndarray):
+    """util/metrics.py:37-51 Chamfer3D.update on bool [B,1,S,S,S]: (cd_sum, valid count)."""
+    cd, valid = 0.0, 0
+    for ip in range(pred.shape[0]):
+        pp = np.argwhere(pred[ip, 0]).astype(np.float32)
+        pt = np.argwhere(target[ip, 0]).astype(np.float32)
+        if pp.shape[0] == 0 or pt.shape[0] == 0:      # mean of an empty tensor is NaN and skipped (:48)
+            continue
+        d1, _ = chamfer_nn(pt, pp)
+        d2, _ = chamfer_nn(pp, pt)
+        cd += float(torch.from_numpy(d1).mean() + torch.from_numpy(d2).mean())
+        valid += 1
+    return cd, valid

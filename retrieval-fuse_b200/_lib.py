@@ -87,6 +87,12 @@ PROTOTYPES = {
                                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "rf_attention_features": (c_int, [c_void_p, c_void_p, c_void_p, _ptr4, _ptr4, _ptr4, _ptr4, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "rf_sobel_normals": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "rf_occupancy_counts": (c_int, [c_void_p, c_void_p, c_int, c_long, c_void_p, c_void_p]),
+    "rf_chamfer_nn": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "rf_ntxent_workspace_bytes": (c_size_t, [c_int]),
+    "rf_ntxent_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_float, c_float, c_int, c_void_p, c_void_p,
+                              c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -77,6 +77,12 @@ class PatchedSceneDataset(Dataset):
     def denormalize_target(self, target):
         return target * self.target_std + self.target_mean
 
+    def compute_normals(self, target):
+        """dataset/patched_scene_dataset.py:139-146: Sobel normals of a (denormalised) target batch [B,1,D,H,W] on the
+        GPU, padded with the target truncation value."""
+        from .. import ops
+        return ops.sobel_normals(target, self.scene_handler.target_trunc)
+
     def __getitem__(self, index):  # :117-137
         scene, ei, et = self.data[index]
         sin = self.scene_handler.get_scene_input(scene)

@@ -725,3 +725,71 @@ def attention_features(x, t, occ, theta, phi, E, normalize=True):
                                       _stream(x)), "rf_attention_features")
     _count(13)
     return xf, pf, oa.bool()
+
+
+# ---------------------------------------------------------------------------
+# target normals, contrastive loss, evaluation metrics
+# ---------------------------------------------------------------------------
+
+def sobel_normals(target, pad_val):
+    """dataset/patched_scene_dataset.py:139-146 compute_normals: [B,1,D,H,W] -> [B,3,D,H,W]."""
+    _forward_only(target)
+    target = _dev(target, name="target")
+    assert target.dim() == 5 and target.shape[1] == 1, "compute_normals expects [B,1,D,H,W]"
+    B, _, D, H, W = target.shape
+    out = torch.empty((B, 3, D, H, W), device=target.device, dtype=torch.float32)
+    with torch.cuda.device(target.device):
+        check(_lib.lib().rf_sobel_normals(target.data_ptr(), out.data_ptr(), B, D, H, W, float(pad_val), _stream(target)),
+              "rf_sobel_normals")
+    _count()
+    return out
+
+
+def occupancy_counts(pred, target):
+    """The integer sums of util/metrics.py: bool [B,1,S,S,S] x2 -> int64 [B,4] = (and, or, pred, target)."""
+    assert pred.shape == target.shape and pred.dtype == torch.bool and target.dtype == torch.bool
+    if not pred.is_cuda:
+        raise _lib.RfError("occupancy_counts: CPU tensors are not supported (no CPU fallback)")
+    pred, target = pred.contiguous(), target.contiguous()
+    B = pred.shape[0]
+    counts = torch.empty((B, 4), device=pred.device, dtype=torch.int64)
+    with torch.cuda.device(pred.device):
+        check(_lib.lib().rf_occupancy_counts(pred.data_ptr(), target.data_ptr(), B, pred[0].numel(), counts.data_ptr(),
+                                             _stream(pred)), "rf_occupancy_counts")
+    _count()
+    return counts
+
+
+def chamfer_nn(a, b):
+    """Nearest neighbour in b of every point of a: a [na,3], b [nb,3] fp32 -> (dist fp32 [na], idx int32 [na])."""
+    a = _dev(a, name="a")
+    b = _dev(b, name="b")
+    assert a.dim() == 2 and a.shape[1] == 3 and b.dim() == 2 and b.shape[1] == 3
+    dist = torch.empty(a.shape[0], device=a.device, dtype=torch.float32)
+    idx = torch.empty(a.shape[0], device=a.device, dtype=torch.int32)
+    with torch.cuda.device(a.device):
+        check(_lib.lib().rf_chamfer_nn(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], dist.data_ptr(), idx.data_ptr(),
+                                       _stream(a)), "rf_chamfer_nn")
+    _count()
+    return dist, idx
+
+
+def ntxent(zis, zjs, temperature, cosine=True, iou_matrix=None, sig_scale=80.0, sig_shift=-65.0):
+    """model/loss.py:48-69 NTXentLoss.forward -> scalar tensor."""
+    _forward_only(zis, zjs)
+    zis = _dev(zis, name="zis")
+    zjs = _dev(zjs, name="zjs")
+    assert zis.shape == zjs.shape and zis.dim() == 2
+    N, C = zis.shape
+    if iou_matrix is not None:
+        iou_matrix = _dev(iou_matrix, name="iou_matrix")
+        assert iou_matrix.shape == (2 * N, 2 * N)
+    L = _lib.lib()
+    ws = torch.empty(max(L.rf_ntxent_workspace_bytes(N), 16), device=zis.device, dtype=torch.uint8)
+    loss = torch.empty(1, device=zis.device, dtype=torch.float32)
+    with torch.cuda.device(zis.device):
+        check(L.rf_ntxent_fwd(zis.data_ptr(), zjs.data_ptr(), N, C, iou_matrix.data_ptr() if iou_matrix is not None else None,
+                              float(temperature), float(sig_scale), float(sig_shift), 1 if cosine else 0, loss.data_ptr(),
+                              ws.data_ptr(), ws.numel(), _stream(zis)), "rf_ntxent_fwd")
+    _count(3 if cosine else 2)
+    return loss[0]

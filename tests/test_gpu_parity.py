@@ -607,6 +607,84 @@ def test_compose_bit_exact(dev):
     assert np.array_equal(gotn.cpu().numpy(), ((want - d["target_mean"]) / d["target_std"]).astype(np.float32))
 
 
+# --------------------------------------------------------------------------- SURVEY 8f rows
+
+def test_ntxent_loss(dev):
+    """model/loss.py:48-69 on the GPU against the reference's own values (tests/golden/adjuncts.npz) and the oracle."""
+    from retrieval_fuse_b200.model.loss import NTXentLoss, compute_sliced_attn_nt_xent_loss
+    g = np.load(os.path.join(GOLD, "adjuncts.npz"))
+    for tag in ("cos", "dot", "cos_iou", "cos_big"):
+        temp, cosine = float(g[f"ntxent.{tag}.cfg"][0]), bool(g[f"ntxent.{tag}.cfg"][1])
+        iou = torch.from_numpy(g[f"ntxent.{tag}.iou"]).to(dev) if f"ntxent.{tag}.iou" in g else None
+        got = float(NTXentLoss(temp, cosine)(torch.from_numpy(g[f"ntxent.{tag}.zis"]).to(dev), torch.from_numpy(g[f"ntxent.{tag}.zjs"]).to(dev), iou))
+        want = float(g[f"ntxent.{tag}.loss"])
+        assert abs(got - want) <= 1e-5 * max(1.0, abs(want)), (tag, got, want)
+    # the sliced form of train_refinement.py:208-221, odd sizes, a slice without occupied rows, the 1280-row budget
+    gen = torch.Generator().manual_seed(5)
+    bs, split = 6, 300
+    fp, ft = torch.randn(bs * split, 32, generator=gen), torch.randn(bs * split, 32, generator=gen)
+    ft = 0.5 * fp + 0.5 * ft
+    occ = (torch.rand(bs * split, generator=gen) > 0.2).float()
+    occ[split:2 * split] = 0
+    want = float(O.sliced_attn_nt_xent(0.2, bs, fp, ft, occ))
+    got = float(compute_sliced_attn_nt_xent_loss(NTXentLoss(0.2, True), bs, fp.to(dev), ft.to(dev), occ.to(dev)))
+    assert abs(got - want) <= 1e-5 * abs(want), (got, want)
+
+
+def test_sobel_normals(dev):
+    """dataset/patched_scene_dataset.py:139-146 compute_normals: golden volume and a ragged random one."""
+    from retrieval_fuse_b200 import ops
+    g = np.load(os.path.join(GOLD, "adjuncts.npz"))
+    got = ops.sobel_normals(torch.from_numpy(g["normals.target"]).to(dev), float(g["normals.trunc"]))
+    close(got, g["normals.out"], tol=2e-5, what="compute_normals (golden)")
+    x = torch.randn(3, 1, 5, 9, 7, generator=torch.Generator().manual_seed(1))
+    close(ops.sobel_normals(x.to(dev), 0.75), O.compute_normals(x, 0.75), tol=2e-5, what="compute_normals (ragged)")
+    const = torch.full((1, 1, 6, 6, 6), 0.75)   # constant volume padded with the same value: zero gradient everywhere
+    assert float(ops.sobel_normals(const.to(dev), 0.75).abs().max()) == 0.0
+
+
+def test_occupancy_metrics_and_chamfer(dev):
+    """util/metrics.py IoU / Precision / Recall / Chamfer3D: integer sums and nearest-neighbour searches bit-exact
+    against the oracle, the metric values as torch computes them from those sums."""
+    from retrieval_fuse_b200 import ops
+    from retrieval_fuse_b200.util import metrics as M
+    rng = np.random.default_rng(8)
+    tgt = np.stack([O.synthetic_tsdf(40 + i, 64, 0.05) for i in range(5)])[:, None]
+    pred = tgt + rng.normal(size=tgt.shape).astype(np.float32) * 0.02
+    p, t = pred <= 0.05 * 0.75, tgt <= 0.05 * 0.75          # trainer/train_refinement.py:224-225
+    p[3] = False                                             # a sample with an empty prediction
+    p[4] = False
+    t[4] = False                                             # and one with an empty union
+    iou_sum, iou_n, prec, rec, counts = O.occupancy_metrics(p, t)
+    pd, td = torch.from_numpy(p).to(dev), torch.from_numpy(t).to(dev)
+    assert np.array_equal(ops.occupancy_counts(pd, td).cpu().numpy(), counts)
+    # unaligned / ragged volume: the byte tail path
+    pr, tr = rng.random((3, 1, 5, 7, 3)) > 0.5, rng.random((3, 1, 5, 7, 3)) > 0.5
+    assert np.array_equal(ops.occupancy_counts(torch.from_numpy(pr).to(dev), torch.from_numpy(tr).to(dev)).cpu().numpy(),
+                          O.occupancy_metrics(pr, tr)[4])
+    iou, pre, re_ = M.IoU(), M.Precision(), M.Recall()
+    for m in (iou, pre, re_):
+        m(pd, td)
+    assert iou.total == iou_n and abs(iou.iou_sum - iou_sum) <= 1e-6 * max(1.0, iou_sum)
+    assert abs(pre.precision_sum - prec) <= 1e-6 * max(1.0, prec) and abs(re_.recall_sum - rec) <= 1e-6 * max(1.0, rec)
+    # nearest neighbours on voxel coordinates (exact in fp32): bit-exact distances and indices, both directions
+    pp, pt = np.argwhere(p[0, 0]).astype(np.float32), np.argwhere(t[0, 0]).astype(np.float32)
+    d1, d2, i1, i2 = M.chamfer_3d_dist(torch.from_numpy(pt).to(dev), torch.from_numpy(pp).to(dev))
+    w1, wi1 = O.chamfer_nn(pt, pp)
+    w2, wi2 = O.chamfer_nn(pp, pt)
+    assert np.array_equal(d1.cpu().numpy(), w1) and np.array_equal(i1.cpu().numpy(), wi1)
+    assert np.array_equal(d2.cpu().numpy(), w2) and np.array_equal(i2.cpu().numpy(), wi2)
+    # general fp32 clouds, more points than one shared-memory tile
+    a, b = rng.normal(size=(3001, 3)).astype(np.float32), rng.normal(size=(5000, 3)).astype(np.float32)
+    d, i = ops.chamfer_nn(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev))
+    wd, wi = O.chamfer_nn(a, b)
+    assert np.array_equal(i.cpu().numpy(), wi) and float(np.abs(d.cpu().numpy() - wd).max()) <= 1e-6
+    ch = M.Chamfer3D()
+    ch(pd, td)
+    cd, valid = O.chamfer_metric(p, t)
+    assert ch.total == valid and abs(ch.cd_sum - cd) <= 1e-5 * max(1.0, cd)
+
+
 # --------------------------------------------------------------------------- end to end
 
 def test_hot_path_end_to_end_small(dev):

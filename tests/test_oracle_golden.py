@@ -138,3 +138,42 @@ def test_refine_full_forward():
     np.testing.assert_allclose(pred.numpy(), g["pred"], rtol=0, atol=TOL)
     # the output must not be degenerate, or 1e-4 would be vacuous
     assert float(np.abs(g["pred"]).max()) > 0.2 and float(g["pred"].std()) > 0.05
+
+
+# --------------------------------------------------------------------------- SURVEY 8f rows
+
+def test_oracle_adjuncts_against_reference_golden():
+    """NT-Xent (model/loss.py:48-69, produced by the reference's own class) and compute_normals
+    (dataset/patched_scene_dataset.py:139-146, Sobel literals parsed from the reference source) golden vectors."""
+    import numpy as np
+    import torch
+    from oracle import rf_oracle as O
+    g = np.load(os.path.join(GOLD, "adjuncts.npz"))
+    for tag in ("cos", "dot", "cos_iou", "cos_big"):
+        temp, cosine = float(g[f"ntxent.{tag}.cfg"][0]), bool(g[f"ntxent.{tag}.cfg"][1])
+        iou = torch.from_numpy(g[f"ntxent.{tag}.iou"]) if f"ntxent.{tag}.iou" in g else None
+        got = float(O.ntxent_loss(torch.from_numpy(g[f"ntxent.{tag}.zis"]), torch.from_numpy(g[f"ntxent.{tag}.zjs"]), temp, cosine, iou))
+        assert abs(got - float(g[f"ntxent.{tag}.loss"])) <= 1e-6 * max(1.0, abs(got)), tag
+    nrm = O.compute_normals(torch.from_numpy(g["normals.target"]), float(g["normals.trunc"])).numpy()
+    assert np.array_equal(nrm, g["normals.out"])
+    assert float(np.abs(np.linalg.norm(nrm, axis=1)).max()) <= 1.0 + 1e-6
+
+
+def test_oracle_metrics_small_cases():
+    """util/metrics.py semantics on hand-checkable volumes: empty union skipped by IoU, first-index ties and the
+    empty-cloud skip of Chamfer3D."""
+    import numpy as np
+    from oracle import rf_oracle as O
+    p = np.zeros((3, 1, 4, 4, 4), dtype=bool)
+    t = np.zeros((3, 1, 4, 4, 4), dtype=bool)
+    p[0, 0, 0, 0, :2] = True
+    t[0, 0, 0, 0, 1:4] = True          # inter 1, union 4
+    p[1, 0, 1, 1, 1] = True            # target empty: union 1, inter 0
+    iou_sum, iou_n, prec, rec, counts = O.occupancy_metrics(p, t)
+    assert counts.tolist() == [[1, 4, 2, 3], [0, 1, 1, 0], [0, 0, 0, 0]]
+    assert iou_n == 2 and abs(iou_sum - 1 / (4 + 1e-5)) < 1e-6
+    assert abs(prec - (1 / (2 + 1e-5))) < 1e-6 and abs(rec - (1 / (3 + 1e-5))) < 1e-6
+    d, i = O.chamfer_nn(np.array([[0, 0, 0], [5, 5, 5]], dtype=np.float32), np.array([[1, 0, 0], [0, 1, 0], [5, 5, 4]], dtype=np.float32))
+    assert d.tolist() == [1.0, 1.0] and i.tolist() == [0, 2]   # tie -> first index
+    cd, valid = O.chamfer_metric(p, t)
+    assert valid == 1 and cd > 0
