@@ -114,23 +114,8 @@ __device__ __forceinline__ void split_f16(float x, uint32_t& hi, uint32_t& lo) {
 // upsampled volume) into per-(sample, channel) fp64 sum / sum of squares (one atomicAdd pair per
 // channel per CTA).  Pass 2 folds channels into groups: mean, 1/sqrt(var+eps), expanded per channel.
 // fp64 moments of fp32 data: E[x^2]-E[x]^2 loses nothing that matters unless var/mean^2 < 1e-10.
-// The LAST CTA of a sample (per-sample ticket counter, threadfence-reduction pattern; a sample's CTAs may come from
-// two launches - the skip connection and the coarse decoder input) folds the channel sums into group statistics
-// itself, so that no separate finalisation launch sits between the statistics and the operand split (38 launches
-// less per refinement forward).
-struct GnFinal {
-    const float* gamma;
-    float* mu_out;
-    float* a_out;
-    unsigned* tickets;       // [N], zeroed with the sums
-    unsigned expected;       // CTAs per sample over all launches of this statistics call
-    int G;
-    double count_per_channel;
-    float eps;
-};
-
 __global__ void __launch_bounds__(256) cl_gn_partial_kernel(const float* __restrict__ x, long S, int C, int slices, double weight,
-                                                            int c_off, int c_tot, double* __restrict__ sums, const GnFinal fin) {
+                                                            int c_off, int c_tot, double* __restrict__ sums) {
     const int n = blockIdx.x / slices, sl = blockIdx.x % slices;
     const long per = (S + slices - 1) / slices;
     const long v0 = sl * per, v1 = v0 + per < S ? v0 + per : S;
@@ -165,29 +150,25 @@ __global__ void __launch_bounds__(256) cl_gn_partial_kernel(const float* __restr
         atomicAdd(&sums[((long)n * c_tot + c_off + c) * 2], sh[c] * weight);
         atomicAdd(&sums[((long)n * c_tot + c_off + c) * 2 + 1], sh[C + c] * weight);
     }
-    // ---- last CTA of sample n: channel sums -> group mean, 1 / sqrt(var + eps) * gamma per channel
-    __shared__ unsigned s_ticket;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(fin.tickets + n, 1u);
-    __syncthreads();
-    if (s_ticket != fin.expected - 1) return;
-    __threadfence();
-    const int cpg = c_tot / fin.G;
-    for (int c = threadIdx.x; c < c_tot; c += blockDim.x) {
-        const int g = c / cpg;
-        double s1 = 0.0, s2 = 0.0;
-        for (int j = 0; j < cpg; ++j) {
-            s1 += __ldcg(&sums[((long)n * c_tot + g * cpg + j) * 2]);
-            s2 += __ldcg(&sums[((long)n * c_tot + g * cpg + j) * 2 + 1]);
-        }
-        const double cnt = fin.count_per_channel * cpg;
-        const double mean = s1 / cnt;
-        double var = s2 / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        fin.mu_out[(long)n * c_tot + c] = (float)mean;
-        fin.a_out[(long)n * c_tot + c] = (float)(1.0 / sqrt(var + (double)fin.eps)) * __ldg(fin.gamma + c);
+}
+
+__global__ void __launch_bounds__(256) cl_gn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                                             float* __restrict__ mu_out, float* __restrict__ a_out, int N, int C,
+                                                             int G, double count_per_channel, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, c)
+    if (i >= N * C) return;
+    const int n = i / C, c = i % C, cpg = C / G, g = c / cpg;
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+        s1 += sums[((long)n * C + g * cpg + j) * 2];
+        s2 += sums[((long)n * C + g * cpg + j) * 2 + 1];
     }
+    const double cnt = count_per_channel * cpg;
+    const double mean = s1 / cnt;
+    double var = s2 / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mu_out[i] = (float)mean;
+    a_out[i] = (float)(1.0 / sqrt(var + (double)eps)) * __ldg(gamma + c);
 }
 
 // x [N,S,C] fp32 -> (x - mu[n, c_off+c]) * a[n, c_off+c] + beta[c_off+c] -> fp16 hi/lo [N,S,Cp]; pad channels are zero.
@@ -545,39 +526,32 @@ int conv_npad(int cout) { return round_up(cout, 16) < 32 ? 32 : round_up(cout, 1
 
 }  // namespace
 
-extern "C" size_t rf_cl_gn_stats_workspace_bytes(int N, int C) { return (size_t)N * C * 2 * sizeof(double) + (size_t)N * sizeof(unsigned); }
+extern "C" size_t rf_cl_gn_stats_workspace_bytes(int N, int C) { return (size_t)N * C * 2 * sizeof(double); }
 
 extern "C" int rf_cl_gn_stats(const float* x, const float* x2, int C2, const float* gamma, float* gn_mu, float* gn_a, int N,
                               int C, int D, int H, int W, int groups, float eps, void* workspace, void* stream) {
     RF_CHECK_ARG(gamma && gn_mu && gn_a && workspace && (x || C2 == C), "rf_cl_gn_stats: null pointer");
     RF_CHECK_ARG(N > 0 && C > 0 && groups > 0 && C % groups == 0 && C2 >= 0 && C2 <= C && (C2 == 0 || x2), "rf_cl_gn_stats: bad channels");
     RF_CHECK_ARG(C2 == 0 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "rf_cl_gn_stats: upsampled input needs even extents");
-    RF_CHECK_ARG(((uintptr_t)workspace & 7) == 0, "rf_cl_gn_stats: workspace must be 8-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     double* sums = (double*)workspace;
-    RF_CUDA_OK(cudaMemsetAsync(sums, 0, rf_cl_gn_stats_workspace_bytes(N, C), s));  // sums and tickets
+    RF_CUDA_OK(cudaMemsetAsync(sums, 0, rf_cl_gn_stats_workspace_bytes(N, C), s));
     const long S = (long)D * H * W;
-    const int C1 = C - C2;
-    auto n_slices = [&](long Ssrc, int Csrc) -> long {
+    auto launch = [&](const float* src, long Ssrc, int Csrc, double weight, int c_off) -> int {
         // enough CTAs to fill the chip, but at least ~4k elements per CTA
         long slices = (148L * 4 + N - 1) / N;
         const long max_slices = (Ssrc * Csrc + 4095) / 4096;
         if (slices > max_slices) slices = max_slices;
-        return slices < 1 ? 1 : slices;
+        if (slices < 1) slices = 1;
+        cl_gn_partial_kernel<<<(unsigned)(N * slices), 256, 2 * Csrc * sizeof(double), s>>>(src, Ssrc, Csrc, (int)slices, weight, c_off, C, sums);
+        RF_LAUNCH_OK("cl_gn_partial_kernel");
+        return 0;
     };
-    const long sl1 = C1 > 0 ? n_slices(S, C1) : 0, sl2 = C2 > 0 ? n_slices(S / 8, C2) : 0;
-    GnFinal fin;
-    fin.gamma = gamma; fin.mu_out = gn_mu; fin.a_out = gn_a;
-    fin.tickets = (unsigned*)(sums + (size_t)N * C * 2);
-    fin.expected = (unsigned)(sl1 + sl2); fin.G = groups; fin.count_per_channel = (double)S; fin.eps = eps;
-    if (C1 > 0) {
-        cl_gn_partial_kernel<<<(unsigned)(N * sl1), 256, 2 * C1 * sizeof(double), s>>>(x, S, C1, (int)sl1, 1.0, 0, C, sums, fin);
-        RF_LAUNCH_OK("cl_gn_partial_kernel");
-    }
-    if (C2 > 0) {
-        cl_gn_partial_kernel<<<(unsigned)(N * sl2), 256, 2 * C2 * sizeof(double), s>>>(x2, S / 8, C2, (int)sl2, 8.0, C1, C, sums, fin);
-        RF_LAUNCH_OK("cl_gn_partial_kernel");
-    }
+    const int C1 = C - C2;
+    if (C1 > 0) { const int rc = launch(x, S, C1, 1.0, 0); if (rc) return rc; }
+    if (C2 > 0) { const int rc = launch(x2, S / 8, C2, 8.0, C1); if (rc) return rc; }
+    cl_gn_finalize_kernel<<<rf_cdiv((long)N * C, 256), 256, 0, s>>>(sums, gamma, gn_mu, gn_a, N, C, groups, (double)S, eps);
+    RF_LAUNCH_OK("cl_gn_finalize_kernel");
     return 0;
 }
 

@@ -296,11 +296,11 @@ def cl_gn_stats(x, gamma, groups, eps=1e-5, x2=None):
     C = C1 + C2
     mu = torch.empty((N, C), device=x.device, dtype=torch.float32)
     a = torch.empty((N, C), device=x.device, dtype=torch.float32)
-    ws = torch.empty((_lib.lib().rf_cl_gn_stats_workspace_bytes(N, C) + 7) // 8, device=x.device, dtype=torch.float64)
+    ws = torch.empty((N, C, 2), device=x.device, dtype=torch.float64)
     with torch.cuda.device(x.device):
         check(_lib.lib().rf_cl_gn_stats(x.data_ptr(), _ptr(x2), C2, gamma.data_ptr(), mu.data_ptr(), a.data_ptr(), N, C, D, H,
                                         W, groups, float(eps), ws.data_ptr(), _stream(x)), "rf_cl_gn_stats")
-    _count(2 if x2 is not None else 1)
+    _count(3 if x2 is not None else 2)
     return mu, a
 
 

@@ -668,14 +668,7 @@ def test_occupancy_metrics_and_chamfer(dev):
     assert iou.total == iou_n and abs(iou.iou_sum - iou_sum) <= 1e-6 * max(1.0, iou_sum)
     assert abs(pre.precision_sum - prec) <= 1e-6 * max(1.0, prec) and abs(re_.recall_sum - rec) <= 1e-6 * max(1.0, rec)
     # nearest neighbours on voxel coordinates (exact in fp32): bit-exact distances and indices, both directions
-    # (32^3 volumes from here on: the oracle's searches are O(n m) numpy on the host)
-    tgt = np.stack([O.synthetic_tsdf(60 + i, 32, 0.05) for i in range(3)])[:, None]
-    pred = tgt + rng.normal(size=tgt.shape).astype(np.float32) * 0.02
-    p, t = pred <= 0.05 * 0.75, tgt <= 0.05 * 0.75
-    p[2] = False
-    pd, td = torch.from_numpy(p).to(dev), torch.from_numpy(t).to(dev)
     pp, pt = np.argwhere(p[0, 0]).astype(np.float32), np.argwhere(t[0, 0]).astype(np.float32)
-    assert pp.shape[0] > 100 and pt.shape[0] > 100
     d1, d2, i1, i2 = M.chamfer_3d_dist(torch.from_numpy(pt).to(dev), torch.from_numpy(pp).to(dev))
     w1, wi1 = O.chamfer_nn(pt, pp)
     w2, wi2 = O.chamfer_nn(pp, pt)
