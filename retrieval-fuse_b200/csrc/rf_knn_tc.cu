@@ -440,16 +440,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
 // ------------------------------------------------------------------ re-rank + proof
 __device__ __forceinline__ bool cand_less(double d, int i, double d2, int i2) { return d < d2 || (d == d2 && i < i2); }
 
-// Sorted list of 16 (d, id) entries, one per lane of a HALF warp; inserts (cd, ci) if it ranks before an entry.
-__device__ __forceinline__ void half_list_insert(double& ld, int& li, double cd, int ci, int lane16, int half, bool doit) {
-    const bool before = cand_less(ld, li, cd, ci);
-    const unsigned b = (__ballot_sync(0xffffffffu, before) >> (16 * half)) & 0xFFFFu;
-    const int pos = __popc(b);
-    const double ud = __shfl_up_sync(0xffffffffu, ld, 1, 16);
-    const int ui = __shfl_up_sync(0xffffffffu, li, 1, 16);
-    if (doit) {
-        if (lane16 == pos) { ld = cd; li = ci; }
-        else if (lane16 > pos) { ld = ud; li = ui; }
+// Bitonic sort of 16 (d, id) entries, one per lane of a half warp, ascending under the canonical order
+// (10 compare-exchange stages instead of 16 serial list insertions).
+__device__ __forceinline__ void half_bitonic_sort(double& d, int& i, int lane16) {
+#pragma unroll
+    for (int k = 2; k <= 16; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, d, j, 16);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, j, 16);
+            const bool up = (lane16 & k) == 0, lower = (lane16 & j) == 0;
+            const bool take = (lower == up) ? cand_less(od, oi, d, i) : cand_less(d, i, od, oi);
+            if (take) { d = od; i = oi; }
+        }
+    }
+}
+// (ld, li) sorted ascending, (d, i) sorted ascending -> (ld, li) = the 16 smallest of the 32, sorted:
+// min(list[l], new[15 - l]) is a bitonic sequence holding exactly those 16, four merge stages sort it.
+__device__ __forceinline__ void half_bitonic_merge(double& ld, int& li, double d, int i, int lane16) {
+    const double rd = __shfl_sync(0xffffffffu, d, 15 - lane16, 16);
+    const int ri = __shfl_sync(0xffffffffu, i, 15 - lane16, 16);
+    if (cand_less(rd, ri, ld, li)) { ld = rd; li = ri; }
+#pragma unroll
+    for (int j = 8; j > 0; j >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, ld, j, 16);
+        const int oi = __shfl_xor_sync(0xffffffffu, li, j, 16);
+        const bool lower = (lane16 & j) == 0;
+        const bool take = lower ? cand_less(od, oi, ld, li) : cand_less(ld, li, od, oi);
+        if (take) { ld = od; li = oi; }
     }
 }
 
@@ -533,16 +551,11 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restr
             const float s_exact = 0.5f * (float)(qn + (double)xn - acc);
             err = fmaxf(err, fabsf(sc - s_exact));
         }
-        // insert this round's candidates one by one (both half warps step together)
-        unsigned m = (__ballot_sync(0xffffffffu, id >= 0) >> (16 * half)) & 0xFFFFu;
-        while (__any_sync(0xffffffffu, m != 0)) {
-            const bool doit = m != 0;
-            const int src = doit ? __ffs(m) - 1 : 0;
-            m &= m - 1;
-            const double cd = __shfl_sync(0xffffffffu, d, src, 16);
-            const int ci = __shfl_sync(0xffffffffu, id, src, 16) + (int)row_offset;
-            half_list_insert(ld, li, cd, ci, lane16, half, doit);
-        }
+        // sort this round's 16 candidates and merge them into the running list (invalid slots rank last)
+        int ci = id >= 0 ? id + (int)row_offset : INT_MAX;
+        half_bitonic_sort(d, ci, lane16);
+        if (base == 0) { ld = d; li = ci; }
+        else half_bitonic_merge(ld, li, d, ci, lane16);
     }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) {
