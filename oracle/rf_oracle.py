@@ -938,16 +938,17 @@ def chamfer_nn(a: np.ndarray, b: np.ndarray):
     b = np.ascontiguousarray(b, dtype=np.float32)
     dist = np.empty(a.shape[0], dtype=np.float32)
     idx = np.empty(a.shape[0], dtype=np.int32)
-    for lo in range(0, a.shape[0], 1024):
-        aa = a[lo:lo + 1024, None, :]
+    step = 128  # small blocks: the float64 temporaries stay cache-sized
+    for lo in range(0, a.shape[0], step):
+        aa = a[lo:lo + step, None, :]
         df = (b[None, :, :] - aa).astype(np.float32)                      # fp32 differences
         dd = df.astype(np.float64)
         t = (dd[..., 0] * dd[..., 0]).astype(np.float32)                  # __fmul_rn
         t = (dd[..., 1] * dd[..., 1] + t.astype(np.float64)).astype(np.float32)
         t = (dd[..., 2] * dd[..., 2] + t.astype(np.float64)).astype(np.float32)
         j = np.argmin(t, axis=1)                                          # first minimal index
-        idx[lo:lo + 1024] = j
-        dist[lo:lo + 1024] = t[np.arange(t.shape[0]), j]
+        idx[lo:lo + step] = j
+        dist[lo:lo + step] = t[np.arange(t.shape[0]), j]
     return dist, idx
 
 
