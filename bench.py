@@ -88,8 +88,44 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.stop_flag = None, False
+
+    def _nvml_start(self):
+        """NVML in-process, one sample every ~3 ms (nvidia-smi -lms delivers its first row after ~100 ms, longer
+        than the timed region of the refine workload)."""
+        import pynvml as N
+        N.nvmlInit()
+        h = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = N.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)  # fails here, not in the thread, if unsupported
+
+        def loop():
+            while not self.stop_flag:
+                try:
+                    sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                    r = int(get_reasons(h))
+                    self.rows.append([str(sm), str(mx)] + ["Active" if r & bits[k] else "Not Active" for k in
+                                                           ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+                except Exception:
+                    pass
+                time.sleep(0.003)
+        self.nvml = threading.Thread(target=loop, daemon=True)
+        self.nvml.start()
 
     def start(self):
+        try:
+            self._nvml_start()
+            return
+        except Exception as e:
+            log("[clocks] NVML sampler unavailable, using nvidia-smi:", e)
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -105,13 +141,17 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.nvml.join(timeout=1)
+        elif self.proc is None:
             return None
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons = [], [], set()
         for r in self.rows:
             try:
