@@ -1,8 +1,11 @@
 // Patch fold / unfold / pad-unfold / recompose / compose / pool / upsample:
-// pure re-indexing kernels, HBM-bound.  Each thread moves one contiguous run
-// of the innermost axis so that both the read and the write side coalesce as
-// far as the permutation allows; grids are sized in multiples of the SM count
-// (rf_grid_1d) and walk the output with a grid-stride loop.
+// pure re-indexing kernels, HBM-bound.  The fast paths move one float4 per
+// thread with consecutive threads walking the contiguous (patch) side, so every
+// warp access there is one 512-byte segment and the permuted side is touched in
+// whole 32-byte sectors; flat indices are decomposed with an exact
+// multiply-high division (FastDiv) or once per thread (pad-unfold); E = 2 is
+// transposed through shared memory.  Grids are sized in multiples of the SM
+// count (rf_grid_1d).  DESIGN.md 4.4 has the measurements behind these choices.
 #include "rf_common.cuh"
 
 // Exact division of a 32-bit index by a run-time divisor with one 64-bit high multiply: m = ceil(2^64 / d) gives
