@@ -177,3 +177,67 @@ def test_oracle_metrics_small_cases():
     assert d.tolist() == [1.0, 1.0] and i.tolist() == [0, 2]   # tie -> first index
     cd, valid = O.chamfer_metric(p, t)
     assert valid == 1 and cd > 0
+
+
+# --------------------------------------------------------------------------- properties of the oracle (hypothesis)
+
+def test_oracle_reindex_properties():
+    """Random shapes: the oracle's Unfold3DPadStride equals torch's pad + unfold (the reference's own formulation,
+    model/attention.py:200-203), Fold3D inverts Unfold3D, Patcher.recompose inverts Patcher when the patches cover
+    the padded volume."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 3), st.integers(1, 3), st.integers(1, 4), st.integers(1, 4), st.integers(0, 3), st.integers(0, 2 ** 31 - 1))
+    def prop(B, C_, cnt, stride, pad, seed):
+        rng = np.random.default_rng(seed)
+        kern = stride + int(rng.integers(0, 3))                      # overlapping or not
+        size = (cnt - 1) * stride + kern - 2 * pad
+        if size < 1:
+            return
+        x = rng.normal(size=(B, C_, size, size, size)).astype(np.float32)
+        got = O.unfold3d_pad_stride(x, kern, pad, -2.5, stride)
+        xt = torch.nn.functional.pad(torch.from_numpy(x), (pad,) * 6, value=-2.5)
+        w = xt.unfold(2, kern, stride).unfold(3, kern, stride).unfold(4, kern, stride)
+        want = w.permute(0, 2, 3, 4, 1, 5, 6, 7).reshape(-1, C_, kern, kern, kern).numpy()
+        assert np.array_equal(got.reshape(want.shape), want)
+    prop()
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(1, 3), st.integers(1, 5), st.integers(1, 4), st.sampled_from([1, 2, 3, 4]), st.integers(0, 2 ** 31 - 1))
+    def inv(B, C_, R, E, seed):
+        x = np.random.default_rng(seed).normal(size=(B, C_, R * E, R * E, R * E)).astype(np.float32)
+        u = O.unfold3d(x, E)
+        assert u.shape == (B * R ** 3, C_, E, E, E)
+        assert np.array_equal(O.fold3d(u, R, E, C_), x)
+    inv()
+
+
+def test_oracle_knn_and_demotion_properties():
+    """Random small banks: the C oracle equals a brute-force float64 sort under (d, id); demotion is a stable
+    partition (util/retrieval.py:94-97) that keeps K entries and never reorders inside the two classes."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=30, deadline=None)
+    @given(st.integers(1, 60), st.integers(1, 12), st.integers(1, 8), st.integers(0, 2 ** 31 - 1))
+    def prop(N, Q, k, seed):
+        rng = np.random.default_rng(seed)
+        k = min(k, N)
+        db = rng.integers(-2, 3, size=(N, 64)).astype(np.float32)        # small integers: many exact ties
+        q = rng.integers(-2, 3, size=(Q, 64)).astype(np.float32)
+        idx, dist = O.knn_exact(db, q, k)
+        d = ((q[:, None, :].astype(np.float64) - db[None].astype(np.float64)) ** 2).sum(-1)
+        for i in range(Q):
+            order = sorted(range(N), key=lambda j: (d[i, j], j))[:k]
+            assert idx[i].tolist() == order
+            assert np.array_equal(dist[i], d[i, order].astype(np.float32))
+        if k >= 2:
+            K = k // 2
+            row_scene = rng.integers(0, 3, size=N)
+            qs = rng.integers(-1, 3, size=Q)
+            di, dd = O.demote_same_scene(idx, dist, row_scene, qs, K)
+            for i in range(Q):
+                other = [j for j in idx[i] if row_scene[j] != qs[i]]
+                same = [j for j in idx[i] if row_scene[j] == qs[i]]
+                assert di[i].tolist() == (other + same)[:K]
+    prop()
