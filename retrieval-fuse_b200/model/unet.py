@@ -16,6 +16,25 @@ from ._base import RfModule
 USE_TENSOR_CORES = True
 # 3x3x3 layers: shifted-window kernel (rf_tc_conv_halo.cu) instead of the gathering implicit GEMM (rf_tc_conv.cu)
 USE_HALO_CONV = True
+# EXPERIMENTAL, OFF by default (tools/wpack_formulation.py): run small-channel 3x3x3 layers through the
+# shifted-window kernel on W-packed views [N,D,H,W/Bw,Bw*C] with Toeplitz-expanded weights.  The identity is verified on
+# the CPU; the kernel has not been measured on these shapes yet, so nothing selects this path unless W_PACK maps
+# (in_channels, out_channels) -> Bw, e.g. {(1, 8): 8, (8, 16): 4}.
+W_PACK = {}
+
+
+def wpack_weights(w, Bw):
+    """Conv3d weight [Cout, Cin, 3,3,3] -> [Bw*Cout, Bw*Cin, 3,3,3] with
+    W'[(dw,co), (iw,ci), kd, kh, kw''] = W[co, ci, kd, kh, kw],  Bw * (kw'' - 1) + iw = dw + kw - 1."""
+    import torch
+    Cout, Cin = w.shape[:2]
+    wp = torch.zeros(Bw * Cout, Bw * Cin, 3, 3, 3, dtype=w.dtype, device=w.device)
+    for dw in range(Bw):
+        for kw in range(3):
+            s = dw + kw - 1
+            kwp, iw = s // Bw + 1, s % Bw
+            wp[dw * Cout:(dw + 1) * Cout, iw * Cin:(iw + 1) * Cin, :, :, kwp] += w[:, :, :, :, kw]
+    return wp
 
 
 def number_of_features_per_level(init_channel_number, num_levels):
@@ -77,6 +96,22 @@ class SingleConv(RfModule):
             mu, a = ops.cl_gn_stats(x2, g.weight, g.num_groups, g.eps)
         else:
             mu, a = ops.cl_gn_stats(x, g.weight, g.num_groups, g.eps, x2=x2)
+        Bw = W_PACK.get((c1, self.out_channels), 0) if (c2 == 0 and not out_ncdhw and self.conv.bias is None) else 0
+        if Bw > 1 and x.shape[3] % Bw == 0 and ops.tc_conv_halo_supported(x.shape[0], x.shape[1], x.shape[2], x.shape[3] // Bw,
+                                                                            Bw * self.out_channels, Bw * c1, 0):
+            # W-packed view: Bw consecutive voxels along w become channels on both sides (pure reinterpretations of the
+            # channels-last buffers); the per-channel GroupNorm terms repeat Bw times, the weights expand (Toeplitz)
+            N, D, H, W = x.shape[:4]
+            if not hasattr(self, "_halo_planes_wp"):
+                object.__setattr__(self, "_halo_planes_wp", {})
+            split = ops.cl_norm_split_halo(x.view(N, D, H, W // Bw, Bw * c1), None,
+                                           (mu.repeat(1, Bw).contiguous(), a.repeat(1, Bw).contiguous(), g.bias.repeat(Bw).contiguous()),
+                                           scale=ops.ACT_SCALE_GN, buffers=self._halo_planes_wp)
+            img, sw = self._wcache.derived(("halo_wpack", Bw, c1), [self.conv.weight],
+                                           lambda w: ops.tc_conv_halo_weight_image(wpack_weights(w.detach(), Bw).contiguous(), Bw * c1, 0))
+            y = ops.tc_conv3d_halo(split, img, None, Bw * self.out_channels, act=self.act, slope=0.1,
+                                   out_scale=1.0 / (ops.ACT_SCALE_GN * sw))
+            return y.view(N, D, H, W, self.out_channels)
         if c1 == 1 and c2 == 0 and self.out_channels <= 32 and not out_ncdhw:
             # first layer (single input channel): direct convolution with the normalisation on the fly
             return ops.conv3d_cin1_cl(x, self.conv.weight, self.conv.bias, (mu, a, g.bias), ks=3, stride=1, pad=1,

@@ -175,3 +175,19 @@ def test_fixed_divisor_division_is_ieee(tmp_path):
     subprocess.check_call(["gcc"] + flags + ["-o", exe, src, "-lm"])
     out = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and " bad 0" in out.stdout, out.stdout
+
+
+def test_wpack_weight_expansion_identity():
+    """The experimental W-packing of small-channel 3x3x3 layers (model.unet.W_PACK, off by default): conv3d on the
+    packed view with the expanded weights equals the original convolution (CPU, float64)."""
+    from retrieval_fuse_b200.model.unet import W_PACK, wpack_weights
+    assert W_PACK == {}, "the experimental path must stay off by default"
+    g = torch.Generator().manual_seed(3)
+    for (cin, cout, W, Bw) in [(1, 8, 16, 8), (8, 16, 16, 4), (3, 5, 12, 2)]:
+        x = torch.randn(2, cin, 5, 6, W, generator=g, dtype=torch.float64)
+        w = torch.randn(cout, cin, 3, 3, 3, generator=g, dtype=torch.float64)
+        want = torch.nn.functional.conv3d(x, w, padding=1).permute(0, 2, 3, 4, 1)
+        xp = x.permute(0, 2, 3, 4, 1).contiguous().view(2, 5, 6, W // Bw, Bw * cin).permute(0, 4, 1, 2, 3)
+        yp = torch.nn.functional.conv3d(xp, wpack_weights(w, Bw), padding=1)
+        got = yp.permute(0, 2, 3, 4, 1).contiguous().view(2, 5, 6, W, cout)
+        assert float((got - want).abs().max()) < 1e-12

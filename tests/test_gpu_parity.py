@@ -607,6 +607,24 @@ def test_compose_bit_exact(dev):
     assert np.array_equal(gotn.cpu().numpy(), ((want - d["target_mean"]) / d["target_std"]).astype(np.float32))
 
 
+@pytest.mark.skipif(not os.environ.get("RF_EXPERIMENTAL"), reason="round-2 experiment (model.unet.W_PACK), not yet verified on hardware")
+def test_w_packed_small_channel_layers(dev):
+    """RF_EXPERIMENTAL=1: the retrieval U-Net with its 1->8 and 8->16 layers routed through the W-packed
+    shifted-window path must give the same features as the default path."""
+    from retrieval_fuse_b200.model import unet as U
+    from retrieval_fuse_b200.model import get_retrieval_backbone
+    m, _ = load(get_retrieval_backbone(dict(nf=16, retrieval_fmaps=16, retrieval_num_level=4, layer_order="gcr")),
+                O.retrieval_backbone_shapes(16, 16, 4), dev)
+    x = C.rnd("wpack.x", (24, 1, 16, 16, 16)).to(dev)
+    want = m(x)
+    try:
+        U.W_PACK.update({(1, 8): 8, (8, 16): 4})
+        got = m(x)
+    finally:
+        U.W_PACK.clear()
+    close(got, want, tol=2e-5, rel_to_max=True, what="W-packed layers vs default path")
+
+
 # --------------------------------------------------------------------------- SURVEY 8f rows
 
 def test_ntxent_loss(dev):
