@@ -242,7 +242,9 @@ int rf_knn_demote_rows(const int* idx2k, const double* d2k, const float* meta, c
  *   (unpadded destination extents inside a chunk); scene_store [S,sx,sy,sz]
  *   unpadded train targets; out [n_chunks,K,cx,cy,cz];
  *   out[c,k,dst] = scene_store[row.scene][x0:x1,y0:y1,z0:z1] * ratio, or
- *   trunc * ratio when row.scene < 0 (the sentinel row, :160-161).
+ *   trunc * ratio when row.scene == -1 (the sentinel row, :160-161); a row with
+ *   scene < -1 leaves its destination block untouched (cells nobody owns when
+ *   the host has resolved overlapping patches, :156, into single-owner cells).
  *   norm_div != 0 additionally maps v -> (v - norm_sub) / norm_div, the
  *   dataloader's retrieval normalisation (patched_scene_dataset.py:133). */
 int rf_compose_gather(const float* rows, const int* dst_extents, const float* scene_store, float* out, int n_chunks,

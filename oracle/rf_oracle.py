@@ -16,13 +16,23 @@ Pinning status
   only), drives them with the seeded inputs and synthetic weights defined
   below, and commits the outputs under `tests/golden/`.
   `tests/test_oracle_golden.py` checks this restatement against those files.
-* kNN + demotion + compose + database rows: PARITY UNPINNED.  The reference
-  calls `pyflann` (un-vendored, unpinned, approximate randomized kd-forest;
-  util/retrieval.py:8,50,92), which is absent here and has no golden vectors
-  in the tree.  The oracle therefore defines the thing FLANN approximates -
-  exact squared-L2 kNN under the canonical rule stated at `knn_exact` - and
-  follows the reference's call sites for everything around it
-  (util/retrieval.py:79-105 demotion, :21-45 database rows, :145-164 compose).
+* patch enumeration (a1), database rows + sentinel (a10), fetch-2K / demotion /
+  mapping rows (a11), compose incl. the overlapping-stride rule (a12): PINNED.
+  `tests/golden/make_golden_retrieval.py` imports the reference's own
+  `util/retrieval.py`, `dataset/scene.py`, `dataset/patched_scene_dataset.py`
+  unmodified (pyflann, trimesh, pyrender, marching_cubes, torchmetrics stubbed in
+  sys.modules) and executes SceneHandler / PatchedSceneDataset,
+  create_dictionary, get_zero_patch_entry, flann_knn_worker (with and without
+  ignore_patches_from_source) and create_retrieval_from_mapping on a tiny
+  on-disk dataset; `tests/test_oracle_retrieval_golden.py` checks this
+  restatement against the committed outputs, bit-exact.
+* the nearest-neighbour SEARCH itself: the reference calls `pyflann`
+  (un-vendored, unpinned, approximate randomized kd-forest;
+  util/retrieval.py:8,50,92), absent here, no golden vectors in the tree.  The
+  golden run replaces `FLANN.nn_index` by the thing it approximates - exact
+  squared-L2 neighbours under the canonical rule stated at `knn_exact`
+  (written out independently in the golden script) - so every line of the
+  reference AROUND the search is pinned, and the search is pinned to that rule.
 
 Every function cites the reference file:line it follows.
 """
@@ -262,6 +272,37 @@ def chunk_patches(chunk: np.ndarray, patch_size: int, patch_context: int, patch_
     ext = get_extents_for_size(chunk.shape, patch_size, patch_context, patch_stride)
     out = np.stack([padded[e[0]:e[1], e[2]:e[3], e[4]:e[5]] for e in ext])[:, None]
     return ((out - mean) / std).astype(np.float32)
+
+
+def patch_occupancy(target_padded: np.ndarray, extent, target_voxel_size) -> int:
+    """dataset/scene.py:149-151 calculate_occupancy_for_name: voxels of the PADDED patch extent that lie within
+    0.75 * 2 voxels of the surface (the dataset keeps patches with occupancy > occupancy_threshold,
+    patched_scene_dataset.py:28).  target_voxel_size is the float16-rounded voxel size (scene.py:31)."""
+    e = extent
+    return int((target_padded[e[0]:e[1], e[2]:e[3], e[4]:e[5]] <= 0.75 * 2 * target_voxel_size).sum())
+
+
+def scene_patch_table(inp: np.ndarray, tgt: np.ndarray, d: dict, occupancy_threshold):
+    """What PatchedSceneDataset enumerates for one scene (patched_scene_dataset.py:24-29,117-128): inp / tgt are the
+    arrays stored on disk (fp16), d the dataset config.  Loading casts through float16 and pads by the context with
+    the truncation value (dataset/scene.py:60-61,92-95).  Returns (input extents, target extents (padded coords),
+    normalised input patches, normalised target patches, occupancies) of the KEPT patches, in dataset order."""
+    itr, ttr = np.float32(f16_trunc(d["voxel_size_input"])), np.float32(f16_trunc(d["voxel_size_target"]))
+    vox_t = np.float16(d["voxel_size_target"]).astype(np.float32)
+    pin = np.pad(inp.astype(np.float16), d["patch_context_input"], mode="constant", constant_values=itr).astype(np.float32)
+    ptg = np.pad(tgt.astype(np.float32), d["patch_context_target"], mode="constant", constant_values=ttr)
+    size_t = list(tgt.shape)
+    sf = d["patch_size_target"] / d["patch_size_input"]
+    size_i = [int(s / sf) for s in size_t]
+    stride_i = int(d["patch_stride"] * d["patch_size_input"] / d["patch_size_target"])
+    et = get_extents_for_size(size_t, d["patch_size_target"], d["patch_context_target"], d["patch_stride"])
+    ei = get_extents_for_size(size_i, d["patch_size_input"], d["patch_context_input"], stride_i)
+    occ = np.array([patch_occupancy(ptg, e, vox_t) for e in et])
+    keep = np.nonzero(occ > occupancy_threshold)[0]
+    cut = lambda a, e: a[e[0]:e[1], e[2]:e[3], e[4]:e[5]]
+    p_in = np.stack([(cut(pin, ei[i])[None] - d["input_mean"]) / d["input_std"] for i in keep]).astype(np.float32)
+    p_tg = np.stack([(cut(ptg, et[i])[None] - d["target_mean"]) / d["target_std"] for i in keep]).astype(np.float32)
+    return ei[keep], et[keep], p_in, p_tg, occ
 
 
 # ---------------------------------------------------------------------------

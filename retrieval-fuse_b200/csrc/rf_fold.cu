@@ -463,6 +463,7 @@ __global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ 
     const int p = blockIdx.x, k = blockIdx.y, c = blockIdx.z;
     const float* row = rows + (((long)c * P + p) * K + k) * 8;
     const int scene = (int)row[0];
+    if (scene < -1) return;  // cell without an owner (overlapping compose): the pre-filled truncation value stays
     // .astype(np.int32) on fp32 extents (util/retrieval.py:153)
     const int X0 = (int)row[1], X1 = (int)row[2], Y0 = (int)row[3], Y1 = (int)row[4], Z0 = (int)row[5], Z1 = (int)row[6];
     const int* de = dst_ext + p * 6;

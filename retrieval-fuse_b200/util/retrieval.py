@@ -213,22 +213,71 @@ def query_dictionary_using_features(query_config, patch_names, input_features, d
     return {name: rows[i] for i, name in enumerate(patch_names)}
 
 
+def _overlap_cells(rows, dst, size):
+    """Overlapping target patches (patch_stride < patch_size_target): util/retrieval.py:149-164 pastes the patches of a
+    scene in order and a paste happens only while `distances[k, region].mean() > current_distance`, where `distances`
+    records the distance of whatever was pasted last.  That accept / reject sequence depends on the mapping alone, not
+    on voxel data, so it is replayed here on the host with the reference's own torch fp32 arithmetic; the volume is
+    then cut along every patch boundary into cells that have ONE owner (the last accepted patch covering them), and
+    the cells go through rf_compose_gather like non-overlapping patches.  Cells nobody owns get scene id -2 (= keep
+    the pre-filled truncation value).  rows [P,K,8], dst int [P,6] -> (cell rows [Pc,K,8], cell extents [Pc,6])."""
+    P, K = rows.shape[:2]
+    cuts = [sorted({0, int(size[a])} | {int(v) for v in dst[:, 2 * a]} | {int(v) for v in dst[:, 2 * a + 1]}) for a in range(3)]
+    cuts = [[c for c in cs if 0 <= c <= size[a]] for a, cs in enumerate(cuts)]
+    ncell = [len(c) - 1 for c in cuts]
+    pos = [{c: i for i, c in enumerate(cs)} for cs in cuts]
+    owner = np.full([K] + ncell, -1, dtype=np.int64)
+    distances = torch.ones((K,) + tuple(int(v) for v in size), dtype=torch.float32) * 100
+    for k in range(K):
+        for p in range(P):
+            cur = rows[p, k, 7]
+            x0, x1, y0, y1, z0, z1 = [int(v) for v in dst[p]]
+            if distances[k, x0:x1, y0:y1, z0:z1].mean() > cur:
+                distances[k, x0:x1, y0:y1, z0:z1] = float(cur)
+                owner[k, pos[0][x0]:pos[0][x1], pos[1][y0]:pos[1][y1], pos[2][z0]:pos[2][z1]] = p
+    cells = [(i, j, l) for i in range(ncell[0]) for j in range(ncell[1]) for l in range(ncell[2])]
+    cell_ext = np.array([[cuts[0][i], cuts[0][i + 1], cuts[1][j], cuts[1][j + 1], cuts[2][l], cuts[2][l + 1]] for i, j, l in cells],
+                        dtype=np.int32)
+    cell_rows = np.zeros((len(cells), K, 8), dtype=np.float32)
+    cell_rows[:, :, 0] = -2
+    for ci, (i, j, l) in enumerate(cells):
+        for k in range(K):
+            p = owner[k, i, j, l]
+            if p < 0:
+                continue
+            r = rows[p, k]
+            off = cell_ext[ci, 0::2] - dst[p, 0::2]            # where the cell starts inside the owner's block
+            ext = cell_ext[ci, 1::2] - cell_ext[ci, 0::2]
+            src0 = r[1:7:2].astype(np.int32) + off
+            src1 = np.minimum(src0 + ext, r[2:7:2].astype(np.int32))
+            cell_rows[ci, k] = [r[0], src0[0], src1[0], src0[1], src1[1], src0[2], src1[2], r[7]]
+    return cell_rows, cell_ext
+
+
 def create_retrieval_from_mapping(scene_name, retrieval_mappings, K, dataset_train, dataset, tree_path, dataset_index=None):
     """util/retrieval.py:145-164 for one scene -> CPU tensor [K, X, Y, Z].
-    The retrieved scenes are uploaded once and gathered by rf_compose_gather."""
-    if not dataset.no_overlap:
-        raise NotImplementedError("compose with overlapping target patches (patch_stride != patch_size_target) is "
-                                  "not implemented on the GPU; every shipped config is non-overlapping")
+    The retrieved scenes are uploaded once (padded to a common size when the bank's scenes differ) and gathered by
+    rf_compose_gather; with overlapping strides the reference's accept / reject sequence is replayed first
+    (_overlap_cells)."""
     if dataset_index is None:
         dataset_index = json.loads((Path(tree_path) / "index.json").read_text())
     dev = torch.device("cuda", torch.cuda.current_device())
-    size = tuple(dataset.get_scene_size(scene_name))
+    size = tuple(int(v) for v in dataset.get_scene_size(scene_name))
     patches = dataset.patch_from_scene_lookup[scene_name]
+    trunc = float(dataset.target_trunc)
+    if len(patches) == 0:
+        return torch.from_numpy(np.ones((K,) + size, dtype=np.float32)) * dataset.target_trunc
     rows = np.stack([np.asarray(retrieval_mappings[p], dtype=np.float32)[:K] for p in patches])  # [P,K,8]
     dst = np.array([dataset_train.unpad(*dataset.scene_handler.get_extent_from_name(p)[1]) for p in patches], dtype=np.int32)
+    if not dataset.no_overlap:
+        rows, dst = _overlap_cells(rows, dst, size)
     used = sorted({int(v) for v in rows[:, :, 0].reshape(-1) if v >= 0})
     if used:
-        store = np.stack([dataset_train.get_scene_target(dataset_index[s]).astype(np.float32) for s in used])
+        scenes = [dataset_train.get_scene_target(dataset_index[s]).astype(np.float32) for s in used]
+        ssz = tuple(max(sc.shape[a] for sc in scenes) for a in range(3))
+        store = np.full((len(scenes),) + ssz, np.float32(dataset_train.target_trunc), dtype=np.float32)
+        for i, sc in enumerate(scenes):  # the source extents address the scene's own coordinates: padding is never read
+            store[i, :sc.shape[0], :sc.shape[1], :sc.shape[2]] = sc
     else:
         store = np.zeros((1,) + size, dtype=np.float32)
     remap = {s: i for i, s in enumerate(used)}
@@ -236,8 +285,8 @@ def create_retrieval_from_mapping(scene_name, retrieval_mappings, K, dataset_tra
     for s, i in remap.items():
         rows_local[:, :, 0][rows[:, :, 0] == s] = i
     ratio = np.float32(dataset.target_trunc) / np.float32(dataset_train.target_trunc)
-    out = ops.compose_gather(torch.from_numpy(rows_local).to(dev), torch.from_numpy(dst).to(dev),
-                             torch.from_numpy(store).to(dev), 1, size, float(dataset.target_trunc), float(ratio),
+    out = ops.compose_gather(torch.from_numpy(rows_local).to(dev), torch.from_numpy(np.ascontiguousarray(dst)).to(dev),
+                             torch.from_numpy(store).to(dev), 1, size, trunc, float(ratio),
                              prefill=True)  # patches the dataset filtered out keep the truncation value (:148)
     return out[0].cpu()
 

@@ -500,6 +500,12 @@ def test_knn_full_size_properties(dev):
     want_i, want_d = O.knn_exact(bank.numpy(), q.numpy()[pick], k)
     assert np.array_equal(idx[pick].cpu().numpy(), want_i)
     assert np.array_equal(d[pick].cpu().numpy().astype(np.float32), want_d)
+    # ---- ALL 640 000 queries against the exact fp64 sweep (method 1, itself bit-exact against the oracle in
+    # test_knn_bit_exact): the tensor-core path returns the identical ids and distances for every query
+    for lo in range(0, Q, 160000):
+        hi = min(Q, lo + 160000)
+        ei, ed = ops.knn_topk(bank_d, q_d[lo:hi].contiguous(), k, method=1)
+        assert torch.equal(ei, idx[lo:hi]) and torch.equal(ed, d[lo:hi]), f"method 0 != method 1 in queries [{lo}, {hi})"
     # ---- two ragged row shards + merge == one bank
     cut = 70001
     i0, d0 = ops.knn_topk(bank_d[:cut], q_d, k, row_offset=0)
@@ -814,3 +820,64 @@ def test_retrieval_interface_roundtrip(dev, tmp_path):
     rows = np.stack([mapping[p] for p in P])
     want = O.compose_chunks(cfg, rows, np.stack([tg[s] for s in ds.scenes]), 1)[0]
     assert np.array_equal(vol.numpy(), want)
+
+
+@pytest.mark.parametrize("case", ["tile", "overlap"])
+def test_retrieval_prepass_matches_reference_golden(dev, tmp_path, case):
+    """SURVEY 8 rows a1, a10, a11, a12 against the REFERENCE's own util/retrieval.py + dataset/*.py, executed on the
+    same on-disk dataset (tests/golden/make_golden_retrieval.py; pyflann = exact brute force): SceneHandler /
+    PatchedSceneDataset enumeration, create_dictionary rows, get_retrieval_mapping (with and without
+    ignore_patches_from_source) and create_retrieval_from_mapping (tiling: filtered patches stay at the truncation value,
+    scenes of different sizes; overlap: the mean-distance rule) - ids, extents, mapping rows and composed volumes bit-exact."""
+    import retrieval_cases as RC
+    from retrieval_fuse_b200.dataset.patched_scene_dataset import PatchedSceneDataset
+    from retrieval_fuse_b200.dataset.scene import SceneHandler
+    from retrieval_fuse_b200.model import get_retrieval_networks
+    from retrieval_fuse_b200.util import retrieval as UR
+    Z, IDX = RC.load_golden()
+    RC.write_dataset(tmp_path)
+    cfg = RC.make_config(tmp_path, case)
+    fi, ft = get_retrieval_networks(cfg["retrieval_model"])
+    sd_in, sd_tg = RC.encoder_state_dicts()
+    fi.load_state_dict(sd_in)
+    ft.load_state_dict(sd_tg)
+    fi, ft = fi.to(dev).eval(), ft.to(dev).eval()
+    ds = {s: PatchedSceneDataset(s, cfg[f"dataset_{s}"], SceneHandler(s, cfg)) for s in ("train", "val")}
+    for split in ("train", "val"):  # a1
+        items = [ds[split][i] for i in range(len(ds[split]))]
+        assert [it["name"] for it in items] == IDX[f"{case}.{split}.patch_names"]
+        assert [[int(v) for v in it["extent"]] for it in items] == IDX[f"{case}.{split}.extent"]
+        assert np.array_equal(np.stack([it["input"] for it in items]).astype(np.float32), Z[f"{case}.{split}.patch_input"])
+        assert {n: int(v) for n, v in ds[split].scene_handler.scene_occupancy.items()} == IDX[f"{case}.{split}.occupancy"]
+    tree = tmp_path / "tree"
+    UR.create_dictionary(ft, cfg["dictionary"], RC.LATENT, ds["train"], tree)  # a10
+    db, gold_db = np.load(tree / "database.npy"), Z[f"{case}.database"]
+    assert db.shape == gold_db.shape and db.dtype == gold_db.dtype
+    assert np.array_equal(db[:, :7], gold_db[:, :7])
+    assert np.abs(db[:, 7:] - gold_db[:, 7:]).max() <= 1e-5
+    assert json.loads((tree / "index.json").read_text()) == IDX[f"{case}.index"]
+    # a11 on the reference's own database and features (isolates kNN + demotion + row format from the encoders' 1e-5)
+    np.save(tree / "database", gold_db)
+    UR._BANK_CACHE.clear()
+    for split, dsn, ignore in (("train", "train", True), ("train_keep", "train", False), ("val", "val", False),
+                               ("val_ignore", "val", True)):
+        names = IDX[f"{case}.{split}.patch_names"]
+        mapping = UR.query_dictionary_using_features(cfg["query"], names, Z[f"{case}.{split}.features"], ds[dsn], tree, ignore)
+        got = np.stack([mapping[n] for n in names])
+        gold = Z[f"{case}.{split}.mapping"]
+        assert got.dtype == gold.dtype and np.array_equal(got, gold), (case, split)
+        if split == "train_keep":
+            continue
+        for scene in ds[dsn].scenes:  # a12
+            vol = UR.create_retrieval_from_mapping(scene, mapping, RC.K, ds["train"], ds[dsn], tree).numpy()
+            assert np.array_equal(vol, Z[f"{case}.{split}.compose.{scene}"]), (case, split, scene)
+    # end to end through the product's own encoders: the same neighbours wherever the reference's margins allow it
+    UR._BANK_CACHE.clear()
+    np.save(tree / "database", db)
+    ri = UR.RetrievalInterface(cfg["query"], RC.LATENT)
+    mapping = ri.get_retrieval_mapping(fi, UR.extract_input_features, tree, ds["val"], False)
+    names = IDX[f"{case}.val.patch_names"]
+    got = np.stack([mapping[n] for n in names])
+    gold = Z[f"{case}.val.mapping"]
+    same = (got[:, :, :7] == gold[:, :, :7]).all(axis=(1, 2))
+    assert same.mean() > 0.9 and np.abs(got[same][:, :, 7] - gold[same][:, :, 7]).max() <= 1e-4
