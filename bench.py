@@ -4,18 +4,16 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N ...            # the CPU arm (oracle port)
 
-Workload at N = 1 (BASELINE.json configs[1]): ShapeNetV2 super_resolution
-retrieval_008_064 - query encoder (Patch04) + exact kNN (fetch 2K = 8, demote,
-keep K = 4) for 10 000 synthetic 8^3 chunks (640 000 queries) per step against
-a bank of 2 048 encoded synthetic 64^3 targets (131 072 rows + the sentinel).
-At N > 1 every rank brings its own 10 000 chunks (weak scaling) and the
-bank is sharded by rows into `--bank-shards` shards (default 2): the ranks form
-N / shards groups, each group holds one full copy of the bank, queries are
-all-gathered inside the group, every rank ranks its group's queries against its
-shard, the per-shard top-2K lists are exchanged (all-to-all) and merged.
-`--bank-shards N` is the fully sharded layout; the line also carries the fully
-replicated variant (no collective on the data path) as `replicated_bank`.  `--workload refine` times the full refinement forward (config 3
-shapes) instead; it is reported, not the headline.
+Default workload (`--workload full`, BASELINE.json's metric: encode + kNN + attn-fuse): per step and GPU, `--chunks`
+raw 8^3 chunks go through the WHOLE path - pad/unfold/normalise + Patch04 query encoder, exact kNN against a bank of
+2 048 encoded synthetic 64^3 targets (131 072 rows + sentinel; fetch 2K = 8, demote, keep K = 4), compose from the
+GPU-resident scene store, input U-Net + retrieval U-Net on 16^3 blocks + patch attention + decoder - to 64^3 TSDF
+predictions (3DFront super_resolution 008 -> 064 shapes, BASELINE configs[2]).  At N > 1 every rank brings its own
+chunks (weak scaling) and the bank is sharded by rows inside groups of `--bank-shards` ranks (all-gather of queries,
+all-to-all of per-shard top-2K lists, merge); everything else is chunk data parallel.
+Other workloads: `retrieval` (configs[1]: encode + kNN only, 10 000 chunks per step), `surface` (configs[3]: Matterport
+surface reconstruction, 128^3 occupancy grid -> 64^3, K = 8), `sweep` (configs[4]: 1 M-row isotropic bank, k sweep +
+attention sweep), `refine` (refinement forward alone), `stages` (every SURVEY 8d stage against its own roofline).
 
 One JSON line on stdout (rank 0); everything else goes to stderr.
 """
@@ -34,7 +32,8 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
-METRIC = "64^3 TSDF chunks/sec (encode+kNN)"
+METRIC = "64^3 TSDF chunks/sec (encode+kNN+attn-fuse)"
+METRIC_RETRIEVAL = "64^3 TSDF chunks/sec (encode+kNN only)"
 UNIT = "chunks/s"
 
 
@@ -61,8 +60,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="retrieval", choices=["retrieval", "refine", "stages"])
-    ap.add_argument("--chunks", type=int, default=10000, help="chunks per step per GPU")
+    ap.add_argument("--workload", default="full", choices=["full", "surface", "retrieval", "sweep", "refine", "stages"])
+    ap.add_argument("--chunks", type=int, default=0, help="chunks per step per GPU (0 = workload default: full 64, surface 16, "
+                                                         "retrieval 10000)")
     ap.add_argument("--bank-scenes", type=int, default=2048, help="64^3 scenes encoded into the bank (x64 rows)")
     ap.add_argument("--knn-method", type=int, default=0, help="0 auto, 1 exact fp64 sweep, 2 tcgen05 fp16, 3 tcgen05 bf16x3")
     ap.add_argument("--bank", default="encoded", choices=["encoded", "random"],
@@ -72,11 +72,24 @@ def parse():
                     help="N > 1: row shards of the bank (0 = auto: 2, the smallest sharding that keeps the NCCL exchange "
                          "on the data path; the N / shards groups of ranks each hold one full copy and exchange "
                          "inside the group).  --bank-shards N = one shard per rank")
-    ap.add_argument("--refine-batch", type=int, default=8)
+    ap.add_argument("--refine-batch", type=int, default=0, help="chunks per refinement sub-batch (0 = workload default: full 16, "
+                                                               "surface 4, refine 8)")
     ap.add_argument("--no-cuda-graph", action="store_true", help="refine workload: launch kernels eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--cpu-sample-chunks", type=int, default=2048, help="chunks of the workload the CPU arm runs per step (~10-15 s)")
+    ap.add_argument("--cpu-sample-chunks", type=int, default=0, help="chunks of the workload the CPU arm runs per step "
+                                                                    "(0 = workload default: retrieval 2048, full 4, surface 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    full_like = a.workload in ("full", "surface")
+    if a.chunks <= 0:
+        a.chunks = {"full": 64, "surface": 16}.get(a.workload, 10000)
+    if a.refine_batch <= 0:
+        a.refine_batch = {"full": 16, "surface": 4}.get(a.workload, 8)
+    if a.cpu_sample_chunks <= 0:
+        a.cpu_sample_chunks = {"full": 4, "surface": 1}.get(a.workload, 2048)
+    if a.workload == "surface" and a.bank_scenes == 2048:
+        a.bank_scenes = 512
+    a.full_like = full_like
+    return a
 
 
 # ---------------------------------------------------------------------------
@@ -204,6 +217,74 @@ def cpu_refine_sample(cfg, sds, chunks_np, retr_np, threads):
     return time.perf_counter() - t0
 
 
+def cpu_full_sample(cfg, sds, bank_emb, bank_meta, scene_store, chunks_np, threads):
+    """One bounded sample of the WHOLE path through the reference's CPU arithmetic (the oracle port): patch extraction
+    + query encoder + F.normalize, the kNN baseline BASELINE.md names (fp32 torch.cdist + topk brute force in batches of
+    1024 queries; FLANN is not installable) + demotion + mapping rows, compose (util/retrieval.py:145-164), the
+    dataloader normalisation and forward_full's inference part (U-Nets + attention + decoder).  Returns seconds."""
+    from oracle import rf_oracle as O
+    torch.set_num_threads(threads)
+    n = chunks_np.shape[0]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        q = torch.from_numpy(O.encode_chunk_queries(cfg, sds["fenc_input"], chunks_np))
+        db = torch.from_numpy(bank_emb)
+        K2 = 2 * cfg["K"]
+        idx = torch.empty((q.shape[0], K2), dtype=torch.int64)
+        dist = torch.empty((q.shape[0], K2), dtype=torch.float32)
+        for lo in range(0, q.shape[0], 1024):
+            d2 = torch.cdist(q[lo:lo + 1024], db) ** 2
+            v, i = torch.topk(d2, K2, dim=1, largest=False)
+            idx[lo:lo + 1024], dist[lo:lo + 1024] = i, v
+        qs = np.full(q.shape[0], -1)
+        oi, od = O.demote_same_scene(idx.numpy().astype(np.int32), dist.numpy(), bank_meta[:, 0].astype(np.int64), qs, cfg["K"])
+        rows = O.mapping_rows(bank_meta, oi, od)
+        retr = O.compose_chunks(cfg, rows, scene_store, n)
+        O.refine_chunks(cfg, {k: v for k, v in sds.items() if k != "fenc_input"}, chunks_np, retr)
+    return time.perf_counter() - t0
+
+
+def synth_sds_cpu(cfg, seed=1234):
+    """Synthetic state dicts of every network on the path (oracle shape tables), for the reference arm."""
+    from oracle import rf_oracle as O
+    nf, lv = cfg["nf"], cfg["unet_num_level"]
+    kind = {8: "sr08", 16: "sr16", 128: "surface"}[cfg["dataset"]["input_chunk_size"]]
+    rm = cfg["retrieval_model"]
+    enc = O._INPUT_ENCODER[rm["network_input"]]
+    return dict(fenc_input=O.synth_state_dict(O.encoder_param_shapes(enc, rm["nf_input"], rm["latent_dim"]), seed),
+                unet_backbone=O.synth_state_dict(O.unet_backbone_shapes(kind, nf, lv), seed),
+                retrieval_backbone=O.synth_state_dict(O.retrieval_backbone_shapes(nf, cfg["retrieval_fmaps"], cfg["retrieval_num_level"]), seed),
+                attention=O.synth_state_dict(O.attention_shapes(nf, cfg["attn_patch_extent"] // 2), seed),
+                decoder=O.synth_state_dict(O.final_decoder_shapes(nf), seed))
+
+
+def synthetic_chunks_cpu(cfg, n, seed=0):
+    """n raw input chunks of the workload on the host: low-res TSDF (super-resolution) or the 128^3 occupancy grid of
+    a 1000-point cloud (surface reconstruction; dataset/scene.py:81-90, util/misc.py:73-78)."""
+    from oracle import rf_oracle as O
+    d = cfg["dataset"]
+    rng = np.random.default_rng(seed)
+    if cfg["task"] == "surface_reconstruction":
+        return np.stack([O.point_cloud_to_grid(rng.random((d.get("num_points", 1000), 3)) * 64, d["input_chunk_size"],
+                                               d["input_chunk_size"] / 64.0, 0)[None] for _ in range(n)])
+    f = d["target_chunk_size"] // d["input_chunk_size"]
+    return np.stack([O.downsample_tsdf(O.synthetic_tsdf(1000 + seed * 131 + i, 64, d["voxel_size_target"]) / d["voxel_size_target"]
+                                       * d["voxel_size_input"], f, d["voxel_size_input"])[None] for i in range(n)]).astype(np.float32)
+
+
+def workload_text(cfg, B, n_rows, rb):
+    d = cfg["dataset"]
+    enc = cfg["retrieval_model"]["network_input"]
+    if cfg["task"] == "surface_reconstruction":
+        return (f"Matterport3D surface_reconstruction 128->064 (BASELINE configs[3] shapes): {B} chunks/step/GPU, 128^3 occupancy "
+                f"grid of a 1000-point cloud -> 64 x 48^3 patches -> PCPatch48 queries -> exact kNN vs {n_rows} rows (fetch "
+                f"{2 * cfg['K']}, demote, keep {cfg['K']}) -> compose -> 5-level U-Net nf 12 + retrieval U-Net + attention K={cfg['K']} "
+                f"+ decoder, refine sub-batch {rb}")
+    return (f"3DFront super_resolution 008->064 (BASELINE configs[2] shapes): {B} chunks/step/GPU, pad+unfold+normalise + Patch04 "
+            f"({enc}) queries -> exact kNN vs {n_rows} rows (fetch {2 * cfg['K']}, demote, keep {cfg['K']}) -> compose -> "
+            f"U-Net + retrieval U-Net on 16^3 blocks + patch attention + decoder -> 64^3 TSDF, refine sub-batch {rb}")
+
+
 def synthetic_bank_cpu(n_rows, seed=1):
     rng = np.random.default_rng(seed)
     emb = rng.standard_normal((n_rows, 64), dtype=np.float32)
@@ -220,7 +301,34 @@ def run_reference(args, rank, world):
     from oracle import rf_oracle as O
     from retrieval_fuse_b200.pipeline import FRONT3D_SR, SHAPENET_SR_RETRIEVAL
     threads = os.cpu_count() or 1
-    if args.workload == "retrieval":
+    metric = METRIC
+    if args.full_like:
+        from retrieval_fuse_b200.pipeline import MATTERPORT_SURFACE
+        cfg = FRONT3D_SR if args.workload == "full" else MATTERPORT_SURFACE
+        n_rows = args.bank_scenes * 64 + 1
+        n_store = 32  # distinct synthetic scenes in the host scene store (the bank's scene ids wrap around them)
+        emb, meta = synthetic_bank_cpu(n_rows)
+        ps = cfg["dataset"]["patch_size_target"]
+        ext = np.array([[x * ps, x * ps + ps, y * ps, y * ps + ps, z * ps, z * ps + ps] for x in range(4) for y in range(4)
+                        for z in range(4)], dtype=np.float32)
+        meta[:-1, 0] = (np.arange(n_rows - 1) // 64) % n_store
+        meta[:-1, 1:] = np.tile(ext, (args.bank_scenes, 1))
+        meta[-1] = [-1, 0, ps, 0, ps, 0, ps]
+        store = np.stack([O.synthetic_tsdf(100 + i, 64, cfg["dataset"]["voxel_size_target"]) for i in range(n_store)])
+        sds = synth_sds_cpu(cfg)
+        per_step = min(args.cpu_sample_chunks, args.chunks)
+        chunks = synthetic_chunks_cpu(cfg, per_step)
+        for _ in range(min(args.warmup, 1)):
+            cpu_full_sample(cfg, sds, emb, meta, store, chunks[:1], threads)
+        times = [cpu_full_sample(cfg, sds, emb, meta, store, chunks, threads) for _ in range(args.steps)]
+        config = {"workload": workload_text(cfg, args.chunks, n_rows, args.refine_batch), "chunks_per_step": per_step,
+                  "bank_rows": n_rows, "K": cfg["K"],
+                  "bank": f"{n_rows} random unit rows (same size as the GPU arm's encoded bank; the content does not change the "
+                          f"cost of a brute-force cdist), scene store of {n_store} synthetic 64^3 scenes"}
+        sample = (f"{per_step} chunks/step through the whole path (encode, cdist+topk kNN vs {n_rows} rows, compose, refine "
+                  f"forward), torch CPU fp32, {threads} threads")
+    elif args.workload == "retrieval":
+        metric = METRIC_RETRIEVAL
         cfg = SHAPENET_SR_RETRIEVAL
         n_rows = args.bank_scenes * 64 + 1
         emb, meta = synthetic_bank_cpu(n_rows)
@@ -235,6 +343,7 @@ def run_reference(args, rank, world):
                   "bank_rows": n_rows, "queries_per_chunk": 64}
         sample = f"{per_step} chunks/step ({per_step * 64} queries x {n_rows} rows), torch CPU fp32 cdist+topk"
     else:
+        metric = "64^3 TSDF chunks/sec (refine forward)"
         cfg = FRONT3D_SR
         sds = dict(unet_backbone=O.synth_state_dict(O.unet_backbone_shapes("sr08", 16, 4), 1234),
                    retrieval_backbone=O.synth_state_dict(O.retrieval_backbone_shapes(16, 16, 4), 1234),
@@ -251,7 +360,7 @@ def run_reference(args, rank, world):
         sample = f"{per_step} chunks/step, torch CPU fp32"
     total = float(sum(times))
     value = per_step * args.steps / total
-    line = {"impl": "reference", "metric": METRIC if args.workload == "retrieval" else "64^3 TSDF chunks/sec (refine forward)",
+    line = {"impl": "reference", "metric": metric,
             "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
@@ -405,12 +514,68 @@ def run_stages(args, local):
     print(json.dumps(line), flush=True)
 
 
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def load_traffic(key):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture of THIS workload
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when there is no capture."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(key)
+    except Exception:
+        return None
+
+
+def build_world(args, cfg, dev, rank, world, need_store):
+    """Bank (this rank's row shard), scene store, process group of the shard exchange."""
+    import torch.distributed as dist
+    from retrieval_fuse_b200.pipeline import build_bank_from_targets, synthetic_tsdf_batch
+    from retrieval_fuse_b200.util.retrieval import EmbeddingBank
+    d = cfg["dataset"]
+    S_tot = args.bank_scenes
+    S_b = args.bank_shards if args.bank_shards > 0 else (min(world, 4) if args.full_like else min(world, 2))
+    if S_b > world or world % S_b:
+        S_b = world
+    shard, gidx, my_group = rank % S_b, rank // S_b, None
+    if world > 1:
+        for gi in range(world // S_b):  # every rank creates every group (collective call)
+            grp = dist.new_group(list(range(gi * S_b, (gi + 1) * S_b)))
+            if gi == gidx:
+                my_group = grp
+    per = (S_tot + S_b - 1) // S_b
+    lo, hi = min(shard * per, S_tot), min((shard + 1) * per, S_tot)
+    store = None
+    if args.bank == "encoded":
+        if need_store:  # compose reads any scene of the bank: the store is replicated (1 MB per scene)
+            store = torch.cat([synthetic_tsdf_batch(min((s + 1) * per, S_tot) - min(s * per, S_tot), 64, d["voxel_size_target"],
+                                                    seed=100 + s, device=dev) for s in range(S_b)])
+            targets = store[lo:hi]
+        else:
+            targets = synthetic_tsdf_batch(hi - lo, 64, d["voxel_size_target"], seed=100 + shard, device=dev)
+        bank, _ = build_bank_from_targets(cfg, targets, dev, weight_seed=11, scene_offset=lo, n_scenes_total=S_tot,
+                                          batch_patches=4096)
+        del targets
+    else:
+        g = torch.Generator(device=dev).manual_seed(1 + shard)
+        n_loc = (hi - lo) * 64 + (1 if hi == S_tot else 0)
+        emb = torch.nn.functional.normalize(torch.randn(n_loc, 64, generator=g, device=dev), dim=1)
+        meta = torch.zeros((S_tot * 64 + 1, 7), device=dev)
+        meta[:, 0] = torch.arange(S_tot * 64 + 1, device=dev) // 64
+        bank = EmbeddingBank(emb, meta, [f"scene{i:05d}" for i in range(S_tot)], row_offset=lo * 64, n_total=S_tot * 64 + 1)
+    return bank, store, my_group, S_b, per
+
+
 def run_ours(args, rank, local, world):
     import torch.distributed as dist
     from retrieval_fuse_b200 import ops
-    from retrieval_fuse_b200.pipeline import (FRONT3D_SR, SHAPENET_SR_RETRIEVAL, RefinementPipeline, RetrievalPipeline,
-                                              build_bank_from_targets, f16_trunc, synthetic_tsdf_batch)
+    from retrieval_fuse_b200.pipeline import (FRONT3D_SR, MATTERPORT_SURFACE, SHAPENET_SR_RETRIEVAL, RefinementPipeline,
+                                              RetrievalPipeline, synthetic_tsdf_batch, downsample_tsdf_batch)
     from retrieval_fuse_b200.sharded import ShardedBankQuery
+    from retrieval_fuse_b200.util.retrieval import EmbeddingBank
 
     assert torch.cuda.is_available(), "bench.py (impl ours) needs a GPU; there is no CPU fallback"
     torch.cuda.set_device(local)
@@ -424,57 +589,88 @@ def run_ours(args, rank, local, world):
         _REAL_STDOUT = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = load_peaks()
+    peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    def rank_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    if args.workload == "retrieval":
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    t0 = time.time()
+    extra = {}
+    e2e_pipelined = None
+    profile_step = None
+    B = args.chunks
+
+    if args.full_like:
+        # ------------------------------------------------------------------ the whole path (headline)
+        cfg = FRONT3D_SR if args.workload == "full" else MATTERPORT_SURFACE
+        d = cfg["dataset"]
+        bank, store, my_group, S_b, per = build_world(args, cfg, dev, rank, world, need_store=True)
+        sq = ShardedBankQuery(bank, group=my_group) if world > 1 else None
+        pipe = RefinementPipeline(cfg, bank, store, device=dev, weight_seed=1234, sharded_query=sq)
+        rb = min(args.refine_batch, B)
+        if cfg["task"] == "surface_reconstruction":
+            g = torch.Generator(device="cpu").manual_seed(7 + rank)
+            pts = (torch.rand((B, d["num_points"], 3), generator=g) * 128).long().clamp_(0, 127).to(dev)
+            chunks = torch.zeros((B, 1, 128, 128, 128), device=dev)
+            chunks[torch.arange(B, device=dev)[:, None], 0, pts[..., 0], pts[..., 1], pts[..., 2]] = 1.0
+        else:
+            qt = synthetic_tsdf_batch(B, 64, d["voxel_size_target"], seed=5000 + rank, device=dev)
+            chunks = downsample_tsdf_batch(qt, 64 // d["input_chunk_size"], d["voxel_size_target"], d["voxel_size_input"])
+            del qt
+        chunks_host = chunks.cpu().pin_memory()
+        out_host = torch.empty((B, 1, 64, 64, 64), dtype=torch.float32).pin_memory()
+        n_rows = bank.n_total
+        use_graph = not args.no_cuda_graph
+        if use_graph:
+            try:
+                pipe.infer(chunks, None, args.knn_method, rb, True)
+            except Exception as e:  # same kernels either way; say so instead of failing the measurement
+                log(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); launching eagerly")
+                use_graph = False
+        pred_buf = torch.empty((B, 1, 64, 64, 64), dtype=torch.float32, device=dev)
+        stage_names = ["encode", "knn", "compose", "refine"]
+
+        def step(timed):
+            marks = [] if timed else None
+            pipe.infer(chunks, None, args.knn_method, rb, use_graph, out=pred_buf, marks=marks)
+            return marks
+
+        def e2e_step():
+            return pipe.infer_host(chunks_host, out_host, None, args.knn_method, rb, use_graph)
+
+        def profile_step():
+            pipe.infer(chunks, None, args.knn_method, rb, False)
+
+        h2d, d2h = chunks_host.numel() * 4, out_host.numel() * 4
+        metric = METRIC
+        config = {"workload": workload_text(cfg, B, n_rows, rb), "chunks_per_step_per_gpu": B, "refine_sub_batch": rb,
+                  "bank_rows": n_rows, "K": cfg["K"], "bank_shards": S_b if world > 1 else 1,
+                  "bank": (f"{S_b} row shards x {world // S_b} replica groups, exchange (all-gather queries, all-to-all "
+                           f"top-2K lists) inside a group; scene store replicated") if world > 1 else "single GPU",
+                  "l2": "flushed between timed steps (256 MiB write)", "launch": "refinement sub-batches replay a CUDA graph" if use_graph else "eager",
+                  "knn_method": args.knn_method, "embeddings": args.bank}
+        flops_per_chunk = {"full": 87.4e9 + 0.041e9 + 8192.0 * n_rows, "surface": (50.0 + 85.8 + 3.62 + 4.08 + 91.9) * 1e9 + 8192.0 * n_rows}[args.workload]
+        units_per_step = B
+        dom_op, dom_name = "rf_tc_conv3d_halo_fwd", "tc_conv3d_halo_kernel (shifted-window 3x3x3 conv, tcgen05, fp16 hi/lo split)"
+    elif args.workload == "retrieval":
+        # ------------------------------------------------------------------ configs[1]: encode + kNN only
         cfg = SHAPENET_SR_RETRIEVAL
         d = cfg["dataset"]
+        bank, _, my_group, S_b, per = build_world(args, cfg, dev, rank, world, need_store=False)
         S_tot = args.bank_scenes
-        # Bank placement: the bank is sharded by rows only as far as asked (default 2 shards: a 33.5 MB
-        # bank needs no sharding for memory, and every additional shard makes every rank rank ALL of a group's
-        # queries); the world is world / shards groups of ranks, each group holds one full copy of the bank and runs
-        # the all-gather / all-to-all exchange among its own ranks.
-        S_b = args.bank_shards if args.bank_shards > 0 else min(world, 2)
-        if S_b > world or world % S_b:
-            S_b = world
-        shard, gidx, my_group = rank % S_b, rank // S_b, None
-        if world > 1:
-            for gi in range(world // S_b):  # every rank creates every group (collective call)
-                grp = dist.new_group(list(range(gi * S_b, (gi + 1) * S_b)))
-                if gi == gidx:
-                    my_group = grp
-        per = (S_tot + S_b - 1) // S_b
-        lo, hi = min(shard * per, S_tot), min((shard + 1) * per, S_tot)
-        t0 = time.time()
-        if args.bank == "encoded":
-            targets = synthetic_tsdf_batch(hi - lo, 64, d["voxel_size_target"], seed=100 + shard, device=dev)
-            bank, _ = build_bank_from_targets(cfg, targets, dev, weight_seed=11, scene_offset=lo, n_scenes_total=S_tot,
-                                              batch_patches=4096)
-            del targets
-        else:
-            from retrieval_fuse_b200.util.retrieval import EmbeddingBank
-            g = torch.Generator(device=dev).manual_seed(1 + shard)
-            n_loc = (hi - lo) * 64 + (1 if hi == S_tot else 0)
-            emb = torch.nn.functional.normalize(torch.randn(n_loc, 64, generator=g, device=dev), dim=1)
-            meta = torch.zeros((S_tot * 64 + 1, 7), device=dev)
-            meta[:, 0] = torch.arange(S_tot * 64 + 1, device=dev) // 64
-            bank = EmbeddingBank(emb, meta, [f"scene{i:05d}" for i in range(S_tot)], row_offset=lo * 64, n_total=S_tot * 64 + 1)
-        torch.cuda.synchronize(dev)
-        log(f"[rank {rank}] bank shard rows {bank.emb.shape[0]} of {bank.n_total} built in {time.time() - t0:.1f}s")
         sq = ShardedBankQuery(bank, group=my_group) if world > 1 else None
         pipe = RetrievalPipeline(cfg, bank, device=dev, weight_seed=1234, sharded_query=sq)
-        B = args.chunks
         chunks = synthetic_tsdf_batch(B, 8, d["voxel_size_input"], seed=7 + rank, device=dev, batch=2048).unsqueeze(1).contiguous()
         chunks_host = chunks.cpu().pin_memory()
         n_rows = bank.n_total
@@ -483,19 +679,19 @@ def run_ours(args, rank, local, world):
         if args.bank == "random":
             g = torch.Generator(device=dev).manual_seed(2 + rank)
             q_rand = torch.nn.functional.normalize(torch.randn(Q, 64, generator=g, device=dev), dim=1)
-
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        stage_names = ["encode", "knn"]
 
         def step(timed):
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timed else None
             if timed:
-                ev[0].record()
+                marks[0].record()
             q = pipe.encode_queries(chunks)
             if timed:
-                ev[1].record()
-            rows, idx = pipe.lookup(q if q_rand is None else q_rand, None, args.knn_method)
+                marks[1].record()
+            pipe.lookup(q if q_rand is None else q_rand, None, args.knn_method)
             if timed:
-                ev[2].record()
-            return rows
+                marks[2].record()
+            return marks
 
         def e2e_step():
             return pipe.retrieve_host(chunks_host, None, args.knn_method)
@@ -510,26 +706,20 @@ def run_ours(args, rank, local, world):
                     pending.pop(0).synchronize()  # the rows of batch i-1 are in host memory
             pending[-1].synchronize()
 
-        h2d = chunks_host.numel() * 4
-        d2h = Q * cfg["K"] * 8 * 4
-        # the same workload with the bank REPLICATED on every rank (33.5 MB): no data-path collective at all
-        pipe_repl = None
-        if world > 1:
-            parts = [torch.empty((min((r + 1) * per, S_tot) - min(r * per, S_tot)) * 64 + (1 if min((r + 1) * per, S_tot) == S_tot else 0),
-                                 64, device=dev) for r in range(S_b)]
-            dist.all_gather(parts, bank.emb, group=my_group)
-            from retrieval_fuse_b200.util.retrieval import EmbeddingBank
-            full = EmbeddingBank(torch.cat(parts), bank.meta, bank.scenes)
-            pipe_repl = RetrievalPipeline(cfg, full, device=dev, fenc_input=pipe.fenc_input)
-            del parts
-        workload = f"ShapeNetV2 SR retrieval_008_064: Patch04 encode + exact kNN (fetch 8, demote, keep 4), {B} chunks x 64 queries vs {n_rows} rows"
-        config = {"workload": workload, "chunks_per_step_per_gpu": B, "bank_rows": n_rows, "K": cfg["K"],
+        def profile_step():
+            step(False)
+
+        h2d, d2h = chunks_host.numel() * 4, Q * cfg["K"] * 8 * 4
+        metric = METRIC_RETRIEVAL
+        config = {"workload": f"ShapeNetV2 SR retrieval_008_064 (BASELINE configs[1]): Patch04 encode + exact kNN (fetch 8, demote, keep 4), "
+                              f"{B} chunks x 64 queries vs {n_rows} rows", "chunks_per_step_per_gpu": B, "bank_rows": n_rows, "K": cfg["K"],
                   "bank": (f"{S_b} row shards x {world // S_b} replica groups, exchange (all-gather queries, all-to-all "
-                           f"top-2K lists) inside a group") if world > 1 else "single GPU", "bank_shards": S_b if world > 1 else 1, "l2": "flushed between timed steps (256 MiB write)",
-                  "knn_method": args.knn_method, "embeddings": args.bank}
-        algo_flops = 2.0 * Q * (S_b if world > 1 else 1) * bank.emb.shape[0] * 64  # per rank: its group's queries x its shard
+                           f"top-2K lists) inside a group") if world > 1 else "single GPU", "bank_shards": S_b if world > 1 else 1,
+                  "l2": "flushed between timed steps (256 MiB write)", "knn_method": args.knn_method, "embeddings": args.bank}
         units_per_step = B
+        dom_op, dom_name = "rf_knn_l2_topk", "rf_knn_l2_topk (operand images + knn_tc_candidates_kernel tcgen05 score GEMM with running top lists + fp64 re-rank)"
     else:
+        # ------------------------------------------------------------------ refinement forward alone
         cfg = FRONT3D_SR
         d = cfg["dataset"]
         pipe = RefinementPipeline(cfg, bank=None, device=dev, weight_seed=1234)
@@ -539,27 +729,24 @@ def run_ours(args, rank, local, world):
         retr = ((tg - d["target_mean"]) / d["target_std"]).reshape(B, 4, 64, 64, 64).contiguous()
         x_in_host, retr_host = x_in.cpu().pin_memory(), retr.cpu().pin_memory()
         out_host = torch.empty((B, 1, 64, 64, 64), dtype=torch.float32).pin_memory()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-
         use_graph = not args.no_cuda_graph
         if use_graph:
             try:
                 pipe.refine_graphed(x_in, retr)
-            except Exception as e:  # same kernels either way; say so instead of failing the measurement
+            except Exception as e:
                 log(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); launching eagerly")
                 use_graph = False
         fwd = (lambda a, b: pipe.refine_graphed(a, b)) if use_graph else (lambda a, b: pipe.refine(a, b)[0])
-        ops.reset_launches()
-        pipe.refine(x_in, retr)
-        launches_per_forward = ops.launches()
+        stage_names = ["refine"]
 
         def step(timed):
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timed else None
             if timed:
-                ev[0].record(); ev[1].record()
-            pred = fwd(x_in, retr)
+                marks[0].record()
+            fwd(x_in, retr)
             if timed:
-                ev[2].record()
-            return pred
+                marks[1].record()
+            return marks
 
         def e2e_step():
             p = fwd(x_in_host.to(dev, non_blocking=True), retr_host.to(dev, non_blocking=True))
@@ -567,13 +754,18 @@ def run_ours(args, rank, local, world):
             torch.cuda.current_stream(dev).synchronize()
             return out_host
 
-        h2d = (x_in.numel() + retr.numel()) * 4
-        d2h = out_host.numel() * 4
+        def profile_step():
+            pipe.refine(x_in, retr)
+
+        h2d, d2h = (x_in.numel() + retr.numel()) * 4, out_host.numel() * 4
+        metric = "64^3 TSDF chunks/sec (refine forward)"
         config = {"workload": f"3DFront SR 008->064 refine forward, batch {B}, K=4 (unet + retrieval unet + attention + decoder)",
                   "chunks_per_step_per_gpu": B, "l2": "flushed between timed steps (256 MiB write)",
-                  "launch": "CUDA graph replay" if use_graph else "eager", "kernels_per_forward": launches_per_forward}
-        algo_flops = 87.4e9 * B
+                  "launch": "CUDA graph replay" if use_graph else "eager"}
         units_per_step = B
+        dom_op, dom_name = "rf_tc_conv3d_halo_fwd", "tc_conv3d_halo_kernel (shifted-window 3x3x3 conv, tcgen05, fp16 hi/lo split)"
+    torch.cuda.synchronize(dev)
+    log(f"[rank {rank}] setup {time.time() - t0:.1f}s")
 
     # ---- warm-up
     for _ in range(max(args.warmup, 3)):
@@ -584,32 +776,22 @@ def run_ours(args, rank, local, world):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ops.reset_launches()
     barrier()
     wall0 = time.perf_counter()
-    t_step, t_enc, t_knn, t_cand = [], [], [], []
-    from retrieval_fuse_b200 import _lib as rf_lib
+    t_step, t_stage = [], {n: [] for n in stage_names}
     ev_end = torch.cuda.Event(enable_timing=True)
     for _ in range(args.steps):
         flush_buf.fill_(1)
-        step(True)
+        marks = step(True)
         ev_end.record()
         ev_end.synchronize()
-        t_step.append(ev[0].elapsed_time(ev_end))
-        t_enc.append(ev[0].elapsed_time(ev[1]))
-        t_knn.append(ev[1].elapsed_time(ev[2]))
-        t_cand.append(float(rf_lib.lib().rf_knn_last_candidates_ms()))  # CUDA-event time of the tcgen05 candidates kernel
+        t_step.append(marks[0].elapsed_time(ev_end))
+        for i, n in enumerate(stage_names):
+            t_stage[n].append(marks[i].elapsed_time(marks[i + 1]))
     barrier()
     wall = time.perf_counter() - wall0
-    launches = ops.launches()
-    if args.workload == "refine" and launches == 0:  # graph replays bypass the Python-side counter
-        launches = launches_per_forward * args.steps
     clocks = sampler.stop() if rank == 0 else None
-
-    dev_ms = torch.tensor([sum(t_step)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(dev_ms.item())
+    total_ms = rank_max(sum(t_step))
     value = units_per_step * world * args.steps / (total_ms / 1e3)
 
     # ---- e2e: host buffers in and out through the reference-facing call
@@ -620,101 +802,114 @@ def run_ours(args, rank, local, world):
     for _ in range(args.steps):
         e2e_step()
     barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = units_per_step * world * args.steps / float(e2e_s.item())
+    e2e_value = units_per_step * world * args.steps / rank_max(time.perf_counter() - t0)
     e2e_pipe_value = None
-    if args.workload == "retrieval":
+    if e2e_pipelined is not None:
         e2e_pipelined(2)
         barrier()
         t0 = time.perf_counter()
         e2e_pipelined(args.steps)
         barrier()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_pipe_value = units_per_step * world * args.steps / float(t.item())
+        e2e_pipe_value = units_per_step * world * args.steps / rank_max(time.perf_counter() - t0)
 
-    replicated = None
-    if args.workload == "retrieval" and world > 1 and pipe_repl is not None:
+    # ---- launches per step + per-op device times (one eager, untimed pass with a CUDA event pair around every op; the
+    # GPU spins first so that the host runs ahead and the ops execute back to back as they do inside the timed steps)
+    ops.reset_launches()
+    profile_step()
+    torch.cuda.synchronize(dev)
+    launches_per_step = ops.launches()
+    prof = None
+    torch.cuda._sleep(int(2e7))
+    if rank == 0:
+        ops.profile_start()
+    profile_step()  # every rank takes part (the sharded lookup is a collective); only rank 0 records events
+    if rank == 0:
+        prof = ops.profile_stop()
+    barrier()
+
+    # ---- the retrieval half alone on the same bank (BASELINE configs[1] style: encode + kNN, no compose / refine)
+    if args.full_like and args.workload == "full":
+        nR = 10000
+        rch = synthetic_tsdf_batch(nR, 8, d["voxel_size_input"], seed=7 + rank, device=dev, batch=2048).unsqueeze(1).contiguous()
         for _ in range(2):
-            pipe_repl.retrieve(chunks, None, args.knn_method)
+            pipe.retrieve(rch, None, args.knn_method)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tot = 0.0
-        for _ in range(args.steps):
+        for _ in range(3):
             flush_buf.fill_(1)
             e0.record()
-            pipe_repl.retrieve(chunks, None, args.knn_method)
+            pipe.retrieve(rch, None, args.knn_method)
             e1.record()
             e1.synchronize()
             tot += e0.elapsed_time(e1)
         barrier()
-        t = torch.tensor([tot], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        replicated = {"value": units_per_step * world * args.steps / (float(t.item()) / 1e3), "unit": UNIT,
-                      "ms_per_step": float(t.item()) / args.steps,
-                      "note": "bank replicated on every rank, queries data parallel, no collective on the data path"}
+        tot = rank_max(tot)
+        extra["retrieval_only"] = {"value": nR * world * 3 / (tot / 1e3), "unit": UNIT, "ms_per_step": tot / 3,
+                                   "workload": f"encode + kNN only (no compose / refine), {nR} chunks per GPU and step vs the same {n_rows}-row bank"}
+        del rch
 
     if rank == 0:
-        knn_ms = float(np.mean(t_knn))
-        peak = peaks.get("bf16_tflops_sustained") or 1400.0
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)"
-        if args.workload == "retrieval":
-            cand_ms = float(np.mean(t_cand)) if t_cand and min(t_cand) > 0 else None
-            k_ms = cand_ms if cand_ms else knn_ms
-            # dram bytes per launch of knn_tc_candidates_kernel<1> from the ncu --set full capture of this workload
-            # (profiles/r01_knn_tc_candidates_fp16_full.txt: 99.6 MB read + 47.1 MB write); null for other shapes
-            traffic = 146.7e6 if (cand_ms and world == 1 and B == 10000 and n_rows == 131073 and args.bank == "encoded") else None
-            roof = {"bound": "tensor", "kernel": "knn_tc_candidates_kernel (tcgen05 score GEMM + running top-16)" if cand_ms
-                    else "rf_knn_l2_topk (whole call)",
-                    "achieved": algo_flops / (k_ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                    "frac": algo_flops / (k_ms / 1e3) / 1e12 / peak, "traffic": traffic, "peak_source": peak_src,
-                    "avg_launch_ms": k_ms, "algorithmic_flops_per_launch": algo_flops,
-                    "note": "algorithmic flops = 2*Q*N*64, one fp16 tcgen05 pass; every one of the Q*N fp32 scores is read back "
-                            "from TMEM by the epilogue (K = 64 is too short to amortise that), which bounds this GEMM far below "
-                            "the MMA rate; bank rows are scanned in descending projection on the mean query so that the "
-                            "running top-16 thresholds tighten early (exactness unaffected)",
-                    "scores_per_clk_per_sm": algo_flops / 128.0 / (k_ms / 1e3) / 148.0 / 1.965e9,
-                    "hbm_view": {"algorithmic_bytes": bank.emb.numel() * 4 + algo_flops / (128.0 * bank.emb.shape[0]) * (256 + 8 * 12),
-                                 "peak_gbs": peaks.get("hbm_gbs")}}
+        step_ms = total_ms / args.steps
+        dom = (prof or {}).get(dom_op)
+        if dom and dom["ms"] > 0:
+            roof = {"bound": "tensor", "kernel": dom_name, "achieved": dom["flops"] / dom["ms"] / 1e9, "peak": peak, "unit": "TFLOP/s",
+                    "frac": dom["flops"] / dom["ms"] / 1e9 / peak, "traffic": load_traffic(f"{args.workload}:{dom_op}"),
+                    "peak_source": peak_src, "launches_per_step": dom["calls"], "avg_launch_ms": dom["ms"] / dom["calls"],
+                    "algorithmic_flops_per_launch": dom["flops"] / dom["calls"], "ms_per_step": dom["ms"],
+                    "share_of_step": dom["ms"] / step_ms,
+                    "note": "achieved = ALGORITHMIC flops of these launches (2*M*27*Cin*Cout for the conv; 2*Q*N*64 for the kNN) / "
+                            "their summed CUDA-event durations in an eager pass of the same step; the convolution spends three "
+                            "fp16 MMAs per product (hi/lo split for fp32-level accuracy) on rows that include halo positions, "
+                            "so 1/3 is the ceiling of frac"}
         else:
-            roof = {"bound": "tensor", "kernel": "refine forward (all kernels)", "achieved": algo_flops / (knn_ms / 1e3) / 1e12,
-                    "peak": peak, "unit": "TFLOP/s", "frac": algo_flops / (knn_ms / 1e3) / 1e12 / peak, "traffic": None,
-                    "peak_source": peak_src, "avg_launch_ms": knn_ms, "algorithmic_flops_per_launch": algo_flops}
-        line = {"metric": METRIC if args.workload == "retrieval" else "64^3 TSDF chunks/sec (refine forward)", "value": value,
-                "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 encode / f64 distance ranking", "data": "synthetic", "config": config,
-                "e2e": ({"value": e2e_pipe_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                         "call": "RetrievalPipeline.retrieve_host_async: host buffers in and out, two batches in flight - every "
-                                 "step's H2D and D2H copies are inside the timed region and overlap the next batch's kernels",
-                         "sync_value": e2e_value,
-                         "sync_call": "RetrievalPipeline.retrieve_host: one synchronous call per step, nothing overlapped"}
+            roof = {"bound": "tensor", "kernel": dom_name, "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None,
+                    "traffic": None, "peak_source": peak_src}
+        roof["whole_step"] = None
+        if args.full_like:
+            roof["whole_step"] = {"algorithmic_tflops": flops_per_chunk * B / step_ms / 1e9,
+                                  "frac_of_peak": flops_per_chunk * B / step_ms / 1e9 / peak,
+                                  "flops_per_chunk": flops_per_chunk}
+        op_table = None
+        if prof:
+            tot_ms = sum(v["ms"] for v in prof.values())
+            op_table = {k: {"calls": v["calls"], "ms": round(v["ms"], 4), "share": round(v["ms"] / tot_ms, 4),
+                            **({"tflops": round(v["flops"] / v["ms"] / 1e9, 1)} if v["flops"] else {}),
+                            **({"gbs": round(v["bytes"] / v["ms"] / 1e6, 1)} if v["bytes"] else {})}
+                        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        e2e = {"value": e2e_pipe_value or e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "call": ("RetrievalPipeline.retrieve_host_async: host buffers in and out, two batches in flight"
                         if e2e_pipe_value else
-                        {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                         "call": "pipeline call with pinned host tensors in and out, one synchronous call per step"}),
-                "gpu_launches": launches, "roofline": roof, "clocks": clocks,
-                "breakdown_ms": {"encode": float(np.mean(t_enc)), "knn": knn_ms,
-                                 "knn_candidates_kernel": float(np.mean(t_cand)) if t_cand else None, "step": total_ms / args.steps,
-                                 "wall_per_step_incl_flush": 1e3 * wall / args.steps}}
-        if replicated is not None:
-            line["replicated_bank"] = replicated
+                        ("RefinementPipeline.infer_host: pinned host chunks in, pinned host predictions out, one synchronous "
+                         "call per step" if args.full_like else "pipeline call with pinned host tensors in and out, one synchronous call per step"))}
+        if e2e_pipe_value:
+            e2e["sync_value"] = e2e_value
+        line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (tcgen05 fp16 hi/lo split products, fp32 accumulate) / f64 distance ranking", "data": "synthetic",
+                "config": config, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+                "roofline": roof, "clocks": clocks,
+                "breakdown_ms": dict({n: float(np.mean(v)) for n, v in t_stage.items()}, step=step_ms,
+                                     wall_per_step_incl_flush=1e3 * wall / args.steps),
+                "op_breakdown_eager": op_table}
+        line.update(extra)
         if args.workload == "retrieval" and world == 1:
-            # proof statistics of the tensor-core kNN on this workload (one extra, untimed call)
             qq = pipe.encode_queries(chunks) if q_rand is None else q_rand
             ops.knn_topk(bank.emb, qq, 2 * cfg["K"], method=args.knn_method, stats=True)
             line["knn_stats"] = dict(ops.last_knn_stats)
         if not args.no_cpu_baseline and world == 1:
             try:
-                from oracle import rf_oracle as O
                 threads = os.cpu_count() or 1
-                if args.workload == "retrieval":
-                    n = min(args.cpu_sample_chunks, args.chunks)
+                n = min(args.cpu_sample_chunks, B)
+                if args.full_like:
+                    sds = pipe.state_dicts()
+                    secs = cpu_full_sample(cfg, sds, bank.emb.cpu().numpy(), bank.meta.cpu().numpy(), store.cpu().numpy(),
+                                           chunks_host[:n].numpy(), threads)
+                    sample = (f"{n} of the step's {B} chunks through the whole path on the same bank, scene store and weights "
+                              f"(oracle port: torch CPU fp32, cdist+topk kNN), {secs:.1f}s")
+                elif args.workload == "retrieval":
                     sd = {k: v.detach().cpu() for k, v in pipe.fenc_input.state_dict().items()}
-                    secs = cpu_retrieval_sample(cfg, sd, bank.emb.cpu().numpy(), bank.meta.cpu().numpy(),
-                                                chunks_host[:n].numpy(), threads)
+                    secs = cpu_retrieval_sample(cfg, sd, bank.emb.cpu().numpy(), bank.meta.cpu().numpy(), chunks_host[:n].numpy(), threads)
                     sample = f"{n} of the {B} chunks ({n * 64} queries x {n_rows} rows), torch CPU fp32 cdist+topk, {secs:.1f}s"
                 else:
                     n = 1

@@ -30,6 +30,9 @@ class WeightCache:
         if hit is None or hit[0] != tag:
             with torch.no_grad():
                 t = fn(*[p.detach() for p in params])
+            if hit is not None:  # the old image is freed: captured CUDA graphs that read it are stale
+                from .. import ops
+                ops.bump_generation()
             self._store[name] = (tag, t)
             return t
         return hit[1]

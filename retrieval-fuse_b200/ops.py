@@ -35,6 +35,69 @@ def _count(n=1):
     _launches += n
 
 
+# ---- per-call device timing (bench.py's live roofline figures) --------------------------------
+# profile_start() makes every op below bracket its launches with a CUDA event pair on the launching
+# stream; profile_stop() returns {op name: {"calls", "ms", "flops", "bytes"}}.  Off by default (two event
+# records per call); never on inside a timed region or a graph capture.
+_prof = None
+
+
+def profile_start():
+    global _prof
+    _prof = []
+
+
+def profile_stop():
+    global _prof
+    recs, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, flops, nbytes in recs:
+        d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["calls"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += flops
+        d["bytes"] += nbytes
+    return out
+
+
+class _timed:
+    __slots__ = ("name", "flops", "bytes", "e0")
+
+    def __init__(self, name, flops=0.0, nbytes=0.0):
+        self.name, self.flops, self.bytes, self.e0 = name, flops, nbytes, None
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None and _prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.name, self.e0, e1, self.flops, self.bytes))
+        return False
+
+
+# ---- persistent device buffers referenced by captured CUDA graphs -----------------------------
+# The halo operand planes and the derived weight images are allocated once and reused across calls, so a captured
+# graph holds raw pointers to them.  Whenever one of them is FREED (a plane set evicted, a weight image rebuilt after
+# load_state_dict / an optimizer step) the generation changes and RefinementPipeline drops its graphs.
+_generation = 0
+MAX_PLANE_SHAPES = 4  # operand-plane sets kept per layer (one per input shape, least recently used evicted)
+
+
+def persistent_generation() -> int:
+    return _generation
+
+
+def bump_generation() -> None:
+    global _generation
+    _generation += 1
+
+
 def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
@@ -70,7 +133,7 @@ def unfold3d(x: torch.Tensor, E: int) -> torch.Tensor:
     assert x.dim() == 5 and x.shape[3] == S and x.shape[4] == S, "Unfold3D expects a cubic [B,C,S,S,S] volume"
     R = S // E
     out = torch.empty((B * R * R * R, C, E, E, E), device=x.device, dtype=x.dtype)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_unfold3d", nbytes=2.0 * x.numel() * 4):
         check(_lib.lib().rf_unfold3d(x.data_ptr(), out.data_ptr(), B, C, S, E, _stream(x)), "rf_unfold3d")
     _count()
     return out
@@ -84,7 +147,7 @@ def fold3d(x: torch.Tensor, R: int, E: int, nf: int) -> torch.Tensor:
     assert x.numel() % per == 0, "Fold3D: input size does not match num_patch_x / patch_extent / nf"
     B = x.numel() // per
     out = torch.empty((B, nf, R * E, R * E, R * E), device=x.device, dtype=x.dtype)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_fold3d", nbytes=2.0 * x.numel() * 4):
         check(_lib.lib().rf_fold3d(x.data_ptr(), out.data_ptr(), B, nf, R, E, _stream(x)), "rf_fold3d")
     _count()
     return out
@@ -101,7 +164,7 @@ def unfold3d_pad_stride(x, kernel, pad, stride, pad_val, norm_sub=0.0, norm_div=
     rows = B * cnt[0] * cnt[1] * cnt[2]
     shape = (rows, C, k[0], k[1], k[2]) if keep_channels else (rows * C, 1, k[0], k[1], k[2])
     out = torch.empty(shape, device=x.device, dtype=x.dtype)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_unfold3d_pad_stride", nbytes=(x.numel() + out.numel()) * 4.0):
         check(_lib.lib().rf_unfold3d_pad_stride(x.data_ptr(), out.data_ptr(), B, C, int3(size), k, p, s, float(pad_val),
                                                 float(norm_sub), float(norm_div), _stream(x)), "rf_unfold3d_pad_stride")
     _count()
@@ -118,7 +181,7 @@ def recompose_patches(patches, out_shape, kernel, pad, stride, count, pad_val):
     if patches.shape[1] != n:  # extra trailing patches are never read by the reference either
         patches = patches[:, :n].contiguous()
     out = torch.empty((B, C) + size, device=patches.device, dtype=patches.dtype)
-    with torch.cuda.device(patches.device):
+    with torch.cuda.device(patches.device), _timed("rf_recompose_patches"):
         check(_lib.lib().rf_recompose_patches(patches.data_ptr(), out.data_ptr(), B, C, int3(size), int3(kernel),
                                               int3(pad), int3(stride), int3(count), float(pad_val), _stream(patches)),
               "rf_recompose_patches")
@@ -155,7 +218,7 @@ def conv3d(x, wt, bias=None, *, cout, ks, stride=1, pad=0, act=ACT_NONE, slope=0
     Do, Ho, Wo = [(v + 2 * pad - ks) // stride + 1 for v in (D, H, W)]
     y = torch.empty((N, cout, Do, Ho, Wo), device=ref.device, dtype=torch.float32)
     g = gn if gn is not None else (None, None, None)
-    with torch.cuda.device(ref.device):
+    with torch.cuda.device(ref.device), _timed("rf_conv3d_fwd"):
         check(_lib.lib().rf_conv3d_fwd(_ptr(x), _ptr(x2), C2, wt.data_ptr(), _ptr(bias), _ptr(oscale), _ptr(oshift),
                                        _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), y.data_ptr(), N, cin, D, H, W, cout, ks,
                                        stride, pad, act, float(slope), _stream(ref)), "rf_conv3d_fwd")
@@ -171,7 +234,7 @@ def linear(x, wt, bias=None, act=ACT_NONE, slope=0.0):
     assert wt.shape[0] == K
     N = wt.shape[1]
     y = torch.empty((M, N), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_linear_fwd"):
         check(_lib.lib().rf_linear_fwd(x.data_ptr(), wt.data_ptr(), _ptr(bias), y.data_ptr(), M, K, N, act, float(slope),
                                        _stream(x)), "rf_linear_fwd")
     _count()
@@ -194,7 +257,7 @@ def tc_weight_image(weight):
     buf = torch.empty(nbytes + 1024, device=weight.device, dtype=torch.uint8)
     off = (-buf.data_ptr()) % 1024
     img = buf[off: off + nbytes]
-    with torch.cuda.device(weight.device):
+    with torch.cuda.device(weight.device), _timed("rf_tc_weight_image"):
         check(L.rf_tc_weight_image(weight.data_ptr(), N, K, img.data_ptr(), _stream(weight)), "rf_tc_weight_image")
     _count()
     return img
@@ -205,7 +268,7 @@ def tc_linear(x, weight_image, bias, N, act=ACT_NONE, slope=0.0):
     x = _dev(x, name="x")
     M, K = x.shape
     y = torch.empty((M, N), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_tc_linear_fwd"):
         check(_lib.lib().rf_tc_linear_fwd(x.data_ptr(), K, weight_image.data_ptr(), _ptr(bias), y.data_ptr(), M, K, N, act,
                                           float(slope), _stream(x)), "rf_tc_linear_fwd")
     _count()
@@ -232,7 +295,7 @@ def tc_mlp_weight_image(weight):
     if nbytes == 0:
         raise _lib.RfError(f"fused MLP does not support a weight of shape {tuple(weight.shape)}")
     img = _aligned_bytes(nbytes, weight.device)
-    with torch.cuda.device(weight.device):
+    with torch.cuda.device(weight.device), _timed("rf_tc_mlp_weight_image"):
         check(L.rf_tc_mlp_weight_image(weight.data_ptr(), N, K, img.data_ptr(), _stream(weight)), "rf_tc_mlp_weight_image")
     _count()
     return img
@@ -245,7 +308,7 @@ def tc_mlp(x, images, biases, widths, act=ACT_RELU, slope=0.0, l2_normalize=Fals
     M = x.shape[0]
     assert x.shape[1] == widths[0] and len(images) == len(widths) - 1
     y = torch.empty((M, widths[-1]), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_tc_mlp_fwd"):
         check(_lib.lib().rf_tc_mlp_fwd(x.data_ptr(), x.shape[1], ptr_array([i.data_ptr() for i in images]),
                                        ptr_array([_ptr(b) for b in biases]), _widths_arr(widths), len(widths) - 1, act,
                                        float(slope), int(bool(l2_normalize)), float(eps), y.data_ptr(), widths[-1], M,
@@ -267,7 +330,7 @@ def cl_from_ncdhw(x):
     if C == 1:
         return x.reshape(N, D, H, W, 1)
     y = torch.empty((N, D, H, W, C), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_cl_transpose"):
         check(_lib.lib().rf_cl_transpose(x.data_ptr(), y.data_ptr(), N, D * H * W, C, 1, _stream(x)), "rf_cl_transpose")
     _count()
     return y
@@ -279,7 +342,7 @@ def cl_to_ncdhw(x):
     if C == 1:
         return x.reshape(N, 1, D, H, W)
     y = torch.empty((N, C, D, H, W), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_cl_transpose"):
         check(_lib.lib().rf_cl_transpose(x.data_ptr(), y.data_ptr(), N, D * H * W, C, 0, _stream(x)), "rf_cl_transpose")
     _count()
     return y
@@ -297,7 +360,7 @@ def cl_gn_stats(x, gamma, groups, eps=1e-5, x2=None):
     mu = torch.empty((N, C), device=x.device, dtype=torch.float32)
     a = torch.empty((N, C), device=x.device, dtype=torch.float32)
     ws = torch.empty((N, C, 2), device=x.device, dtype=torch.float64)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_cl_gn_stats", nbytes=4.0 * x.numel()):
         check(_lib.lib().rf_cl_gn_stats(x.data_ptr(), _ptr(x2), C2, gamma.data_ptr(), mu.data_ptr(), a.data_ptr(), N, C, D, H,
                                         W, groups, float(eps), ws.data_ptr(), _stream(x)), "rf_cl_gn_stats")
     _count(3 if x2 is not None else 2)
@@ -317,7 +380,7 @@ def cl_norm_split(x, gn=None, c_off=0, scale=1.0):
     lo = torch.empty((N, D, H, W, Cp), device=x.device, dtype=torch.int16)
     mu, a, beta = gn if gn is not None else (None, None, None)
     c_tot = mu.shape[1] if mu is not None else C
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_cl_norm_split"):
         check(_lib.lib().rf_cl_norm_split(x.data_ptr(), _ptr(mu), _ptr(a), _ptr(beta), c_off, c_tot, hi.data_ptr(),
                                           lo.data_ptr(), N, D * H * W, C, Cp, float(scale), _stream(x)), "rf_cl_norm_split")
     _count()
@@ -328,7 +391,7 @@ def cl_maxpool3d_2(x):
     x = _dev(x, name="x")
     N, D, H, W, C = x.shape
     y = torch.empty((N, D // 2, H // 2, W // 2, C), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_cl_maxpool3d_2", nbytes=4.5 * x.numel()):
         check(_lib.lib().rf_cl_maxpool3d_2(x.data_ptr(), y.data_ptr(), N, D, H, W, C, _stream(x)), "rf_cl_maxpool3d_2")
     _count()
     return y
@@ -343,7 +406,7 @@ def conv3d_cin1_cl(x, weight, bias, gn=None, ks=3, stride=1, pad=0, act=ACT_NONE
     Do, Ho, Wo = [(v + 2 * pad - ks) // stride + 1 for v in (D, H, W)]
     y = torch.empty((N, Do, Ho, Wo, cout), device=x.device, dtype=torch.float32)
     mu, a, beta = gn if gn is not None else (None, None, None)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_conv3d_cin1_cl_fwd"):
         check(_lib.lib().rf_conv3d_cin1_cl_fwd(x.data_ptr(), weight.data_ptr(), _ptr(bias), _ptr(mu), _ptr(a), _ptr(beta),
                                                y.data_ptr(), N, D, H, W, cout, ks, stride, pad, act, float(slope), _stream(x)),
               "rf_conv3d_cin1_cl_fwd")
@@ -358,7 +421,7 @@ def cl_pointwise_head(x, weight, bias, act=ACT_NONE, slope=0.0):
     weight = _dev(weight.detach().reshape(-1), name="weight")
     assert weight.numel() == C
     y = torch.empty((N, 1, D, H, W), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_cl_pointwise_head"):
         check(_lib.lib().rf_cl_pointwise_head(x.data_ptr(), weight.data_ptr(), _ptr(bias), y.data_ptr(), N * D * H * W, C, act,
                                               float(slope), _stream(x)), "rf_cl_pointwise_head")
     _count()
@@ -383,7 +446,7 @@ def tc_conv_weight_image(weight, c1, c2):
     if nbytes == 0:
         raise _lib.RfError(f"tensor-core conv does not support weight {tuple(weight.shape)}")
     img = _aligned_bytes(nbytes, weight.device)
-    with torch.cuda.device(weight.device):
+    with torch.cuda.device(weight.device), _timed("rf_tc_conv_weight_image"):
         check(L.rf_tc_conv_weight_image(weight.data_ptr(), cout, c1, c2, ks, scale, img.data_ptr(), _stream(weight)),
               "rf_tc_conv_weight_image")
     _count()
@@ -404,7 +467,7 @@ def tc_conv3d(xs, x2s, c1, c2, img, bias, cout, ks, stride=1, pad=0, act=ACT_NON
     y = torch.empty(shape, device=dev, dtype=torch.float32)
     xh, xl = (xs[0].data_ptr(), xs[1].data_ptr()) if xs is not None else (None, None)
     x2h, x2l = (x2s[0].data_ptr(), x2s[1].data_ptr()) if x2s is not None else (None, None)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("rf_tc_conv3d_fwd", flops=2.0 * N * Do * Ho * Wo * ks ** 3 * (c1 + c2) * cout):
         check(_lib.lib().rf_tc_conv3d_fwd(xh, xl, c1, x2h, x2l, c2, img.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W, cout,
                                           ks, stride, pad, act, float(slope), float(out_scale), int(bool(out_ncdhw)),
                                           torch.cuda.current_stream(dev).cuda_stream), "rf_tc_conv3d_fwd")
@@ -449,16 +512,23 @@ def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0, pad=1, buffers=None):
     if buffers is not None:
         key = (N, D, H, W, c1, c2, int(pad), src.device)
         if key not in buffers:
-            buffers.clear()  # one shape at a time per layer: a new batch size replaces the old planes
+            # planes are kept per input shape: a CUDA graph captured for another batch size still points at its own
+            # set.  Only when more than MAX_PLANE_SHAPES shapes are live is the least recently used set freed, and
+            # that invalidates every captured graph (bump_generation)
+            while len(buffers) >= MAX_PLANE_SHAPES:
+                buffers.pop(next(iter(buffers)))
+                bump_generation()
             buffers[key] = (torch.zeros(nbytes, device=src.device, dtype=torch.uint8),
                             torch.zeros(nbytes, device=src.device, dtype=torch.uint8))
+        else:
+            buffers[key] = buffers.pop(key)  # most recently used last
         hi, lo = buffers[key]
         interior_only = 1
     else:
         hi = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
         lo = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
     mu, a, beta = gn if gn is not None else (None, None, None)
-    with torch.cuda.device(src.device):
+    with torch.cuda.device(src.device), _timed("rf_cl_norm_split_halo", nbytes=(c1 + c2) * 8.0 * N * D * H * W):
         check(L.rf_cl_norm_split_halo(_ptr(x), c1, _ptr(x2), c2, _ptr(mu), _ptr(a), _ptr(beta), hi.data_ptr(), lo.data_ptr(),
                                       N, D, H, W, int(pad), float(scale), interior_only, _stream(src)), "rf_cl_norm_split_halo")
     _count()
@@ -478,7 +548,7 @@ def tc_conv_halo_weight_image(weight, c1, c2):
     if nbytes == 0:
         raise _lib.RfError(f"halo conv does not support weight {tuple(weight.shape)}")
     img = _aligned_bytes(nbytes, weight.device)
-    with torch.cuda.device(weight.device):
+    with torch.cuda.device(weight.device), _timed("rf_tc_conv_halo_weight_image"):
         check(L.rf_tc_conv_halo_weight_image(weight.data_ptr(), cout, c1, c2, scale, img.data_ptr(), _stream(weight)),
               "rf_tc_conv_halo_weight_image")
     _count()
@@ -492,7 +562,7 @@ def tc_conv3d_halo(split, img, bias, cout, act=ACT_NONE, slope=0.0, out_ncdhw=Fa
     Do, Ho, Wo = D + 2 * pad - 2, H + 2 * pad - 2, W + 2 * pad - 2
     shape = (N, cout, Do, Ho, Wo) if out_ncdhw else (N, Do, Ho, Wo, cout)
     y = torch.empty(shape, device=hi.device, dtype=torch.float32)
-    with torch.cuda.device(hi.device):
+    with torch.cuda.device(hi.device), _timed("rf_tc_conv3d_halo_fwd", flops=2.0 * N * Do * Ho * Wo * 27 * (c1 + c2) * cout):
         check(_lib.lib().rf_tc_conv3d_halo_fwd(hi.data_ptr(), lo.data_ptr(), img.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W,
                                                pad, cout, c1, c2, act, float(slope), float(out_scale), int(bool(out_ncdhw)),
                                                torch.cuda.current_stream(hi.device).cuda_stream), "rf_tc_conv3d_halo_fwd")
@@ -516,7 +586,7 @@ def groupnorm_stats(x, gamma, groups, eps=1e-5, x2=None):
     C = C1 + C2
     mu = torch.empty((N, C), device=ref.device, dtype=torch.float32)
     a = torch.empty((N, C), device=ref.device, dtype=torch.float32)
-    with torch.cuda.device(ref.device):
+    with torch.cuda.device(ref.device), _timed("rf_groupnorm_stats"):
         check(_lib.lib().rf_groupnorm_stats(_ptr(x), _ptr(x2), C2, gamma.data_ptr(), mu.data_ptr(), a.data_ptr(), N, C,
                                             D, H, W, groups, float(eps), _stream(ref)), "rf_groupnorm_stats")
     _count()
@@ -527,7 +597,7 @@ def maxpool3d_2(x):
     x = _dev(x, name="x")
     N, C, D, H, W = x.shape
     y = torch.empty((N, C, D // 2, H // 2, W // 2), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_maxpool3d_2"):
         check(_lib.lib().rf_maxpool3d_2(x.data_ptr(), y.data_ptr(), N, C, D, H, W, _stream(x)), "rf_maxpool3d_2")
     _count()
     return y
@@ -537,7 +607,7 @@ def upsample_nearest_2(x):
     x = _dev(x, name="x")
     N, C, D, H, W = x.shape
     y = torch.empty((N, C, 2 * D, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_upsample_nearest_2"):
         check(_lib.lib().rf_upsample_nearest_2(x.data_ptr(), y.data_ptr(), N, C, D, H, W, _stream(x)),
               "rf_upsample_nearest_2")
     _count()
@@ -549,7 +619,7 @@ def l2_normalize_rows(x, eps=1e-12):
     x = _dev(x, name="x")
     M, D = x.shape
     y = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_l2_normalize_rows"):
         check(_lib.lib().rf_l2_normalize_rows(x.data_ptr(), y.data_ptr(), M, D, float(eps), _stream(x)),
               "rf_l2_normalize_rows")
     _count()
@@ -568,7 +638,7 @@ def mlp_encode(x, wts, biases, l2_normalize=True):
     ws_bytes = L.rf_mlp_encode_workspace_bytes(M, warr, n)
     ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
     out = torch.empty((M, widths[-1]), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_mlp_encode_fwd"):
         check(L.rf_mlp_encode_fwd(x.data_ptr(), ptr_array([w.data_ptr() for w in wts]),
                                   ptr_array([b.data_ptr() for b in biases]), warr, n, int(bool(l2_normalize)),
                                   out.data_ptr(), M, ws.data_ptr(), ws_bytes, _stream(x)), "rf_mlp_encode_fwd")
@@ -596,7 +666,7 @@ def knn_topk(bank, q, k, row_offset=0, method=0, stats=False):
     d = torch.empty((Q, k), device=q.device, dtype=torch.float64)
     ws_bytes = L.rf_knn_workspace_bytes(Q, n, k, method)
     ws = torch.empty(max(ws_bytes, 256), device=q.device, dtype=torch.uint8)
-    with torch.cuda.device(q.device):
+    with torch.cuda.device(q.device), _timed("rf_knn_l2_topk", flops=2.0 * Q * n * 64):
         check(L.rf_knn_l2_topk(bank.data_ptr(), n, int(row_offset), q.data_ptr(), Q, D, k, method, idx.data_ptr(),
                                d.data_ptr(), ws.data_ptr(), ws.numel(), _stream(q)), "rf_knn_l2_topk")
         if stats:
@@ -617,7 +687,7 @@ def knn_merge(parts_idx, parts_d):
     S, Q, k = parts_idx.shape
     idx = torch.empty((Q, k), device=parts_idx.device, dtype=torch.int32)
     d = torch.empty((Q, k), device=parts_idx.device, dtype=torch.float64)
-    with torch.cuda.device(parts_idx.device):
+    with torch.cuda.device(parts_idx.device), _timed("rf_knn_merge"):
         check(_lib.lib().rf_knn_merge(parts_idx.data_ptr(), parts_d.data_ptr(), S, Q, k, idx.data_ptr(), d.data_ptr(),
                                       _stream(parts_idx)), "rf_knn_merge")
     _count()
@@ -634,7 +704,7 @@ def knn_demote_rows(idx2k, d2k, meta, query_scene, K):
         query_scene = _dev(query_scene, torch.int32, "query_scene")
     rows = torch.empty((Q, K, 8), device=idx2k.device, dtype=torch.float32)
     idx = torch.empty((Q, K), device=idx2k.device, dtype=torch.int32)
-    with torch.cuda.device(idx2k.device):
+    with torch.cuda.device(idx2k.device), _timed("rf_knn_demote_rows"):
         check(_lib.lib().rf_knn_demote_rows(idx2k.data_ptr(), d2k.data_ptr(), meta.data_ptr(), _ptr(query_scene), Q, K2,
                                             K, rows.data_ptr(), idx.data_ptr(), _stream(idx2k)), "rf_knn_demote_rows")
     _count()
@@ -655,7 +725,7 @@ def compose_gather(rows, dst_extents, scene_store, n_chunks, chunk_size, trunc, 
     shape = (n_chunks, K) + tuple(int(v) for v in chunk_size)
     out = (torch.full(shape, float(trunc), device=rows.device, dtype=torch.float32) if prefill
            else torch.empty(shape, device=rows.device, dtype=torch.float32))
-    with torch.cuda.device(rows.device):
+    with torch.cuda.device(rows.device), _timed("rf_compose_gather", nbytes=2.0 * out.numel() * 4):
         check(_lib.lib().rf_compose_gather(rows.data_ptr(), dst_extents.data_ptr(), scene_store.data_ptr(),
                                            out.data_ptr(), n_chunks, P, K, scene_store.shape[0],
                                            int3(scene_store.shape[1:]), int3(chunk_size), float(trunc), float(ratio),
@@ -688,7 +758,7 @@ def attention_fuse(x_back, x_retr, theta, phi, E, K, normalize=True, mode=0, ble
     out = torch.empty_like(x_back)
     if gumbel_noise is not None:
         gumbel_noise = _dev(gumbel_noise, name="gumbel_noise")
-    with torch.cuda.device(x_back.device):
+    with torch.cuda.device(x_back.device), _timed("rf_attention_fuse_fwd", nbytes=(K + 2.0) * nf * S ** 3 * 4 * B):
         check(L.rf_attention_fuse_fwd(x_back.data_ptr(), x_retr.data_ptr(),
                                       ptr_array([w.data_ptr() for w in theta[0]]),
                                       ptr_array([b.data_ptr() for b in theta[1]]),
@@ -715,7 +785,7 @@ def attention_features(x, t, occ, theta, phi, E, normalize=True):
     xf = torch.empty((R, 32), device=x.device, dtype=torch.float32)
     pf = torch.empty((R, 32), device=x.device, dtype=torch.float32)
     oa = torch.empty((R,), device=x.device, dtype=torch.uint8)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("rf_attention_features"):
         check(L.rf_attention_features(x.data_ptr(), t.data_ptr(), occ_u8.data_ptr(),
                                       ptr_array([w.data_ptr() for w in theta[0]]),
                                       ptr_array([b.data_ptr() for b in theta[1]]),
@@ -738,7 +808,7 @@ def sobel_normals(target, pad_val):
     assert target.dim() == 5 and target.shape[1] == 1, "compute_normals expects [B,1,D,H,W]"
     B, _, D, H, W = target.shape
     out = torch.empty((B, 3, D, H, W), device=target.device, dtype=torch.float32)
-    with torch.cuda.device(target.device):
+    with torch.cuda.device(target.device), _timed("rf_sobel_normals"):
         check(_lib.lib().rf_sobel_normals(target.data_ptr(), out.data_ptr(), B, D, H, W, float(pad_val), _stream(target)),
               "rf_sobel_normals")
     _count()
@@ -753,7 +823,7 @@ def occupancy_counts(pred, target):
     pred, target = pred.contiguous(), target.contiguous()
     B = pred.shape[0]
     counts = torch.empty((B, 4), device=pred.device, dtype=torch.int64)
-    with torch.cuda.device(pred.device):
+    with torch.cuda.device(pred.device), _timed("rf_occupancy_counts"):
         check(_lib.lib().rf_occupancy_counts(pred.data_ptr(), target.data_ptr(), B, pred[0].numel(), counts.data_ptr(),
                                              _stream(pred)), "rf_occupancy_counts")
     _count()
@@ -767,7 +837,7 @@ def chamfer_nn(a, b):
     assert a.dim() == 2 and a.shape[1] == 3 and b.dim() == 2 and b.shape[1] == 3
     dist = torch.empty(a.shape[0], device=a.device, dtype=torch.float32)
     idx = torch.empty(a.shape[0], device=a.device, dtype=torch.int32)
-    with torch.cuda.device(a.device):
+    with torch.cuda.device(a.device), _timed("rf_chamfer_nn"):
         check(_lib.lib().rf_chamfer_nn(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], dist.data_ptr(), idx.data_ptr(),
                                        _stream(a)), "rf_chamfer_nn")
     _count()
@@ -787,7 +857,7 @@ def ntxent(zis, zjs, temperature, cosine=True, iou_matrix=None, sig_scale=80.0, 
     L = _lib.lib()
     ws = torch.empty(max(L.rf_ntxent_workspace_bytes(N), 16), device=zis.device, dtype=torch.uint8)
     loss = torch.empty(1, device=zis.device, dtype=torch.float32)
-    with torch.cuda.device(zis.device):
+    with torch.cuda.device(zis.device), _timed("rf_ntxent_fwd"):
         check(L.rf_ntxent_fwd(zis.data_ptr(), zjs.data_ptr(), N, C, iou_matrix.data_ptr() if iou_matrix is not None else None,
                               float(temperature), float(sig_scale), float(sig_shift), 1 if cosine else 0, loss.data_ptr(),
                               ws.data_ptr(), ws.numel(), _stream(zis)), "rf_ntxent_fwd")

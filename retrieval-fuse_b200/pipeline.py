@@ -268,7 +268,11 @@ class RefinementPipeline(RetrievalPipeline):
         launches of a forward are submitted as one graph, which removes the host-side launch
         gaps between the many small kernels of the 8^3 backbone.  Returns pred only."""
         if not hasattr(self, "_graphs"):
-            self._graphs = {}
+            self._graphs, self._graphs_gen = {}, ops.persistent_generation()
+        if self._graphs_gen != ops.persistent_generation():
+            # a persistent buffer the captured kernels point at (operand planes, weight images) was freed since the
+            # capture: every graph is stale
+            self._graphs.clear()
         key = (tuple(x_in.shape), tuple(retrieval.shape))
         if key not in self._graphs:
             sx, sr = x_in.clone(), retrieval.clone()
@@ -282,6 +286,7 @@ class RefinementPipeline(RetrievalPipeline):
             with torch.cuda.graph(graph):
                 out = self.refine(sx, sr)[0]
             self._graphs[key] = (graph, sx, sr, out)
+            self._graphs_gen = ops.persistent_generation()
         graph, sx, sr, out = self._graphs[key]
         sx.copy_(x_in, non_blocking=True)
         sr.copy_(retrieval, non_blocking=True)
@@ -292,6 +297,44 @@ class RefinementPipeline(RetrievalPipeline):
         """network_pred_to_df (trainer/train_refinement.py:242-243) - host-side scaling
         of a result tensor, not part of the kernels' work."""
         return (pred + 1) * self.target_trunc / 2
+
+    def infer(self, chunks, chunk_scene=None, method=0, refine_batch=None, graphed=True, out=None, marks=None):
+        """The whole hot path for a batch of raw low-res chunks on the GPU: encode -> kNN (fetch 2K, demote, keep K)
+        -> compose (the dataloader's normalisation fused) -> U-Nets + patch attention + decoder, i.e. what
+        `util/retrieval.py --mode map compose` followed by `forward_full` (trainer/train_refinement.py:108-120)
+        computes, without the .npz round trip.  chunks [B,1,s,s,s] -> pred [B,1,64,64,64] in [-1, 1].
+        marks: optional list that receives five CUDA events (start, encoded, looked up, composed, refined).
+        The refinement runs in sub-batches of `refine_batch` chunks (CUDA-graph replay per sub-batch shape)."""
+        B = chunks.shape[0]
+        mark = (lambda: None) if marks is None else (lambda: (marks.append(torch.cuda.Event(enable_timing=True)), marks[-1].record()))
+        mark()
+        q = self.encode_queries(chunks)
+        mark()
+        rows, _ = self.lookup(q, self.expand_scene(chunk_scene), method)
+        mark()
+        retr = self.compose(rows, B, normalize=True)
+        x_in = self.normalize_input(chunks)
+        mark()
+        rb = refine_batch or B
+        c = self.ds["target_chunk_size"]
+        pred = out if out is not None else torch.empty((B, 1, c, c, c), dtype=torch.float32, device=self.device)
+        for lo in range(0, B, rb):
+            hi = min(B, lo + rb)
+            if graphed:
+                pred[lo:hi].copy_(self.refine_graphed(x_in[lo:hi], retr[lo:hi]))
+            else:
+                pred[lo:hi].copy_(self.refine(x_in[lo:hi], retr[lo:hi])[0])
+        mark()
+        return pred
+
+    def infer_host(self, chunks_host, out_host, chunk_scene=None, method=0, refine_batch=None, graphed=True):
+        """infer() with HOST buffers on both sides (pinned): chunks_host [B,1,s,s,s] -> out_host [B,1,64,64,64];
+        the host->device copy of the inputs and the device->host copy of the prediction are part of the call."""
+        x = chunks_host.to(self.device, non_blocking=True)
+        pred = self.infer(x, chunk_scene, method, refine_batch, graphed)
+        out_host.copy_(pred, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_host
 
     def retrieve_and_refine(self, chunks, chunk_scene=None, method=0):
         B = chunks.shape[0]
