@@ -206,21 +206,38 @@ int rf_mlp_encode_fwd(const float* x, const float* const* wt_host, const float* 
  * out_idx [Q,k] int32 global ids, out_d [Q,k] fp64.  D must be 64.
  * method: 0 = auto, 1 = exact fp64 sweep, 2 / 3 = tcgen05 candidate pass (2:
  * one fp16 GEMM; 3: bf16 hi/lo split, K = 192; fp32 accumulators in TMEM) that
- * keeps 16 candidates per query, then the canonical fp64 re-rank, a proof that
- * no rejected row can enter or tie the top-k, and the fp64 sweep for the queries
- * whose proof fails.  All methods return identical results (k <= 16 for 2 / 3).
- * Methods 2 / 3 synchronise `stream` once (to read the unproven-query count). */
+ * keeps 16 (k <= 8) or 32 candidates per query and bank slice, then the
+ * canonical fp64 re-rank, a proof that no rejected row can enter or tie the
+ * top-k, and the fp64 sweep for the queries whose proof fails - enqueued
+ * unconditionally and sized by a device-side counter, so no method ever
+ * synchronises `stream` (the call can be captured in a CUDA graph).  All
+ * methods return identical results; k <= 32. */
 size_t rf_knn_workspace_bytes(long Q, long n_rows, int k, int method);
 int rf_knn_l2_topk(const float* bank, long n_rows, long row_offset, const float* q, long Q, int D, int k, int method,
                    int* out_idx, double* out_d, void* workspace, size_t workspace_bytes, void* stream);
-/* Diagnostics of the last method-2/3 call that used `workspace`: number of
- * queries that needed the exact re-check and the largest observed error of the
- * tensor-core score over all re-ranked candidates (validates the bound), and
- * the CUDA-event duration of the last candidates kernel launched by this
- * process (the kernel the roofline is quoted on). */
-int rf_knn_tc_stats(const void* workspace, int* n_unproven, float* max_score_err, float* candidates_ms, void* stream);
-/* CUDA-event duration (ms) of the candidates kernel of the last method-2/3 call in this process; -1 if none. */
-float rf_knn_last_candidates_ms(void);
+/* Prepared banks.  The reference loads its FLANN index once per worker and
+ * queries it many times (util/retrieval.py:81-92); here the bank's tensor-core
+ * operand image (scan order + swizzled 16-bit tiles + |x|^2 range) is built
+ * once by rf_knn_bank_prepare into a caller-owned buffer of
+ * rf_knn_bank_image_bytes and reused by every rf_knn_l2_topk_prepared call.
+ * q_sample (optional, n_sample rows): a sample of typical queries whose mean
+ * direction orders the scan (exactness is unaffected); NULL = the bank's own
+ * mean.  rf_knn_bank_method resolves method 0 for a bank of n_rows (1 = too
+ * small for the tensor-core path: use rf_knn_l2_topk). */
+int rf_knn_bank_method(long n_rows, int method);
+size_t rf_knn_bank_image_bytes(long n_rows, int method);
+size_t rf_knn_bank_scratch_bytes(long n_rows, int method);
+int rf_knn_bank_prepare(const float* bank, long n_rows, int method, const float* q_sample, long n_sample, void* image,
+                        size_t image_bytes, void* scratch, size_t scratch_bytes, void* stream);
+size_t rf_knn_prepared_workspace_bytes(long Q, long n_rows, int k, int method);
+int rf_knn_l2_topk_prepared(const float* bank, long n_rows, long row_offset, const void* image, int method, const float* q,
+                            long Q, int D, int k, int* out_idx, double* out_d, void* workspace, size_t workspace_bytes,
+                            void* stream);
+/* Diagnostics of the last method-2/3 call that used `workspace` (synchronises
+ * the stream): number of queries that needed the exact re-check and the
+ * largest observed error of the tensor-core score over all re-ranked
+ * candidates (validates the bound). */
+int rf_knn_tc_stats(const void* workspace, int* n_unproven, float* max_score_err, void* stream);
 /* Merge S sorted candidate lists per query (shards of one GPU sweep or the
  * all-gathered per-rank lists): parts_idx/parts_d [S,Q,k] -> [Q,k]
  * under the same (d, id) order. */

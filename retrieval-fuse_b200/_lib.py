@@ -75,8 +75,14 @@ PROTOTYPES = {
     "rf_knn_workspace_bytes": (c_size_t, [c_long, c_long, c_int, c_int]),
     "rf_knn_l2_topk": (c_int, [c_void_p, c_long, c_long, c_void_p, c_long, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_size_t, c_void_p]),
-    "rf_knn_tc_stats": (c_int, [c_void_p, POINTER(c_int), POINTER(c_float), POINTER(c_float), c_void_p]),
-    "rf_knn_last_candidates_ms": (c_float, []),
+    "rf_knn_tc_stats": (c_int, [c_void_p, POINTER(c_int), POINTER(c_float), c_void_p]),
+    "rf_knn_bank_method": (c_int, [c_long, c_int]),
+    "rf_knn_bank_image_bytes": (c_size_t, [c_long, c_int]),
+    "rf_knn_bank_scratch_bytes": (c_size_t, [c_long, c_int]),
+    "rf_knn_bank_prepare": (c_int, [c_void_p, c_long, c_int, c_void_p, c_long, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "rf_knn_prepared_workspace_bytes": (c_size_t, [c_long, c_long, c_int, c_int]),
+    "rf_knn_l2_topk_prepared": (c_int, [c_void_p, c_long, c_long, c_void_p, c_int, c_void_p, c_long, c_int, c_int, c_void_p,
+                                        c_void_p, c_void_p, c_size_t, c_void_p]),
     "rf_knn_merge": (c_int, [c_void_p, c_void_p, c_int, c_long, c_int, c_void_p, c_void_p, c_void_p]),
     "rf_knn_demote_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p]),

@@ -40,115 +40,132 @@ __device__ __forceinline__ void warp_list_insert(double& ld, int& li, double cd,
     else if (lane > pos) { ld = ud; li = ui; }
 }
 
+// Query window of one launch.  Host-sized sweeps pass q_count = nullptr (queries [0, Q)).  The re-check of the
+// tensor-core path's unproven queries passes the DEVICE counter instead (no host synchronisation): the launch then
+// covers queries [q_first, min(*q_count, q_first + q_cap)) of the q_sel list, CTAs walk the query blocks with a grid
+// stride and leave at once when there is nothing to do.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) knn_exact_f64_kernel(const float* __restrict__ bank, long n_rows,
                                                                            long row_offset, const float* __restrict__ q,
-                                                                           long Q, int k, int nsplit,
+                                                                           long Q, const int* __restrict__ q_count,
+                                                                           long q_first, long q_cap, int k, int nsplit,
                                                                            const int* __restrict__ q_sel,
                                                                            int* __restrict__ out_idx,
                                                                            double* __restrict__ out_d) {
     __shared__ double qs[QB][D64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long q_cta = (long)blockIdx.x * QB;
-    for (int i = threadIdx.x; i < QB * D64; i += blockDim.x) {
-        const long qi = q_cta + i / D64;
-        // q_sel (optional) selects a subset of the query matrix: the re-check of unproven queries
-        qs[i / D64][i % D64] = qi < Q ? (double)q[(q_sel ? (long)q_sel[qi] : qi) * D64 + (i % D64)] : 0.0;
+    long q_lo = 0, q_hi = Q, stride = Q;
+    if (q_count) {
+        const long n = (long)*q_count;
+        q_lo = q_first;
+        q_hi = n < q_first + q_cap ? n : q_first + q_cap;
+        stride = q_cap;
     }
-    __syncthreads();
-
     const int split = blockIdx.y;
     const long per = ((n_rows + nsplit - 1) / nsplit + 31) / 32 * 32;
     const long r_begin = split * per;
     long r_end = r_begin + per;
     if (r_end > n_rows) r_end = n_rows;
 
-    double ld[QW];
-    int li[QW];
-    double tau_d[QW];
-    int tau_i[QW];
-#pragma unroll
-    for (int j = 0; j < QW; ++j) { ld[j] = DBL_MAX; li[j] = INT_MAX; tau_d[j] = DBL_MAX; tau_i[j] = INT_MAX; }
-
-    const double(*qw)[D64] = &qs[warp * QW];
-    // queries past the end of the list (the re-check of a handful of unproven queries fills a fraction of one CTA):
-    // a warp without queries leaves, the others skip their empty slots - the fp64 pipe is the bound of this kernel
-    const long nq_l = Q - q_cta - (long)warp * QW;
-    const int nq = nq_l >= QW ? QW : (int)nq_l;  // warp-uniform
-    if (nq <= 0) return;                         // (no block-level synchronisation follows)
-    for (long base = r_begin; base < r_end; base += 32) {
-        const long r = base + lane;
-        const bool valid = r < r_end;
-        // the row is converted to fp64 once and kept in registers for all 8 queries
-        double xd[D64];
-        const float4* src = reinterpret_cast<const float4*>(bank + (valid ? r : r_begin) * D64);
-#pragma unroll
-        for (int i = 0; i < D64 / 4; ++i) {
-            const float4 v = __ldg(src + i);
-            xd[4 * i] = (double)v.x; xd[4 * i + 1] = (double)v.y; xd[4 * i + 2] = (double)v.z; xd[4 * i + 3] = (double)v.w;
+    for (long q_cta = q_lo + (long)blockIdx.x * QB; q_cta < q_hi; q_cta += (long)gridDim.x * QB) {
+        __syncthreads();  // the previous block's queries have been consumed
+        for (int i = threadIdx.x; i < QB * D64; i += blockDim.x) {
+            const long qi = q_cta + i / D64;
+            // q_sel (optional) selects a subset of the query matrix: the re-check of unproven queries
+            qs[i / D64][i % D64] = qi < q_hi ? (double)q[(q_sel ? (long)q_sel[qi] : qi) * D64 + (i % D64)] : 0.0;
         }
-        const int gid = (int)(row_offset + r);
+        __syncthreads();
+
+        double ld[QW];
+        int li[QW];
+        double tau_d[QW];
+        int tau_i[QW];
 #pragma unroll
-        for (int j = 0; j < QW; ++j) {
-            if (j >= nq) break;
-            double acc = 0.0;
+        for (int j = 0; j < QW; ++j) { ld[j] = DBL_MAX; li[j] = INT_MAX; tau_d[j] = DBL_MAX; tau_i[j] = INT_MAX; }
+
+        const double(*qw)[D64] = &qs[warp * QW];
+        // queries past the end of the list (the re-check of a handful of unproven queries fills a fraction of one CTA):
+        // a warp without queries idles, the others skip their empty slots - the fp64 pipe is the bound of this kernel
+        const long nq_l = q_hi - q_cta - (long)warp * QW;
+        const int nq = nq_l >= QW ? QW : (int)nq_l;  // warp-uniform
+        if (nq <= 0) continue;                       // (still meets the barriers at the top of the next trip)
+        for (long base = r_begin; base < r_end; base += 32) {
+            const long r = base + lane;
+            const bool valid = r < r_end;
+            // the row is converted to fp64 once and kept in registers for all 8 queries
+            double xd[D64];
+            const float4* src = reinterpret_cast<const float4*>(bank + (valid ? r : r_begin) * D64);
 #pragma unroll
-            for (int i = 0; i < D64; ++i) {
-                const double diff = __dsub_rn(qw[j][i], xd[i]);
-                acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+            for (int i = 0; i < D64 / 4; ++i) {
+                const float4 v = __ldg(src + i);
+                xd[4 * i] = (double)v.x; xd[4 * i + 1] = (double)v.y; xd[4 * i + 2] = (double)v.z; xd[4 * i + 3] = (double)v.w;
             }
-            const bool hit = valid && cand_less(acc, gid, tau_d[j], tau_i[j]);
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int src_lane = __ffs(m) - 1;
-                m &= m - 1;
-                const double cd = __shfl_sync(0xffffffffu, acc, src_lane);
-                const int ci = __shfl_sync(0xffffffffu, gid, src_lane);
-                if (cand_less(cd, ci, tau_d[j], tau_i[j])) {  // warp-uniform
-                    warp_list_insert(ld[j], li[j], cd, ci, lane);
-                    tau_d[j] = __shfl_sync(0xffffffffu, ld[j], k - 1);
-                    tau_i[j] = __shfl_sync(0xffffffffu, li[j], k - 1);
+            const int gid = (int)(row_offset + r);
+#pragma unroll
+            for (int j = 0; j < QW; ++j) {
+                if (j >= nq) break;
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < D64; ++i) {
+                    const double diff = __dsub_rn(qw[j][i], xd[i]);
+                    acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+                }
+                const bool hit = valid && cand_less(acc, gid, tau_d[j], tau_i[j]);
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                while (m) {
+                    const int src_lane = __ffs(m) - 1;
+                    m &= m - 1;
+                    const double cd = __shfl_sync(0xffffffffu, acc, src_lane);
+                    const int ci = __shfl_sync(0xffffffffu, gid, src_lane);
+                    if (cand_less(cd, ci, tau_d[j], tau_i[j])) {  // warp-uniform
+                        warp_list_insert(ld[j], li[j], cd, ci, lane);
+                        tau_d[j] = __shfl_sync(0xffffffffu, ld[j], k - 1);
+                        tau_i[j] = __shfl_sync(0xffffffffu, li[j], k - 1);
+                    }
                 }
             }
         }
-    }
 #pragma unroll
-    for (int j = 0; j < QW; ++j) {
-        const long qi = q_cta + warp * QW + j;
-        if (qi < Q && lane < k) {
-            // single-slice sweeps write the final rows directly (through q_sel when given)
-            const long oq = (nsplit == 1 && q_sel) ? (long)q_sel[qi] : qi;
-            const long o = ((long)split * Q + oq) * k + lane;
-            out_idx[o] = li[j];
-            out_d[o] = ld[j];
+        for (int j = 0; j < QW; ++j) {
+            const long qi = q_cta + warp * QW + j;
+            if (qi < q_hi && lane < k) {
+                // single-slice sweeps write the final rows directly (through q_sel when given)
+                const long oq = (nsplit == 1 && q_sel) ? (long)q_sel[qi] : qi - q_lo;
+                const long o = ((long)split * stride + oq) * k + lane;
+                out_idx[o] = li[j];
+                out_d[o] = ld[j];
+            }
         }
     }
 }
 
 // One warp per query: fold S sorted k-lists into one under (d, id).
 __global__ void __launch_bounds__(128) knn_merge_kernel(const int* __restrict__ parts_idx,
-                                                        const double* __restrict__ parts_d, int S, long Q, int k,
+                                                        const double* __restrict__ parts_d, int S, long Q,
+                                                        const int* __restrict__ q_count, long q_cap, int k,
                                                         const int* __restrict__ q_sel, int* __restrict__ out_idx,
                                                         double* __restrict__ out_d) {
-    const long qi = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (qi >= Q) return;
-    double ld = DBL_MAX, tau_d = DBL_MAX;
-    int li = INT_MAX, tau_i = INT_MAX;
-    for (int s = 0; s < S; ++s) {
-        const long o = ((long)s * Q + qi) * k + lane;
-        const double md = lane < k ? parts_d[o] : DBL_MAX;
-        const int mi = lane < k ? parts_idx[o] : INT_MAX;
-        for (int t = 0; t < k; ++t) {
-            const double cd = __shfl_sync(0xffffffffu, md, t);
-            const int ci = __shfl_sync(0xffffffffu, mi, t);
-            if (!cand_less(cd, ci, tau_d, tau_i)) break;  // part lists are sorted: the rest is worse (warp-uniform)
-            warp_list_insert(ld, li, cd, ci, lane);
-            tau_d = __shfl_sync(0xffffffffu, ld, k - 1);
-            tau_i = __shfl_sync(0xffffffffu, li, k - 1);
+    long n = Q, stride = Q;
+    if (q_count) { n = (long)*q_count < q_cap ? (long)*q_count : q_cap; stride = q_cap; }  // device-sized re-check window
+    for (long qi = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5; qi < n; qi += ((long)gridDim.x * blockDim.x) >> 5) {
+        double ld = DBL_MAX, tau_d = DBL_MAX;
+        int li = INT_MAX, tau_i = INT_MAX;
+        for (int s = 0; s < S; ++s) {
+            const long o = ((long)s * stride + qi) * k + lane;
+            const double md = lane < k ? parts_d[o] : DBL_MAX;
+            const int mi = lane < k ? parts_idx[o] : INT_MAX;
+            for (int t = 0; t < k; ++t) {
+                const double cd = __shfl_sync(0xffffffffu, md, t);
+                const int ci = __shfl_sync(0xffffffffu, mi, t);
+                if (!cand_less(cd, ci, tau_d, tau_i)) break;  // part lists are sorted: the rest is worse (warp-uniform)
+                warp_list_insert(ld, li, cd, ci, lane);
+                tau_d = __shfl_sync(0xffffffffu, ld, k - 1);
+                tau_i = __shfl_sync(0xffffffffu, li, k - 1);
+            }
         }
+        const long oq = q_sel ? (long)q_sel[qi] : qi;
+        if (lane < k) { out_idx[oq * k + lane] = li; out_d[oq * k + lane] = ld; }
     }
-    const long oq = q_sel ? (long)q_sel[qi] : qi;
-    if (lane < k) { out_idx[oq * k + lane] = li; out_d[oq * k + lane] = ld; }
 }
 
 // util/retrieval.py:93-100 per query: stable partition by "same scene as the
@@ -199,9 +216,11 @@ int rf_knn_exact_nsplit(long Q, long n_rows) {
 int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, const int* q_sel,
                         int* out_idx, double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s) {
     const int nsplit = rf_knn_exact_nsplit(Q, n_rows);
-    dim3 grid((unsigned)((Q + QB - 1) / QB), nsplit);
+    long gx = (Q + QB - 1) / QB;
+    if (gx > 65535L * 16) gx = 65535L * 16;  // the kernel walks further query blocks with a grid stride
+    dim3 grid((unsigned)gx, nsplit);
     if (nsplit == 1) {
-        knn_exact_f64_kernel<<<grid, WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, k, 1, q_sel, out_idx, out_d);
+        knn_exact_f64_kernel<<<grid, WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, nullptr, 0, 0, k, 1, q_sel, out_idx, out_d);
         RF_LAUNCH_OK("knn_exact_f64_kernel");
         return 0;
     }
@@ -209,10 +228,45 @@ int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const f
     RF_CHECK_ARG(workspace && workspace_bytes >= need, "rf_knn_l2_topk: workspace too small (%zu < %zu)", workspace_bytes, need);
     double* pd = (double*)workspace;
     int* pi = (int*)(pd + (size_t)nsplit * Q * k);
-    knn_exact_f64_kernel<<<grid, WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, k, nsplit, q_sel, pi, pd);
+    knn_exact_f64_kernel<<<grid, WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, nullptr, 0, 0, k, nsplit, q_sel, pi, pd);
     RF_LAUNCH_OK("knn_exact_f64_kernel");
-    knn_merge_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, s>>>(pi, pd, nsplit, Q, k, q_sel, out_idx, out_d);
+    knn_merge_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, s>>>(pi, pd, nsplit, Q, nullptr, 0, k, q_sel, out_idx, out_d);
     RF_LAUNCH_OK("knn_merge_kernel");
+    return 0;
+}
+
+// The exact sweep for a DEVICE-sized list of queries (q_sel[0 .. *q_count)): the re-check of the tensor-core path's
+// unproven queries, enqueued unconditionally so that no host synchronisation is needed.  The first RF_RECHECK_CAP
+// queries are swept in RF_RECHECK_SLICES bank slices (+ merge) so that a handful of queries still spreads over the
+// chip; anything beyond the cap (a pathological bank) goes through single-slice CTAs.  All three launches return
+// immediately when *q_count is 0.
+static const long RF_RECHECK_CAP = 2048;
+static const int RF_RECHECK_SLICES = 64;
+size_t rf_knn_recheck_workspace_bytes(int k) {
+    return (size_t)RF_RECHECK_SLICES * RF_RECHECK_CAP * k * (sizeof(int) + sizeof(double)) + 256;
+}
+int rf_knn_recheck_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, const int* q_sel,
+                          const int* q_count, int* out_idx, double* out_d, void* workspace, size_t workspace_bytes,
+                          cudaStream_t s) {
+    RF_CHECK_ARG(workspace && workspace_bytes >= rf_knn_recheck_workspace_bytes(k) - 256, "rf_knn_l2_topk: re-check workspace too small");
+    const long cap = RF_RECHECK_CAP < Q ? RF_RECHECK_CAP : Q;
+    int ns = RF_RECHECK_SLICES;
+    const long max_split = (n_rows + 1023) / 1024;
+    if (ns > max_split) ns = (int)max_split;
+    double* pd = (double*)workspace;
+    int* pi = (int*)(pd + (size_t)ns * cap * k);
+    dim3 grid((unsigned)((cap + QB - 1) / QB), ns);
+    knn_exact_f64_kernel<<<grid, WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, q_count, 0, cap, k, ns, q_sel, pi, pd);
+    RF_LAUNCH_OK("knn_exact_f64_kernel(re-check)");
+    knn_merge_kernel<<<(unsigned)rf_cdivl(cap * 32, 128), 128, 0, s>>>(pi, pd, ns, Q, q_count, cap, k, q_sel, out_idx, out_d);
+    RF_LAUNCH_OK("knn_merge_kernel(re-check)");
+    if (Q > cap) {
+        long gx = (Q - cap + QB - 1) / QB;
+        if (gx > 148 * 8) gx = 148 * 8;
+        knn_exact_f64_kernel<<<dim3((unsigned)gx, 1), WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, q_count, cap, Q, k, 1,
+                                                                                 q_sel, out_idx, out_d);
+        RF_LAUNCH_OK("knn_exact_f64_kernel(re-check overflow)");
+    }
     return 0;
 }
 
@@ -220,7 +274,7 @@ extern "C" int rf_knn_merge(const int* parts_idx, const double* parts_d, int S, 
                             double* out_d, void* stream) {
     RF_CHECK_ARG(parts_idx && parts_d && out_idx && out_d, "rf_knn_merge: null pointer");
     RF_CHECK_ARG(S > 0 && Q > 0 && k > 0 && k <= 32, "rf_knn_merge: bad sizes S=%d Q=%ld k=%d", S, Q, k);
-    knn_merge_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, (cudaStream_t)stream>>>(parts_idx, parts_d, S, Q, k, nullptr, out_idx, out_d);
+    knn_merge_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, (cudaStream_t)stream>>>(parts_idx, parts_d, S, Q, nullptr, 0, k, nullptr, out_idx, out_d);
     RF_LAUNCH_OK("knn_merge_kernel");
     return 0;
 }

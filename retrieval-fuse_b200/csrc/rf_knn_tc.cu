@@ -8,14 +8,19 @@
 //        method 2: one fp16 GEMM, K = 64          (eps_rel = 1.0e-3)
 //        method 3: bf16 hi/lo split, K = 3*64: q_hi.x_hi + q_hi.x_lo + q_lo.x_hi
 //                  (x = hi + lo + r, |r| <= 2^-18 |x|; eps_rel = 4e-5)
-//   2. each query keeps its CAND = 16 best s~ (a register-resident sorted list
-//      owned by the epilogue thread that reads the query's TMEM lane).
-//   3. re-rank the 16 candidates with the canonical fp64 arithmetic, and PROVE
-//      completeness: every rejected row has s~ <= tau (the 16th best), hence
-//      d >= |q|^2 + min|x|^2 - 2 (tau + eps); if the k-th best candidate's exact
-//      d is strictly below that bound, no rejected row can enter or tie the
-//      top-k.  Queries that cannot be proven (dense ties, duplicates beyond the
-//      slack) are re-done by the exact fp64 sweep (rf_knn.cu).
+//   2. each query keeps its CAND best s~ per bank slice (a register-resident
+//      sorted list owned by the epilogue thread that reads the query's TMEM
+//      lane).  CAND = 16 for k <= 8, 32 above: the list must be LONGER than k,
+//      otherwise the proof below compares the k-th candidate with itself.
+//      k > 16 additionally splits the bank into >= 2 slices (2 x 32 candidates).
+//   3. re-rank the candidates with the canonical fp64 arithmetic, and PROVE
+//      completeness: every rejected row has s~ <= tau (the CAND-th best of its
+//      slice), hence d >= |q|^2 + min|x|^2 - 2 (tau + eps); if the k-th best
+//      candidate's exact d is strictly below that bound, no rejected row can
+//      enter or tie the top-k.  Queries that cannot be proven (dense ties,
+//      duplicates beyond the slack) are re-done by the exact fp64 sweep
+//      (rf_knn.cu), which is enqueued unconditionally and sized by a DEVICE
+//      counter: the call never synchronises the stream.
 // The result is therefore bit-identical to method 1 by construction.
 //
 // Operand staging: both operands are pre-arranged in HBM as byte images of
@@ -41,9 +46,10 @@
 
 #include "rf_common.cuh"
 
-int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, const int* q_sel,
-                        int* out_idx, double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s);
-int rf_knn_exact_nsplit(long Q, long n_rows);
+size_t rf_knn_recheck_workspace_bytes(int k);
+int rf_knn_recheck_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, const int* q_sel,
+                          const int* q_count, int* out_idx, double* out_d, void* workspace, size_t workspace_bytes,
+                          cudaStream_t s);
 
 namespace {
 
@@ -51,7 +57,6 @@ constexpr int TILE = 128;              // rows per operand tile (UMMA M and N)
 constexpr int MQ = 2;                  // query sub-tiles per CTA
 constexpr int KB_BYTES = TILE * 128;   // one K block: 64 x 16-bit per row, 16 KiB
 constexpr int NACC = 2;                // TMEM accumulator buffers (MQ x 128 columns each)
-constexpr int CAND = 16;               // candidates kept per query and bank slice
 constexpr int MAX_SPLIT = 8;
 constexpr int NTHREADS = 128 + MQ * 128;
 
@@ -64,15 +69,15 @@ template <int KBLK> struct Cfg {
 // (+4e-6: the epilogue tags scores with their column in the low 5 mantissa bits)
 __host__ __device__ constexpr float eps_rel(int kblk) { return kblk == 1 ? 1.004e-3f : 4.4e-5f; }
 
-struct Stats {            // first 256 bytes of the workspace
+struct Stats {            // first 256 bytes of the call workspace
     int n_flagged;        // queries whose top-k could not be proven
     unsigned max_err_bits;  // max observed |s~ - s| over candidates (float bits)
+};
+struct BankStats {        // first 256 bytes of the prepared bank image
     unsigned nmin_bits;   // min |x|^2 over the bank (float bits)
     unsigned nmax_bits;   // max |x|^2
+    int has_perm;         // rows of the image are in scan order (perm[] follows the header)
 };
-// host-side record of the last call (per process): device time of the candidates kernel
-static float g_last_candidates_ms = -1.f;
-static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(256) knn_scan_key_kernel(const float* __restri
 // For the bank the range of |x|^2 is recorded.
 template <int KBLK>
 __global__ void __launch_bounds__(256) knn_tc_prep_kernel(const float* __restrict__ src, long n_rows, long n_rows_padded,
-                                                          int is_bank, uint8_t* __restrict__ img, Stats* stats,
+                                                          int is_bank, uint8_t* __restrict__ img, BankStats* stats,
                                                           const int* __restrict__ perm) {
     const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;  // one thread per (row, 16-byte chunk)
     const long row = gid >> 3;
@@ -264,11 +269,11 @@ __global__ void __launch_bounds__(256) knn_tc_prep_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------ main kernel
-template <int KBLK>
+template <int KBLK, int CAND>
 __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const uint8_t* __restrict__ q_img,
                                                                         const uint8_t* __restrict__ bank_img, long Q,
                                                                         long n_rows, int n_qtiles, int n_btiles,
-                                                                        int tiles_per_split, float* __restrict__ cand_s,
+                                                                        int nsplit, float* __restrict__ cand_s,
                                                                         int* __restrict__ cand_i) {
     constexpr int TILE_BYTES = Cfg<KBLK>::TILE_BYTES;
     constexpr int NSTAGE = Cfg<KBLK>::NSTAGE;
@@ -288,11 +293,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // slice `split` owns bank tiles split, split + nsplit, ...: with the image in scan order every slice sees the
+    // promising rows first, and the slices' lists have statistically the same tail (the proof uses their maximum)
     const int qpair = blockIdx.x, split = blockIdx.y;
-    const int t_begin = split * tiles_per_split;
-    int t_end = t_begin + tiles_per_split;
-    if (t_end > n_btiles) t_end = n_btiles;
-    const int n_iter = t_end > t_begin ? t_end - t_begin : 0;
+    const int n_iter = n_btiles > split ? (n_btiles - split + nsplit - 1) / nsplit : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
                 const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1u);  // a fresh barrier passes the parity-1 wait
                 mbar_arrive_expect_tx(bar_full + 8 * s, TILE_BYTES);
-                const uint8_t* src = bank_img + (long)(t_begin + it) * TILE_BYTES;
+                const uint8_t* src = bank_img + (long)(split + it * nsplit) * TILE_BYTES;
                 for (int kb = 0; kb < KBLK; ++kb)
                     bulk_g2s(sB + s * TILE_BYTES + kb * KB_BYTES, src + (long)kb * KB_BYTES, KB_BYTES, bar_full + 8 * s);
             }
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
             const uint32_t bph = (uint32_t)(it / NACC) & 1u;
             mbar_wait(bar_tfull + 8 * b, bph);
             tc_fence_after();
-            const long col_tile = (long)(t_begin + it) * TILE;
+            const long col_tile = (long)(split + it * nsplit) * TILE;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((b * MQ + m) * TILE);
             tc_ld32_issue(taddr, va);
 #pragma unroll
@@ -440,98 +444,108 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
 // ------------------------------------------------------------------ re-rank + proof
 __device__ __forceinline__ bool cand_less(double d, int i, double d2, int i2) { return d < d2 || (d == d2 && i < i2); }
 
-// Bitonic sort of 16 (d, id) entries, one per lane of a half warp, ascending under the canonical order
-// (10 compare-exchange stages instead of 16 serial list insertions).
-__device__ __forceinline__ void half_bitonic_sort(double& d, int& i, int lane16) {
+// Bitonic sort of LW (d, id) entries, one per lane of an LW-lane group (LW = 16: half a warp, 32: a warp), ascending
+// under the canonical order (log^2 compare-exchange stages instead of LW serial list insertions).
+template <int LW>
+__device__ __forceinline__ void group_bitonic_sort(double& d, int& i, int gl) {
 #pragma unroll
-    for (int k = 2; k <= 16; k <<= 1) {
+    for (int k = 2; k <= LW; k <<= 1) {
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, d, j, 16);
-            const int oi = __shfl_xor_sync(0xffffffffu, i, j, 16);
-            const bool up = (lane16 & k) == 0, lower = (lane16 & j) == 0;
+            const double od = __shfl_xor_sync(0xffffffffu, d, j, LW);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, j, LW);
+            const bool up = (gl & k) == 0, lower = (gl & j) == 0;
             const bool take = (lower == up) ? cand_less(od, oi, d, i) : cand_less(d, i, od, oi);
             if (take) { d = od; i = oi; }
         }
     }
 }
-// (ld, li) sorted ascending, (d, i) sorted ascending -> (ld, li) = the 16 smallest of the 32, sorted:
-// min(list[l], new[15 - l]) is a bitonic sequence holding exactly those 16, four merge stages sort it.
-__device__ __forceinline__ void half_bitonic_merge(double& ld, int& li, double d, int i, int lane16) {
-    const double rd = __shfl_sync(0xffffffffu, d, 15 - lane16, 16);
-    const int ri = __shfl_sync(0xffffffffu, i, 15 - lane16, 16);
+// (ld, li) sorted ascending, (d, i) sorted ascending -> (ld, li) = the LW smallest of the 2 LW, sorted:
+// min(list[l], new[LW - 1 - l]) is a bitonic sequence holding exactly those LW, log LW merge stages sort it.
+template <int LW>
+__device__ __forceinline__ void group_bitonic_merge(double& ld, int& li, double d, int i, int gl) {
+    const double rd = __shfl_sync(0xffffffffu, d, LW - 1 - gl, LW);
+    const int ri = __shfl_sync(0xffffffffu, i, LW - 1 - gl, LW);
     if (cand_less(rd, ri, ld, li)) { ld = rd; li = ri; }
 #pragma unroll
-    for (int j = 8; j > 0; j >>= 1) {
-        const double od = __shfl_xor_sync(0xffffffffu, ld, j, 16);
-        const int oi = __shfl_xor_sync(0xffffffffu, li, j, 16);
-        const bool lower = (lane16 & j) == 0;
+    for (int j = LW >> 1; j > 0; j >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, ld, j, LW);
+        const int oi = __shfl_xor_sync(0xffffffffu, li, j, LW);
+        const bool lower = (gl & j) == 0;
         const bool take = lower ? cand_less(od, oi, ld, li) : cand_less(ld, li, od, oi);
         if (take) { ld = od; li = oi; }
     }
 }
 
-// Half a warp per query (the candidate lists hold 16 entries per slice, so 16 lanes cover one slice at a time and
-// the fp64 pipe is not fed half-empty warps).  Candidate c of slice s: (cand_s, cand_i)[s][q][c].
+// LW lanes per query (LW = 16 for k <= 16: the fp64 pipe is not fed half-empty warps; LW = 32 above).  The group
+// re-ranks its query's S x cand candidates LW at a time.  Candidate c of slice s: (cand_s, cand_i)[s][q][c].
+template <int LW>
 __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restrict__ bank, long row_offset,
-                                                            const float* __restrict__ q, long Q, int k, int S,
+                                                            const float* __restrict__ q, long Q, int k, int S, int cand,
                                                             const float* __restrict__ cand_s, const int* __restrict__ cand_i,
                                                             int* __restrict__ out_idx, double* __restrict__ out_d,
-                                                            int* __restrict__ flagged, Stats* stats, float eps_r,
+                                                            int* __restrict__ flagged, Stats* stats,
+                                                            const BankStats* __restrict__ bstats, float eps_r,
                                                             const int* __restrict__ perm) {
-    const long hw = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 4;  // half-warp index = query
-    const int lane16 = threadIdx.x & 15, half = (threadIdx.x >> 4) & 1;
-    const bool live = hw < Q;
-    const long qi = live ? hw : Q - 1;  // a dead half warp shadows the last query (shuffles need all lanes), writes nothing
-    // the query in fp64, four elements per lane; |q|^2
+    constexpr int GPW = 32 / LW;  // query groups per warp
+    const long grp = (blockIdx.x * (long)blockDim.x + threadIdx.x) / LW;  // group index = query
+    const int gl = threadIdx.x & (LW - 1), sub = (threadIdx.x & 31) / LW;
+    const bool live = grp < Q;
+    const long qi = live ? grp : Q - 1;  // a dead group shadows the last query (shuffles need all lanes), writes nothing
+    // the query in fp64, 64 / LW elements per lane; |q|^2
     const float* qr = q + qi * 64;
     double qn = 0.0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const double v = (double)qr[lane16 + 16 * j]; qn += v * v; }
+    for (int j = 0; j < 64 / LW; ++j) { const double v = (double)qr[gl + LW * j]; qn += v * v; }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o, 16);
+    for (int o = LW >> 1; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o, LW);
 
-    // Staging (per warp: 2 queries x 16 candidate rows).  A lane needs its candidate's whole 256-byte row in index
-    // order (the canonical sum is sequential), so reading rows straight from the bank makes every load instruction
-    // touch 32 different lines; instead each half warp fetches its 16 rows with one contiguous 256-byte access per
-    // row into shared memory (row pitch 272 B: the per-lane float4 reads are conflict-free per quarter warp), and the
+    // Staging (per warp: GPW queries x LW candidate rows = 32 rows).  A lane needs its candidate's whole 256-byte row
+    // in index order (the canonical sum is sequential), so reading rows straight from the bank makes every load
+    // instruction touch 32 different lines; instead each group fetches its rows with contiguous 256-byte accesses
+    // into shared memory (row pitch 272 B: the per-lane float4 reads are conflict-free per quarter warp), and the
     // query sits there once as fp64 (no per-candidate re-conversion).
     __shared__ __align__(16) float xs[4][32][68];
-    __shared__ double qsd[8][64];
-    const int warp_l = threadIdx.x >> 5, hw_l = threadIdx.x >> 4;
+    __shared__ double qsd[4 * GPW][64];
+    const int warp_l = threadIdx.x >> 5, grp_l = threadIdx.x / LW;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) qsd[hw_l][lane16 + 16 * j] = (double)qr[lane16 + 16 * j];
+    for (int j = 0; j < 64 / LW; ++j) qsd[grp_l][gl + LW * j] = (double)qr[gl + LW * j];
     __syncwarp();
-    const double* qd = qsd[hw_l];
+    const double* qd = qsd[grp_l];
 
     double ld = DBL_MAX;
     int li = INT_MAX;
-    float tau = -FLT_MAX;       // max over slices of the slice's 16th best approximate score
+    float tau = -FLT_MAX;       // max over slices of the slice's cand-th best approximate score
     float err = 0.f;
-    const int total = S * CAND;
-    for (int base = 0; base < total; base += 16) {
-        const int c = base + lane16;
+    const int total = S * cand;
+    for (int base = 0; base < total; base += LW) {
+        const int c = base + gl;
         int id = -1;
         float sc = -FLT_MAX;
         if (c < total) {
-            const long o = ((long)(c / CAND) * Q + qi) * CAND + (c % CAND);
+            const long o = ((long)(c / cand) * Q + qi) * cand + (c % cand);
             id = cand_i[o];
             if (perm && id >= 0) id = perm[id];  // scan position -> bank row
             sc = cand_s[o];
-            if ((c % CAND) == CAND - 1 && id >= 0) tau = fmaxf(tau, sc);  // a full list: its tail bounds the rejected rows
+            if ((c % cand) == cand - 1 && id >= 0) tau = fmaxf(tau, sc);  // a full list: its tail bounds the rejected rows
         }
         __syncwarp();  // the previous round's rows have been consumed
-#pragma unroll
-        for (int cc = 0; cc < 16; ++cc) {
-            const int idc = __shfl_sync(0xffffffffu, id, cc, 16);
-            if (idc >= 0)
-                *reinterpret_cast<float4*>(&xs[warp_l][half * 16 + cc][lane16 * 4]) =
-                    __ldg(reinterpret_cast<const float4*>(bank + (long)idc * 64) + lane16);
+#pragma unroll 4
+        for (int cc = 0; cc < LW; ++cc) {
+            const int idc = __shfl_sync(0xffffffffu, id, cc, LW);
+            if (idc >= 0) {
+                const float4* src = reinterpret_cast<const float4*>(bank + (long)idc * 64);
+                if (LW == 16) {
+                    *reinterpret_cast<float4*>(&xs[warp_l][sub * LW + cc][gl * 4]) = __ldg(src + gl);
+                } else if (gl < 16) {
+                    *reinterpret_cast<float4*>(&xs[warp_l][cc][gl * 4]) = __ldg(src + gl);
+                }
+            }
         }
         __syncwarp();
         double d = DBL_MAX;
         if (id >= 0) {  // canonical fp64 distance, same arithmetic as the exact sweep
-            const float4* xr = reinterpret_cast<const float4*>(&xs[warp_l][half * 16 + lane16][0]);
+            const float4* xr = reinterpret_cast<const float4*>(&xs[warp_l][sub * LW + gl][0]);
             double acc = 0.0;
             float xn = 0.f;  // |x|^2 only feeds the error diagnostic: fp32 is plenty
 #pragma unroll 4
@@ -551,29 +565,29 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restr
             const float s_exact = 0.5f * (float)(qn + (double)xn - acc);
             err = fmaxf(err, fabsf(sc - s_exact));
         }
-        // sort this round's 16 candidates and merge them into the running list (invalid slots rank last)
+        // sort this round's candidates and merge them into the running list (invalid slots rank last)
         int ci = id >= 0 ? id + (int)row_offset : INT_MAX;
-        half_bitonic_sort(d, ci, lane16);
+        group_bitonic_sort<LW>(d, ci, gl);
         if (base == 0) { ld = d; li = ci; }
-        else half_bitonic_merge(ld, li, d, ci, lane16);
+        else group_bitonic_merge<LW>(ld, li, d, ci, gl);
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, o, 16));
-        err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o, 16));
+    for (int o = LW >> 1; o > 0; o >>= 1) {
+        tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, o, LW));
+        err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o, LW));
     }
-    if (live && lane16 < k) { out_idx[qi * k + lane16] = li; out_d[qi * k + lane16] = ld; }
+    if (live && gl < k) { out_idx[qi * k + gl] = li; out_d[qi * k + gl] = ld; }
     // proof: rejected rows have s~ <= tau  =>  d >= |q|^2 + min|x|^2 - 2 (tau + eps)
-    const double dk = __shfl_sync(0xffffffffu, ld, k - 1, 16);
+    const double dk = __shfl_sync(0xffffffffu, ld, k - 1, LW);
     bool proven = true;
     if (tau > -FLT_MAX) {
-        const double nmin = (double)__uint_as_float(stats->nmin_bits);
-        const double nmax = (double)__uint_as_float(stats->nmax_bits);
+        const double nmin = (double)__uint_as_float(bstats->nmin_bits);
+        const double nmax = (double)__uint_as_float(bstats->nmax_bits);
         const double eps = (double)eps_r * sqrt(qn * nmax) + 2e-6;
         const double d_lb = qn + nmin * (1.0 - 1e-6) - 2.0 * ((double)tau + eps);
         proven = dk < d_lb - 1e-9;
     }
-    if (live && lane16 == 0) {
+    if (live && gl == 0) {
         if (!proven) flagged[atomicAdd(&stats->n_flagged, 1)] = (int)qi;
         atomicMax(&stats->max_err_bits, __float_as_uint(err));
     }
@@ -582,10 +596,86 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restr
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// per-device one-time function attributes (one process may drive several devices)
+template <int KBLK, int CAND>
+int set_candidates_attr() {
+    static bool done[64] = {};
+    int dev = 0;
+    RF_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && done[dev]) return 0;
+    RF_CUDA_OK(cudaFuncSetAttribute(knn_tc_candidates_kernel<KBLK, CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg<KBLK>::SMEM_BYTES));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return 0;
+}
+
+// ---- the prepared bank image: [BankStats 256 B][perm: bpad int32][tile images, 1024-aligned]
+struct ImgLayout {
+    size_t perm, img, total, key_in, key_out, idx_in, mean, sort_tmp, sort_tmp_bytes, scratch_total;
+    int n_btiles;
+};
+ImgLayout img_layout(long n_rows, int kblk) {
+    ImgLayout L;
+    L.n_btiles = (int)((n_rows + TILE - 1) / TILE);
+    const size_t bpad = (size_t)L.n_btiles * TILE;
+    size_t off = 256;
+    L.perm = off; off += align_up(bpad * sizeof(int), 1024);
+    L.img = off; off += (size_t)L.n_btiles * kblk * KB_BYTES;
+    L.total = off;
+    // scratch of the preparation (scan order): mean direction, projection keys, radix-sort buffers
+    size_t so = 0;
+    L.mean = so; so += 256;
+    L.key_in = so; so += align_up(bpad * sizeof(float), 256);
+    L.key_out = so; so += align_up(bpad * sizeof(float), 256);
+    L.idx_in = so; so += align_up(bpad * sizeof(int), 256);
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairsDescending((void*)nullptr, tmp, (const float*)nullptr, (float*)nullptr, (const int*)nullptr,
+                                              (int*)nullptr, (int)bpad);
+    L.sort_tmp_bytes = tmp;
+    L.sort_tmp = so; so += align_up(tmp, 256);
+    L.scratch_total = so;
+    return L;
+}
+
+// image: 1024-aligned, img_layout().total bytes; scratch: img_layout().scratch_total bytes (only read during the call)
+template <int KBLK>
+int prepare_bank(const float* bank, long n_rows, const float* q_sample, long n_sample, char* image, char* scratch, cudaStream_t s) {
+    const ImgLayout L = img_layout(n_rows, KBLK);
+    BankStats* bstats = (BankStats*)image;
+    const long bpad = (long)L.n_btiles * TILE;
+    const bool order = n_rows >= 16 * TILE;  // scan order (see knn_scan_key_kernel); pointless for tiny banks
+    const BankStats init = {0x7f7fffffu /*FLT_MAX*/, 0u, order ? 1 : 0};
+    RF_CUDA_OK(cudaMemcpyAsync(bstats, &init, sizeof(BankStats), cudaMemcpyHostToDevice, s));
+    const int* perm = nullptr;
+    if (order) {
+        float* mean = (float*)(scratch + L.mean);
+        float* key_in = (float*)(scratch + L.key_in);
+        float* key_out = (float*)(scratch + L.key_out);
+        int* idx_in = (int*)(scratch + L.idx_in);
+        int* perm_w = (int*)(image + L.perm);
+        RF_CUDA_OK(cudaMemsetAsync(mean, 0, 64 * sizeof(float), s));
+        // direction of a typical query: the mean of a query sample when the caller has one, else the bank's own mean
+        const float* src = q_sample ? q_sample : bank;
+        long ns = q_sample ? n_sample : n_rows;
+        if (ns > 65536) ns = 65536;
+        knn_mean_query_kernel<<<(unsigned)(ns / 4 < 592 ? (ns + 3) / 4 : 592), 256, 0, s>>>(src, ns, mean);
+        RF_LAUNCH_OK("knn_mean_query_kernel");
+        knn_scan_key_kernel<<<(unsigned)rf_cdivl(bpad, 256), 256, 0, s>>>(bank, n_rows, bpad, mean, key_in, idx_in);
+        RF_LAUNCH_OK("knn_scan_key_kernel");
+        size_t tmp = L.sort_tmp_bytes;
+        RF_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending((void*)(scratch + L.sort_tmp), tmp, (const float*)key_in, key_out,
+                                                             (const int*)idx_in, perm_w, (int)bpad, 0, 32, s));
+        perm = perm_w;
+    }
+    knn_tc_prep_kernel<KBLK><<<(unsigned)rf_cdivl(bpad * 8, 256), 256, 0, s>>>(bank, n_rows, bpad, 1, (uint8_t*)(image + L.img), bstats, perm);
+    RF_LAUNCH_OK("knn_tc_prep_kernel(bank)");
+    return 0;
+}
+
+// ---- the per-call workspace
 struct TcLayout {
-    size_t stats, bank_img, q_img, cand_s, cand_i, flagged, exact_ws, total, mean, key_in, key_out, idx_in, perm, sort_tmp, sort_tmp_bytes;
-    int n_btiles, n_qtiles, n_qpairs, nsplit, tiles_per_split;
-    size_t exact_ws_bytes;
+    size_t stats, q_img, cand_s, cand_i, flagged, recheck_ws, recheck_ws_bytes, total;
+    int n_btiles, n_qtiles, n_qpairs, nsplit, cand, lw;
 };
 
 TcLayout tc_layout(long Q, long n_rows, int k, int kblk) {
@@ -594,128 +684,123 @@ TcLayout tc_layout(long Q, long n_rows, int k, int kblk) {
     L.n_btiles = (int)((n_rows + TILE - 1) / TILE);
     L.n_qpairs = (int)((Q + MQ * TILE - 1) / (MQ * TILE));
     L.n_qtiles = L.n_qpairs * MQ;
+    L.cand = k <= 8 ? 16 : 32;
+    L.lw = k <= 16 ? 16 : 32;
     int ns = (148 + L.n_qpairs - 1) / L.n_qpairs;  // fill the chip when there are few query tiles
     if (ns > MAX_SPLIT) ns = MAX_SPLIT;
+    if (k > 16 && ns < 2) ns = 2;                   // 2 x 32 candidates for k up to 32
     if (ns > L.n_btiles) ns = L.n_btiles;
     if (ns < 1) ns = 1;
-    L.tiles_per_split = (L.n_btiles + ns - 1) / ns;
-    L.nsplit = (L.n_btiles + L.tiles_per_split - 1) / L.tiles_per_split;
+    L.nsplit = ns;
     size_t off = 0;
     L.stats = off; off += 256;
     off = align_up(off, 1024);
-    L.bank_img = off; off += (size_t)L.n_btiles * tile_bytes;
     L.q_img = off; off += (size_t)L.n_qtiles * tile_bytes;
-    L.cand_s = off; off += align_up((size_t)L.nsplit * Q * CAND * sizeof(float), 256);
-    L.cand_i = off; off += align_up((size_t)L.nsplit * Q * CAND * sizeof(int), 256);
+    L.cand_s = off; off += align_up((size_t)L.nsplit * Q * L.cand * sizeof(float), 256);
+    L.cand_i = off; off += align_up((size_t)L.nsplit * Q * L.cand * sizeof(int), 256);
     L.flagged = off; off += align_up((size_t)Q * sizeof(int), 256);
-    {   // scan order: mean query, projection keys, radix-sort buffers
-        const size_t bpad = (size_t)L.n_btiles * TILE;
-        L.mean = off; off += 256;
-        L.key_in = off; off += align_up(bpad * sizeof(float), 256);
-        L.key_out = off; off += align_up(bpad * sizeof(float), 256);
-        L.idx_in = off; off += align_up(bpad * sizeof(int), 256);
-        L.perm = off; off += align_up(bpad * sizeof(int), 256);
-        size_t tmp = 0;
-        cub::DeviceRadixSort::SortPairsDescending((void*)nullptr, tmp, (const float*)nullptr, (float*)nullptr, (const int*)nullptr,
-                                                  (int*)nullptr, (int)bpad);
-        L.sort_tmp_bytes = tmp;
-        L.sort_tmp = off; off += align_up(tmp, 256);
-    }
-    // the exact re-check of unproven queries: worst case every query, see rf_knn_exact_nsplit
-    L.exact_ws_bytes = ((size_t)148 * 8 * 32 + (size_t)Q) * k * (sizeof(int) + sizeof(double)) + 256;
-    L.exact_ws = off; off += L.exact_ws_bytes;
+    L.recheck_ws_bytes = rf_knn_recheck_workspace_bytes(k);
+    L.recheck_ws = off; off += L.recheck_ws_bytes;
     L.total = off;
     return L;
 }
 
+template <int KBLK, int CAND>
+int launch_candidates(const TcLayout& L, const uint8_t* q_img, const uint8_t* bank_img, long Q, long n_rows, float* cand_s,
+                      int* cand_i, cudaStream_t s) {
+    if (int rc = set_candidates_attr<KBLK, CAND>()) return rc;
+    dim3 grid(L.n_qpairs, L.nsplit);
+    knn_tc_candidates_kernel<KBLK, CAND><<<grid, NTHREADS, Cfg<KBLK>::SMEM_BYTES, s>>>(q_img, bank_img, Q, n_rows, L.n_qtiles,
+                                                                                      L.n_btiles, L.nsplit, cand_s, cand_i);
+    RF_LAUNCH_OK("knn_tc_candidates_kernel");
+    return 0;
+}
+
 template <int KBLK>
-int tc_run(const TcLayout& L, const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, int* out_idx,
-           double* out_d, char* ws, cudaStream_t s) {
+int tc_run(const TcLayout& L, const float* bank, long n_rows, long row_offset, const char* image, const float* q, long Q, int k,
+           int* out_idx, double* out_d, char* ws, cudaStream_t s) {
+    const ImgLayout IL = img_layout(n_rows, KBLK);
     Stats* stats = (Stats*)(ws + L.stats);
-    uint8_t* bank_img = (uint8_t*)(ws + L.bank_img);
+    const BankStats* bstats = (const BankStats*)image;
+    const uint8_t* bank_img = (const uint8_t*)(image + IL.img);
+    const int* perm = n_rows >= 16 * TILE ? (const int*)(image + IL.perm) : nullptr;
     uint8_t* q_img = (uint8_t*)(ws + L.q_img);
     float* cand_s = (float*)(ws + L.cand_s);
     int* cand_i = (int*)(ws + L.cand_i);
     int* flagged = (int*)(ws + L.flagged);
-    static bool attr_set = false;
-    if (!attr_set) {
-        RF_CUDA_OK(cudaFuncSetAttribute(knn_tc_candidates_kernel<KBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg<KBLK>::SMEM_BYTES));
-        attr_set = true;
-    }
-    const Stats init = {0, 0u, 0x7f7fffffu /*FLT_MAX*/, 0u};
-    RF_CUDA_OK(cudaMemcpyAsync(stats, &init, sizeof(Stats), cudaMemcpyHostToDevice, s));
-    const long bpad = (long)L.n_btiles * TILE, qpad = (long)L.n_qtiles * TILE;
-    const int* perm = nullptr;
-    if (n_rows >= 16 * TILE && L.nsplit == 1) {  // scan order (see knn_scan_key_kernel); pointless for tiny banks
-        float* mean = (float*)(ws + L.mean);
-        float* key_in = (float*)(ws + L.key_in);
-        float* key_out = (float*)(ws + L.key_out);
-        int* idx_in = (int*)(ws + L.idx_in);
-        int* perm_w = (int*)(ws + L.perm);
-        RF_CUDA_OK(cudaMemsetAsync(mean, 0, 64 * sizeof(float), s));
-        const long q_sample = Q < 65536 ? Q : 65536;
-        knn_mean_query_kernel<<<(unsigned)(q_sample / 4 < 592 ? (q_sample + 3) / 4 : 592), 256, 0, s>>>(q, q_sample, mean);
-        RF_LAUNCH_OK("knn_mean_query_kernel");
-        knn_scan_key_kernel<<<(unsigned)rf_cdivl(bpad, 256), 256, 0, s>>>(bank, n_rows, bpad, mean, key_in, idx_in);
-        RF_LAUNCH_OK("knn_scan_key_kernel");
-        size_t tmp = L.sort_tmp_bytes;
-        RF_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending((void*)(ws + L.sort_tmp), tmp, (const float*)key_in, key_out,
-                                                             (const int*)idx_in, perm_w, (int)bpad, 0, 32, s));
-        perm = perm_w;
-    }
-    knn_tc_prep_kernel<KBLK><<<(unsigned)rf_cdivl(bpad * 8, 256), 256, 0, s>>>(bank, n_rows, bpad, 1, bank_img, stats, perm);
-    RF_LAUNCH_OK("knn_tc_prep_kernel(bank)");
-    knn_tc_prep_kernel<KBLK><<<(unsigned)rf_cdivl(qpad * 8, 256), 256, 0, s>>>(q, Q, qpad, 0, q_img, stats, nullptr);
+    RF_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(Stats), s));
+    const long qpad = (long)L.n_qtiles * TILE;
+    knn_tc_prep_kernel<KBLK><<<(unsigned)rf_cdivl(qpad * 8, 256), 256, 0, s>>>(q, Q, qpad, 0, q_img, nullptr, nullptr);
     RF_LAUNCH_OK("knn_tc_prep_kernel(queries)");
-    dim3 grid(L.n_qpairs, L.nsplit);
-    if (!g_ev0) {
-        RF_CUDA_OK(cudaEventCreate(&g_ev0));
-        RF_CUDA_OK(cudaEventCreate(&g_ev1));
-    }
-    RF_CUDA_OK(cudaEventRecord(g_ev0, s));  // device time of the dominant kernel, read back by rf_knn_tc_stats
-    knn_tc_candidates_kernel<KBLK><<<grid, NTHREADS, Cfg<KBLK>::SMEM_BYTES, s>>>(q_img, bank_img, Q, n_rows, L.n_qtiles,
-                                                                               L.n_btiles, L.tiles_per_split, cand_s, cand_i);
-    RF_LAUNCH_OK("knn_tc_candidates_kernel");
-    RF_CUDA_OK(cudaEventRecord(g_ev1, s));
-    knn_tc_rerank_kernel<<<(unsigned)rf_cdivl(Q * 16, 128), 128, 0, s>>>(bank, row_offset, q, Q, k, L.nsplit, cand_s, cand_i,
-                                                                        out_idx, out_d, flagged, stats, eps_rel(KBLK), perm);
+    int rc = L.cand == 16 ? launch_candidates<KBLK, 16>(L, q_img, bank_img, Q, n_rows, cand_s, cand_i, s)
+                          : launch_candidates<KBLK, 32>(L, q_img, bank_img, Q, n_rows, cand_s, cand_i, s);
+    if (rc) return rc;
+    if (L.lw == 16)
+        knn_tc_rerank_kernel<16><<<(unsigned)rf_cdivl(Q * 16, 128), 128, 0, s>>>(bank, row_offset, q, Q, k, L.nsplit, L.cand, cand_s, cand_i,
+                                                                                out_idx, out_d, flagged, stats, bstats, eps_rel(KBLK), perm);
+    else
+        knn_tc_rerank_kernel<32><<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, s>>>(bank, row_offset, q, Q, k, L.nsplit, L.cand, cand_s, cand_i,
+                                                                                out_idx, out_d, flagged, stats, bstats, eps_rel(KBLK), perm);
     RF_LAUNCH_OK("knn_tc_rerank_kernel");
-    return 0;
+    // unproven queries (normally none): exact fp64 sweep sized by the device counter, results scattered through `flagged`
+    return rf_knn_recheck_launch(bank, n_rows, row_offset, q, Q, k, flagged, &stats->n_flagged, out_idx, out_d, ws + L.recheck_ws,
+                                 L.recheck_ws_bytes, s);
 }
 
 }  // namespace
 
-size_t rf_knn_tc_workspace_bytes(long Q, long n_rows, int k, int kblk) { return tc_layout(Q, n_rows, k, kblk).total + 1024; }
-
 // kblk = 1: fp16 single pass (method 2); kblk = 3: bf16 hi/lo split (method 3)
-int rf_knn_tc_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, int kblk, int* out_idx,
-                     double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s) {
-    RF_CHECK_ARG(k <= CAND, "rf_knn_l2_topk(tensor-core methods): k=%d exceeds the candidate list (%d)", k, CAND);
+size_t rf_knn_tc_image_bytes(long n_rows, int kblk) { return img_layout(n_rows, kblk).total + 1024; }
+size_t rf_knn_tc_prepare_scratch_bytes(long n_rows, int kblk) { return img_layout(n_rows, kblk).scratch_total + 256; }
+
+int rf_knn_tc_prepare(const float* bank, long n_rows, int kblk, const float* q_sample, long n_sample, void* image,
+                      size_t image_bytes, void* scratch, size_t scratch_bytes, cudaStream_t s) {
+    const ImgLayout IL = img_layout(n_rows, kblk);
+    char* img = (char*)(((uintptr_t)image + 1023) & ~(uintptr_t)1023);
+    RF_CHECK_ARG(image && image_bytes >= IL.total + (size_t)(img - (char*)image), "rf_knn_bank_prepare: image buffer too small (%zu < %zu)",
+                 image_bytes, IL.total + 1024);
+    RF_CHECK_ARG(scratch && scratch_bytes >= IL.scratch_total, "rf_knn_bank_prepare: scratch too small (%zu < %zu)", scratch_bytes,
+                 IL.scratch_total);
+    return kblk == 1 ? prepare_bank<1>(bank, n_rows, q_sample, n_sample, img, (char*)scratch, s)
+                     : prepare_bank<3>(bank, n_rows, q_sample, n_sample, img, (char*)scratch, s);
+}
+
+size_t rf_knn_tc_workspace_bytes(long Q, long n_rows, int k, int kblk, int with_image) {
+    size_t b = tc_layout(Q, n_rows, k, kblk).total + 1024;
+    if (with_image) b += rf_knn_tc_image_bytes(n_rows, kblk) + rf_knn_tc_prepare_scratch_bytes(n_rows, kblk) + 1024;
+    return b;
+}
+
+// image == nullptr: the bank image is built inside the workspace first (one-off lookups); otherwise `image` is a buffer
+// filled by rf_knn_tc_prepare for exactly this bank
+int rf_knn_tc_launch(const float* bank, long n_rows, long row_offset, const void* image, const float* q, long Q, int k, int kblk,
+                     int* out_idx, double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+    RF_CHECK_ARG(k <= 32, "rf_knn_l2_topk(tensor-core methods): k=%d exceeds 32", k);
     RF_CHECK_ARG(n_rows >= k, "rf_knn_l2_topk(tensor-core methods): fewer bank rows than k");
     const TcLayout L = tc_layout(Q, n_rows, k, kblk);
     char* ws = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);  // swizzled tile images need 1024-byte alignment
-    RF_CHECK_ARG(workspace && workspace_bytes >= L.total + (size_t)(ws - (char*)workspace),
-                 "rf_knn_l2_topk(tensor-core methods): workspace too small (%zu < %zu)", workspace_bytes, L.total + 1024);
-    int rc = kblk == 1 ? tc_run<1>(L, bank, n_rows, row_offset, q, Q, k, out_idx, out_d, ws, s)
-                       : tc_run<3>(L, bank, n_rows, row_offset, q, Q, k, out_idx, out_d, ws, s);
-    if (rc) return rc;
-    // unproven queries (normally none): exact fp64 sweep, results scattered through `flagged`
-    int n_flagged = 0;
-    RF_CUDA_OK(cudaMemcpyAsync(&n_flagged, &((Stats*)(ws + L.stats))->n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
-    RF_CUDA_OK(cudaStreamSynchronize(s));
-    if (g_ev0 && cudaEventElapsedTime(&g_last_candidates_ms, g_ev0, g_ev1) != cudaSuccess) g_last_candidates_ms = -1.f;
-    if (n_flagged > 0)
-        return rf_knn_exact_launch(bank, n_rows, row_offset, q, n_flagged, k, (const int*)(ws + L.flagged), out_idx, out_d,
-                                   ws + L.exact_ws, L.exact_ws_bytes, s);
-    return 0;
+    size_t need = L.total + (size_t)(ws - (char*)workspace);
+    const char* img = nullptr;
+    if (image) {
+        img = (const char*)(((uintptr_t)image + 1023) & ~(uintptr_t)1023);
+    } else {
+        char* own = ws + align_up(L.total, 1024);
+        const size_t ib = align_up(img_layout(n_rows, kblk).total, 1024);
+        need += ib + img_layout(n_rows, kblk).scratch_total + 1024;
+        RF_CHECK_ARG(workspace && workspace_bytes >= need, "rf_knn_l2_topk(tensor-core methods): workspace too small (%zu < %zu)",
+                     workspace_bytes, need);
+        int rc = kblk == 1 ? prepare_bank<1>(bank, n_rows, q, Q, own, own + ib, s) : prepare_bank<3>(bank, n_rows, q, Q, own, own + ib, s);
+        if (rc) return rc;
+        img = own;
+    }
+    RF_CHECK_ARG(workspace && workspace_bytes >= need, "rf_knn_l2_topk(tensor-core methods): workspace too small (%zu < %zu)",
+                 workspace_bytes, need);
+    return kblk == 1 ? tc_run<1>(L, bank, n_rows, row_offset, img, q, Q, k, out_idx, out_d, ws, s)
+                     : tc_run<3>(L, bank, n_rows, row_offset, img, q, Q, k, out_idx, out_d, ws, s);
 }
 
-extern "C" float rf_knn_last_candidates_ms(void) { return g_last_candidates_ms; }
-
 // Diagnostics of the last tensor-core call that used `workspace` (synchronises the stream).
-extern "C" int rf_knn_tc_stats(const void* workspace, int* n_unproven, float* max_score_err, float* candidates_ms,
-                               void* stream) {
+extern "C" int rf_knn_tc_stats(const void* workspace, int* n_unproven, float* max_score_err, void* stream) {
     RF_CHECK_ARG(workspace, "rf_knn_tc_stats: null workspace");
     Stats h;
     const void* ws = (const void*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
@@ -723,6 +808,5 @@ extern "C" int rf_knn_tc_stats(const void* workspace, int* n_unproven, float* ma
     RF_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
     if (n_unproven) *n_unproven = h.n_flagged;
     if (max_score_err) memcpy(max_score_err, &h.max_err_bits, sizeof(float));
-    if (candidates_ms) *candidates_ms = g_last_candidates_ms;  // CUDA-event time of the last candidates kernel (this process)
     return 0;
 }

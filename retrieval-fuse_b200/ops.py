@@ -653,9 +653,38 @@ def mlp_encode(x, wts, biases, l2_normalize=True):
 last_knn_stats = {}
 
 
-def knn_topk(bank, q, k, row_offset=0, method=0, stats=False):
+class KnnBankImage:
+    """The prepared tensor-core operand image of one bank (shard): rf_knn_bank_prepare's output, built once and
+    reused by every lookup (the reference loads its FLANN index once per worker, util/retrieval.py:81-83)."""
+
+    def __init__(self, bank, method, image):
+        self.bank_ptr, self.n_rows, self.method, self.image = bank.data_ptr(), bank.shape[0], method, image
+
+
+def knn_prepare_bank(bank, method=0, q_sample=None):
+    """bank [n,64] fp32 -> KnnBankImage, or None when the bank is too small for the tensor-core path."""
+    bank = _dev(bank, name="bank")
+    n = bank.shape[0]
+    L = _lib.lib()
+    m = L.rf_knn_bank_method(n, int(method))
+    if m < 2:
+        return None
+    image = torch.empty(L.rf_knn_bank_image_bytes(n, m), device=bank.device, dtype=torch.uint8)
+    scratch = torch.empty(L.rf_knn_bank_scratch_bytes(n, m), device=bank.device, dtype=torch.uint8)
+    if q_sample is not None:
+        q_sample = _dev(q_sample, name="q_sample")
+    with torch.cuda.device(bank.device), _timed("rf_knn_bank_prepare"):
+        check(L.rf_knn_bank_prepare(bank.data_ptr(), n, m, _ptr(q_sample), 0 if q_sample is None else q_sample.shape[0],
+                                    image.data_ptr(), image.numel(), scratch.data_ptr(), scratch.numel(), _stream(bank)),
+              "rf_knn_bank_prepare")
+    _count(5)
+    return KnnBankImage(bank, m, image)
+
+
+def knn_topk(bank, q, k, row_offset=0, method=0, stats=False, image=None):
     """Exact top-k under the canonical (fp64 d, row id) rule.
     bank [n,64] fp32, q [Q,64] fp32 -> (idx int32 [Q,k] global ids, d fp64 [Q,k]).
+    image: a KnnBankImage of this bank (skips the per-call operand staging).
     stats=True also fills ops.last_knn_stats for the tensor-core methods."""
     bank = _dev(bank, name="bank")
     q = _dev(q, name="q")
@@ -664,19 +693,33 @@ def knn_topk(bank, q, k, row_offset=0, method=0, stats=False):
     L = _lib.lib()
     idx = torch.empty((Q, k), device=q.device, dtype=torch.int32)
     d = torch.empty((Q, k), device=q.device, dtype=torch.float64)
-    ws_bytes = L.rf_knn_workspace_bytes(Q, n, k, method)
-    ws = torch.empty(max(ws_bytes, 256), device=q.device, dtype=torch.uint8)
-    with torch.cuda.device(q.device), _timed("rf_knn_l2_topk", flops=2.0 * Q * n * 64):
-        check(L.rf_knn_l2_topk(bank.data_ptr(), n, int(row_offset), q.data_ptr(), Q, D, k, method, idx.data_ptr(),
-                               d.data_ptr(), ws.data_ptr(), ws.numel(), _stream(q)), "rf_knn_l2_topk")
-        if stats:
-            import ctypes
-            nu, err, ms = ctypes.c_int(-1), ctypes.c_float(-1.0), ctypes.c_float(-1.0)
-            if method != 1:
-                check(L.rf_knn_tc_stats(ws.data_ptr(), ctypes.byref(nu), ctypes.byref(err), ctypes.byref(ms), _stream(q)),
-                      "rf_knn_tc_stats")
-            last_knn_stats.update(n_unproven=nu.value, max_score_err=err.value, candidates_kernel_ms=ms.value)
-    _count(4)
+    if Q == 0:
+        return idx, d
+    if image is not None:
+        if image.bank_ptr != bank.data_ptr() or image.n_rows != n:
+            raise _lib.RfError("knn_topk: the prepared image belongs to another bank")
+        m = image.method
+        ws = torch.empty(max(L.rf_knn_prepared_workspace_bytes(Q, n, k, m), 256), device=q.device, dtype=torch.uint8)
+        with torch.cuda.device(q.device), _timed("rf_knn_l2_topk", flops=2.0 * Q * n * 64):
+            check(L.rf_knn_l2_topk_prepared(bank.data_ptr(), n, int(row_offset), image.image.data_ptr(), m, q.data_ptr(), Q, D, k,
+                                            idx.data_ptr(), d.data_ptr(), ws.data_ptr(), ws.numel(), _stream(q)),
+                  "rf_knn_l2_topk_prepared")
+        tc = True
+        _count(6)
+    else:
+        ws = torch.empty(max(L.rf_knn_workspace_bytes(Q, n, k, method), 256), device=q.device, dtype=torch.uint8)
+        with torch.cuda.device(q.device), _timed("rf_knn_l2_topk", flops=2.0 * Q * n * 64):
+            check(L.rf_knn_l2_topk(bank.data_ptr(), n, int(row_offset), q.data_ptr(), Q, D, k, method, idx.data_ptr(),
+                                   d.data_ptr(), ws.data_ptr(), ws.numel(), _stream(q)), "rf_knn_l2_topk")
+        tc = method != 1
+        _count(10)
+    if stats:
+        import ctypes
+        nu, err = ctypes.c_int(-1), ctypes.c_float(-1.0)
+        if tc:
+            with torch.cuda.device(q.device):
+                check(L.rf_knn_tc_stats(ws.data_ptr(), ctypes.byref(nu), ctypes.byref(err), _stream(q)), "rf_knn_tc_stats")
+        last_knn_stats.update(n_unproven=nu.value, max_score_err=err.value)
     return idx, d
 
 

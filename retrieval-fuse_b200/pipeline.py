@@ -194,6 +194,10 @@ class RetrievalPipeline:
         the copies of one batch overlap the kernels of the next.  Returns (rows in pinned host memory, event); the
         rows are valid after event.synchronize(), and slot s may be reused once its previous event was waited for."""
         if not hasattr(self, "_pipe_streams"):
+            # first use: fill the lazily built caches (weight images, the bank's operand image) on the current stream
+            # and wait, so that the two pipeline streams never race on their first-use initialisation
+            self.retrieve(chunks_host.to(self.device, non_blocking=True), chunk_scene_host, method)
+            torch.cuda.current_stream(self.device).synchronize()
             self._pipe_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
         st = self._pipe_streams[slot & 1]
         st.wait_stream(torch.cuda.current_stream(self.device))

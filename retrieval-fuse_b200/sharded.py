@@ -25,7 +25,7 @@ class ShardedBankQuery:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self._topk = topk_fn or (lambda emb, q, k, off: ops.knn_topk(emb, q, k, row_offset=off))
+        self._topk = topk_fn or (lambda emb, q, k, off: bank_shard.topk(q, k))  # prepared operand image, reused across calls
         self._merge = merge_fn or ops.knn_merge
         self._demote = demote_fn or ops.knn_demote_rows
 

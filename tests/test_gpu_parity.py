@@ -369,7 +369,8 @@ def _unit(rng, n, d=64):
 @pytest.mark.parametrize("N,Q,k,method", [(5000, 200, 8, 1), (2048, 40000, 8, 1), (70, 33, 32, 1), (131, 1, 1, 1),
                                           (5000, 2000, 8, 2), (20000, 4096, 16, 2), (4096, 1500, 2, 2), (129, 300, 8, 2),
                                           (5000, 2000, 8, 3), (20011, 3000, 16, 3), (131073, 2048, 8, 2),
-                                          (131073, 2048, 8, 0)])
+                                          (131073, 2048, 8, 0), (30000, 3000, 32, 2), (30000, 3000, 24, 3), (9000, 700, 9, 2),
+                                          (40000, 70000, 32, 0)])
 def test_knn_bit_exact(dev, N, Q, k, method):
     from retrieval_fuse_b200 import ops
     rng = np.random.default_rng(N * 7 + Q)
@@ -441,6 +442,94 @@ def test_knn_tensor_core_proof_and_fallback(dev):
         assert ops.last_knn_stats["n_unproven"] >= 50, ops.last_knn_stats
         assert np.array_equal(i.cpu().numpy(), want_i) and np.array_equal(d.cpu().numpy().astype(np.float32), want_d)
         assert np.array_equal(np.sort(want_i[0]), np.sort(dup)[:8])  # ties resolved by the lowest row ids
+
+
+@pytest.mark.parametrize("N,Q,method", [(131073, 40000, 2), (131073, 512, 2), (60000, 30000, 3)])
+def test_knn_wide_fetch_stays_on_tensor_cores(dev, N, Q, method):
+    """util/retrieval.py:92 fetches 2K neighbours for ANY K: 2K = 16 (BASELINE config 4, K = 8) and 2K = 32 (config 5's
+    k = 16) must be served by the tcgen05 candidate pass, not by its exact fallback - the candidate lists are longer
+    than k (32 entries, two bank slices above 16), so the proof goes through for (nearly) every query of a random
+    bank.  Results equal the exact fp64 sweep for every query."""
+    from retrieval_fuse_b200 import ops
+    rng = np.random.default_rng(N + Q)
+    bank, q = torch.from_numpy(_unit(rng, N)).to(dev), torch.from_numpy(_unit(rng, Q)).to(dev)
+    for k in (16, 32):
+        i, d = ops.knn_topk(bank, q, k, method=method, stats=True)
+        st = dict(ops.last_knn_stats)
+        assert 0 <= st["n_unproven"] < 0.01 * Q, (k, st)
+        ei, ed = ops.knn_topk(bank, q, k, method=1)
+        assert torch.equal(i, ei) and torch.equal(d, ed), k
+
+
+def test_knn_prepared_bank_and_graph_capture(dev):
+    """The bank's operand image is built once (EmbeddingBank.topk / ops.knn_prepare_bank) and reused; the lookup makes
+    no host synchronisation, so kNN + demotion replay from a CUDA graph - also when some queries need the exact
+    re-check (their count only exists on the device)."""
+    from retrieval_fuse_b200 import ops
+    from retrieval_fuse_b200.util.retrieval import EmbeddingBank
+    rng = np.random.default_rng(77)
+    N, Q, K = 50000, 3000, 4
+    db, q = _unit(rng, N), _unit(rng, Q)
+    dup = rng.choice(N, size=300, replace=False)
+    db[dup] = db[dup[0]]                      # more exact duplicates than a candidate list holds
+    q[:40] = db[dup[0]] + rng.normal(size=(40, 64)).astype(np.float32) * 1e-4
+    meta = np.zeros((N, 7), dtype=np.float32)
+    meta[:, 0] = rng.integers(0, 30, size=N)
+    qs = rng.integers(-1, 30, size=Q).astype(np.int32)
+    bank = EmbeddingBank(torch.from_numpy(db).to(dev), torch.from_numpy(meta).to(dev), [f"s{i}" for i in range(30)])
+    qd, qsd = torch.from_numpy(q).to(dev), torch.from_numpy(qs).to(dev)
+    want_rows, want_idx = O.lookup_rows(db, meta, q, K, qs)
+    img = ops.knn_prepare_bank(bank.emb, 0, q_sample=qd)
+    assert img is not None
+    i1, d1 = ops.knn_topk(bank.emb, qd, 2 * K, image=img, stats=True)
+    assert ops.last_knn_stats["n_unproven"] >= 40
+    i0, d0 = ops.knn_topk(bank.emb, qd, 2 * K, method=1)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    img_b = ops.knn_prepare_bank(bank.emb, 0)  # scan order from the bank's own mean: same result
+    i2, d2 = ops.knn_topk(bank.emb, qd, 2 * K, image=img_b)
+    assert torch.equal(i0, i2) and torch.equal(d0, d2)
+    rows, idx = bank.query(qd, K, qsd)         # builds + caches the image
+    assert np.array_equal(rows.cpu().numpy(), want_rows) and np.array_equal(idx.cpu().numpy(), want_idx)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        bank.query(qd, K, qsd)
+    torch.cuda.current_stream().wait_stream(side)
+    sq, sqs = qd.clone(), qsd.clone()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_rows, g_idx = bank.query(sq, K, sqs)
+    for perm_seed in (1, 2):                   # replay on permuted query batches (other queries need the re-check now)
+        perm = np.random.default_rng(perm_seed).permutation(Q)
+        pd = torch.from_numpy(perm).to(dev)
+        sq.copy_(qd[pd])
+        sqs.copy_(qsd[pd])
+        graph.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(g_idx.cpu().numpy(), want_idx[perm]) and np.array_equal(g_rows.cpu().numpy(), want_rows[perm])
+
+
+def test_knn_one_million_rows(dev):
+    """BASELINE config 5: a 1 M-row isotropic bank (method 3 above 400 k rows by dispatch), fetch 2k for k in {1, 4, 8,
+    16}: every query equals the exact fp64 sweep, a sample equals the oracle, and hardly any query needs the re-check."""
+    from retrieval_fuse_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(1)
+    bank = torch.nn.functional.normalize(torch.randn(1_000_000, 64, generator=g), dim=1).contiguous()
+    g2 = torch.Generator(device="cpu").manual_seed(2)
+    q = torch.nn.functional.normalize(torch.randn(8192, 64, generator=g2), dim=1).contiguous()
+    bank_d, q_d = bank.to(dev), q.to(dev)
+    img = ops.knn_prepare_bank(bank_d, 0, q_sample=q_d)
+    assert img is not None and img.method == 3
+    for k in (1, 4, 8, 16):
+        i, d = ops.knn_topk(bank_d, q_d, 2 * k, image=img, stats=True)
+        assert 0 <= ops.last_knn_stats["n_unproven"] < 0.01 * q.shape[0], (k, ops.last_knn_stats)
+        ei, ed = ops.knn_topk(bank_d, q_d[:2048].contiguous(), 2 * k, method=1)
+        assert torch.equal(i[:2048], ei) and torch.equal(d[:2048], ed), k
+    want_i, want_d = O.knn_exact(bank.numpy(), q.numpy()[:64], 32)
+    assert np.array_equal(i[:64].cpu().numpy(), want_i) and np.array_equal(d[:64].cpu().numpy().astype(np.float32), want_d)
+    i2, d2 = ops.knn_topk(bank_d, q_d, 8, method=2)   # the fp16 single pass is exact here as well
+    i3, d3 = ops.knn_topk(bank_d, q_d, 8, image=img)
+    assert torch.equal(i2, i3) and torch.equal(d2, d3)
 
 
 def test_knn_full_size_properties(dev):
