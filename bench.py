@@ -76,16 +76,16 @@ def parse():
                                                                "surface 4, refine 8)")
     ap.add_argument("--no-cuda-graph", action="store_true", help="refine workload: launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample-chunks", type=int, default=0, help="chunks of the workload the CPU arm runs per step "
-                                                                    "(0 = workload default: retrieval 2048, full 4, surface 1)")
+                                                                    "(0 = workload default: retrieval 2048, full 64 = the whole step, surface 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     full_like = a.workload in ("full", "surface")
     if a.chunks <= 0:
         a.chunks = {"full": 64, "surface": 16}.get(a.workload, 10000)
     if a.refine_batch <= 0:
-        a.refine_batch = {"full": 16, "surface": 4}.get(a.workload, 8)
+        a.refine_batch = {"full": 64, "surface": 4}.get(a.workload, 8)
     if a.cpu_sample_chunks <= 0:
-        a.cpu_sample_chunks = {"full": 4, "surface": 1}.get(a.workload, 2048)
+        a.cpu_sample_chunks = {"full": 64, "surface": 4}.get(a.workload, 2048)
     if a.workload == "surface" and a.bank_scenes == 2048:
         a.bank_scenes = 512
     a.full_like = full_like
@@ -925,6 +925,107 @@ def run_ours(args, rank, local, world):
         dist.destroy_process_group()
 
 
+def run_sweep(args, rank, local, world):
+    """--workload sweep (BASELINE configs[4]): 1 M-row isotropic bank, brute-force kNN for k in {1, 4, 8, 16} (the lookup
+    fetches 2k, util/retrieval.py:92) on a bulk batch (640 000 queries = 10 000 chunks) and on one refinement batch
+    (64 chunks), plus the attention fuse for the same k.  At N > 1 the bank is sharded by rows over all ranks and every
+    rank brings its own queries (weak scaling).  One JSON line; `value` = chunks/s of the k = 4 bulk lookup."""
+    import torch.distributed as dist
+    from retrieval_fuse_b200 import ops
+    from retrieval_fuse_b200.model import get_attention_block
+    from retrieval_fuse_b200.pipeline import FRONT3D_SR, init_unit_gain_
+    from retrieval_fuse_b200.sharded import ShardedBankQuery
+    from retrieval_fuse_b200.util.retrieval import EmbeddingBank
+    assert torch.cuda.is_available(), "bench.py needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.set_grad_enabled(False)
+    if world > 1:
+        global _REAL_STDOUT
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    hbm = peaks.get("hbm_gbs") or 6500.0
+    N_rows = 1_000_000
+    g = torch.Generator(device=dev).manual_seed(1)
+    full = torch.nn.functional.normalize(torch.randn(N_rows, 64, generator=g, device=dev), dim=1)
+    per = (N_rows + world - 1) // world
+    lo, hi = rank * per, min(N_rows, (rank + 1) * per)
+    meta = torch.zeros((N_rows, 7), device=dev)
+    meta[:, 0] = torch.arange(N_rows, device=dev) // 64
+    bank = EmbeddingBank(full[lo:hi].contiguous(), meta, ["s"], row_offset=lo, n_total=N_rows)
+    del full
+    sq = ShardedBankQuery(bank) if world > 1 else None
+    gq = torch.Generator(device=dev).manual_seed(2 + rank)
+    Qb = 640_000
+    q_bulk = torch.nn.functional.normalize(torch.randn(Qb, 64, generator=gq, device=dev), dim=1)
+    q_small = q_bulk[:4096].contiguous()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, iters):
+        for _ in range(2):
+            fn()
+        if world > 1:
+            dist.barrier()
+        tot = 0.0
+        for _ in range(iters):
+            flush_buf.fill_(1)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        t = torch.tensor([tot / iters], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    rows = []
+    for k in (1, 4, 8, 16):
+        look = (lambda q: sq.query(q, k)) if sq is not None else (lambda q: bank.query(q, k))
+        ms_bulk = timed(lambda: look(q_bulk), max(2, min(args.steps, 3)))
+        ms_small = timed(lambda: look(q_small), args.steps)
+        st = None
+        if world == 1:
+            ops.knn_topk(bank.emb, q_bulk, 2 * k, image=bank._image, stats=True)
+            st = dict(ops.last_knn_stats)
+        cfg = dict(FRONT3D_SR, K=k)
+        attn = init_unit_gain_(get_attention_block(cfg), 5).to(dev).eval()
+        ga = torch.Generator(device=dev).manual_seed(3)
+        B = 8
+        xb = torch.randn(B, 16, 32, 32, 32, generator=ga, device=dev)
+        xr = torch.randn(B * k, 16, 32, 32, 32, generator=ga, device=dev)
+        ms_attn = timed(lambda: attn(xb, xr), args.steps)
+        flops = 2.0 * Qb * world * (hi - lo) * 64   # per rank: all ranks' queries x its shard
+        rows.append({"k": k, "fetch": 2 * k, "knn_bulk_ms": ms_bulk, "knn_bulk_chunks_per_s": Qb / 64 * world / (ms_bulk / 1e3),
+                     "knn_bulk_algorithmic_tflops_per_gpu": flops / ms_bulk / 1e9, "knn_bulk_frac_of_bf16_peak": flops / ms_bulk / 1e9 / peak,
+                     "knn_64chunks_ms": ms_small, "knn_stats": st, "attention_fuse_ms_batch8": ms_attn,
+                     "attention_fuse_gbs": (k + 2.0) * 16 * 32 ** 3 * 4 * B / ms_attn / 1e6,
+                     "attention_fuse_frac_of_hbm": (k + 2.0) * 16 * 32 ** 3 * 4 * B / ms_attn / 1e6 / hbm})
+        log(f"[sweep] {rows[-1]}")
+        del attn, xb, xr
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        r4 = [r for r in rows if r["k"] == 4][0]
+        emit({"metric": "1M-row bank brute-force kNN + attention-fuse sweep (BASELINE configs[4])", "value": r4["knn_bulk_chunks_per_s"],
+              "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": 2, "ms_per_step": r4["knn_bulk_ms"], "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 tcgen05 scores / f64 distance ranking", "data": "synthetic",
+              "config": {"workload": f"1 M-row isotropic unit bank (seed 1), {Qb} isotropic queries per GPU (10 000 chunks), k in 1/4/8/16 "
+                                     f"(fetch 2k), bank in {world} row shard(s); attention fuse on randn [8,16,32^3] + [8k,16,32^3]",
+                         "l2": "flushed between timed launches (256 MiB write)"},
+              "sweep": rows, "clocks": clocks,
+              "peaks": {"bf16_tflops_sustained": peak, "hbm_gbs": hbm, "source": "MEASURED_PEAKS.json" if peaks else "fallback"}})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank, local, world = dist_setup(args)
@@ -934,6 +1035,9 @@ def main():
     if args.workload == "stages":
         if rank == 0:
             run_stages(args, local)
+        return
+    if args.workload == "sweep":
+        run_sweep(args, rank, local, world)
         return
     run_ours(args, rank, local, world)
 

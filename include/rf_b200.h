@@ -36,6 +36,15 @@ int rf_version(void);
 /* sm count / compute capability of `device`; fails if it is not sm_100. */
 int rf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
+/* Handle (SURVEY 8b "no hidden global state besides a handle from rf_create(device) / rf_destroy").  The kernels keep
+ * no mutable global state - every entry point takes its buffers, workspaces and stream as arguments - so the handle
+ * only records its device and performs the per-device one-time setup (opt-in to > 48 KB dynamic shared memory for the
+ * tcgen05 kernels) eagerly; entry points called without a handle do that setup lazily on first use. */
+typedef struct rf_handle_s rf_handle;
+int rf_create(int device, rf_handle** out);
+int rf_destroy(rf_handle* handle);
+int rf_handle_device(const rf_handle* handle, int* device, int* sm_count);
+
 /* ---- a2-a4  patch fold / unfold (bit-exact re-indexing) ------------------- */
 
 /* model/attention.py:186-188 Unfold3D.forward: [B,C,S,S,S] -> [B*(S/E)^3,C,E,E,E] */

@@ -20,6 +20,9 @@ PROTOTYPES = {
     "rf_last_error": (c_char_p, []),
     "rf_version": (c_int, []),
     "rf_device_info": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "rf_create": (c_int, [c_int, POINTER(c_void_p)]),
+    "rf_destroy": (c_int, [c_void_p]),
+    "rf_handle_device": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
     "rf_unfold3d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rf_fold3d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rf_unfold3d_pad_stride": (c_int, [c_void_p, c_void_p, c_int, c_int, _int3, _int3, _int3, _int3, c_float, c_float,
@@ -123,6 +126,19 @@ def lib():
             fn.argtypes = args
         _lib = handle
     return _lib
+
+
+_handles = {}
+
+
+def handle(device_index):
+    """rf_create(device) once per device of this process (eager per-device kernel setup); kept until exit."""
+    h = _handles.get(device_index)
+    if h is None:
+        out = c_void_p()
+        check(lib().rf_create(int(device_index), ctypes.byref(out)), "rf_create")
+        _handles[device_index] = h = out
+    return h
 
 
 def check(rc, what=""):

@@ -26,6 +26,53 @@ extern "C" int rf_device_info(int device, int* sm_count, int* cc_major, int* cc_
     return 0;
 }
 
+int rf_tc_conv_init();
+int rf_tc_conv_halo_init();
+int rf_tc_linear_init();
+int rf_tc_mlp_init();
+int rf_knn_tc_init();
+
+struct rf_handle_s {
+    int device, sm_count;
+};
+
+/* The library keeps no mutable global state: kernels take everything through their arguments, the only per-device
+ * setup is the opt-in to large dynamic shared memory, which rf_create performs for every kernel of `device` (the launch
+ * sites repeat it lazily, so calls without a handle work too).  The handle records the device it was created for. */
+extern "C" int rf_create(int device, rf_handle** out) {
+    RF_CHECK_ARG(out, "rf_create: null output pointer");
+    *out = nullptr;
+    int sm = 0, major = 0, minor = 0;
+    if (int rc = rf_device_info(device, &sm, &major, &minor)) return rc;
+    int prev = 0;
+    RF_CUDA_OK(cudaGetDevice(&prev));
+    RF_CUDA_OK(cudaSetDevice(device));
+    int rc = rf_tc_conv_init();
+    if (!rc) rc = rf_tc_conv_halo_init();
+    if (!rc) rc = rf_tc_linear_init();
+    if (!rc) rc = rf_tc_mlp_init();
+    if (!rc) rc = rf_knn_tc_init();
+    cudaSetDevice(prev);
+    if (rc) return rc;
+    rf_handle* h = new rf_handle_s;
+    h->device = device;
+    h->sm_count = sm;
+    *out = h;
+    return 0;
+}
+
+extern "C" int rf_destroy(rf_handle* h) {
+    delete h;
+    return 0;
+}
+
+extern "C" int rf_handle_device(const rf_handle* h, int* device, int* sm_count) {
+    RF_CHECK_ARG(h, "rf_handle_device: null handle");
+    if (device) *device = h->device;
+    if (sm_count) *sm_count = h->sm_count;
+    return 0;
+}
+
 int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, const int* q_sel,
                         int* out_idx, double* out_d, void* workspace, size_t workspace_bytes, cudaStream_t s);
 int rf_knn_exact_nsplit(long Q, long n_rows);

@@ -38,6 +38,21 @@ void rf_set_error(const char* fmt, ...);
         }                                                                                \
     } while (0)
 
+// One-time, PER-DEVICE opt-in to more than 48 KB of dynamic shared memory for `kernel` (function attributes belong to
+// a device's context; a process may drive several devices).  rf_create(device) runs every kernel's opt-in eagerly;
+// the launch sites repeat it lazily, so the library also works without a handle.  The flags are idempotent caches,
+// not state: a race between threads merely sets the attribute twice.
+#define RF_SMEM_OPT_IN(kernel, bytes)                                                                        \
+    do {                                                                                                     \
+        static bool done__[64] = {};                                                                         \
+        int dev__ = 0;                                                                                       \
+        RF_CUDA_OK(cudaGetDevice(&dev__));                                                                   \
+        if (dev__ < 0 || dev__ >= 64 || !done__[dev__]) {                                                    \
+            RF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            if (dev__ >= 0 && dev__ < 64) done__[dev__] = true;                                              \
+        }                                                                                                    \
+    } while (0)
+
 static inline int rf_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 static inline long rf_cdivl(long a, long b) { return (a + b - 1) / b; }
 

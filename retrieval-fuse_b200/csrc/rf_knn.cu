@@ -253,6 +253,14 @@ int rf_knn_recheck_launch(const float* bank, long n_rows, long row_offset, const
     int ns = RF_RECHECK_SLICES;
     const long max_split = (n_rows + 1023) / 1024;
     if (ns > max_split) ns = (int)max_split;
+    if (ns == 1) {  // a bank of at most 1024 rows: one slice, the sweep writes the final rows itself
+        long gx = (Q + QB - 1) / QB;
+        if (gx > 148 * 8) gx = 148 * 8;
+        knn_exact_f64_kernel<<<dim3((unsigned)gx, 1), WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, q_count, 0, Q, k, 1, q_sel,
+                                                                                 out_idx, out_d);
+        RF_LAUNCH_OK("knn_exact_f64_kernel(re-check)");
+        return 0;
+    }
     double* pd = (double*)workspace;
     int* pi = (int*)(pd + (size_t)ns * cap * k);
     dim3 grid((unsigned)((cap + QB - 1) / QB), ns);

@@ -391,34 +391,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
 #pragma unroll
                 for (int j = 2; j < 32; j += 2) mx = fmaxf(mx, fmaxf(v[j], v[j + 1]));
                 if (mx > tau) {
-                    // Rare path, ONE code site: tag every score with its column (low 5
-                    // mantissa bits; costs 2^-18 relative, covered by the proof's eps),
-                    // then repeatedly pull the maximum while it beats tau.
-                    float key[32];
+                    // Rare path (the whole warp takes it when ANY of its 32 queries has a hit): walk the 32 columns;
+                    // a column that beats the CURRENT tau is inserted into the descending list at once (the column
+                    // index is a compile-time constant here - no tagging, no max extraction, no second scan), and
+                    // tau tightens for the remaining columns.  Insertion order does not matter: the list always
+                    // holds the CAND best scores seen so far.
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)  // masked (padded) columns stay at -FLT_MAX and can never beat tau
-                        key[j] = v[j] == -FLT_MAX ? -FLT_MAX : __uint_as_float((__float_as_uint(v[j]) & ~31u) | (uint32_t)j);
-#pragma unroll 1
-                    for (int guard = 0; guard < 32; ++guard) {
-                        float km = fmaxf(key[0], key[1]);
+                    for (int j = 0; j < 32; ++j) {
+                        if (v[j] > tau) {  // masked (padded) columns sit at -FLT_MAX and can never beat tau
+                            float cs = v[j];
+                            int ci = (int)(col0 + j);
 #pragma unroll
-                        for (int j = 2; j < 32; j += 2) km = fmaxf(km, fmaxf(key[j], key[j + 1]));
-                        if (!(km > tau)) break;
-                        float cs = km;
-                        int ci = (int)(col0 + (long)(__float_as_uint(km) & 31u));
-#pragma unroll
-                        for (int i = 0; i < CAND; ++i) {  // insert into the descending list, dropping the last
-                            const bool gt = cs > ls[i];
-                            const float ts = gt ? ls[i] : cs;
-                            const int ti = gt ? li[i] : ci;
-                            ls[i] = gt ? cs : ls[i];
-                            li[i] = gt ? ci : li[i];
-                            cs = ts;
-                            ci = ti;
+                            for (int i = 0; i < CAND; ++i) {  // insert into the descending list, dropping the last
+                                const bool gt = cs > ls[i];
+                                const float ts = gt ? ls[i] : cs;
+                                const int ti = gt ? li[i] : ci;
+                                ls[i] = gt ? cs : ls[i];
+                                li[i] = gt ? ci : li[i];
+                                cs = ts;
+                                ci = ti;
+                            }
+                            tau = ls[CAND - 1];
                         }
-                        tau = ls[CAND - 1];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) key[j] = (key[j] == km) ? -FLT_MAX : key[j];
                     }
                 }
             }
@@ -596,16 +590,9 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restr
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// per-device one-time function attributes (one process may drive several devices)
 template <int KBLK, int CAND>
 int set_candidates_attr() {
-    static bool done[64] = {};
-    int dev = 0;
-    RF_CUDA_OK(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && done[dev]) return 0;
-    RF_CUDA_OK(cudaFuncSetAttribute(knn_tc_candidates_kernel<KBLK, CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg<KBLK>::SMEM_BYTES));
-    if (dev >= 0 && dev < 64) done[dev] = true;
+    RF_SMEM_OPT_IN((knn_tc_candidates_kernel<KBLK, CAND>), Cfg<KBLK>::SMEM_BYTES);
     return 0;
 }
 
@@ -748,6 +735,13 @@ int tc_run(const TcLayout& L, const float* bank, long n_rows, long row_offset, c
 }
 
 }  // namespace
+
+int rf_knn_tc_init() {
+    if (int rc = set_candidates_attr<1, 16>()) return rc;
+    if (int rc = set_candidates_attr<1, 32>()) return rc;
+    if (int rc = set_candidates_attr<3, 16>()) return rc;
+    return set_candidates_attr<3, 32>();
+}
 
 // kblk = 1: fp16 single pass (method 2); kblk = 3: bf16 hi/lo split (method 3)
 size_t rf_knn_tc_image_bytes(long n_rows, int kblk) { return img_layout(n_rows, kblk).total + 1024; }

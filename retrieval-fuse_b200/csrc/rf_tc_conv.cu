@@ -134,8 +134,22 @@ __global__ void __launch_bounds__(256) cl_gn_partial_kernel(const float* __restr
                 const double v = (double)__ldg(base + e);
                 s1 += v; s2 += v * v;
             }
-            atomicAdd(&sh[c], s1);
-            atomicAdd(&sh[C + c], s2);
+            if (C <= 32 && (32 % C) == 0) {
+                // lanes l, l + C, l + 2C, ... of a warp hold the same channel (T is a multiple of 32 here): fold them
+                // with shuffles so that only C lanes per warp touch the shared accumulators (a 1-channel tensor made
+                // all 256 threads hit one shared-memory word)
+                for (int o = 16; o >= C; o >>= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                if ((int)(threadIdx.x & 31) < C) {
+                    atomicAdd(&sh[c], s1);
+                    atomicAdd(&sh[C + c], s2);
+                }
+            } else {
+                atomicAdd(&sh[c], s1);
+                atomicAdd(&sh[C + c], s2);
+            }
         }
     } else {
         for (long e = threadIdx.x; e < total; e += 256) {
@@ -609,6 +623,11 @@ extern "C" int rf_tc_conv_weight_image(const float* w, int Cout, int C1, int C2,
     return 0;
 }
 
+int rf_tc_conv_init() {
+    RF_SMEM_OPT_IN(tc_conv3d_kernel, conv_smem(MAX_A_STAGES, MAX_B_STAGES, 128));
+    return 0;
+}
+
 extern "C" int rf_tc_conv3d_fwd(const void* x_hi, const void* x_lo, int C1, const void* x2_hi, const void* x2_lo, int C2,
                                 const void* weight_image, const float* bias, float* y, int N, int Di, int Hi, int Wi, int Cout,
                                 int KS, int stride, int pad, int act, float slope, float out_scale, int out_ncdhw, void* stream) {
@@ -634,12 +653,7 @@ extern "C" int rf_tc_conv3d_fwd(const void* x_hi, const void* x_lo, int C1, cons
     RF_CHECK_ARG(!a.cin1 || C1 == 1, "rf_tc_conv3d_fwd: a single input channel must come from x");
     a.a_stages = MAX_A_STAGES;
     a.b_stages = 2;  // Npad <= 64: 97 KiB per CTA -> two CTAs per SM; Npad = 128: 129 KiB, one CTA
-    static bool attr_set = false;
-    if (!attr_set) {
-        RF_CUDA_OK(cudaFuncSetAttribute(tc_conv3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        conv_smem(MAX_A_STAGES, MAX_B_STAGES, 128)));
-        attr_set = true;
-    }
+    if (int rc = rf_tc_conv_init()) return rc;
     tc_conv3d_kernel<<<(unsigned)rf_cdivl(M, TM), NTHREADS, conv_smem(a.a_stages, a.b_stages, a.Npad), (cudaStream_t)stream>>>(a);
     RF_LAUNCH_OK("tc_conv3d_kernel");
     return 0;

@@ -53,15 +53,19 @@ __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs
     // writes, so only the D x H x W interior of the real chunks is visited (half the slots of an 8^3 patch are halo)
     const int Dv = s.interior_only ? s.D : Dp, Hv = s.interior_only ? s.H : Hp, Wv = s.interior_only ? s.W : Wp;
     const int off = s.interior_only ? s.pad : 0;
-    const long total = (long)(s.interior_only ? s.CC : s.CCe) * s.N * Dv * Hv * Wv;
+    const int CCv = s.interior_only ? s.CC : s.CCe;
+    const long total = (long)CCv * s.N * Dv * Hv * Wv;
     const int c_tot = s.C1 + s.C2;
+    // thread <-> (voxel, channel chunk) with the CHUNK fastest: consecutive threads read consecutive 32-byte pieces of
+    // one voxel's channels (whole lines of the channels-last source), and the 8 / CC voxels a warp covers per chunk
+    // land in consecutive slots of that chunk's plane (128-byte runs on the store side)
     for (long j = blockIdx.x * (long)blockDim.x + threadIdx.x; j < total; j += (long)gridDim.x * blockDim.x) {
         long t = j;
+        const int cc = (int)(t % CCv); t /= CCv;
         const int ww = (int)(t % Wv) + off; t /= Wv;
         const int hh = (int)(t % Hv) + off; t /= Hv;
         const int dd = (int)(t % Dv) + off; t /= Dv;
-        const int n = (int)(t % s.N);
-        const int cc = (int)(t / s.N);
+        const int n = (int)t;
         const long i = (((long)cc * s.N + n) * Dp + dd) * Hp * Wp + (long)hh * Wp + ww;  // slot index in the haloed planes
         uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
         if (cc < s.CC && ww >= s.pad && ww < s.W + s.pad && hh >= s.pad && hh < s.H + s.pad && dd >= s.pad && dd < s.D + s.pad) {
@@ -626,6 +630,11 @@ extern "C" int rf_tc_conv3d_halo_supported(int N, int D, int H, int W, int Cout,
     return choose_geometry(N, Do, Ho, Wo, CCe, pair, Npad, g) && g.n_tiles <= 32 ? 1 : 0;
 }
 
+int rf_tc_conv_halo_init() {
+    RF_SMEM_OPT_IN(tc_conv3d_halo_kernel, SMEM_LIMIT);
+    return 0;
+}
+
 extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y,
                                      int N, int D, int H, int W, int pad, int Cout, int C1, int C2, int act, float slope,
                                      float out_scale, int out_ncdhw, void* stream) {
@@ -658,11 +667,7 @@ extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void*
         const long off = g.lines ? (long)(t / g.n_wblk) * 16 * a.Wp + (t % g.n_wblk) * 8 : (long)t * 128;
         a.tile_off[t] = (uint16_t)(t < g.n_tiles ? off : 0);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        RF_CUDA_OK(cudaFuncSetAttribute(tc_conv3d_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        attr_set = true;
-    }
+    if (int rc = rf_tc_conv_halo_init()) return rc;
     a.n_items = g.n_items; a.n_sets = g.n_sets; a.fused = g.fused;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

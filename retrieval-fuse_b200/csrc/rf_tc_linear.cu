@@ -310,18 +310,18 @@ extern "C" int rf_tc_weight_image(const float* w, int N, int K, void* image, voi
     return 0;
 }
 
+int rf_tc_linear_init() {
+    RF_SMEM_OPT_IN(tc_linear_kernel, lin_smem(MAX_A_STAGES, MAX_B_STAGES));
+    return 0;
+}
+
 extern "C" int rf_tc_linear_fwd(const float* x, int ldx, const void* weight_image, const float* bias, float* y, long M, int K,
                                 int N, int act, float slope, void* stream) {
     RF_CHECK_ARG(x && weight_image && y, "rf_tc_linear_fwd: null pointer");
     RF_CHECK_ARG(tc_shape_ok(K, N) && M > 0 && ldx >= K, "rf_tc_linear_fwd: unsupported shape M=%ld K=%d N=%d ldx=%d", M, K, N, ldx);
     RF_CHECK_ARG(((uintptr_t)x & 15) == 0 && (ldx % 4) == 0 && ((uintptr_t)y & 15) == 0, "rf_tc_linear_fwd: x / y must be 16-byte aligned, ldx % 4 == 0");
     RF_CHECK_ARG(((uintptr_t)weight_image & 1023) == 0, "rf_tc_linear_fwd: weight image must be 1024-byte aligned");
-    static bool attr_set = false;
-    if (!attr_set) {
-        RF_CUDA_OK(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        lin_smem(MAX_A_STAGES, MAX_B_STAGES)));
-        attr_set = true;
-    }
+    if (int rc = rf_tc_linear_init()) return rc;
     LinArgs a;
     a.x = x; a.wimg = (const uint8_t*)weight_image; a.bias = bias; a.y = y; a.M = M; a.K = K;
     a.Kp = (K + KBE - 1) / KBE * KBE; a.N = N; a.nt = pick_nt(N); a.ldx = ldx; a.act = act; a.slope = slope;

@@ -403,6 +403,11 @@ extern "C" int rf_tc_mlp_weight_image(const float* w, int N, int K, void* image,
     return 0;
 }
 
+int rf_tc_mlp_init() {
+    RF_SMEM_OPT_IN(tc_mlp_kernel, SMEM_LIMIT);
+    return 0;
+}
+
 extern "C" int rf_tc_mlp_fwd(const float* x, int ldx, const void* const* images_host, const float* const* bias_host,
                              const int* widths_host, int n_layers, int act, float slope, int l2_normalize, float eps, float* y,
                              int ldy, long M, void* stream) {
@@ -433,11 +438,7 @@ extern "C" int rf_tc_mlp_fwd(const float* x, int ldx, const void* const* images_
     a.nbw = (int)nbw;
     a.n_tiles = (int)rf_cdivl(M, TM);
     const size_t smem = 1024 + 2 * (size_t)ACT_BYTES + (size_t)a.nbw * a.slot_bytes + 16 * MAX_SLOTS + 32 + 1024 + 64;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RF_CUDA_OK(cudaFuncSetAttribute(tc_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        attr_set = true;
-    }
+    if (int rc = rf_tc_mlp_init()) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

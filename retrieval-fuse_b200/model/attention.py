@@ -60,6 +60,23 @@ class AttentionBlock(RfModule):
             imgs = [self._wcache.derived((tag, j), [m.weight], ops.tc_mlp_weight_image) for j, m in enumerate(lin)]
         return [self._wt(m.weight) for m in lin], [m.bias for m in lin], imgs
 
+    def forward(self, x, p, gumbel_noise=None):
+        """model/attention.py:84-113.  x [b, C, E,E,E] predicted sub-patches, p [b, K, C, E,E,E] their K retrieved
+        candidates -> [b, C, E,E,E].  Every sub-patch is handed to rf_attention_fuse_fwd as a volume of edge E (one
+        sub-patch per volume), which is exactly the computation PatchedAttentionBlock runs on unfolded volumes."""
+        ops._forward_only(x, p, *self.parameters())
+        b, k, c, e = p.shape[0], p.shape[1], p.shape[2], p.shape[3]
+        if k != self.K:
+            raise ValueError(f"AttentionBlock was built for K = {self.K} retrievals, got {k} (MaxPool1d(kernel_size=K), :59)")
+        if b == 0:
+            return x.new_empty(x.shape)
+        mode = 1 if self.retrieval_mode else 0
+        if mode == 1 and gumbel_noise is None:
+            gumbel_noise = -torch.empty(b, k, device=x.device, dtype=torch.float32).exponential_().log()
+        return ops.attention_fuse(x.reshape(b, c, e, e, e), p.reshape(b * k, c, e, e, e), self._branch(self.theta),
+                                  self._branch(self.phi), e, k, normalize=self.normalize, mode=mode, blend=self.blend_mode,
+                                  gumbel_noise=gumbel_noise)
+
     def get_regularization_losses(self):
         return ((self.sig_scale - self.init_scale) ** 2 + (self.sig_shift - self.init_shift) ** 2) if self.use_switching else 0
 

@@ -315,6 +315,31 @@ def test_attention(dev, nf, K, mode):
         assert np.array_equal(of.cpu().numpy(), g[tag + ".feat_occ"])
 
 
+def test_attention_block_forward_on_sub_patches(dev):
+    """AttentionBlock.forward(x, p) (model/attention.py:84-113) called directly on unfolded sub-patches, as
+    PatchedAttentionBlock does internally: x [b, C, 2,2,2], p [b, K, C, 2,2,2]; K must match the configuration."""
+    from retrieval_fuse_b200.model import get_attention_block
+    nf, K = 16, 4
+    cfg = dict(nf=nf, attn_patch_extent=4, K=K, attn_normalize=True, attn_use_switching=True, attn_retrieval_mode=False,
+               attn_no_output_mapping=True, attn_blend=True, attn_num_patch=16)
+    m, sd = load(get_attention_block(cfg), O.attention_shapes(nf, 2), dev)
+    ab = m.attention_blocks_layer
+    b = 777
+    x = C.rnd("ab.x", (b, nf, 2, 2, 2))
+    p = C.rnd("ab.p", (b, K, nf, 2, 2, 2))
+    p[:5, 1] = x[:5]  # an exact match among the candidates: score 1, switch 1, output = that candidate
+    y64 = O.attention_block_forward(x.double(), p.double(), {k: v.double() for k, v in sd.items()})
+    y32 = O.attention_block_forward(x, p, sd)
+    y = ab(x.to(dev), p.to(dev))
+    assert y.shape == x.shape
+    ref_noise = float((y32.double() - y64).abs().max())
+    ours = float((y.cpu().double() - y64).abs().max())
+    assert ours <= max(2 * ref_noise, TOL), f"|ours-fp64| {ours:.3e} vs reference fp32 noise {ref_noise:.3e}"
+    with pytest.raises(ValueError):
+        ab(x.to(dev), p[:, :3].contiguous().to(dev))
+    assert ab(x[:0].to(dev), p[:0].to(dev)).shape == (0, nf, 2, 2, 2)
+
+
 # --------------------------------------------------------------------------- a17
 
 def test_refine_full_forward(dev):
@@ -806,6 +831,80 @@ def test_hot_path_end_to_end_small(dev):
     G.smoke()
 
 
+def test_config3_bank_in_four_shards_full_path(dev):
+    """BASELINE configs[2]: 3DFront SR 008 -> 064, the bank in 4 row shards, full refine forward.  On one GPU the four
+    shards are queried one after the other (the N > 1 exchange itself is tests/test_sharded_gloo.py, world 4): per-shard
+    top-2K with global ids + rf_knn_merge + demotion must equal the single-bank lookup and the oracle, and
+    RefinementPipeline.infer (graph replay, sub-batches) must reproduce the oracle's TSDF for every chunk."""
+    from retrieval_fuse_b200 import ops
+    from retrieval_fuse_b200.pipeline import FRONT3D_SR as CFG, RefinementPipeline, build_synthetic_world
+    world = build_synthetic_world(n_bank_scenes=40, n_query_chunks=6, seed=3, device=dev)
+    bank, store = world["bank"], world["scene_store"]
+    pipe = RefinementPipeline(CFG, bank, store, device=dev, weight_seed=77)
+    chunks = world["query_inputs"]
+    scene = pipe.expand_scene(world["query_scene"])
+    q = pipe.encode_queries(chunks)
+    rows1, idx1 = pipe.lookup(q, scene)
+    K = CFG["K"]
+    parts_i, parts_d = [], []
+    for sh in range(4):
+        b = bank.shard(sh, 4)
+        i, d = b.topk(q, 2 * K)
+        parts_i.append(i)
+        parts_d.append(d)
+    mi, md = ops.knn_merge(torch.stack(parts_i), torch.stack(parts_d))
+    rows4, idx4 = ops.knn_demote_rows(mi, md, bank.meta, scene, K)
+    assert torch.equal(rows4, rows1) and torch.equal(idx4, idx1)
+    qs = np.repeat(np.asarray(world["query_scene"]), pipe.patches_per_chunk)
+    rows_ref, idx_ref = O.lookup_rows(bank.emb.cpu().numpy(), bank.meta.cpu().numpy(), q.cpu().numpy(), K, qs)
+    assert np.array_equal(idx4.cpu().numpy(), idx_ref) and np.array_equal(rows4.cpu().numpy(), rows_ref)
+    pred = pipe.infer(chunks, world["query_scene"], refine_batch=4, graphed=True)
+    pred_e = pipe.infer(chunks, world["query_scene"], refine_batch=6, graphed=False)
+    assert float((pred - pred_e).abs().max()) <= 1e-6
+    sds = pipe.state_dicts()
+    retr_ref = O.compose_chunks(CFG, rows_ref, store.cpu().numpy(), chunks.shape[0])
+    pred_ref = O.refine_chunks(CFG, {k: v for k, v in sds.items() if k != "fenc_input"}, chunks.cpu().numpy(), retr_ref)[0].numpy()
+    e_tanh = float(np.abs(pred.cpu().numpy() - pred_ref).max())
+    e_df = e_tanh * pipe.target_trunc / 2
+    print(f"config 3 full path: max |pred - oracle| = {e_tanh:.2e} (tanh domain) = {e_df:.2e} (TSDF units)")
+    assert e_df <= 1e-4, f"TSDF prediction differs from the oracle by {e_df:.2e}"
+    # host buffers in and out
+    out_host = torch.empty((6, 1, 64, 64, 64)).pin_memory()
+    pipe.infer_host(chunks.cpu().pin_memory(), out_host, world["query_scene"], refine_batch=4)
+    assert torch.equal(out_host, pred.cpu())
+
+
+def test_refine_graphs_survive_alternating_batch_sizes(dev):
+    """Captured CUDA graphs hold raw pointers to the layers' operand planes and weight images: a second input shape
+    must not free what the first graph reads (planes are kept per shape), and rebuilding the weight images
+    (load_state_dict) must invalidate the graphs instead of replaying stale pointers."""
+    from retrieval_fuse_b200 import ops
+    from retrieval_fuse_b200.pipeline import FRONT3D_SR as CFG, RefinementPipeline
+    pipe = RefinementPipeline(CFG, bank=None, device=dev, weight_seed=9)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    xs = {B: (torch.randn(B, 1, 8, 8, 8, generator=g).to(dev), (torch.rand(B, 4, 64, 64, 64, generator=g) * 3 - 1).to(dev)) for B in (2, 3)}
+    want = {B: pipe.refine(*xs[B])[0].clone() for B in (2, 3)}
+    for B in (2, 3, 2, 3, 2):
+        got = pipe.refine_graphed(*xs[B])
+        assert float((got - want[B]).abs().max()) <= 1e-6, B
+    assert len(pipe._graphs) == 2
+    # new weights: the derived images are rebuilt, every graph is re-captured, results follow the new weights
+    sd = {k: v.clone() for k, v in pipe.decoder.state_dict().items()}
+    for k in sd:
+        if k.endswith("conv.weight"):
+            sd[k] = sd[k] * 0.5
+    pipe.decoder.load_state_dict(sd)
+    want2 = pipe.refine(*xs[2])[0].clone()
+    assert float((want2 - want[2]).abs().max()) > 1e-4
+    got2 = pipe.refine_graphed(*xs[2])
+    assert float((got2 - want2).abs().max()) <= 1e-6
+    # more shapes than a layer keeps plane sets for: the oldest set is freed and the graphs are dropped, not replayed
+    for B in (1, 4, 5, 6):
+        x = (torch.randn(B, 1, 8, 8, 8, generator=g).to(dev), (torch.rand(B, 4, 64, 64, 64, generator=g) * 3 - 1).to(dev))
+        assert float((pipe.refine_graphed(*x) - pipe.refine(*x)[0]).abs().max()) <= 1e-6
+    assert float((pipe.refine_graphed(*xs[2]) - want2).abs().max()) <= 1e-6
+
+
 def test_host_pipeline_matches_synchronous_call(dev):
     """retrieve_host_async (two batches in flight on alternating streams) returns exactly what retrieve_host does."""
     from retrieval_fuse_b200.pipeline import FRONT3D_SR, RetrievalPipeline, build_bank_from_targets, synthetic_tsdf_batch
@@ -855,10 +954,26 @@ def test_surface_reconstruction_config_end_to_end(dev):
     assert retr.shape == (1, 8, 64, 64, 64) and np.array_equal(retr.cpu().numpy(), retr_ref)
     pred = pipe.refine(pipe.normalize_input(chunks), pipe.compose(rows, 1, normalize=True))[0]
     pred_ref = O.refine_chunks(CFG, {k: v for k, v in sds.items() if k != "fenc_input"}, grid, retr_ref)[0]
-    # TSDF units here are centimetres-scale (trunc = 11.25): compare in the network's tanh domain against
-    # the fp32 noise of this 5-level network instead
-    err = float((pred.cpu() - pred_ref).abs().max())
-    assert err <= 2e-3, f"surface-reconstruction refine forward differs by {err:.2e}"
+    # north_star's "fp32 TSDF values within 1e-4" has two readings for this dataset, whose TSDF unit makes trunc = 11.25
+    # (3 x 3.75): in TSDF units 1e-4 is 1.8e-5 of the tanh range, below the fp32 noise of this 5-level network on
+    # 128^3 inputs.  Both domains are reported; the gate is the same as for config 1: no further from an fp64
+    # evaluation of the network than 4x the reference arithmetic's own fp32 distance from it, plus 1e-4 in the
+    # tanh domain against the oracle.
+    err_tanh = float((pred.cpu() - pred_ref).abs().max())
+    err_df = err_tanh * pipe.target_trunc / 2
+    cfg64 = dict(kind="surface", nf=CFG["nf"], unet_num_level=CFG["unet_num_level"], retrieval_fmaps=CFG["retrieval_fmaps"],
+                 retrieval_num_level=CFG["retrieval_num_level"], K=CFG["K"], E=CFG["attn_patch_extent"] // 2)
+    d_ = CFG["dataset"]
+    x_in64 = torch.from_numpy(((grid - d_["input_mean"]) / d_["input_std"]).astype(np.float32)).double()
+    x_re64 = torch.from_numpy(((retr_ref - d_["target_mean"]) / d_["target_std"]).astype(np.float32)).double()
+    sd64 = {k: {n: v.double() for n, v in dd.items()} for k, dd in sds.items() if k != "fenc_input"}
+    p64 = O.refine_forward(x_in64, x_re64, sd64, cfg64)[0]
+    ref_noise = float((pred_ref.double() - p64).abs().max())
+    ours = float((pred.cpu().double() - p64).abs().max())
+    print(f"surface config: |pred - oracle| = {err_tanh:.2e} (tanh domain) = {err_df:.2e} (TSDF units, trunc {pipe.target_trunc}); "
+          f"|ours - fp64| = {ours:.2e}, reference arithmetic |fp32 - fp64| = {ref_noise:.2e}")
+    assert ours <= 4 * ref_noise + 1e-5, f"|ours-fp64| {ours:.3e} vs reference's fp32 noise {ref_noise:.3e}"
+    assert err_tanh <= max(1e-4, 5 * ref_noise), f"surface-reconstruction refine forward differs by {err_tanh:.2e} (tanh domain)"
 
 
 def test_retrieval_interface_roundtrip(dev, tmp_path):

@@ -84,7 +84,7 @@ def _worker(rank, world, port, N, Ql, K, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,N", [(2, 1001), (3, 50)])
+@pytest.mark.parametrize("world,N", [(2, 1001), (3, 50), (4, 403)])  # 4 = BASELINE configs[2]: bank over 4 ranks
 def test_sharded_query_equals_single_bank(world, N):
     ctx = mp.get_context("spawn")
     out = ctx.Manager().dict()
