@@ -994,7 +994,7 @@ def run_sweep(args, rank, local, world):
         ms_small = timed(lambda: look(q_small), args.steps)
         st = None
         if world == 1:
-            ops.knn_topk(bank.emb, q_bulk, 2 * k, image=bank._image, stats=True)
+            ops.knn_topk(bank.emb, q_bulk, 2 * k, stats=True)
             st = dict(ops.last_knn_stats)
         cfg = dict(FRONT3D_SR, K=k)
         attn = init_unit_gain_(get_attention_block(cfg), 5).to(dev).eval()

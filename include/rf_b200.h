@@ -229,9 +229,10 @@ int rf_knn_l2_topk(const float* bank, long n_rows, long row_offset, const float*
  * operand image (scan order + swizzled 16-bit tiles + |x|^2 range) is built
  * once by rf_knn_bank_prepare into a caller-owned buffer of
  * rf_knn_bank_image_bytes and reused by every rf_knn_l2_topk_prepared call.
- * q_sample (optional, n_sample rows): a sample of typical queries whose mean
- * direction orders the scan (exactness is unaffected); NULL = the bank's own
- * mean.  rf_knn_bank_method resolves method 0 for a bank of n_rows (1 = too
+ * q_sample (optional, n_sample rows): a sample of the queries the image will
+ * serve; their mean direction orders the scan (rows that score high for a
+ * typical query first - fewer list insertions, exactness unaffected).  NULL =
+ * rows stay in bank order, the right choice when later queries are unknown.  rf_knn_bank_method resolves method 0 for a bank of n_rows (1 = too
  * small for the tensor-core path: use rf_knn_l2_topk). */
 int rf_knn_bank_method(long n_rows, int method);
 size_t rf_knn_bank_image_bytes(long n_rows, int method);
@@ -324,6 +325,40 @@ int rf_chamfer_nn(const float* a, int na, const float* b, int nb, float* dist, i
 size_t rf_ntxent_workspace_bytes(int N);
 int rf_ntxent_fwd(const float* zis, const float* zjs, int N, int C, const float* iou_matrix, float temperature, float sig_scale,
                   float sig_shift, int cosine, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- 8f.3  backward passes (training_step_full, trainer/train_refinement.py:74-89) ---------- */
+
+/* Adjoint of rf_conv3d_fwd with respect to the filter: dw [Cout, Cin, KS,KS,KS] (the nn.Conv3d / nn.Linear layout,
+ * overwritten) = sum over all output positions of dz [N,Cout,Do,Ho,Wo] x the normalised, zero-padded, virtually
+ * upsampled + concatenated input (same arguments as the forward).  KS = 1 with D = H = W = 1 is nn.Linear's
+ * weight gradient.  The adjoint with respect to the INPUT is rf_conv3d_fwd itself on the flipped, transposed filter. */
+int rf_conv3d_wgrad(const float* x, const float* x2, int C2, const float* gn_mu, const float* gn_a, const float* gn_beta,
+                    const float* dz, float* dw, int N, int Cin, int Di, int Hi, int Wi, int Cout, int KS, int stride, int pad,
+                    void* stream);
+/* dz = dy * act'(pre-activation), written through the saved OUTPUT y (ReLU, LeakyReLU(slope > 0), tanh, none). */
+int rf_act_bwd(const float* dy, const float* y, float* dz, long n, int act, float slope, void* stream);
+/* out[c] = sum over n, v of x [N,C,V] (bias gradients; V = 1 for Linear layers). */
+int rf_channel_sum(const float* x, int N, int C, long V, float* out, void* stream);
+/* GroupNorm backward (model/unet.py:60-64 in front of every conv): g = dL/d(normalised input) of the virtual input
+ * concat(x [N,C-C2,...], up2(x2 [N,C2,...])); gn_mu / gn_rstd [N,C] per-channel copies of the group statistics.
+ * dx (fine part), dx2 (coarse part: its 8 children summed), dgamma / dbeta [C] (may be NULL). */
+size_t rf_gn_bwd_workspace_bytes(int N, int C);
+int rf_gn_bwd(const float* x, const float* x2, int C2, const float* g, const float* gn_mu, const float* gn_rstd,
+              const float* gamma, int N, int C, int D, int H, int W, int groups, float* dx, float* dx2, float* dgamma,
+              float* dbeta, void* workspace, void* stream);
+/* Nearest x2 upsampling backward for channels [C1, C) of g [N,C,D,H,W] -> dx2 [N,C-C1,D/2,H/2,W/2] (no GroupNorm). */
+int rf_upsample2_bwd(const float* g, int N, int C, int C1, int D, int H, int W, float* dx2, void* stream);
+/* MaxPool3d(2) backward: the first maximum of each window (scan order d, h, w) receives dy. */
+int rf_maxpool3d_2_bwd(const float* x, const float* dy, float* dx, int N, int C, int D, int H, int W, void* stream);
+/* model/attention.py:84-113 on precomputed theta / phi features (rows in Unfold3D order: xf [R,32], xu [R,V]; pf, pu
+ * in (b, k, r) order), and its adjoint with respect to the features and the row vectors.  The differentiable path
+ * runs theta / phi layer by layer so that autograd keeps the activations; rf_attention_fuse_fwd is the fused
+ * inference call. */
+int rf_attention_epilogue_fwd(const float* xf, const float* pf, const float* xu, const float* pu, const float* noise, float* orows,
+                              long R, int rp3, int K, int V, int normalize, int mode, int blend, float sharp, void* stream);
+int rf_attention_epilogue_bwd(const float* xf, const float* pf, const float* xu, const float* pu, const float* noise,
+                              const float* dout, float* dxf, float* dpf, float* dxu, float* dpu, long R, int rp3, int K, int V,
+                              int normalize, int mode, int blend, float sharp, void* stream);
 
 #ifdef __cplusplus
 }

@@ -99,6 +99,19 @@ PROTOTYPES = {
     "rf_sobel_normals": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "rf_occupancy_counts": (c_int, [c_void_p, c_void_p, c_int, c_long, c_void_p, c_void_p]),
     "rf_chamfer_nn": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "rf_conv3d_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "rf_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_float, c_void_p]),
+    "rf_channel_sum": (c_int, [c_void_p, c_int, c_int, c_long, c_void_p, c_void_p]),
+    "rf_gn_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "rf_gn_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                          c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rf_upsample2_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "rf_maxpool3d_2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "rf_attention_epilogue_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int,
+                                          c_int, c_int, c_int, c_float, c_void_p]),
+    "rf_attention_epilogue_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_long, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "rf_ntxent_workspace_bytes": (c_size_t, [c_int]),
     "rf_ntxent_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_float, c_float, c_int, c_void_p, c_void_p,
                               c_size_t, c_void_p]),

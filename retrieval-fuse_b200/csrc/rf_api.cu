@@ -89,19 +89,20 @@ static size_t exact_ws(long Q, long n_rows, int k) {
     return ns == 1 ? 256 : (size_t)ns * Q * k * (sizeof(int) + sizeof(double)) + 256;
 }
 
-// 0 = auto: the tensor-core candidate pass whenever it applies (k <= 32, enough
-// work to amortise the operand images); fp16 single pass up to 400k rows, the
-// bf16 split above (denser banks need the tighter error bound).
+// 0 = auto: the tensor-core candidate pass whenever it applies (k <= 32, enough work to amortise the operand
+// images), as ONE fp16 GEMM (method 2).  Measured on a 1 M-row isotropic bank (BASELINE configs[4]) the fp16 pass
+// proves every query and is ~3x faster than the bf16 hi/lo split (method 3: three times the MMAs, two instead of six
+// pipeline stages); method 3 stays available for banks so dense in near-ties that the 1e-3 score bound of method 2
+// sends many queries to the exact re-check (ops.last_knn_stats / rf_knn_tc_stats report that count).
 static int resolve_method(int method, long Q, long n_rows, int k) {
     if (method != 0) return method;
     if (k > 32 || n_rows < 1024 || Q * n_rows < (1L << 24)) return 1;
-    return n_rows <= 400000 ? 2 : 3;
+    return 2;
 }
 // the method a PREPARED image of this bank is built for (no query count yet): tensor cores unless the bank is tiny
 static int resolve_bank_method(int method, long n_rows) {
     if (method != 0) return method;
-    if (n_rows < 1024) return 1;
-    return n_rows <= 400000 ? 2 : 3;
+    return n_rows < 1024 ? 1 : 2;
 }
 
 extern "C" size_t rf_knn_workspace_bytes(long Q, long n_rows, int k, int method) {

@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const float* __restr
         if (c < total) {
             const long o = ((long)(c / cand) * Q + qi) * cand + (c % cand);
             id = cand_i[o];
-            if (perm && id >= 0) id = perm[id];  // scan position -> bank row
+            if (bstats->has_perm && id >= 0) id = perm[id];  // scan position -> bank row
             sc = cand_s[o];
             if ((c % cand) == cand - 1 && id >= 0) tau = fmaxf(tau, sc);  // a full list: its tail bounds the rejected rows
         }
@@ -630,7 +630,10 @@ int prepare_bank(const float* bank, long n_rows, const float* q_sample, long n_s
     const ImgLayout L = img_layout(n_rows, KBLK);
     BankStats* bstats = (BankStats*)image;
     const long bpad = (long)L.n_btiles * TILE;
-    const bool order = n_rows >= 16 * TILE;  // scan order (see knn_scan_key_kernel); pointless for tiny banks
+    // scan order (see knn_scan_key_kernel) only when the caller supplies a sample of the queries the image will serve:
+    // an order derived from OTHER queries can be worse than none (rows that look unpromising for the sample come last
+    // and then beat every list).  Pointless for tiny banks.
+    const bool order = q_sample != nullptr && n_rows >= 16 * TILE;
     const BankStats init = {0x7f7fffffu /*FLT_MAX*/, 0u, order ? 1 : 0};
     RF_CUDA_OK(cudaMemcpyAsync(bstats, &init, sizeof(BankStats), cudaMemcpyHostToDevice, s));
     const int* perm = nullptr;
@@ -641,11 +644,9 @@ int prepare_bank(const float* bank, long n_rows, const float* q_sample, long n_s
         int* idx_in = (int*)(scratch + L.idx_in);
         int* perm_w = (int*)(image + L.perm);
         RF_CUDA_OK(cudaMemsetAsync(mean, 0, 64 * sizeof(float), s));
-        // direction of a typical query: the mean of a query sample when the caller has one, else the bank's own mean
-        const float* src = q_sample ? q_sample : bank;
-        long ns = q_sample ? n_sample : n_rows;
+        long ns = n_sample;  // direction of a typical query: the mean of the sample
         if (ns > 65536) ns = 65536;
-        knn_mean_query_kernel<<<(unsigned)(ns / 4 < 592 ? (ns + 3) / 4 : 592), 256, 0, s>>>(src, ns, mean);
+        knn_mean_query_kernel<<<(unsigned)(ns / 4 < 592 ? (ns + 3) / 4 : 592), 256, 0, s>>>(q_sample, ns, mean);
         RF_LAUNCH_OK("knn_mean_query_kernel");
         knn_scan_key_kernel<<<(unsigned)rf_cdivl(bpad, 256), 256, 0, s>>>(bank, n_rows, bpad, mean, key_in, idx_in);
         RF_LAUNCH_OK("knn_scan_key_kernel");
@@ -710,7 +711,7 @@ int tc_run(const TcLayout& L, const float* bank, long n_rows, long row_offset, c
     Stats* stats = (Stats*)(ws + L.stats);
     const BankStats* bstats = (const BankStats*)image;
     const uint8_t* bank_img = (const uint8_t*)(image + IL.img);
-    const int* perm = n_rows >= 16 * TILE ? (const int*)(image + IL.perm) : nullptr;
+    const int* perm = (const int*)(image + IL.perm);  // used when the image header says the rows are in scan order
     uint8_t* q_img = (uint8_t*)(ws + L.q_img);
     float* cand_s = (float*)(ws + L.cand_s);
     int* cand_i = (int*)(ws + L.cand_i);

@@ -106,12 +106,14 @@ class PatchedAttentionBlock(nn.Module):
         In retrieval (Gumbel) mode the noise [B*R^3, K] may be injected; when it
         is not, it is drawn on the device as torch's gumbel_softmax does."""
         ab = self.attention_blocks_layer
-        ops._forward_only(x_predicted, x_retrieved, *ab.parameters())
         K = self.num_nearest_neighbors
         if x_retrieved.shape[0] != x_predicted.shape[0] * K:
             raise ValueError(f"x_retrieved has {x_retrieved.shape[0]} volumes, expected B*K = {x_predicted.shape[0] * K}")
         if x_predicted.shape[2] != self.num_patch_x * self.patch_extent:
             raise ValueError("feature volume edge must equal attn_num_patch * patch_extent")
+        if ops.grad_needed(x_predicted, x_retrieved, *ab.parameters()):  # training: differentiable composition
+            from ..autograd import patched_attention
+            return patched_attention(self, x_predicted, x_retrieved, gumbel_noise)
         mode = 1 if ab.retrieval_mode else 0
         if mode == 1 and gumbel_noise is None:
             rows = x_predicted.shape[0] * self.num_patch_x ** 3
@@ -131,6 +133,9 @@ class Fold3D(nn.Module):
         self.patch_extent = patch_extent
 
     def forward(self, x):
+        if ops.grad_needed(x):
+            from ..autograd import Fold3DFn
+            return Fold3DFn.apply(x.contiguous(), self.num_patch_x, self.patch_extent, self.nf)
         return ops.fold3d(x, self.num_patch_x, self.patch_extent, self.nf)
 
 
@@ -145,6 +150,9 @@ class Unfold3D(nn.Module):
     def forward(self, x):
         if x.shape[1] != self.nf:
             raise ValueError(f"Unfold3D was built for nf={self.nf}, input has {x.shape[1]} channels")
+        if ops.grad_needed(x):
+            from ..autograd import Unfold3DFn
+            return Unfold3DFn.apply(x.contiguous(), self.patch_extent)
         return ops.unfold3d(x, self.patch_extent)
 
 

@@ -11,9 +11,9 @@ class _Chain(nn.Module):
     def forward(self, x):
         from . import unet as U
         nets = list(self.network)
-        if U.USE_TENSOR_CORES and x.is_cuda and nets[0].tc_ok(x.shape[1]) and all(
+        training_path = ops.grad_needed(x, *self.parameters())  # autograd is recording: differentiable NCDHW path
+        if not training_path and U.USE_TENSOR_CORES and x.is_cuda and nets[0].tc_ok(x.shape[1]) and all(
                 n.basic_module.tc_ok(0, n.basic_module.SingleConv1.in_channels) for n in nets[1:]):
-            ops._forward_only(x, *self.parameters())
             h = nets[0].forward_cl(ops.cl_from_ncdhw(x))          # channels-last all the way through
             for i, n in enumerate(nets[1:]):
                 h = n.forward_cl(h, out_ncdhw=i == len(nets) - 2)
@@ -74,10 +74,13 @@ class Superresolution08FinalDecoder(RfModule):
         ])
 
     def forward(self, x):
-        ops._forward_only(x, *self.parameters())
         from . import unet as U
         head = self.network[1]
         nf = head.in_channels
+        if ops.grad_needed(x, *self.parameters()):  # training: DoubleConv + (1x1x1 conv, bias, tanh) as differentiable ops
+            from ..autograd import ConvGnAct
+            h = self.network[0](x)
+            return ConvGnAct.apply(h, None, head.weight, head.bias, None, None, 0, 0.0, 0, ops.ACT_TANH, 0.0)
         if U.USE_TENSOR_CORES and x.is_cuda and self.network[0].basic_module.tc_ok(0, nf):
             h = self.network[0].forward_cl(ops.cl_from_ncdhw(x))
             # the 1x1x1 head is memory-bound: one fp32 FMA pass over the channels-last volume, bias + tanh fused

@@ -70,6 +70,9 @@ class SingleConv(RfModule):
     def forward(self, x, x2=None):
         """x2: optional half-resolution tensor, virtually upsampled x2 and
         concatenated after x's channels (Decoder joining)."""
+        if ops.grad_needed(x, x2, *self.parameters()):
+            from ..autograd import single_conv
+            return single_conv(self, x, x2)
         gn = None
         if "g" in self.order:
             g = self.groupnorm
@@ -83,8 +86,11 @@ class SingleConv(RfModule):
 
 
     def tc_ok(self, c1, c2):
+        """Structure the channels-last tensor-core path handles: GroupNorm in front of a 3x3x3 'same' conv.  Whether
+        the shifted-window kernel, the gathering kernel or (for shapes neither takes) the fp32 kernel runs a layer is
+        decided per call in forward_cl, from the actual shape and (c1, c2) split."""
         return ("g" in self.order and self.order.index("g") < self.order.index("c") and self.kernel_size == 3
-                and self.padding == 1 and ops.tc_conv_supported(self.out_channels, c1, c2, 3))
+                and self.padding == 1)
 
     def forward_cl(self, x, x2=None, out_ncdhw=False):
         """Channels-last tensor-core path.  x: fp32 [N,D,H,W,C1] or None; x2: fp32 half-resolution
@@ -127,6 +133,11 @@ class SingleConv(RfModule):
                                            lambda w: ops.tc_conv_halo_weight_image(w, c1, c2))
             return ops.tc_conv3d_halo(split, img, self.conv.bias, self.out_channels, act=self.act, slope=0.1,
                                       out_ncdhw=out_ncdhw, out_scale=1.0 / (sa * sw))
+        if not ops.tc_conv_supported(self.out_channels, c1, c2, 3):
+            # neither tensor-core kernel takes this shape (e.g. Cout > 128 on extents the shifted-window kernel cannot
+            # tile): this one layer runs on the fp32 NCDHW kernel, the rest of the network stays channels-last
+            y = self.forward(ops.cl_to_ncdhw(x) if x is not None else None, ops.cl_to_ncdhw(x2) if x2 is not None else None)
+            return y if out_ncdhw else ops.cl_from_ncdhw(y)
         xs = ops.cl_norm_split(x, (mu, a, g.bias), 0, scale=sa) if x is not None else None
         x2s = ops.cl_norm_split(x2, (mu, a, g.bias), c1, scale=sa) if x2 is not None else None
         img, sw = self._wcache.derived(("tcconv", c1, c2), [self.conv.weight], lambda w: ops.tc_conv_weight_image(w, c1, c2))
@@ -188,7 +199,11 @@ class Encoder(nn.Module):
 
     def forward(self, x):
         if self.pooling is not None:
-            x = ops.maxpool3d_2(x)
+            if ops.grad_needed(x):
+                from ..autograd import MaxPool3d2
+                x = MaxPool3d2.apply(x)
+            else:
+                x = ops.maxpool3d_2(x)
         return self.basic_module(x)
 
     def forward_cl(self, x):
@@ -224,7 +239,7 @@ class DecoderNoJoining(Decoder):
     side effect is not reproduced (it does not influence any output)."""
 
     def forward(self, x):
-        if USE_TENSOR_CORES and x.is_cuda and self.basic_module.tc_ok(0, x.shape[1]):
+        if not ops.grad_needed(x, *self.parameters()) and USE_TENSOR_CORES and x.is_cuda and self.basic_module.tc_ok(0, x.shape[1]):
             return self.forward_cl(ops.cl_from_ncdhw(x), out_ncdhw=True)
         return self.basic_module(None, x)
 
@@ -274,11 +289,11 @@ class Abstract3DUNet(nn.Module):
     def tc_ok(self, in_channels):
         """Every SingleConv is a [g]c[r|l] 3x3x3 block the tensor-core kernel supports (Cout <= 128)."""
         convs = [m for m in self.modules() if isinstance(m, SingleConv)]
-        return all(m.tc_ok(m.in_channels, 0) for m in convs)
+        return all(m.tc_ok(m.in_channels, 0) for m in convs)  # structural only; (c1, c2) is resolved per call
 
     def forward(self, x):
-        ops._forward_only(x, *self.parameters())
-        if USE_TENSOR_CORES and x.is_cuda and self.tc_ok(x.shape[1]):
+        # autograd recording -> the differentiable NCDHW path (SingleConv / Encoder route through retrieval_fuse_b200.autograd)
+        if not ops.grad_needed(x, *self.parameters()) and USE_TENSOR_CORES and x.is_cuda and self.tc_ok(x.shape[1]):
             return self.forward_cl(ops.cl_from_ncdhw(x), out_ncdhw=True)
         feats = []
         for encoder in self.encoders:

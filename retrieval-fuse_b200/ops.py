@@ -110,11 +110,17 @@ def _dev(t: torch.Tensor, dtype=torch.float32, name="tensor") -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def grad_needed(*tensors) -> bool:
+    """True when autograd is recording and one of the tensors takes part in it: the modules then run their
+    differentiable path (retrieval_fuse_b200.autograd: fp32 NCDHW kernels + the adjoint kernels of rf_backward.cu)."""
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
 def _forward_only(*tensors):
-    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+    if grad_needed(*tensors):
         raise NotImplementedError(
-            "rf_b200 kernels are forward-only in this round: call under torch.no_grad() "
-            "(the reference's --sanity_steps -1 inference mode)")
+            "this rf_b200 op has no backward pass: call it under torch.no_grad().  Differentiable: the U-Nets, the patch "
+            "attention, the final decoder, Fold3D / Unfold3D (what training_step_full back-propagates through)")
 
 
 def _ptr(t):
@@ -906,3 +912,121 @@ def ntxent(zis, zjs, temperature, cosine=True, iou_matrix=None, sig_scale=80.0, 
                               ws.data_ptr(), ws.numel(), _stream(zis)), "rf_ntxent_fwd")
     _count(3 if cosine else 2)
     return loss[0]
+
+
+# ---------------------------------------------------------------------------
+# adjoint kernels (rf_backward.cu), used by retrieval_fuse_b200.autograd
+# ---------------------------------------------------------------------------
+
+def conv3d_wgrad(x, x2, gn, dz, ks, stride=1, pad=0):
+    """Filter gradient of conv3d(): x [N,C1,D,H,W] or None, x2 [N,C2,D/2,..] or None, gn = (mu, a, beta) or None,
+    dz [N,Cout,Do,Ho,Wo] -> dW [Cout, C1+C2, ks,ks,ks]."""
+    ref = x if x is not None else x2
+    dz = _dev(dz, name="dz")
+    C1 = C2 = 0
+    if x is not None:
+        x = _dev(x, name="x")
+        N, C1, D, H, W = x.shape
+    if x2 is not None:
+        x2 = _dev(x2, name="x2")
+        C2 = x2.shape[1]
+        if x is None:
+            N, D, H, W = x2.shape[0], 2 * x2.shape[2], 2 * x2.shape[3], 2 * x2.shape[4]
+    cin, cout = C1 + C2, dz.shape[1]
+    dw = torch.empty((cout, cin, ks, ks, ks), device=ref.device, dtype=torch.float32)
+    g = gn if gn is not None else (None, None, None)
+    with torch.cuda.device(ref.device), _timed("rf_conv3d_wgrad"):
+        check(_lib.lib().rf_conv3d_wgrad(_ptr(x), _ptr(x2), C2, _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), dz.data_ptr(), dw.data_ptr(), N, cin,
+                                         D, H, W, cout, ks, stride, pad, _stream(ref)), "rf_conv3d_wgrad")
+    _count(2)
+    return dw
+
+
+def act_bwd(dy, y, act, slope=0.0):
+    dy, y = _dev(dy, name="dy"), _dev(y, name="y")
+    if act == ACT_NONE:
+        return dy
+    dz = torch.empty_like(dy)
+    with torch.cuda.device(dy.device), _timed("rf_act_bwd"):
+        check(_lib.lib().rf_act_bwd(dy.data_ptr(), y.data_ptr(), dz.data_ptr(), dy.numel(), act, float(slope), _stream(dy)), "rf_act_bwd")
+    _count()
+    return dz
+
+
+def channel_sum(x):
+    """x [N, C, ...] -> [C] sums over everything but the channel axis."""
+    x = _dev(x, name="x")
+    N, C = x.shape[0], x.shape[1]
+    V = x.numel() // (N * C)
+    out = torch.empty(C, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _timed("rf_channel_sum"):
+        check(_lib.lib().rf_channel_sum(x.data_ptr(), N, C, V, out.data_ptr(), _stream(x)), "rf_channel_sum")
+    _count(2)
+    return out
+
+
+def gn_bwd(x, x2, g, mu, rstd, gamma, groups):
+    """GroupNorm backward on the virtual input concat(x, up2(x2)); g = grad of the normalised input [N,C,D,H,W].
+    -> (dx or None, dx2 or None, dgamma [C], dbeta [C])."""
+    g = _dev(g, name="g")
+    N, C, D, H, W = g.shape
+    C2 = x2.shape[1] if x2 is not None else 0
+    x = _dev(x, name="x") if x is not None else None
+    x2 = _dev(x2, name="x2") if x2 is not None else None
+    dx = torch.empty_like(x) if x is not None else None
+    dx2 = torch.empty_like(x2) if x2 is not None else None
+    dgamma = torch.empty(C, device=g.device, dtype=torch.float32)
+    dbeta = torch.empty(C, device=g.device, dtype=torch.float32)
+    L = _lib.lib()
+    ws = torch.empty(L.rf_gn_bwd_workspace_bytes(N, C), device=g.device, dtype=torch.uint8)
+    with torch.cuda.device(g.device), _timed("rf_gn_bwd"):
+        check(L.rf_gn_bwd(_ptr(x), _ptr(x2), C2, g.data_ptr(), mu.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), N, C, D, H, W, groups,
+                          _ptr(dx), _ptr(dx2), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), _stream(g)), "rf_gn_bwd")
+    _count(5)
+    return dx, dx2, dgamma, dbeta
+
+
+def upsample2_bwd(g, C1):
+    g = _dev(g, name="g")
+    N, C, D, H, W = g.shape
+    dx2 = torch.empty((N, C - C1, D // 2, H // 2, W // 2), device=g.device, dtype=torch.float32)
+    with torch.cuda.device(g.device), _timed("rf_upsample2_bwd"):
+        check(_lib.lib().rf_upsample2_bwd(g.data_ptr(), N, C, C1, D, H, W, dx2.data_ptr(), _stream(g)), "rf_upsample2_bwd")
+    _count()
+    return dx2
+
+
+def maxpool3d_2_bwd(x, dy):
+    x, dy = _dev(x, name="x"), _dev(dy, name="dy")
+    N, C, D, H, W = x.shape
+    dx = torch.empty_like(x)
+    with torch.cuda.device(x.device), _timed("rf_maxpool3d_2_bwd"):
+        check(_lib.lib().rf_maxpool3d_2_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), N, C, D, H, W, _stream(x)), "rf_maxpool3d_2_bwd")
+    _count()
+    return dx
+
+
+def attention_epilogue(xf, pf, xu, pu, noise, rp3, K, normalize, mode, blend, sharp):
+    """model/attention.py:84-113 on precomputed features: xf [R,32], pf [(b,k,r),32], xu [R,V], pu [(b,k,r),V] -> [R,V]."""
+    xf, pf, xu, pu = _dev(xf, name="xf"), _dev(pf, name="pf"), _dev(xu, name="xu"), _dev(pu, name="pu")
+    R, V = xu.shape
+    out = torch.empty_like(xu)
+    with torch.cuda.device(xu.device), _timed("rf_attention_epilogue_fwd"):
+        check(_lib.lib().rf_attention_epilogue_fwd(xf.data_ptr(), pf.data_ptr(), xu.data_ptr(), pu.data_ptr(), _ptr(noise), out.data_ptr(), R,
+                                                   rp3, K, V, int(bool(normalize)), int(mode), int(bool(blend)), float(sharp), _stream(xu)),
+              "rf_attention_epilogue_fwd")
+    _count()
+    return out
+
+
+def attention_epilogue_bwd(xf, pf, xu, pu, noise, dout, rp3, K, normalize, mode, blend, sharp):
+    dout = _dev(dout, name="dout")
+    R, V = xu.shape
+    dxf, dpf, dxu, dpu = torch.empty_like(xf), torch.empty_like(pf), torch.empty_like(xu), torch.empty_like(pu)
+    with torch.cuda.device(xu.device), _timed("rf_attention_epilogue_bwd"):
+        check(_lib.lib().rf_attention_epilogue_bwd(xf.data_ptr(), pf.data_ptr(), xu.data_ptr(), pu.data_ptr(), _ptr(noise), dout.data_ptr(),
+                                                   dxf.data_ptr(), dpf.data_ptr(), dxu.data_ptr(), dpu.data_ptr(), R, rp3, K, V,
+                                                   int(bool(normalize)), int(mode), int(bool(blend)), float(sharp), _stream(xu)),
+              "rf_attention_epilogue_bwd")
+    _count()
+    return dxf, dpf, dxu, dpu

@@ -244,6 +244,20 @@ class RefinementPipeline(RetrievalPipeline):
         out = ops.unfold3d_pad_stride(chunks, s, 0, s, 0.0, norm_sub=d["input_mean"], norm_div=d["input_std"])
         return out.reshape(chunks.shape)
 
+    def refine_train(self, x_in, retrieval, gumbel_noise=None):
+        """refine() with autograd recording (trainer/train_refinement.py:108-120 inside training_step_full): the same
+        modules, routed through their differentiable path; returns (pred, x_back, x_retr, x_attn) attached to the graph."""
+        from .model.attention import Fold3D, Unfold3D
+        nf = self.retrieval_backbone.nf
+        B, S = retrieval.shape[0], retrieval.shape[2]
+        with torch.enable_grad():
+            x_back = self.unet_backbone(x_in)
+            retr = retrieval[:, :self.K].reshape(B * self.K, 1, S, S, S)
+            patches = Unfold3D(16, 1)(retr)
+            x_retr = Fold3D(4, 8, nf)(self.retrieval_backbone(patches))
+            x = self.patched_attention_block(x_back, x_retr, gumbel_noise)
+            return self.decoder(x), x_back, x_retr, x
+
     def refine(self, x_in, retrieval, gumbel_noise=None):
         """x_in [B,1,s,s,s] normalised, retrieval [B,K',64,64,64] normalised -> pred [B,1,64,64,64] in [-1,1]."""
         nf = self.retrieval_backbone.nf

@@ -102,18 +102,22 @@ class EmbeddingBank:
         lookup = {s: i for i, s in reversed(list(enumerate(self.scenes)))}  # list.index == first occurrence
         return torch.tensor([lookup.get(s, -1) for s in scene_names], dtype=torch.int32)
 
+    _BULK_QUERIES = 32768  # from here on a lookup re-stages the bank in the scan order of ITS queries (~0.15 ms)
+
     def topk(self, q, k, method=0):
         """Exact top-k of this shard: (global ids int32 [Q,k], fp64 d [Q,k]).  The tensor-core operand image of the
-        bank is built at the first lookup (its scan order uses that batch's mean query direction; the result does not
-        depend on it) and reused afterwards - the bank is static, like the reference's loaded FLANN index."""
-        if method in (0, 2, 3):
+        (static) bank is built once, in bank order, and reused by every lookup - the reference likewise loads its
+        FLANN index once per worker (util/retrieval.py:81-83).  Bulk lookups re-stage the bank per call in the scan
+        order of their own queries, which pays off from a few ten thousand queries on."""
+        if method in (0, 2, 3) and q.shape[0] < self._BULK_QUERIES:
             key = (method, self.emb.data_ptr(), self.emb.shape[0])
             if getattr(self, "_image_key", None) != key:
-                self._image = ops.knn_prepare_bank(self.emb, method, q_sample=q)
+                self._image = ops.knn_prepare_bank(self.emb, method)
                 self._image_key = key
             if self._image is not None:
                 return ops.knn_topk(self.emb, q, k, row_offset=self.row_offset, image=self._image)
-        return ops.knn_topk(self.emb, q, k, row_offset=self.row_offset, method=1 if method == 0 else method)
+            return ops.knn_topk(self.emb, q, k, row_offset=self.row_offset, method=1 if method == 0 else method)
+        return ops.knn_topk(self.emb, q, k, row_offset=self.row_offset, method=method)
 
     def query(self, q, K, query_scene=None, method=0):
         """q [Q,64] unit rows on the GPU -> (rows fp32 [Q,K,8], ids int32 [Q,K]):

@@ -510,7 +510,7 @@ def test_knn_prepared_bank_and_graph_capture(dev):
     assert ops.last_knn_stats["n_unproven"] >= 40
     i0, d0 = ops.knn_topk(bank.emb, qd, 2 * K, method=1)
     assert torch.equal(i0, i1) and torch.equal(d0, d1)
-    img_b = ops.knn_prepare_bank(bank.emb, 0)  # scan order from the bank's own mean: same result
+    img_b = ops.knn_prepare_bank(bank.emb, 0)  # rows in bank order (no query sample): same result
     i2, d2 = ops.knn_topk(bank.emb, qd, 2 * K, image=img_b)
     assert torch.equal(i0, i2) and torch.equal(d0, d2)
     rows, idx = bank.query(qd, K, qsd)         # builds + caches the image
@@ -535,26 +535,32 @@ def test_knn_prepared_bank_and_graph_capture(dev):
 
 
 def test_knn_one_million_rows(dev):
-    """BASELINE config 5: a 1 M-row isotropic bank (method 3 above 400 k rows by dispatch), fetch 2k for k in {1, 4, 8,
-    16}: every query equals the exact fp64 sweep, a sample equals the oracle, and hardly any query needs the re-check."""
+    """BASELINE config 5: a 1 M-row isotropic bank, fetch 2k for k in {1, 4, 8, 16}, through the fp16 single pass (auto)
+    and the bf16 hi/lo split: every query equals the exact fp64 sweep, a sample equals the oracle, and hardly any
+    query needs the re-check."""
     from retrieval_fuse_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(1)
     bank = torch.nn.functional.normalize(torch.randn(1_000_000, 64, generator=g), dim=1).contiguous()
     g2 = torch.Generator(device="cpu").manual_seed(2)
     q = torch.nn.functional.normalize(torch.randn(8192, 64, generator=g2), dim=1).contiguous()
     bank_d, q_d = bank.to(dev), q.to(dev)
-    img = ops.knn_prepare_bank(bank_d, 0, q_sample=q_d)
-    assert img is not None and img.method == 3
+    img = ops.knn_prepare_bank(bank_d, 0)              # auto = the fp16 single pass, rows in bank order
+    assert img is not None and img.method == 2
+    img3 = ops.knn_prepare_bank(bank_d, 3, q_sample=q_d)  # bf16 hi/lo split, scan order of these queries
+    assert img3.method == 3
     for k in (1, 4, 8, 16):
         i, d = ops.knn_topk(bank_d, q_d, 2 * k, image=img, stats=True)
         assert 0 <= ops.last_knn_stats["n_unproven"] < 0.01 * q.shape[0], (k, ops.last_knn_stats)
         ei, ed = ops.knn_topk(bank_d, q_d[:2048].contiguous(), 2 * k, method=1)
         assert torch.equal(i[:2048], ei) and torch.equal(d[:2048], ed), k
+        i3, d3 = ops.knn_topk(bank_d, q_d, 2 * k, image=img3, stats=True)
+        assert 0 <= ops.last_knn_stats["n_unproven"] < 0.01 * q.shape[0], (k, ops.last_knn_stats)
+        assert torch.equal(i, i3) and torch.equal(d, d3), k
     want_i, want_d = O.knn_exact(bank.numpy(), q.numpy()[:64], 32)
     assert np.array_equal(i[:64].cpu().numpy(), want_i) and np.array_equal(d[:64].cpu().numpy().astype(np.float32), want_d)
-    i2, d2 = ops.knn_topk(bank_d, q_d, 8, method=2)   # the fp16 single pass is exact here as well
-    i3, d3 = ops.knn_topk(bank_d, q_d, 8, image=img)
-    assert torch.equal(i2, i3) and torch.equal(d2, d3)
+    i2, d2 = ops.knn_topk(bank_d, q_d, 8, method=0)   # unprepared call: image staged per call in the queries' scan order
+    i4, d4 = ops.knn_topk(bank_d, q_d, 8, image=img)
+    assert torch.equal(i2, i4) and torch.equal(d2, d4)
 
 
 def test_knn_full_size_properties(dev):
@@ -860,7 +866,8 @@ def test_config3_bank_in_four_shards_full_path(dev):
     assert np.array_equal(idx4.cpu().numpy(), idx_ref) and np.array_equal(rows4.cpu().numpy(), rows_ref)
     pred = pipe.infer(chunks, world["query_scene"], refine_batch=4, graphed=True)
     pred_e = pipe.infer(chunks, world["query_scene"], refine_batch=6, graphed=False)
-    assert float((pred - pred_e).abs().max()) <= 1e-6
+    # other sub-batch sizes pick other item shapes in the conv kernels (another accumulation order): fp32-level agreement
+    assert float((pred - pred_e).abs().max()) <= 1e-4
     sds = pipe.state_dicts()
     retr_ref = O.compose_chunks(CFG, rows_ref, store.cpu().numpy(), chunks.shape[0])
     pred_ref = O.refine_chunks(CFG, {k: v for k, v in sds.items() if k != "fenc_input"}, chunks.cpu().numpy(), retr_ref)[0].numpy()
