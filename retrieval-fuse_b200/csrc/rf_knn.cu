@@ -141,12 +141,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) knn_exact_f64_kernel(const
 // One warp per query: fold S sorted k-lists into one under (d, id).
 __global__ void __launch_bounds__(128) knn_merge_kernel(const int* __restrict__ parts_idx,
                                                         const double* __restrict__ parts_d, int S, long Q,
-                                                        const int* __restrict__ q_count, long q_cap, int k,
+                                                        const int* __restrict__ q_count, long q_first, long q_cap, int k,
                                                         const int* __restrict__ q_sel, int* __restrict__ out_idx,
                                                         double* __restrict__ out_d) {
     const int lane = threadIdx.x & 31;
     long n = Q, stride = Q;
-    if (q_count) { n = (long)*q_count < q_cap ? (long)*q_count : q_cap; stride = q_cap; }  // device-sized re-check window
+    if (q_count) {  // device-sized re-check window [q_first, q_first + q_cap) of the q_sel list; parts are window-relative
+        n = (long)*q_count - q_first;
+        if (n > q_cap) n = q_cap;
+        stride = q_cap;
+        q_sel += q_first;
+    }
     for (long qi = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5; qi < n; qi += ((long)gridDim.x * blockDim.x) >> 5) {
         double ld = DBL_MAX, tau_d = DBL_MAX;
         int li = INT_MAX, tau_i = INT_MAX;
@@ -230,30 +235,31 @@ int rf_knn_exact_launch(const float* bank, long n_rows, long row_offset, const f
     int* pi = (int*)(pd + (size_t)nsplit * Q * k);
     knn_exact_f64_kernel<<<grid, WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, nullptr, 0, 0, k, nsplit, q_sel, pi, pd);
     RF_LAUNCH_OK("knn_exact_f64_kernel");
-    knn_merge_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, s>>>(pi, pd, nsplit, Q, nullptr, 0, k, q_sel, out_idx, out_d);
+    knn_merge_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, s>>>(pi, pd, nsplit, Q, nullptr, 0, 0, k, q_sel, out_idx, out_d);
     RF_LAUNCH_OK("knn_merge_kernel");
     return 0;
 }
 
 // The exact sweep for a DEVICE-sized list of queries (q_sel[0 .. *q_count)): the re-check of the tensor-core path's
-// unproven queries, enqueued unconditionally so that no host synchronisation is needed.  The first RF_RECHECK_CAP
-// queries are swept in RF_RECHECK_SLICES bank slices (+ merge) so that a handful of queries still spreads over the
-// chip; anything beyond the cap (a pathological bank) goes through single-slice CTAs.  All three launches return
-// immediately when *q_count is 0.
+// unproven queries, enqueued unconditionally so that no host synchronisation is needed.  The list is covered by
+// windows: the first RF_RECHECK_CAP queries in RF_RECHECK_SLICES bank slices (+ merge), so that a handful of queries
+// still spreads over the chip, then windows of RF_RECHECK_WINDOW queries in 8 slices.  Every launch leaves at once
+// when its window starts beyond *q_count (the common case: nothing, or a few queries, to re-check).
 static const long RF_RECHECK_CAP = 2048;
 static const int RF_RECHECK_SLICES = 64;
+static const long RF_RECHECK_WINDOW = 65536;
+static const int RF_RECHECK_WINDOW_SLICES = 8;
 size_t rf_knn_recheck_workspace_bytes(int k) {
-    return (size_t)RF_RECHECK_SLICES * RF_RECHECK_CAP * k * (sizeof(int) + sizeof(double)) + 256;
+    const size_t rows = (size_t)RF_RECHECK_SLICES * RF_RECHECK_CAP > (size_t)RF_RECHECK_WINDOW_SLICES * RF_RECHECK_WINDOW
+                            ? (size_t)RF_RECHECK_SLICES * RF_RECHECK_CAP : (size_t)RF_RECHECK_WINDOW_SLICES * RF_RECHECK_WINDOW;
+    return rows * k * (sizeof(int) + sizeof(double)) + 256;
 }
 int rf_knn_recheck_launch(const float* bank, long n_rows, long row_offset, const float* q, long Q, int k, const int* q_sel,
                           const int* q_count, int* out_idx, double* out_d, void* workspace, size_t workspace_bytes,
                           cudaStream_t s) {
     RF_CHECK_ARG(workspace && workspace_bytes >= rf_knn_recheck_workspace_bytes(k) - 256, "rf_knn_l2_topk: re-check workspace too small");
-    const long cap = RF_RECHECK_CAP < Q ? RF_RECHECK_CAP : Q;
-    int ns = RF_RECHECK_SLICES;
     const long max_split = (n_rows + 1023) / 1024;
-    if (ns > max_split) ns = (int)max_split;
-    if (ns == 1) {  // a bank of at most 1024 rows: one slice, the sweep writes the final rows itself
+    if (max_split <= 1) {  // a bank of at most 1024 rows: one slice, the sweep writes the final rows itself
         long gx = (Q + QB - 1) / QB;
         if (gx > 148 * 8) gx = 148 * 8;
         knn_exact_f64_kernel<<<dim3((unsigned)gx, 1), WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, q_count, 0, Q, k, 1, q_sel,
@@ -261,19 +267,20 @@ int rf_knn_recheck_launch(const float* bank, long n_rows, long row_offset, const
         RF_LAUNCH_OK("knn_exact_f64_kernel(re-check)");
         return 0;
     }
-    double* pd = (double*)workspace;
-    int* pi = (int*)(pd + (size_t)ns * cap * k);
-    dim3 grid((unsigned)((cap + QB - 1) / QB), ns);
-    knn_exact_f64_kernel<<<grid, WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, q_count, 0, cap, k, ns, q_sel, pi, pd);
-    RF_LAUNCH_OK("knn_exact_f64_kernel(re-check)");
-    knn_merge_kernel<<<(unsigned)rf_cdivl(cap * 32, 128), 128, 0, s>>>(pi, pd, ns, Q, q_count, cap, k, q_sel, out_idx, out_d);
-    RF_LAUNCH_OK("knn_merge_kernel(re-check)");
-    if (Q > cap) {
-        long gx = (Q - cap + QB - 1) / QB;
-        if (gx > 148 * 8) gx = 148 * 8;
-        knn_exact_f64_kernel<<<dim3((unsigned)gx, 1), WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, q_count, cap, Q, k, 1,
-                                                                                 q_sel, out_idx, out_d);
-        RF_LAUNCH_OK("knn_exact_f64_kernel(re-check overflow)");
+    for (long first = 0; first < Q;) {
+        const bool head = first == 0;
+        long cap = head ? RF_RECHECK_CAP : RF_RECHECK_WINDOW;
+        if (cap > Q - first) cap = Q - first;
+        int ns = head ? RF_RECHECK_SLICES : RF_RECHECK_WINDOW_SLICES;
+        if (ns > max_split) ns = (int)max_split;
+        double* pd = (double*)workspace;
+        int* pi = (int*)(pd + (size_t)ns * cap * k);
+        dim3 grid((unsigned)((cap + QB - 1) / QB), ns);
+        knn_exact_f64_kernel<<<grid, WARPS_PER_CTA * 32, 0, s>>>(bank, n_rows, row_offset, q, Q, q_count, first, cap, k, ns, q_sel, pi, pd);
+        RF_LAUNCH_OK("knn_exact_f64_kernel(re-check)");
+        knn_merge_kernel<<<(unsigned)rf_cdivl(cap * 32, 128), 128, 0, s>>>(pi, pd, ns, Q, q_count, first, cap, k, q_sel, out_idx, out_d);
+        RF_LAUNCH_OK("knn_merge_kernel(re-check)");
+        first += cap;
     }
     return 0;
 }
@@ -282,7 +289,7 @@ extern "C" int rf_knn_merge(const int* parts_idx, const double* parts_d, int S, 
                             double* out_d, void* stream) {
     RF_CHECK_ARG(parts_idx && parts_d && out_idx && out_d, "rf_knn_merge: null pointer");
     RF_CHECK_ARG(S > 0 && Q > 0 && k > 0 && k <= 32, "rf_knn_merge: bad sizes S=%d Q=%ld k=%d", S, Q, k);
-    knn_merge_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, (cudaStream_t)stream>>>(parts_idx, parts_d, S, Q, nullptr, 0, k, nullptr, out_idx, out_d);
+    knn_merge_kernel<<<(unsigned)rf_cdivl(Q * 32, 128), 128, 0, (cudaStream_t)stream>>>(parts_idx, parts_d, S, Q, nullptr, 0, 0, k, nullptr, out_idx, out_d);
     RF_LAUNCH_OK("knn_merge_kernel");
     return 0;
 }

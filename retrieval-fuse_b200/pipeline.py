@@ -291,20 +291,30 @@ class RefinementPipeline(RetrievalPipeline):
             # a persistent buffer the captured kernels point at (operand planes, weight images) was freed since the
             # capture: every graph is stale
             self._graphs.clear()
+            self._graphs_gen = ops.persistent_generation()
         key = (tuple(x_in.shape), tuple(retrieval.shape))
         if key not in self._graphs:
             sx, sr = x_in.clone(), retrieval.clone()
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):  # warm-up: weight images, function attributes, allocator
+            with torch.cuda.stream(side):  # warm-up: weight images, function attributes, allocator, operand planes
                 for _ in range(2):
                     self.refine(sx, sr)
             torch.cuda.current_stream(self.device).wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = self.refine(sx, sr)[0]
-            self._graphs[key] = (graph, sx, sr, out)
-            self._graphs_gen = ops.persistent_generation()
+            for _ in range(3):
+                if self._graphs_gen != ops.persistent_generation():
+                    # the warm-up of this shape (or a capture attempt) freed buffers of other shapes: their graphs are stale
+                    self._graphs.clear()
+                    self._graphs_gen = ops.persistent_generation()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self.refine(sx, sr)[0]
+                if self._graphs_gen == ops.persistent_generation():  # nothing was freed while capturing
+                    self._graphs[key] = (graph, sx, sr, out)
+                    break
+                del graph
+            else:
+                raise RuntimeError("refine_graphed: persistent buffers kept changing during CUDA graph capture")
         graph, sx, sr, out = self._graphs[key]
         sx.copy_(x_in, non_blocking=True)
         sr.copy_(retrieval, non_blocking=True)

@@ -6,17 +6,35 @@ from .. import ops
 
 
 class _Metric:
+    """The slice of torchmetrics.Metric the reference's callers use: `IoU(compute_on_step=False).cuda()` then
+    `metric(preds, target)` per batch and `metric.compute()` (util/retrieval.py:168-175, trainer/*.py)."""
+
+    def __init__(self, *args, **kwargs):  # torchmetrics options (compute_on_step, dist_sync_on_step, ...) are accepted
+        self._reset_state()
+
+    def _reset_state(self):
+        raise NotImplementedError
+
     def __call__(self, preds, target):
         self.update(preds, target)
 
     def reset(self):
-        self.__init__()
+        self._reset_state()
+
+    def cuda(self, *args, **kwargs):  # the state lives on the host; the kernels run where the inputs are
+        return self
+
+    def to(self, *args, **kwargs):
+        return self
+
+    def cpu(self):
+        return self
 
 
 class IoU(_Metric):
     """util/metrics.py:6-25."""
 
-    def __init__(self):
+    def _reset_state(self):
         self.iou_sum = 0.0
         self.total = 0.0
 
@@ -36,7 +54,7 @@ class IoU(_Metric):
 class Precision(_Metric):
     """util/metrics.py:56-70."""
 
-    def __init__(self):
+    def _reset_state(self):
         self.precision_sum = 0.0
         self.total = 0.0
 
@@ -52,7 +70,7 @@ class Precision(_Metric):
 class Recall(_Metric):
     """util/metrics.py:73-87."""
 
-    def __init__(self):
+    def _reset_state(self):
         self.recall_sum = 0.0
         self.total = 0.0
 
@@ -77,7 +95,7 @@ class Chamfer3D(_Metric):
     """util/metrics.py:28-53.  An empty cloud yields a NaN mean in the reference, which it skips (:48); here the
     pair is skipped before the search."""
 
-    def __init__(self):
+    def _reset_state(self):
         self.cd_sum = 0.0
         self.total = 0.0
 

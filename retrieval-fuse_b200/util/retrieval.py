@@ -304,6 +304,23 @@ def create_retrieval_from_mapping(scene_name, retrieval_mappings, K, dataset_tra
     return out[0].cpu()
 
 
+def get_metrics_for_retrieval(retrievals, dataset):
+    """util/retrieval.py:167-175: [IoU, Chamfer, Precision, Recall] of the first retrieved volume of every scene against
+    its target, both thresholded at 0.75 voxels.  retrievals[i]: [K, X, Y, Z] array or tensor of scene i."""
+    from .metrics import Chamfer3D, IoU, Precision, Recall
+    dev = torch.device("cuda", torch.cuda.current_device())
+    metrics = [IoU(compute_on_step=False).cuda(), Chamfer3D(compute_on_step=False).cuda(), Precision(compute_on_step=False).cuda(),
+               Recall(compute_on_step=False).cuda()]
+    thr = 0.75 * dataset.target_voxel_size
+    for idx, scene in enumerate(dataset.scenes):
+        r = torch.as_tensor(np.asarray(retrievals[idx]))[0]
+        nn1 = (r <= thr)[None, None].to(dev)
+        target = (torch.as_tensor(dataset.get_scene_target(scene)) <= thr)[None, None].to(dev)
+        for metric in metrics:
+            metric(nn1, target)
+    return [float(m.compute()) for m in metrics]
+
+
 class RetrievalInterface:
     """util/retrieval.py:178-207."""
 
@@ -369,6 +386,11 @@ def retrievals_to_disk(mode, config, use_target_for_feats, fenc_input=None, fenc
             for scene in [x for i, x in enumerate(dataset.scenes) if i % num_proc == proc]:
                 vol = RetrievalInterface.retrieve_nearest_scenes(mapping, scene, config["K"], tree_path, dataset_train, dataset)
                 np.savez_compressed(retrievals_dir / "compose" / f"{scene}.npz", vol.numpy())
+    elif mode == "evaluate":  # util/retrieval.py:250-255: metrics of the first retrieval of every val scene
+        retrievals = [np.load(retrievals_dir / "compose" / f"{scene}.npz")["arr_0"][:1] for scene in dataset_val.scenes]
+        metrics = get_metrics_for_retrieval(retrievals, dataset_val)
+        print(metrics)
+        return metrics
     else:
-        raise NotImplementedError(f"mode '{mode}' (metrics evaluation) is out of scope of the hot path")
+        raise ValueError(f"unknown mode '{mode}' (map | compose | evaluate)")
     return tree_path, retrievals_dir

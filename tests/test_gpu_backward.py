@@ -26,6 +26,13 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(autouse=True)
+def _grad_on():
+    """Other test modules switch autograd off globally at import time (inference tests); these tests need it on."""
+    with torch.enable_grad():
+        yield
+
+
 def synth_for(module):
     return O.synth_state_dict({k: tuple(v.shape) for k, v in module.state_dict().items()}, BC.SEED)
 

@@ -837,6 +837,26 @@ def test_hot_path_end_to_end_small(dev):
     G.smoke()
 
 
+def test_evaluation_metrics_match_reference_golden(dev):
+    """The drop-in metric classes (constructed the way the reference's callers do: IoU(compute_on_step=False).cuda())
+    against values the reference's own util/metrics.py classes produced (tests/golden/adjuncts.npz)."""
+    from retrieval_fuse_b200.util import metrics as M
+    g = np.load(os.path.join(GOLD, "adjuncts.npz"))
+    p, t = torch.from_numpy(g["metrics.pred"]).to(dev), torch.from_numpy(g["metrics.target"]).to(dev)
+    vals = []
+    for cls in (M.IoU, M.Chamfer3D, M.Precision, M.Recall):
+        m = cls(compute_on_step=False).cuda()
+        m(p[:3], t[:3])
+        m(p[3:], t[3:])
+        vals.append(float(m.compute()))
+    np.testing.assert_allclose(vals, g["metrics.values"], rtol=1e-5, atol=1e-7)
+    a = torch.nonzero(t[0, 0], as_tuple=False).float()
+    b = torch.nonzero(p[0, 0], as_tuple=False).float()
+    d1, d2, i1, i2 = M.chamfer_3d_dist(a, b)
+    assert np.array_equal(d1.cpu().numpy(), g["chamfer.d1"]) and np.array_equal(i1.cpu().numpy(), g["chamfer.i1"])
+    assert np.array_equal(d2.cpu().numpy(), g["chamfer.d2"]) and np.array_equal(i2.cpu().numpy(), g["chamfer.i2"])
+
+
 def test_config3_bank_in_four_shards_full_path(dev):
     """BASELINE configs[2]: 3DFront SR 008 -> 064, the bank in 4 row shards, full refine forward.  On one GPU the four
     shards are queried one after the other (the N > 1 exchange itself is tests/test_sharded_gloo.py, world 4): per-shard

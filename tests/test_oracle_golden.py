@@ -241,3 +241,20 @@ def test_oracle_knn_and_demotion_properties():
                 same = [j for j in idx[i] if row_scene[j] == qs[i]]
                 assert di[i].tolist() == (other + same)[:K]
     prop()
+
+
+def test_evaluation_metrics_match_reference_classes():
+    """IoU / Chamfer3D / Precision / Recall as the reference's own util/metrics.py classes compute them
+    (tests/golden/make_golden_adjuncts.py ran them with a stubbed torchmetrics base and the submodule's pure-torch
+    distChamfer), and the nearest-neighbour search on voxel coordinates bit-exact."""
+    g = np.load(os.path.join(GOLD, "adjuncts.npz"))
+    p, t = g["metrics.pred"], g["metrics.target"]
+    iou_sum, iou_n, prec, rec, _ = O.occupancy_metrics(p, t)
+    cd, valid = O.chamfer_metric(p, t)
+    mine = np.array([iou_sum / iou_n, cd / valid, prec / p.shape[0], rec / p.shape[0]])
+    np.testing.assert_allclose(mine, g["metrics.values"], rtol=1e-5, atol=1e-7)
+    a, b = np.argwhere(t[0, 0]).astype(np.float32), np.argwhere(p[0, 0]).astype(np.float32)
+    d1, i1 = O.chamfer_nn(a, b)
+    d2, i2 = O.chamfer_nn(b, a)
+    assert np.array_equal(d1, g["chamfer.d1"]) and np.array_equal(d2, g["chamfer.d2"])
+    assert np.array_equal(i1, g["chamfer.i1"]) and np.array_equal(i2, g["chamfer.i2"])
