@@ -133,6 +133,8 @@ class ClockSampler:
         self.nvml.start()
 
     def start(self):
+        if os.environ.get("RF_BENCH_NO_CLOCKS"):  # debugging aid: no sampler thread at all
+            return
         try:
             self._nvml_start()
             return
@@ -154,6 +156,8 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is None and self.proc is None:
+            return None
         if self.nvml is not None:
             self.stop_flag = True
             self.nvml.join(timeout=1)

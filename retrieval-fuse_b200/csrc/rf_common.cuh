@@ -88,6 +88,30 @@ __device__ __forceinline__ float rf_div_rn_fixed(float a, float b, float y) {
     return __fdiv_rn(a, b);
 }
 
+// Exact division of a 32-bit index by a run-time divisor with one 64-bit high multiply: m = ceil(2^64 / d) gives
+// floor(n / d) for every n < 2^32 (error term n * (m * d - 2^64) / (d * 2^64) < 1 / d).  The re-indexing kernels
+// decompose one linear index per 16-byte access, so the ~20-instruction hardware-less integer division matters.
+struct FastDiv {
+    unsigned long long m;
+    unsigned d;
+};
+static inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = (unsigned)d;
+    f.m = d <= 1 ? 0ull : (~0ull) / (unsigned long long)d + 1ull;
+    return f;
+}
+__device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
+    return f.d == 1u ? n : (unsigned)__umul64hi((unsigned long long)n, f.m);
+}
+// n -> n / d, returns n % d
+__device__ __forceinline__ unsigned fd_divmod(unsigned& n, const FastDiv& f) {
+    const unsigned q = fd_div(n, f);
+    const unsigned r = n - q * f.d;
+    n = q;
+    return r;
+}
+
 __device__ __forceinline__ float rf_act(float v, int act, float slope) {
     if (act == RF_ACT_RELU) return v > 0.f ? v : 0.f;
     if (act == RF_ACT_LEAKY) return v > 0.f ? v : v * slope;

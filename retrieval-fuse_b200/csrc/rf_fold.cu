@@ -8,30 +8,6 @@
 // count (rf_grid_1d).  DESIGN.md 4.4 has the measurements behind these choices.
 #include "rf_common.cuh"
 
-// Exact division of a 32-bit index by a run-time divisor with one 64-bit high multiply: m = ceil(2^64 / d) gives
-// floor(n / d) for every n < 2^32 (error term n * (m * d - 2^64) / (d * 2^64) < 1 / d).  The re-indexing kernels
-// decompose one linear index per 16-byte access, so the ~20-instruction hardware-less integer division matters.
-struct FastDiv {
-    unsigned long long m;
-    unsigned d;
-};
-static inline FastDiv make_fastdiv(int d) {
-    FastDiv f;
-    f.d = (unsigned)d;
-    f.m = d <= 1 ? 0ull : (~0ull) / (unsigned long long)d + 1ull;
-    return f;
-}
-__device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
-    return f.d == 1u ? n : (unsigned)__umul64hi((unsigned long long)n, f.m);
-}
-// n -> n / d, returns n % d
-__device__ __forceinline__ unsigned fd_divmod(unsigned& n, const FastDiv& f) {
-    const unsigned q = fd_div(n, f);
-    const unsigned r = n - q * f.d;
-    n = q;
-    return r;
-}
-
 // ---------------------------------------------------------------------------
 // Unfold3D / Fold3D (model/attention.py:160-188).  One index space for both:
 // element (b, px,py,pz, c, ex,ey,ez) of the patch tensor <-> element

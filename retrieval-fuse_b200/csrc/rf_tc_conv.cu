@@ -130,10 +130,23 @@ __global__ void __launch_bounds__(256) cl_gn_partial_kernel(const float* __restr
         if ((int)threadIdx.x < T) {
             const int c = threadIdx.x % C;
             double s1 = 0.0, s2 = 0.0;
-            for (long e = threadIdx.x; e < total; e += T) {
+            long e = threadIdx.x;
+            // four independent loads in flight per thread (one load per trip left the kernel waiting on DRAM latency:
+            // 1.5 TB/s), two accumulator pairs to shorten the fp64 dependency chains
+            double t1 = 0.0, t2 = 0.0;
+            for (; e + 3L * T < total; e += 4L * T) {
+                const float f0 = __ldg(base + e), f1 = __ldg(base + e + T), f2 = __ldg(base + e + 2L * T), f3 = __ldg(base + e + 3L * T);
+                const double v0 = (double)f0, v1 = (double)f1, v2 = (double)f2, v3 = (double)f3;
+                s1 += v0; s2 += v0 * v0;
+                t1 += v1; t2 += v1 * v1;
+                s1 += v2; s2 += v2 * v2;
+                t1 += v3; t2 += v3 * v3;
+            }
+            for (; e < total; e += T) {
                 const double v = (double)__ldg(base + e);
                 s1 += v; s2 += v * v;
             }
+            s1 += t1; s2 += t2;
             if (C <= 32 && (32 % C) == 0) {
                 // lanes l, l + C, l + 2C, ... of a warp hold the same channel (T is a multiple of 32 here): fold them
                 // with shuffles so that only C lanes per warp touch the shared accumulators (a 1-channel tensor made
@@ -245,15 +258,15 @@ __global__ void __launch_bounds__(256) cl_norm_split_c1_kernel(const float* __re
 }
 
 __global__ void __launch_bounds__(256) cl_maxpool2_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int D,
-                                                          int H, int W, int C) {
+                                                          int H, int W, int C, FastDiv fC, FastDiv fW, FastDiv fH, FastDiv fD) {
     const int Do = D / 2, Ho = H / 2, Wo = W / 2;
-    const long total = (long)N * Do * Ho * Wo * C;
+    const long total = (long)N * Do * Ho * Wo * C;  // < 2^32 (checked on the host): multiply-high index decomposition
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        long t = i;
-        const int c = (int)(t % C); t /= C;
-        const int w = (int)(t % Wo); t /= Wo;
-        const int h = (int)(t % Ho); t /= Ho;
-        const int d = (int)(t % Do); t /= Do;
+        unsigned t = (unsigned)i;
+        const int c = (int)fd_divmod(t, fC);
+        const int w = (int)fd_divmod(t, fW);
+        const int h = (int)fd_divmod(t, fH);
+        const int d = (int)fd_divmod(t, fD);
         float m = -3.402823466e38f;
 #pragma unroll
         for (int dz = 0; dz < 2; ++dz)
@@ -261,7 +274,7 @@ __global__ void __launch_bounds__(256) cl_maxpool2_kernel(const float* __restric
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx)
-                    m = fmaxf(m, __ldg(x + ((((t * D + 2 * d + dz) * H + 2 * h + dy) * (long)W + 2 * w + dx) * C + c)));
+                    m = fmaxf(m, __ldg(x + (((((long)t * D + 2 * d + dz) * H + 2 * h + dy) * (long)W + 2 * w + dx) * C + c)));
         y[i] = m;
     }
 }
@@ -591,7 +604,9 @@ extern "C" int rf_cl_norm_split(const float* x, const float* gn_mu, const float*
 extern "C" int rf_cl_maxpool3d_2(const float* x, float* y, int N, int D, int H, int W, int C, void* stream) {
     RF_CHECK_ARG(x && y && N > 0 && C > 0 && D >= 2 && H >= 2 && W >= 2, "rf_cl_maxpool3d_2: bad arguments");
     const long total = (long)N * (D / 2) * (H / 2) * (W / 2) * C;
-    cl_maxpool2_kernel<<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, N, D, H, W, C);
+    RF_CHECK_ARG(total < (1L << 32), "rf_cl_maxpool3d_2: more than 2^32 elements");
+    cl_maxpool2_kernel<<<rf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, N, D, H, W, C, make_fastdiv(C), make_fastdiv(W / 2),
+                                                                                 make_fastdiv(H / 2), make_fastdiv(D / 2));
     RF_LAUNCH_OK("cl_maxpool2_kernel");
     return 0;
 }

@@ -44,6 +44,7 @@ struct SplitArgs {
     uint4 *hi, *lo;
     int N, D, H, W, C1, C2, CC1, CC, CCe, pad, interior_only;
     float scale;
+    FastDiv fCC, fW, fH, fD;  // exact 32-bit divisions of the flat index (total < 2^32 is checked on the host)
 };
 
 __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs s) {
@@ -59,12 +60,14 @@ __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs
     // thread <-> (voxel, channel chunk) with the CHUNK fastest: consecutive threads read consecutive 32-byte pieces of
     // one voxel's channels (whole lines of the channels-last source), and the 8 / CC voxels a warp covers per chunk
     // land in consecutive slots of that chunk's plane (128-byte runs on the store side)
+    // (the flat index is decomposed with multiply-high divisions: five 64-bit div / mod pairs per 48 bytes of traffic
+    // made this kernel issue-bound at a third of the HBM rate)
     for (long j = blockIdx.x * (long)blockDim.x + threadIdx.x; j < total; j += (long)gridDim.x * blockDim.x) {
-        long t = j;
-        const int cc = (int)(t % CCv); t /= CCv;
-        const int ww = (int)(t % Wv) + off; t /= Wv;
-        const int hh = (int)(t % Hv) + off; t /= Hv;
-        const int dd = (int)(t % Dv) + off; t /= Dv;
+        unsigned t = (unsigned)j;
+        const int cc = (int)fd_divmod(t, s.fCC);
+        const int ww = (int)fd_divmod(t, s.fW) + off;
+        const int hh = (int)fd_divmod(t, s.fH) + off;
+        const int dd = (int)fd_divmod(t, s.fD) + off;
         const int n = (int)t;
         const long i = (((long)cc * s.N + n) * Dp + dd) * Hp * Wp + (long)hh * Wp + ww;  // slot index in the haloed planes
         uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
@@ -593,6 +596,11 @@ extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, in
     s.x = x; s.x2 = x2; s.mu = gn_mu; s.a = gn_a; s.beta = gn_beta; s.hi = (uint4*)hi; s.lo = (uint4*)lo;
     s.N = N; s.D = D; s.H = H; s.W = W; s.C1 = C1; s.C2 = C2; s.CC1 = Cp1 / 8; s.CC = CC; s.CCe = CCe; s.pad = pad; s.scale = scale; s.interior_only = interior_only ? 1 : 0;
     const long total = interior_only ? (long)CC * N * (long)D * H * W : (long)CCe * N * (long)(D + 2 * pad) * (H + 2 * pad) * (W + 2 * pad);
+    RF_CHECK_ARG(total < (1L << 32), "rf_cl_norm_split_halo: more than 2^32 slots");
+    s.fCC = make_fastdiv(interior_only ? CC : CCe);
+    s.fW = make_fastdiv(interior_only ? W : W + 2 * pad);
+    s.fH = make_fastdiv(interior_only ? H : H + 2 * pad);
+    s.fD = make_fastdiv(interior_only ? D : D + 2 * pad);
     cl_norm_split_halo_kernel<<<rf_grid_1d(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(s);
     RF_LAUNCH_OK("cl_norm_split_halo_kernel");
     return 0;

@@ -659,6 +659,25 @@ def mlp_encode(x, wts, biases, l2_normalize=True):
 last_knn_stats = {}
 
 
+_knn_ws = {}
+
+
+def _knn_workspace(nbytes, device):
+    """One lookup workspace per (device, stream), grown on demand and reused: a bulk lookup needs a few hundred MB of
+    scratch, and taking that from the caching allocator on every call made the lookup's latency depend on the
+    allocator's state.  Lookups on one stream are ordered, so they can share it; other streams get their own."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(nbytes, device=device, dtype=torch.uint8)  # graph-private pool
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _knn_ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _knn_ws.pop(key, None)
+        buf = torch.empty(int(nbytes * 1.25) + 4096, device=device, dtype=torch.uint8)
+        _knn_ws[key] = buf
+    return buf
+
+
 class KnnBankImage:
     """The prepared tensor-core operand image of one bank (shard): rf_knn_bank_prepare's output, built once and
     reused by every lookup (the reference loads its FLANN index once per worker, util/retrieval.py:81-83)."""
@@ -705,7 +724,7 @@ def knn_topk(bank, q, k, row_offset=0, method=0, stats=False, image=None):
         if image.bank_ptr != bank.data_ptr() or image.n_rows != n:
             raise _lib.RfError("knn_topk: the prepared image belongs to another bank")
         m = image.method
-        ws = torch.empty(max(L.rf_knn_prepared_workspace_bytes(Q, n, k, m), 256), device=q.device, dtype=torch.uint8)
+        ws = _knn_workspace(max(L.rf_knn_prepared_workspace_bytes(Q, n, k, m), 256), q.device)
         with torch.cuda.device(q.device), _timed("rf_knn_l2_topk", flops=2.0 * Q * n * 64):
             check(L.rf_knn_l2_topk_prepared(bank.data_ptr(), n, int(row_offset), image.image.data_ptr(), m, q.data_ptr(), Q, D, k,
                                             idx.data_ptr(), d.data_ptr(), ws.data_ptr(), ws.numel(), _stream(q)),
@@ -713,7 +732,7 @@ def knn_topk(bank, q, k, row_offset=0, method=0, stats=False, image=None):
         tc = True
         _count(6)
     else:
-        ws = torch.empty(max(L.rf_knn_workspace_bytes(Q, n, k, method), 256), device=q.device, dtype=torch.uint8)
+        ws = _knn_workspace(max(L.rf_knn_workspace_bytes(Q, n, k, method), 256), q.device)
         with torch.cuda.device(q.device), _timed("rf_knn_l2_topk", flops=2.0 * Q * n * 64):
             check(L.rf_knn_l2_topk(bank.data_ptr(), n, int(row_offset), q.data_ptr(), Q, D, k, method, idx.data_ptr(),
                                    d.data_ptr(), ws.data_ptr(), ws.numel(), _stream(q)), "rf_knn_l2_topk")
