@@ -8,10 +8,13 @@
 // core reads all 27 shifted windows of it in place:
 //
 //   * rf_cl_norm_split_halo writes the normalised activations (virtual concat of x and
-//     the nearest-upsampled x2 included) as fp16 hi / lo "slot planes"
-//         [channel chunk][sample][D+2][H+2][W+2] x 16 B   (slot = 8 channels of one voxel)
-//     with a zero halo, so that a patch / slab of one chunk plane is contiguous and one
-//     cp.async.bulk moves it to shared memory.
+//     the nearest-upsampled x2 included) as COMPACT fp16 hi / lo "slot planes"
+//         [channel chunk][sample][D][H][W] x 16 B   (slot = 8 channels of one voxel).
+//     One TMA tile copy (cp.async.bulk.tensor.4d) per plane moves a patch / slab WITH its
+//     halo to shared memory: the box starts one voxel outside the volume and the TMA unit
+//     zero-fills what lies out of bounds, so the zero padding of the convolution never
+//     exists in HBM (the first version kept haloed planes in HBM: 1.4-2x the bytes on both
+//     sides, and interior lines that start mid-sector).
 //   * UMMA operand descriptors in the NO-swizzle K-major layout address core matrices
 //     of 8 rows x 16 B at arbitrary 16-byte granularity: 8 consecutive slots are the 8
 //     rows of a core matrix, the next 8-row group sits SBO bytes further, the second
@@ -27,6 +30,7 @@
 //     accumulators for the whole item in TMEM (n_tiles x Npad columns <= 512).
 //   * Single-chunk inputs (C <= 8) pair two taps into one K = 16 step: LBO = 16 B makes
 //     the second K chunk the neighbouring slot, i.e. tap kw+1.
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -35,79 +39,110 @@
 namespace {
 using namespace rf_tc;
 
+// TMA tile copy global -> shared of one 4-D box (coordinates in elements of the tensor map, innermost first; parts of
+// the box outside the tensor are zero-filled and still counted in the barrier's transaction bytes)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+
 constexpr int TM = 128, NTHREADS = 512, NB = 4, MAX_ABUF = 2;
 constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in maximum per CTA on sm_100
+// same for the 5-D form (slot words, W, H, D, plane) used when a haloed line exceeds 256 8-byte words (W > 126)
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+        : "memory");
+}
 
 // ------------------------------------------------------------------ activations -> haloed slot planes
 struct SplitArgs {
     const float *x, *x2, *mu, *a, *beta;
     uint4 *hi, *lo;
-    int N, D, H, W, C1, C2, CC1, CC, CCe, pad, interior_only;
+    int N, D, H, W, C1, C2, CC1, CC;
     float scale;
     FastDiv fCC, fW, fH, fD;  // exact 32-bit divisions of the flat index (total < 2^32 is checked on the host)
+    FastDiv fCG;              // octet mapping: chunk groups of 4
+    unsigned n_vox;
+    long total_oct;
 };
 
+template <int OCT>
 __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs s) {
-    const int Dp = s.D + 2 * s.pad, Hp = s.H + 2 * s.pad, Wp = s.W + 2 * s.pad;
-    const long V = (long)Dp * Hp * Wp;
-    // interior_only: the caller owns a zero-initialised buffer whose halo (and padding chunk planes) nobody ever
-    // writes, so only the D x H x W interior of the real chunks is visited (half the slots of an 8^3 patch are halo)
-    const int Dv = s.interior_only ? s.D : Dp, Hv = s.interior_only ? s.H : Hp, Wv = s.interior_only ? s.W : Wp;
-    const int off = s.interior_only ? s.pad : 0;
-    const int CCv = s.interior_only ? s.CC : s.CCe;
-    const long total = (long)CCv * s.N * Dv * Hv * Wv;
     const int c_tot = s.C1 + s.C2;
-    // thread <-> (voxel, channel chunk) with the CHUNK fastest: consecutive threads read consecutive 32-byte pieces of
-    // one voxel's channels (whole lines of the channels-last source), and the 8 / CC voxels a warp covers per chunk
-    // land in consecutive slots of that chunk's plane (128-byte runs on the store side)
+    // OCT = 0: thread <-> (voxel, channel chunk) with the CHUNK fastest: consecutive threads read consecutive 32-byte
+    // pieces of one voxel's channels, and the 32 / CC voxels a warp covers per chunk land in consecutive slots of that
+    // chunk's plane.  With many chunks (joins: 12 or 24) that leaves 43-byte runs per plane and store instruction.
+    // OCT = 1 (CC >= 5): a warp covers 8 consecutive voxels x 4 consecutive chunks, lane = chunk * 8 + voxel: every
+    // store instruction writes four aligned 128-byte runs, every load instruction reads whole 32-byte sectors of 128
+    // contiguous bytes per voxel.
     // (the flat index is decomposed with multiply-high divisions: five 64-bit div / mod pairs per 48 bytes of traffic
     // made this kernel issue-bound at a third of the HBM rate)
+    const long total = OCT ? s.total_oct : (long)s.CC * s.n_vox;
     for (long j = blockIdx.x * (long)blockDim.x + threadIdx.x; j < total; j += (long)gridDim.x * blockDim.x) {
-        unsigned t = (unsigned)j;
-        const int cc = (int)fd_divmod(t, s.fCC);
-        const int ww = (int)fd_divmod(t, s.fW) + off;
-        const int hh = (int)fd_divmod(t, s.fH) + off;
-        const int dd = (int)fd_divmod(t, s.fD) + off;
+        int cc;
+        unsigned v;  // voxel in (n, d, h, w) order
+        if (OCT) {
+            unsigned t = (unsigned)(j >> 5);
+            cc = (int)fd_divmod(t, s.fCG) * 4 + (int)((j >> 3) & 3);
+            v = t * 8u + (unsigned)(j & 7);
+            if (cc >= s.CC || v >= s.n_vox) continue;
+        } else {
+            unsigned t = (unsigned)j;
+            cc = (int)fd_divmod(t, s.fCC);
+            v = t;
+        }
+        const long i = (long)cc * s.n_vox + v;  // slot index in the compact planes [chunk][n][d][h][w]
+        unsigned t = v;
+        const int w = (int)fd_divmod(t, s.fW);
+        const int hq = (int)fd_divmod(t, s.fH);
+        const int d = (int)fd_divmod(t, s.fD);
         const int n = (int)t;
-        const long i = (((long)cc * s.N + n) * Dp + dd) * Hp * Wp + (long)hh * Wp + ww;  // slot index in the haloed planes
         uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
-        if (cc < s.CC && ww >= s.pad && ww < s.W + s.pad && hh >= s.pad && hh < s.H + s.pad && dd >= s.pad && dd < s.D + s.pad) {
-            const int d = dd - s.pad, hq = hh - s.pad, w = ww - s.pad;
-            const float* src;
-            int C, c0, goff;
-            if (cc < s.CC1) {
-                C = s.C1; c0 = cc * 8; goff = 0;
-                src = s.x + ((((long)n * s.D + d) * s.H + hq) * s.W + w) * C;
-            } else {
-                C = s.C2; c0 = (cc - s.CC1) * 8; goff = s.C1;
-                src = s.x2 + ((((long)n * (s.D >> 1) + (d >> 1)) * (s.H >> 1) + (hq >> 1)) * (s.W >> 1) + (w >> 1)) * C;
-            }
-            float f[8];
-            if ((C & 3) == 0 && c0 + 8 <= C) {
-                const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + c0));
-                const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + c0 + 4));
-                f[0] = v0.x; f[1] = v0.y; f[2] = v0.z; f[3] = v0.w; f[4] = v1.x; f[5] = v1.y; f[6] = v1.z; f[7] = v1.w;
+        const float* src;
+        int C, c0, goff;
+        if (cc < s.CC1) {
+            C = s.C1; c0 = cc * 8; goff = 0;
+            src = s.x + (long)v * C;
+        } else {
+            C = s.C2; c0 = (cc - s.CC1) * 8; goff = s.C1;
+            src = s.x2 + ((((long)n * (s.D >> 1) + (d >> 1)) * (s.H >> 1) + (hq >> 1)) * (s.W >> 1) + (w >> 1)) * C;
+        }
+        float f[8];
+        const bool full = (C & 3) == 0 && c0 + 8 <= C;
+        if (full) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + c0));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + c0 + 4));
+            f[0] = v0.x; f[1] = v0.y; f[2] = v0.z; f[3] = v0.w; f[4] = v1.x; f[5] = v1.y; f[6] = v1.z; f[7] = v1.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = c0 + e < C ? __ldg(src + c0 + e) : 0.f;
+        }
+        if (s.mu) {
+            const long si = (long)n * c_tot + goff + c0;
+            if (full && ((c_tot | goff) & 3) == 0) {  // whole chunk, 16-byte aligned statistics: six vector loads
+                float m[8], sa[8], sb[8];
+                *reinterpret_cast<float4*>(m) = __ldg(reinterpret_cast<const float4*>(s.mu + si));
+                *reinterpret_cast<float4*>(m + 4) = __ldg(reinterpret_cast<const float4*>(s.mu + si + 4));
+                *reinterpret_cast<float4*>(sa) = __ldg(reinterpret_cast<const float4*>(s.a + si));
+                *reinterpret_cast<float4*>(sa + 4) = __ldg(reinterpret_cast<const float4*>(s.a + si + 4));
+                *reinterpret_cast<float4*>(sb) = __ldg(reinterpret_cast<const float4*>(s.beta + goff + c0));
+                *reinterpret_cast<float4*>(sb + 4) = __ldg(reinterpret_cast<const float4*>(s.beta + goff + c0 + 4));
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e] - m[e], sa[e], sb[e]);
             } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = c0 + e < C ? __ldg(src + c0 + e) : 0.f;
+                for (int e = 0; e < 8; ++e)
+                    if (c0 + e < C) f[e] = fmaf(f[e] - __ldg(s.mu + si + e), __ldg(s.a + si + e), __ldg(s.beta + goff + c0 + e));
             }
+        }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float val = f[e];
-                if (c0 + e < C) {
-                    if (s.mu) {
-                        const long si = (long)n * c_tot + goff + c0 + e;
-                        val = fmaf(val - __ldg(s.mu + si), __ldg(s.a + si), __ldg(s.beta + goff + c0 + e));
-                    }
-                    val *= s.scale;
-                } else {
-                    val = 0.f;
-                }
-                uint32_t hv, lv;
-                split_f16(val, hv, lv);
-                h[e >> 1] |= hv << (16 * (e & 1));
-                l[e >> 1] |= lv << (16 * (e & 1));
-            }
+        for (int e = 0; e < 8; e += 2) {
+            const float v0 = c0 + e < C ? f[e] * s.scale : 0.f, v1 = c0 + e + 1 < C ? f[e + 1] * s.scale : 0.f;
+            split_f16x2(v0, v1, h[e >> 1], l[e >> 1]);
         }
         s.hi[i] = make_uint4(h[0], h[1], h[2], h[3]);
         s.lo[i] = make_uint4(l[0], l[1], l[2], l[3]);
@@ -162,11 +197,12 @@ __global__ void __launch_bounds__(256) halo_weight_image_kernel(const float* __r
 __device__ long long g_halo_dbg[64];
 
 struct HaloArgs {
-    const uint8_t *hi, *lo, *wimg;
+    const uint8_t* wimg;
     const float* bias;
     float* y;
     int N, D, H, W, Hp, Wp;
-    long V, plane_slots;          // slots per haloed sample volume, slots per channel-chunk plane (N * V)
+    int pad, CC, tm5;             // conv padding (0 / 1); real channel chunks (chunk >= CC: all zero); 5-D tensor maps
+    long V;                       // slots per haloed sample volume
     int Dt, Ht, Hs, G, stacked;   // item = G stacked whole samples, or a Dt x Ht x W slab of one sample
     int n_dt, n_ht, Ls;           // slabs per sample; lines per stacked sample (Dp * Hp)
     int lines, n_wblk, n_tiles, P;  // P = slots per staged plane (incl. over-read slack)
@@ -183,7 +219,11 @@ struct HaloArgs {
 // allocation and first-load latency (10-30 thousand cycles per item when every item was its own CTA) are paid once
 // per CTA instead of once per item.
 //   warp 0: activation producer   warp 3: weight producer   warps 1,2,4-7: MMA issuers   warps 8-15: epilogue
-__global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloArgs a) {
+//
+// tm_hi / tm_lo: 4-D tensor maps of the compact hi / lo planes, dims (2 W 8-byte words, H, D, CC * N), box = the
+// haloed block of one item (2 (W+2), Hs, Dt+2, G); coordinates that fall outside are zero-filled by the TMA unit.
+__global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tm_hi,
+                                                                     const __grid_constant__ CUtensorMap tm_lo) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
@@ -215,9 +255,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(a.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // Zero the staging buffers once: the bulk copies never fill the over-read slack (nor the missing samples of a
-    // ragged last item).  Operand rows that touch it are dropped, but in pair mode a REAL row multiplies one such
-    // slot by a zero weight, and 0 * NaN would poison it; later items leave finite values there.
+    // Zero the staging buffers once: the tile copies never fill the over-read slack behind the item's block.  Operand
+    // rows that touch it are dropped, but in pair mode a REAL row multiplies one such slot by a zero weight, and
+    // 0 * NaN would poison it.
     {
         const int total = a.nbuf * planes * a.P;
         for (int i = threadIdx.x; i < total; i += NTHREADS) *reinterpret_cast<uint4*>(smem_al + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
@@ -246,18 +286,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
 
     if (warp == 0) {
       if (lane == 0) {
-        // ---- activation producer: one stage = ck channel chunks x (hi, lo) planes of the item's haloed block; two
-        // passes over the channel stages (cross products first, then hi * hi; see the issuers)
-        const long slab = (long)a.Hp * a.Wp;
+        // ---- activation producer: one stage = ck channel chunks x (hi, lo) planes of the item's haloed block (one
+        // TMA tile copy per plane); two passes over the channel stages (cross products first, then hi * hi; see the
+        // issuers)
         const int n_pass = a.fused ? 1 : 2;
         const int n_loads = resident ? 1 : n_pass * a.n_stages;
+        const uint32_t plane_bytes = (uint32_t)a.S_st * 16u;
         uint32_t lc = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-            int n0, gact = 1, d0 = 0, h0 = 0;
-            if (a.stacked) { n0 = item * a.G; gact = min(a.G, a.N - n0); }
+            int n0, d0 = 0, h0 = 0;
+            if (a.stacked) { n0 = item * a.G; }
             else { n0 = item / per_sample; const int r = item % per_sample; d0 = (r / a.n_ht) * a.Dt; h0 = (r % a.n_ht) * a.Ht; }
-            const bool one_copy = a.stacked || a.Ht == a.H;
-            const uint32_t plane_bytes = a.stacked ? (uint32_t)(gact * a.V) * 16u : (uint32_t)a.S_st * 16u;
             for (int l = 0; l < n_loads; ++l, ++lc) {
                 const int s = l >= a.n_stages ? l - a.n_stages : l;
                 const uint32_t b = lc % (uint32_t)a.nbuf;
@@ -265,17 +304,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
                 mbar_arrive_expect_tx(bar_afull + 8 * b, plane_bytes * planes);
                 for (int pl = 0; pl < planes; ++pl) {
                     const int hl = pl / a.ck, c = pl % a.ck;
-                    const long cc = (long)s * a.ck + c;
-                    const uint8_t* src = (hl ? a.lo : a.hi) + (cc * a.plane_slots + (long)n0 * a.V) * 16;
+                    const int cc = s * a.ck + c;
+                    // a padding chunk (cc >= CC) or the samples past N of a ragged last item lie outside the tensor: zeros
+                    const int plane = cc < a.CC ? cc * a.N + n0 : a.CC * a.N;
                     const uint32_t dst = sA + b * abuf_bytes + (uint32_t)pl * (uint32_t)a.P * 16u;
-                    if (one_copy) {
-                        bulk_g2s(dst, src + (long)d0 * slab * 16, plane_bytes, bar_afull + 8 * b);
-                    } else {
-                        const uint32_t row_bytes = (uint32_t)(a.Hs * a.Wp) * 16u;
-                        for (int dd = 0; dd < a.Dt + 2; ++dd)
-                            bulk_g2s(dst + dd * row_bytes, src + ((long)(d0 + dd) * slab + (long)h0 * a.Wp) * 16, row_bytes,
-                                     bar_afull + 8 * b);
-                    }
+                    if (a.tm5) tma_load_5d(dst, hl ? &tm_lo : &tm_hi, 0, -a.pad, h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
+                    else tma_load_4d(dst, hl ? &tm_lo : &tm_hi, -2 * a.pad, h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
                 }
             }
         }
@@ -458,6 +492,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup: the library must load (and export its
+// symbols) on machines without a driver, so it cannot link against libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
 struct Geo {
     int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, two_resident, n_sets, fused;
     uint32_t tmem_cols, bslot;
@@ -578,12 +628,13 @@ bool halo_shape(int Cout, int C1, int C2, int& Cp1, int& Cp2, int& CC, int& CCe,
 extern "C" size_t rf_halo_act_bytes(int N, int D, int H, int W, int C1, int C2, int pad) {
     int Cp1, Cp2, CC, CCe, pair, Npad;
     if (!halo_shape(16, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad) || N < 1 || D < 1 || H < 1 || W < 1 || pad < 0 || pad > 1) return 0;
-    return (size_t)CCe * N * (size_t)(D + 2 * pad) * (H + 2 * pad) * (W + 2 * pad) * 16;
+    return (size_t)CC * N * (size_t)D * H * W * 16;  // compact planes: the halo is made by the TMA unit's zero fill
 }
 
 extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a,
                                      const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, int pad, float scale,
                                      int interior_only, void* stream) {
+    (void)interior_only;  // the planes have no halo any more: every call writes every slot
     int Cp1, Cp2, CC, CCe, pair, Npad;
     RF_CHECK_ARG(halo_shape(16, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad), "rf_cl_norm_split_halo: bad channel counts");
     RF_CHECK_ARG(hi && lo && (C1 == 0 || x) && (C2 == 0 || x2) && N > 0 && D > 0 && H > 0 && W > 0 && (pad == 0 || pad == 1),
@@ -594,14 +645,22 @@ extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, in
                  "rf_cl_norm_split_halo: pointers must be 16-byte aligned");
     SplitArgs s;
     s.x = x; s.x2 = x2; s.mu = gn_mu; s.a = gn_a; s.beta = gn_beta; s.hi = (uint4*)hi; s.lo = (uint4*)lo;
-    s.N = N; s.D = D; s.H = H; s.W = W; s.C1 = C1; s.C2 = C2; s.CC1 = Cp1 / 8; s.CC = CC; s.CCe = CCe; s.pad = pad; s.scale = scale; s.interior_only = interior_only ? 1 : 0;
-    const long total = interior_only ? (long)CC * N * (long)D * H * W : (long)CCe * N * (long)(D + 2 * pad) * (H + 2 * pad) * (W + 2 * pad);
-    RF_CHECK_ARG(total < (1L << 32), "rf_cl_norm_split_halo: more than 2^32 slots");
-    s.fCC = make_fastdiv(interior_only ? CC : CCe);
-    s.fW = make_fastdiv(interior_only ? W : W + 2 * pad);
-    s.fH = make_fastdiv(interior_only ? H : H + 2 * pad);
-    s.fD = make_fastdiv(interior_only ? D : D + 2 * pad);
-    cl_norm_split_halo_kernel<<<rf_grid_1d(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(s);
+    s.N = N; s.D = D; s.H = H; s.W = W; s.C1 = C1; s.C2 = C2; s.CC1 = Cp1 / 8; s.CC = CC; s.scale = scale;
+    const long n_vox = (long)N * D * H * W;
+    const long total = (long)CC * n_vox;
+    RF_CHECK_ARG(total < (1L << 32) - 256, "rf_cl_norm_split_halo: more than 2^32 slots");
+    s.fCC = make_fastdiv(CC);
+    s.fW = make_fastdiv(W);
+    s.fH = make_fastdiv(H);
+    s.fD = make_fastdiv(D);
+    const int CG = (CC + 3) / 4;
+    s.fCG = make_fastdiv(CG);
+    s.n_vox = (unsigned)n_vox;
+    s.total_oct = (n_vox + 7) / 8 * CG * 32;
+    if (CC >= 5)
+        cl_norm_split_halo_kernel<1><<<rf_grid_1d(s.total_oct, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(s);
+    else
+        cl_norm_split_halo_kernel<0><<<rf_grid_1d(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(s);
     RF_LAUNCH_OK("cl_norm_split_halo_kernel");
     return 0;
 }
@@ -659,9 +718,10 @@ extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void*
     RF_CHECK_ARG(choose_geometry(N, D, H, W, CCe, pair, Npad, g), "rf_tc_conv3d_halo_fwd: no item shape fits (N=%d out %dx%dx%d Cout=%d C=%d+%d)",
                  N, D, H, W, Cout, C1, C2);
     HaloArgs a;
-    a.hi = (const uint8_t*)hi; a.lo = (const uint8_t*)lo; a.wimg = (const uint8_t*)weight_image; a.bias = bias; a.y = y;
+    a.wimg = (const uint8_t*)weight_image; a.bias = bias; a.y = y;
     a.N = N; a.D = D; a.H = H; a.W = W; a.Hp = H + 2; a.Wp = W + 2;
-    a.V = (long)(D + 2) * (H + 2) * (W + 2); a.plane_slots = (long)N * a.V;
+    a.pad = pad; a.CC = CC;
+    a.V = (long)(D + 2) * (H + 2) * (W + 2);
     a.Dt = g.Dt; a.Ht = g.Ht; a.Hs = g.Hs; a.G = g.G; a.stacked = g.stacked;
     a.n_dt = D / g.Dt; a.n_ht = H / g.Ht; a.Ls = (D + 2) * (H + 2);
     a.lines = g.lines; a.n_wblk = g.n_wblk; a.n_tiles = g.n_tiles; a.P = g.P; a.S_st = g.S_st;
@@ -677,11 +737,40 @@ extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void*
     }
     if (int rc = rf_tc_conv_halo_init()) return rc;
     a.n_items = g.n_items; a.n_sets = g.n_sets; a.fused = g.fused;
+    // tensor maps of the compact planes [CC * N][Din][Hin][Win] x 16 B, seen as 8-byte words so that a whole haloed line
+    // (W + 2 slots) is the innermost box extent (<= 256 elements)
+    const int Din = D + 2 - 2 * pad, Hin = H + 2 - 2 * pad, Win = W + 2 - 2 * pad;
+    RF_CHECK_ARG(W + 2 <= 256 && g.Hs <= 256 && g.Dt + 2 <= 256 && g.G <= 256, "rf_tc_conv3d_halo_fwd: item box exceeds the TMA limits");
+    a.tm5 = 2 * (W + 2) > 256 ? 1 : 0;  // a haloed line longer than 256 words: slots as a dimension of their own
+    CUtensorMap tm[2];
+    const EncodeTiledFn encode = encode_tiled_fn();
+    RF_CHECK_ARG(encode != nullptr, "rf_tc_conv3d_halo_fwd: the driver does not export cuTensorMapEncodeTiled");
+    for (int k = 0; k < 2; ++k) {
+        const cuuint32_t bG = (cuuint32_t)(g.stacked ? g.G : 1);
+        const cuuint64_t planes = (cuuint64_t)CC * (cuuint64_t)N;
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult cr;
+        if (a.tm5) {
+            const cuuint64_t gdim[5] = {2, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)Din, planes};
+            const cuuint64_t gstr[4] = {16, 16ull * Win, 16ull * Win * Hin, 16ull * Win * Hin * Din};
+            const cuuint32_t box[5] = {2, (cuuint32_t)(W + 2), (cuuint32_t)g.Hs, (cuuint32_t)(g.Dt + 2), bG};
+            cr = encode(&tm[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void*>(k ? lo : hi), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            const cuuint64_t gdim[4] = {(cuuint64_t)(2 * Win), (cuuint64_t)Hin, (cuuint64_t)Din, planes};
+            const cuuint64_t gstr[3] = {16ull * Win, 16ull * Win * Hin, 16ull * Win * Hin * Din};
+            const cuuint32_t box[4] = {(cuuint32_t)(2 * (W + 2)), (cuuint32_t)g.Hs, (cuuint32_t)(g.Dt + 2), bG};
+            cr = encode(&tm[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(k ? lo : hi), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        RF_CHECK_ARG(cr == CUDA_SUCCESS, "rf_tc_conv3d_halo_fwd: cuTensorMapEncodeTiled failed (%d) for planes %dx%dx%dx%d, item box %dx%dx%dx%u", (int)cr,
+                     Win, Hin, Din, CC * N, W + 2, g.Hs, g.Dt + 2, bG);
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int slots = sms * (g.two_resident ? 2 : 1);
-    tc_conv3d_halo_kernel<<<(unsigned)(g.n_items < slots ? g.n_items : slots), NTHREADS, g.smem, (cudaStream_t)stream>>>(a);
+    tc_conv3d_halo_kernel<<<(unsigned)(g.n_items < slots ? g.n_items : slots), NTHREADS, g.smem, (cudaStream_t)stream>>>(a, tm[0], tm[1]);
     RF_LAUNCH_OK("tc_conv3d_halo_kernel");
     return 0;
 }

@@ -498,8 +498,8 @@ def tc_conv_halo_geometry(N, D, H, W, cout, c1, c2, pad=1):
 
 def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0, pad=1, buffers=None):
     """fp32 channels-last x [N,D,H,W,C1] (or None) and half-resolution x2 [N,D/2,H/2,W/2,C2] (or None) ->
-    (hi, lo) fp16 slot planes [chunk][N][D+2p][H+2p][W+2p][8] of scale * GroupNorm(concat(x, up2(x2))), zero halo of
-    width p = pad."""
+    (hi, lo) compact fp16 slot planes [chunk][N][D][H][W][8] of scale * GroupNorm(concat(x, up2(x2))); the zero halo
+    of width pad is produced by the convolution's TMA loads (out-of-bounds zero fill)."""
     src = x if x is not None else x2
     src = _dev(src, name="x")
     c1 = x.shape[-1] if x is not None else 0
@@ -512,8 +512,8 @@ def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0, pad=1, buffers=None):
     nbytes = L.rf_halo_act_bytes(N, D, H, W, c1, c2, int(pad))
     if nbytes == 0:
         raise _lib.RfError(f"halo layout does not support C={c1}+{c2}")
-    # buffers: a dict owned by the caller (one per layer).  The planes for this shape are allocated zeroed once and
-    # reused; nobody ever writes their halo, so later calls only write the interior slots.
+    # buffers: a dict owned by the caller (one per layer): the planes for this shape are allocated once and reused
+    # (compact planes, every slot is rewritten by every call; the conv's TMA loads make the zero halo on the fly)
     interior_only = 0
     if buffers is not None:
         key = (N, D, H, W, c1, c2, int(pad), src.device)
@@ -524,12 +524,11 @@ def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0, pad=1, buffers=None):
             while len(buffers) >= MAX_PLANE_SHAPES:
                 buffers.pop(next(iter(buffers)))
                 bump_generation()
-            buffers[key] = (torch.zeros(nbytes, device=src.device, dtype=torch.uint8),
-                            torch.zeros(nbytes, device=src.device, dtype=torch.uint8))
+            buffers[key] = (torch.empty(nbytes, device=src.device, dtype=torch.uint8),
+                            torch.empty(nbytes, device=src.device, dtype=torch.uint8))
         else:
             buffers[key] = buffers.pop(key)  # most recently used last
         hi, lo = buffers[key]
-        interior_only = 1
     else:
         hi = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
         lo = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
