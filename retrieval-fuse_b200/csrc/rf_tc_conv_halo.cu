@@ -510,21 +510,27 @@ EncodeTiledFn encode_tiled_fn() {
 
 struct Geo {
     int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, two_resident, n_sets, fused;
+    int halo;  // 2: every sample / slab carries its own halo; 1 (stacked, 'same' padding): neighbours share it
     uint32_t tmem_cols, bslot;
     size_t smem;
     double score;
 };
 
 // Chooses the item shape: maximise (real outputs / computed GEMM rows), penalise grids that leave SMs idle.
-bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, Geo& best) {
-    const int Dp = D + 2, Hp = H + 2, Wp = W + 2;
-    const long V = (long)Dp * Hp * Wp;
+bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, int pad, Geo& best) {
     const int ck = pair ? 1 : 2, planes = 2 * ck, kpg = pair ? 2 : 3;
     const int n_stages = pair ? 1 : CCe / 2;
     const uint32_t bslot = (uint32_t)kpg * 2u * (uint32_t)Npad * 32u;
     const long avail_all = (long)SMEM_LIMIT - 1024 - 256 - (long)NB * bslot;
     best.score = -1.0;
-    auto consider = [&](int stacked, int G, int Dt, int Ht, int lines) {
+    // halo = 1 ("shared halo", stacked whole samples with zero padding only): the TMA box starts one voxel before the
+    // volume and ends AT its far faces, so a sample occupies (D+1)(H+1)(W+1) slots whose index-0 faces are zero: the
+    // far neighbours of the last voxel of a line / plane / sample are the zero slots that open the next line / plane /
+    // sample (the zeroed slack behind the block for the last sample).  51 % of the rows of stacked 4^3 patches are
+    // real outputs instead of 30 %.
+    auto consider = [&](int stacked, int G, int Dt, int Ht, int lines, int halo) {
+        const int Dp = D + halo, Hp = H + halo, Wp = W + halo;
+        const long V = (long)Dp * Hp * Wp;
         const int Hs = stacked ? Hp : Ht + 2;
         const long S_st = stacked ? (long)G * V : (long)(Dt + 2) * Hs * Wp;
         const long lines_needed = stacked ? (long)(G - 1) * Dp * Hp + (long)(D - 1) * Hp + H : (long)(Dt - 1) * Hs + Ht;
@@ -586,7 +592,7 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, Ge
                     best.lines = lines; best.n_wblk = n_wblk; best.n_tiles = (int)n_tiles; best.P = (int)P; best.S_st = (int)S_st;
                     best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot; best.two_resident = two_resident ? 1 : 0;
                     best.tmem_cols = cols_needed;
-                    best.n_sets = n_sets; best.fused = fused;
+                    best.n_sets = n_sets; best.fused = fused; best.halo = halo;
                     best.smem = (size_t)smem_total;
                     best.score = score;
                 }
@@ -594,19 +600,22 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, Ge
         }
     };
     if (const char* e = getenv("RF_HALO_GEO")) {  // tuning aid: "stacked,G,Dt,Ht,lines" forces the item shape
-        int st, G, Dt, Ht, ln;
-        if (sscanf(e, "%d,%d,%d,%d,%d", &st, &G, &Dt, &Ht, &ln) == 5) {
-            consider(st, G, st ? D : Dt, st ? H : Ht, ln);
+        int st, G, Dt, Ht, ln, hl = 2;
+        if (sscanf(e, "%d,%d,%d,%d,%d,%d", &st, &G, &Dt, &Ht, &ln, &hl) >= 5) {
+            consider(st, G, st ? D : Dt, st ? H : Ht, ln, st && pad == 1 && hl == 1 ? 1 : 2);
             return best.score > 0.0;
         }
     }
     for (int lines = 0; lines < 2; ++lines) {
-        for (int G = 1; G <= 64 && G <= N; ++G) consider(1, G, D, H, lines);
+        for (int G = 1; G <= 32 && G <= N; ++G) {  // (the row table keeps the stacked sample index in 5 bits)
+            consider(1, G, D, H, lines, 2);
+            if (pad == 1) consider(1, G, D, H, lines, 1);
+        }
         for (int Dt = 1; Dt <= D; ++Dt) {
             if (D % Dt) continue;
             for (int Ht = 1; Ht <= H; ++Ht) {
                 if (H % Ht) continue;
-                consider(0, 1, Dt, Ht, lines);
+                consider(0, 1, Dt, Ht, lines, 2);
             }
         }
     }
@@ -694,7 +703,7 @@ extern "C" int rf_tc_conv3d_halo_supported(int N, int D, int H, int W, int Cout,
     if (Do < 1 || Ho < 1 || Wo < 1) return 0;
     if ((long)N * (Do + 2) * (Ho + 2) * (Wo + 2) * CCe >= (1L << 31)) return 0;
     Geo g;
-    return choose_geometry(N, Do, Ho, Wo, CCe, pair, Npad, g) && g.n_tiles <= 32 ? 1 : 0;
+    return choose_geometry(N, Do, Ho, Wo, CCe, pair, Npad, pad, g) && g.n_tiles <= 32 ? 1 : 0;
 }
 
 int rf_tc_conv_halo_init() {
@@ -715,15 +724,15 @@ extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void*
     D += 2 * pad - 2; H += 2 * pad - 2; W += 2 * pad - 2;
     RF_CHECK_ARG(D > 0 && H > 0 && W > 0, "rf_tc_conv3d_halo_fwd: empty output");
     Geo g;
-    RF_CHECK_ARG(choose_geometry(N, D, H, W, CCe, pair, Npad, g), "rf_tc_conv3d_halo_fwd: no item shape fits (N=%d out %dx%dx%d Cout=%d C=%d+%d)",
+    RF_CHECK_ARG(choose_geometry(N, D, H, W, CCe, pair, Npad, pad, g), "rf_tc_conv3d_halo_fwd: no item shape fits (N=%d out %dx%dx%d Cout=%d C=%d+%d)",
                  N, D, H, W, Cout, C1, C2);
     HaloArgs a;
     a.wimg = (const uint8_t*)weight_image; a.bias = bias; a.y = y;
-    a.N = N; a.D = D; a.H = H; a.W = W; a.Hp = H + 2; a.Wp = W + 2;
+    a.N = N; a.D = D; a.H = H; a.W = W; a.Hp = H + g.halo; a.Wp = W + g.halo;
     a.pad = pad; a.CC = CC;
-    a.V = (long)(D + 2) * (H + 2) * (W + 2);
+    a.V = (long)(D + g.halo) * (H + g.halo) * (W + g.halo);
     a.Dt = g.Dt; a.Ht = g.Ht; a.Hs = g.Hs; a.G = g.G; a.stacked = g.stacked;
-    a.n_dt = D / g.Dt; a.n_ht = H / g.Ht; a.Ls = (D + 2) * (H + 2);
+    a.n_dt = D / g.Dt; a.n_ht = H / g.Ht; a.Ls = (D + g.halo) * (H + g.halo);
     a.lines = g.lines; a.n_wblk = g.n_wblk; a.n_tiles = g.n_tiles; a.P = g.P; a.S_st = g.S_st;
     a.pair = pair; a.n_stages = pair ? 1 : CCe / 2; a.nbuf = g.nbuf; a.ck = pair ? 1 : 2; a.kpg = pair ? 2 : 3;
     a.Cout = Cout; a.Npad = Npad; a.act = act; a.out_ncdhw = out_ncdhw; a.slope = slope; a.out_scale = out_scale;
@@ -740,8 +749,9 @@ extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void*
     // tensor maps of the compact planes [CC * N][Din][Hin][Win] x 16 B, seen as 8-byte words so that a whole haloed line
     // (W + 2 slots) is the innermost box extent (<= 256 elements)
     const int Din = D + 2 - 2 * pad, Hin = H + 2 - 2 * pad, Win = W + 2 - 2 * pad;
-    RF_CHECK_ARG(W + 2 <= 256 && g.Hs <= 256 && g.Dt + 2 <= 256 && g.G <= 256, "rf_tc_conv3d_halo_fwd: item box exceeds the TMA limits");
-    a.tm5 = 2 * (W + 2) > 256 ? 1 : 0;  // a haloed line longer than 256 words: slots as a dimension of their own
+    const int bW = W + g.halo, bD = g.stacked ? D + g.halo : g.Dt + 2;  // the item's box (its H extent is g.Hs)
+    RF_CHECK_ARG(bW <= 256 && g.Hs <= 256 && bD <= 256 && g.G <= 256, "rf_tc_conv3d_halo_fwd: item box exceeds the TMA limits");
+    a.tm5 = 2 * bW > 256 ? 1 : 0;  // a haloed line longer than 256 words: slots as a dimension of their own
     CUtensorMap tm[2];
     const EncodeTiledFn encode = encode_tiled_fn();
     RF_CHECK_ARG(encode != nullptr, "rf_tc_conv3d_halo_fwd: the driver does not export cuTensorMapEncodeTiled");
@@ -753,18 +763,18 @@ extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void*
         if (a.tm5) {
             const cuuint64_t gdim[5] = {2, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)Din, planes};
             const cuuint64_t gstr[4] = {16, 16ull * Win, 16ull * Win * Hin, 16ull * Win * Hin * Din};
-            const cuuint32_t box[5] = {2, (cuuint32_t)(W + 2), (cuuint32_t)g.Hs, (cuuint32_t)(g.Dt + 2), bG};
+            const cuuint32_t box[5] = {2, (cuuint32_t)bW, (cuuint32_t)g.Hs, (cuuint32_t)bD, bG};
             cr = encode(&tm[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void*>(k ? lo : hi), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         } else {
             const cuuint64_t gdim[4] = {(cuuint64_t)(2 * Win), (cuuint64_t)Hin, (cuuint64_t)Din, planes};
             const cuuint64_t gstr[3] = {16ull * Win, 16ull * Win * Hin, 16ull * Win * Hin * Din};
-            const cuuint32_t box[4] = {(cuuint32_t)(2 * (W + 2)), (cuuint32_t)g.Hs, (cuuint32_t)(g.Dt + 2), bG};
+            const cuuint32_t box[4] = {(cuuint32_t)(2 * bW), (cuuint32_t)g.Hs, (cuuint32_t)bD, bG};
             cr = encode(&tm[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(k ? lo : hi), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         }
         RF_CHECK_ARG(cr == CUDA_SUCCESS, "rf_tc_conv3d_halo_fwd: cuTensorMapEncodeTiled failed (%d) for planes %dx%dx%dx%d, item box %dx%dx%dx%u", (int)cr,
-                     Win, Hin, Din, CC * N, W + 2, g.Hs, g.Dt + 2, bG);
+                     Win, Hin, Din, CC * N, bW, g.Hs, bD, bG);
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -780,8 +790,8 @@ extern "C" int rf_tc_conv3d_halo_geometry(int N, int D, int H, int W, int Cout, 
     int Cp1, Cp2, CC, CCe, pair, Npad;
     if (!halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad)) return 0;
     Geo g;
-    if (!choose_geometry(N, D + 2 * pad - 2, H + 2 * pad - 2, W + 2 * pad - 2, CCe, pair, Npad, g)) return 0;
-    out8[0] = g.stacked; out8[1] = g.G; out8[2] = g.Dt; out8[3] = g.Ht; out8[4] = g.lines + 2 * g.fused; out8[5] = g.n_tiles;
+    if (!choose_geometry(N, D + 2 * pad - 2, H + 2 * pad - 2, W + 2 * pad - 2, CCe, pair, Npad, pad, g)) return 0;
+    out8[0] = g.stacked; out8[1] = g.G; out8[2] = g.Dt; out8[3] = g.Ht; out8[4] = g.lines + 2 * g.fused + 4 * (g.halo == 1); out8[5] = g.n_tiles;
     out8[6] = g.n_items; out8[7] = (int)g.smem;
     return 1;
 }
