@@ -1020,7 +1020,7 @@ def run_sweep(args, rank, local, world):
         r4 = [r for r in rows if r["k"] == 4][0]
         emit({"metric": "1M-row bank brute-force kNN + attention-fuse sweep (BASELINE configs[4])", "value": r4["knn_bulk_chunks_per_s"],
               "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": 2, "ms_per_step": r4["knn_bulk_ms"], "higher_is_better": True,
-              "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 tcgen05 scores / f64 distance ranking", "data": "synthetic",
+              "scaling": "weak", "vs_baseline": None, "dtype": "fp16 tcgen05 scores (one K = 64 GEMM, proven bound) / f64 distance ranking", "data": "synthetic",
               "config": {"workload": f"1 M-row isotropic unit bank (seed 1), {Qb} isotropic queries per GPU (10 000 chunks), k in 1/4/8/16 "
                                      f"(fetch 2k), bank in {world} row shard(s); attention fuse on randn [8,16,32^3] + [8k,16,32^3]",
                          "l2": "flushed between timed launches (256 MiB write)"},

@@ -8,9 +8,10 @@
 //        method 2: one fp16 GEMM, K = 64          (eps_rel = 1.0e-3)
 //        method 3: bf16 hi/lo split, K = 3*64: q_hi.x_hi + q_hi.x_lo + q_lo.x_hi
 //                  (x = hi + lo + r, |r| <= 2^-18 |x|; eps_rel = 4e-5)
-//   2. each query keeps its CAND best s~ per bank slice (a register-resident
-//      sorted list owned by the epilogue thread that reads the query's TMEM
-//      lane).  CAND = 16 for k <= 8, 32 above: the list must be LONGER than k,
+//   2. each query keeps its CAND best s~ per bank slice (a sorted list in shared
+//      memory owned by the epilogue thread that reads the query's TMEM lane; hits
+//      are inserted cooperatively by the warp when few lanes have one, by every
+//      lane for itself when many do).  CAND = 16 for k <= 8, 32 above: the list must be LONGER than k,
 //      otherwise the proof below compares the k-th candidate with itself.
 //      k > 16 additionally splits the bank into >= 2 slices (2 x 32 candidates).
 //   3. re-rank the candidates with the canonical fp64 arithmetic, and PROVE
@@ -39,6 +40,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <float.h>
+#include <stdlib.h>
 #include <string.h>
 #include <limits.h>
 
@@ -60,10 +62,15 @@ constexpr int NACC = 2;                // TMEM accumulator buffers (MQ x 128 col
 constexpr int MAX_SPLIT = 8;
 constexpr int NTHREADS = 128 + MQ * 128;
 
-template <int KBLK> struct Cfg {
+template <int KBLK, int CAND = 16> struct Cfg {
     static constexpr int TILE_BYTES = KBLK * KB_BYTES;
     static constexpr int NSTAGE = KBLK == 1 ? 6 : 2;
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + TILE_BYTES * (MQ + NSTAGE) + 256 /*barriers*/;
+    // query sub-tile in shared memory: the bf16 split's K blocks are (hi, hi, lo) - the duplicate hi block is staged once
+    static constexpr int A_BLOCKS = KBLK == 3 ? 2 : 1;
+    static constexpr int A_BYTES = A_BLOCKS * KB_BYTES;
+    // per epilogue warp: 32 candidate lists (score, position) + a 32-float staging row for the cooperative insertion
+    static constexpr int LIST_BYTES = 32 * CAND * 8 + 128;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_BYTES * MQ + TILE_BYTES * NSTAGE + 256 /*barriers*/ + 8 * LIST_BYTES;
 };
 // bound on |s~ - q.x| / (|q| |x|), see DESIGN.md "kNN proof"
 // (+4e-6: the epilogue tags scores with their column in the low 5 mantissa bits)
@@ -269,20 +276,24 @@ __global__ void __launch_bounds__(256) knn_tc_prep_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------ main kernel
-template <int KBLK, int CAND>
+// COOP = 1: lists in shared memory, hits inserted cooperatively by the warp, one hot lane at a time.
+// COOP = 0: lists in registers, every lane inserts its own hits with a parallel shift-insert network.
+template <int KBLK, int CAND, int COOP>
 __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const uint8_t* __restrict__ q_img,
                                                                         const uint8_t* __restrict__ bank_img, long Q,
                                                                         long n_rows, int n_qtiles, int n_btiles,
                                                                         int nsplit, float* __restrict__ cand_s,
-                                                                        int* __restrict__ cand_i) {
-    constexpr int TILE_BYTES = Cfg<KBLK>::TILE_BYTES;
-    constexpr int NSTAGE = Cfg<KBLK>::NSTAGE;
+                                                                        int* __restrict__ cand_i, int coop_max) {
+    using C = Cfg<KBLK, CAND>;
+    constexpr int TILE_BYTES = C::TILE_BYTES;
+    constexpr int NSTAGE = C::NSTAGE;
+    constexpr int A_BYTES = C::A_BYTES;
     constexpr uint32_t IDESC = idesc(KBLK == 1 ? 0 : 1);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
     const uint32_t sA = smem_base;                          // MQ query sub-tiles
-    const uint32_t sB = smem_base + MQ * TILE_BYTES;        // NSTAGE bank tiles
-    const uint32_t bars = smem_base + TILE_BYTES * (MQ + NSTAGE);
+    const uint32_t sB = smem_base + MQ * A_BYTES;           // NSTAGE bank tiles
+    const uint32_t bars = sB + TILE_BYTES * NSTAGE;
     const uint32_t bar_full = bars;                     // NSTAGE x 8 B
     const uint32_t bar_empty = bars + 8 * NSTAGE;       // NSTAGE x 8 B
     const uint32_t bar_a = bars + 16 * NSTAGE;          // 8 B
@@ -291,6 +302,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
     const uint32_t tmem_slot = bar_tempty + 8 * NACC;   // 4 B
     volatile uint32_t* tmem_slot_gen =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    uint8_t* list_base = smem_raw + (bars + 256 - smem_u32(smem_raw));  // 8 x LIST_BYTES, 16-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // slice `split` owns bank tiles split, split + nsplit, ...: with the image in scan order every slice sees the
@@ -316,9 +328,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
     if (warp == 0) {
         if (lane == 0) {  // ---------------- producer
             // the query pair: sub-tile m of this CTA is query tile 2*qpair+m (the image is padded to an even tile count)
-            mbar_arrive_expect_tx(bar_a, MQ * TILE_BYTES);
-            for (int j = 0; j < MQ * KBLK; ++j)
-                bulk_g2s(sA + j * KB_BYTES, q_img + (long)qpair * MQ * TILE_BYTES + (long)j * KB_BYTES, KB_BYTES, bar_a);
+            mbar_arrive_expect_tx(bar_a, MQ * A_BYTES);
+            for (int m = 0; m < MQ; ++m)
+                for (int j = 0; j < C::A_BLOCKS; ++j)  // image K blocks (hi, hi, lo): blocks 0 and 2 are staged
+                    bulk_g2s(sA + m * A_BYTES + j * KB_BYTES,
+                             q_img + ((long)qpair * MQ + m) * TILE_BYTES + (long)(KBLK == 3 ? 2 * j : j) * KB_BYTES, KB_BYTES, bar_a);
             for (int it = 0; it < n_iter; ++it) {
                 const int s = it % NSTAGE;
                 const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
@@ -345,7 +359,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
                     for (int kb = 0; kb < KBLK; ++kb) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {  // 4 x K=16 (32 B) steps inside one 128 B swizzle atom
-                            const uint64_t ad = umma_desc(sA + m * TILE_BYTES + kb * KB_BYTES + k * 32);
+                            const uint64_t ad = umma_desc(sA + m * A_BYTES + (KBLK == 3 ? (kb >> 1) : kb) * KB_BYTES + k * 32);
                             const uint64_t bd = umma_desc(sB + s * TILE_BYTES + kb * KB_BYTES + k * 32);
                             tc_mma_bf16(d_tmem, ad, bd, IDESC, (kb | k) ? 1u : 0u);
                         }
@@ -359,10 +373,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
         const int ew = warp - 4;          // 0..7
         const int quad = ew & 3;          // a warp may only touch TMEM lanes [32*(warp%4), +32); warp%4 == ew%4
         const int m = ew >> 2;            // query sub-tile
-        float ls[CAND];
-        int li[CAND];
-#pragma unroll
-        for (int i = 0; i < CAND; ++i) { ls[i] = -FLT_MAX; li[i] = -1; }
+      if constexpr (COOP) {
+        // Candidate lists live in shared memory, entry-major and XOR-swizzled (entry i of query l at word
+        // i * 32 + (l ^ i): conflict-free both when every lane walks its own list and when CAND lanes hold one list),
+        // sorted descending; a thread keeps only tau, the CAND-th best score of ITS query, in a register.
+        float* ls_sm = reinterpret_cast<float*>(list_base + ew * C::LIST_BYTES);
+        int* li_sm = reinterpret_cast<int*>(ls_sm + 32 * CAND);
+        float* stage = reinterpret_cast<float*>(li_sm + 32 * CAND);
+        for (int t = lane; t < 32 * CAND; t += 32) { ls_sm[t] = -FLT_MAX; li_sm[t] = -1; }
+        __syncwarp();
         float tau = -FLT_MAX;
         // Software pipeline over the tile's four 32-column chunks: the TMEM load of
         // chunk c+1 is in flight while chunk c is scanned (two register buffers).
@@ -382,7 +401,133 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
                 tc_ld_wait();
                 if (c + 1 < TILE / 32) tc_ld32_issue(taddr + (uint32_t)((c + 1) * 32), vn);
                 const long col0 = col_tile + c * 32;
-                if (col0 + 32 > n_rows) {  // padded rows of the last tile never compete
+                const bool ragged = col0 + 32 > n_rows;
+                if (ragged) {  // padded rows of the last tile never compete
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j >= n_rows) v[j] = -FLT_MAX;
+                }
+                float mx = fmaxf(v[0], v[1]);
+#pragma unroll
+                for (int j = 2; j < 32; j += 2) mx = fmaxf(mx, fmaxf(v[j], v[j + 1]));
+                uint32_t hot = __ballot_sync(0xffffffffu, mx > tau);
+                if (hot == 0u) continue;
+                // Rare path, executed by the whole warp when ANY of its 32 queries has a score above its threshold.
+                // Per-thread insertion (tag the 32 scores with their columns, pull maxima, shift-insert) costs every
+                // lane of the warp ~350 instructions for what is usually ONE lane's single hit; on banks without
+                // structure ~38 % of the chunks come here and the kernel ran 2.4x slower.  So:
+                //  * few hot lanes (the long sparse tail of a scan): the warp serves one hot lane at a time
+                //    COOPERATIVELY - the lane drops its 32 scores into shared memory, lane j looks at column j, and a
+                //    hit is inserted by CAND lanes at once (position = number of entries >= score, the neighbours
+                //    shift by one shuffle): ~60 instructions per hot lane;
+                //  * many hot lanes (the first tiles of a scan): every lane inserts its own hits in parallel, list in
+                //    registers for the duration (shift-insert network, no carried dependency).
+                if (__popc(hot) <= coop_max) {
+                    while (hot) {
+                        const int L = __ffs(hot) - 1;
+                        hot &= hot - 1;
+                        if (lane == L) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stage + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                        __syncwarp();
+                        const float sj = stage[lane];
+                        float tauL = __shfl_sync(0xffffffffu, tau, L);
+                        uint32_t hm = __ballot_sync(0xffffffffu, sj > tauL);
+                        const bool in = lane < CAND;
+                        const int le = in ? lane : 0;
+                        float* lsL = ls_sm + le * 32 + (L ^ le);
+                        int* liL = li_sm + le * 32 + (L ^ le);
+                        while (hm) {
+                            const int j = __ffs(hm) - 1;
+                            hm &= hm - 1;
+                            const float sc = __shfl_sync(0xffffffffu, sj, j);
+                            if (!(sc > tauL)) continue;  // the threshold rose since the mask was taken (warp-uniform)
+                            const float e = in ? *lsL : -FLT_MAX;
+                            const int ei = in ? *liL : -1;
+                            const int pos = __popc(__ballot_sync(0xffffffffu, in && e >= sc));  // after its equals; < CAND as sc > tau
+                            const float eu = __shfl_up_sync(0xffffffffu, e, 1);
+                            const int eiu = __shfl_up_sync(0xffffffffu, ei, 1);
+                            const float ne = lane < pos ? e : (lane == pos ? sc : eu);
+                            const int nei = lane < pos ? ei : (lane == pos ? (int)(col0 + j) : eiu);
+                            if (in) { *lsL = ne; *liL = nei; }
+                            tauL = __shfl_sync(0xffffffffu, ne, CAND - 1);
+                        }
+                        if (lane == L) tau = tauL;
+                        __syncwarp();
+                    }
+                } else if (mx > tau) {
+                    float ls[CAND];
+                    int li[CAND];
+#pragma unroll
+                    for (int i = 0; i < CAND; ++i) { ls[i] = ls_sm[i * 32 + (lane ^ i)]; li[i] = li_sm[i * 32 + (lane ^ i)]; }
+                    float key[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float t = __uint_as_float((__float_as_uint(v[j]) & ~31u) | (uint32_t)j);
+                        key[j] = (ragged && v[j] == -FLT_MAX) ? -FLT_MAX : t;  // masked columns can never beat tau
+                    }
+#pragma unroll 1
+                    for (int guard = 0; guard < 32; ++guard) {
+                        float km = fmaxf(key[0], key[1]);
+#pragma unroll
+                        for (int j = 2; j < 32; j += 2) km = fmaxf(km, fmaxf(key[j], key[j + 1]));
+                        if (!(km > tau)) break;
+                        const int ci = (int)(col0 + (long)(__float_as_uint(km) & 31u));
+                        bool pb[CAND];
+#pragma unroll
+                        for (int i = 0; i < CAND; ++i) pb[i] = km > ls[i];
+#pragma unroll
+                        for (int i = CAND - 1; i >= 1; --i) {  // descending i: ls[i - 1] is still the old value
+                            ls[i] = pb[i] ? (pb[i - 1] ? ls[i - 1] : km) : ls[i];
+                            li[i] = pb[i] ? (pb[i - 1] ? li[i - 1] : ci) : li[i];
+                        }
+                        ls[0] = pb[0] ? km : ls[0];
+                        li[0] = pb[0] ? ci : li[0];
+                        tau = ls[CAND - 1];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) key[j] = (key[j] == km) ? -FLT_MAX : key[j];
+                    }
+#pragma unroll
+                    for (int i = 0; i < CAND; ++i) { ls_sm[i * 32 + (lane ^ i)] = ls[i]; li_sm[i * 32 + (lane ^ i)] = li[i]; }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * b);
+        }
+        __syncwarp();
+        const long q0 = ((long)qpair * MQ + m) * TILE + quad * 32;
+        float* os = cand_s + ((long)split * Q + q0) * CAND;
+        int* oi = cand_i + ((long)split * Q + q0) * CAND;
+        for (int t = lane; t < 32 * CAND; t += 32) {
+            const int ql = t / CAND, i = t % CAND;
+            if (q0 + ql < Q) { os[t] = ls_sm[i * 32 + (ql ^ i)]; oi[t] = li_sm[i * 32 + (ql ^ i)]; }
+        }
+      } else {
+        float ls[CAND];
+        int li[CAND];
+#pragma unroll
+        for (int i = 0; i < CAND; ++i) { ls[i] = -FLT_MAX; li[i] = -1; }
+        float tau = -FLT_MAX;
+        float va[32], vb[32];
+        for (int it = 0; it < n_iter; ++it) {
+            const int b = it % NACC;
+            const uint32_t bph = (uint32_t)(it / NACC) & 1u;
+            mbar_wait(bar_tfull + 8 * b, bph);
+            tc_fence_after();
+            const long col_tile = (long)(split + it * nsplit) * TILE;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((b * MQ + m) * TILE);
+            tc_ld32_issue(taddr, va);
+#pragma unroll
+            for (int c = 0; c < TILE / 32; ++c) {
+                float(&v)[32] = (c & 1) ? vb : va;
+                float(&vn)[32] = (c & 1) ? va : vb;
+                tc_ld_wait();
+                if (c + 1 < TILE / 32) tc_ld32_issue(taddr + (uint32_t)((c + 1) * 32), vn);
+                const long col0 = col_tile + c * 32;
+                const bool ragged = col0 + 32 > n_rows;
+                if (ragged) {  // padded rows of the last tile never compete
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (col0 + j >= n_rows) v[j] = -FLT_MAX;
@@ -394,31 +539,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
                     // Rare path, ONE code site (the whole warp takes it when ANY of its 32 queries has a hit): tag every
                     // score with its column (low 5 mantissa bits; costs 2^-18 relative, covered by the proof's eps),
                     // then repeatedly pull the maximum while it beats tau.  Every lane extracts ITS OWN maximum per
-                    // trip, so the trip count is the largest number of hits of any one query in this chunk - walking
-                    // the 32 columns with a per-column branch instead was tried and serialises the lanes' hits
-                    // (one 80-instruction insertion per distinct column: 3-9x slower on insert-heavy small batches).
+                    // trip, so the trip count is the largest number of hits of any one query in this chunk.
+                    // The insertion is a shift-insert NETWORK: all CAND comparisons against the new score are
+                    // independent, entry i becomes (score beats i) ? ((score beats i-1) ? old i-1 : score) : old i.
+                    // The first version carried the displaced element through CAND dependent compare-exchange steps
+                    // - a ~250-cycle latency chain per hit that two warps per scheduler cannot hide (banks without
+                    // structure, where ~38 % of the chunks come here, ran 2.4x slower).
                     float key[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)  // masked (padded) columns stay at -FLT_MAX and can never beat tau
-                        key[j] = v[j] == -FLT_MAX ? -FLT_MAX : __uint_as_float((__float_as_uint(v[j]) & ~31u) | (uint32_t)j);
+                    for (int j = 0; j < 32; ++j) {
+                        const float t = __uint_as_float((__float_as_uint(v[j]) & ~31u) | (uint32_t)j);
+                        key[j] = (ragged && v[j] == -FLT_MAX) ? -FLT_MAX : t;  // masked columns can never beat tau
+                    }
 #pragma unroll 1
                     for (int guard = 0; guard < 32; ++guard) {
                         float km = fmaxf(key[0], key[1]);
 #pragma unroll
                         for (int j = 2; j < 32; j += 2) km = fmaxf(km, fmaxf(key[j], key[j + 1]));
                         if (!(km > tau)) break;
-                        float cs = km;
-                        int ci = (int)(col0 + (long)(__float_as_uint(km) & 31u));
+                        const int ci = (int)(col0 + (long)(__float_as_uint(km) & 31u));
+                        bool pb[CAND];
 #pragma unroll
-                        for (int i = 0; i < CAND; ++i) {  // insert into the descending list, dropping the last
-                            const bool gt = cs > ls[i];
-                            const float ts = gt ? ls[i] : cs;
-                            const int ti = gt ? li[i] : ci;
-                            ls[i] = gt ? cs : ls[i];
-                            li[i] = gt ? ci : li[i];
-                            cs = ts;
-                            ci = ti;
+                        for (int i = 0; i < CAND; ++i) pb[i] = km > ls[i];
+#pragma unroll
+                        for (int i = CAND - 1; i >= 1; --i) {  // descending i: ls[i - 1] is still the old value
+                            ls[i] = pb[i] ? (pb[i - 1] ? ls[i - 1] : km) : ls[i];
+                            li[i] = pb[i] ? (pb[i - 1] ? li[i - 1] : ci) : li[i];
                         }
+                        ls[0] = pb[0] ? km : ls[0];
+                        li[0] = pb[0] ? ci : li[0];
                         tau = ls[CAND - 1];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) key[j] = (key[j] == km) ? -FLT_MAX : key[j];
@@ -435,6 +584,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_candidates_kernel(const ui
 #pragma unroll
             for (int i = 0; i < CAND; ++i) { os[i] = ls[i]; oi[i] = li[i]; }
         }
+      }
     }
     tc_fence_before();
     __syncthreads();
@@ -601,7 +751,8 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 template <int KBLK, int CAND>
 int set_candidates_attr() {
-    RF_SMEM_OPT_IN((knn_tc_candidates_kernel<KBLK, CAND>), Cfg<KBLK>::SMEM_BYTES);
+    RF_SMEM_OPT_IN((knn_tc_candidates_kernel<KBLK, CAND, 0>), (Cfg<KBLK, CAND>::SMEM_BYTES));
+    RF_SMEM_OPT_IN((knn_tc_candidates_kernel<KBLK, CAND, 1>), (Cfg<KBLK, CAND>::SMEM_BYTES));
     return 0;
 }
 
@@ -707,8 +858,16 @@ int launch_candidates(const TcLayout& L, const uint8_t* q_img, const uint8_t* ba
                       int* cand_i, cudaStream_t s) {
     if (int rc = set_candidates_attr<KBLK, CAND>()) return rc;
     dim3 grid(L.n_qpairs, L.nsplit);
-    knn_tc_candidates_kernel<KBLK, CAND><<<grid, NTHREADS, Cfg<KBLK>::SMEM_BYTES, s>>>(q_img, bank_img, Q, n_rows, L.n_qtiles,
-                                                                                      L.n_btiles, L.nsplit, cand_s, cand_i);
+    // tuning aids: RF_KNN_COOP=0 selects the register-list kernel, RF_KNN_COOP_MAX the largest number of hot lanes
+    // the cooperative insertion serves before the per-lane path takes over
+    static const int coop = [] { const char* e = getenv("RF_KNN_COOP"); return e ? atoi(e) : 1; }();
+    static const int coop_max = [] { const char* e = getenv("RF_KNN_COOP_MAX"); return e ? atoi(e) : 2; }();
+    if (coop)
+        knn_tc_candidates_kernel<KBLK, CAND, 1><<<grid, NTHREADS, Cfg<KBLK, CAND>::SMEM_BYTES, s>>>(q_img, bank_img, Q, n_rows, L.n_qtiles,
+                                                                                             L.n_btiles, L.nsplit, cand_s, cand_i, coop_max);
+    else
+        knn_tc_candidates_kernel<KBLK, CAND, 0><<<grid, NTHREADS, Cfg<KBLK, CAND>::SMEM_BYTES, s>>>(q_img, bank_img, Q, n_rows, L.n_qtiles,
+                                                                                             L.n_btiles, L.nsplit, cand_s, cand_i, coop_max);
     RF_LAUNCH_OK("knn_tc_candidates_kernel");
     return 0;
 }

@@ -151,7 +151,9 @@ def test_tc_linear(dev, M, K, N, act):
 # (N, S, C1, C2, Cout, out_ncdhw): every item geometry of rf_tc_conv_halo.cu - "lines" and "linear" row modes, whole
 # stacked samples (ragged last item), d/h slabs, the single-chunk tap-pairing mode, odd chunk counts, Npad 128
 HALO_CASES = [(5, 8, 16, 0, 32, 0), (3, 8, 32, 64, 56, 0), (7, 4, 64, 128, 64, 0), (3, 16, 8, 0, 16, 0), (2, 8, 56, 0, 16, 1),
-              (9, 2, 64, 0, 128, 0), (1, 32, 0, 16, 16, 1), (2, 16, 12, 24, 24, 0), (300, 8, 16, 0, 32, 0), (301, 4, 32, 0, 32, 0)]
+              (9, 2, 64, 0, 128, 0), (1, 32, 0, 16, 16, 1), (2, 16, 12, 24, 24, 0), (300, 8, 16, 0, 32, 0), (301, 4, 32, 0, 32, 0),
+              # shared-halo stacked items: tap-pairing mode, ragged last item with many samples per item, 2^3 and 4^3
+              (37, 2, 8, 0, 16, 0), (21, 4, 8, 0, 16, 0), (41, 2, 64, 0, 64, 0), (11, 4, 16, 32, 24, 1)]
 
 
 @pytest.mark.parametrize("N,S,C1,C2,Cout,ncdhw", HALO_CASES)
