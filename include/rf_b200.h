@@ -153,19 +153,19 @@ int rf_tc_conv3d_fwd(const void* x_hi, const void* x_lo, int C1, const void* x2_
 
 /* "Shifted window" variant of the tensor-core convolution for the 3x3x3 / stride 1 /
  * pad 1 layers of the U-Nets (model/unet.py:19-100 create_conv 'gcr'): the
- * normalised activations are written once as fp16 hi / lo slot planes with a zero
- * halo, [channel chunk][N][D+2][H+2][W+2] x 16 B (one slot = 8 channels of a voxel;
- * x2, when given, is nearest-upsampled and concatenated after x's channels, each
- * source padded to 8 channels; the chunk count is padded to an even number unless
- * it is 1), and the convolution kernel stages a patch / slab of those planes in
- * shared memory once, addressing all 27 taps in place through no-swizzle UMMA
+ * normalised activations are written once as COMPACT fp16 hi / lo slot planes,
+ * [channel chunk][N][D][H][W] x 16 B (one slot = 8 channels of a voxel; x2, when
+ * given, is nearest-upsampled and concatenated after x's channels, each source
+ * padded to 8 channels), and the convolution kernel stages a patch / slab of those
+ * planes WITH its halo in shared memory through TMA tile loads (the box starts one
+ * voxel outside the volume; out-of-bounds slots are zero-filled, so the padding
+ * never exists in HBM), addressing all 27 taps in place through no-swizzle UMMA
  * descriptors (no im2col).  rf_halo_act_bytes = size of ONE of hi / lo.
  * rf_tc_conv3d_halo_supported tells whether an item shape fits shared memory and
  * TMEM for this layer; callers use rf_tc_conv3d_fwd otherwise.  D, H, W are the
- * INPUT extents; pad = 1 ('same', the U-Nets; zero halo written by the split kernel)
- * or 0 ('valid', the conv patch encoders of model/retrieval.py: no halo, output
- * extents D-2).  interior_only = 1: hi / lo are caller-owned buffers that were zeroed once and whose halo
- * nobody writes; only the interior slots are written (the halo is half of an 8^3 patch's slots).
+ * INPUT extents; pad = 1 ('same', the U-Nets) or 0 ('valid', the conv patch
+ * encoders of model/retrieval.py: output extents D-2).  interior_only is ignored
+ * (kept for ABI stability: the planes had a halo in the first version).
  * y is fp32 channels-last [N,Do,Ho,Wo,Cout] or NCDHW. */
 size_t rf_halo_act_bytes(int N, int D, int H, int W, int C1, int C2, int pad);
 int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a,
@@ -179,6 +179,24 @@ int rf_tc_conv3d_halo_debug_read(long long* out64); /* tuning aid: phase timesta
 int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D,
                           int H, int W, int pad, int Cout, int C1, int C2, int act, float slope, float out_scale,
                           int out_ncdhw, void* stream);
+
+/* Single-input-channel layers on the same kernel (the first Conv3d of every patch
+ * encoder, model/retrieval.py:4-388, kernel edge 3 or 5, no padding; the first
+ * SingleConv of the U-Nets, model/unet.py:79-100, 3^3 'same'): the slot of voxel
+ * (d,h,p) holds the 8 consecutive values x[d,h,p-pad .. p-pad+7] of its line
+ * ("W-run", zero outside the line, GroupNorm(1 group) applied first when gn_* are
+ * given), so one 16-byte K chunk carries all kw taps of a (kd,kh) line and a K = 16
+ * MMA step two lines: 5 steps for 3^3, 13 for 5^3.  D, H, W: INPUT extents; planes
+ * [N][D][H][Wo] slots, Wo = W + 2 pad - KS + 1; y fp32 channels-last [N,Do,Ho,Wo,Cout]. */
+size_t rf_wrun_act_bytes(int N, int D, int H, int W, int KS, int pad);
+int rf_cl_norm_split_wrun(const float* x, const float* gn_mu, const float* gn_a, const float* gn_beta, void* hi, void* lo,
+                          int N, int D, int H, int W, int KS, int pad, float scale, void* stream);
+size_t rf_tc_conv_wrun_weight_image_bytes(int Cout, int KS);
+int rf_tc_conv_wrun_weight_image(const float* w, int Cout, int KS, float scale, void* image, void* stream);
+int rf_tc_conv3d_wrun_supported(int N, int D, int H, int W, int Cout, int KS, int pad);
+int rf_tc_conv3d_wrun_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D,
+                          int H, int W, int KS, int pad, int Cout, int act, float slope, float out_scale, int out_ncdhw,
+                          void* stream);
 
 /* First layers (single input channel: the TSDF / occupancy volume): direct
  * convolution, one thread per output voxel, filter bank in shared memory,

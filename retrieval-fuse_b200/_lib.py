@@ -69,6 +69,14 @@ PROTOTYPES = {
     "rf_tc_conv3d_halo_debug_read": (c_int, [c_void_p]),
     "rf_tc_conv3d_halo_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
+    "rf_wrun_act_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "rf_cl_norm_split_wrun": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_float, c_void_p]),
+    "rf_tc_conv_wrun_weight_image_bytes": (c_size_t, [c_int, c_int]),
+    "rf_tc_conv_wrun_weight_image": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "rf_tc_conv3d_wrun_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "rf_tc_conv3d_wrun_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_int, c_float, c_float, c_int, c_void_p]),
     "rf_cl_pointwise_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_float, c_void_p]),
     "rf_conv3d_cin1_cl_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),

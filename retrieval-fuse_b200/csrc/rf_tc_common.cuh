@@ -127,6 +127,14 @@ __device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, float* v) {
         : "memory");
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Ties 16 registers that an earlier tc_ld16_issue filled to this point of the program: arithmetic on them cannot be
+// scheduled above it (place it right after tc_ld_wait when other work sits between the issue and the wait).
+__device__ __forceinline__ void tc_ld_fence16(float* v) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                 "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :
+                 : "memory");
+}
 // instruction descriptor: D f32, A/B f16, both K-major, N >> 3 at bit 17, M (128) >> 4 at bit 24
 __device__ __forceinline__ uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
 // x = hi + lo + r with hi, lo fp16: |r| <= 2^-24 |x| for |x| in fp16's normal range (the operands here are

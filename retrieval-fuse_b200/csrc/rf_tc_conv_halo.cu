@@ -149,35 +149,56 @@ __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs
     }
 }
 
-// ------------------------------------------------------------------ weight image
-// [stage][(kd,kh) group][k step][K chunk][hi rows | lo rows (Npad each)][16 B]; a ring slot of the conv kernel = one group.
-// normal: k step = kw, K chunk c <-> channel chunk 2*stage + c.   pair (one channel chunk): k step 0 = taps
-// kw 0 (chunk 0) and kw 1 (chunk 1); k step 1 = tap kw 2 (chunk 0) and zeros.
-__global__ void __launch_bounds__(256) halo_weight_image_kernel(const float* __restrict__ w, int Cout, int C1, int C2, int Cp1,
-                                                                int Cp2, int Npad, int n_stages, int pair, float scale,
+// ------------------------------------------------------------------ layer modes and the weight image
+// A K = 16 step of the MMA reads two 16-byte chunks per GEMM row: the slot at the step's offset and the slot LBO
+// further.  What the two chunks are depends on the layer:
+//   mode 0 (>= 2 channel chunks): one tap, the two chunk planes of a channel-chunk pair ("stage"); 27 steps per stage;
+//   mode 1 (one channel chunk, C <= 8): two neighbouring TAPS of the same plane (LBO = one slot): (kw 0, kw 1) and
+//          (kw 2, zeros) per (kd,kh) line, 18 steps (pairing across lines, 14 steps with other LBOs, measured slower:
+//          8 -> 16 @ 16^3 3.98 -> 4.43 ms);
+//   mode 2 (ONE input channel, kernel edge 3 or 5): the slot of voxel w holds the 8 consecutive values x[w .. w+7] of
+//          its line ("W-run", written by rf_cl_norm_split_wrun), so one chunk carries all kw taps of a (kd,kh) line and
+//          a step pairs two lines: 5 steps for 3^3, 13 for 5^3 - the single-channel first layers of the U-Nets and
+//          patch encoders on tensor cores instead of the fp32 FMA kernel.
+// Steps are grouped kpg at a time into the weight ring's slots (n_groups groups per stage; padded steps carry zero
+// weights).  Image: [stage][group][k step][K chunk][hi rows | lo rows (Npad each)][16 B].
+struct Layer {
+    int mode, KS;
+    int C1, C2, Cp1, Cp2, CC, CCe, Cout, Npad;
+    int ck, n_stages, kpg, n_groups;
+    int hd, hw;  // block extent beyond the output extent: D / H (KS - 1) and W (KS - 1; 0 in mode 2)
+};
+
+__global__ void __launch_bounds__(256) halo_weight_image_kernel(const float* __restrict__ w, const Layer L, float scale,
                                                                 uint8_t* __restrict__ img) {
-    const int kpg = pair ? 2 : 3, Cin = C1 + C2;
-    const long total = (long)n_stages * 9 * kpg * 2 * Npad;
+    const int Cin = L.C1 + L.C2, Npad = L.Npad, kpg = L.kpg, taps = L.KS * L.KS * L.KS;
+    const long total = (long)L.n_stages * L.n_groups * kpg * 2 * Npad;
     const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (gid >= total) return;
     long t = gid;
     const int n = (int)(t % Npad); t /= Npad;
     const int kc = (int)(t % 2); t /= 2;
     const int ks = (int)(t % kpg); t /= kpg;
-    const int g = (int)(t % 9);
-    const int st = (int)(t / 9);
-    int kw, cc;
-    if (pair) { kw = ks * 2 + kc; cc = 0; } else { kw = ks; cc = st * 2 + kc; }
+    const int g = (int)(t % L.n_groups);
+    const int st = (int)(t / L.n_groups);
+    const int idx = g * kpg + ks;
     uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
-    if (n < Cout && kw < 3 && cc * 8 < Cp1 + Cp2) {
-        const int tap = g * 3 + kw;
+    if (n < L.Cout) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int cs = cc * 8 + e;
-            int ci = -1;
-            if (cs < Cp1) { if (cs < C1) ci = cs; }
-            else if (cs - Cp1 < C2) ci = C1 + (cs - Cp1);
-            const float val = ci >= 0 ? w[((long)n * Cin + ci) * 27 + tap] * scale : 0.f;
+            float val = 0.f;
+            if (L.mode == 2) {
+                const int line = 2 * idx + kc;  // (kd, kh); element e of the chunk <-> kw
+                if (line < L.KS * L.KS && e < L.KS) val = w[(long)n * taps + line * L.KS + e] * scale;
+            } else {
+                // mode 1: step 2 l = taps (kw 0, kw 1) of line l = (kd, kh), step 2 l + 1 = (kw 2, zeros)
+                const int tap = L.mode == 1 ? ((idx & 1) && kc ? 27 : (idx >> 1) * 3 + (idx & 1) * 2 + kc) : idx;
+                const int cs = (L.mode == 1 ? 0 : st * 2 + kc) * 8 + e;
+                int ci = -1;
+                if (cs < L.Cp1) { if (cs < L.C1) ci = cs; }
+                else if (cs - L.Cp1 < L.C2) ci = L.C1 + (cs - L.Cp1);
+                if (tap < 27 && ci >= 0) val = w[((long)n * Cin + ci) * 27 + tap] * scale;
+            }
             uint32_t hv, lv;
             split_f16(val, hv, lv);
             hi[e >> 1] |= hv << (16 * (e & 1));
@@ -187,7 +208,7 @@ __global__ void __launch_bounds__(256) halo_weight_image_kernel(const float* __r
     // one k step = a K-major operand of 2*Npad rows: rows [0, Npad) the hi parts, rows [Npad, 2 Npad) the lo parts, so
     // that [W_hi; W_lo] can be ONE N = 2 Npad operand (LBO = 2 Npad * 16 B between the two K chunks)
     const long step = (long)Npad * 64;
-    uint8_t* base = img + ((long)(st * 9 + g) * kpg + ks) * step + (long)kc * (2L * Npad * 16) + (long)n * 16;
+    uint8_t* base = img + ((long)(st * L.n_groups + g) * kpg + ks) * step + (long)kc * (2L * Npad * 16) + (long)n * 16;
     *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(base + (long)Npad * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
@@ -207,11 +228,12 @@ struct HaloArgs {
     int n_dt, n_ht, Ls;           // slabs per sample; lines per stacked sample (Dp * Hp)
     int lines, n_wblk, n_tiles, P;  // P = slots per staged plane (incl. over-read slack)
     int S_st;                     // staged slots per plane that the bulk copies fill
-    int pair, n_stages, nbuf, ck, kpg;
+    int n_stages, nbuf, ck, kpg, n_groups, w0;  // w0: W coordinate of the block's first slot (-pad; 0 for W-runs)
     int Cout, Npad, act, out_ncdhw, n_iss, n_items, n_sets, fused;
     float slope, out_scale;
     uint32_t bslot_bytes, tmem_cols;
     uint16_t tile_off[32];        // first slot of M tile t within the staged block (uniform-indexed constant loads)
+    uint32_t ktab[32];            // k step -> slot offset of its first chunk | (slots to its second chunk) << 16
 };
 
 // Persistent: CTA c walks over items c, c + gridDim.x, ...  Barriers, TMEM and the zeroed staging buffers are set
@@ -222,8 +244,11 @@ struct HaloArgs {
 //
 // tm_hi / tm_lo: 4-D tensor maps of the compact hi / lo planes, dims (2 W 8-byte words, H, D, CC * N), box = the
 // haloed block of one item (2 (W+2), Hs, Dt+2, G); coordinates that fall outside are zero-filled by the TMA unit.
-__global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tm_hi,
-                                                                     const __grid_constant__ CUtensorMap tm_lo) {
+// RES = CTAs per SM the register budget allows: 2 (64 registers; small items whose shared memory lets two CTAs share
+// an SM) or 1 (128 registers: the epilogue keeps the next accumulator block in flight).
+template <int RES, int PIPE>
+__global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tm_hi,
+                                                                       const __grid_constant__ CUtensorMap tm_lo) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
@@ -308,8 +333,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
                     // a padding chunk (cc >= CC) or the samples past N of a ragged last item lie outside the tensor: zeros
                     const int plane = cc < a.CC ? cc * a.N + n0 : a.CC * a.N;
                     const uint32_t dst = sA + b * abuf_bytes + (uint32_t)pl * (uint32_t)a.P * 16u;
-                    if (a.tm5) tma_load_5d(dst, hl ? &tm_lo : &tm_hi, 0, -a.pad, h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
-                    else tma_load_4d(dst, hl ? &tm_lo : &tm_hi, -2 * a.pad, h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
+                    if (a.tm5) tma_load_5d(dst, hl ? &tm_lo : &tm_hi, 0, a.w0, h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
+                    else tma_load_4d(dst, hl ? &tm_lo : &tm_hi, 2 * a.w0, h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
                 }
             }
         }
@@ -317,7 +342,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
     } else if (warp == 3) {
       if (lane == 0) {
         // ---- weight producer: ring of (kd,kh) groups; the second pass of every item streams the same groups again
-        const int per_pass = a.n_stages * 9, n_pass = a.fused ? 1 : 2;
+        const int per_pass = a.n_stages * a.n_groups, n_pass = a.fused ? 1 : 2;
         uint32_t gc = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x)
             for (int gi = 0; gi < n_pass * per_pass; ++gi, ++gc) {
@@ -343,7 +368,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
             // descriptor = {lo: start >> 4 | (LBO >> 4) << 16, hi: SBO >> 4 | version 1 << 14}; addresses advance in
             // 16-byte units = slots, so "+ slots" on the low word moves the window.
             const uint32_t a_hi32 = (a.lines ? (uint32_t)a.Wp : 8u) | (1u << 14);
-            const uint32_t a_lbo = (a.pair ? 1u : (uint32_t)a.P) << 16;
             const uint32_t b_hi32 = 8u | (1u << 14);
             const uint32_t b_lbo = (uint32_t)(2 * a.Npad) << 16;  // K chunks of a k step are 2 Npad rows apart
             const uint32_t step_u = (uint32_t)a.Npad * 4u;        // one k step of weights, in 16-byte units
@@ -374,20 +398,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
                         tc_fence_after();
                         if (dbg && vs == 0) g_halo_dbg[it * 8 + 2] = clock64();
                     }
-                    const uint32_t abase = (((sA + b * abuf_bytes) & 0x3FFFFu) >> 4) | a_lbo;
-                    for (int g = 0; g < 9; ++g, ++gc) {
+                    const uint32_t abase = ((sA + b * abuf_bytes) & 0x3FFFFu) >> 4;
+                    // k step table entry (slot offset | LBO << 16, added to the descriptor's low word), fetched one
+                    // step ahead: the issue loop is latency-critical, a load in front of every step's first MMA cost 4 %
+                    uint32_t kt_next = a.ktab[0];
+                    int kidx = 0;
+                    for (int g = 0; g < a.n_groups; ++g, ++gc) {
                         const uint32_t sl = gc % NB;
                         mbar_wait_warp_backoff(bar_bfull + 8 * sl, (gc / NB) & 1u, 40);
                         tc_fence_after();
-                        const int kd = g / 3, kh = g % 3;
                         const uint32_t bbase = (((sB + sl * a.bslot_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                         for (int ks = 0; ks < a.kpg; ++ks) {
-                            const uint32_t koff = (uint32_t)((kd * a.Hs + kh) * a.Wp + (a.pair ? 2 * ks : ks));
+                            const uint32_t kt = kt_next;
+                            kidx = kidx + 1 < 32 ? kidx + 1 : 31;
+                            kt_next = a.ktab[kidx];
                             const uint32_t b_hi = bbase + (uint32_t)ks * step_u, b_lo = b_hi + npad;  // lo rows follow the hi rows
                             const uint32_t acc = (vs | g | ks) ? 1u : 0u;  // the very first MMA of a tile overwrites its accumulator
                             for (int t = iss; t < a.n_tiles; t += a.n_iss) {
                                 const uint32_t d = tmem_u + set * set_cols + (uint32_t)t * tile_cols;
-                                const uint32_t da = abase + koff + a.tile_off[t];
+                                const uint32_t da = abase + kt + a.tile_off[t];
                                 if (a.fused) {
                                     // A_hi x [W_hi; W_lo] as ONE N = 2 Npad MMA -> columns [main | cross]; A_lo x W_hi into
                                     // the cross block.  For N <= 64 the pipe time is set by reading the A operand, so
@@ -435,45 +464,77 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_conv3d_halo_kernel(const HaloA
             mbar_wait_warp_sleepy(bar_dfull + 8 * set, use & 1u);
             tc_fence_after();
             if (dbg) g_halo_dbg[it * 8 + 5] = clock64();
-            for (int t = half; t < a.n_tiles; t += 2) {
+            // (tile, 16-column block) pairs of this warp, software-pipelined: the TMEM loads of the next pair are in
+            // flight while the current one is scaled, activated and stored (one pair took ~1200 cycles of exposed
+            // TMEM latency + store issue; small-Cout layers were bound by this loop, not by the MMAs)
+            const int nblk = a.Npad >> 4;
+            const int n_my = ((a.n_tiles - half + 1) >> 1) * nblk;
+            auto issue = [&](int j, float* v, float* u) {
+                const int t = half + 2 * (j / nblk), c0 = (j % nblk) << 4;
+                const uint32_t ta = tm_set + ((uint32_t)(q * 32) << 16) + (uint32_t)t * tile_cols + (uint32_t)c0;
+                tc_ld16_issue(ta, v);
+                if (a.fused) tc_ld16_issue(ta + (uint32_t)a.Npad, u);  // main + cross blocks
+            };
+            auto process = [&](int j, float* v, float* u) {
+                tc_ld_fence16(v);
+                const int t = half + 2 * (j / nblk), c0 = (j % nblk) << 4;
+                if (a.fused) {
+                    tc_ld_fence16(u);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] += u[e];
+                }
+                if (dbg && t == 0 && c0 == 0) g_halo_dbg[it * 8 + 7] = clock64();
+                if (dbg && t == 2 && c0 == 0) g_halo_dbg[48 + it] = clock64();
                 const int rt = row_tab[t * TM + q * 32 + lane];
                 const bool valid = rt >= 0 && (rt >> 26) < gact;
+                if (!valid) return;
                 const long vox = vox0 + (rt & 0x3FFFFFF);
-                for (int c0 = 0; c0 < a.Npad; c0 += 16) {
-                    float v[16];
-                    tc_ld16(tm_set + ((uint32_t)(q * 32) << 16) + (uint32_t)t * tile_cols + (uint32_t)c0, v);
-                    if (a.fused) {  // main + cross blocks
-                        float u[16];
-                        tc_ld16(tm_set + ((uint32_t)(q * 32) << 16) + (uint32_t)t * tile_cols + (uint32_t)(a.Npad + c0), u);
+                if (a.bias) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] += u[e];
+                    for (int e = 0; e < 16; ++e) v[e] = fmaf(v[e], a.out_scale, c0 + e < a.Cout ? __ldg(a.bias + c0 + e) : 0.f);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] *= a.out_scale;
+                }
+                float w16[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) w16[e] = v[e];
+                rf_act_vec(w16, a.act, a.slope);
+                if (vec4) {
+                    float* dst = a.y + vox * a.Cout + c0;
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4)
+                        if (c0 + e < a.Cout) *reinterpret_cast<float4*>(dst + e) = make_float4(w16[e], w16[e + 1], w16[e + 2], w16[e + 3]);
+                } else if (a.out_ncdhw) {
+                    const long nn = vox / So, sp = vox % So;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (c0 + e < a.Cout) a.y[(nn * a.Cout + c0 + e) * So + sp] = w16[e];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (c0 + e < a.Cout) a.y[vox * a.Cout + c0 + e] = w16[e];
+                }
+            };
+            if constexpr (PIPE == 1) {
+                float v0[16], u0[16], v1[16], u1[16];
+                if (n_my > 0) issue(0, v0, u0);
+                for (int j = 0; j < n_my; j += 2) {
+                    tc_ld_wait();
+                    if (j + 1 < n_my) issue(j + 1, v1, u1);
+                    process(j, v0, u0);
+                    if (j + 1 < n_my) {
+                        tc_ld_wait();
+                        if (j + 2 < n_my) issue(j + 2, v0, u0);
+                        process(j + 1, v1, u1);
                     }
-                    if (dbg && t == 0 && c0 == 0) g_halo_dbg[it * 8 + 7] = clock64();
-                    if (dbg && t == 2 && c0 == 0) g_halo_dbg[48 + it] = clock64();
-                    if (!valid) continue;
-                    if (a.bias) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] = fmaf(v[e], a.out_scale, c0 + e < a.Cout ? __ldg(a.bias + c0 + e) : 0.f);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] *= a.out_scale;
-                    }
-                    rf_act_vec(v, a.act, a.slope);
-                    if (vec4) {
-                        float* dst = a.y + vox * a.Cout + c0;
-#pragma unroll
-                        for (int e = 0; e < 16; e += 4)
-                            if (c0 + e < a.Cout) *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-                    } else if (a.out_ncdhw) {
-                        const long nn = vox / So, sp = vox % So;
-#pragma unroll
-                        for (int e = 0; e < 16; ++e)
-                            if (c0 + e < a.Cout) a.y[(nn * a.Cout + c0 + e) * So + sp] = v[e];
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e)
-                            if (c0 + e < a.Cout) a.y[vox * a.Cout + c0 + e] = v[e];
-                    }
+                }
+            } else {
+                float v0[16], u0[16];
+                for (int j = 0; j < n_my; ++j) {
+                    issue(j, v0, u0);
+                    tc_ld_wait();
+                    process(j, v0, u0);
                 }
             }
             tc_fence_before();
@@ -510,18 +571,19 @@ EncodeTiledFn encode_tiled_fn() {
 
 struct Geo {
     int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, two_resident, n_sets, fused;
-    int halo;  // 2: every sample / slab carries its own halo; 1 (stacked, 'same' padding): neighbours share it
+    int halo;  // 0: every sample / slab carries its own halo; 1 (stacked, 'same' padding): neighbours share it
+    int hd, hw;  // extent of the item's block beyond its outputs in D / H and in W
     uint32_t tmem_cols, bslot;
     size_t smem;
     double score;
 };
 
 // Chooses the item shape: maximise (real outputs / computed GEMM rows), penalise grids that leave SMs idle.
-bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, int pad, Geo& best) {
-    const int ck = pair ? 1 : 2, planes = 2 * ck, kpg = pair ? 2 : 3;
-    const int n_stages = pair ? 1 : CCe / 2;
+bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& best) {
+    const int planes = 2 * L.ck, kpg = L.kpg, n_stages = L.n_stages, Npad = L.Npad;
     const uint32_t bslot = (uint32_t)kpg * 2u * (uint32_t)Npad * 32u;
     const long avail_all = (long)SMEM_LIMIT - 1024 - 256 - (long)NB * bslot;
+    const bool shareable = pad == 1 && L.KS == 3 && L.mode != 2;  // zero padding of one voxel all around
     best.score = -1.0;
     // halo = 1 ("shared halo", stacked whole samples with zero padding only): the TMA box starts one voxel before the
     // volume and ends AT its far faces, so a sample occupies (D+1)(H+1)(W+1) slots whose index-0 faces are zero: the
@@ -529,21 +591,24 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, in
     // sample (the zeroed slack behind the block for the last sample).  51 % of the rows of stacked 4^3 patches are
     // real outputs instead of 30 %.
     auto consider = [&](int stacked, int G, int Dt, int Ht, int lines, int halo) {
-        const int Dp = D + halo, Hp = H + halo, Wp = W + halo;
+        const int hd = halo ? 1 : L.hd, hw = halo ? 1 : L.hw;
+        const int Dp = D + hd, Hp = H + hd, Wp = W + hw;
         const long V = (long)Dp * Hp * Wp;
-        const int Hs = stacked ? Hp : Ht + 2;
-        const long S_st = stacked ? (long)G * V : (long)(Dt + 2) * Hs * Wp;
+        const int Hs = stacked ? Hp : Ht + L.hd;
+        const long S_st = stacked ? (long)G * V : (long)(Dt + L.hd) * Hs * Wp;
+        // furthest slot a row reads beyond its own: the last tap (second chunk of the last k step included)
+        const long reach = ((long)(L.KS - 1) * Hs + (L.KS - 1)) * Wp + (L.mode == 2 ? 0 : L.KS - 1) + 1;
         const long lines_needed = stacked ? (long)(G - 1) * Dp * Hp + (long)(D - 1) * Hp + H : (long)(Dt - 1) * Hs + Ht;
         long n_tiles, max_slot;
         const int n_wblk = lines ? (W + 7) / 8 : 1;
         if (lines) {
             const long lb = (lines_needed + 15) / 16;
             n_tiles = lb * n_wblk;
-            max_slot = (lb * 16 - 1 + 2L * Hs + 2) * Wp + (n_wblk * 8 - 1) + 2 + 1;
+            max_slot = (lb * 16 - 1) * Wp + (n_wblk * 8 - 1) + reach;
         } else {
             const long rows = (lines_needed - 1) * Wp + W;
             n_tiles = (rows + 127) / 128;
-            max_slot = n_tiles * 128 - 1 + 2L * Hs * Wp + 2L * Wp + 2 + 1;
+            max_slot = n_tiles * 128 - 1 + reach;
         }
         long P = max_slot + 1 > S_st ? max_slot + 1 : S_st;
         P = (P + 7) / 8 * 8;
@@ -562,7 +627,7 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, in
         // cycles per (tile pair, 16 columns), and every item pays ~3000 cycles of pipeline fill.  Accumulators are
         // double-buffered (epilogue of item i under the MMAs of item i+1) when two sets fit TMEM; otherwise a second
         // resident CTA hides part of the epilogue.
-        const double k_steps = (double)n_stages * 9 * kpg * (double)n_tiles;  // (k step, tile) pairs of one item
+        const double k_steps = (double)n_stages * L.n_groups * kpg * (double)n_tiles;  // (k step, tile) pairs of one item
         const int n_iss = n_tiles < 6 ? (int)n_tiles : 6;
         const double waves = (double)((n_items + 147) / 148);   // items every SM walks through (the tensor pipe is per SM)
         auto pipe_cycles = [](int n) { return n <= 32 ? 40.0 : n <= 64 ? 48.0 : n <= 128 ? 64.0 : 128.0; };
@@ -578,7 +643,8 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, in
                 uint32_t cols_needed = 32;
                 while ((long)cols_needed < n_tiles * tile_cols * n_sets) cols_needed <<= 1;
                 const long smem_total = 1024 + smemA + (long)NB * bslot + 256 + n_tiles * 512;
-                const bool two_resident = smem_total <= 113 * 1024 && cols_needed <= 256;
+                static const int force_res = [] { const char* e = getenv("RF_HALO_RES"); return e ? atoi(e) : 0; }();  // tuning aid
+                const bool two_resident = force_res != 1 && smem_total <= 113 * 1024 && cols_needed <= 256;
                 const double issue = 150.0 / (n_iss * (two_resident ? 2 : 1));
                 const double per_step = fused ? fmax(pipe_cycles(2 * Npad), issue) + fmax(pipe_cycles(Npad), issue)
                                               : 3.0 * fmax(pipe_cycles(Npad), issue);
@@ -592,7 +658,7 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, in
                     best.lines = lines; best.n_wblk = n_wblk; best.n_tiles = (int)n_tiles; best.P = (int)P; best.S_st = (int)S_st;
                     best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot; best.two_resident = two_resident ? 1 : 0;
                     best.tmem_cols = cols_needed;
-                    best.n_sets = n_sets; best.fused = fused; best.halo = halo;
+                    best.n_sets = n_sets; best.fused = fused; best.halo = halo; best.hd = hd; best.hw = hw;
                     best.smem = (size_t)smem_total;
                     best.score = score;
                 }
@@ -600,52 +666,166 @@ bool choose_geometry(int N, int D, int H, int W, int CCe, int pair, int Npad, in
         }
     };
     if (const char* e = getenv("RF_HALO_GEO")) {  // tuning aid: "stacked,G,Dt,Ht,lines" forces the item shape
-        int st, G, Dt, Ht, ln, hl = 2;
+        int st, G, Dt, Ht, ln, hl = 0;
         if (sscanf(e, "%d,%d,%d,%d,%d,%d", &st, &G, &Dt, &Ht, &ln, &hl) >= 5) {
-            consider(st, G, st ? D : Dt, st ? H : Ht, ln, st && pad == 1 && hl == 1 ? 1 : 2);
+            consider(st, G, st ? D : Dt, st ? H : Ht, ln, st && shareable && hl == 1 ? 1 : 0);
             return best.score > 0.0;
         }
     }
     for (int lines = 0; lines < 2; ++lines) {
         for (int G = 1; G <= 32 && G <= N; ++G) {  // (the row table keeps the stacked sample index in 5 bits)
-            consider(1, G, D, H, lines, 2);
-            if (pad == 1) consider(1, G, D, H, lines, 1);
+            consider(1, G, D, H, lines, 0);
+            if (shareable) consider(1, G, D, H, lines, 1);
         }
         for (int Dt = 1; Dt <= D; ++Dt) {
             if (D % Dt) continue;
             for (int Ht = 1; Ht <= H; ++Ht) {
                 if (H % Ht) continue;
-                consider(0, 1, Dt, Ht, lines, 2);
+                consider(0, 1, Dt, Ht, lines, 0);
             }
         }
     }
     return best.score > 0.0;
 }
 
-bool halo_shape(int Cout, int C1, int C2, int& Cp1, int& Cp2, int& CC, int& CCe, int& pair, int& Npad) {
+// mode 0 / 1 layers: 3x3x3 over C1 + C2 channels (x2 upsampled); mode 2: KS^3 over ONE channel (C1 = 1, KS 3 or 5)
+bool make_layer(int Cout, int C1, int C2, int KS, bool wrun, Layer& L) {
     if (Cout < 1 || Cout > 256 || C1 < 0 || C2 < 0 || C1 + C2 < 1) return false;
-    Cp1 = round_up(C1, 8); Cp2 = round_up(C2, 8);
-    CC = (Cp1 + Cp2) / 8;
-    pair = CC == 1;
-    CCe = pair ? 1 : round_up(CC, 2);
-    Npad = round_up(Cout, 16);
+    L.KS = KS; L.C1 = C1; L.C2 = C2; L.Cout = Cout;
+    L.Cp1 = round_up(C1, 8); L.Cp2 = round_up(C2, 8);
+    L.CC = (L.Cp1 + L.Cp2) / 8;
+    L.Npad = round_up(Cout, 16);
+    if (wrun) {
+        if (C1 != 1 || C2 != 0 || (KS != 3 && KS != 5)) return false;
+        const int n_ks = (KS * KS + 1) / 2;  // two (kd,kh) lines per K = 16 step
+        L.mode = 2; L.CCe = 1; L.ck = 1; L.n_stages = 1;
+        L.kpg = n_ks <= 6 ? n_ks : 7; L.n_groups = (n_ks + L.kpg - 1) / L.kpg;
+        L.hd = KS - 1; L.hw = 0;
+        return true;
+    }
+    if (KS != 3) return false;
+    L.hd = L.hw = 2;
+    if (L.CC == 1) { L.mode = 1; L.CCe = 1; L.ck = 1; L.n_stages = 1; L.kpg = 2; L.n_groups = 9; }
+    else { L.mode = 0; L.CCe = round_up(L.CC, 2); L.ck = 2; L.n_stages = L.CCe / 2; L.kpg = 3; L.n_groups = 9; }
     return true;
+}
+
+size_t weight_image_bytes(const Layer& L) { return (size_t)L.n_stages * L.n_groups * L.kpg * 2 * L.Npad * 32; }
+
+int weight_image(const float* w, const Layer& L, float scale, void* image, void* stream) {
+    const long threads = (long)L.n_stages * L.n_groups * L.kpg * 2 * L.Npad;
+    halo_weight_image_kernel<<<(unsigned)rf_cdivl(threads, 256), 256, 0, (cudaStream_t)stream>>>(w, L, scale, (uint8_t*)image);
+    RF_LAUNCH_OK("halo_weight_image_kernel");
+    return 0;
+}
+
+int conv_init() {
+    RF_SMEM_OPT_IN((tc_conv3d_halo_kernel<1, 1>), SMEM_LIMIT);
+    RF_SMEM_OPT_IN((tc_conv3d_halo_kernel<1, 0>), SMEM_LIMIT);
+    RF_SMEM_OPT_IN((tc_conv3d_halo_kernel<2, 0>), SMEM_LIMIT);
+    return 0;
+}
+
+// D, H, W: OUTPUT extents.  The planes hold Din x Hin x Win slots per (chunk, sample): Din = D + hd - 2 pad, likewise H;
+// Win = W + hw - 2 pad (mode 2: Win = W, the W-runs already cover the taps and the padding along W).
+int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D, int H,
+                int W, int pad, int act, float slope, float out_scale, int out_ncdhw, void* stream) {
+    Geo g;
+    RF_CHECK_ARG(choose_geometry(N, D, H, W, L, pad, g), "rf_tc_conv3d_halo_fwd: no item shape fits (N=%d out %dx%dx%d Cout=%d C=%d+%d KS=%d)",
+                 N, D, H, W, L.Cout, L.C1, L.C2, L.KS);
+    HaloArgs a;
+    a.wimg = (const uint8_t*)weight_image; a.bias = bias; a.y = y;
+    a.N = N; a.D = D; a.H = H; a.W = W; a.Hp = H + g.hd; a.Wp = W + g.hw;
+    a.pad = pad; a.CC = L.CC; a.w0 = L.mode == 2 ? 0 : -pad;
+    a.V = (long)(D + g.hd) * (H + g.hd) * (W + g.hw);
+    a.Dt = g.Dt; a.Ht = g.Ht; a.Hs = g.Hs; a.G = g.G; a.stacked = g.stacked;
+    a.n_dt = D / g.Dt; a.n_ht = H / g.Ht; a.Ls = (D + g.hd) * (H + g.hd);
+    a.lines = g.lines; a.n_wblk = g.n_wblk; a.n_tiles = g.n_tiles; a.P = g.P; a.S_st = g.S_st;
+    a.n_stages = L.n_stages; a.nbuf = g.nbuf; a.ck = L.ck; a.kpg = L.kpg; a.n_groups = L.n_groups;
+    a.Cout = L.Cout; a.Npad = L.Npad; a.act = act; a.out_ncdhw = out_ncdhw; a.slope = slope; a.out_scale = out_scale;
+    a.bslot_bytes = g.bslot; a.tmem_cols = g.tmem_cols;
+    a.n_iss = g.n_tiles < 6 ? g.n_tiles : 6;
+    // tile t = lb * n_wblk + wb starts at slot lb * (16 lines) + wb * 8 (linear mode: n_wblk = 1, 128 slots per tile)
+    RF_CHECK_ARG(g.n_tiles <= 32, "rf_tc_conv3d_halo_fwd: internal: more than 32 M tiles");
+    for (int t = 0; t < 32; ++t) {
+        const long off = g.lines ? (long)(t / g.n_wblk) * 16 * a.Wp + (t % g.n_wblk) * 8 : (long)t * 128;
+        a.tile_off[t] = (uint16_t)(t < g.n_tiles ? off : 0);
+    }
+    // k step table: slot offset of the step's first chunk, distance to its second chunk
+    RF_CHECK_ARG(L.kpg * L.n_groups <= 32, "rf_tc_conv3d_halo_fwd: internal: more than 32 k steps per stage");
+    for (int i = 0; i < 32; ++i) {
+        long off = 0, lbo = 1;
+        auto tap_off = [&](int t) { return ((long)(t / 9) * a.Hs + (t / 3) % 3) * a.Wp + t % 3; };
+        auto line_off = [&](int l) { return ((long)(l / L.KS) * a.Hs + l % L.KS) * a.Wp; };
+        if (i < L.kpg * L.n_groups) {
+            if (L.mode == 0) { off = tap_off(i); lbo = a.P; }
+            else if (L.mode == 1) { off = tap_off((i / 2) * 3 + (i % 2) * 2); }  // (kw 0, kw 1) and (kw 2, zeros) of line i / 2
+            else { if (2 * i < L.KS * L.KS) { off = line_off(2 * i); if (2 * i + 1 < L.KS * L.KS) lbo = line_off(2 * i + 1) - off; } }
+        }
+        RF_CHECK_ARG(off >= 0 && off < 65536 && lbo > 0 && lbo < 16384, "rf_tc_conv3d_halo_fwd: internal: k step offsets out of range");
+        a.ktab[i] = (uint32_t)off | ((uint32_t)lbo << 16);
+    }
+    if (int rc = conv_init()) return rc;
+    a.n_items = g.n_items; a.n_sets = g.n_sets; a.fused = g.fused;
+    // tensor maps of the compact planes [CC * N][Din][Hin][Win] x 16 B, seen as 8-byte words so that a whole line of
+    // the item's block is the innermost box extent (<= 256 elements)
+    const int Din = D + L.hd - 2 * pad, Hin = H + L.hd - 2 * pad, Win = L.mode == 2 ? W : W + L.hw - 2 * pad;
+    const int bW = W + g.hw, bD = g.stacked ? D + g.hd : g.Dt + L.hd;  // the item's box (its H extent is g.Hs)
+    RF_CHECK_ARG(bW <= 256 && g.Hs <= 256 && bD <= 256 && g.G <= 256, "rf_tc_conv3d_halo_fwd: item box exceeds the TMA limits");
+    a.tm5 = 2 * bW > 256 ? 1 : 0;  // a line longer than 256 words: slots as a dimension of their own
+    CUtensorMap tm[2];
+    const EncodeTiledFn encode = encode_tiled_fn();
+    RF_CHECK_ARG(encode != nullptr, "rf_tc_conv3d_halo_fwd: the driver does not export cuTensorMapEncodeTiled");
+    for (int k = 0; k < 2; ++k) {
+        const cuuint32_t bG = (cuuint32_t)(g.stacked ? g.G : 1);
+        const cuuint64_t planes = (cuuint64_t)L.CC * (cuuint64_t)N;
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult cr;
+        if (a.tm5) {
+            const cuuint64_t gdim[5] = {2, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)Din, planes};
+            const cuuint64_t gstr[4] = {16, 16ull * Win, 16ull * Win * Hin, 16ull * Win * Hin * Din};
+            const cuuint32_t box[5] = {2, (cuuint32_t)bW, (cuuint32_t)g.Hs, (cuuint32_t)bD, bG};
+            cr = encode(&tm[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void*>(k ? lo : hi), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            const cuuint64_t gdim[4] = {(cuuint64_t)(2 * Win), (cuuint64_t)Hin, (cuuint64_t)Din, planes};
+            const cuuint64_t gstr[3] = {16ull * Win, 16ull * Win * Hin, 16ull * Win * Hin * Din};
+            const cuuint32_t box[4] = {(cuuint32_t)(2 * bW), (cuuint32_t)g.Hs, (cuuint32_t)bD, bG};
+            cr = encode(&tm[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(k ? lo : hi), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        RF_CHECK_ARG(cr == CUDA_SUCCESS, "rf_tc_conv3d_halo_fwd: cuTensorMapEncodeTiled failed (%d) for planes %dx%dx%dx%d, item box %dx%dx%dx%u", (int)cr,
+                     Win, Hin, Din, L.CC * N, bW, g.Hs, bD, bG);
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int slots = sms * (g.two_resident ? 2 : 1);
+    const unsigned grid = (unsigned)(g.n_items < slots ? g.n_items : slots);
+    static const int pipe = [] { const char* e = getenv("RF_HALO_PIPE"); return e ? atoi(e) : 1; }();  // tuning aid
+    if (g.two_resident) tc_conv3d_halo_kernel<2, 0><<<grid, NTHREADS, g.smem, (cudaStream_t)stream>>>(a, tm[0], tm[1]);
+    else if (pipe) tc_conv3d_halo_kernel<1, 1><<<grid, NTHREADS, g.smem, (cudaStream_t)stream>>>(a, tm[0], tm[1]);
+    else tc_conv3d_halo_kernel<1, 0><<<grid, NTHREADS, g.smem, (cudaStream_t)stream>>>(a, tm[0], tm[1]);
+    RF_LAUNCH_OK("tc_conv3d_halo_kernel");
+    return 0;
 }
 
 }  // namespace
 
+int rf_tc_conv_halo_init() { return conv_init(); }
+
 extern "C" size_t rf_halo_act_bytes(int N, int D, int H, int W, int C1, int C2, int pad) {
-    int Cp1, Cp2, CC, CCe, pair, Npad;
-    if (!halo_shape(16, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad) || N < 1 || D < 1 || H < 1 || W < 1 || pad < 0 || pad > 1) return 0;
-    return (size_t)CC * N * (size_t)D * H * W * 16;  // compact planes: the halo is made by the TMA unit's zero fill
+    Layer L;
+    if (!make_layer(16, C1, C2, 3, false, L) || N < 1 || D < 1 || H < 1 || W < 1 || pad < 0 || pad > 1) return 0;
+    return (size_t)L.CC * N * (size_t)D * H * W * 16;  // compact planes: the halo is made by the TMA unit's zero fill
 }
 
 extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a,
                                      const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, int pad, float scale,
                                      int interior_only, void* stream) {
     (void)interior_only;  // the planes have no halo any more: every call writes every slot
-    int Cp1, Cp2, CC, CCe, pair, Npad;
-    RF_CHECK_ARG(halo_shape(16, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad), "rf_cl_norm_split_halo: bad channel counts");
+    Layer L;
+    RF_CHECK_ARG(make_layer(16, C1, C2, 3, false, L), "rf_cl_norm_split_halo: bad channel counts");
     RF_CHECK_ARG(hi && lo && (C1 == 0 || x) && (C2 == 0 || x2) && N > 0 && D > 0 && H > 0 && W > 0 && (pad == 0 || pad == 1),
                  "rf_cl_norm_split_halo: bad arguments");
     RF_CHECK_ARG(C2 == 0 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "rf_cl_norm_split_halo: upsampled input needs even extents");
@@ -654,7 +834,8 @@ extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, in
                  "rf_cl_norm_split_halo: pointers must be 16-byte aligned");
     SplitArgs s;
     s.x = x; s.x2 = x2; s.mu = gn_mu; s.a = gn_a; s.beta = gn_beta; s.hi = (uint4*)hi; s.lo = (uint4*)lo;
-    s.N = N; s.D = D; s.H = H; s.W = W; s.C1 = C1; s.C2 = C2; s.CC1 = Cp1 / 8; s.CC = CC; s.scale = scale;
+    s.N = N; s.D = D; s.H = H; s.W = W; s.C1 = C1; s.C2 = C2; s.CC1 = L.Cp1 / 8; s.CC = L.CC; s.scale = scale;
+    const int CC = L.CC;
     const long n_vox = (long)N * D * H * W;
     const long total = (long)CC * n_vox;
     RF_CHECK_ARG(total < (1L << 32) - 256, "rf_cl_norm_split_halo: more than 2^32 slots");
@@ -675,125 +856,161 @@ extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, in
 }
 
 extern "C" size_t rf_tc_conv_halo_weight_image_bytes(int Cout, int C1, int C2) {
-    int Cp1, Cp2, CC, CCe, pair, Npad;
-    if (!halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad)) return 0;
-    const int n_stages = pair ? 1 : CCe / 2, kpg = pair ? 2 : 3;
-    return (size_t)n_stages * 9 * kpg * 2 * Npad * 32;
+    Layer L;
+    return make_layer(Cout, C1, C2, 3, false, L) ? weight_image_bytes(L) : 0;
 }
 
 extern "C" int rf_tc_conv_halo_weight_image(const float* w, int Cout, int C1, int C2, float scale, void* image, void* stream) {
-    int Cp1, Cp2, CC, CCe, pair, Npad;
+    Layer L;
     RF_CHECK_ARG(w && image, "rf_tc_conv_halo_weight_image: null pointer");
-    RF_CHECK_ARG(halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad), "rf_tc_conv_halo_weight_image: unsupported shape");
+    RF_CHECK_ARG(make_layer(Cout, C1, C2, 3, false, L), "rf_tc_conv_halo_weight_image: unsupported shape");
     RF_CHECK_ARG(((uintptr_t)image & 15) == 0, "rf_tc_conv_halo_weight_image: image must be 16-byte aligned");
-    const int n_stages = pair ? 1 : CCe / 2, kpg = pair ? 2 : 3;
-    const long threads = (long)n_stages * 9 * kpg * 2 * Npad;
-    halo_weight_image_kernel<<<(unsigned)rf_cdivl(threads, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, C1, C2, Cp1, Cp2, Npad, n_stages,
-                                                                                                pair, scale, (uint8_t*)image);
-    RF_LAUNCH_OK("halo_weight_image_kernel");
-    return 0;
+    return weight_image(w, L, scale, image, stream);
 }
 
 /* 1 when rf_tc_conv3d_halo_fwd can run this layer (an item shape fits shared memory and TMEM).  D, H, W are the
  * INPUT extents; the output extents are D + 2 pad - 2 (pad 1: 'same', pad 0: 'valid'). */
 extern "C" int rf_tc_conv3d_halo_supported(int N, int D, int H, int W, int Cout, int C1, int C2, int pad) {
-    int Cp1, Cp2, CC, CCe, pair, Npad;
-    if (!halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad) || N < 1 || pad < 0 || pad > 1) return 0;
+    Layer L;
+    if (!make_layer(Cout, C1, C2, 3, false, L) || N < 1 || pad < 0 || pad > 1) return 0;
     const int Do = D + 2 * pad - 2, Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
     if (Do < 1 || Ho < 1 || Wo < 1) return 0;
-    if ((long)N * (Do + 2) * (Ho + 2) * (Wo + 2) * CCe >= (1L << 31)) return 0;
+    if ((long)N * D * H * W * L.CC >= (1L << 32) - 256) return 0;
     Geo g;
-    return choose_geometry(N, Do, Ho, Wo, CCe, pair, Npad, pad, g) && g.n_tiles <= 32 ? 1 : 0;
-}
-
-int rf_tc_conv_halo_init() {
-    RF_SMEM_OPT_IN(tc_conv3d_halo_kernel, SMEM_LIMIT);
-    return 0;
+    return choose_geometry(N, Do, Ho, Wo, L, pad, g) && g.n_tiles <= 32 ? 1 : 0;
 }
 
 extern "C" int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y,
                                      int N, int D, int H, int W, int pad, int Cout, int C1, int C2, int act, float slope,
                                      float out_scale, int out_ncdhw, void* stream) {
     RF_CHECK_ARG(hi && lo && weight_image && y, "rf_tc_conv3d_halo_fwd: null pointer");
-    int Cp1, Cp2, CC, CCe, pair, Npad;
-    RF_CHECK_ARG(halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad) && N > 0 && (pad == 0 || pad == 1),
+    Layer L;
+    RF_CHECK_ARG(make_layer(Cout, C1, C2, 3, false, L) && N > 0 && (pad == 0 || pad == 1),
                  "rf_tc_conv3d_halo_fwd: unsupported shape Cout=%d C1=%d C2=%d pad=%d", Cout, C1, C2, pad);
     RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)weight_image & 15) == 0 && ((uintptr_t)y & 15) == 0,
                  "rf_tc_conv3d_halo_fwd: pointers must be 16-byte aligned");
-    // from here on D, H, W are the OUTPUT extents; the stored block is (D+2) x (H+2) x (W+2) either way
+    // from here on D, H, W are the OUTPUT extents
     D += 2 * pad - 2; H += 2 * pad - 2; W += 2 * pad - 2;
     RF_CHECK_ARG(D > 0 && H > 0 && W > 0, "rf_tc_conv3d_halo_fwd: empty output");
-    Geo g;
-    RF_CHECK_ARG(choose_geometry(N, D, H, W, CCe, pair, Npad, pad, g), "rf_tc_conv3d_halo_fwd: no item shape fits (N=%d out %dx%dx%d Cout=%d C=%d+%d)",
-                 N, D, H, W, Cout, C1, C2);
-    HaloArgs a;
-    a.wimg = (const uint8_t*)weight_image; a.bias = bias; a.y = y;
-    a.N = N; a.D = D; a.H = H; a.W = W; a.Hp = H + g.halo; a.Wp = W + g.halo;
-    a.pad = pad; a.CC = CC;
-    a.V = (long)(D + g.halo) * (H + g.halo) * (W + g.halo);
-    a.Dt = g.Dt; a.Ht = g.Ht; a.Hs = g.Hs; a.G = g.G; a.stacked = g.stacked;
-    a.n_dt = D / g.Dt; a.n_ht = H / g.Ht; a.Ls = (D + g.halo) * (H + g.halo);
-    a.lines = g.lines; a.n_wblk = g.n_wblk; a.n_tiles = g.n_tiles; a.P = g.P; a.S_st = g.S_st;
-    a.pair = pair; a.n_stages = pair ? 1 : CCe / 2; a.nbuf = g.nbuf; a.ck = pair ? 1 : 2; a.kpg = pair ? 2 : 3;
-    a.Cout = Cout; a.Npad = Npad; a.act = act; a.out_ncdhw = out_ncdhw; a.slope = slope; a.out_scale = out_scale;
-    a.bslot_bytes = g.bslot; a.tmem_cols = g.tmem_cols;
-    a.n_iss = g.n_tiles < 6 ? g.n_tiles : 6;
-    // tile t = lb * n_wblk + wb starts at slot lb * (16 lines) + wb * 8 (linear mode: n_wblk = 1, 128 slots per tile)
-    RF_CHECK_ARG(g.n_tiles <= 32, "rf_tc_conv3d_halo_fwd: internal: more than 32 M tiles");
-    for (int t = 0; t < 32; ++t) {
-        const long off = g.lines ? (long)(t / g.n_wblk) * 16 * a.Wp + (t % g.n_wblk) * 8 : (long)t * 128;
-        a.tile_off[t] = (uint16_t)(t < g.n_tiles ? off : 0);
-    }
-    if (int rc = rf_tc_conv_halo_init()) return rc;
-    a.n_items = g.n_items; a.n_sets = g.n_sets; a.fused = g.fused;
-    // tensor maps of the compact planes [CC * N][Din][Hin][Win] x 16 B, seen as 8-byte words so that a whole haloed line
-    // (W + 2 slots) is the innermost box extent (<= 256 elements)
-    const int Din = D + 2 - 2 * pad, Hin = H + 2 - 2 * pad, Win = W + 2 - 2 * pad;
-    const int bW = W + g.halo, bD = g.stacked ? D + g.halo : g.Dt + 2;  // the item's box (its H extent is g.Hs)
-    RF_CHECK_ARG(bW <= 256 && g.Hs <= 256 && bD <= 256 && g.G <= 256, "rf_tc_conv3d_halo_fwd: item box exceeds the TMA limits");
-    a.tm5 = 2 * bW > 256 ? 1 : 0;  // a haloed line longer than 256 words: slots as a dimension of their own
-    CUtensorMap tm[2];
-    const EncodeTiledFn encode = encode_tiled_fn();
-    RF_CHECK_ARG(encode != nullptr, "rf_tc_conv3d_halo_fwd: the driver does not export cuTensorMapEncodeTiled");
-    for (int k = 0; k < 2; ++k) {
-        const cuuint32_t bG = (cuuint32_t)(g.stacked ? g.G : 1);
-        const cuuint64_t planes = (cuuint64_t)CC * (cuuint64_t)N;
-        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        CUresult cr;
-        if (a.tm5) {
-            const cuuint64_t gdim[5] = {2, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)Din, planes};
-            const cuuint64_t gstr[4] = {16, 16ull * Win, 16ull * Win * Hin, 16ull * Win * Hin * Din};
-            const cuuint32_t box[5] = {2, (cuuint32_t)bW, (cuuint32_t)g.Hs, (cuuint32_t)bD, bG};
-            cr = encode(&tm[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void*>(k ? lo : hi), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        } else {
-            const cuuint64_t gdim[4] = {(cuuint64_t)(2 * Win), (cuuint64_t)Hin, (cuuint64_t)Din, planes};
-            const cuuint64_t gstr[3] = {16ull * Win, 16ull * Win * Hin, 16ull * Win * Hin * Din};
-            const cuuint32_t box[4] = {(cuuint32_t)(2 * bW), (cuuint32_t)g.Hs, (cuuint32_t)bD, bG};
-            cr = encode(&tm[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(k ? lo : hi), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        }
-        RF_CHECK_ARG(cr == CUDA_SUCCESS, "rf_tc_conv3d_halo_fwd: cuTensorMapEncodeTiled failed (%d) for planes %dx%dx%dx%d, item box %dx%dx%dx%u", (int)cr,
-                     Win, Hin, Din, CC * N, bW, g.Hs, bD, bG);
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int slots = sms * (g.two_resident ? 2 : 1);
-    tc_conv3d_halo_kernel<<<(unsigned)(g.n_items < slots ? g.n_items : slots), NTHREADS, g.smem, (cudaStream_t)stream>>>(a, tm[0], tm[1]);
-    RF_LAUNCH_OK("tc_conv3d_halo_kernel");
-    return 0;
+    return launch_conv(L, hi, lo, weight_image, bias, y, N, D, H, W, pad, act, slope, out_scale, out_ncdhw, stream);
 }
 
 /* Debug / test aid: the item shape the chooser picks (returns 0 when unsupported). */
 extern "C" int rf_tc_conv3d_halo_geometry(int N, int D, int H, int W, int Cout, int C1, int C2, int pad, int* out8) {
-    int Cp1, Cp2, CC, CCe, pair, Npad;
-    if (!halo_shape(Cout, C1, C2, Cp1, Cp2, CC, CCe, pair, Npad)) return 0;
+    Layer L;
+    if (!make_layer(Cout, C1, C2, 3, false, L)) return 0;
     Geo g;
-    if (!choose_geometry(N, D + 2 * pad - 2, H + 2 * pad - 2, W + 2 * pad - 2, CCe, pair, Npad, pad, g)) return 0;
+    if (!choose_geometry(N, D + 2 * pad - 2, H + 2 * pad - 2, W + 2 * pad - 2, L, pad, g)) return 0;
     out8[0] = g.stacked; out8[1] = g.G; out8[2] = g.Dt; out8[3] = g.Ht; out8[4] = g.lines + 2 * g.fused + 4 * (g.halo == 1); out8[5] = g.n_tiles;
     out8[6] = g.n_items; out8[7] = (int)g.smem;
     return 1;
+}
+
+// ------------------------------------------------------------------ single-channel layers as W-runs (mode 2)
+namespace {
+struct WrunArgs {
+    const float *x, *mu, *a, *beta;
+    uint4 *hi, *lo;
+    int W, Wo, pad;
+    float scale;
+    FastDiv fWo, fH, fD;
+    unsigned total;
+};
+
+// slot (n, d, h, p), p in [0, Wo): the 8 values x[n, d, h, p - pad + e], e = 0..7 (zero outside the line), normalised
+// (single channel: one GroupNorm group) and split into fp16 hi / lo
+__global__ void __launch_bounds__(256) cl_norm_split_wrun_kernel(const WrunArgs s) {
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < s.total; j += gridDim.x * blockDim.x) {
+        unsigned t = j;
+        const int p = (int)fd_divmod(t, s.fWo);
+        const unsigned line = t;  // (n * D + d) * H + h
+        (void)fd_divmod(t, s.fH);
+        (void)fd_divmod(t, s.fD);
+        const int n = (int)t;
+        const float* src = s.x + (long)line * s.W;
+        float m = 0.f, sa = 1.f, sb = 0.f;
+        if (s.mu) { m = __ldg(s.mu + n); sa = __ldg(s.a + n); sb = __ldg(s.beta); }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            float v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int w = p - s.pad + e + u;
+                float val = 0.f;  // zero padding is applied AFTER the normalisation
+                if (w >= 0 && w < s.W) {
+                    val = __ldg(src + w);
+                    if (s.mu) val = fmaf(val - m, sa, sb);
+                    val *= s.scale;
+                }
+                v[u] = val;
+            }
+            split_f16x2(v[0], v[1], h[e >> 1], l[e >> 1]);
+        }
+        s.hi[j] = make_uint4(h[0], h[1], h[2], h[3]);
+        s.lo[j] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+}  // namespace
+
+/* Single-channel KS^3 convolution (KS = 3 or 5, stride 1, zero padding pad <= 1) on tensor cores.  D, H, W: INPUT
+ * extents; outputs Do = D + 2 pad - KS + 1 etc.  Planes: [N][D][H][Wo] slots. */
+extern "C" size_t rf_wrun_act_bytes(int N, int D, int H, int W, int KS, int pad) {
+    const int Wo = W + 2 * pad - KS + 1;
+    if (N < 1 || D < 1 || H < 1 || Wo < 1 || (KS != 3 && KS != 5) || pad < 0 || pad > 1) return 0;
+    return (size_t)N * D * H * Wo * 16;
+}
+
+extern "C" int rf_cl_norm_split_wrun(const float* x, const float* gn_mu, const float* gn_a, const float* gn_beta, void* hi, void* lo, int N,
+                                     int D, int H, int W, int KS, int pad, float scale, void* stream) {
+    RF_CHECK_ARG(x && hi && lo && rf_wrun_act_bytes(N, D, H, W, KS, pad) > 0, "rf_cl_norm_split_wrun: bad arguments");
+    RF_CHECK_ARG((gn_mu == nullptr) == (gn_a == nullptr) && (gn_mu == nullptr) == (gn_beta == nullptr), "rf_cl_norm_split_wrun: partial GroupNorm arguments");
+    RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0, "rf_cl_norm_split_wrun: planes must be 16-byte aligned");
+    WrunArgs s;
+    s.x = x; s.mu = gn_mu; s.a = gn_a; s.beta = gn_beta; s.hi = (uint4*)hi; s.lo = (uint4*)lo;
+    s.W = W; s.Wo = W + 2 * pad - KS + 1; s.pad = pad; s.scale = scale;
+    const long total = (long)N * D * H * s.Wo;
+    RF_CHECK_ARG(total < (1L << 32) - 256, "rf_cl_norm_split_wrun: more than 2^32 slots");
+    s.total = (unsigned)total;
+    s.fWo = make_fastdiv(s.Wo); s.fH = make_fastdiv(H); s.fD = make_fastdiv(D);
+    cl_norm_split_wrun_kernel<<<rf_grid_1d(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(s);
+    RF_LAUNCH_OK("cl_norm_split_wrun_kernel");
+    return 0;
+}
+
+extern "C" size_t rf_tc_conv_wrun_weight_image_bytes(int Cout, int KS) {
+    Layer L;
+    return make_layer(Cout, 1, 0, KS, true, L) ? weight_image_bytes(L) : 0;
+}
+
+extern "C" int rf_tc_conv_wrun_weight_image(const float* w, int Cout, int KS, float scale, void* image, void* stream) {
+    Layer L;
+    RF_CHECK_ARG(w && image && make_layer(Cout, 1, 0, KS, true, L), "rf_tc_conv_wrun_weight_image: unsupported shape Cout=%d KS=%d", Cout, KS);
+    RF_CHECK_ARG(((uintptr_t)image & 15) == 0, "rf_tc_conv_wrun_weight_image: image must be 16-byte aligned");
+    return weight_image(w, L, scale, image, stream);
+}
+
+extern "C" int rf_tc_conv3d_wrun_supported(int N, int D, int H, int W, int Cout, int KS, int pad) {
+    Layer L;
+    if (!make_layer(Cout, 1, 0, KS, true, L) || rf_wrun_act_bytes(N, D, H, W, KS, pad) == 0) return 0;
+    const int Do = D + 2 * pad - KS + 1, Ho = H + 2 * pad - KS + 1, Wo = W + 2 * pad - KS + 1;
+    if (Do < 1 || Ho < 1) return 0;
+    Geo g;
+    return choose_geometry(N, Do, Ho, Wo, L, pad, g) && g.n_tiles <= 32 ? 1 : 0;
+}
+
+extern "C" int rf_tc_conv3d_wrun_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D,
+                                     int H, int W, int KS, int pad, int Cout, int act, float slope, float out_scale, int out_ncdhw,
+                                     void* stream) {
+    RF_CHECK_ARG(hi && lo && weight_image && y, "rf_tc_conv3d_wrun_fwd: null pointer");
+    Layer L;
+    RF_CHECK_ARG(make_layer(Cout, 1, 0, KS, true, L) && rf_wrun_act_bytes(N, D, H, W, KS, pad) > 0,
+                 "rf_tc_conv3d_wrun_fwd: unsupported shape Cout=%d KS=%d pad=%d", Cout, KS, pad);
+    RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)weight_image & 15) == 0 && ((uintptr_t)y & 15) == 0,
+                 "rf_tc_conv3d_wrun_fwd: pointers must be 16-byte aligned");
+    const int Do = D + 2 * pad - KS + 1, Ho = H + 2 * pad - KS + 1, Wo = W + 2 * pad - KS + 1;
+    RF_CHECK_ARG(Do > 0 && Ho > 0 && Wo > 0, "rf_tc_conv3d_wrun_fwd: empty output");
+    return launch_conv(L, hi, lo, weight_image, bias, y, N, Do, Ho, Wo, pad, act, slope, out_scale, out_ncdhw, stream);
 }
 
 /* Tuning aid: phase timestamps (clock64) of CTA 0's first six items of the last rf_tc_conv3d_halo_fwd launch:

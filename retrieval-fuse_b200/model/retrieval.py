@@ -48,6 +48,7 @@ class _ConvPatchEncoder(RfModule):
 
     use_tensor_cores = True  # tcgen05 implicit-GEMM convs on channels-last fp16-split activations
     use_halo_conv = True     # stride-1 3x3x3 layers through the shifted-window kernel (rf_tc_conv_halo.cu)
+    use_wrun_conv = True     # single-channel first layer (3^3 / 5^3) through the same kernel on W-run operand planes
 
     def _forward_tc(self, x):
         """Channels-last tensor-core path: split -> tc_conv3d (bias + LeakyReLU fused) per layer."""
@@ -55,6 +56,12 @@ class _ConvPatchEncoder(RfModule):
         h = ops.cl_from_ncdhw(x)
         for li, (conv, (_mult, k, s)) in enumerate(zip(convs, self._spec)):
             cin = conv.in_channels
+            if (cin == 1 and s == 1 and self.use_wrun_conv and (k == 5 or conv.out_channels >= 16) and
+                    ops.tc_conv_wrun_supported(h.shape[0], h.shape[1], h.shape[2], h.shape[3], conv.out_channels, k, 0)):
+                # first layer on tensor cores: W-run operand planes, one K chunk = all kw taps of a (kd,kh) line
+                img, sw = self._wcache.derived(("wrun", li), [conv.weight], ops.tc_conv_wrun_weight_image)
+                h = ops.tc_conv3d_wrun(h, img, conv.bias, conv.out_channels, k, pad=0, act=ops.ACT_LEAKY, slope=0.2, out_scale=1.0 / sw)
+                continue
             if cin == 1 and conv.out_channels <= 32:  # first layer: direct convolution on the raw single-channel patch
                 h = ops.conv3d_cin1_cl(h, conv.weight, conv.bias, None, ks=k, stride=s, pad=0, act=ops.ACT_LEAKY, slope=0.2)
                 continue

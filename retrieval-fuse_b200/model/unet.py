@@ -16,6 +16,11 @@ from ._base import RfModule
 USE_TENSOR_CORES = True
 # 3x3x3 layers: shifted-window kernel (rf_tc_conv_halo.cu) instead of the gathering implicit GEMM (rf_tc_conv.cu)
 USE_HALO_CONV = True
+# single-input-channel first layers through the same kernel (W-run operand planes) instead of the fp32 FMA kernel.
+# Measured on the 1 -> 8 @ 16^3 layer of the retrieval U-Net (16 384 patches): 0.51 ms split + 1.63 ms convolution (bound
+# by the epilogue's 2.1 GB of fp32 output, 8 of 16 accumulator columns used) against 1.85 ms for the FMA kernel, so the
+# U-Nets keep the FMA kernel; the 5^3 / wide first layers of the patch encoders (model/retrieval.py) take the tensor cores.
+USE_WRUN_CONV = False
 # EXPERIMENTAL, OFF by default (tools/wpack_formulation.py): run small-channel 3x3x3 layers through the
 # shifted-window kernel on W-packed views [N,D,H,W/Bw,Bw*C] with Toeplitz-expanded weights.  The identity is verified on
 # the CPU; the kernel has not been measured on these shapes yet, so nothing selects this path unless W_PACK maps
@@ -118,6 +123,16 @@ class SingleConv(RfModule):
             y = ops.tc_conv3d_halo(split, img, None, Bw * self.out_channels, act=self.act, slope=0.1,
                                    out_scale=1.0 / (ops.ACT_SCALE_GN * sw))
             return y.view(N, D, H, W, self.out_channels)
+        if (c1 == 1 and c2 == 0 and not out_ncdhw and USE_WRUN_CONV and
+                ops.tc_conv_wrun_supported(x.shape[0], x.shape[1], x.shape[2], x.shape[3], self.out_channels, 3, 1)):
+            # first layer (single input channel) on tensor cores: the operand slot of a voxel holds 8 consecutive values
+            # of its line, one K chunk = the three kw taps of a (kd,kh) line (rf_tc_conv3d_wrun_fwd)
+            if not hasattr(self, "_wrun_planes"):
+                object.__setattr__(self, "_wrun_planes", {})
+            sa = ops.ACT_SCALE_GN
+            img, sw = self._wcache.derived(("wrun",), [self.conv.weight], ops.tc_conv_wrun_weight_image)
+            return ops.tc_conv3d_wrun(x, img, self.conv.bias, self.out_channels, 3, pad=1, gn=(mu, a, g.bias), scale=sa,
+                                      act=self.act, slope=0.1, out_scale=1.0 / (sa * sw), buffers=self._wrun_planes)
         if c1 == 1 and c2 == 0 and self.out_channels <= 32 and not out_ncdhw:
             # first layer (single input channel): direct convolution with the normalisation on the fly
             return ops.conv3d_cin1_cl(x, self.conv.weight, self.conv.bias, (mu, a, g.bias), ks=3, stride=1, pad=1,

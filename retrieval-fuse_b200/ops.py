@@ -420,6 +420,68 @@ def conv3d_cin1_cl(x, weight, bias, gn=None, ks=3, stride=1, pad=0, act=ACT_NONE
     return y
 
 
+def tc_conv_wrun_supported(N, D, H, W, cout, ks, pad):
+    """Whether the single-input-channel ks^3 layer runs on the tensor-core kernel (W-run operand planes)."""
+    return bool(_lib.lib().rf_tc_conv3d_wrun_supported(int(N), int(D), int(H), int(W), int(cout), int(ks), int(pad)))
+
+
+def tc_conv_wrun_weight_image(weight):
+    """Conv3d weight [Cout, 1, ks,ks,ks] -> (pre-split fp16 operand image for rf_tc_conv3d_wrun_fwd, weight scale)."""
+    weight = _dev(weight.detach(), name="weight")
+    cout, cin, ks = weight.shape[0], weight.shape[1], weight.shape[2]
+    assert cin == 1 and tuple(weight.shape[2:]) == (ks, ks, ks)
+    wmax = float(weight.abs().max())
+    scale = 2.0 ** (4 - math.floor(math.log2(wmax))) if wmax > 0 and math.isfinite(wmax) else 1.0
+    scale = min(max(scale, 2.0 ** -8), 2.0 ** 24)
+    L = _lib.lib()
+    nbytes = L.rf_tc_conv_wrun_weight_image_bytes(cout, ks)
+    if nbytes == 0:
+        raise _lib.RfError(f"W-run conv does not support weight {tuple(weight.shape)}")
+    img = _aligned_bytes(nbytes, weight.device)
+    with torch.cuda.device(weight.device), _timed("rf_tc_conv_wrun_weight_image"):
+        check(L.rf_tc_conv_wrun_weight_image(weight.data_ptr(), cout, ks, scale, img.data_ptr(), _stream(weight)),
+              "rf_tc_conv_wrun_weight_image")
+    _count()
+    return img, scale
+
+
+def tc_conv3d_wrun(x, img, bias, cout, ks, pad=0, gn=None, scale=1.0, act=ACT_NONE, slope=0.0, out_scale=1.0, buffers=None):
+    """Single-channel channels-last volume x [N,D,H,W,1] -> fp32 [N,Do,Ho,Wo,Cout] through the shifted-window tensor-core
+    kernel: normalise (GroupNorm with one group, gn = (mu, a, beta)) + W-run split, then the convolution."""
+    x = _dev(x, name="x")
+    N, D, H, W = x.shape[:4]
+    L = _lib.lib()
+    nbytes = L.rf_wrun_act_bytes(N, D, H, W, int(ks), int(pad))
+    if nbytes == 0:
+        raise _lib.RfError(f"W-run layout does not support {tuple(x.shape)} ks={ks} pad={pad}")
+    key = (N, D, H, W, int(ks), int(pad), x.device)
+    if buffers is not None:
+        if key not in buffers:
+            while len(buffers) >= MAX_PLANE_SHAPES:
+                buffers.pop(next(iter(buffers)))
+                bump_generation()
+            buffers[key] = (torch.empty(nbytes, device=x.device, dtype=torch.uint8), torch.empty(nbytes, device=x.device, dtype=torch.uint8))
+        else:
+            buffers[key] = buffers.pop(key)
+        hi, lo = buffers[key]
+    else:
+        hi = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+        lo = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    mu, a, beta = gn if gn is not None else (None, None, None)
+    Do, Ho, Wo = [v + 2 * pad - ks + 1 for v in (D, H, W)]
+    y = torch.empty((N, Do, Ho, Wo, cout), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        with _timed("rf_cl_norm_split_wrun", nbytes=N * D * H * (4.0 * W + 32.0 * Wo)):
+            check(L.rf_cl_norm_split_wrun(x.data_ptr(), _ptr(mu), _ptr(a), _ptr(beta), hi.data_ptr(), lo.data_ptr(), N, D, H, W, int(ks),
+                                          int(pad), float(scale), _stream(x)), "rf_cl_norm_split_wrun")
+        _count()
+        with _timed("rf_tc_conv3d_wrun_fwd", flops=2.0 * N * Do * Ho * Wo * ks ** 3 * cout):
+            check(L.rf_tc_conv3d_wrun_fwd(hi.data_ptr(), lo.data_ptr(), img.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W, int(ks),
+                                          int(pad), int(cout), act, float(slope), float(out_scale), 0, _stream(x)), "rf_tc_conv3d_wrun_fwd")
+        _count()
+    return y
+
+
 def cl_pointwise_head(x, weight, bias, act=ACT_NONE, slope=0.0):
     """Conv3d(C, 1, 1) + bias + activation of a channels-last volume x [N,D,H,W,C] -> NCDHW [N,1,D,H,W]."""
     x = _dev(x, name="x")

@@ -193,6 +193,54 @@ def test_shifted_window_conv(dev, N, S, C1, C2, Cout, ncdhw):
     close(y, ref32, rel_to_max=True, what="shifted-window conv vs oracle")
 
 
+# (N, S, Cout, KS, pad, groupnorm): the single-channel first layers - U-Net 'gcr' 3^3 'same' (stacked 8^3 / slab 16^3 /
+# 64^3 items), encoder 3^3 and 5^3 'valid' layers with bias + LeakyReLU (Patch08 / Patch32 / PCPatch48 shapes)
+WRUN_CASES = [(5, 16, 8, 3, 1, True), (301, 8, 8, 3, 1, True), (2, 64, 16, 3, 1, True), (37, 8, 16, 3, 0, False),
+              (9, 32, 8, 5, 0, False), (3, 48, 16, 5, 0, False), (70, 12, 24, 5, 0, False), (4, 128, 12, 3, 1, True)]
+
+
+@pytest.mark.parametrize("N,S,Cout,KS,pad,gn", WRUN_CASES)
+def test_single_channel_conv_on_tensor_cores(dev, N, S, Cout, KS, pad, gn):
+    """First Conv3d of the patch encoders (model/retrieval.py:4-28,136-156: Conv3d(1, nf, k) + LeakyReLU(0.2)) and first
+    SingleConv of the U-Nets (model/unet.py:79-100, GroupNorm(1 group) -> Conv3d(1, C, 3, padding=1) -> ReLU) through
+    rf_tc_conv3d_wrun_fwd, against torch's CPU conv3d in fp32 and fp64."""
+    from retrieval_fuse_b200 import ops
+    g = torch.Generator().manual_seed(11 * N + S + Cout + KS)
+    x = torch.randn(N, 1, S, S, S, generator=g) * 1.3 + 0.4
+    if N > 1:
+        x[1] = 0.25  # constant sample: variance 0 under GroupNorm
+    w = torch.randn(Cout, 1, KS, KS, KS, generator=g) / KS ** 1.5
+    b = None if gn else torch.randn(Cout, generator=g) * 0.1
+    gamma, beta = torch.rand(1, generator=g) + 0.5, torch.randn(1, generator=g) * 0.1
+    n_ref = min(N, 4)
+    sel = list(range(n_ref)) + ([N - 1] if N > n_ref else [])
+
+    def ref(dt):
+        xx = x[sel].to(dt)
+        if gn:
+            xx = torch.nn.functional.group_norm(xx, 1, gamma.to(dt), beta.to(dt), 1e-5)
+        y = torch.nn.functional.conv3d(xx, w.to(dt), None if b is None else b.to(dt), padding=pad)
+        return torch.relu(y) if gn else torch.nn.functional.leaky_relu(y, 0.2)
+    ref32, ref64 = ref(torch.float32), ref(torch.float64)
+    assert ops.tc_conv_wrun_supported(N, S, S, S, Cout, KS, pad)
+    xd = x.permute(0, 2, 3, 4, 1).contiguous().to(dev)
+    img, sw = ops.tc_conv_wrun_weight_image(w.to(dev))
+    if gn:
+        mu, a = ops.cl_gn_stats(xd, gamma.to(dev), 1, 1e-5)
+        sa = ops.ACT_SCALE_GN
+        y = ops.tc_conv3d_wrun(xd, img, None, Cout, KS, pad=pad, gn=(mu, a, beta.to(dev)), scale=sa, act=ops.ACT_RELU,
+                               out_scale=1.0 / (sa * sw))
+    else:
+        y = ops.tc_conv3d_wrun(xd, img, b.to(dev), Cout, KS, pad=pad, act=ops.ACT_LEAKY, slope=0.2, out_scale=1.0 / sw)
+    y = y.permute(0, 4, 1, 2, 3).cpu()[sel]
+    assert y.shape == ref32.shape
+    scale = max(1.0, float(ref64.abs().max()))
+    err64 = float((y.double() - ref64).abs().max())
+    noise = float((ref32.double() - ref64).abs().max())
+    assert err64 <= 2e-5 * scale, f"|ours - fp64| {err64:.2e} (reference fp32 noise {noise:.2e}, scale {scale:.1f})"
+    close(y, ref32, rel_to_max=True, what="single-channel tensor-core conv vs torch fp32")
+
+
 @pytest.mark.parametrize("M,widths,act,l2", [(1000, [64, 128, 256, 512, 256, 64], 1, True), (129, [64, 128, 256, 512, 256, 64], 1, False),
                                              (4097, [128, 128, 128, 128, 32], 2, False), (300, [96, 128, 128, 128, 32], 2, False),
                                              (640, [40, 72, 24], 1, True), (20000, [125, 128, 256, 512, 256, 64], 1, True)])
