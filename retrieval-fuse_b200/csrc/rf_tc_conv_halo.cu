@@ -224,8 +224,8 @@ struct HaloArgs {
     int N, D, H, W, Hp, Wp;
     int pad, CC, tm5;             // conv padding (0 / 1); real channel chunks (chunk >= CC: all zero); 5-D tensor maps
     long V;                       // slots per haloed sample volume
-    int Dt, Ht, Hs, G, stacked;   // item = G stacked whole samples, or a Dt x Ht x W slab of one sample
-    int n_dt, n_ht, Ls;           // slabs per sample; lines per stacked sample (Dp * Hp)
+    int Dt, Ht, Wt, Hs, G, stacked;  // item = G stacked whole samples, or a Dt x Ht x Wt slab of one sample
+    int n_dt, n_ht, n_wt, Ls;     // slabs per sample; lines per stacked sample (Dp * Hp)
     int lines, n_wblk, n_tiles, P;  // P = slots per staged plane (incl. over-read slack)
     int S_st;                     // staged slots per plane that the bulk copies fill
     int n_stages, nbuf, ck, kpg, n_groups, w0;  // w0: W coordinate of the block's first slot (-pad; 0 for W-runs)
@@ -300,14 +300,14 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
         const int g = a.stacked ? line / a.Ls : 0;
         const int rem = a.stacked ? line % a.Ls : line;
         const int dd = rem / a.Hs, hh = rem % a.Hs;
-        const bool valid = g < a.G && dd < a.Dt && hh < a.Ht && w < a.W;
+        const bool valid = g < a.G && dd < a.Dt && hh < a.Ht && w < a.Wt;
         row_tab[i] = valid ? ((((g * a.D + dd) * a.H + hh) * a.W + w) | (g << 26)) : -1;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
-    const int per_sample = a.n_dt * a.n_ht;
+    const int per_sample = a.n_dt * a.n_ht * a.n_wt;
 
     if (warp == 0) {
       if (lane == 0) {
@@ -319,9 +319,14 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
         const uint32_t plane_bytes = (uint32_t)a.S_st * 16u;
         uint32_t lc = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-            int n0, d0 = 0, h0 = 0;
+            int n0, d0 = 0, h0 = 0, w0 = 0;
             if (a.stacked) { n0 = item * a.G; }
-            else { n0 = item / per_sample; const int r = item % per_sample; d0 = (r / a.n_ht) * a.Dt; h0 = (r % a.n_ht) * a.Ht; }
+            else {
+                n0 = item / per_sample;
+                int r = item % per_sample;
+                w0 = (r % a.n_wt) * a.Wt; r /= a.n_wt;
+                d0 = (r / a.n_ht) * a.Dt; h0 = (r % a.n_ht) * a.Ht;
+            }
             for (int l = 0; l < n_loads; ++l, ++lc) {
                 const int s = l >= a.n_stages ? l - a.n_stages : l;
                 const uint32_t b = lc % (uint32_t)a.nbuf;
@@ -333,8 +338,8 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
                     // a padding chunk (cc >= CC) or the samples past N of a ragged last item lie outside the tensor: zeros
                     const int plane = cc < a.CC ? cc * a.N + n0 : a.CC * a.N;
                     const uint32_t dst = sA + b * abuf_bytes + (uint32_t)pl * (uint32_t)a.P * 16u;
-                    if (a.tm5) tma_load_5d(dst, hl ? &tm_lo : &tm_hi, 0, a.w0, h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
-                    else tma_load_4d(dst, hl ? &tm_lo : &tm_hi, 2 * a.w0, h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
+                    if (a.tm5) tma_load_5d(dst, hl ? &tm_lo : &tm_hi, 0, a.w0 + w0, h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
+                    else tma_load_4d(dst, hl ? &tm_lo : &tm_hi, 2 * (a.w0 + w0), h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
                 }
             }
         }
@@ -452,10 +457,15 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
         const bool vec4 = !a.out_ncdhw && (a.Cout & 3) == 0;
         uint32_t it = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
-            int n0, gact = 1, d0 = 0, h0 = 0;
+            int n0, gact = 1, d0 = 0, h0 = 0, w0 = 0;
             if (a.stacked) { n0 = item * a.G; gact = min(a.G, a.N - n0); }
-            else { n0 = item / per_sample; const int r = item % per_sample; d0 = (r / a.n_ht) * a.Dt; h0 = (r % a.n_ht) * a.Ht; }
-            const long vox0 = (((long)n0 * a.D + d0) * a.H + h0) * a.W;
+            else {
+                n0 = item / per_sample;
+                int r = item % per_sample;
+                w0 = (r % a.n_wt) * a.Wt; r /= a.n_wt;
+                d0 = (r / a.n_ht) * a.Dt; h0 = (r % a.n_ht) * a.Ht;
+            }
+            const long vox0 = (((long)n0 * a.D + d0) * a.H + h0) * a.W + w0;
             const bool dbg = blockIdx.x == 0 && threadIdx.x == 256 && it < 6;
             if (dbg) g_halo_dbg[it * 8 + 4] = clock64();
             const uint32_t set = a.n_sets == 2 ? (it & 1u) : 0u, use = a.n_sets == 2 ? (it >> 1) : it;
@@ -570,6 +580,7 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 struct Geo {
+    int Wt;
     int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, two_resident, n_sets, fused;
     int halo;  // 0: every sample / slab carries its own halo; 1 (stacked, 'same' padding): neighbours share it
     int hd, hw;  // extent of the item's block beyond its outputs in D / H and in W
@@ -590,7 +601,9 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
     // far neighbours of the last voxel of a line / plane / sample are the zero slots that open the next line / plane /
     // sample (the zeroed slack behind the block for the last sample).  51 % of the rows of stacked 4^3 patches are
     // real outputs instead of 30 %.
-    auto consider = [&](int stacked, int G, int Dt, int Ht, int lines, int halo) {
+    const int Wfull = W;
+    auto consider = [&](int stacked, int G, int Dt, int Ht, int Wt, int lines, int halo) {
+        const int W = Wt;  // the item's extent along w (the full line unless the slab is tiled along w too)
         const int hd = halo ? 1 : L.hd, hw = halo ? 1 : L.hw;
         const int Dp = D + hd, Hp = H + hd, Wp = W + hw;
         const long V = (long)Dp * Hp * Wp;
@@ -621,7 +634,7 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
         const long smemA = nbuf * smemA1;
         if (smemA > avail || S_st * 16 * planes >= (1L << 20)) return;
         const long outputs = stacked ? (long)G * D * H * W : (long)Dt * Ht * W;
-        const long n_items = stacked ? (N + G - 1) / G : (long)N * (D / Dt) * (H / Ht);
+        const long n_items = stacked ? (N + G - 1) / G : (long)N * (D / Dt) * (H / Ht) * (Wfull / Wt);
         // Cost model, calibrated on B200 (tools/halo_geo_sweep.sh): an M128 K16 MMA occupies the tensor pipe for ~40
         // (N <= 32) to 48 (N = 64) cycles, one issuer warp sustains one MMA per ~150 cycles, the epilogue costs ~1200
         // cycles per (tile pair, 16 columns), and every item pays ~3000 cycles of pipeline fill.  Accumulators are
@@ -649,11 +662,16 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
                 const double per_step = fused ? fmax(pipe_cycles(2 * Npad), issue) + fmax(pipe_cycles(Npad), issue)
                                               : 3.0 * fmax(pipe_cycles(Npad), issue);
                 const double t_mma = k_steps * per_step;
-                const double t_epi = 1000.0 + (double)((n_tiles + 1) / 2) * (tile_cols / 16) * 1200.0 + (nbuf == 1 ? 4000.0 : 0.0);
-                const double t_item = (fused ? 2000.0 : 3000.0) +
-                                      (n_sets == 2 ? fmax(t_mma, t_epi) : t_mma + (two_resident ? 0.3 : 1.0) * t_epi);
+                const double t_epi = 1000.0 + (double)((n_tiles + 1) / 2) * (tile_cols / 16) * 1200.0;
+                // staging: ~25 bytes per clock and SM from L2 when every SM pulls (decoder 16 -> 16 @ 64^3: 127 KB per
+                // item in ~5000 cycles); hidden behind the MMAs only with a second buffer or a second resident CTA
+                const double n_loads = n_stages == 1 ? 1.0 : (fused ? 1.0 : 2.0) * n_stages;
+                const double t_load = (double)planes * (double)S_st * 16.0 * n_loads / 25.0;
+                const double t_core = n_sets == 2 ? fmax(t_mma, t_epi) : t_mma + (two_resident ? 0.3 : 1.0) * t_epi;
+                const double t_item = (fused ? 2000.0 : 3000.0) + ((nbuf == 2 || two_resident) ? fmax(t_core, t_load) : t_core + t_load);
                 const double score = (double)outputs * (double)n_items / (waves * t_item);
                 if (score > best.score) {
+                    best.Wt = Wt;
                     best.Dt = stacked ? D : Dt; best.Ht = stacked ? H : Ht; best.Hs = Hs; best.G = stacked ? G : 1; best.stacked = stacked;
                     best.lines = lines; best.n_wblk = n_wblk; best.n_tiles = (int)n_tiles; best.P = (int)P; best.S_st = (int)S_st;
                     best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot; best.two_resident = two_resident ? 1 : 0;
@@ -668,20 +686,28 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
     if (const char* e = getenv("RF_HALO_GEO")) {  // tuning aid: "stacked,G,Dt,Ht,lines" forces the item shape
         int st, G, Dt, Ht, ln, hl = 0;
         if (sscanf(e, "%d,%d,%d,%d,%d,%d", &st, &G, &Dt, &Ht, &ln, &hl) >= 5) {
-            consider(st, G, st ? D : Dt, st ? H : Ht, ln, st && shareable && hl == 1 ? 1 : 0);
+            int wt = W;
+            if (const char* e2 = getenv("RF_HALO_WT")) wt = atoi(e2);
+            consider(st, G, st ? D : Dt, st ? H : Ht, st || W % wt ? W : wt, ln, st && shareable && hl == 1 ? 1 : 0);
             return best.score > 0.0;
         }
     }
     for (int lines = 0; lines < 2; ++lines) {
         for (int G = 1; G <= 32 && G <= N; ++G) {  // (the row table keeps the stacked sample index in 5 bits)
-            consider(1, G, D, H, lines, 0);
-            if (shareable) consider(1, G, D, H, lines, 1);
+            consider(1, G, D, H, W, lines, 0);
+            if (shareable) consider(1, G, D, H, W, lines, 1);
         }
         for (int Dt = 1; Dt <= D; ++Dt) {
             if (D % Dt) continue;
             for (int Ht = 1; Ht <= H; ++Ht) {
                 if (H % Ht) continue;
-                consider(0, 1, Dt, Ht, lines, 0);
+                // long lines may be tiled along w as well (halves, quarters, ...: the block's halo overhead and the
+                // bytes staged per item shrink, two staging buffers fit)
+                for (int Wt = W; Wt >= 8; Wt >>= 1) {
+                    if (W % Wt) break;
+                    consider(0, 1, Dt, Ht, Wt, lines, 0);
+                    if (Wt <= 16) break;
+                }
             }
         }
     }
@@ -735,11 +761,11 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
                  N, D, H, W, L.Cout, L.C1, L.C2, L.KS);
     HaloArgs a;
     a.wimg = (const uint8_t*)weight_image; a.bias = bias; a.y = y;
-    a.N = N; a.D = D; a.H = H; a.W = W; a.Hp = H + g.hd; a.Wp = W + g.hw;
+    a.N = N; a.D = D; a.H = H; a.W = W; a.Hp = H + g.hd; a.Wp = g.Wt + g.hw;
     a.pad = pad; a.CC = L.CC; a.w0 = L.mode == 2 ? 0 : -pad;
     a.V = (long)(D + g.hd) * (H + g.hd) * (W + g.hw);
-    a.Dt = g.Dt; a.Ht = g.Ht; a.Hs = g.Hs; a.G = g.G; a.stacked = g.stacked;
-    a.n_dt = D / g.Dt; a.n_ht = H / g.Ht; a.Ls = (D + g.hd) * (H + g.hd);
+    a.Dt = g.Dt; a.Ht = g.Ht; a.Wt = g.Wt; a.Hs = g.Hs; a.G = g.G; a.stacked = g.stacked;
+    a.n_dt = D / g.Dt; a.n_ht = H / g.Ht; a.n_wt = W / g.Wt; a.Ls = (D + g.hd) * (H + g.hd);
     a.lines = g.lines; a.n_wblk = g.n_wblk; a.n_tiles = g.n_tiles; a.P = g.P; a.S_st = g.S_st;
     a.n_stages = L.n_stages; a.nbuf = g.nbuf; a.ck = L.ck; a.kpg = L.kpg; a.n_groups = L.n_groups;
     a.Cout = L.Cout; a.Npad = L.Npad; a.act = act; a.out_ncdhw = out_ncdhw; a.slope = slope; a.out_scale = out_scale;
@@ -770,7 +796,7 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
     // tensor maps of the compact planes [CC * N][Din][Hin][Win] x 16 B, seen as 8-byte words so that a whole line of
     // the item's block is the innermost box extent (<= 256 elements)
     const int Din = D + L.hd - 2 * pad, Hin = H + L.hd - 2 * pad, Win = L.mode == 2 ? W : W + L.hw - 2 * pad;
-    const int bW = W + g.hw, bD = g.stacked ? D + g.hd : g.Dt + L.hd;  // the item's box (its H extent is g.Hs)
+    const int bW = g.Wt + g.hw, bD = g.stacked ? D + g.hd : g.Dt + L.hd;  // the item's box (its H extent is g.Hs)
     RF_CHECK_ARG(bW <= 256 && g.Hs <= 256 && bD <= 256 && g.G <= 256, "rf_tc_conv3d_halo_fwd: item box exceeds the TMA limits");
     a.tm5 = 2 * bW > 256 ? 1 : 0;  // a line longer than 256 words: slots as a dimension of their own
     CUtensorMap tm[2];
