@@ -17,6 +17,8 @@
 //   * the layer epilogue (all 8 worker warps) reads TMEM, adds bias, applies the activation, splits to fp16
 //     hi / lo and writes the next layer's operand planes; the last layer optionally L2-normalises rows and
 //     writes fp32 output.
+#include <stdlib.h>
+
 #include "rf_tc_common.cuh"
 
 namespace {
@@ -70,6 +72,8 @@ struct MlpArgs {
     float slope, eps;
     uint32_t slot_bytes;
     int nbw, n_tiles;
+    int act_chunks;        // 8-channel chunk planes resident per hi / lo (32 = 256 channels; 16 when no layer is wider than 128)
+    uint32_t act_bytes, tmem_cols;
 };
 
 // TMEM columns [c0, c1) of the finished layer (bias, activation) -> operand planes, chunks from 0
@@ -112,18 +116,21 @@ __device__ __forceinline__ void convert_slab(const MlpArgs& a, int l, int c0, in
             for (int e = 0; e < 8; e += 2) split_f16x2(v[8 * c + e], v[8 * c + e + 1], h[e >> 1], lw[e >> 1]);
             uint8_t* p = act_hi + (size_t)(((cb - c0) >> 3) + c) * PLANE + row * 16;
             *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4*>(p + ACT_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            *reinterpret_cast<uint4*>(p + a.act_bytes) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
+// RES = 2: narrow chains (no layer wider than 128: the attention's theta / phi) need half the operand planes and a
+// quarter of the TMEM columns, so two CTAs share an SM and one's conversion phases overlap the other's MMAs.
+template <int RES>
+__global__ void __launch_bounds__(NTHREADS, RES) tc_mlp_kernel(const MlpArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sACT = base;                       // hi planes, then lo planes
-    const uint32_t sW = base + 2 * ACT_BYTES;
+    const uint32_t sW = base + 2 * a.act_bytes;
     const uint32_t bars = sW + (uint32_t)a.nbw * a.slot_bytes;
     const uint32_t bar_wfull = bars, bar_wempty = bars + 8 * MAX_SLOTS, bar_mma = bars + 16 * MAX_SLOTS;
     const uint32_t tmem_slot = bar_mma + 8;
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(a.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
                     for (int e = 0; e < 8; e += 2) split_f16x2(f[e], f[e + 1], h[e >> 1], lw[e >> 1]);
                     uint8_t* p = act_hi + (size_t)c * PLANE + row * 16;
                     *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4*>(p + ACT_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    *reinterpret_cast<uint4*>(p + a.act_bytes) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
@@ -217,8 +224,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
                 if (dbg) g_mlp_dbg[2 + 3 * l] = clock64();
                 const int Kp = l == 0 ? a.K0p : a.Np[l - 1];
                 const int nks = Kp >> 4, Np = a.Np[l];
-                for (int ks0 = 0; ks0 < nks; ks0 += ACT_CHUNKS / 2) {  // slabs of 16 k steps = 256 input channels
-                    const int ks1 = min(nks, ks0 + ACT_CHUNKS / 2);
+                for (int ks0 = 0; ks0 < nks; ks0 += a.act_chunks / 2) {  // slabs of 16 k steps = 256 input channels
+                    const int ks1 = min(nks, ks0 + a.act_chunks / 2);
                     if (ks0 > 0) {  // next 256 input channels: still in TMEM as the previous layer's columns
                         convert_slab(a, l - 1, ks0 * 16, ks1 * 16, tmem_base, act_hi, tid);
                         tc_fence_before();
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
                                 const uint32_t db = ((((sW + sl * a.slot_bytes) & 0x3FFFFu) >> 4) | b_lbo) + (uint32_t)(iss * 128);
                                 const uint32_t db_lo = db + (uint32_t)(2 * Np);       // lo block: 2 * Np * 16 bytes further
                                 tc_mma2(d, da, a_hi32, db_lo, b_hi32, idesc, ks > 0 ? 1u : 0u, leader);            // hi * lo
-                                tc_mma2(d, da + (ACT_BYTES >> 4), a_hi32, db, b_hi32, idesc, 1u, leader);          // lo * hi
+                                tc_mma2(d, da + (a.act_bytes >> 4), a_hi32, db, b_hi32, idesc, 1u, leader);          // lo * hi
                                 tc_mma2(d, da, a_hi32, db, b_hi32, idesc, 1u, leader);                             // hi * hi
                                 if (leader) tc_commit(bar_wempty + 8 * sl);
                             } else if (leader) {
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpArgs a) {
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
     }
 }
 
@@ -404,7 +411,8 @@ extern "C" int rf_tc_mlp_weight_image(const float* w, int N, int K, void* image,
 }
 
 int rf_tc_mlp_init() {
-    RF_SMEM_OPT_IN(tc_mlp_kernel, SMEM_LIMIT);
+    RF_SMEM_OPT_IN(tc_mlp_kernel<1>, SMEM_LIMIT);
+    RF_SMEM_OPT_IN(tc_mlp_kernel<2>, SMEM_LIMIT);
     return 0;
 }
 
@@ -431,19 +439,29 @@ extern "C" int rf_tc_mlp_fwd(const float* x, int ldx, const void* const* images_
     RF_CHECK_ARG(a.K0p <= 8 * ACT_CHUNKS, "rf_tc_mlp_fwd: input wider than 256 channels");
     a.act = act; a.slope = slope; a.l2norm = l2_normalize; a.eps = eps;
     a.slot_bytes = 64u * (uint32_t)max_np;
-    const long avail = (long)SMEM_LIMIT - 1024 - 2L * ACT_BYTES - (16 * MAX_SLOTS + 32 + 1024 + 64);
+    // narrow chain: every layer input and output fits 128 channels -> half the operand planes, 128 TMEM columns, a
+    // shared-memory footprint that lets two CTAs share an SM
+    static const int force_wide = [] { const char* e = getenv("RF_MLP_WIDE"); return e ? atoi(e) : 0; }();  // tuning aid
+    const bool narrow = !force_wide && max_np <= 128 && a.K0p <= 128;
+    a.act_chunks = narrow ? 16 : ACT_CHUNKS;
+    a.act_bytes = (uint32_t)a.act_chunks * PLANE;
+    a.tmem_cols = narrow ? 128u : 512u;
+    const long misc = 16 * MAX_SLOTS + 32 + 1024 + 64;
+    const long avail = (narrow ? 113L * 1024 : (long)SMEM_LIMIT) - 1024 - 2L * a.act_bytes - misc;
     long nbw = avail / a.slot_bytes;
     if (nbw > MAX_SLOTS) nbw = MAX_SLOTS;
     RF_CHECK_ARG(nbw >= 2, "rf_tc_mlp_fwd: weight ring does not fit");
     a.nbw = (int)nbw;
     a.n_tiles = (int)rf_cdivl(M, TM);
-    const size_t smem = 1024 + 2 * (size_t)ACT_BYTES + (size_t)a.nbw * a.slot_bytes + 16 * MAX_SLOTS + 32 + 1024 + 64;
+    const size_t smem = 1024 + 2 * (size_t)a.act_bytes + (size_t)a.nbw * a.slot_bytes + misc;
     if (int rc = rf_tc_mlp_init()) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = a.n_tiles < sms ? a.n_tiles : sms;
-    tc_mlp_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+    const int slots = narrow ? 2 * sms : sms;
+    const int grid = a.n_tiles < slots ? a.n_tiles : slots;
+    if (narrow) tc_mlp_kernel<2><<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+    else tc_mlp_kernel<1><<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
     RF_LAUNCH_OK("tc_mlp_kernel");
     return 0;
 }
