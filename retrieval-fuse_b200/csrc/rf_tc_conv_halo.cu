@@ -229,7 +229,8 @@ struct HaloArgs {
     int lines, n_wblk, n_tiles, P;  // P = slots per staged plane (incl. over-read slack)
     int S_st;                     // staged slots per plane that the bulk copies fill
     int n_stages, nbuf, ck, kpg, n_groups, w0;  // w0: W coordinate of the block's first slot (-pad; 0 for W-runs)
-    int Cout, Npad, act, out_ncdhw, n_iss, n_items, n_sets, fused;
+    int Cout, Npad, act, out_ncdhw, n_iss, n_items, n_sets;
+    int n_fused;  // tiles [0, n_fused) use the fused cross-product scheme (2 Npad accumulator columns), the rest two passes
     float slope, out_scale;
     uint32_t bslot_bytes, tmem_cols;
     uint16_t tile_off[32];        // first slot of M tile t within the staged block (uniform-indexed constant loads)
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
         // ---- activation producer: one stage = ck channel chunks x (hi, lo) planes of the item's haloed block (one
         // TMA tile copy per plane); two passes over the channel stages (cross products first, then hi * hi; see the
         // issuers)
-        const int n_pass = a.fused ? 1 : 2;
+        const int n_pass = a.n_fused == a.n_tiles ? 1 : 2;
         const int n_loads = resident ? 1 : n_pass * a.n_stages;
         const uint32_t plane_bytes = (uint32_t)a.S_st * 16u;
         uint32_t lc = 0;
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
     } else if (warp == 3) {
       if (lane == 0) {
         // ---- weight producer: ring of (kd,kh) groups; the second pass of every item streams the same groups again
-        const int per_pass = a.n_stages * a.n_groups, n_pass = a.fused ? 1 : 2;
+        const int per_pass = a.n_stages * a.n_groups, n_pass = a.n_fused == a.n_tiles ? 1 : 2;
         uint32_t gc = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x)
             for (int gi = 0; gi < n_pass * per_pass; ++gi, ++gc) {
@@ -377,8 +378,9 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
             const uint32_t b_lbo = (uint32_t)(2 * a.Npad) << 16;  // K chunks of a k step are 2 Npad rows apart
             const uint32_t step_u = (uint32_t)a.Npad * 4u;        // one k step of weights, in 16-byte units
             const uint32_t lo_off = (uint32_t)(a.ck * a.P);     // hi -> lo plane, in slots
-            const uint32_t npad = (uint32_t)a.Npad, tile_cols = a.fused ? 2u * npad : npad, set_cols = (uint32_t)a.n_tiles * tile_cols;
-            const int n_vs = (a.fused ? 1 : 2) * a.n_stages;
+            const uint32_t npad = (uint32_t)a.Npad, nf = (uint32_t)a.n_fused;
+            const uint32_t set_cols = (nf + (uint32_t)a.n_tiles) * npad;  // fused tiles take 2 Npad columns
+            const int n_vs = (a.n_fused == a.n_tiles ? 1 : 2) * a.n_stages;
             // The tensor core truncates when it aligns the 16 products of a K step with the fp32 accumulator, a
             // bias that grows with the number of accumulations at full magnitude (measured: error linear in the
             // MMA count).  So the two small cross products (hi*lo, lo*hi: 2^-11 of the result) of ALL taps and
@@ -420,9 +422,11 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
                             const uint32_t b_hi = bbase + (uint32_t)ks * step_u, b_lo = b_hi + npad;  // lo rows follow the hi rows
                             const uint32_t acc = (vs | g | ks) ? 1u : 0u;  // the very first MMA of a tile overwrites its accumulator
                             for (int t = iss; t < a.n_tiles; t += a.n_iss) {
-                                const uint32_t d = tmem_u + set * set_cols + (uint32_t)t * tile_cols;
+                                const bool tf = (uint32_t)t < nf;
+                                const uint32_t d = tmem_u + set * set_cols + ((uint32_t)t + (tf ? (uint32_t)t : nf)) * npad;
                                 const uint32_t da = abase + kt + a.tile_off[t];
-                                if (a.fused) {
+                                if (tf) {
+                                    if (pass) continue;  // (mixed items: the second pass serves the two-pass tiles only)
                                     // A_hi x [W_hi; W_lo] as ONE N = 2 Npad MMA -> columns [main | cross]; A_lo x W_hi into
                                     // the cross block.  For N <= 64 the pipe time is set by reading the A operand, so
                                     // the doubled N is almost free: two MMAs instead of three, one pass over the stages,
@@ -469,8 +473,8 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
             const bool dbg = blockIdx.x == 0 && threadIdx.x == 256 && it < 6;
             if (dbg) g_halo_dbg[it * 8 + 4] = clock64();
             const uint32_t set = a.n_sets == 2 ? (it & 1u) : 0u, use = a.n_sets == 2 ? (it >> 1) : it;
-            const uint32_t tile_cols = a.fused ? 2u * (uint32_t)a.Npad : (uint32_t)a.Npad;
-            const uint32_t tm_set = tmem_base + set * (uint32_t)a.n_tiles * tile_cols;
+            const uint32_t npad = (uint32_t)a.Npad, nf = (uint32_t)a.n_fused;
+            const uint32_t tm_set = tmem_base + set * (nf + (uint32_t)a.n_tiles) * npad;
             mbar_wait_warp_sleepy(bar_dfull + 8 * set, use & 1u);
             tc_fence_after();
             if (dbg) g_halo_dbg[it * 8 + 5] = clock64();
@@ -481,14 +485,15 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
             const int n_my = ((a.n_tiles - half + 1) >> 1) * nblk;
             auto issue = [&](int j, float* v, float* u) {
                 const int t = half + 2 * (j / nblk), c0 = (j % nblk) << 4;
-                const uint32_t ta = tm_set + ((uint32_t)(q * 32) << 16) + (uint32_t)t * tile_cols + (uint32_t)c0;
+                const bool tf = (uint32_t)t < nf;
+                const uint32_t ta = tm_set + ((uint32_t)(q * 32) << 16) + ((uint32_t)t + (tf ? (uint32_t)t : nf)) * npad + (uint32_t)c0;
                 tc_ld16_issue(ta, v);
-                if (a.fused) tc_ld16_issue(ta + (uint32_t)a.Npad, u);  // main + cross blocks
+                if (tf) tc_ld16_issue(ta + npad, u);  // main + cross blocks
             };
             auto process = [&](int j, float* v, float* u) {
                 tc_ld_fence16(v);
                 const int t = half + 2 * (j / nblk), c0 = (j % nblk) << 4;
-                if (a.fused) {
+                if ((uint32_t)t < nf) {
                     tc_ld_fence16(u);
 #pragma unroll
                     for (int e = 0; e < 16; ++e) v[e] += u[e];
@@ -581,7 +586,7 @@ EncodeTiledFn encode_tiled_fn() {
 
 struct Geo {
     int Wt;
-    int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, two_resident, n_sets, fused;
+    int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, two_resident, n_sets, fused, n_fused;
     int halo;  // 0: every sample / slab carries its own halo; 1 (stacked, 'same' padding): neighbours share it
     int hd, hw;  // extent of the item's block beyond its outputs in D / H and in W
     uint32_t tmem_cols, bslot;
@@ -647,28 +652,40 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
         const char* force = getenv("RF_HALO_FUSED");  // tuning aid: "0" / "1" forces the MMA scheme
         // fused = 1: two MMAs per step, A_hi x [W_hi; W_lo] (N = 2 Npad) and A_lo x W_hi, accumulators [main | cross]
         // of 2 Npad columns per tile, one pass over the stages; fused = 0: three N = Npad MMAs in two passes.
-        for (int fused = 0; fused < 2; ++fused) {
-            if (force && atoi(force) != fused) continue;
-            const int tile_cols = fused ? 2 * Npad : Npad;
+        // fused = 2 ("mixed"): when TMEM cannot hold 2 Npad columns for every tile, as many leading tiles as fit use the
+        // fused scheme and the rest the two-pass scheme (96 -> 56 @ 8^3: 3 of 5 tiles; two passes over the stages, the
+        // second serves only the two-pass tiles).  Measured on that layer: 2.25 ms against 2.12 ms for plain two-pass
+        // (the second pass leaves three of five issuers idle and becomes issue-bound), so it is only reachable through
+        // RF_HALO_FUSED=2.
+        for (int fused = 0; fused < 3; ++fused) {
+            if (force ? atoi(force) != fused : fused == 2) continue;
             if (fused && 2 * Npad > 256) continue;
             for (int n_sets = 1; n_sets <= 2; ++n_sets) {
-                if ((long)n_sets * n_tiles * tile_cols > 512) break;
+                int n_fused = fused == 1 ? (int)n_tiles : 0;
+                if (fused == 2) {  // only where the fused scheme cannot cover every tile even with one accumulator set
+                    if (n_sets == 2 || 2L * Npad * n_tiles <= 512) continue;
+                    n_fused = (int)((512 - n_tiles * Npad) / Npad);
+                    if (n_fused < 1 || n_fused >= n_tiles) continue;
+                }
+                const long cols = (long)(n_tiles + n_fused) * Npad;
+                if ((long)n_sets * cols > 512) break;
                 uint32_t cols_needed = 32;
-                while ((long)cols_needed < n_tiles * tile_cols * n_sets) cols_needed <<= 1;
+                while ((long)cols_needed < cols * n_sets) cols_needed <<= 1;
+                const int tile_cols = (int)(cols / n_tiles);  // average, for the epilogue estimate
                 const long smem_total = 1024 + smemA + (long)NB * bslot + 256 + n_tiles * 512;
                 static const int force_res = [] { const char* e = getenv("RF_HALO_RES"); return e ? atoi(e) : 0; }();  // tuning aid
                 const bool two_resident = force_res != 1 && smem_total <= 113 * 1024 && cols_needed <= 256;
                 const double issue = 150.0 / (n_iss * (two_resident ? 2 : 1));
-                const double per_step = fused ? fmax(pipe_cycles(2 * Npad), issue) + fmax(pipe_cycles(Npad), issue)
-                                              : 3.0 * fmax(pipe_cycles(Npad), issue);
-                const double t_mma = k_steps * per_step;
-                const double t_epi = 1000.0 + (double)((n_tiles + 1) / 2) * (tile_cols / 16) * 1200.0;
+                const double step_fused = fmax(pipe_cycles(2 * Npad), issue) + fmax(pipe_cycles(Npad), issue);
+                const double step_two = 3.0 * fmax(pipe_cycles(Npad), issue);
+                const double t_mma = (double)n_stages * L.n_groups * kpg * (n_fused * step_fused + (n_tiles - n_fused) * step_two);
+                const double t_epi = 1000.0 + (double)((n_tiles + 1) / 2) * ((tile_cols + 15) / 16) * 1200.0;
                 // staging: ~25 bytes per clock and SM from L2 when every SM pulls (decoder 16 -> 16 @ 64^3: 127 KB per
                 // item in ~5000 cycles); hidden behind the MMAs only with a second buffer or a second resident CTA
-                const double n_loads = n_stages == 1 ? 1.0 : (fused ? 1.0 : 2.0) * n_stages;
+                const double n_loads = n_stages == 1 ? 1.0 : (fused == 1 ? 1.0 : 2.0) * n_stages;
                 const double t_load = (double)planes * (double)S_st * 16.0 * n_loads / 25.0;
                 const double t_core = n_sets == 2 ? fmax(t_mma, t_epi) : t_mma + (two_resident ? 0.3 : 1.0) * t_epi;
-                const double t_item = (fused ? 2000.0 : 3000.0) + ((nbuf == 2 || two_resident) ? fmax(t_core, t_load) : t_core + t_load);
+                const double t_item = (fused == 1 ? 2000.0 : 3000.0) + ((nbuf == 2 || two_resident) ? fmax(t_core, t_load) : t_core + t_load);
                 const double score = (double)outputs * (double)n_items / (waves * t_item);
                 if (score > best.score) {
                     best.Wt = Wt;
@@ -676,7 +693,7 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
                     best.lines = lines; best.n_wblk = n_wblk; best.n_tiles = (int)n_tiles; best.P = (int)P; best.S_st = (int)S_st;
                     best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot; best.two_resident = two_resident ? 1 : 0;
                     best.tmem_cols = cols_needed;
-                    best.n_sets = n_sets; best.fused = fused; best.halo = halo; best.hd = hd; best.hw = hw;
+                    best.n_sets = n_sets; best.fused = fused; best.n_fused = n_fused; best.halo = halo; best.hd = hd; best.hw = hw;
                     best.smem = (size_t)smem_total;
                     best.score = score;
                 }
@@ -792,7 +809,7 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
         a.ktab[i] = (uint32_t)off | ((uint32_t)lbo << 16);
     }
     if (int rc = conv_init()) return rc;
-    a.n_items = g.n_items; a.n_sets = g.n_sets; a.fused = g.fused;
+    a.n_items = g.n_items; a.n_sets = g.n_sets; a.n_fused = g.n_fused;
     // tensor maps of the compact planes [CC * N][Din][Hin][Win] x 16 B, seen as 8-byte words so that a whole line of
     // the item's block is the innermost box extent (<= 256 elements)
     const int Din = D + L.hd - 2 * pad, Hin = H + L.hd - 2 * pad, Win = L.mode == 2 ? W : W + L.hw - 2 * pad;
@@ -927,7 +944,7 @@ extern "C" int rf_tc_conv3d_halo_geometry(int N, int D, int H, int W, int Cout, 
     if (!make_layer(Cout, C1, C2, 3, false, L)) return 0;
     Geo g;
     if (!choose_geometry(N, D + 2 * pad - 2, H + 2 * pad - 2, W + 2 * pad - 2, L, pad, g)) return 0;
-    out8[0] = g.stacked; out8[1] = g.G; out8[2] = g.Dt; out8[3] = g.Ht; out8[4] = g.lines + 2 * g.fused + 4 * (g.halo == 1); out8[5] = g.n_tiles;
+    out8[0] = g.stacked; out8[1] = g.G; out8[2] = g.Dt; out8[3] = g.Ht; out8[4] = g.lines + 2 * (g.fused != 0) + 4 * (g.halo == 1) + 8 * (g.fused == 2); out8[5] = g.n_tiles;
     out8[6] = g.n_items; out8[7] = (int)g.smem;
     return 1;
 }
