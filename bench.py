@@ -888,6 +888,9 @@ def run_ours(args, rank, local, world):
                          "call per step" if args.full_like else "pipeline call with pinned host tensors in and out, one synchronous call per step"))}
         if e2e_pipe_value:
             e2e["sync_value"] = e2e_value
+        if args.workload == "retrieval" and args.bank == "random":
+            e2e["note"] = ("the host-buffer call encodes the synthetic chunks, so its queries are the encoded ones against the random "
+                           "bank; the isotropic queries of `value` exist on the device only - not comparable with `value`")
         line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (tcgen05 fp16 hi/lo split products, fp32 accumulate) / f64 distance ranking", "data": "synthetic",
