@@ -653,6 +653,18 @@ def run_ours(args, rank, local, world):
         def e2e_step():
             return pipe.infer_host(chunks_host, out_host, None, args.knn_method, rb, use_graph)
 
+        out_host2 = torch.empty((B, 1, 64, 64, 64), dtype=torch.float32).pin_memory()
+
+        def e2e_pipelined(n):
+            """n batches through the two-deep host pipeline: every batch pays its own H2D and D2H inside the timed
+            region; the D2H copy of batch i's prediction overlaps the kernels of batch i+1."""
+            pending = []
+            for i in range(n):
+                pending.append(pipe.infer_host_async(chunks_host, (out_host, out_host2)[i & 1], None, args.knn_method, rb, use_graph, slot=i)[1])
+                if len(pending) > 1:
+                    pending.pop(0).synchronize()  # the prediction of batch i-1 is in host memory
+            pending[-1].synchronize()
+
         def profile_step():
             pipe.infer(chunks, None, args.knn_method, rb, False)
 
@@ -882,7 +894,9 @@ def run_ours(args, rank, local, world):
                             **({"gbs": round(v["bytes"] / v["ms"] / 1e6, 1)} if v["bytes"] else {})}
                         for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
         e2e = {"value": e2e_pipe_value or e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "call": ("RetrievalPipeline.retrieve_host_async: host buffers in and out, two batches in flight"
+               "call": (("RefinementPipeline.infer_host_async: pinned host chunks in, pinned host predictions out, the D2H copy of a "
+                         "batch overlaps the kernels of the next (two slots); sync_value = infer_host, one synchronous call per step"
+                         if args.full_like else "RetrievalPipeline.retrieve_host_async: host buffers in and out, two batches in flight")
                         if e2e_pipe_value else
                         ("RefinementPipeline.infer_host: pinned host chunks in, pinned host predictions out, one synchronous "
                          "call per step" if args.full_like else "pipeline call with pinned host tensors in and out, one synchronous call per step"))}

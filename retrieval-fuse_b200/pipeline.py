@@ -364,6 +364,38 @@ class RefinementPipeline(RetrievalPipeline):
         torch.cuda.current_stream(self.device).synchronize()
         return out_host
 
+    def infer_host_async(self, chunks_host, out_host, chunk_scene=None, method=0, refine_batch=None, graphed=True, slot=0):
+        """infer_host without the final wait, for a two-deep pipeline over batches: the kernels of every batch run on the
+        current stream, the device->host copy of batch i's prediction runs on copy stream `slot` (0 / 1, alternate them,
+        with one out_host buffer per slot) and overlaps the kernels of batch i+1.  Returns (out_host, event): the
+        prediction is in host memory after event.synchronize(); a slot may be reused once its previous event was waited
+        for."""
+        cur = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_copy_streams"):
+            self._copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+            self._copy_events = [None, None]
+            self._pred_slots = {}
+        k = slot & 1
+        B, c = chunks_host.shape[0], self.ds["target_chunk_size"]
+        key = (k, B)
+        if key not in self._pred_slots:
+            self._pred_slots[key] = torch.empty((B, 1, c, c, c), dtype=torch.float32, device=self.device)
+        pred = self._pred_slots[key]
+        if self._copy_events[k] is not None:
+            cur.wait_event(self._copy_events[k])  # the slot's device buffer is still being copied out
+        x = chunks_host.to(self.device, non_blocking=True)
+        self.infer(x, chunk_scene, method, refine_batch, graphed, out=pred)
+        done = torch.cuda.Event()
+        done.record(cur)
+        cs = self._copy_streams[k]
+        cs.wait_event(done)
+        with torch.cuda.stream(cs):
+            out_host.copy_(pred, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._copy_events[k] = ev
+        return out_host, ev
+
     def retrieve_and_refine(self, chunks, chunk_scene=None, method=0):
         B = chunks.shape[0]
         rows, idx = self.retrieve(chunks, chunk_scene, method)

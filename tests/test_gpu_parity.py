@@ -1005,6 +1005,31 @@ def test_host_pipeline_matches_synchronous_call(dev):
         assert torch.equal(w, g)
 
 
+def test_full_path_host_pipeline_matches_synchronous_call(dev):
+    """RefinementPipeline.infer_host_async (the D2H copy of a batch overlaps the kernels of the next, two slots) returns
+    exactly what infer_host does, batch after batch."""
+    from retrieval_fuse_b200.pipeline import FRONT3D_SR, RefinementPipeline, build_bank_from_targets, synthetic_tsdf_batch
+    d = FRONT3D_SR["dataset"]
+    targets = synthetic_tsdf_batch(6, 64, d["voxel_size_target"], seed=33, device=dev)
+    bank, _ = build_bank_from_targets(FRONT3D_SR, targets, dev, weight_seed=3)
+    pipe = RefinementPipeline(FRONT3D_SR, bank, targets, device=dev, weight_seed=5)
+    batches = [synthetic_tsdf_batch(4, 8, d["voxel_size_input"], seed=70 + i, device=dev).unsqueeze(1).cpu().pin_memory() for i in range(5)]
+    host = [torch.empty((4, 1, 64, 64, 64), dtype=torch.float32).pin_memory() for _ in range(3)]
+    want = [pipe.infer_host(b, host[2], refine_batch=2).clone() for b in batches]
+    got, pending = [], []
+    for i, b in enumerate(batches):
+        pending.append(pipe.infer_host_async(b, host[i & 1], refine_batch=2, slot=i))
+        if len(pending) > 1:
+            out, ev = pending.pop(0)
+            ev.synchronize()
+            got.append(out.clone())
+    out, ev = pending.pop(0)
+    ev.synchronize()
+    got.append(out.clone())
+    for w, g in zip(want, got):
+        assert torch.equal(w, g)
+
+
 def test_surface_reconstruction_config_end_to_end(dev):
     """BASELINE config 4 shapes: 128^3 occupancy grid of a point cloud -> PCPatch48 queries -> kNN against a
     Patch24 bank -> compose -> 5-level U-Net (nf 12) + retrieval U-Net + attention (K = 8) + decoder, vs the oracle."""
