@@ -180,6 +180,13 @@ int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void* weight_ima
                           int H, int W, int pad, int Cout, int C1, int C2, int act, float slope, float out_scale,
                           int out_ncdhw, void* stream);
 
+/* Stride-2 'valid' 3x3x3 layers (the down-sampling Conv3d of the conv patch encoders, model/retrieval.py:4-28,187-275)
+ * on the same kernel: planes of rf_cl_norm_split_halo (pad 0), weight image of rf_tc_conv_halo_weight_image; the item's
+ * block is staged as its 8 parity sub-blocks (TMA boxes with element strides 2).  D, H, W: INPUT extents. */
+int rf_tc_conv3d_halo_s2_supported(int N, int D, int H, int W, int Cout, int C1);
+int rf_tc_conv3d_halo_s2_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D,
+                             int H, int W, int Cout, int C1, int act, float slope, float out_scale, int out_ncdhw, void* stream);
+
 /* Single-input-channel layers on the same kernel (the first Conv3d of every patch
  * encoder, model/retrieval.py:4-388, kernel edge 3 or 5, no padding; the first
  * SingleConv of the U-Nets, model/unet.py:79-100, 3^3 'same'): the slot of voxel

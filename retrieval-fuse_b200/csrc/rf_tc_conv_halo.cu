@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs
 // Steps are grouped kpg at a time into the weight ring's slots (n_groups groups per stage; padded steps carry zero
 // weights).  Image: [stage][group][k step][K chunk][hi rows | lo rows (Npad each)][16 B].
 struct Layer {
-    int mode, KS;
+    int mode, KS, stride;  // stride 2: 'valid' 3^3 only (the patch encoders' down-sampling layers)
     int C1, C2, Cp1, Cp2, CC, CCe, Cout, Npad;
     int ck, n_stages, kpg, n_groups;
     int hd, hw;  // block extent beyond the output extent: D / H (KS - 1) and W (KS - 1; 0 in mode 2)
@@ -223,6 +223,7 @@ struct HaloArgs {
     float* y;
     int N, D, H, W, Hp, Wp;
     int pad, CC, tm5;             // conv padding (0 / 1); real channel chunks (chunk >= CC: all zero); 5-D tensor maps
+    int s2, P_sub;                // stride 2: 8 parity sub-blocks per plane, P_sub slots apart
     long V;                       // slots per haloed sample volume
     int Dt, Ht, Wt, Hs, G, stacked;  // item = G stacked whole samples, or a Dt x Ht x Wt slab of one sample
     int n_dt, n_ht, n_wt, Ls;     // slabs per sample; lines per stacked sample (Dp * Hp)
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
         // issuers)
         const int n_pass = a.n_fused == a.n_tiles ? 1 : 2;
         const int n_loads = resident ? 1 : n_pass * a.n_stages;
-        const uint32_t plane_bytes = (uint32_t)a.S_st * 16u;
+        const uint32_t plane_bytes = (uint32_t)a.S_st * 16u * (a.s2 ? 8u : 1u);
         uint32_t lc = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
             int n0, d0 = 0, h0 = 0, w0 = 0;
@@ -339,7 +340,13 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
                     // a padding chunk (cc >= CC) or the samples past N of a ragged last item lie outside the tensor: zeros
                     const int plane = cc < a.CC ? cc * a.N + n0 : a.CC * a.N;
                     const uint32_t dst = sA + b * abuf_bytes + (uint32_t)pl * (uint32_t)a.P * 16u;
-                    if (a.tm5) tma_load_5d(dst, hl ? &tm_lo : &tm_hi, 0, a.w0 + w0, h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
+                    if (a.s2) {
+                        // stride 2: parity sub-block (qd,qh,qw) = every second voxel from (2 d0 + qd, 2 h0 + qh, 2 w0 + qw)
+                        // (tensor map with element strides 2; the box traverses 2 B - 1 positions per dimension)
+                        for (int pq = 0; pq < 8; ++pq)
+                            tma_load_5d(dst + (uint32_t)(pq * a.P_sub) * 16u, hl ? &tm_lo : &tm_hi, 0, 2 * w0 + (pq & 1), 2 * h0 + ((pq >> 1) & 1),
+                                        2 * d0 + (pq >> 2), plane, bar_afull + 8 * b);
+                    } else if (a.tm5) tma_load_5d(dst, hl ? &tm_lo : &tm_hi, 0, a.w0 + w0, h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
                     else tma_load_4d(dst, hl ? &tm_lo : &tm_hi, 2 * (a.w0 + w0), h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
                 }
             }
@@ -585,7 +592,7 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 struct Geo {
-    int Wt;
+    int Wt, P_sub;
     int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, two_resident, n_sets, fused, n_fused;
     int halo;  // 0: every sample / slab carries its own halo; 1 (stacked, 'same' padding): neighbours share it
     int hd, hw;  // extent of the item's block beyond its outputs in D / H and in W
@@ -599,7 +606,7 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
     const int planes = 2 * L.ck, kpg = L.kpg, n_stages = L.n_stages, Npad = L.Npad;
     const uint32_t bslot = (uint32_t)kpg * 2u * (uint32_t)Npad * 32u;
     const long avail_all = (long)SMEM_LIMIT - 1024 - 256 - (long)NB * bslot;
-    const bool shareable = pad == 1 && L.KS == 3 && L.mode != 2;  // zero padding of one voxel all around
+    const bool shareable = pad == 1 && L.KS == 3 && L.mode != 2 && L.stride == 1;  // zero padding of one voxel all around
     best.score = -1.0;
     // halo = 1 ("shared halo", stacked whole samples with zero padding only): the TMA box starts one voxel before the
     // volume and ends AT its far faces, so a sample occupies (D+1)(H+1)(W+1) slots whose index-0 faces are zero: the
@@ -614,8 +621,9 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
         const long V = (long)Dp * Hp * Wp;
         const int Hs = stacked ? Hp : Ht + L.hd;
         const long S_st = stacked ? (long)G * V : (long)(Dt + L.hd) * Hs * Wp;
+        const int tr = L.stride == 2 ? 1 : L.KS - 1;  // largest tap offset per dimension inside a (sub-)block
         // furthest slot a row reads beyond its own: the last tap (second chunk of the last k step included)
-        const long reach = ((long)(L.KS - 1) * Hs + (L.KS - 1)) * Wp + (L.mode == 2 ? 0 : L.KS - 1) + 1;
+        const long reach = ((long)tr * Hs + tr) * Wp + (L.mode == 2 ? 0 : tr) + 1;
         const long lines_needed = stacked ? (long)(G - 1) * Dp * Hp + (long)(D - 1) * Hp + H : (long)(Dt - 1) * Hs + Ht;
         long n_tiles, max_slot;
         const int n_wblk = lines ? (W + 7) / 8 : 1;
@@ -630,6 +638,13 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
         }
         long P = max_slot + 1 > S_st ? max_slot + 1 : S_st;
         P = (P + 7) / 8 * 8;
+        long P_sub = 0;
+        if (L.stride == 2) {  // 8 parity sub-blocks, the over-read slack only behind the last one
+            P_sub = (S_st + 7) / 8 * 8;
+            P += 7 * P_sub;
+            if (2L * Wp - 1 > 256 || 2L * Hs - 1 > 256 || 2L * (stacked ? Dp : Dt + L.hd) - 1 > 256) return;  // TMA box limits
+        }
+        const long n_sub = L.stride == 2 ? 8 : 1;
         if (n_tiles * Npad > 512 || n_tiles > 32 || P * 16 >= (1L << 18)) return;  // (the fused scheme needs twice the columns: checked below)
         const long avail = avail_all - n_tiles * 512;  // the row table: n_tiles x 128 ints
         // two staging buffers whenever they fit: the next stage (or the next item's block) loads during the MMAs
@@ -637,7 +652,7 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
         const int nbuf = 2 * smemA1 <= avail ? 2 : 1;
         if (nbuf == 1 && n_stages > 1) return;
         const long smemA = nbuf * smemA1;
-        if (smemA > avail || S_st * 16 * planes >= (1L << 20)) return;
+        if (smemA > avail || S_st * n_sub * 16 * planes >= (1L << 20)) return;
         const long outputs = stacked ? (long)G * D * H * W : (long)Dt * Ht * W;
         const long n_items = stacked ? (N + G - 1) / G : (long)N * (D / Dt) * (H / Ht) * (Wfull / Wt);
         // Cost model, calibrated on B200 (tools/halo_geo_sweep.sh): an M128 K16 MMA occupies the tensor pipe for ~40
@@ -683,12 +698,12 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
                 // staging: ~25 bytes per clock and SM from L2 when every SM pulls (decoder 16 -> 16 @ 64^3: 127 KB per
                 // item in ~5000 cycles); hidden behind the MMAs only with a second buffer or a second resident CTA
                 const double n_loads = n_stages == 1 ? 1.0 : (fused == 1 ? 1.0 : 2.0) * n_stages;
-                const double t_load = (double)planes * (double)S_st * 16.0 * n_loads / 25.0;
+                const double t_load = (double)planes * (double)(S_st * n_sub) * 16.0 * n_loads / 25.0;
                 const double t_core = n_sets == 2 ? fmax(t_mma, t_epi) : t_mma + (two_resident ? 0.3 : 1.0) * t_epi;
                 const double t_item = (fused == 1 ? 2000.0 : 3000.0) + ((nbuf == 2 || two_resident) ? fmax(t_core, t_load) : t_core + t_load);
                 const double score = (double)outputs * (double)n_items / (waves * t_item);
                 if (score > best.score) {
-                    best.Wt = Wt;
+                    best.Wt = Wt; best.P_sub = (int)P_sub;
                     best.Dt = stacked ? D : Dt; best.Ht = stacked ? H : Ht; best.Hs = Hs; best.G = stacked ? G : 1; best.stacked = stacked;
                     best.lines = lines; best.n_wblk = n_wblk; best.n_tiles = (int)n_tiles; best.P = (int)P; best.S_st = (int)S_st;
                     best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot; best.two_resident = two_resident ? 1 : 0;
@@ -720,11 +735,8 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
                 if (H % Ht) continue;
                 // long lines may be tiled along w as well (halves, quarters, ...: the block's halo overhead and the
                 // bytes staged per item shrink, two staging buffers fit)
-                for (int Wt = W; Wt >= 8; Wt >>= 1) {
-                    if (W % Wt) break;
-                    consider(0, 1, Dt, Ht, Wt, lines, 0);
-                    if (Wt <= 16) break;
-                }
+                consider(0, 1, Dt, Ht, W, lines, 0);
+                for (int Wt = W >> 1; Wt >= 16 && W % Wt == 0; Wt >>= 1) consider(0, 1, Dt, Ht, Wt, lines, 0);
             }
         }
     }
@@ -732,9 +744,10 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
 }
 
 // mode 0 / 1 layers: 3x3x3 over C1 + C2 channels (x2 upsampled); mode 2: KS^3 over ONE channel (C1 = 1, KS 3 or 5)
-bool make_layer(int Cout, int C1, int C2, int KS, bool wrun, Layer& L) {
-    if (Cout < 1 || Cout > 256 || C1 < 0 || C2 < 0 || C1 + C2 < 1) return false;
-    L.KS = KS; L.C1 = C1; L.C2 = C2; L.Cout = Cout;
+bool make_layer(int Cout, int C1, int C2, int KS, bool wrun, Layer& L, int stride = 1) {
+    if (Cout < 1 || Cout > 256 || C1 < 0 || C2 < 0 || C1 + C2 < 1 || (stride != 1 && stride != 2)) return false;
+    if (stride == 2 && (wrun || C2 != 0)) return false;
+    L.KS = KS; L.C1 = C1; L.C2 = C2; L.Cout = Cout; L.stride = stride;
     L.Cp1 = round_up(C1, 8); L.Cp2 = round_up(C2, 8);
     L.CC = (L.Cp1 + L.Cp2) / 8;
     L.Npad = round_up(Cout, 16);
@@ -747,7 +760,9 @@ bool make_layer(int Cout, int C1, int C2, int KS, bool wrun, Layer& L) {
         return true;
     }
     if (KS != 3) return false;
-    L.hd = L.hw = 2;
+    // stride 2: the item's block is split into its 8 parity sub-blocks (tap k reads parity k & 1 at offset k >> 1), each
+    // one slot larger than the output extent per dimension
+    L.hd = L.hw = stride == 2 ? 1 : 2;
     if (L.CC == 1) { L.mode = 1; L.CCe = 1; L.ck = 1; L.n_stages = 1; L.kpg = 2; L.n_groups = 9; }
     else { L.mode = 0; L.CCe = round_up(L.CC, 2); L.ck = 2; L.n_stages = L.CCe / 2; L.kpg = 3; L.n_groups = 9; }
     return true;
@@ -772,7 +787,8 @@ int conv_init() {
 // D, H, W: OUTPUT extents.  The planes hold Din x Hin x Win slots per (chunk, sample): Din = D + hd - 2 pad, likewise H;
 // Win = W + hw - 2 pad (mode 2: Win = W, the W-runs already cover the taps and the padding along W).
 int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D, int H,
-                int W, int pad, int act, float slope, float out_scale, int out_ncdhw, void* stream) {
+                int W, int pad, int act, float slope, float out_scale, int out_ncdhw, void* stream, int Din_in = 0, int Hin_in = 0,
+                int Win_in = 0) {
     Geo g;
     RF_CHECK_ARG(choose_geometry(N, D, H, W, L, pad, g), "rf_tc_conv3d_halo_fwd: no item shape fits (N=%d out %dx%dx%d Cout=%d C=%d+%d KS=%d)",
                  N, D, H, W, L.Cout, L.C1, L.C2, L.KS);
@@ -780,6 +796,7 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
     a.wimg = (const uint8_t*)weight_image; a.bias = bias; a.y = y;
     a.N = N; a.D = D; a.H = H; a.W = W; a.Hp = H + g.hd; a.Wp = g.Wt + g.hw;
     a.pad = pad; a.CC = L.CC; a.w0 = L.mode == 2 ? 0 : -pad;
+    a.s2 = L.stride == 2 ? 1 : 0; a.P_sub = g.P_sub;
     a.V = (long)(D + g.hd) * (H + g.hd) * (W + g.hw);
     a.Dt = g.Dt; a.Ht = g.Ht; a.Wt = g.Wt; a.Hs = g.Hs; a.G = g.G; a.stacked = g.stacked;
     a.n_dt = D / g.Dt; a.n_ht = H / g.Ht; a.n_wt = W / g.Wt; a.Ls = (D + g.hd) * (H + g.hd);
@@ -798,11 +815,20 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
     RF_CHECK_ARG(L.kpg * L.n_groups <= 32, "rf_tc_conv3d_halo_fwd: internal: more than 32 k steps per stage");
     for (int i = 0; i < 32; ++i) {
         long off = 0, lbo = 1;
-        auto tap_off = [&](int t) { return ((long)(t / 9) * a.Hs + (t / 3) % 3) * a.Wp + t % 3; };
+        auto tap_off = [&](int t) {
+            const int kd = t / 9, kh = (t / 3) % 3, kw = t % 3;
+            if (L.stride == 2)  // parity sub-block (kd & 1, kh & 1, kw & 1), offset (kd >> 1, kh >> 1, kw >> 1) inside it
+                return (long)((kd & 1) * 4 + (kh & 1) * 2 + (kw & 1)) * a.P_sub + ((long)(kd >> 1) * a.Hs + (kh >> 1)) * a.Wp + (kw >> 1);
+            return ((long)kd * a.Hs + kh) * a.Wp + kw;
+        };
         auto line_off = [&](int l) { return ((long)(l / L.KS) * a.Hs + l % L.KS) * a.Wp; };
         if (i < L.kpg * L.n_groups) {
             if (L.mode == 0) { off = tap_off(i); lbo = a.P; }
-            else if (L.mode == 1) { off = tap_off((i / 2) * 3 + (i % 2) * 2); }  // (kw 0, kw 1) and (kw 2, zeros) of line i / 2
+            else if (L.mode == 1) {  // (kw 0, kw 1) and (kw 2, zeros) of line i / 2
+                const int t0 = (i / 2) * 3 + (i % 2) * 2;
+                off = tap_off(t0);
+                if (L.stride == 2 && !(i % 2)) lbo = tap_off(t0 + 1) - off;  // kw 1 lives in the next parity sub-block
+            }
             else { if (2 * i < L.KS * L.KS) { off = line_off(2 * i); if (2 * i + 1 < L.KS * L.KS) lbo = line_off(2 * i + 1) - off; } }
         }
         RF_CHECK_ARG(off >= 0 && off < 65536 && lbo > 0 && lbo < 16384, "rf_tc_conv3d_halo_fwd: internal: k step offsets out of range");
@@ -812,22 +838,24 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
     a.n_items = g.n_items; a.n_sets = g.n_sets; a.n_fused = g.n_fused;
     // tensor maps of the compact planes [CC * N][Din][Hin][Win] x 16 B, seen as 8-byte words so that a whole line of
     // the item's block is the innermost box extent (<= 256 elements)
-    const int Din = D + L.hd - 2 * pad, Hin = H + L.hd - 2 * pad, Win = L.mode == 2 ? W : W + L.hw - 2 * pad;
+    const int Din = Din_in ? Din_in : D + L.hd - 2 * pad, Hin = Hin_in ? Hin_in : H + L.hd - 2 * pad;
+    const int Win = Win_in ? Win_in : (L.mode == 2 ? W : W + L.hw - 2 * pad);
     const int bW = g.Wt + g.hw, bD = g.stacked ? D + g.hd : g.Dt + L.hd;  // the item's box (its H extent is g.Hs)
     RF_CHECK_ARG(bW <= 256 && g.Hs <= 256 && bD <= 256 && g.G <= 256, "rf_tc_conv3d_halo_fwd: item box exceeds the TMA limits");
-    a.tm5 = 2 * bW > 256 ? 1 : 0;  // a line longer than 256 words: slots as a dimension of their own
+    a.tm5 = (a.s2 || 2 * bW > 256) ? 1 : 0;  // a line longer than 256 words, or strided boxes: slots as a dimension of their own
     CUtensorMap tm[2];
     const EncodeTiledFn encode = encode_tiled_fn();
     RF_CHECK_ARG(encode != nullptr, "rf_tc_conv3d_halo_fwd: the driver does not export cuTensorMapEncodeTiled");
     for (int k = 0; k < 2; ++k) {
         const cuuint32_t bG = (cuuint32_t)(g.stacked ? g.G : 1);
         const cuuint64_t planes = (cuuint64_t)L.CC * (cuuint64_t)N;
-        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        const cuuint32_t es = a.s2 ? 2u : 1u;  // stride 2: every second voxel, the box spans 2 B - 1 positions
+        const cuuint32_t estr[5] = {1, es, es, es, 1};
         CUresult cr;
         if (a.tm5) {
             const cuuint64_t gdim[5] = {2, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)Din, planes};
             const cuuint64_t gstr[4] = {16, 16ull * Win, 16ull * Win * Hin, 16ull * Win * Hin * Din};
-            const cuuint32_t box[5] = {2, (cuuint32_t)bW, (cuuint32_t)g.Hs, (cuuint32_t)bD, bG};
+            const cuuint32_t box[5] = {2, (cuuint32_t)(es * bW - (es - 1)), (cuuint32_t)(es * g.Hs - (es - 1)), (cuuint32_t)(es * bD - (es - 1)), bG};
             cr = encode(&tm[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void*>(k ? lo : hi), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         } else {
@@ -947,6 +975,31 @@ extern "C" int rf_tc_conv3d_halo_geometry(int N, int D, int H, int W, int Cout, 
     out8[0] = g.stacked; out8[1] = g.G; out8[2] = g.Dt; out8[3] = g.Ht; out8[4] = g.lines + 2 * (g.fused != 0) + 4 * (g.halo == 1) + 8 * (g.fused == 2); out8[5] = g.n_tiles;
     out8[6] = g.n_items; out8[7] = (int)g.smem;
     return 1;
+}
+
+/* Stride-2 'valid' 3x3x3 convolution (the down-sampling layers of the conv patch encoders, model/retrieval.py:4-28,
+ * 187-275) on the same kernel: the planes are those of rf_cl_norm_split_halo (pad 0); the producer stages the item's 8
+ * parity sub-blocks with strided TMA boxes and tap (kd,kh,kw) reads sub-block (kd&1, kh&1, kw&1) at offset
+ * (kd>>1, kh>>1, kw>>1).  D, H, W: INPUT extents; outputs (D - 3) / 2 + 1 etc.  Weight image: rf_tc_conv_halo_weight_image. */
+extern "C" int rf_tc_conv3d_halo_s2_supported(int N, int D, int H, int W, int Cout, int C1) {
+    Layer L;
+    if (!make_layer(Cout, C1, 0, 3, false, L, 2) || N < 1 || D < 3 || H < 3 || W < 3) return 0;
+    if ((long)N * D * H * W * L.CC >= (1L << 32) - 256) return 0;
+    Geo g;
+    return choose_geometry(N, (D - 3) / 2 + 1, (H - 3) / 2 + 1, (W - 3) / 2 + 1, L, 0, g) && g.n_tiles <= 32 ? 1 : 0;
+}
+
+extern "C" int rf_tc_conv3d_halo_s2_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N,
+                                        int D, int H, int W, int Cout, int C1, int act, float slope, float out_scale, int out_ncdhw,
+                                        void* stream) {
+    RF_CHECK_ARG(hi && lo && weight_image && y, "rf_tc_conv3d_halo_s2_fwd: null pointer");
+    Layer L;
+    RF_CHECK_ARG(make_layer(Cout, C1, 0, 3, false, L, 2) && N > 0 && D >= 3 && H >= 3 && W >= 3,
+                 "rf_tc_conv3d_halo_s2_fwd: unsupported shape Cout=%d C=%d in %dx%dx%d", Cout, C1, D, H, W);
+    RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)weight_image & 15) == 0 && ((uintptr_t)y & 15) == 0,
+                 "rf_tc_conv3d_halo_s2_fwd: pointers must be 16-byte aligned");
+    return launch_conv(L, hi, lo, weight_image, bias, y, N, (D - 3) / 2 + 1, (H - 3) / 2 + 1, (W - 3) / 2 + 1, 0, act, slope, out_scale,
+                       out_ncdhw, stream, D, H, W);
 }
 
 // ------------------------------------------------------------------ single-channel layers as W-runs (mode 2)

@@ -72,6 +72,13 @@ class _ConvPatchEncoder(RfModule):
                 h = ops.tc_conv3d_halo(ops.cl_norm_split_halo(h, None, None, scale=1.0, pad=0), img, conv.bias, conv.out_channels,
                                        act=ops.ACT_LEAKY, slope=0.2, out_scale=1.0 / sw)
                 continue
+            if (self.use_halo_conv and k == 3 and s == 2 and
+                    ops.tc_conv_halo_s2_supported(h.shape[0], h.shape[1], h.shape[2], h.shape[3], conv.out_channels, cin)):
+                # stride-2 'valid' 3x3x3 layers: same kernel, the block staged as its 8 parity sub-blocks
+                img, sw = self._wcache.derived(("halo", li), [conv.weight], lambda w, c=cin: ops.tc_conv_halo_weight_image(w, c, 0))
+                h = ops.tc_conv3d_halo_s2(ops.cl_norm_split_halo(h, None, None, scale=1.0, pad=0), img, conv.bias, conv.out_channels,
+                                          act=ops.ACT_LEAKY, slope=0.2, out_scale=1.0 / sw)
+                continue
             img, sw = self._wcache.derived(("tcconv", li), [conv.weight], lambda w, c=cin: ops.tc_conv_weight_image(w, c, 0))
             h = ops.tc_conv3d(ops.cl_norm_split(h), None, cin, 0, img, conv.bias, conv.out_channels, k, stride=s, pad=0,
                               act=ops.ACT_LEAKY, slope=0.2, out_scale=1.0 / sw)

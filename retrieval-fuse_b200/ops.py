@@ -420,6 +420,25 @@ def conv3d_cin1_cl(x, weight, bias, gn=None, ks=3, stride=1, pad=0, act=ACT_NONE
     return y
 
 
+def tc_conv_halo_s2_supported(N, D, H, W, cout, c1):
+    """Whether the stride-2 'valid' 3x3x3 layer runs on the shifted-window kernel (parity sub-blocks)."""
+    return bool(_lib.lib().rf_tc_conv3d_halo_s2_supported(int(N), int(D), int(H), int(W), int(cout), int(c1)))
+
+
+def tc_conv3d_halo_s2(split, img, bias, cout, act=ACT_NONE, slope=0.0, out_scale=1.0):
+    """split = cl_norm_split_halo(x, pad=0) result.  Conv3d(k3, stride 2, no padding) -> fp32 channels-last [N,Do,Ho,Wo,Cout]."""
+    hi, lo, (N, D, H, W, c1, c2, pad) = split
+    assert c2 == 0 and pad == 0
+    Do, Ho, Wo = (D - 3) // 2 + 1, (H - 3) // 2 + 1, (W - 3) // 2 + 1
+    y = torch.empty((N, Do, Ho, Wo, cout), device=hi.device, dtype=torch.float32)
+    with torch.cuda.device(hi.device), _timed("rf_tc_conv3d_halo_s2_fwd", flops=2.0 * N * Do * Ho * Wo * 27 * c1 * cout):
+        check(_lib.lib().rf_tc_conv3d_halo_s2_fwd(hi.data_ptr(), lo.data_ptr(), img.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W,
+                                                  int(cout), int(c1), act, float(slope), float(out_scale), 0,
+                                                  torch.cuda.current_stream(hi.device).cuda_stream), "rf_tc_conv3d_halo_s2_fwd")
+    _count()
+    return y
+
+
 def tc_conv_wrun_supported(N, D, H, W, cout, ks, pad):
     """Whether the single-input-channel ks^3 layer runs on the tensor-core kernel (W-run operand planes)."""
     return bool(_lib.lib().rf_tc_conv3d_wrun_supported(int(N), int(D), int(H), int(W), int(cout), int(ks), int(pad)))

@@ -241,6 +241,36 @@ def test_single_channel_conv_on_tensor_cores(dev, N, S, Cout, KS, pad, gn):
     close(y, ref32, rel_to_max=True, what="single-channel tensor-core conv vs torch fp32")
 
 
+# (N, S_in, Cin, Cout): the stride-2 'valid' 3^3 layers of Patch32 (16->32 @ 28^3, 64->64 @ 11^3), PCPatch48 (32->64 @ 42^3,
+# 64->64 @ 20^3, 64->128 @ 9^3 at reduced batch), a single-chunk (tap-pairing) case and even / odd extents
+S2_CASES = [(40, 28, 16, 32), (70, 11, 64, 64), (3, 42, 32, 64), (9, 20, 64, 64), (33, 9, 64, 128), (21, 7, 8, 16), (5, 12, 24, 40)]
+
+
+@pytest.mark.parametrize("N,S,Cin,Cout", S2_CASES)
+def test_stride2_conv_on_shifted_window_kernel(dev, N, S, Cin, Cout):
+    """Conv3d(Cin, Cout, 3, stride=2) + LeakyReLU(0.2) (model/retrieval.py:4-28) through rf_tc_conv3d_halo_s2_fwd
+    (parity sub-blocks staged by strided TMA boxes) against torch's CPU conv3d in fp32 and fp64."""
+    from retrieval_fuse_b200 import ops
+    g = torch.Generator().manual_seed(5 * N + S + Cin + Cout)
+    x = torch.randn(N, Cin, S, S, S, generator=g) * 1.2 + 0.1
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    sel = list(range(min(N, 4))) + ([N - 1] if N > 4 else [])
+    ref32 = torch.nn.functional.leaky_relu(torch.nn.functional.conv3d(x[sel], w, b, stride=2), 0.2)
+    ref64 = torch.nn.functional.leaky_relu(torch.nn.functional.conv3d(x[sel].double(), w.double(), b.double(), stride=2), 0.2)
+    assert ops.tc_conv_halo_s2_supported(N, S, S, S, Cout, Cin)
+    xd = x.permute(0, 2, 3, 4, 1).contiguous().to(dev)
+    img, sw = ops.tc_conv_halo_weight_image(w.to(dev), Cin, 0)
+    y = ops.tc_conv3d_halo_s2(ops.cl_norm_split_halo(xd, None, None, scale=1.0, pad=0), img, b.to(dev), Cout, act=ops.ACT_LEAKY, slope=0.2,
+                              out_scale=1.0 / sw)
+    y = y.permute(0, 4, 1, 2, 3).cpu()[sel]
+    assert y.shape == ref32.shape
+    scale = max(1.0, float(ref64.abs().max()))
+    err64 = float((y.double() - ref64).abs().max())
+    assert err64 <= 2e-5 * scale, f"|ours - fp64| {err64:.2e} (scale {scale:.1f})"
+    close(y, ref32, rel_to_max=True, what="stride-2 shifted-window conv vs torch fp32")
+
+
 @pytest.mark.parametrize("M,widths,act,l2", [(1000, [64, 128, 256, 512, 256, 64], 1, True), (129, [64, 128, 256, 512, 256, 64], 1, False),
                                              (4097, [128, 128, 128, 128, 32], 2, False), (300, [96, 128, 128, 128, 32], 2, False),
                                              (640, [40, 72, 24], 1, True), (20000, [125, 128, 256, 512, 256, 64], 1, True)])

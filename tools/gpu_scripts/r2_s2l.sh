@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT"
+timeout 900 python -m pytest tests -x -q -m gpu -k "stride2" > gpurun_out/r2s2_pytest_l.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/r2s2_pytest_l.log
+timeout 900 python -m pytest tests -x -q -m gpu -k "encoders or single_channel or shifted_window or surface or backbone" > gpurun_out/r2s2_pytest_l2.log 2>&1; echo "pytest2 rc=$?"; tail -5 gpurun_out/r2s2_pytest_l2.log
+bash tools/gpu_scripts/r2_enc_list.sh 2>&1 | grep -v "^at::"
+timeout 600 python bench.py --workload surface --no-cpu-baseline > /tmp/s.json 2> /dev/null; python -c "
+import json
+l=json.load(open('/tmp/s.json')); print('surface', l['value'], l['breakdown_ms'])"
