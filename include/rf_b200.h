@@ -187,6 +187,30 @@ int rf_tc_conv3d_halo_s2_supported(int N, int D, int H, int W, int Cout, int C1)
 int rf_tc_conv3d_halo_s2_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D,
                              int H, int W, int Cout, int C1, int act, float slope, float out_scale, int out_ncdhw, void* stream);
 
+/* W-pair variant for small Cout (2 Cout <= 128; model/unet.py:79-100 SingleConv and the 'valid' Conv3d layers of
+ * model/retrieval.py:4-388): one GEMM row = the output voxels (w, w + 1), N = 2 Cout; planes W-de-interleaved
+ * [chunk][w parity][n][d][h][w/2] (rf_cl_norm_split_halo_wp, sized by rf_halo_act_bytes).  D, H, W: INPUT extents.
+ * _supported: 0 = no, 1 = runs, 2 = runs and the item cost model rates it faster than rf_tc_conv3d_halo_fwd. */
+int rf_cl_norm_split_halo_wp(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a,
+                             const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, int pad, float scale, void* stream);
+size_t rf_tc_conv_halo_wp_weight_image_bytes(int Cout, int C1, int C2);
+int rf_tc_conv_halo_wp_weight_image(const float* w, int Cout, int C1, int C2, float scale, void* image, void* stream);
+int rf_tc_conv3d_halo_wp_supported(int N, int D, int H, int W, int Cout, int C1, int C2, int pad);
+int rf_tc_conv3d_halo_wp_geometry(int N, int D, int H, int W, int Cout, int C1, int C2, int pad, int* out16, double* scores2);
+int rf_tc_conv3d_halo_wp_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D,
+                             int H, int W, int pad, int Cout, int C1, int C2, int act, float slope, float out_scale, void* stream);
+
+/* Fused front of the first DoubleConv of a 'gcr' U-Net encoder on 16^3 single-channel samples (model/unet.py:79-144,
+ * the retrieval U-Net's patches, model/refinement.py:64-73): GroupNorm(1,1) -> Conv3d(1,8,3,p=1) -> ReLU ->
+ * GroupNorm(groups2, 8) -> x scale -> fp16 hi / lo operand planes of rf_tc_conv3d_halo_fwd (wp = 0) or
+ * rf_tc_conv3d_halo_wp_fwd (wp = 1), sized by rf_halo_act_bytes(N,16,16,16,8,0,1).  One persistent CTA per sample;
+ * the 8-channel fp32 activations never reach HBM.  x [N,16,16,16]; conv_w [8,1,3,3,3]; gn2_w / gn2_b [8] on the device.
+ * _fwd reads conv_w / gn1_w / gn1_b back (stream sync); _fwd_host takes them from the host and can be graph-captured. */
+int rf_unet_front16_fwd(const float* x, const float* gn1_w, const float* gn1_b, float eps1, const float* conv_w, const float* gn2_w,
+                        const float* gn2_b, int groups2, float eps2, float scale, void* hi, void* lo, int N, int wp, void* stream);
+int rf_unet_front16_fwd_host(const float* x, float gn1_w, float gn1_b, float eps1, const float* conv_w_host, const float* gn2_w,
+                             const float* gn2_b, int groups2, float eps2, float scale, void* hi, void* lo, int N, int wp, void* stream);
+
 /* Single-input-channel layers on the same kernel (the first Conv3d of every patch
  * encoder, model/retrieval.py:4-388, kernel edge 3 or 5, no padding; the first
  * SingleConv of the U-Nets, model/unet.py:79-100, 3^3 'same'): the slot of voxel

@@ -48,7 +48,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
         : "memory");
 }
 
-constexpr int TM = 128, NTHREADS = 512, NB = 4, MAX_ABUF = 2;
+constexpr int TM = 128, NTHREADS = 512, NB_MAX = 8, MAX_ABUF = 2;  // NB_MAX: most slots of the weight ring (4 or 8 are used)
 constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in maximum per CTA on sm_100
 // same for the 5-D form (slot words, W, H, D, plane) used when a haloed line exceeds 256 8-byte words (W > 126)
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
@@ -68,6 +68,8 @@ struct SplitArgs {
     FastDiv fCG;              // octet mapping: chunk groups of 4
     unsigned n_vox;
     long total_oct;
+    int wp;         // W-pair planes: [chunk][w parity][n][d][h][w / 2] (rf_cl_norm_split_halo_wp)
+    long half_vol;  // D * H * W / 2
 };
 
 template <int OCT>
@@ -95,12 +97,14 @@ __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs
             cc = (int)fd_divmod(t, s.fCC);
             v = t;
         }
-        const long i = (long)cc * s.n_vox + v;  // slot index in the compact planes [chunk][n][d][h][w]
+        long i = (long)cc * s.n_vox + v;  // slot index in the compact planes [chunk][n][d][h][w]
         unsigned t = v;
         const int w = (int)fd_divmod(t, s.fW);
         const int hq = (int)fd_divmod(t, s.fH);
         const int d = (int)fd_divmod(t, s.fD);
         const int n = (int)t;
+        // W-pair planes: the even and the odd voxels of every line form two planes of half-lines
+        if (s.wp) i = ((long)(cc * 2 + (w & 1)) * s.N + n) * s.half_vol + ((long)d * s.H + hq) * (s.W >> 1) + (w >> 1);
         uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
         const float* src;
         int C, c0, goff;
@@ -159,11 +163,20 @@ __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs
 //   mode 2 (ONE input channel, kernel edge 3 or 5): the slot of voxel w holds the 8 consecutive values x[w .. w+7] of
 //          its line ("W-run", written by rf_cl_norm_split_wrun), so one chunk carries all kw taps of a (kd,kh) line and
 //          a step pairs two lines: 5 steps for 3^3, 13 for 5^3 - the single-channel first layers of the U-Nets and
-//          patch encoders on tensor cores instead of the fp32 FMA kernel.
+//          patch encoders on tensor cores instead of the fp32 FMA kernel;
+//   mode 3 ("W pairs", small Cout): a GEMM row is a PAIR of output voxels (w, w+1), N = 2 Cout.  For N <= 64 the tensor
+//          pipe is bound by reading the A operand (40-48 cycles per M128 K16 MMA whatever N is), so halving the rows at
+//          twice the columns halves the pipe time.  The pair reads the 4 input positions u = 2r .. 2r+3 (padded
+//          coordinates) of each (kd,kh) line: the planes are W-de-interleaved (rf_cl_norm_split_halo_wp), the item's
+//          block is staged as two sub-blocks A = even u, B = odd u (P_sub slots apart), and a K = 16 step pairs
+//          (A[r+p], B[r+p]), p = 0 / 1, with LBO = P_sub: 18 steps per channel chunk and row pair, none of them
+//          padding (a Toeplitz expansion of the weights over [N,D,H,W/2,2C] views needs 27 half-empty steps).
+//          One stage per channel chunk.  B rows: n = v * Cout + co for output voxel v of the pair.
 // Steps are grouped kpg at a time into the weight ring's slots (n_groups groups per stage; padded steps carry zero
 // weights).  Image: [stage][group][k step][K chunk][hi rows | lo rows (Npad each)][16 B].
 struct Layer {
     int mode, KS, stride;  // stride 2: 'valid' 3^3 only (the patch encoders' down-sampling layers)
+    int wp;                // mode 3: W pairs (two output voxels per GEMM row)
     int C1, C2, Cp1, Cp2, CC, CCe, Cout, Npad;
     int ck, n_stages, kpg, n_groups;
     int hd, hw;  // block extent beyond the output extent: D / H (KS - 1) and W (KS - 1; 0 in mode 2)
@@ -183,11 +196,21 @@ __global__ void __launch_bounds__(256) halo_weight_image_kernel(const float* __r
     const int st = (int)(t / L.n_groups);
     const int idx = g * kpg + ks;
     uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
-    if (n < L.Cout) {
+    if (n < (L.wp ? 2 * L.Cout : L.Cout)) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             float val = 0.f;
-            if (L.mode == 2) {
+            if (L.mode == 3) {
+                // step 2 l + p of line l = (kd, kh): chunk kc = position u = 2 p + kc of the pair's window; output voxel
+                // v of the pair sees it as tap kw = u - v
+                const int v = n >= L.Cout ? 1 : 0, co = n - v * L.Cout;
+                const int kw = 2 * (idx & 1) + kc - v;
+                const int cs = st * 8 + e;
+                int ci = -1;
+                if (cs < L.Cp1) { if (cs < L.C1) ci = cs; }
+                else if (cs - L.Cp1 < L.C2) ci = L.C1 + (cs - L.Cp1);
+                if (kw >= 0 && kw < 3 && ci >= 0) val = w[((long)co * Cin + ci) * 27 + (idx >> 1) * 3 + kw] * scale;
+            } else if (L.mode == 2) {
                 const int line = 2 * idx + kc;  // (kd, kh); element e of the chunk <-> kw
                 if (line < L.KS * L.KS && e < L.KS) val = w[(long)n * taps + line * L.KS + e] * scale;
             } else {
@@ -224,6 +247,8 @@ struct HaloArgs {
     int N, D, H, W, Hp, Wp;
     int pad, CC, tm5;             // conv padding (0 / 1); real channel chunks (chunk >= CC: all zero); 5-D tensor maps
     int s2, P_sub;                // stride 2: 8 parity sub-blocks per plane, P_sub slots apart
+    int nb_shift;                 // log2 of the weight ring's slots
+    int wp, Cb;                   // W pairs: 2 sub-blocks per plane (even / odd padded positions); channels of the bias vector
     long V;                       // slots per haloed sample volume
     int Dt, Ht, Wt, Hs, G, stacked;  // item = G stacked whole samples, or a Dt x Ht x Wt slab of one sample
     int n_dt, n_ht, n_wt, Ls;     // slabs per sample; lines per stacked sample (Dp * Hp)
@@ -258,10 +283,11 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
     const uint32_t abuf_bytes = (uint32_t)planes * (uint32_t)a.P * 16u;
     const uint32_t sA = base;
     const uint32_t sB = sA + (uint32_t)a.nbuf * abuf_bytes;
+    const uint32_t NB = 1u << a.nb_shift;  // slots of the weight ring
     const uint32_t bars = sB + NB * a.bslot_bytes;
     const uint32_t bar_afull = bars, bar_aempty = bars + 8 * MAX_ABUF;
-    const uint32_t bar_bfull = bars + 16 * MAX_ABUF, bar_bempty = bar_bfull + 8 * NB;
-    const uint32_t bar_dfull = bar_bempty + 8 * NB, bar_dempty = bar_dfull + 16;  // one pair per accumulator set
+    const uint32_t bar_bfull = bars + 16 * MAX_ABUF, bar_bempty = bar_bfull + 8 * NB_MAX;
+    const uint32_t bar_dfull = bar_bempty + 8 * NB_MAX, bar_dempty = bar_dfull + 16;  // one pair per accumulator set
     const uint32_t tmem_slot = bar_dempty + 16;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
     // row table: GEMM row (tile, r) -> output voxel offset relative to the item's first voxel, stacked sample index in
@@ -274,7 +300,7 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nbuf; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, a.n_iss); }
-        for (int s = 0; s < NB; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, a.n_iss); }
+        for (int s = 0; s < NB_MAX; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, a.n_iss); }
         for (int k = 0; k < 2; ++k) { mbar_init(bar_dfull + 8 * k, a.n_iss); mbar_init(bar_dempty + 8 * k, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -318,7 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
         // issuers)
         const int n_pass = a.n_fused == a.n_tiles ? 1 : 2;
         const int n_loads = resident ? 1 : n_pass * a.n_stages;
-        const uint32_t plane_bytes = (uint32_t)a.S_st * 16u * (a.s2 ? 8u : 1u);
+        const uint32_t plane_bytes = (uint32_t)a.S_st * 16u * (a.s2 ? 8u : a.wp ? 2u : 1u);
         uint32_t lc = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
             int n0, d0 = 0, h0 = 0, w0 = 0;
@@ -346,6 +372,16 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
                         for (int pq = 0; pq < 8; ++pq)
                             tma_load_5d(dst + (uint32_t)(pq * a.P_sub) * 16u, hl ? &tm_lo : &tm_hi, 0, 2 * w0 + (pq & 1), 2 * h0 + ((pq >> 1) & 1),
                                         2 * d0 + (pq >> 2), plane, bar_afull + 8 * b);
+                    } else if (a.wp) {
+                        // W pairs: sub-block A = the padded positions u = 2 r (voxels of parity 'pad', from half-line index
+                        // w0 - pad), sub-block B = u = 2 r + 1 (the other parity, from w0); planes [chunk][parity][n]
+                        for (int sb = 0; sb < 2; ++sb) {
+                            const int par = sb ? 1 - a.pad : a.pad, ws = w0 - (sb ? 0 : a.pad);
+                            const int pq = cc < a.CC ? (cc * 2 + par) * a.N + n0 : 2 * a.CC * a.N;
+                            const uint32_t dq = dst + (uint32_t)(sb * a.P_sub) * 16u;
+                            if (a.tm5) tma_load_5d(dq, hl ? &tm_lo : &tm_hi, 0, ws, h0 - a.pad, d0 - a.pad, pq, bar_afull + 8 * b);
+                            else tma_load_4d(dq, hl ? &tm_lo : &tm_hi, 2 * ws, h0 - a.pad, d0 - a.pad, pq, bar_afull + 8 * b);
+                        }
                     } else if (a.tm5) tma_load_5d(dst, hl ? &tm_lo : &tm_hi, 0, a.w0 + w0, h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
                     else tma_load_4d(dst, hl ? &tm_lo : &tm_hi, 2 * (a.w0 + w0), h0 - a.pad, d0 - a.pad, plane, bar_afull + 8 * b);
                 }
@@ -359,9 +395,9 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
         uint32_t gc = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x)
             for (int gi = 0; gi < n_pass * per_pass; ++gi, ++gc) {
-                const uint32_t sl = gc % NB;
+                const uint32_t sl = gc & (NB - 1u);
                 const int img = gi >= per_pass ? gi - per_pass : gi;
-                mbar_wait_relaxed(bar_bempty + 8 * sl, ((gc / NB) & 1u) ^ 1u);
+                mbar_wait_relaxed(bar_bempty + 8 * sl, ((gc >> a.nb_shift) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(bar_bfull + 8 * sl, a.bslot_bytes);
                 bulk_g2s(sB + sl * a.bslot_bytes, a.wimg + (long)img * a.bslot_bytes, a.bslot_bytes, bar_bfull + 8 * sl);
             }
@@ -413,38 +449,49 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
                         if (dbg && vs == 0) g_halo_dbg[it * 8 + 2] = clock64();
                     }
                     const uint32_t abase = ((sA + b * abuf_bytes) & 0x3FFFFu) >> 4;
-                    // k step table entry (slot offset | LBO << 16, added to the descriptor's low word), fetched one
-                    // step ahead: the issue loop is latency-critical, a load in front of every step's first MMA cost 4 %
-                    uint32_t kt_next = a.ktab[0];
-                    int kidx = 0;
+                    // Issue order inside a weight group: tile-major.  The per-tile terms (accumulator address, first slot,
+                    // scheme) are derived once per (group, tile) and the k step table entries (slot offset | LBO << 16, added
+                    // to the descriptor's low word) of up to four steps are fetched before the wait, so an MMA costs a handful
+                    // of uniform-datapath instructions: with one tile per issuer the k-step-major loop spent ~350 cycles
+                    // per step and warp on dependent constant loads and address arithmetic, which bounded items of few tiles
+                    // (3 tiles: 118 cycles per step and tile against 88 of pipe time).
                     for (int g = 0; g < a.n_groups; ++g, ++gc) {
-                        const uint32_t sl = gc % NB;
-                        mbar_wait_warp_backoff(bar_bfull + 8 * sl, (gc / NB) & 1u, 40);
-                        tc_fence_after();
-                        const uint32_t bbase = (((sB + sl * a.bslot_bytes) & 0x3FFFFu) >> 4) | b_lbo;
-                        for (int ks = 0; ks < a.kpg; ++ks) {
-                            const uint32_t kt = kt_next;
-                            kidx = kidx + 1 < 32 ? kidx + 1 : 31;
-                            kt_next = a.ktab[kidx];
-                            const uint32_t b_hi = bbase + (uint32_t)ks * step_u, b_lo = b_hi + npad;  // lo rows follow the hi rows
-                            const uint32_t acc = (vs | g | ks) ? 1u : 0u;  // the very first MMA of a tile overwrites its accumulator
+                        const uint32_t sl = gc & (NB - 1u);
+                        const int k0 = g * a.kpg;
+                        for (int kc0 = 0; kc0 < a.kpg; kc0 += 4) {
+                            uint32_t ktg[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) ktg[j] = a.ktab[(k0 + kc0 + j) & 31];
+                            if (kc0 == 0) {
+                                mbar_wait_warp_backoff(bar_bfull + 8 * sl, (gc >> a.nb_shift) & 1u, 40);
+                                tc_fence_after();
+                            }
+                            const uint32_t bbase = ((((sB + sl * a.bslot_bytes) & 0x3FFFFu) >> 4) | b_lbo) + (uint32_t)kc0 * step_u;
+                            const int nk = a.kpg - kc0 < 4 ? a.kpg - kc0 : 4;
                             for (int t = iss; t < a.n_tiles; t += a.n_iss) {
                                 const bool tf = (uint32_t)t < nf;
+                                if (tf && pass) continue;  // (mixed items: the second pass serves the two-pass tiles only)
                                 const uint32_t d = tmem_u + set * set_cols + ((uint32_t)t + (tf ? (uint32_t)t : nf)) * npad;
-                                const uint32_t da = abase + kt + a.tile_off[t];
-                                if (tf) {
-                                    if (pass) continue;  // (mixed items: the second pass serves the two-pass tiles only)
-                                    // A_hi x [W_hi; W_lo] as ONE N = 2 Npad MMA -> columns [main | cross]; A_lo x W_hi into
-                                    // the cross block.  For N <= 64 the pipe time is set by reading the A operand, so
-                                    // the doubled N is almost free: two MMAs instead of three, one pass over the stages,
-                                    // and the main block still sees only the hi*hi accumulations.
-                                    tc_mma2(d, da, a_hi32, b_hi, b_hi32, idesc2, acc, leader);                 // hi * [hi | lo]
-                                    tc_mma2(d + npad, da + lo_off, a_hi32, b_hi, b_hi32, idesc, 1u, leader);   // lo * hi -> cross
-                                } else if (pass == 0) {
-                                    tc_mma2(d, da, a_hi32, b_lo, b_hi32, idesc, acc, leader);          // hi * lo
-                                    tc_mma2(d, da + lo_off, a_hi32, b_hi, b_hi32, idesc, 1u, leader);  // lo * hi
-                                } else {
-                                    tc_mma2(d, da, a_hi32, b_hi, b_hi32, idesc, 1u, leader);           // hi * hi
+                                const uint32_t da0 = abase + a.tile_off[t];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    if (j >= nk) break;
+                                    const uint32_t b_hi = bbase + (uint32_t)j * step_u, b_lo = b_hi + npad;  // lo rows follow the hi rows
+                                    const uint32_t acc = (vs | g | kc0 | j) ? 1u : 0u;  // the very first MMA of a tile overwrites its accumulator
+                                    const uint32_t da = da0 + ktg[j];
+                                    if (tf) {
+                                        // A_hi x [W_hi; W_lo] as ONE N = 2 Npad MMA -> columns [main | cross]; A_lo x W_hi into
+                                        // the cross block.  For N <= 64 the pipe time is set by reading the A operand, so
+                                        // the doubled N is almost free: two MMAs instead of three, one pass over the stages,
+                                        // and the main block still sees only the hi*hi accumulations.
+                                        tc_mma2(d, da, a_hi32, b_hi, b_hi32, idesc2, acc, leader);                 // hi * [hi | lo]
+                                        tc_mma2(d + npad, da + lo_off, a_hi32, b_hi, b_hi32, idesc, 1u, leader);   // lo * hi -> cross
+                                    } else if (pass == 0) {
+                                        tc_mma2(d, da, a_hi32, b_lo, b_hi32, idesc, acc, leader);          // hi * lo
+                                        tc_mma2(d, da + lo_off, a_hi32, b_hi, b_hi32, idesc, 1u, leader);  // lo * hi
+                                    } else {
+                                        tc_mma2(d, da, a_hi32, b_hi, b_hi32, idesc, 1u, leader);           // hi * hi
+                                    }
                                 }
                             }
                         }
@@ -513,7 +560,8 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
                 const long vox = vox0 + (rt & 0x3FFFFFF);
                 if (a.bias) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = fmaf(v[e], a.out_scale, c0 + e < a.Cout ? __ldg(a.bias + c0 + e) : 0.f);
+                    for (int e = 0; e < 16; ++e)  // (W pairs: columns [Cb, 2 Cb) are the second voxel's channels)
+                        v[e] = fmaf(v[e], a.out_scale, c0 + e < a.Cout ? __ldg(a.bias + (c0 + e >= a.Cb ? c0 + e - a.Cb : c0 + e)) : 0.f);
                 } else {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) v[e] *= a.out_scale;
@@ -592,7 +640,7 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 struct Geo {
-    int Wt, P_sub;
+    int Wt, P_sub, nb;
     int Dt, Ht, Hs, G, stacked, lines, n_wblk, n_tiles, P, S_st, n_items, nbuf, two_resident, n_sets, fused, n_fused;
     int halo;  // 0: every sample / slab carries its own halo; 1 (stacked, 'same' padding): neighbours share it
     int hd, hw;  // extent of the item's block beyond its outputs in D / H and in W
@@ -605,6 +653,8 @@ struct Geo {
 bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& best) {
     const int planes = 2 * L.ck, kpg = L.kpg, n_stages = L.n_stages, Npad = L.Npad;
     const uint32_t bslot = (uint32_t)kpg * 2u * (uint32_t)Npad * 32u;
+    static const int nb_env = [] { const char* e = getenv("RF_HALO_NB"); return e ? atoi(e) : 0; }();  // tuning aid
+    const int NB = nb_env == 8 ? 8 : 4;
     const long avail_all = (long)SMEM_LIMIT - 1024 - 256 - (long)NB * bslot;
     const bool shareable = pad == 1 && L.KS == 3 && L.mode != 2 && L.stride == 1;  // zero padding of one voxel all around
     best.score = -1.0;
@@ -623,7 +673,7 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
         const long S_st = stacked ? (long)G * V : (long)(Dt + L.hd) * Hs * Wp;
         const int tr = L.stride == 2 ? 1 : L.KS - 1;  // largest tap offset per dimension inside a (sub-)block
         // furthest slot a row reads beyond its own: the last tap (second chunk of the last k step included)
-        const long reach = ((long)tr * Hs + tr) * Wp + (L.mode == 2 ? 0 : tr) + 1;
+        const long reach = ((long)tr * Hs + tr) * Wp + (L.mode == 2 ? 0 : L.wp ? 1 : tr) + 1;
         const long lines_needed = stacked ? (long)(G - 1) * Dp * Hp + (long)(D - 1) * Hp + H : (long)(Dt - 1) * Hs + Ht;
         long n_tiles, max_slot;
         const int n_wblk = lines ? (W + 7) / 8 : 1;
@@ -644,7 +694,11 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
             P += 7 * P_sub;
             if (2L * Wp - 1 > 256 || 2L * Hs - 1 > 256 || 2L * (stacked ? Dp : Dt + L.hd) - 1 > 256) return;  // TMA box limits
         }
-        const long n_sub = L.stride == 2 ? 8 : 1;
+        if (L.wp) {  // two sub-blocks (even / odd padded positions), each with its own zeroed over-read slack: with a
+            P_sub = P;  // shared halo the far neighbours of a sample's last voxels are read from that slack
+            P += P_sub;
+        }
+        const long n_sub = L.stride == 2 ? 8 : L.wp ? 2 : 1;
         if (n_tiles * Npad > 512 || n_tiles > 32 || P * 16 >= (1L << 18)) return;  // (the fused scheme needs twice the columns: checked below)
         const long avail = avail_all - n_tiles * 512;  // the row table: n_tiles x 128 ints
         // two staging buffers whenever they fit: the next stage (or the next item's block) loads during the MMAs
@@ -653,7 +707,7 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
         if (nbuf == 1 && n_stages > 1) return;
         const long smemA = nbuf * smemA1;
         if (smemA > avail || S_st * n_sub * 16 * planes >= (1L << 20)) return;
-        const long outputs = stacked ? (long)G * D * H * W : (long)Dt * Ht * W;
+        const long outputs = (stacked ? (long)G * D * H * W : (long)Dt * Ht * W) * (L.wp ? 2 : 1);
         const long n_items = stacked ? (N + G - 1) / G : (long)N * (D / Dt) * (H / Ht) * (Wfull / Wt);
         // Cost model, calibrated on B200 (tools/halo_geo_sweep.sh): an M128 K16 MMA occupies the tensor pipe for ~40
         // (N <= 32) to 48 (N = 64) cycles, one issuer warp sustains one MMA per ~150 cycles, the epilogue costs ~1200
@@ -708,7 +762,7 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
                     best.lines = lines; best.n_wblk = n_wblk; best.n_tiles = (int)n_tiles; best.P = (int)P; best.S_st = (int)S_st;
                     best.n_items = (int)n_items; best.nbuf = nbuf; best.bslot = bslot; best.two_resident = two_resident ? 1 : 0;
                     best.tmem_cols = cols_needed;
-                    best.n_sets = n_sets; best.fused = fused; best.n_fused = n_fused; best.halo = halo; best.hd = hd; best.hw = hw;
+                    best.nb = NB; best.n_sets = n_sets; best.fused = fused; best.n_fused = n_fused; best.halo = halo; best.hd = hd; best.hw = hw;
                     best.smem = (size_t)smem_total;
                     best.score = score;
                 }
@@ -744,13 +798,20 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
 }
 
 // mode 0 / 1 layers: 3x3x3 over C1 + C2 channels (x2 upsampled); mode 2: KS^3 over ONE channel (C1 = 1, KS 3 or 5)
-bool make_layer(int Cout, int C1, int C2, int KS, bool wrun, Layer& L, int stride = 1) {
+bool make_layer(int Cout, int C1, int C2, int KS, bool wrun, Layer& L, int stride = 1, bool wp = false) {
     if (Cout < 1 || Cout > 256 || C1 < 0 || C2 < 0 || C1 + C2 < 1 || (stride != 1 && stride != 2)) return false;
     if (stride == 2 && (wrun || C2 != 0)) return false;
-    L.KS = KS; L.C1 = C1; L.C2 = C2; L.Cout = Cout; L.stride = stride;
+    L.KS = KS; L.C1 = C1; L.C2 = C2; L.Cout = Cout; L.stride = stride; L.wp = wp ? 1 : 0;
     L.Cp1 = round_up(C1, 8); L.Cp2 = round_up(C2, 8);
     L.CC = (L.Cp1 + L.Cp2) / 8;
     L.Npad = round_up(Cout, 16);
+    if (wp) {  // W pairs: N = 2 Cout (both scheme's operands [W_hi; W_lo] must stay within N = 256), one stage per chunk
+        if (wrun || stride != 1 || KS != 3 || 2 * Cout > 128) return false;
+        L.Npad = round_up(2 * Cout, 16);
+        L.mode = 3; L.CCe = L.CC; L.ck = 1; L.n_stages = L.CC; L.kpg = 2; L.n_groups = 9;
+        L.hd = 2; L.hw = 1;
+        return true;
+    }
     if (wrun) {
         if (C1 != 1 || C2 != 0 || (KS != 3 && KS != 5)) return false;
         const int n_ks = (KS * KS + 1) / 2;  // two (kd,kh) lines per K = 16 step
@@ -797,12 +858,13 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
     a.N = N; a.D = D; a.H = H; a.W = W; a.Hp = H + g.hd; a.Wp = g.Wt + g.hw;
     a.pad = pad; a.CC = L.CC; a.w0 = L.mode == 2 ? 0 : -pad;
     a.s2 = L.stride == 2 ? 1 : 0; a.P_sub = g.P_sub;
+    a.wp = L.wp; a.Cb = L.Cout; a.nb_shift = g.nb == 8 ? 3 : 2;
     a.V = (long)(D + g.hd) * (H + g.hd) * (W + g.hw);
     a.Dt = g.Dt; a.Ht = g.Ht; a.Wt = g.Wt; a.Hs = g.Hs; a.G = g.G; a.stacked = g.stacked;
     a.n_dt = D / g.Dt; a.n_ht = H / g.Ht; a.n_wt = W / g.Wt; a.Ls = (D + g.hd) * (H + g.hd);
     a.lines = g.lines; a.n_wblk = g.n_wblk; a.n_tiles = g.n_tiles; a.P = g.P; a.S_st = g.S_st;
     a.n_stages = L.n_stages; a.nbuf = g.nbuf; a.ck = L.ck; a.kpg = L.kpg; a.n_groups = L.n_groups;
-    a.Cout = L.Cout; a.Npad = L.Npad; a.act = act; a.out_ncdhw = out_ncdhw; a.slope = slope; a.out_scale = out_scale;
+    a.Cout = L.wp ? 2 * L.Cout : L.Cout; a.Npad = L.Npad; a.act = act; a.out_ncdhw = out_ncdhw; a.slope = slope; a.out_scale = out_scale;
     a.bslot_bytes = g.bslot; a.tmem_cols = g.tmem_cols;
     a.n_iss = g.n_tiles < 6 ? g.n_tiles : 6;
     // tile t = lb * n_wblk + wb starts at slot lb * (16 lines) + wb * 8 (linear mode: n_wblk = 1, 128 slots per tile)
@@ -823,7 +885,8 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
         };
         auto line_off = [&](int l) { return ((long)(l / L.KS) * a.Hs + l % L.KS) * a.Wp; };
         if (i < L.kpg * L.n_groups) {
-            if (L.mode == 0) { off = tap_off(i); lbo = a.P; }
+            if (L.mode == 3) { off = ((long)(i / 6) * a.Hs + (i / 2) % 3) * a.Wp + (i & 1); lbo = a.P_sub; }  // (A[r + p], B[r + p]) of line i / 2
+            else if (L.mode == 0) { off = tap_off(i); lbo = a.P; }
             else if (L.mode == 1) {  // (kw 0, kw 1) and (kw 2, zeros) of line i / 2
                 const int t0 = (i / 2) * 3 + (i % 2) * 2;
                 off = tap_off(t0);
@@ -839,7 +902,7 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
     // tensor maps of the compact planes [CC * N][Din][Hin][Win] x 16 B, seen as 8-byte words so that a whole line of
     // the item's block is the innermost box extent (<= 256 elements)
     const int Din = Din_in ? Din_in : D + L.hd - 2 * pad, Hin = Hin_in ? Hin_in : H + L.hd - 2 * pad;
-    const int Win = Win_in ? Win_in : (L.mode == 2 ? W : W + L.hw - 2 * pad);
+    const int Win = Win_in ? Win_in : (L.mode == 2 ? W : L.wp ? W + 1 - pad : W + L.hw - 2 * pad);  // (W pairs: half-lines)
     const int bW = g.Wt + g.hw, bD = g.stacked ? D + g.hd : g.Dt + L.hd;  // the item's box (its H extent is g.Hs)
     RF_CHECK_ARG(bW <= 256 && g.Hs <= 256 && bD <= 256 && g.G <= 256, "rf_tc_conv3d_halo_fwd: item box exceeds the TMA limits");
     a.tm5 = (a.s2 || 2 * bW > 256) ? 1 : 0;  // a line longer than 256 words, or strided boxes: slots as a dimension of their own
@@ -848,7 +911,7 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
     RF_CHECK_ARG(encode != nullptr, "rf_tc_conv3d_halo_fwd: the driver does not export cuTensorMapEncodeTiled");
     for (int k = 0; k < 2; ++k) {
         const cuuint32_t bG = (cuuint32_t)(g.stacked ? g.G : 1);
-        const cuuint64_t planes = (cuuint64_t)L.CC * (cuuint64_t)N;
+        const cuuint64_t planes = (cuuint64_t)L.CC * (cuuint64_t)N * (L.wp ? 2u : 1u);
         const cuuint32_t es = a.s2 ? 2u : 1u;  // stride 2: every second voxel, the box spans 2 B - 1 positions
         const cuuint32_t estr[5] = {1, es, es, es, 1};
         CUresult cr;
@@ -891,15 +954,14 @@ extern "C" size_t rf_halo_act_bytes(int N, int D, int H, int W, int C1, int C2, 
     return (size_t)L.CC * N * (size_t)D * H * W * 16;  // compact planes: the halo is made by the TMA unit's zero fill
 }
 
-extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a,
-                                     const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, int pad, float scale,
-                                     int interior_only, void* stream) {
-    (void)interior_only;  // the planes have no halo any more: every call writes every slot
+static int split_halo(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a, const float* gn_beta,
+                      void* hi, void* lo, int N, int D, int H, int W, int pad, float scale, int wp, void* stream) {
     Layer L;
     RF_CHECK_ARG(make_layer(16, C1, C2, 3, false, L), "rf_cl_norm_split_halo: bad channel counts");
     RF_CHECK_ARG(hi && lo && (C1 == 0 || x) && (C2 == 0 || x2) && N > 0 && D > 0 && H > 0 && W > 0 && (pad == 0 || pad == 1),
                  "rf_cl_norm_split_halo: bad arguments");
     RF_CHECK_ARG(C2 == 0 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "rf_cl_norm_split_halo: upsampled input needs even extents");
+    RF_CHECK_ARG(!wp || W % 2 == 0, "rf_cl_norm_split_halo_wp: W-pair planes need an even W");
     RF_CHECK_ARG((gn_mu == nullptr) == (gn_a == nullptr) && (gn_mu == nullptr) == (gn_beta == nullptr), "rf_cl_norm_split_halo: partial GroupNorm arguments");
     RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)x2 & 15) == 0,
                  "rf_cl_norm_split_halo: pointers must be 16-byte aligned");
@@ -917,6 +979,7 @@ extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, in
     const int CG = (CC + 3) / 4;
     s.fCG = make_fastdiv(CG);
     s.n_vox = (unsigned)n_vox;
+    s.wp = wp; s.half_vol = (long)D * H * W / 2;
     s.total_oct = (n_vox + 7) / 8 * CG * 32;
     if (CC >= 5)
         cl_norm_split_halo_kernel<1><<<rf_grid_1d(s.total_oct, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(s);
@@ -924,6 +987,21 @@ extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, in
         cl_norm_split_halo_kernel<0><<<rf_grid_1d(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(s);
     RF_LAUNCH_OK("cl_norm_split_halo_kernel");
     return 0;
+}
+
+extern "C" int rf_cl_norm_split_halo(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a,
+                                     const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, int pad, float scale,
+                                     int interior_only, void* stream) {
+    (void)interior_only;  // the planes have no halo any more: every call writes every slot
+    return split_halo(x, C1, x2, C2, gn_mu, gn_a, gn_beta, hi, lo, N, D, H, W, pad, scale, 0, stream);
+}
+
+/* Same activations as W-PAIR planes [chunk][w parity][n][d][h][w / 2] x 16 B (same size as rf_halo_act_bytes, W even):
+ * the operand layout of rf_tc_conv3d_halo_wp_fwd. */
+extern "C" int rf_cl_norm_split_halo_wp(const float* x, int C1, const float* x2, int C2, const float* gn_mu, const float* gn_a,
+                                        const float* gn_beta, void* hi, void* lo, int N, int D, int H, int W, int pad, float scale,
+                                        void* stream) {
+    return split_halo(x, C1, x2, C2, gn_mu, gn_a, gn_beta, hi, lo, N, D, H, W, pad, scale, 1, stream);
 }
 
 extern "C" size_t rf_tc_conv_halo_weight_image_bytes(int Cout, int C1, int C2) {
@@ -1000,6 +1078,70 @@ extern "C" int rf_tc_conv3d_halo_s2_fwd(const void* hi, const void* lo, const vo
                  "rf_tc_conv3d_halo_s2_fwd: pointers must be 16-byte aligned");
     return launch_conv(L, hi, lo, weight_image, bias, y, N, (D - 3) / 2 + 1, (H - 3) / 2 + 1, (W - 3) / 2 + 1, 0, act, slope, out_scale,
                        out_ncdhw, stream, D, H, W);
+}
+
+/* W-pair variant of the 3x3x3 stride-1 layer for small Cout (2 Cout <= 128): a GEMM row is a PAIR of output voxels
+ * (w, w + 1) with N = 2 Cout columns - half the rows at the same pipe time per MMA (the tensor pipe is bound by the A
+ * read for N <= 64), 18 K steps per channel chunk and row pair.  Planes: rf_cl_norm_split_halo_wp; weight image:
+ * rf_tc_conv_halo_wp_weight_image.  D, H, W: INPUT extents (output W must be even).  _supported: 0 = no, 1 = runs,
+ * 2 = runs and the item cost model rates it faster than rf_tc_conv3d_halo_fwd on this shape.  Output: channels-last. */
+extern "C" size_t rf_tc_conv_halo_wp_weight_image_bytes(int Cout, int C1, int C2) {
+    Layer L;
+    return make_layer(Cout, C1, C2, 3, false, L, 1, true) ? weight_image_bytes(L) : 0;
+}
+
+extern "C" int rf_tc_conv_halo_wp_weight_image(const float* w, int Cout, int C1, int C2, float scale, void* image, void* stream) {
+    Layer L;
+    RF_CHECK_ARG(w && image, "rf_tc_conv_halo_wp_weight_image: null pointer");
+    RF_CHECK_ARG(make_layer(Cout, C1, C2, 3, false, L, 1, true), "rf_tc_conv_halo_wp_weight_image: unsupported shape");
+    RF_CHECK_ARG(((uintptr_t)image & 15) == 0, "rf_tc_conv_halo_wp_weight_image: image must be 16-byte aligned");
+    return weight_image(w, L, scale, image, stream);
+}
+
+extern "C" int rf_tc_conv3d_halo_wp_supported(int N, int D, int H, int W, int Cout, int C1, int C2, int pad) {
+    Layer L, L0;
+    if (!make_layer(Cout, C1, C2, 3, false, L, 1, true) || N < 1 || pad < 0 || pad > 1) return 0;
+    const int Do = D + 2 * pad - 2, Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+    if (Do < 1 || Ho < 1 || Wo < 2 || (Wo & 1)) return 0;
+    if ((long)N * D * H * W * L.CC >= (1L << 32) - 256) return 0;
+    Geo g, g0;
+    if (!choose_geometry(N, Do, Ho, Wo / 2, L, pad, g) || g.n_tiles > 32) return 0;
+    if (make_layer(Cout, C1, C2, 3, false, L0) && choose_geometry(N, Do, Ho, Wo, L0, pad, g0) && g0.n_tiles <= 32 && 1.15 * g0.score >= g.score) return 1;  // (the model overrates the variant: measured 1.15-1.25x where it says 1.2-1.5x, and losses below that)
+    return 2;
+}
+
+/* Debug / test aid: item shape and cost-model score (outputs per cycle and SM) of the W-pair variant [0] and of the plain
+ * layout [1]; out16 = 2 x {stacked, G, Dt, Ht, flags, n_tiles, n_items, smem}. */
+extern "C" int rf_tc_conv3d_halo_wp_geometry(int N, int D, int H, int W, int Cout, int C1, int C2, int pad, int* out16, double* scores2) {
+    const int Do = D + 2 * pad - 2, Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+    int ok = 0;
+    for (int k = 0; k < 2; ++k) {
+        Layer L;
+        Geo g;
+        scores2[k] = -1.0;
+        if (!make_layer(Cout, C1, C2, 3, false, L, 1, k == 0) || (k == 0 && (Wo & 1))) continue;
+        if (!choose_geometry(N, Do, Ho, k == 0 ? Wo / 2 : Wo, L, pad, g)) continue;
+        int* o = out16 + 8 * k;
+        o[0] = g.stacked; o[1] = g.G; o[2] = g.Dt; o[3] = g.Ht; o[4] = g.lines + 2 * (g.fused != 0) + 4 * (g.halo == 1) + 8 * (g.fused == 2) + 16 * (g.n_sets == 2) + 32 * g.two_resident;
+        o[5] = g.n_tiles; o[6] = g.n_items; o[7] = (int)g.smem;
+        scores2[k] = g.score;
+        ok |= 1 << k;
+    }
+    return ok;
+}
+
+extern "C" int rf_tc_conv3d_halo_wp_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N,
+                                        int D, int H, int W, int pad, int Cout, int C1, int C2, int act, float slope, float out_scale,
+                                        void* stream) {
+    RF_CHECK_ARG(hi && lo && weight_image && y, "rf_tc_conv3d_halo_wp_fwd: null pointer");
+    Layer L;
+    RF_CHECK_ARG(make_layer(Cout, C1, C2, 3, false, L, 1, true) && N > 0 && (pad == 0 || pad == 1),
+                 "rf_tc_conv3d_halo_wp_fwd: unsupported shape Cout=%d C1=%d C2=%d pad=%d", Cout, C1, C2, pad);
+    RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)weight_image & 15) == 0 && ((uintptr_t)y & 15) == 0,
+                 "rf_tc_conv3d_halo_wp_fwd: pointers must be 16-byte aligned");
+    D += 2 * pad - 2; H += 2 * pad - 2; W += 2 * pad - 2;  // OUTPUT extents
+    RF_CHECK_ARG(D > 0 && H > 0 && W > 0 && (W & 1) == 0, "rf_tc_conv3d_halo_wp_fwd: the output W must be even and positive");
+    return launch_conv(L, hi, lo, weight_image, bias, y, N, D, H, W / 2, pad, act, slope, out_scale, 0, stream);
 }
 
 // ------------------------------------------------------------------ single-channel layers as W-runs (mode 2)

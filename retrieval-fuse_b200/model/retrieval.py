@@ -67,9 +67,12 @@ class _ConvPatchEncoder(RfModule):
                 continue
             if (self.use_halo_conv and k == 3 and s == 1 and
                     ops.tc_conv_halo_supported(h.shape[0], h.shape[1], h.shape[2], h.shape[3], conv.out_channels, cin, 0, pad=0)):
-                # 'valid' 3x3x3 layers: shifted-window kernel, the patch block staged in shared memory once
-                img, sw = self._wcache.derived(("halo", li), [conv.weight], lambda w, c=cin: ops.tc_conv_halo_weight_image(w, c, 0))
-                h = ops.tc_conv3d_halo(ops.cl_norm_split_halo(h, None, None, scale=1.0, pad=0), img, conv.bias, conv.out_channels,
+                # 'valid' 3x3x3 layers: shifted-window kernel, the patch block staged in shared memory once (small Cout:
+                # its W-pair variant, two output voxels per GEMM row, where the kernel's cost model prefers it)
+                wp = ops.tc_conv_halo_wp_wanted(h.shape[0], h.shape[1], h.shape[2], h.shape[3], conv.out_channels, cin, 0, pad=0)
+                img, sw = self._wcache.derived(("halo", li, wp), [conv.weight],
+                                               lambda w, c=cin, q=wp: ops.tc_conv_halo_weight_image(w, c, 0, wp=q))
+                h = ops.tc_conv3d_halo(ops.cl_norm_split_halo(h, None, None, scale=1.0, pad=0, wp=wp), img, conv.bias, conv.out_channels,
                                        act=ops.ACT_LEAKY, slope=0.2, out_scale=1.0 / sw)
                 continue
             if (self.use_halo_conv and k == 3 and s == 2 and

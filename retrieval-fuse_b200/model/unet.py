@@ -21,6 +21,9 @@ USE_HALO_CONV = True
 # by the epilogue's 2.1 GB of fp32 output, 8 of 16 accumulator columns used) against 1.85 ms for the FMA kernel, so the
 # U-Nets keep the FMA kernel; the 5^3 / wide first layers of the patch encoders (model/retrieval.py) take the tensor cores.
 USE_WRUN_CONV = False
+# first DoubleConv on 16^3 single-channel patches: statistics, 1 -> 8 convolution, statistics of its output, normalisation
+# and operand split in one kernel (rf_unet_front.cu) instead of four launches and three HBM passes over the activations
+USE_FUSED_FRONT = True
 # EXPERIMENTAL, OFF by default (tools/wpack_formulation.py): run small-channel 3x3x3 layers through the
 # shifted-window kernel on W-packed views [N,D,H,W/Bw,Bw*C] with Toeplitz-expanded weights.  The identity is verified on
 # the CPU; the kernel has not been measured on these shapes yet, so nothing selects this path unless W_PACK maps
@@ -143,9 +146,11 @@ class SingleConv(RfModule):
             # shifted-window kernel: activations staged in shared memory once, all 27 taps addressed in place
             if not hasattr(self, "_halo_planes"):
                 object.__setattr__(self, "_halo_planes", {})  # zeroed operand planes of this layer, reused across calls
-            split = ops.cl_norm_split_halo(x, x2, (mu, a, g.bias), scale=sa, buffers=self._halo_planes)
-            img, sw = self._wcache.derived(("halo", c1, c2), [self.conv.weight],
-                                           lambda w: ops.tc_conv_halo_weight_image(w, c1, c2))
+            # small Cout: W-pair variant (a GEMM row = two output voxels, N = 2 Cout) where the kernel's cost model prefers it
+            wp = not out_ncdhw and ops.tc_conv_halo_wp_wanted(N, D, H, W, self.out_channels, c1, c2)
+            split = ops.cl_norm_split_halo(x, x2, (mu, a, g.bias), scale=sa, buffers=self._halo_planes, wp=wp)
+            img, sw = self._wcache.derived(("halo", c1, c2, wp), [self.conv.weight],
+                                           lambda w: ops.tc_conv_halo_weight_image(w, c1, c2, wp=wp))
             return ops.tc_conv3d_halo(split, img, self.conv.bias, self.out_channels, act=self.act, slope=0.1,
                                       out_ncdhw=out_ncdhw, out_scale=1.0 / (sa * sw))
         if not ops.tc_conv_supported(self.out_channels, c1, c2, 3):
@@ -168,6 +173,24 @@ class _TwoConvs(nn.Module):
         return self.SingleConv1.tc_ok(c1, c2) and self.SingleConv2.tc_ok(self.SingleConv1.out_channels, 0)
 
     def forward_cl(self, x, x2=None, out_ncdhw=False):
+        c1, c2 = self.SingleConv1, self.SingleConv2
+        if (USE_FUSED_FRONT and x2 is None and x is not None and tuple(x.shape[1:]) == (16, 16, 16, 1) and c1.out_channels == 8
+                and c2.in_channels == 8 and not out_ncdhw and c1.order == "gcr" and c2.order == "gcr" and USE_HALO_CONV
+                and c2.groupnorm.num_groups in (1, 8) and ops.tc_conv_halo_supported(x.shape[0], 16, 16, 16, c2.out_channels, 8, 0)):
+            # first DoubleConv of the retrieval U-Net on its 16^3 patches: GroupNorm -> 1 -> 8 conv -> ReLU -> statistics ->
+            # normalise -> split in ONE kernel that hands the operand planes to the second conv (rf_unet_front.cu)
+            N = x.shape[0]
+            g1, g2 = c1.groupnorm, c2.groupnorm
+            host = c1._wcache.derived(("front16",), [c1.conv.weight, g1.weight, g1.bias],
+                                      lambda w, gw, gb: (w.float().cpu().contiguous(), float(gw[0]), float(gb[0])))
+            wp = ops.tc_conv_halo_wp_wanted(N, 16, 16, 16, c2.out_channels, 8, 0)
+            if not hasattr(c2, "_halo_planes"):
+                object.__setattr__(c2, "_halo_planes", {})
+            split = ops.unet_front16(x, host[1], host[2], g1.eps, host[0], g2.weight, g2.bias, g2.num_groups, g2.eps, ops.ACT_SCALE_GN,
+                                     wp=wp, buffers=c2._halo_planes)
+            img, sw = c2._wcache.derived(("halo", 8, 0, wp), [c2.conv.weight], lambda w: ops.tc_conv_halo_weight_image(w, 8, 0, wp=wp))
+            return ops.tc_conv3d_halo(split, img, c2.conv.bias, c2.out_channels, act=c2.act, slope=0.1,
+                                      out_scale=1.0 / (ops.ACT_SCALE_GN * sw))
         return self.SingleConv2.forward_cl(self.SingleConv1.forward_cl(x, x2), None, out_ncdhw)
 
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import torch
 
@@ -577,10 +578,31 @@ def tc_conv_halo_geometry(N, D, H, W, cout, c1, c2, pad=1):
     return dict(zip(["stacked", "G", "Dt", "Ht", "lines", "n_tiles", "n_items", "smem"], list(out)))
 
 
-def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0, pad=1, buffers=None):
+class _SplitShape(tuple):
+    """(N, D, H, W, c1, c2, pad) of a pair of operand planes; wp: W-pair layout (rf_cl_norm_split_halo_wp)."""
+    wp = False
+
+
+def tc_conv_halo_wp_mode():
+    """RF_HALO_WP: '0' never use the W-pair variant, '1' wherever it runs, unset: where the cost model prefers it."""
+    return os.environ.get("RF_HALO_WP", "")
+
+
+def tc_conv_halo_wp_wanted(N, D, H, W, cout, c1, c2, pad=1):
+    """Whether the W-pair variant of the shifted-window kernel (one GEMM row = two output voxels, N = 2 Cout) should run
+    this 3x3x3 stride-1 layer.  D, H, W: input extents."""
+    mode = tc_conv_halo_wp_mode()
+    if mode == "0":
+        return False
+    r = _lib.lib().rf_tc_conv3d_halo_wp_supported(int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2), int(pad))
+    return r >= (1 if mode == "1" else 2)
+
+
+def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0, pad=1, buffers=None, wp=False):
     """fp32 channels-last x [N,D,H,W,C1] (or None) and half-resolution x2 [N,D/2,H/2,W/2,C2] (or None) ->
     (hi, lo) compact fp16 slot planes [chunk][N][D][H][W][8] of scale * GroupNorm(concat(x, up2(x2))); the zero halo
-    of width pad is produced by the convolution's TMA loads (out-of-bounds zero fill)."""
+    of width pad is produced by the convolution's TMA loads (out-of-bounds zero fill).  wp: W-pair planes
+    [chunk][w parity][N][D][H][W/2][8] for tc_conv3d_halo on a weight image made with wp=True."""
     src = x if x is not None else x2
     src = _dev(src, name="x")
     c1 = x.shape[-1] if x is not None else 0
@@ -597,7 +619,7 @@ def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0, pad=1, buffers=None):
     # (compact planes, every slot is rewritten by every call; the conv's TMA loads make the zero halo on the fly)
     interior_only = 0
     if buffers is not None:
-        key = (N, D, H, W, c1, c2, int(pad), src.device)
+        key = (N, D, H, W, c1, c2, int(pad), src.device, bool(wp))
         if key not in buffers:
             # planes are kept per input shape: a CUDA graph captured for another batch size still points at its own
             # set.  Only when more than MAX_PLANE_SHAPES shapes are live is the least recently used set freed, and
@@ -615,14 +637,53 @@ def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0, pad=1, buffers=None):
         lo = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
     mu, a, beta = gn if gn is not None else (None, None, None)
     with torch.cuda.device(src.device), _timed("rf_cl_norm_split_halo", nbytes=(c1 + c2) * 8.0 * N * D * H * W):
-        check(L.rf_cl_norm_split_halo(_ptr(x), c1, _ptr(x2), c2, _ptr(mu), _ptr(a), _ptr(beta), hi.data_ptr(), lo.data_ptr(),
-                                      N, D, H, W, int(pad), float(scale), interior_only, _stream(src)), "rf_cl_norm_split_halo")
+        if wp:
+            check(L.rf_cl_norm_split_halo_wp(_ptr(x), c1, _ptr(x2), c2, _ptr(mu), _ptr(a), _ptr(beta), hi.data_ptr(), lo.data_ptr(),
+                                             N, D, H, W, int(pad), float(scale), _stream(src)), "rf_cl_norm_split_halo_wp")
+        else:
+            check(L.rf_cl_norm_split_halo(_ptr(x), c1, _ptr(x2), c2, _ptr(mu), _ptr(a), _ptr(beta), hi.data_ptr(), lo.data_ptr(),
+                                          N, D, H, W, int(pad), float(scale), interior_only, _stream(src)), "rf_cl_norm_split_halo")
     _count()
-    return hi, lo, (N, D, H, W, c1, c2, int(pad))
+    shape = _SplitShape((N, D, H, W, c1, c2, int(pad)))
+    shape.wp = bool(wp)
+    return hi, lo, shape
 
 
-def tc_conv_halo_weight_image(weight, c1, c2):
-    """Conv3d weight [Cout, C1+C2, 3,3,3] -> (pre-split fp16 operand image for rf_tc_conv3d_halo_fwd, weight scale)."""
+def unet_front16(x, gn1_w, gn1_b, eps1, conv_w_host, gn2_w, gn2_b, groups2, eps2, scale, wp=False, buffers=None):
+    """Fused front of a 'gcr' DoubleConv on 16^3 single-channel samples (rf_unet_front16_fwd_host): x [N,16,16,16,1] ->
+    the operand planes cl_norm_split_halo(relu(conv(GroupNorm(x))), GroupNorm 2) would produce, as a split tuple for
+    tc_conv3d_halo.  gn1_w / gn1_b: floats; conv_w_host: contiguous CPU fp32 [8,1,3,3,3]; gn2_w / gn2_b: device [8]."""
+    x = _dev(x, name="x")
+    N = x.shape[0]
+    assert tuple(x.shape[1:]) == (16, 16, 16, 1) and conv_w_host.device.type == "cpu" and conv_w_host.numel() == 216
+    L = _lib.lib()
+    nbytes = L.rf_halo_act_bytes(N, 16, 16, 16, 8, 0, 1)
+    key = (N, 16, 16, 16, 8, 0, 1, x.device, bool(wp))
+    if buffers is not None:
+        if key not in buffers:
+            while len(buffers) >= MAX_PLANE_SHAPES:
+                buffers.pop(next(iter(buffers)))
+                bump_generation()
+            buffers[key] = (torch.empty(nbytes, device=x.device, dtype=torch.uint8), torch.empty(nbytes, device=x.device, dtype=torch.uint8))
+        else:
+            buffers[key] = buffers.pop(key)
+        hi, lo = buffers[key]
+    else:
+        hi = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+        lo = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device), _timed("rf_unet_front16_fwd", flops=2.0 * N * 4096 * 27 * 8):
+        check(L.rf_unet_front16_fwd_host(x.data_ptr(), float(gn1_w), float(gn1_b), float(eps1), conv_w_host.data_ptr(), gn2_w.data_ptr(),
+                                         gn2_b.data_ptr(), int(groups2), float(eps2), float(scale), hi.data_ptr(), lo.data_ptr(), N,
+                                         int(bool(wp)), _stream(x)), "rf_unet_front16_fwd_host")
+    _count()
+    shape = _SplitShape((N, 16, 16, 16, 8, 0, 1))
+    shape.wp = bool(wp)
+    return hi, lo, shape
+
+
+def tc_conv_halo_weight_image(weight, c1, c2, wp=False):
+    """Conv3d weight [Cout, C1+C2, 3,3,3] -> (pre-split fp16 operand image for rf_tc_conv3d_halo_fwd, weight scale).
+    wp: the image of the W-pair variant (rf_tc_conv3d_halo_wp_fwd)."""
     weight = _dev(weight.detach(), name="weight")
     assert tuple(weight.shape[2:]) == (3, 3, 3) and weight.shape[1] == c1 + c2
     wmax = float(weight.abs().max())
@@ -630,13 +691,13 @@ def tc_conv_halo_weight_image(weight, c1, c2):
     scale = min(max(scale, 2.0 ** -8), 2.0 ** 24)
     cout = weight.shape[0]
     L = _lib.lib()
-    nbytes = L.rf_tc_conv_halo_weight_image_bytes(cout, c1, c2)
+    nbytes = (L.rf_tc_conv_halo_wp_weight_image_bytes if wp else L.rf_tc_conv_halo_weight_image_bytes)(cout, c1, c2)
     if nbytes == 0:
         raise _lib.RfError(f"halo conv does not support weight {tuple(weight.shape)}")
     img = _aligned_bytes(nbytes, weight.device)
     with torch.cuda.device(weight.device), _timed("rf_tc_conv_halo_weight_image"):
-        check(L.rf_tc_conv_halo_weight_image(weight.data_ptr(), cout, c1, c2, scale, img.data_ptr(), _stream(weight)),
-              "rf_tc_conv_halo_weight_image")
+        check((L.rf_tc_conv_halo_wp_weight_image if wp else L.rf_tc_conv_halo_weight_image)(
+            weight.data_ptr(), cout, c1, c2, scale, img.data_ptr(), _stream(weight)), "rf_tc_conv_halo_weight_image")
     _count()
     return img, scale
 
@@ -649,9 +710,15 @@ def tc_conv3d_halo(split, img, bias, cout, act=ACT_NONE, slope=0.0, out_ncdhw=Fa
     shape = (N, cout, Do, Ho, Wo) if out_ncdhw else (N, Do, Ho, Wo, cout)
     y = torch.empty(shape, device=hi.device, dtype=torch.float32)
     with torch.cuda.device(hi.device), _timed("rf_tc_conv3d_halo_fwd", flops=2.0 * N * Do * Ho * Wo * 27 * (c1 + c2) * cout):
-        check(_lib.lib().rf_tc_conv3d_halo_fwd(hi.data_ptr(), lo.data_ptr(), img.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W,
-                                               pad, cout, c1, c2, act, float(slope), float(out_scale), int(bool(out_ncdhw)),
-                                               torch.cuda.current_stream(hi.device).cuda_stream), "rf_tc_conv3d_halo_fwd")
+        if getattr(split[2], "wp", False):  # W-pair planes (img must come from tc_conv_halo_weight_image(..., wp=True))
+            assert not out_ncdhw, "the W-pair variant writes channels-last"
+            check(_lib.lib().rf_tc_conv3d_halo_wp_fwd(hi.data_ptr(), lo.data_ptr(), img.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W,
+                                                      pad, cout, c1, c2, act, float(slope), float(out_scale),
+                                                      torch.cuda.current_stream(hi.device).cuda_stream), "rf_tc_conv3d_halo_wp_fwd")
+        else:
+            check(_lib.lib().rf_tc_conv3d_halo_fwd(hi.data_ptr(), lo.data_ptr(), img.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W,
+                                                   pad, cout, c1, c2, act, float(slope), float(out_scale), int(bool(out_ncdhw)),
+                                                   torch.cuda.current_stream(hi.device).cuda_stream), "rf_tc_conv3d_halo_fwd")
     _count()
     return y
 

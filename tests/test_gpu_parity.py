@@ -193,6 +193,127 @@ def test_shifted_window_conv(dev, N, S, C1, C2, Cout, ncdhw):
     close(y, ref32, rel_to_max=True, what="shifted-window conv vs oracle")
 
 
+# (N, S, C1, C2, Cout): the W-pair variant (one GEMM row = two output voxels, N = 2 Cout): single-chunk inputs, odd chunk
+# counts (one stage per chunk), concat + upsampled inputs, W' = 1 / 2 / 4 / 8 / 32 half-lines, stacked (ragged, shared
+# halo) and slab items
+WP_CASES = [(3, 16, 8, 0, 16), (2, 8, 56, 0, 16), (5, 8, 16, 0, 32), (300, 8, 16, 0, 16), (301, 4, 32, 0, 32), (1, 32, 0, 16, 16),
+            (2, 64, 16, 0, 16), (37, 2, 8, 0, 16), (21, 4, 8, 0, 16), (11, 4, 16, 32, 24), (3, 8, 32, 64, 56), (70, 8, 16, 0, 16)]
+
+
+@pytest.mark.parametrize("N,S,C1,C2,Cout", WP_CASES)
+def test_shifted_window_conv_w_pairs(dev, N, S, C1, C2, Cout):
+    """model/unet.py:79-100 SingleConv 'gcr' through rf_tc_conv3d_halo_wp_fwd (W-de-interleaved operand planes, the item
+    staged as even / odd sub-blocks, K steps pairing (A[r+p], B[r+p])) against the oracle's restatement and fp64, and
+    against the plain shifted-window kernel."""
+    from retrieval_fuse_b200 import ops, _lib
+    g = torch.Generator().manual_seed(3 * N + 7 * S + C1 + C2 + Cout)
+    C = C1 + C2
+    x = torch.randn(N, C1, S, S, S, generator=g) * 1.5 + 0.3 if C1 else None
+    x2 = torch.randn(N, C2, S // 2, S // 2, S // 2, generator=g) * 0.7 - 0.2 if C2 else None
+    if N > 1 and C1:
+        x[1] = 0.25
+    sd = {"c.groupnorm.weight": torch.rand(C, generator=g) + 0.5, "c.groupnorm.bias": torch.randn(C, generator=g) * 0.1,
+          "c.conv.weight": torch.randn(Cout, C, 3, 3, 3, generator=g) / (27 * C) ** 0.5}
+    parts = ([x] if C1 else []) + ([torch.nn.functional.interpolate(x2, scale_factor=2, mode="nearest")] if C2 else [])
+    xc = torch.cat(parts, 1)
+    groups = 8 if C % 8 == 0 else 1
+    n_ref = min(N, 6)
+    sel = list(range(n_ref)) + ([N - 1] if N > n_ref else [])
+    ref32 = O._single_conv(xc[sel], sd, "c", "gcr", groups)
+    ref64 = O._single_conv(xc[sel].double(), {k: v.double() for k, v in sd.items()}, "c", "gcr", groups)
+    assert _lib.lib().rf_tc_conv3d_halo_wp_supported(N, S, S, S, Cout, C1, C2, 1) >= 1
+    xd = x.permute(0, 2, 3, 4, 1).contiguous().to(dev) if C1 else None
+    x2d = x2.permute(0, 2, 3, 4, 1).contiguous().to(dev) if C2 else None
+    gamma, beta, w = sd["c.groupnorm.weight"].to(dev), sd["c.groupnorm.bias"].to(dev), sd["c.conv.weight"].to(dev)
+    mu, a = ops.cl_gn_stats(xd, gamma, groups, 1e-5, x2=x2d) if C1 else ops.cl_gn_stats(x2d, gamma, groups, 1e-5)
+    sa = ops.ACT_SCALE_GN
+    img, sw = ops.tc_conv_halo_weight_image(w, C1, C2, wp=True)
+    yd = ops.tc_conv3d_halo(ops.cl_norm_split_halo(xd, x2d, (mu, a, beta), scale=sa, wp=True), img, None, Cout, act=ops.ACT_RELU,
+                            out_scale=1.0 / (sa * sw))
+    img0, sw0 = ops.tc_conv_halo_weight_image(w, C1, C2)
+    y0 = ops.tc_conv3d_halo(ops.cl_norm_split_halo(xd, x2d, (mu, a, beta), scale=sa), img0, None, Cout, act=ops.ACT_RELU,
+                            out_scale=1.0 / (sa * sw0))
+    y = yd.permute(0, 4, 1, 2, 3).cpu()[sel]
+    scale = max(1.0, float(ref64.abs().max()))
+    err64 = float((y.double() - ref64).abs().max())
+    assert err64 <= 2e-5 * scale, f"|ours - fp64| {err64:.2e} (scale {scale:.1f})"
+    close(y, ref32, rel_to_max=True, what="W-pair shifted-window conv vs oracle")
+    assert float((yd - y0).abs().max()) <= 4e-5 * scale, "W-pair variant vs plain shifted-window kernel (all samples)"
+
+
+# (N, S_in, Cin, Cout): 'valid' layers of the conv patch encoders (Patch32 8->16 @ 28^3, PCPatch48 16->32 @ 44^3, Patch08 shapes)
+WP_VALID_CASES = [(40, 28, 8, 16), (3, 44, 16, 32), (150, 8, 8, 16), (33, 6, 16, 32), (9, 12, 24, 40)]
+
+
+@pytest.mark.parametrize("N,S,Cin,Cout", WP_VALID_CASES)
+def test_valid_conv_w_pairs(dev, N, S, Cin, Cout):
+    """Conv3d(Cin, Cout, 3) + LeakyReLU(0.2) without padding (model/retrieval.py:4-28) through the W-pair variant of the
+    shifted-window kernel (bias repeated for the second voxel of a pair) against torch's CPU conv3d in fp32 and fp64."""
+    from retrieval_fuse_b200 import ops, _lib
+    g = torch.Generator().manual_seed(5 * N + S + Cin + Cout)
+    x = torch.randn(N, Cin, S, S, S, generator=g) * 1.2 + 0.1
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    sel = list(range(min(N, 4))) + ([N - 1] if N > 4 else [])
+    ref32 = torch.nn.functional.leaky_relu(torch.nn.functional.conv3d(x[sel], w, b), 0.2)
+    ref64 = torch.nn.functional.leaky_relu(torch.nn.functional.conv3d(x[sel].double(), w.double(), b.double()), 0.2)
+    assert _lib.lib().rf_tc_conv3d_halo_wp_supported(N, S, S, S, Cout, Cin, 0, 0) >= 1
+    xd = x.permute(0, 2, 3, 4, 1).contiguous().to(dev)
+    img, sw = ops.tc_conv_halo_weight_image(w.to(dev), Cin, 0, wp=True)
+    y = ops.tc_conv3d_halo(ops.cl_norm_split_halo(xd, None, None, scale=1.0, pad=0, wp=True), img, b.to(dev), Cout, act=ops.ACT_LEAKY,
+                           slope=0.2, out_scale=1.0 / sw)
+    y = y.permute(0, 4, 1, 2, 3).cpu()[sel]
+    assert y.shape == ref32.shape
+    scale = max(1.0, float(ref64.abs().max()))
+    err64 = float((y.double() - ref64).abs().max())
+    assert err64 <= 2e-5 * scale, f"|ours - fp64| {err64:.2e} (scale {scale:.1f})"
+    close(y, ref32, rel_to_max=True, what="W-pair 'valid' conv vs torch fp32")
+
+
+@pytest.mark.parametrize("N,groups,wp", [(5, 8, "1"), (301, 8, "0"), (3, 1, "1"), (150, 8, "")])
+def test_fused_front_of_first_double_conv(dev, N, groups, wp, monkeypatch):
+    """model/unet.py:103-144 DoubleConv(1, 16, encoder=True, 'gcr') on 16^3 patches (first block of the retrieval U-Net,
+    model/refinement.py:64-73): the fused front kernel (GroupNorm -> 1->8 conv -> ReLU -> statistics -> normalise -> operand
+    split, rf_unet_front16_fwd_host) + second conv against torch CPU in fp64 / fp32 and against the unfused launches."""
+    from retrieval_fuse_b200 import ops
+    from retrieval_fuse_b200.model import unet as U
+    monkeypatch.setenv("RF_HALO_WP", wp)
+    g = torch.Generator().manual_seed(17 * N + groups)
+    blk = U.DoubleConv(1, 16, encoder=True, order="gcr", num_groups=groups)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.3 if p.dim() > 1 else 0.2) + (1.0 if p.dim() == 1 else 0.0))
+    x = torch.randn(N, 1, 16, 16, 16, generator=g) * 0.8 + 0.2
+    x[1 % N] = -0.4  # constant sample: variance 0 in both GroupNorms
+    F = torch.nn.functional
+    c1, c2 = blk.SingleConv1, blk.SingleConv2
+
+    def ref(xx, dt):
+        h = F.group_norm(xx.to(dt), 1, c1.groupnorm.weight.to(dt), c1.groupnorm.bias.to(dt), 1e-5)
+        h = F.relu(F.conv3d(h, c1.conv.weight.to(dt), padding=1))
+        h = F.group_norm(h, c2.groupnorm.num_groups, c2.groupnorm.weight.to(dt), c2.groupnorm.bias.to(dt), 1e-5)
+        return F.relu(F.conv3d(h, c2.conv.weight.to(dt), padding=1))
+    sel = list(range(min(N, 4))) + ([N - 1] if N > 4 else [])
+    with torch.no_grad():
+        ref64, ref32 = ref(x[sel], torch.float64), ref(x[sel], torch.float32)
+    blk = blk.to(dev)
+    xd = x.permute(0, 2, 3, 4, 1).contiguous().to(dev)
+    with torch.no_grad():
+        ops.reset_launches()
+        y = blk.forward_cl(xd)
+        n_fused = ops.launches()
+        monkeypatch.setattr(U, "USE_FUSED_FRONT", False)
+        y0 = blk.forward_cl(xd)
+    assert n_fused <= 3, f"{n_fused} launches: the fused front did not run"
+    yc = y.permute(0, 4, 1, 2, 3).cpu()[sel]
+    scale = max(1.0, float(ref64.abs().max()))
+    err64 = float((yc.double() - ref64).abs().max())
+    noise = float((ref32.double() - ref64).abs().max())
+    assert err64 <= max(2e-5 * scale, 4 * noise), f"|ours - fp64| {err64:.2e} (torch fp32 noise {noise:.2e}, scale {scale:.1f})"
+    close(yc, ref32, rel_to_max=True, what="fused front + second conv vs torch fp32")
+    assert float((y - y0).abs().max()) <= 4e-5 * scale, "fused front vs separate launches (all samples)"
+
+
 # (N, S, Cout, KS, pad, groupnorm): the single-channel first layers - U-Net 'gcr' 3^3 'same' (stacked 8^3 / slab 16^3 /
 # 64^3 items), encoder 3^3 and 5^3 'valid' layers with bias + LeakyReLU (Patch08 / Patch32 / PCPatch48 shapes)
 WRUN_CASES = [(5, 16, 8, 3, 1, True), (301, 8, 8, 3, 1, True), (2, 64, 16, 3, 1, True), (37, 8, 16, 3, 0, False),
