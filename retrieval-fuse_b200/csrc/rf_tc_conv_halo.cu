@@ -319,7 +319,10 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
     for (int i = threadIdx.x; i < a.n_tiles * TM; i += NTHREADS) {
         const int t = i >> 7, r = i & 127;
         int line, w;
-        if (a.lines) {
+        if (a.lines == 2) {  // "planes": tile = the 16 lines of ONE d plane of the slab (Ht = 16): no halo line is a GEMM row
+            line = (t / a.n_wblk) * a.Hs + (r >> 3);
+            w = (t % a.n_wblk) * 8 + (r & 7);
+        } else if (a.lines) {
             line = (t / a.n_wblk) * 16 + (r >> 3);
             w = (t % a.n_wblk) * 8 + (r & 7);
         } else {
@@ -677,7 +680,11 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
         const long lines_needed = stacked ? (long)(G - 1) * Dp * Hp + (long)(D - 1) * Hp + H : (long)(Dt - 1) * Hs + Ht;
         long n_tiles, max_slot;
         const int n_wblk = lines ? (W + 7) / 8 : 1;
-        if (lines) {
+        if (lines == 2) {  // planes: one tile per (d plane, 8-voxel block) of a slab with exactly 16 lines per plane
+            if (stacked || Ht != 16) return;
+            n_tiles = (long)Dt * n_wblk;
+            max_slot = ((long)(Dt - 1) * Hs + 15) * Wp + (n_wblk * 8 - 1) + reach;
+        } else if (lines) {
             const long lb = (lines_needed + 15) / 16;
             n_tiles = lb * n_wblk;
             max_slot = (lb * 16 - 1) * Wp + (n_wblk * 8 - 1) + reach;
@@ -748,7 +755,10 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
                 const double step_fused = fmax(pipe_cycles(2 * Npad), issue) + fmax(pipe_cycles(Npad), issue);
                 const double step_two = 3.0 * fmax(pipe_cycles(Npad), issue);
                 const double t_mma = (double)n_stages * L.n_groups * kpg * (n_fused * step_fused + (n_tiles - n_fused) * step_two);
-                const double t_epi = 1000.0 + (double)((n_tiles + 1) / 2) * ((tile_cols + 15) / 16) * 1200.0;
+                // (per 16 OUTPUT columns: the fused scheme's cross block is a second TMEM load added to the same registers,
+                // not a second block of work - counting it as one made the chooser avoid the fused scheme for W pairs)
+                const double t_epi = 1000.0 + (double)((n_tiles + 1) / 2) * (Npad / 16) * (n_fused ? 1500.0 : 1200.0);
+                (void)tile_cols;
                 // staging: ~25 bytes per clock and SM from L2 when every SM pulls (decoder 16 -> 16 @ 64^3: 127 KB per
                 // item in ~5000 cycles); hidden behind the MMAs only with a second buffer or a second resident CTA
                 const double n_loads = n_stages == 1 ? 1.0 : (fused == 1 ? 1.0 : 2.0) * n_stages;
@@ -778,8 +788,8 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
             return best.score > 0.0;
         }
     }
-    for (int lines = 0; lines < 2; ++lines) {
-        for (int G = 1; G <= 32 && G <= N; ++G) {  // (the row table keeps the stacked sample index in 5 bits)
+    for (int lines = 0; lines < 3; ++lines) {
+        for (int G = 1; G <= 32 && G <= N && lines < 2; ++G) {  // (the row table keeps the stacked sample index in 5 bits)
             consider(1, G, D, H, W, lines, 0);
             if (shareable) consider(1, G, D, H, W, lines, 1);
         }
@@ -870,7 +880,8 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
     // tile t = lb * n_wblk + wb starts at slot lb * (16 lines) + wb * 8 (linear mode: n_wblk = 1, 128 slots per tile)
     RF_CHECK_ARG(g.n_tiles <= 32, "rf_tc_conv3d_halo_fwd: internal: more than 32 M tiles");
     for (int t = 0; t < 32; ++t) {
-        const long off = g.lines ? (long)(t / g.n_wblk) * 16 * a.Wp + (t % g.n_wblk) * 8 : (long)t * 128;
+        const long off = g.lines == 2 ? (long)(t / g.n_wblk) * g.Hs * a.Wp + (t % g.n_wblk) * 8
+                       : g.lines ? (long)(t / g.n_wblk) * 16 * a.Wp + (t % g.n_wblk) * 8 : (long)t * 128;
         a.tile_off[t] = (uint16_t)(t < g.n_tiles ? off : 0);
     }
     // k step table: slot offset of the step's first chunk, distance to its second chunk
@@ -1050,7 +1061,7 @@ extern "C" int rf_tc_conv3d_halo_geometry(int N, int D, int H, int W, int Cout, 
     if (!make_layer(Cout, C1, C2, 3, false, L)) return 0;
     Geo g;
     if (!choose_geometry(N, D + 2 * pad - 2, H + 2 * pad - 2, W + 2 * pad - 2, L, pad, g)) return 0;
-    out8[0] = g.stacked; out8[1] = g.G; out8[2] = g.Dt; out8[3] = g.Ht; out8[4] = g.lines + 2 * (g.fused != 0) + 4 * (g.halo == 1) + 8 * (g.fused == 2); out8[5] = g.n_tiles;
+    out8[0] = g.stacked; out8[1] = g.G; out8[2] = g.Dt; out8[3] = g.Ht; out8[4] = (g.lines & 1) + 2 * (g.fused != 0) + 4 * (g.halo == 1) + 8 * (g.fused == 2) + 64 * (g.lines == 2); out8[5] = g.n_tiles;
     out8[6] = g.n_items; out8[7] = (int)g.smem;
     return 1;
 }
@@ -1122,7 +1133,7 @@ extern "C" int rf_tc_conv3d_halo_wp_geometry(int N, int D, int H, int W, int Cou
         if (!make_layer(Cout, C1, C2, 3, false, L, 1, k == 0) || (k == 0 && (Wo & 1))) continue;
         if (!choose_geometry(N, Do, Ho, k == 0 ? Wo / 2 : Wo, L, pad, g)) continue;
         int* o = out16 + 8 * k;
-        o[0] = g.stacked; o[1] = g.G; o[2] = g.Dt; o[3] = g.Ht; o[4] = g.lines + 2 * (g.fused != 0) + 4 * (g.halo == 1) + 8 * (g.fused == 2) + 16 * (g.n_sets == 2) + 32 * g.two_resident;
+        o[0] = g.stacked; o[1] = g.G; o[2] = g.Dt; o[3] = g.Ht; o[4] = (g.lines & 1) + 2 * (g.fused != 0) + 4 * (g.halo == 1) + 8 * (g.fused == 2) + 16 * (g.n_sets == 2) + 32 * g.two_resident + 64 * (g.lines == 2);
         o[5] = g.n_tiles; o[6] = g.n_items; o[7] = (int)g.smem;
         scores2[k] = g.score;
         ok |= 1 << k;

@@ -40,7 +40,7 @@ for wp in (False, True):
     img, sw = ops.tc_conv_halo_weight_image(w, C1, C2, wp=wp)
     split = ops.cl_norm_split_halo(x, x2, None, scale=16.0, pad=pad, wp=wp)
     res = []
-    shapes = [(0, 1, dt, ht, ln, 0) for dt in divs for ht in divs for ln in (0, 1)]
+    shapes = [(0, 1, dt, ht, ln, 0) for dt in divs for ht in divs for ln in (0, 1, 2) if ln < 2 or ht == 16]
     if So <= 8:
         shapes += [(1, G, So, So, ln, hl) for G in (1, 2, 3, 4, 6, 8) for ln in (0, 1) for hl in ((0, 1) if pad else (0,))]
     for shp in shapes:
