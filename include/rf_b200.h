@@ -196,6 +196,12 @@ int rf_cl_norm_split_halo_wp(const float* x, int C1, const float* x2, int C2, co
 size_t rf_tc_conv_halo_wp_weight_image_bytes(int Cout, int C1, int C2);
 int rf_tc_conv_halo_wp_weight_image(const float* w, int Cout, int C1, int C2, float scale, void* image, void* stream);
 int rf_tc_conv3d_halo_wp_supported(int N, int D, int H, int W, int Cout, int C1, int C2, int pad);
+/* Same convolution with MaxPool3d(2) of the activated output taken in the epilogue (model/unet.py:210-253: an encoder
+ * level whose full-resolution output only feeds the next level's pooling): y is [N, D/2, H/2, W/2, Cout] channels-last.
+ * 'same' padding, Cout % 16 == 0, even extents. */
+int rf_tc_conv3d_halo_wp_pool_supported(int N, int D, int H, int W, int Cout, int C1, int C2);
+int rf_tc_conv3d_halo_wp_pool_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D,
+                                  int H, int W, int Cout, int C1, int C2, int act, float slope, float out_scale, void* stream);
 int rf_tc_conv3d_halo_wp_geometry(int N, int D, int H, int W, int Cout, int C1, int C2, int pad, int* out16, double* scores2);
 int rf_tc_conv3d_halo_wp_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D,
                              int H, int W, int pad, int Cout, int C1, int C2, int act, float slope, float out_scale, void* stream);

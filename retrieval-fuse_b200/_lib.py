@@ -77,6 +77,9 @@ PROTOTYPES = {
     "rf_tc_conv_halo_wp_weight_image_bytes": (c_size_t, [c_int, c_int, c_int]),
     "rf_tc_conv_halo_wp_weight_image": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "rf_tc_conv3d_halo_wp_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "rf_tc_conv3d_halo_wp_pool_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "rf_tc_conv3d_halo_wp_pool_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                              c_int, c_int, c_float, c_float, c_void_p]),
     "rf_tc_conv3d_halo_wp_geometry": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rf_tc_conv3d_halo_wp_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_int, c_int, c_float, c_float, c_void_p]),

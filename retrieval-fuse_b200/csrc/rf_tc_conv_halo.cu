@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs
 struct Layer {
     int mode, KS, stride;  // stride 2: 'valid' 3^3 only (the patch encoders' down-sampling layers)
     int wp;                // mode 3: W pairs (two output voxels per GEMM row)
+    int pool;              // W pairs + 'planes' items: the epilogue writes MaxPool3d(2) of the activated output
     int C1, C2, Cp1, Cp2, CC, CCe, Cout, Npad;
     int ck, n_stages, kpg, n_groups;
     int hd, hw;  // block extent beyond the output extent: D / H (KS - 1) and W (KS - 1; 0 in mode 2)
@@ -248,6 +249,7 @@ struct HaloArgs {
     int pad, CC, tm5;             // conv padding (0 / 1); real channel chunks (chunk >= CC: all zero); 5-D tensor maps
     int s2, P_sub;                // stride 2: 8 parity sub-blocks per plane, P_sub slots apart
     int nb_shift;                 // log2 of the weight ring's slots
+    int pool;                     // epilogue max-pools 2x2x2 (W pairs, planes mode): y is [N, D/2, H/2, W/2, Cb]
     int wp, Cb;                   // W pairs: 2 sub-blocks per plane (even / odd padded positions); channels of the bias vector
     long V;                       // slots per haloed sample volume
     int Dt, Ht, Wt, Hs, G, stacked;  // item = G stacked whole samples, or a Dt x Ht x Wt slab of one sample
@@ -535,6 +537,52 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
             mbar_wait_warp_sleepy(bar_dfull + 8 * set, use & 1u);
             tc_fence_after();
             if (dbg) g_halo_dbg[it * 8 + 5] = clock64();
+            if constexpr (RES == 1) {
+              if (a.pool) {
+                // MaxPool3d(2) of the activated output in the epilogue (W pairs, planes mode: tile t = d plane t of the slab,
+                // row = (h = q * 4 + lane / 8, pair lane & 7)): the pooling window is the thread's two voxels (w), the
+                // same row of lane ^ 8 (h) and the same row of tile t ^ 1 (d).  max commutes with the monotone scale /
+                // bias / activation, so those run once on the pooled values.  The full-resolution output never exists.
+                const int nkb = a.Cb >> 4;  // 16-channel blocks per voxel
+                const int hh = q * 4 + (lane >> 3);
+                for (int p = half; p < (a.n_tiles >> 1); p += 2)
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        float m[16];
+#pragma unroll
+                        for (int sv = 0; sv < 4; ++sv) {  // (tile, voxel of the pair) = (2 p + sv / 2, sv % 2)
+                            const uint32_t t = 2u * (uint32_t)p + (uint32_t)(sv >> 1);
+                            const bool tf = t < nf;
+                            const uint32_t ta = tm_set + ((uint32_t)(q * 32) << 16) + (t + (tf ? t : nf)) * npad + (uint32_t)(((sv & 1) * nkb + kb) << 4);
+                            float v[16], u[16];
+                            tc_ld16_issue(ta, v);
+                            if (tf) tc_ld16_issue(ta + npad, u);
+                            tc_ld_wait();
+                            tc_ld_fence16(v);
+                            if (tf) {
+                                tc_ld_fence16(u);
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) v[e] += u[e];
+                            }
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) m[e] = sv ? fmaxf(m[e], v[e]) : v[e];
+                        }
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) m[e] = fmaxf(m[e], __shfl_xor_sync(0xffffffffu, m[e], 8));
+                        if (!(lane & 8)) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) m[e] = fmaf(m[e], a.out_scale, a.bias ? __ldg(a.bias + kb * 16 + e) : 0.f);
+                            rf_act_vec(m, a.act, a.slope);
+                            const long po = ((((long)n0 * (a.D >> 1) + ((d0 >> 1) + p)) * (a.H >> 1) + ((h0 + hh) >> 1)) * a.W + (w0 + (lane & 7))) * a.Cb + kb * 16;
+#pragma unroll
+                            for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(a.y + po + e) = make_float4(m[e], m[e + 1], m[e + 2], m[e + 3]);
+                        }
+                    }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_dempty + 8 * set);
+                continue;
+              }
+            }
             // (tile, 16-column block) pairs of this warp, software-pipelined: the TMEM loads of the next pair are in
             // flight while the current one is scaled, activated and stored (one pair took ~1200 cycles of exposed
             // TMEM latency + store issue; small-Cout layers were bound by this loop, not by the MMAs)
@@ -680,6 +728,7 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
         const long lines_needed = stacked ? (long)(G - 1) * Dp * Hp + (long)(D - 1) * Hp + H : (long)(Dt - 1) * Hs + Ht;
         long n_tiles, max_slot;
         const int n_wblk = lines ? (W + 7) / 8 : 1;
+        if (L.pool && (lines != 2 || (Dt & 1) || n_wblk != 1)) return;  // pooling epilogue: d planes in tile pairs, one 8-pair block per line
         if (lines == 2) {  // planes: one tile per (d plane, 8-voxel block) of a slab with exactly 16 lines per plane
             if (stacked || Ht != 16) return;
             n_tiles = (long)Dt * n_wblk;
@@ -750,7 +799,7 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
                 const int tile_cols = (int)(cols / n_tiles);  // average, for the epilogue estimate
                 const long smem_total = 1024 + smemA + (long)NB * bslot + 256 + n_tiles * 512;
                 static const int force_res = [] { const char* e = getenv("RF_HALO_RES"); return e ? atoi(e) : 0; }();  // tuning aid
-                const bool two_resident = force_res != 1 && smem_total <= 113 * 1024 && cols_needed <= 256;
+                const bool two_resident = force_res != 1 && smem_total <= 113 * 1024 && cols_needed <= 256 && !L.pool;
                 const double issue = 150.0 / (n_iss * (two_resident ? 2 : 1));
                 const double step_fused = fmax(pipe_cycles(2 * Npad), issue) + fmax(pipe_cycles(Npad), issue);
                 const double step_two = 3.0 * fmax(pipe_cycles(Npad), issue);
@@ -808,10 +857,11 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
 }
 
 // mode 0 / 1 layers: 3x3x3 over C1 + C2 channels (x2 upsampled); mode 2: KS^3 over ONE channel (C1 = 1, KS 3 or 5)
-bool make_layer(int Cout, int C1, int C2, int KS, bool wrun, Layer& L, int stride = 1, bool wp = false) {
+bool make_layer(int Cout, int C1, int C2, int KS, bool wrun, Layer& L, int stride = 1, bool wp = false, bool pool = false) {
     if (Cout < 1 || Cout > 256 || C1 < 0 || C2 < 0 || C1 + C2 < 1 || (stride != 1 && stride != 2)) return false;
     if (stride == 2 && (wrun || C2 != 0)) return false;
-    L.KS = KS; L.C1 = C1; L.C2 = C2; L.Cout = Cout; L.stride = stride; L.wp = wp ? 1 : 0;
+    if (pool && (!wp || (Cout & 15))) return false;
+    L.KS = KS; L.C1 = C1; L.C2 = C2; L.Cout = Cout; L.stride = stride; L.wp = wp ? 1 : 0; L.pool = pool ? 1 : 0;
     L.Cp1 = round_up(C1, 8); L.Cp2 = round_up(C2, 8);
     L.CC = (L.Cp1 + L.Cp2) / 8;
     L.Npad = round_up(Cout, 16);
@@ -868,7 +918,7 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
     a.N = N; a.D = D; a.H = H; a.W = W; a.Hp = H + g.hd; a.Wp = g.Wt + g.hw;
     a.pad = pad; a.CC = L.CC; a.w0 = L.mode == 2 ? 0 : -pad;
     a.s2 = L.stride == 2 ? 1 : 0; a.P_sub = g.P_sub;
-    a.wp = L.wp; a.Cb = L.Cout; a.nb_shift = g.nb == 8 ? 3 : 2;
+    a.wp = L.wp; a.Cb = L.Cout; a.pool = L.pool; a.nb_shift = g.nb == 8 ? 3 : 2;
     a.V = (long)(D + g.hd) * (H + g.hd) * (W + g.hw);
     a.Dt = g.Dt; a.Ht = g.Ht; a.Wt = g.Wt; a.Hs = g.Hs; a.G = g.G; a.stacked = g.stacked;
     a.n_dt = D / g.Dt; a.n_ht = H / g.Ht; a.n_wt = W / g.Wt; a.Ls = (D + g.hd) * (H + g.hd);
@@ -1119,6 +1169,30 @@ extern "C" int rf_tc_conv3d_halo_wp_supported(int N, int D, int H, int W, int Co
     if (!choose_geometry(N, Do, Ho, Wo / 2, L, pad, g) || g.n_tiles > 32) return 0;
     if (make_layer(Cout, C1, C2, 3, false, L0) && choose_geometry(N, Do, Ho, Wo, L0, pad, g0) && g0.n_tiles <= 32 && 1.15 * g0.score >= g.score) return 1;  // (the model overrates the variant: measured 1.15-1.25x where it says 1.2-1.5x, and losses below that)
     return 2;
+}
+
+/* W-pair convolution whose epilogue writes MaxPool3d(2) of the activated output: y is [N, D/2, H/2, W/2, Cout]
+ * channels-last (model/unet.py:210-253: an encoder level whose full-resolution output only feeds the next level's pooling).
+ * Needs Cout % 16 == 0, 'same' padding, 16-line slabs ("planes" items); _supported says whether an item shape exists. */
+extern "C" int rf_tc_conv3d_halo_wp_pool_supported(int N, int D, int H, int W, int Cout, int C1, int C2) {
+    Layer L;
+    if (!make_layer(Cout, C1, C2, 3, false, L, 1, true, true) || N < 1 || D < 2 || H < 2 || W < 2 || ((D | H | W) & 1)) return 0;
+    if ((long)N * D * H * W * L.CC >= (1L << 32) - 256) return 0;
+    Geo g;
+    return choose_geometry(N, D, H, W / 2, L, 1, g) && g.n_tiles <= 32 ? 1 : 0;
+}
+
+extern "C" int rf_tc_conv3d_halo_wp_pool_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N,
+                                             int D, int H, int W, int Cout, int C1, int C2, int act, float slope, float out_scale,
+                                             void* stream) {
+    RF_CHECK_ARG(hi && lo && weight_image && y, "rf_tc_conv3d_halo_wp_pool_fwd: null pointer");
+    Layer L;
+    RF_CHECK_ARG(make_layer(Cout, C1, C2, 3, false, L, 1, true, true) && N > 0 && D > 1 && H > 1 && W > 1 && !((D | H | W) & 1),
+                 "rf_tc_conv3d_halo_wp_pool_fwd: unsupported shape Cout=%d C1=%d C2=%d %dx%dx%d", Cout, C1, C2, D, H, W);
+    RF_CHECK_ARG(out_scale > 0.f, "rf_tc_conv3d_halo_wp_pool_fwd: the output scale must be positive (max is taken before it)");
+    RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)weight_image & 15) == 0 && ((uintptr_t)y & 15) == 0,
+                 "rf_tc_conv3d_halo_wp_pool_fwd: pointers must be 16-byte aligned");
+    return launch_conv(L, hi, lo, weight_image, bias, y, N, D, H, W / 2, 1, act, slope, out_scale, 0, stream);
 }
 
 /* Debug / test aid: item shape and cost-model score (outputs per cycle and SM) of the W-pair variant [0] and of the plain

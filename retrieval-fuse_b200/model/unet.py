@@ -24,6 +24,9 @@ USE_WRUN_CONV = False
 # first DoubleConv on 16^3 single-channel patches: statistics, 1 -> 8 convolution, statistics of its output, normalisation
 # and operand split in one kernel (rf_unet_front.cu) instead of four launches and three HBM passes over the activations
 USE_FUSED_FRONT = True
+# encoder levels whose output is not a skip connection hand MaxPool3d(2) of it to the next level (pooled in the
+# convolution's epilogue where the W-pair variant of the shifted-window kernel runs the layer)
+FUSE_POOL = True
 # EXPERIMENTAL, OFF by default (tools/wpack_formulation.py): run small-channel 3x3x3 layers through the
 # shifted-window kernel on W-packed views [N,D,H,W/Bw,Bw*C] with Toeplitz-expanded weights.  The identity is verified on
 # the CPU; the kernel has not been measured on these shapes yet, so nothing selects this path unless W_PACK maps
@@ -93,6 +96,29 @@ class SingleConv(RfModule):
                           stride=1, pad=self.padding, act=self.act, slope=0.1, x2=x2, gn=gn)
 
 
+    def _halo_image(self, c1, c2, wp):
+        return self._wcache.derived(("halo", c1, c2, wp), [self.conv.weight], lambda w: ops.tc_conv_halo_weight_image(w, c1, c2, wp=wp))
+
+    def _pool_in_epilogue(self, x, x2):
+        """The W-pair variant of the shifted-window kernel can take MaxPool3d(2) in its epilogue for this input."""
+        c2 = x2.shape[-1] if x2 is not None else 0
+        N, D, H, W, c1 = x.shape
+        return (USE_TENSOR_CORES and USE_HALO_CONV and self.tc_ok(c1, c2) and
+                ops.tc_conv_halo_wp_pool_supported(N, D, H, W, self.out_channels, c1, c2))
+
+    def _forward_cl_halo(self, x, x2, wp, pool):
+        """GroupNorm statistics -> operand planes -> shifted-window convolution (optionally pooled in the epilogue)."""
+        g = self.groupnorm
+        c1 = x.shape[-1] if x is not None else 0
+        c2 = x2.shape[-1] if x2 is not None else 0
+        mu, a = ops.cl_gn_stats(x, g.weight, g.num_groups, g.eps, x2=x2)
+        if not hasattr(self, "_halo_planes"):
+            object.__setattr__(self, "_halo_planes", {})
+        sa = ops.ACT_SCALE_GN
+        split = ops.cl_norm_split_halo(x, x2, (mu, a, g.bias), scale=sa, buffers=self._halo_planes, wp=wp)
+        img, sw = self._halo_image(c1, c2, wp)
+        return ops.tc_conv3d_halo(split, img, self.conv.bias, self.out_channels, act=self.act, slope=0.1, out_scale=1.0 / (sa * sw), pool=pool)
+
     def tc_ok(self, c1, c2):
         """Structure the channels-last tensor-core path handles: GroupNorm in front of a 3x3x3 'same' conv.  Whether
         the shifted-window kernel, the gathering kernel or (for shapes neither takes) the fp32 kernel runs a layer is
@@ -100,9 +126,14 @@ class SingleConv(RfModule):
         return ("g" in self.order and self.order.index("g") < self.order.index("c") and self.kernel_size == 3
                 and self.padding == 1)
 
-    def forward_cl(self, x, x2=None, out_ncdhw=False):
+    def forward_cl(self, x, x2=None, out_ncdhw=False, pool=False):
         """Channels-last tensor-core path.  x: fp32 [N,D,H,W,C1] or None; x2: fp32 half-resolution
-        [N,D/2,H/2,W/2,C2] or None (virtually upsampled and concatenated after x)."""
+        [N,D/2,H/2,W/2,C2] or None (virtually upsampled and concatenated after x).  pool: return MaxPool3d(2) of the
+        output (taken in the convolution's epilogue where the W-pair variant can, by a pooling launch otherwise)."""
+        if pool:
+            if x is not None and self._pool_in_epilogue(x, x2):
+                return self._forward_cl_halo(x, x2, wp=True, pool=True)
+            return ops.cl_maxpool3d_2(self.forward_cl(x, x2))
         g = self.groupnorm
         c1 = x.shape[-1] if x is not None else 0
         c2 = x2.shape[-1] if x2 is not None else 0
@@ -149,8 +180,7 @@ class SingleConv(RfModule):
             # small Cout: W-pair variant (a GEMM row = two output voxels, N = 2 Cout) where the kernel's cost model prefers it
             wp = not out_ncdhw and ops.tc_conv_halo_wp_wanted(N, D, H, W, self.out_channels, c1, c2)
             split = ops.cl_norm_split_halo(x, x2, (mu, a, g.bias), scale=sa, buffers=self._halo_planes, wp=wp)
-            img, sw = self._wcache.derived(("halo", c1, c2, wp), [self.conv.weight],
-                                           lambda w: ops.tc_conv_halo_weight_image(w, c1, c2, wp=wp))
+            img, sw = self._halo_image(c1, c2, wp)
             return ops.tc_conv3d_halo(split, img, self.conv.bias, self.out_channels, act=self.act, slope=0.1,
                                       out_ncdhw=out_ncdhw, out_scale=1.0 / (sa * sw))
         if not ops.tc_conv_supported(self.out_channels, c1, c2, 3):
@@ -172,7 +202,9 @@ class _TwoConvs(nn.Module):
     def tc_ok(self, c1, c2):
         return self.SingleConv1.tc_ok(c1, c2) and self.SingleConv2.tc_ok(self.SingleConv1.out_channels, 0)
 
-    def forward_cl(self, x, x2=None, out_ncdhw=False):
+    def forward_cl(self, x, x2=None, out_ncdhw=False, pool=False):
+        """pool: return MaxPool3d(2) of the block's output (model/unet.py:210-253: the next encoder's pooling, for a level
+        whose full-resolution output is not a skip connection)."""
         c1, c2 = self.SingleConv1, self.SingleConv2
         if (USE_FUSED_FRONT and x2 is None and x is not None and tuple(x.shape[1:]) == (16, 16, 16, 1) and c1.out_channels == 8
                 and c2.in_channels == 8 and not out_ncdhw and c1.order == "gcr" and c2.order == "gcr" and USE_HALO_CONV
@@ -183,15 +215,17 @@ class _TwoConvs(nn.Module):
             g1, g2 = c1.groupnorm, c2.groupnorm
             host = c1._wcache.derived(("front16",), [c1.conv.weight, g1.weight, g1.bias],
                                       lambda w, gw, gb: (w.float().cpu().contiguous(), float(gw[0]), float(gb[0])))
-            wp = ops.tc_conv_halo_wp_wanted(N, 16, 16, 16, c2.out_channels, 8, 0)
+            pool_ep = pool and ops.tc_conv_halo_wp_pool_supported(N, 16, 16, 16, c2.out_channels, 8, 0)
+            wp = pool_ep or ops.tc_conv_halo_wp_wanted(N, 16, 16, 16, c2.out_channels, 8, 0)
             if not hasattr(c2, "_halo_planes"):
                 object.__setattr__(c2, "_halo_planes", {})
             split = ops.unet_front16(x, host[1], host[2], g1.eps, host[0], g2.weight, g2.bias, g2.num_groups, g2.eps, ops.ACT_SCALE_GN,
                                      wp=wp, buffers=c2._halo_planes)
-            img, sw = c2._wcache.derived(("halo", 8, 0, wp), [c2.conv.weight], lambda w: ops.tc_conv_halo_weight_image(w, 8, 0, wp=wp))
-            return ops.tc_conv3d_halo(split, img, c2.conv.bias, c2.out_channels, act=c2.act, slope=0.1,
-                                      out_scale=1.0 / (ops.ACT_SCALE_GN * sw))
-        return self.SingleConv2.forward_cl(self.SingleConv1.forward_cl(x, x2), None, out_ncdhw)
+            img, sw = c2._halo_image(8, 0, wp)
+            y = ops.tc_conv3d_halo(split, img, c2.conv.bias, c2.out_channels, act=c2.act, slope=0.1,
+                                   out_scale=1.0 / (ops.ACT_SCALE_GN * sw), pool=pool_ep)
+            return ops.cl_maxpool3d_2(y) if pool and not pool_ep else y
+        return self.SingleConv2.forward_cl(self.SingleConv1.forward_cl(x, x2), None, out_ncdhw, pool=pool)
 
 
 class DoubleConv(_TwoConvs):
@@ -244,10 +278,12 @@ class Encoder(nn.Module):
                 x = ops.maxpool3d_2(x)
         return self.basic_module(x)
 
-    def forward_cl(self, x):
-        if self.pooling is not None:
+    def forward_cl(self, x, pooled_input=False, pool_output=False):
+        """pooled_input: x is already this level's pooled input (the previous level pooled in its last convolution's
+        epilogue); pool_output: return the NEXT level's pooled input instead of this level's output."""
+        if self.pooling is not None and not pooled_input:
             x = ops.cl_maxpool3d_2(x)
-        return self.basic_module.forward_cl(x)
+        return self.basic_module.forward_cl(x, pool=pool_output)
 
 
 class Decoder(nn.Module):
@@ -345,9 +381,15 @@ class Abstract3DUNet(nn.Module):
     def forward_cl(self, x, out_ncdhw=False):
         """x: fp32 channels-last [N,D,H,W,C]; returns channels-last (or NCDHW when out_ncdhw)."""
         feats = []
-        for encoder in self.encoders:
-            x = encoder.forward_cl(x)
-            feats.insert(0, x)
+        n_enc, n_dec = len(self.encoders), len(self.decoders)
+        pooled = False
+        for i, encoder in enumerate(self.encoders):
+            # a level whose output is no decoder's skip connection only feeds the next level's MaxPool3d(2): its last
+            # convolution pools in the epilogue and the full-resolution tensor is never written
+            only_pooled = FUSE_POOL and i + 1 < n_enc and i < n_enc - 1 - n_dec and self.encoders[i + 1].pooling is not None
+            x = encoder.forward_cl(x, pooled_input=pooled, pool_output=only_pooled)
+            pooled = only_pooled
+            feats.insert(0, None if only_pooled else x)
         feats = feats[1:]
         pairs = list(zip(self.decoders, feats))
         if not pairs:

@@ -702,11 +702,28 @@ def tc_conv_halo_weight_image(weight, c1, c2, wp=False):
     return img, scale
 
 
-def tc_conv3d_halo(split, img, bias, cout, act=ACT_NONE, slope=0.0, out_ncdhw=False, out_scale=1.0):
+def tc_conv_halo_wp_pool_supported(N, D, H, W, cout, c1, c2):
+    """Whether the W-pair variant can max-pool 2x2x2 in its epilogue for this 'same' 3x3x3 layer (D, H, W: input extents)."""
+    if tc_conv_halo_wp_mode() == "0":
+        return False
+    return bool(_lib.lib().rf_tc_conv3d_halo_wp_pool_supported(int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2)))
+
+
+def tc_conv3d_halo(split, img, bias, cout, act=ACT_NONE, slope=0.0, out_ncdhw=False, out_scale=1.0, pool=False):
     """split = cl_norm_split_halo(...) result.  Returns fp32 channels-last [N,Do,Ho,Wo,Cout] or NCDHW
-    (output extents = input + 2 pad - 2)."""
+    (output extents = input + 2 pad - 2).  pool (W-pair planes only): MaxPool3d(2) of the activated output is taken in
+    the epilogue, the result is [N,Do/2,Ho/2,Wo/2,Cout]."""
     hi, lo, (N, D, H, W, c1, c2, pad) = split
     Do, Ho, Wo = D + 2 * pad - 2, H + 2 * pad - 2, W + 2 * pad - 2
+    if pool:
+        assert getattr(split[2], "wp", False) and pad == 1 and not out_ncdhw, "the pooling epilogue belongs to the W-pair variant"
+        y = torch.empty((N, Do // 2, Ho // 2, Wo // 2, cout), device=hi.device, dtype=torch.float32)
+        with torch.cuda.device(hi.device), _timed("rf_tc_conv3d_halo_fwd", flops=2.0 * N * Do * Ho * Wo * 27 * (c1 + c2) * cout):
+            check(_lib.lib().rf_tc_conv3d_halo_wp_pool_fwd(hi.data_ptr(), lo.data_ptr(), img.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W,
+                                                           cout, c1, c2, act, float(slope), float(out_scale),
+                                                           torch.cuda.current_stream(hi.device).cuda_stream), "rf_tc_conv3d_halo_wp_pool_fwd")
+        _count()
+        return y
     shape = (N, cout, Do, Ho, Wo) if out_ncdhw else (N, Do, Ho, Wo, cout)
     y = torch.empty(shape, device=hi.device, dtype=torch.float32)
     with torch.cuda.device(hi.device), _timed("rf_tc_conv3d_halo_fwd", flops=2.0 * N * Do * Ho * Wo * 27 * (c1 + c2) * cout):

@@ -241,6 +241,28 @@ def test_shifted_window_conv_w_pairs(dev, N, S, C1, C2, Cout):
     assert float((yd - y0).abs().max()) <= 4e-5 * scale, "W-pair variant vs plain shifted-window kernel (all samples)"
 
 
+@pytest.mark.parametrize("N,C1,Cout", [(5, 8, 16), (150, 8, 16), (3, 16, 32), (2, 24, 16)])
+def test_w_pair_conv_pools_in_epilogue(dev, N, C1, Cout):
+    """model/unet.py:210-253: MaxPool3d(2) of a level's output taken in the epilogue of its last convolution
+    (rf_tc_conv3d_halo_wp_pool_fwd, 16^3 patches) is bit-identical to pooling the stored output."""
+    from retrieval_fuse_b200 import ops
+    g = torch.Generator().manual_seed(N + C1 + Cout)
+    x = (torch.randn(N, 16, 16, 16, C1, generator=g) * 1.3 - 0.1).to(dev)
+    w = (torch.randn(Cout, C1, 3, 3, 3, generator=g) / (27 * C1) ** 0.5).to(dev)
+    gamma, beta = (torch.rand(C1, generator=g) + 0.5).to(dev), (torch.randn(C1, generator=g) * 0.1).to(dev)
+    groups = 8 if C1 % 8 == 0 else 1
+    mu, a = ops.cl_gn_stats(x, gamma, groups, 1e-5)
+    assert ops.tc_conv_halo_wp_pool_supported(N, 16, 16, 16, Cout, C1, 0)
+    img, sw = ops.tc_conv_halo_weight_image(w, C1, 0, wp=True)
+    sa = ops.ACT_SCALE_GN
+    split = ops.cl_norm_split_halo(x, None, (mu, a, beta), scale=sa, wp=True)
+    y = ops.tc_conv3d_halo(split, img, None, Cout, act=ops.ACT_RELU, out_scale=1.0 / (sa * sw))
+    yp = ops.tc_conv3d_halo(split, img, None, Cout, act=ops.ACT_RELU, out_scale=1.0 / (sa * sw), pool=True)
+    ref = torch.nn.functional.max_pool3d(y.permute(0, 4, 1, 2, 3), 2).permute(0, 2, 3, 4, 1)
+    assert yp.shape == ref.shape
+    assert torch.equal(yp, ref), f"max |diff| {float((yp - ref).abs().max()):.2e}"
+
+
 # (N, S_in, Cin, Cout): 'valid' layers of the conv patch encoders (Patch32 8->16 @ 28^3, PCPatch48 16->32 @ 44^3, Patch08 shapes)
 WP_VALID_CASES = [(40, 28, 8, 16), (3, 44, 16, 32), (150, 8, 8, 16), (33, 6, 16, 32), (9, 12, 24, 40)]
 
