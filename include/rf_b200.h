@@ -181,8 +181,11 @@ int rf_tc_conv3d_halo_fwd(const void* hi, const void* lo, const void* weight_ima
                           int out_ncdhw, void* stream);
 
 /* Stride-2 'valid' 3x3x3 layers (the down-sampling Conv3d of the conv patch encoders, model/retrieval.py:4-28,187-275)
- * on the same kernel: planes of rf_cl_norm_split_halo (pad 0), weight image of rf_tc_conv_halo_weight_image; the item's
- * block is staged as its 8 parity sub-blocks (TMA boxes with element strides 2).  D, H, W: INPUT extents. */
+ * on the same kernel: parity planes of rf_cl_split_parity_planes ([chunk][parity][n][D/2][H/2][W/2] slots, sized by
+ * rf_halo_s2_act_bytes), weight image of rf_tc_conv_halo_weight_image; the item's block is staged as its 8 parity
+ * sub-blocks.  D, H, W: INPUT extents. */
+size_t rf_halo_s2_act_bytes(int N, int D, int H, int W, int C1);
+int rf_cl_split_parity_planes(const float* x, int C1, void* hi, void* lo, int N, int D, int H, int W, float scale, void* stream);
 int rf_tc_conv3d_halo_s2_supported(int N, int D, int H, int W, int Cout, int C1);
 int rf_tc_conv3d_halo_s2_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D,
                              int H, int W, int Cout, int C1, int act, float slope, float out_scale, int out_ncdhw, void* stream);

@@ -69,6 +69,8 @@ PROTOTYPES = {
     "rf_tc_conv3d_halo_debug_read": (c_int, [c_void_p]),
     "rf_tc_conv3d_halo_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
+    "rf_halo_s2_act_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "rf_cl_split_parity_planes": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "rf_tc_conv3d_halo_s2_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "rf_tc_conv3d_halo_s2_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_float, c_float, c_int, c_void_p]),

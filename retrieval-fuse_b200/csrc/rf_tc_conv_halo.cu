@@ -153,6 +153,50 @@ __global__ void __launch_bounds__(256) cl_norm_split_halo_kernel(const SplitArgs
     }
 }
 
+// Parity planes for the stride-2 layers: [chunk][parity (d,h,w)][n][ceil(D/2)][ceil(H/2)][ceil(W/2)] x 16 B, i.e. the 8
+// sub-lattices of every sample as dense volumes, so that the convolution stages an item's 8 parity sub-blocks with plain
+// TMA boxes (element-strided boxes over the compact planes fetched every sub-block's bounding box: the 32 -> 64 layer of
+// PCPatch48 at 42^3 ran slower than the gathering kernel).  Slots past an odd extent are written as zeros (a real row
+// multiplies them by the zero weights of a padded tap).  No GroupNorm: the conv patch encoders have none.
+struct SplitP8Args {
+    const float* x;
+    uint4 *hi, *lo;
+    int N, D, H, W, C, CC, D2, H2, W2;
+    float scale;
+    FastDiv fCC, fW2, fH2, fD2, fN;
+    long total;
+};
+
+__global__ void __launch_bounds__(256) cl_split_parity_planes_kernel(const SplitP8Args s) {
+    for (long j = blockIdx.x * (long)blockDim.x + threadIdx.x; j < s.total; j += (long)gridDim.x * blockDim.x) {
+        unsigned t = (unsigned)j;  // (parity, n, d2, h2, w2, chunk), chunk fastest: a voxel's channels are read as one run
+        const int cc = (int)fd_divmod(t, s.fCC);
+        const int w2 = (int)fd_divmod(t, s.fW2);
+        const int h2 = (int)fd_divmod(t, s.fH2);
+        const int d2 = (int)fd_divmod(t, s.fD2);
+        const int n = (int)fd_divmod(t, s.fN);
+        const int pq = (int)t;
+        const int d = 2 * d2 + (pq >> 2), h = 2 * h2 + ((pq >> 1) & 1), w = 2 * w2 + (pq & 1);
+        uint32_t hh[4] = {0, 0, 0, 0}, ll[4] = {0, 0, 0, 0};
+        if (d < s.D && h < s.H && w < s.W) {
+            const float* src = s.x + ((((long)n * s.D + d) * s.H + h) * s.W + w) * s.C + cc * 8;
+            float f[8];
+            if ((s.C & 3) == 0 && cc * 8 + 8 <= s.C) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                f[0] = v0.x; f[1] = v0.y; f[2] = v0.z; f[3] = v0.w; f[4] = v1.x; f[5] = v1.y; f[6] = v1.z; f[7] = v1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = cc * 8 + e < s.C ? __ldg(src + e) : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) split_f16x2(f[e] * s.scale, f[e + 1] * s.scale, hh[e >> 1], ll[e >> 1]);
+        }
+        const long i = ((((long)(cc * 8 + pq) * s.N + n) * s.D2 + d2) * s.H2 + h2) * s.W2 + w2;
+        s.hi[i] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+        s.lo[i] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+    }
+}
+
 // ------------------------------------------------------------------ layer modes and the weight image
 // A K = 16 step of the MMA reads two 16-byte chunks per GEMM row: the slot at the step's offset and the slot LBO
 // further.  What the two chunks are depends on the layer:
@@ -372,11 +416,11 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
                     const int plane = cc < a.CC ? cc * a.N + n0 : a.CC * a.N;
                     const uint32_t dst = sA + b * abuf_bytes + (uint32_t)pl * (uint32_t)a.P * 16u;
                     if (a.s2) {
-                        // stride 2: parity sub-block (qd,qh,qw) = every second voxel from (2 d0 + qd, 2 h0 + qh, 2 w0 + qw)
-                        // (tensor map with element strides 2; the box traverses 2 B - 1 positions per dimension)
+                        // stride 2: the 8 parity sub-blocks of the item, dense boxes of the parity planes
+                        // [chunk][parity][n][D/2][H/2][W/2] (rf_cl_split_parity_planes); sub-block coordinates = output coordinates
                         for (int pq = 0; pq < 8; ++pq)
-                            tma_load_5d(dst + (uint32_t)(pq * a.P_sub) * 16u, hl ? &tm_lo : &tm_hi, 0, 2 * w0 + (pq & 1), 2 * h0 + ((pq >> 1) & 1),
-                                        2 * d0 + (pq >> 2), plane, bar_afull + 8 * b);
+                            tma_load_5d(dst + (uint32_t)(pq * a.P_sub) * 16u, hl ? &tm_lo : &tm_hi, 0, w0, h0, d0,
+                                        cc < a.CC ? (cc * 8 + pq) * a.N + n0 : 8 * a.CC * a.N, bar_afull + 8 * b);
                     } else if (a.wp) {
                         // W pairs: sub-block A = the padded positions u = 2 r (voxels of parity 'pad', from half-line index
                         // w0 - pad), sub-block B = u = 2 r + 1 (the other parity, from w0); planes [chunk][parity][n]
@@ -748,7 +792,6 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
         if (L.stride == 2) {  // 8 parity sub-blocks, the over-read slack only behind the last one
             P_sub = (S_st + 7) / 8 * 8;
             P += 7 * P_sub;
-            if (2L * Wp - 1 > 256 || 2L * Hs - 1 > 256 || 2L * (stacked ? Dp : Dt + L.hd) - 1 > 256) return;  // TMA box limits
         }
         if (L.wp) {  // two sub-blocks (even / odd padded positions), each with its own zeroed over-read slack: with a
             P_sub = P;  // shared halo the far neighbours of a sample's last voxels are read from that slack
@@ -962,8 +1005,9 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
     a.n_items = g.n_items; a.n_sets = g.n_sets; a.n_fused = g.n_fused;
     // tensor maps of the compact planes [CC * N][Din][Hin][Win] x 16 B, seen as 8-byte words so that a whole line of
     // the item's block is the innermost box extent (<= 256 elements)
-    const int Din = Din_in ? Din_in : D + L.hd - 2 * pad, Hin = Hin_in ? Hin_in : H + L.hd - 2 * pad;
-    const int Win = Win_in ? Win_in : (L.mode == 2 ? W : L.wp ? W + 1 - pad : W + L.hw - 2 * pad);  // (W pairs: half-lines)
+    // (stride 2: the parity planes hold ceil(extent / 2) slots per dimension)
+    const int Din = Din_in ? (Din_in + 1) / 2 : D + L.hd - 2 * pad, Hin = Hin_in ? (Hin_in + 1) / 2 : H + L.hd - 2 * pad;
+    const int Win = Win_in ? (Win_in + 1) / 2 : (L.mode == 2 ? W : L.wp ? W + 1 - pad : W + L.hw - 2 * pad);  // (W pairs: half-lines)
     const int bW = g.Wt + g.hw, bD = g.stacked ? D + g.hd : g.Dt + L.hd;  // the item's box (its H extent is g.Hs)
     RF_CHECK_ARG(bW <= 256 && g.Hs <= 256 && bD <= 256 && g.G <= 256, "rf_tc_conv3d_halo_fwd: item box exceeds the TMA limits");
     a.tm5 = (a.s2 || 2 * bW > 256) ? 1 : 0;  // a line longer than 256 words, or strided boxes: slots as a dimension of their own
@@ -972,9 +1016,9 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
     RF_CHECK_ARG(encode != nullptr, "rf_tc_conv3d_halo_fwd: the driver does not export cuTensorMapEncodeTiled");
     for (int k = 0; k < 2; ++k) {
         const cuuint32_t bG = (cuuint32_t)(g.stacked ? g.G : 1);
-        const cuuint64_t planes = (cuuint64_t)L.CC * (cuuint64_t)N * (L.wp ? 2u : 1u);
-        const cuuint32_t es = a.s2 ? 2u : 1u;  // stride 2: every second voxel, the box spans 2 B - 1 positions
-        const cuuint32_t estr[5] = {1, es, es, es, 1};
+        const cuuint64_t planes = (cuuint64_t)L.CC * (cuuint64_t)N * (L.wp ? 2u : a.s2 ? 8u : 1u);
+        const cuuint32_t es = 1u;
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult cr;
         if (a.tm5) {
             const cuuint64_t gdim[5] = {2, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)Din, planes};
@@ -1116,14 +1160,35 @@ extern "C" int rf_tc_conv3d_halo_geometry(int N, int D, int H, int W, int Cout, 
     return 1;
 }
 
+/* Operand planes of the stride-2 layers: the 8 parity sub-lattices of every sample as dense volumes
+ * [chunk][parity][n][ceil(D/2)][ceil(H/2)][ceil(W/2)] x 16 B (fp16 hi / lo of scale * x; slots past an odd extent are zero). */
+extern "C" size_t rf_halo_s2_act_bytes(int N, int D, int H, int W, int C1) {
+    if (N < 1 || D < 1 || H < 1 || W < 1 || C1 < 1) return 0;
+    return (size_t)((C1 + 7) / 8) * 8 * N * (size_t)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2) * 16;
+}
+
+extern "C" int rf_cl_split_parity_planes(const float* x, int C1, void* hi, void* lo, int N, int D, int H, int W, float scale, void* stream) {
+    RF_CHECK_ARG(x && hi && lo && N > 0 && D > 0 && H > 0 && W > 0 && C1 > 0, "rf_cl_split_parity_planes: bad arguments");
+    RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)x & 15) == 0, "rf_cl_split_parity_planes: pointers must be 16-byte aligned");
+    SplitP8Args s;
+    s.x = x; s.hi = (uint4*)hi; s.lo = (uint4*)lo; s.N = N; s.D = D; s.H = H; s.W = W; s.C = C1; s.CC = (C1 + 7) / 8;
+    s.D2 = (D + 1) / 2; s.H2 = (H + 1) / 2; s.W2 = (W + 1) / 2; s.scale = scale;
+    s.total = (long)s.CC * 8 * N * s.D2 * s.H2 * s.W2;
+    RF_CHECK_ARG(s.total < (1L << 32) - 256, "rf_cl_split_parity_planes: more than 2^32 slots");
+    s.fCC = make_fastdiv(s.CC); s.fW2 = make_fastdiv(s.W2); s.fH2 = make_fastdiv(s.H2); s.fD2 = make_fastdiv(s.D2); s.fN = make_fastdiv(N);
+    cl_split_parity_planes_kernel<<<rf_grid_1d(s.total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(s);
+    RF_LAUNCH_OK("cl_split_parity_planes_kernel");
+    return 0;
+}
+
 /* Stride-2 'valid' 3x3x3 convolution (the down-sampling layers of the conv patch encoders, model/retrieval.py:4-28,
- * 187-275) on the same kernel: the planes are those of rf_cl_norm_split_halo (pad 0); the producer stages the item's 8
- * parity sub-blocks with strided TMA boxes and tap (kd,kh,kw) reads sub-block (kd&1, kh&1, kw&1) at offset
+ * 187-275) on the same kernel: the planes are the parity planes of rf_cl_split_parity_planes; the producer stages the item's 8
+ * parity sub-blocks (plain TMA boxes) and tap (kd,kh,kw) reads sub-block (kd&1, kh&1, kw&1) at offset
  * (kd>>1, kh>>1, kw>>1).  D, H, W: INPUT extents; outputs (D - 3) / 2 + 1 etc.  Weight image: rf_tc_conv_halo_weight_image. */
 extern "C" int rf_tc_conv3d_halo_s2_supported(int N, int D, int H, int W, int Cout, int C1) {
     Layer L;
     if (!make_layer(Cout, C1, 0, 3, false, L, 2) || N < 1 || D < 3 || H < 3 || W < 3) return 0;
-    if ((long)N * D * H * W * L.CC >= (1L << 32) - 256) return 0;
+    if ((long)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2) * L.CC * 8 >= (1L << 32) - 256) return 0;
     Geo g;
     return choose_geometry(N, (D - 3) / 2 + 1, (H - 3) / 2 + 1, (W - 3) / 2 + 1, L, 0, g) && g.n_tiles <= 32 ? 1 : 0;
 }

@@ -426,8 +426,24 @@ def tc_conv_halo_s2_supported(N, D, H, W, cout, c1):
     return bool(_lib.lib().rf_tc_conv3d_halo_s2_supported(int(N), int(D), int(H), int(W), int(cout), int(c1)))
 
 
+def cl_split_parity_planes(x, scale=1.0):
+    """fp32 channels-last x [N,D,H,W,C] -> (hi, lo) parity planes [chunk][parity][N][D/2][H/2][W/2][8] of scale * x (the 8
+    sub-lattices of every sample as dense volumes): the operand layout of tc_conv3d_halo_s2."""
+    x = _dev(x, name="x")
+    N, D, H, W, C = x.shape
+    L = _lib.lib()
+    nbytes = L.rf_halo_s2_act_bytes(N, D, H, W, C)
+    hi = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    lo = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device), _timed("rf_cl_split_parity_planes", nbytes=8.0 * x.numel()):
+        check(L.rf_cl_split_parity_planes(x.data_ptr(), C, hi.data_ptr(), lo.data_ptr(), N, D, H, W, float(scale), _stream(x)),
+              "rf_cl_split_parity_planes")
+    _count()
+    return hi, lo, (N, D, H, W, C, 0, 0)
+
+
 def tc_conv3d_halo_s2(split, img, bias, cout, act=ACT_NONE, slope=0.0, out_scale=1.0):
-    """split = cl_norm_split_halo(x, pad=0) result.  Conv3d(k3, stride 2, no padding) -> fp32 channels-last [N,Do,Ho,Wo,Cout]."""
+    """split = cl_split_parity_planes(x) result.  Conv3d(k3, stride 2, no padding) -> fp32 channels-last [N,Do,Ho,Wo,Cout]."""
     hi, lo, (N, D, H, W, c1, c2, pad) = split
     assert c2 == 0 and pad == 0
     Do, Ho, Wo = (D - 3) // 2 + 1, (H - 3) // 2 + 1, (W - 3) // 2 + 1

@@ -392,7 +392,7 @@ S2_CASES = [(40, 28, 16, 32), (70, 11, 64, 64), (3, 42, 32, 64), (9, 20, 64, 64)
 @pytest.mark.parametrize("N,S,Cin,Cout", S2_CASES)
 def test_stride2_conv_on_shifted_window_kernel(dev, N, S, Cin, Cout):
     """Conv3d(Cin, Cout, 3, stride=2) + LeakyReLU(0.2) (model/retrieval.py:4-28) through rf_tc_conv3d_halo_s2_fwd
-    (parity sub-blocks staged by strided TMA boxes) against torch's CPU conv3d in fp32 and fp64."""
+    (parity planes, the item staged as its 8 parity sub-blocks) against torch's CPU conv3d in fp32 and fp64."""
     from retrieval_fuse_b200 import ops
     g = torch.Generator().manual_seed(5 * N + S + Cin + Cout)
     x = torch.randn(N, Cin, S, S, S, generator=g) * 1.2 + 0.1
@@ -404,7 +404,7 @@ def test_stride2_conv_on_shifted_window_kernel(dev, N, S, Cin, Cout):
     assert ops.tc_conv_halo_s2_supported(N, S, S, S, Cout, Cin)
     xd = x.permute(0, 2, 3, 4, 1).contiguous().to(dev)
     img, sw = ops.tc_conv_halo_weight_image(w.to(dev), Cin, 0)
-    y = ops.tc_conv3d_halo_s2(ops.cl_norm_split_halo(xd, None, None, scale=1.0, pad=0), img, b.to(dev), Cout, act=ops.ACT_LEAKY, slope=0.2,
+    y = ops.tc_conv3d_halo_s2(ops.cl_split_parity_planes(xd), img, b.to(dev), Cout, act=ops.ACT_LEAKY, slope=0.2,
                               out_scale=1.0 / sw)
     y = y.permute(0, 4, 1, 2, 3).cpu()[sel]
     assert y.shape == ref32.shape
