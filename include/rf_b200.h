@@ -205,6 +205,16 @@ int rf_tc_conv3d_halo_wp_supported(int N, int D, int H, int W, int Cout, int C1,
 int rf_tc_conv3d_halo_wp_pool_supported(int N, int D, int H, int W, int Cout, int C1, int C2);
 int rf_tc_conv3d_halo_wp_pool_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D,
                                   int H, int W, int Cout, int C1, int C2, int act, float slope, float out_scale, void* stream);
+/* First convolution of a DoubleConv (model/unet.py:103-144) whose epilogue applies the SECOND SingleConv's GroupNorm
+ * (model/unet.py:79-100) and writes that layer's operand planes straight from the accumulators: per-sample statistics of
+ * the activated output, normalisation, x scale2, fp16 hi / lo split.  out_hi / out_lo: rf_halo_act_bytes(N, Do, Ho, Wo,
+ * Cout, 0, 1) bytes each, in rf_cl_norm_split_halo's layout (out_wp = 0) or rf_cl_norm_split_halo_wp's (out_wp = 1).
+ * D, H, W: INPUT extents.  Needs Cout <= 64 and an item shape with one whole sample per item (_supported). */
+int rf_tc_conv3d_halo_gn_supported(int N, int D, int H, int W, int pad, int Cout, int C1, int C2, int groups2);
+int rf_tc_conv3d_halo_gn_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, int N, int D, int H, int W,
+                             int pad, int Cout, int C1, int C2, int act, float slope, float out_scale, const float* gn2_w,
+                             const float* gn2_b, int groups2, float eps2, float scale2, void* out_hi, void* out_lo, int out_wp,
+                             void* stream);
 int rf_tc_conv3d_halo_wp_geometry(int N, int D, int H, int W, int Cout, int C1, int C2, int pad, int* out16, double* scores2);
 int rf_tc_conv3d_halo_wp_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D,
                              int H, int W, int pad, int Cout, int C1, int C2, int act, float slope, float out_scale, void* stream);

@@ -82,6 +82,10 @@ PROTOTYPES = {
     "rf_tc_conv3d_halo_wp_pool_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "rf_tc_conv3d_halo_wp_pool_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                               c_int, c_int, c_float, c_float, c_void_p]),
+    "rf_tc_conv3d_halo_gn_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "rf_tc_conv3d_halo_gn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_float, c_float, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_int,
+                                         c_void_p]),
     "rf_tc_conv3d_halo_wp_geometry": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rf_tc_conv3d_halo_wp_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_int, c_int, c_float, c_float, c_void_p]),

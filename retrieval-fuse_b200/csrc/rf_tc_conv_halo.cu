@@ -222,6 +222,7 @@ struct Layer {
     int mode, KS, stride;  // stride 2: 'valid' 3^3 only (the patch encoders' down-sampling layers)
     int wp;                // mode 3: W pairs (two output voxels per GEMM row)
     int pool;              // W pairs + 'planes' items: the epilogue writes MaxPool3d(2) of the activated output
+    int gn_out;            // whole-sample items: the epilogue applies the NEXT layer's GroupNorm and writes its operand planes
     int C1, C2, Cp1, Cp2, CC, CCe, Cout, Npad;
     int ck, n_stages, kpg, n_groups;
     int hd, hw;  // block extent beyond the output extent: D / H (KS - 1) and W (KS - 1; 0 in mode 2)
@@ -294,6 +295,12 @@ struct HaloArgs {
     int s2, P_sub;                // stride 2: 8 parity sub-blocks per plane, P_sub slots apart
     int nb_shift;                 // log2 of the weight ring's slots
     int pool;                     // epilogue max-pools 2x2x2 (W pairs, planes mode): y is [N, D/2, H/2, W/2, Cb]
+    // gn_out: the epilogue computes the GroupNorm statistics of the sample's activated output, normalises, splits and
+    // writes the operand planes of the next convolution (o_hi / o_lo; o_wp: its W-pair layout) instead of y
+    int gn_out, o_wp, o_cpg;
+    float o_eps, o_scale;
+    const float *o_gamma, *o_beta;
+    uint4 *o_hi, *o_lo;
     int wp, Cb;                   // W pairs: 2 sub-blocks per plane (even / odd padded positions); channels of the bias vector
     long V;                       // slots per haloed sample volume
     int Dt, Ht, Wt, Hs, G, stacked;  // item = G stacked whole samples, or a Dt x Ht x Wt slab of one sample
@@ -319,7 +326,9 @@ struct HaloArgs {
 // haloed block of one item (2 (W+2), Hs, Dt+2, G); coordinates that fall outside are zero-filled by the TMA unit.
 // RES = CTAs per SM the register budget allows: 2 (64 registers; small items whose shared memory lets two CTAs share
 // an SM) or 1 (128 registers: the epilogue keeps the next accumulator block in flight).
-template <int RES, int PIPE>
+// EPI = 1: the instantiation that carries the special epilogues (pooling, next layer's GroupNorm), kept out of the
+// standard kernels' register budget.
+template <int RES, int PIPE, int EPI = 0>
 __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tm_hi,
                                                                        const __grid_constant__ CUtensorMap tm_lo) {
     extern __shared__ uint8_t smem_raw[];
@@ -581,7 +590,127 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_conv3d_halo_kernel(const Hal
             mbar_wait_warp_sleepy(bar_dfull + 8 * set, use & 1u);
             tc_fence_after();
             if (dbg) g_halo_dbg[it * 8 + 5] = clock64();
-            if constexpr (RES == 1) {
+            if constexpr (EPI == 1) {
+              if (a.gn_out) {
+                // ---- GroupNorm of the NEXT layer in the epilogue (item = one whole sample): phase A reduces the per-channel
+                // sums of the activated outputs (warp: transposing shuffle reduction in fp32 over its 32 rows, then fp64
+                // per lane; CTA: shared memory), phase B re-reads the accumulators from TMEM, normalises, splits into fp16
+                // hi / lo and writes the slots of the next convolution's operand planes.  The fp32 activations, the
+                // statistics pass and the split pass over them never touch HBM.
+                double* red = reinterpret_cast<double*>(smem_al + (((tmem_slot + 16 - base) + (uint32_t)a.n_tiles * 512u + 15u) & ~15u));
+                float* stt = reinterpret_cast<float*>(red + 8 * 2 * 64);  // [3][64]: mean, rstd * gamma, beta per channel
+                const int nblk = a.Npad >> 4, ew = warp - 8, etid = threadIdx.x - 256;
+                // (tile, 16-column block) -> activated outputs of the thread's row (zeros on rows that are no output voxel)
+                auto load_act = [&](int t, int blk, bool valid, float* w16) {
+                    const bool tf = (uint32_t)t < nf;
+                    const uint32_t ta = tm_set + ((uint32_t)(q * 32) << 16) + ((uint32_t)t + (tf ? (uint32_t)t : nf)) * npad + (uint32_t)(blk << 4);
+                    float v[16], u[16];
+                    tc_ld16_issue(ta, v);
+                    if (tf) tc_ld16_issue(ta + npad, u);
+                    tc_ld_wait();
+                    tc_ld_fence16(v);
+                    if (tf) {
+                        tc_ld_fence16(u);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] += u[e];
+                    }
+                    float z[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int c = (blk << 4) + e;
+                        z[e] = fmaf(v[e], a.out_scale, (a.bias && c < a.Cout) ? __ldg(a.bias + c) : 0.f);
+                    }
+                    rf_act_vec(z, a.act, a.slope);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) w16[e] = valid ? z[e] : 0.f;
+                };
+                // 16 values per lane -> lanes 2 i, 2 i + 1 hold the warp total of value i
+                auto reduce16 = [&](float* v) {
+#pragma unroll
+                    for (int hf = 8, bit = 16; hf >= 1; hf >>= 1, bit >>= 1) {
+                        const bool up = (lane & bit) != 0;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            if (k < hf) {
+                                const float send = up ? v[k] : v[k + hf], keep = up ? v[k + hf] : v[k];
+                                v[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                            }
+                        }
+                    }
+                    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+                };
+                // ---- phase A, block-major: a thread first adds up its rows of all its tiles, then ONE shuffle reduction per
+                // 16 channels (fp32 over <= 32 x tiles rows, fp64 from there on).  (Keeping the loads of two tiles in flight
+                // needs more registers than the kernel has: the spills made the epilogue 2.3x slower.)
+                for (int blk = 0; blk < nblk; ++blk) {
+                    float s16[16], q16[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { s16[e] = 0.f; q16[e] = 0.f; }
+                    for (int t = half; t < a.n_tiles; t += 2) {
+                        const int rt = row_tab[t * TM + q * 32 + lane];
+                        float w16[16];
+                        load_act(t, blk, rt >= 0 && (rt >> 26) < gact, w16);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) { s16[e] += w16[e]; q16[e] = fmaf(w16[e], w16[e], q16[e]); }
+                    }
+                    const double ts = (double)reduce16(s16), tq = (double)reduce16(q16);
+                    if (!(lane & 1)) { red[(ew * 2 + 0) * 64 + blk * 16 + (lane >> 1)] = ts; red[(ew * 2 + 1) * 64 + blk * 16 + (lane >> 1)] = tq; }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (etid < a.Cout) {  // channel etid: sums of its group over the 8 warps
+                    const int g0 = etid / a.o_cpg * a.o_cpg;
+                    double s1 = 0.0, s2 = 0.0;
+                    for (int c = g0; c < g0 + a.o_cpg; ++c)
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { s1 += red[(k * 2 + 0) * 64 + c]; s2 += red[(k * 2 + 1) * 64 + c]; }
+                    const double cnt = (double)a.D * a.H * a.W * a.o_cpg;
+                    const double mean = s1 / cnt;
+                    double var = s2 / cnt - mean * mean;
+                    if (var < 0.0) var = 0.0;
+                    stt[etid] = (float)mean;
+                    stt[64 + etid] = (float)(1.0 / sqrt(var + (double)a.o_eps)) * __ldg(a.o_gamma + etid);
+                    stt[128 + etid] = __ldg(a.o_beta + etid);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                // ---- phase B: accumulators again -> normalise -> split -> the next convolution's operand planes
+                const long Vs = (long)a.D * a.H * a.W;
+                for (int t = half; t < a.n_tiles; t += 2) {
+                    const int rt = row_tab[t * TM + q * 32 + lane];
+                    const bool valid = rt >= 0 && (rt >> 26) < gact;
+                    const int vox = rt & 0x3FFFFFF;  // (d * H + h) * W + w within the sample
+                    long slot = (long)n0 * Vs + vox, cstride = (long)a.N * Vs;
+                    if (a.o_wp) {  // W-pair planes [chunk][w parity][n][d][h][w / 2]
+                        const int line = vox / a.W, wq = vox - line * a.W;
+                        slot = ((long)(wq & 1) * a.N + n0) * (Vs >> 1) + (long)line * (a.W >> 1) + (wq >> 1);
+                        cstride = 2 * (long)a.N * (Vs >> 1);
+                    }
+                    for (int blk = 0; blk < nblk; ++blk) {
+                        float w16[16];
+                        load_act(t, blk, valid, w16);
+                        if (!valid) continue;
+#pragma unroll
+                        for (int ch = 0; ch < 2; ++ch) {
+                            const int c0 = (blk << 4) + ch * 8;
+                            if (c0 >= a.Cout) break;
+                            uint32_t hh[4], ll[4];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                const int c = c0 + e;
+                                const float f0 = c < a.Cout ? fmaf(w16[ch * 8 + e] - stt[c], stt[64 + c], stt[128 + c]) * a.o_scale : 0.f;
+                                const float f1 = c + 1 < a.Cout ? fmaf(w16[ch * 8 + e + 1] - stt[c + 1], stt[64 + c + 1], stt[128 + c + 1]) * a.o_scale : 0.f;
+                                split_f16x2(f0, f1, hh[e >> 1], ll[e >> 1]);
+                            }
+                            const long i = slot + (long)(c0 >> 3) * cstride;
+                            a.o_hi[i] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                            a.o_lo[i] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_dempty + 8 * set);
+                continue;
+              }
               if (a.pool) {
                 // MaxPool3d(2) of the activated output in the epilogue (W pairs, planes mode: tile t = d plane t of the slab,
                 // row = (h = q * 4 + lane / 8, pair lane & 7)): the pooling window is the thread's two voxels (w), the
@@ -772,6 +901,7 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
         const long lines_needed = stacked ? (long)(G - 1) * Dp * Hp + (long)(D - 1) * Hp + H : (long)(Dt - 1) * Hs + Ht;
         long n_tiles, max_slot;
         const int n_wblk = lines ? (W + 7) / 8 : 1;
+        if (L.gn_out && !(stacked && G == 1)) return;  // GroupNorm epilogue: one whole sample per item
         if (L.pool && (lines != 2 || (Dt & 1) || n_wblk != 1)) return;  // pooling epilogue: d planes in tile pairs, one 8-pair block per line
         if (lines == 2) {  // planes: one tile per (d plane, 8-voxel block) of a slab with exactly 16 lines per plane
             if (stacked || Ht != 16) return;
@@ -799,7 +929,8 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
         }
         const long n_sub = L.stride == 2 ? 8 : L.wp ? 2 : 1;
         if (n_tiles * Npad > 512 || n_tiles > 32 || P * 16 >= (1L << 18)) return;  // (the fused scheme needs twice the columns: checked below)
-        const long avail = avail_all - n_tiles * 512;  // the row table: n_tiles x 128 ints
+        const long gn_smem = L.gn_out ? 16 + 8 * 2 * 64 * 8 + 3 * 64 * 4 : 0;  // per-warp channel sums (fp64) + the sample's mean / rstd table
+        const long avail = avail_all - n_tiles * 512 - gn_smem;  // the row table: n_tiles x 128 ints
         // two staging buffers whenever they fit: the next stage (or the next item's block) loads during the MMAs
         const long smemA1 = (long)planes * P * 16;
         const int nbuf = 2 * smemA1 <= avail ? 2 : 1;
@@ -840,9 +971,9 @@ bool choose_geometry(int N, int D, int H, int W, const Layer& L, int pad, Geo& b
                 uint32_t cols_needed = 32;
                 while ((long)cols_needed < cols * n_sets) cols_needed <<= 1;
                 const int tile_cols = (int)(cols / n_tiles);  // average, for the epilogue estimate
-                const long smem_total = 1024 + smemA + (long)NB * bslot + 256 + n_tiles * 512;
+                const long smem_total = 1024 + smemA + (long)NB * bslot + 256 + n_tiles * 512 + gn_smem;
                 static const int force_res = [] { const char* e = getenv("RF_HALO_RES"); return e ? atoi(e) : 0; }();  // tuning aid
-                const bool two_resident = force_res != 1 && smem_total <= 113 * 1024 && cols_needed <= 256 && !L.pool;
+                const bool two_resident = force_res != 1 && smem_total <= 113 * 1024 && cols_needed <= 256 && !L.pool && !L.gn_out;
                 const double issue = 150.0 / (n_iss * (two_resident ? 2 : 1));
                 const double step_fused = fmax(pipe_cycles(2 * Npad), issue) + fmax(pipe_cycles(Npad), issue);
                 const double step_two = 3.0 * fmax(pipe_cycles(Npad), issue);
@@ -904,7 +1035,7 @@ bool make_layer(int Cout, int C1, int C2, int KS, bool wrun, Layer& L, int strid
     if (Cout < 1 || Cout > 256 || C1 < 0 || C2 < 0 || C1 + C2 < 1 || (stride != 1 && stride != 2)) return false;
     if (stride == 2 && (wrun || C2 != 0)) return false;
     if (pool && (!wp || (Cout & 15))) return false;
-    L.KS = KS; L.C1 = C1; L.C2 = C2; L.Cout = Cout; L.stride = stride; L.wp = wp ? 1 : 0; L.pool = pool ? 1 : 0;
+    L.KS = KS; L.C1 = C1; L.C2 = C2; L.Cout = Cout; L.stride = stride; L.wp = wp ? 1 : 0; L.pool = pool ? 1 : 0; L.gn_out = 0;
     L.Cp1 = round_up(C1, 8); L.Cp2 = round_up(C2, 8);
     L.CC = (L.Cp1 + L.Cp2) / 8;
     L.Npad = round_up(Cout, 16);
@@ -945,14 +1076,22 @@ int conv_init() {
     RF_SMEM_OPT_IN((tc_conv3d_halo_kernel<1, 1>), SMEM_LIMIT);
     RF_SMEM_OPT_IN((tc_conv3d_halo_kernel<1, 0>), SMEM_LIMIT);
     RF_SMEM_OPT_IN((tc_conv3d_halo_kernel<2, 0>), SMEM_LIMIT);
+    RF_SMEM_OPT_IN((tc_conv3d_halo_kernel<1, 0, 1>), SMEM_LIMIT);
     return 0;
 }
 
 // D, H, W: OUTPUT extents.  The planes hold Din x Hin x Win slots per (chunk, sample): Din = D + hd - 2 pad, likewise H;
 // Win = W + hw - 2 pad (mode 2: Win = W, the W-runs already cover the taps and the padding along W).
+struct GnOut {  // the next layer's GroupNorm + operand planes (Layer::gn_out)
+    const float *gamma, *beta;
+    int groups, wp;
+    float eps, scale;
+    void *hi, *lo;
+};
+
 int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weight_image, const float* bias, float* y, int N, int D, int H,
                 int W, int pad, int act, float slope, float out_scale, int out_ncdhw, void* stream, int Din_in = 0, int Hin_in = 0,
-                int Win_in = 0) {
+                int Win_in = 0, const GnOut* gn = nullptr) {
     Geo g;
     RF_CHECK_ARG(choose_geometry(N, D, H, W, L, pad, g), "rf_tc_conv3d_halo_fwd: no item shape fits (N=%d out %dx%dx%d Cout=%d C=%d+%d KS=%d)",
                  N, D, H, W, L.Cout, L.C1, L.C2, L.KS);
@@ -961,7 +1100,8 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
     a.N = N; a.D = D; a.H = H; a.W = W; a.Hp = H + g.hd; a.Wp = g.Wt + g.hw;
     a.pad = pad; a.CC = L.CC; a.w0 = L.mode == 2 ? 0 : -pad;
     a.s2 = L.stride == 2 ? 1 : 0; a.P_sub = g.P_sub;
-    a.wp = L.wp; a.Cb = L.Cout; a.pool = L.pool; a.nb_shift = g.nb == 8 ? 3 : 2;
+    a.wp = L.wp; a.Cb = L.Cout; a.pool = L.pool; a.gn_out = 0;
+    if (gn) { a.gn_out = 1; a.o_wp = gn->wp; a.o_cpg = L.Cout / gn->groups; a.o_eps = gn->eps; a.o_scale = gn->scale; a.o_gamma = gn->gamma; a.o_beta = gn->beta; a.o_hi = (uint4*)gn->hi; a.o_lo = (uint4*)gn->lo; } a.nb_shift = g.nb == 8 ? 3 : 2;
     a.V = (long)(D + g.hd) * (H + g.hd) * (W + g.hw);
     a.Dt = g.Dt; a.Ht = g.Ht; a.Wt = g.Wt; a.Hs = g.Hs; a.G = g.G; a.stacked = g.stacked;
     a.n_dt = D / g.Dt; a.n_ht = H / g.Ht; a.n_wt = W / g.Wt; a.Ls = (D + g.hd) * (H + g.hd);
@@ -1042,7 +1182,8 @@ int launch_conv(const Layer& L, const void* hi, const void* lo, const void* weig
     const int slots = sms * (g.two_resident ? 2 : 1);
     const unsigned grid = (unsigned)(g.n_items < slots ? g.n_items : slots);
     static const int pipe = [] { const char* e = getenv("RF_HALO_PIPE"); return e ? atoi(e) : 1; }();  // tuning aid
-    if (g.two_resident) tc_conv3d_halo_kernel<2, 0><<<grid, NTHREADS, g.smem, (cudaStream_t)stream>>>(a, tm[0], tm[1]);
+    if (a.pool || a.gn_out) tc_conv3d_halo_kernel<1, 0, 1><<<grid, NTHREADS, g.smem, (cudaStream_t)stream>>>(a, tm[0], tm[1]);
+    else if (g.two_resident) tc_conv3d_halo_kernel<2, 0><<<grid, NTHREADS, g.smem, (cudaStream_t)stream>>>(a, tm[0], tm[1]);
     else if (pipe) tc_conv3d_halo_kernel<1, 1><<<grid, NTHREADS, g.smem, (cudaStream_t)stream>>>(a, tm[0], tm[1]);
     else tc_conv3d_halo_kernel<1, 0><<<grid, NTHREADS, g.smem, (cudaStream_t)stream>>>(a, tm[0], tm[1]);
     RF_LAUNCH_OK("tc_conv3d_halo_kernel");
@@ -1258,6 +1399,45 @@ extern "C" int rf_tc_conv3d_halo_wp_pool_fwd(const void* hi, const void* lo, con
     RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)weight_image & 15) == 0 && ((uintptr_t)y & 15) == 0,
                  "rf_tc_conv3d_halo_wp_pool_fwd: pointers must be 16-byte aligned");
     return launch_conv(L, hi, lo, weight_image, bias, y, N, D, H, W / 2, 1, act, slope, out_scale, 0, stream);
+}
+
+/* Convolution whose epilogue applies the NEXT SingleConv's GroupNorm (model/unet.py:79-144: the first convolution of a
+ * DoubleConv, whose output only feeds the second) and writes that layer's operand planes: statistics of the sample's
+ * activated output, normalisation, x scale2, fp16 hi / lo split, all from the accumulators in TMEM.  out_hi / out_lo:
+ * rf_halo_act_bytes(N, Do, Ho, Wo, Cout, 0, 1) bytes each, in rf_cl_norm_split_halo's layout (out_wp = 0) or
+ * rf_cl_norm_split_halo_wp's (out_wp = 1).  Needs an item shape with one whole sample per item (_supported). */
+extern "C" int rf_tc_conv3d_halo_gn_supported(int N, int D, int H, int W, int pad, int Cout, int C1, int C2, int groups2) {
+    Layer L;
+    if (!make_layer(Cout, C1, C2, 3, false, L) || N < 1 || pad < 0 || pad > 1 || groups2 < 1 || Cout % groups2 || Cout > 64) return 0;
+    const int Do = D + 2 * pad - 2, Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+    if (Do < 1 || Ho < 1 || Wo < 1) return 0;
+    if ((long)N * D * H * W * L.CC >= (1L << 32) - 256) return 0;
+    Geo g, g0;
+    const bool free_ok = choose_geometry(N, Do, Ho, Wo, L, pad, g0) && g0.n_tiles <= 32;
+    L.gn_out = 1;
+    if (!choose_geometry(N, Do, Ho, Wo, L, pad, g) || g.n_tiles > 32) return 0;
+    // 2: worth it - the one-sample item is (about) what the chooser would take anyway AND the layer has enough MMA work per
+    // item (>= 8 channel chunks) to carry an epilogue that visits every accumulator block twice (measured, 16 384 samples
+    // of 8^3: 96 -> 56 9.12 ms against 8.25 + 0.52 + 0.70 as separate launches; 16 -> 16 1.08 against 0.72 + 0.18 + 0.18);
+    // 1: it runs
+    return (!free_ok || g.score >= 0.9 * g0.score) && L.CC >= 8 ? 2 : 1;
+}
+
+extern "C" int rf_tc_conv3d_halo_gn_fwd(const void* hi, const void* lo, const void* weight_image, const float* bias, int N, int D, int H,
+                                        int W, int pad, int Cout, int C1, int C2, int act, float slope, float out_scale,
+                                        const float* gn2_w, const float* gn2_b, int groups2, float eps2, float scale2, void* out_hi,
+                                        void* out_lo, int out_wp, void* stream) {
+    RF_CHECK_ARG(hi && lo && weight_image && gn2_w && gn2_b && out_hi && out_lo, "rf_tc_conv3d_halo_gn_fwd: null pointer");
+    Layer L;
+    RF_CHECK_ARG(make_layer(Cout, C1, C2, 3, false, L) && N > 0 && (pad == 0 || pad == 1) && groups2 >= 1 && Cout % groups2 == 0 && Cout <= 64,
+                 "rf_tc_conv3d_halo_gn_fwd: unsupported shape Cout=%d C1=%d C2=%d pad=%d groups=%d", Cout, C1, C2, pad, groups2);
+    L.gn_out = 1;
+    RF_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)weight_image & 15) == 0 && ((uintptr_t)out_hi & 15) == 0 &&
+                 ((uintptr_t)out_lo & 15) == 0, "rf_tc_conv3d_halo_gn_fwd: pointers must be 16-byte aligned");
+    D += 2 * pad - 2; H += 2 * pad - 2; W += 2 * pad - 2;
+    RF_CHECK_ARG(D > 0 && H > 0 && W > 0 && (!out_wp || (W & 1) == 0), "rf_tc_conv3d_halo_gn_fwd: empty output (or odd W for W-pair planes)");
+    GnOut gn{gn2_w, gn2_b, groups2, out_wp ? 1 : 0, eps2, scale2, out_hi, out_lo};
+    return launch_conv(L, hi, lo, weight_image, bias, nullptr, N, D, H, W, pad, act, slope, out_scale, 0, stream, 0, 0, 0, &gn);
 }
 
 /* Debug / test aid: item shape and cost-model score (outputs per cycle and SM) of the W-pair variant [0] and of the plain

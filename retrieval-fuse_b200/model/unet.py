@@ -27,6 +27,8 @@ USE_FUSED_FRONT = True
 # encoder levels whose output is not a skip connection hand MaxPool3d(2) of it to the next level (pooled in the
 # convolution's epilogue where the W-pair variant of the shifted-window kernel runs the layer)
 FUSE_POOL = True
+# DoubleConv: the first convolution applies the second layer's GroupNorm in its epilogue and writes its operand planes
+FUSE_GN_EPILOGUE = True
 # EXPERIMENTAL, OFF by default (tools/wpack_formulation.py): run small-channel 3x3x3 layers through the
 # shifted-window kernel on W-packed views [N,D,H,W/Bw,Bw*C] with Toeplitz-expanded weights.  The identity is verified on
 # the CPU; the kernel has not been measured on these shapes yet, so nothing selects this path unless W_PACK maps
@@ -225,6 +227,32 @@ class _TwoConvs(nn.Module):
             y = ops.tc_conv3d_halo(split, img, c2.conv.bias, c2.out_channels, act=c2.act, slope=0.1,
                                    out_scale=1.0 / (ops.ACT_SCALE_GN * sw), pool=pool_ep)
             return ops.cl_maxpool3d_2(y) if pool and not pool_ep else y
+        if FUSE_GN_EPILOGUE and USE_TENSOR_CORES and USE_HALO_CONV and c1.order == "gcr" and c2.order == "gcr":
+            # DoubleConv: the first convolution's epilogue applies the second SingleConv's GroupNorm and writes its operand
+            # planes (items of one whole sample: statistics, normalisation and split straight from the accumulators)
+            n1 = x.shape[-1] if x is not None else 0
+            n2 = x2.shape[-1] if x2 is not None else 0
+            N, D, H, W = x.shape[:4] if x is not None else (x2.shape[0], 2 * x2.shape[1], 2 * x2.shape[2], 2 * x2.shape[3])
+            mid, g2 = c1.out_channels, c2.groupnorm
+            if (n1 != 1 and c1.tc_ok(n1, n2) and ops.tc_conv_halo_supported(N, D, H, W, mid, n1, n2)
+                    and ops.tc_conv_halo_gn_supported(N, D, H, W, mid, n1, n2, g2.num_groups)
+                    and ops.tc_conv_halo_supported(N, D, H, W, c2.out_channels, mid, 0)):
+                g1 = c1.groupnorm
+                mu, a = ops.cl_gn_stats(x, g1.weight, g1.num_groups, g1.eps, x2=x2) if x is not None else ops.cl_gn_stats(x2, g1.weight, g1.num_groups, g1.eps)
+                for m in (c1, c2):
+                    if not hasattr(m, "_halo_planes"):
+                        object.__setattr__(m, "_halo_planes", {})
+                sa = ops.ACT_SCALE_GN
+                split1 = ops.cl_norm_split_halo(x, x2, (mu, a, g1.bias), scale=sa, buffers=c1._halo_planes)
+                img1, sw1 = c1._halo_image(n1, n2, False)
+                pool_ep = pool and not out_ncdhw and ops.tc_conv_halo_wp_pool_supported(N, D, H, W, c2.out_channels, mid, 0)
+                wp2 = pool_ep or (not out_ncdhw and ops.tc_conv_halo_wp_wanted(N, D, H, W, c2.out_channels, mid, 0))
+                split2 = ops.tc_conv3d_halo_gn(split1, img1, c1.conv.bias, mid, g2.weight, g2.bias, g2.num_groups, g2.eps, sa, act=c1.act,
+                                               slope=0.1, out_scale=1.0 / (sa * sw1), out_wp=wp2, buffers=c2._halo_planes)
+                img2, sw2 = c2._halo_image(mid, 0, wp2)
+                y = ops.tc_conv3d_halo(split2, img2, c2.conv.bias, c2.out_channels, act=c2.act, slope=0.1, out_ncdhw=out_ncdhw,
+                                       out_scale=1.0 / (sa * sw2), pool=pool_ep)
+                return ops.cl_maxpool3d_2(y) if pool and not pool_ep else y
         return self.SingleConv2.forward_cl(self.SingleConv1.forward_cl(x, x2), None, out_ncdhw, pool=pool)
 
 

@@ -756,6 +756,45 @@ def tc_conv3d_halo(split, img, bias, cout, act=ACT_NONE, slope=0.0, out_ncdhw=Fa
     return y
 
 
+def tc_conv_halo_gn_supported(N, D, H, W, cout, c1, c2, groups2, pad=1):
+    """Whether the shifted-window kernel can apply the next layer's GroupNorm in its epilogue (one whole sample per item)."""
+    r = _lib.lib().rf_tc_conv3d_halo_gn_supported(int(N), int(D), int(H), int(W), int(pad), int(cout), int(c1), int(c2), int(groups2))
+    return r >= (1 if os.environ.get("RF_HALO_GN", "") == "1" else 2)  # RF_HALO_GN=1: wherever it runs (tests)
+
+
+def tc_conv3d_halo_gn(split, img, bias, cout, gn2_w, gn2_b, groups2, eps2, scale2, act=ACT_NONE, slope=0.0, out_scale=1.0, out_wp=False,
+                      buffers=None):
+    """Convolution (plain operand planes in `split`) whose epilogue applies the NEXT layer's GroupNorm and writes that layer's
+    operand planes: returns the split tuple cl_norm_split_halo(conv_output, GroupNorm 2, scale2, wp=out_wp) would give."""
+    hi, lo, (N, D, H, W, c1, c2, pad) = split
+    assert not getattr(split[2], "wp", False)
+    Do, Ho, Wo = D + 2 * pad - 2, H + 2 * pad - 2, W + 2 * pad - 2
+    L = _lib.lib()
+    nbytes = L.rf_halo_act_bytes(N, Do, Ho, Wo, cout, 0, 1)
+    key = (N, Do, Ho, Wo, cout, 0, 1, hi.device, bool(out_wp))
+    if buffers is not None:
+        if key not in buffers:
+            while len(buffers) >= MAX_PLANE_SHAPES:
+                buffers.pop(next(iter(buffers)))
+                bump_generation()
+            buffers[key] = (torch.empty(nbytes, device=hi.device, dtype=torch.uint8), torch.empty(nbytes, device=hi.device, dtype=torch.uint8))
+        else:
+            buffers[key] = buffers.pop(key)
+        ohi, olo = buffers[key]
+    else:
+        ohi = torch.empty(nbytes, device=hi.device, dtype=torch.uint8)
+        olo = torch.empty(nbytes, device=hi.device, dtype=torch.uint8)
+    with torch.cuda.device(hi.device), _timed("rf_tc_conv3d_halo_fwd", flops=2.0 * N * Do * Ho * Wo * 27 * (c1 + c2) * cout):
+        check(L.rf_tc_conv3d_halo_gn_fwd(hi.data_ptr(), lo.data_ptr(), img.data_ptr(), _ptr(bias), N, D, H, W, pad, int(cout), c1, c2, act,
+                                         float(slope), float(out_scale), gn2_w.data_ptr(), gn2_b.data_ptr(), int(groups2), float(eps2),
+                                         float(scale2), ohi.data_ptr(), olo.data_ptr(), int(bool(out_wp)),
+                                         torch.cuda.current_stream(hi.device).cuda_stream), "rf_tc_conv3d_halo_gn_fwd")
+    _count()
+    shape = _SplitShape((N, Do, Ho, Wo, int(cout), 0, 1))
+    shape.wp = bool(out_wp)
+    return ohi, olo, shape
+
+
 def groupnorm_stats(x, gamma, groups, eps=1e-5, x2=None):
     """Returns (gn_mu [N,C], gn_a [N,C]) for the virtual input concat(x, up2(x2))."""
     ref = x if x is not None else x2

@@ -263,6 +263,71 @@ def test_w_pair_conv_pools_in_epilogue(dev, N, C1, Cout):
     assert torch.equal(yp, ref), f"max |diff| {float((yp - ref).abs().max()):.2e}"
 
 
+# (N, S, C1, C2, mid, out, groups, order/encoder): DoubleConvs whose first convolution applies the second layer's GroupNorm in
+# its epilogue - encoder 16 -> 16 -> 32 @ 8^3, decoder join 96 -> 56 -> 16 (StepDown), 4^3 / 2^3 one-sample items, 1 group
+GN_EPI_CASES = [(5, 8, 16, 0, 16, 32, 8), (3, 8, 32, 64, 56, 16, 8), (301, 8, 16, 0, 16, 32, 8), (9, 4, 32, 0, 32, 64, 8),
+                (4, 2, 64, 0, 64, 128, 8), (6, 8, 12, 24, 24, 12, 1)]
+
+
+@pytest.mark.parametrize("N,S,C1,C2,mid,cout,groups", GN_EPI_CASES)
+def test_double_conv_groupnorm_in_epilogue(dev, N, S, C1, C2, mid, cout, groups, monkeypatch):
+    """model/unet.py:103-159 DoubleConv / StepDownDoubleConv: conv 1 (rf_tc_conv3d_halo_gn_fwd) reduces the per-sample
+    statistics of its activated output in the epilogue, applies SingleConv2's GroupNorm and writes conv 2's operand planes
+    (plain and W-pair layouts).  Against torch CPU fp64 / fp32 and against the separate launches."""
+    from retrieval_fuse_b200 import ops
+    from retrieval_fuse_b200.model import unet as U
+    monkeypatch.setenv("RF_HALO_GN", "1")
+    g = torch.Generator().manual_seed(N + 3 * S + C1 + C2 + mid + cout)
+    C = C1 + C2
+    blk = U._TwoConvs()
+    blk.SingleConv1 = U.SingleConv(C, mid, 3, "gcr", groups)
+    blk.SingleConv2 = U.SingleConv(mid, cout, 3, "gcr", groups)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (1.0 / (27 * p.shape[1]) ** 0.5 if p.dim() > 1 else 0.2) + (1.0 if p.dim() == 1 else 0.0))
+    x = torch.randn(N, C1, S, S, S, generator=g) * 1.5 + 0.3
+    x2 = torch.randn(N, C2, S // 2, S // 2, S // 2, generator=g) * 0.7 - 0.2 if C2 else None
+    x[1 % N] = 0.25
+    if C2:
+        x2[1 % N] = -0.5  # constant sample: conv 1's outputs are constant per channel away from the border
+    F = torch.nn.functional
+    c1, c2 = blk.SingleConv1, blk.SingleConv2
+
+    def ref(sel, dt):
+        xc = x[sel] if not C2 else torch.cat([x[sel], F.interpolate(x2[sel], scale_factor=2, mode="nearest")], 1)
+        h = F.group_norm(xc.to(dt), c1.groupnorm.num_groups, c1.groupnorm.weight.to(dt), c1.groupnorm.bias.to(dt), 1e-5)
+        h = F.relu(F.conv3d(h, c1.conv.weight.to(dt), padding=1))
+        h = F.group_norm(h, c2.groupnorm.num_groups, c2.groupnorm.weight.to(dt), c2.groupnorm.bias.to(dt), 1e-5)
+        return F.relu(F.conv3d(h, c2.conv.weight.to(dt), padding=1))
+    sel = list(range(min(N, 4))) + ([N - 1] if N > 4 else [])
+    with torch.no_grad():
+        ref64, ref32 = ref(sel, torch.float64), ref(sel, torch.float32)
+    blk = blk.to(dev)
+    xd = x.permute(0, 2, 3, 4, 1).contiguous().to(dev)
+    x2d = x2.permute(0, 2, 3, 4, 1).contiguous().to(dev) if C2 else None
+    assert ops.tc_conv_halo_gn_supported(N, S, S, S, mid, C1, C2, c2.groupnorm.num_groups)
+    outs = {}
+    with torch.no_grad():
+        for wp in ("0", "1"):
+            monkeypatch.setenv("RF_HALO_WP", wp)
+            monkeypatch.setattr(U, "FUSE_GN_EPILOGUE", True)
+            ops.reset_launches()
+            outs[wp] = blk.forward_cl(xd, x2d)
+            n_launch = ops.launches()
+            assert n_launch <= 9, f"{n_launch} launches: the GroupNorm epilogue did not run"
+        monkeypatch.setattr(U, "FUSE_GN_EPILOGUE", False)
+        monkeypatch.setenv("RF_HALO_WP", "0")
+        y0 = blk.forward_cl(xd, x2d)
+    scale = max(1.0, float(ref64.abs().max()))
+    noise = float((ref32.double() - ref64).abs().max())
+    for wp, y in outs.items():
+        yc = y.permute(0, 4, 1, 2, 3).cpu()[sel]
+        err64 = float((yc.double() - ref64).abs().max())
+        assert err64 <= max(2e-5 * scale, 4 * noise), f"wp={wp}: |ours - fp64| {err64:.2e} (torch fp32 noise {noise:.2e}, scale {scale:.1f})"
+        close(yc, ref32, rel_to_max=True, what="DoubleConv with the GroupNorm epilogue vs torch fp32")
+        assert float((y - y0).abs().max()) <= max(4e-5 * scale, 4 * noise), f"wp={wp}: GroupNorm epilogue vs separate launches (all samples)"
+
+
 # (N, S_in, Cin, Cout): 'valid' layers of the conv patch encoders (Patch32 8->16 @ 28^3, PCPatch48 16->32 @ 44^3, Patch08 shapes)
 WP_VALID_CASES = [(40, 28, 8, 16), (3, 44, 16, 32), (150, 8, 8, 16), (33, 6, 16, 32), (9, 12, 24, 40)]
 
