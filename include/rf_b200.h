@@ -223,12 +223,11 @@ int rf_tc_conv3d_halo_wp_fwd(const void* hi, const void* lo, const void* weight_
  * the retrieval U-Net's patches, model/refinement.py:64-73): GroupNorm(1,1) -> Conv3d(1,8,3,p=1) -> ReLU ->
  * GroupNorm(groups2, 8) -> x scale -> fp16 hi / lo operand planes of rf_tc_conv3d_halo_fwd (wp = 0) or
  * rf_tc_conv3d_halo_wp_fwd (wp = 1), sized by rf_halo_act_bytes(N,16,16,16,8,0,1).  One persistent CTA per sample;
- * the 8-channel fp32 activations never reach HBM.  x [N,16,16,16]; conv_w [8,1,3,3,3]; gn2_w / gn2_b [8] on the device.
- * _fwd reads conv_w / gn1_w / gn1_b back (stream sync); _fwd_host takes them from the host and can be graph-captured. */
-int rf_unet_front16_fwd(const float* x, const float* gn1_w, const float* gn1_b, float eps1, const float* conv_w, const float* gn2_w,
+ * the 8-channel fp32 activations never reach HBM.  x [N,16,16,16], gn2_w / gn2_b [8]: device pointers.  The 218 scalars
+ * the FMAs read as kernel-parameter constants come from the HOST: conv_w_host [8][27] (the Conv3d weight [8,1,3,3,3]) and
+ * gn1_w / gn1_b by value.  No stream synchronisation (graph-capturable; re-capture after a weight update). */
+int rf_unet_front16_fwd(const float* x, float gn1_w, float gn1_b, float eps1, const float* conv_w_host, const float* gn2_w,
                         const float* gn2_b, int groups2, float eps2, float scale, void* hi, void* lo, int N, int wp, void* stream);
-int rf_unet_front16_fwd_host(const float* x, float gn1_w, float gn1_b, float eps1, const float* conv_w_host, const float* gn2_w,
-                             const float* gn2_b, int groups2, float eps2, float scale, void* hi, void* lo, int N, int wp, void* stream);
 
 /* Single-input-channel layers on the same kernel (the first Conv3d of every patch
  * encoder, model/retrieval.py:4-388, kernel edge 3 or 5, no padding; the first

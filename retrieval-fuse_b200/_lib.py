@@ -89,10 +89,8 @@ PROTOTYPES = {
     "rf_tc_conv3d_halo_wp_geometry": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rf_tc_conv3d_halo_wp_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_int, c_int, c_float, c_float, c_void_p]),
-    "rf_unet_front16_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p,
-                                    c_void_p, c_int, c_int, c_void_p]),
-    "rf_unet_front16_fwd_host": (c_int, [c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
-                                         c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "rf_unet_front16_fwd": (c_int, [c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
+                                    c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "rf_wrun_act_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "rf_cl_norm_split_wrun": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_float, c_void_p]),

@@ -200,45 +200,16 @@ __global__ void __launch_bounds__(NT, 1) unet_front16_kernel(const __grid_consta
 /* Fused front of the first DoubleConv of a 'gcr' U-Net encoder on 16^3 single-channel samples (model/unet.py:79-144):
  * GroupNorm(1,1) -> Conv3d(1,8,3,p=1) -> ReLU -> GroupNorm(groups2, 8) -> x scale -> fp16 hi / lo operand planes of
  * rf_tc_conv3d_halo_fwd (wp = 0: rf_cl_norm_split_halo's layout) or rf_tc_conv3d_halo_wp_fwd (wp = 1).
- * x [N,16,16,16]; conv_w [8,1,3,3,3]; gn1_w / gn1_b [1]; gn2_w / gn2_b [8] (device pointers).  hi / lo: rf_halo_act_bytes(N,16,16,16,8,0,1). */
-extern "C" int rf_unet_front16_fwd(const float* x, const float* gn1_w, const float* gn1_b, float eps1, const float* conv_w,
-                                   const float* gn2_w, const float* gn2_b, int groups2, float eps2, float scale, void* hi, void* lo,
-                                   int N, int wp, void* stream) {
-    RF_CHECK_ARG(x && gn1_w && gn1_b && conv_w && gn2_w && gn2_b && hi && lo && N > 0, "rf_unet_front16_fwd: bad arguments");
+ * x [N,16,16,16] and gn2_w / gn2_b [8] on the device; the 218 scalars the FMAs read as kernel-parameter constants come
+ * from the HOST: conv_w_host [8][27] (= Conv3d weight [8,1,3,3,3]), gn1_w / gn1_b by value.  No stream synchronisation,
+ * so the call can be captured into a CUDA graph (the graph then holds these values: re-capture after a weight update).
+ * hi / lo: rf_halo_act_bytes(N,16,16,16,8,0,1) bytes each. */
+extern "C" int rf_unet_front16_fwd(const float* x, float gn1_w, float gn1_b, float eps1, const float* conv_w_host, const float* gn2_w,
+                                   const float* gn2_b, int groups2, float eps2, float scale, void* hi, void* lo, int N, int wp,
+                                   void* stream) {
+    RF_CHECK_ARG(x && conv_w_host && gn2_w && gn2_b && hi && lo && N > 0, "rf_unet_front16_fwd: bad arguments");
     RF_CHECK_ARG(groups2 == 1 || groups2 == CO, "rf_unet_front16_fwd: the second GroupNorm must have 1 or 8 groups");
     RF_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0, "rf_unet_front16_fwd: pointers must be 16-byte aligned");
-    FrontArgs a;
-    a.x = x; a.gamma2 = gn2_w; a.beta2 = gn2_b; a.hi = (uint4*)hi; a.lo = (uint4*)lo;
-    a.eps1 = eps1; a.eps2 = eps2; a.scale = scale; a.N = N; a.wp = wp ? 1 : 0; a.cpg = CO / groups2;
-    // the 218 scalars the kernel reads as constants come from device memory: one small synchronous-to-stream copy
-    float host[27 * CO + 2];
-    cudaStream_t s = (cudaStream_t)stream;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    RF_CUDA_OK(cudaStreamIsCapturing(s, &cap));
-    RF_CHECK_ARG(cap == cudaStreamCaptureStatusNone, "rf_unet_front16_fwd: reads its weights back to the host; use rf_unet_front16_fwd_host inside a capture");
-    RF_CUDA_OK(cudaMemcpyAsync(host, conv_w, sizeof(float) * 27 * CO, cudaMemcpyDeviceToHost, s));
-    RF_CUDA_OK(cudaMemcpyAsync(host + 27 * CO, gn1_w, sizeof(float), cudaMemcpyDeviceToHost, s));
-    RF_CUDA_OK(cudaMemcpyAsync(host + 27 * CO + 1, gn1_b, sizeof(float), cudaMemcpyDeviceToHost, s));
-    RF_CUDA_OK(cudaStreamSynchronize(s));
-    for (int t = 0; t < 27; ++t)
-        for (int c = 0; c < CO; ++c) a.w[t][c] = host[c * 27 + t];
-    a.gamma1 = host[27 * CO]; a.beta1 = host[27 * CO + 1];
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    unet_front16_kernel<<<N < sms ? N : sms, NT, 0, s>>>(a);
-    RF_LAUNCH_OK("unet_front16_kernel");
-    return 0;
-}
-
-/* Same with the 218 scalars given on the HOST (conv_w_host [8][27], gn1 weight / bias as values): no read-back, so the
- * call can be captured into a CUDA graph (the graph then holds these values: re-capture after a weight update). */
-extern "C" int rf_unet_front16_fwd_host(const float* x, float gn1_w, float gn1_b, float eps1, const float* conv_w_host,
-                                        const float* gn2_w, const float* gn2_b, int groups2, float eps2, float scale, void* hi,
-                                        void* lo, int N, int wp, void* stream) {
-    RF_CHECK_ARG(x && conv_w_host && gn2_w && gn2_b && hi && lo && N > 0, "rf_unet_front16_fwd_host: bad arguments");
-    RF_CHECK_ARG(groups2 == 1 || groups2 == CO, "rf_unet_front16_fwd_host: the second GroupNorm must have 1 or 8 groups");
-    RF_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0, "rf_unet_front16_fwd_host: pointers must be 16-byte aligned");
     FrontArgs a;
     a.x = x; a.gamma2 = gn2_w; a.beta2 = gn2_b; a.hi = (uint4*)hi; a.lo = (uint4*)lo;
     a.eps1 = eps1; a.eps2 = eps2; a.scale = scale; a.N = N; a.wp = wp ? 1 : 0; a.cpg = CO / groups2;

@@ -7,6 +7,7 @@ Every function launches the hand-written sm_100a kernels through ctypes on
 from __future__ import annotations
 
 import ctypes
+import functools
 import math
 import os
 
@@ -583,7 +584,7 @@ def tc_conv3d(xs, x2s, c1, c2, img, bias, cout, ks, stride=1, pad=0, act=ACT_NON
 
 def tc_conv_halo_supported(N, D, H, W, cout, c1, c2, pad=1):
     """D, H, W: input extents; pad 1 = 'same' (U-Nets), pad 0 = 'valid' (conv patch encoders)."""
-    return bool(_lib.lib().rf_tc_conv3d_halo_supported(int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2), int(pad)))
+    return bool(_halo_query("rf_tc_conv3d_halo_supported", int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2), int(pad)))
 
 
 def tc_conv_halo_geometry(N, D, H, W, cout, c1, c2, pad=1):
@@ -604,13 +605,20 @@ def tc_conv_halo_wp_mode():
     return os.environ.get("RF_HALO_WP", "")
 
 
+# The per-layer questions below are pure functions of the shape (the item chooser runs on the host): memoised, because a
+# U-Net forward asks several of them per layer and an eager forward on 8 chunks is host-bound.
+@functools.lru_cache(maxsize=4096)
+def _halo_query(fn, *args):
+    return int(getattr(_lib.lib(), fn)(*args))
+
+
 def tc_conv_halo_wp_wanted(N, D, H, W, cout, c1, c2, pad=1):
     """Whether the W-pair variant of the shifted-window kernel (one GEMM row = two output voxels, N = 2 Cout) should run
     this 3x3x3 stride-1 layer.  D, H, W: input extents."""
     mode = tc_conv_halo_wp_mode()
     if mode == "0":
         return False
-    r = _lib.lib().rf_tc_conv3d_halo_wp_supported(int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2), int(pad))
+    r = _halo_query("rf_tc_conv3d_halo_wp_supported", int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2), int(pad))
     return r >= (1 if mode == "1" else 2)
 
 
@@ -666,7 +674,7 @@ def cl_norm_split_halo(x, x2=None, gn=None, scale=1.0, pad=1, buffers=None, wp=F
 
 
 def unet_front16(x, gn1_w, gn1_b, eps1, conv_w_host, gn2_w, gn2_b, groups2, eps2, scale, wp=False, buffers=None):
-    """Fused front of a 'gcr' DoubleConv on 16^3 single-channel samples (rf_unet_front16_fwd_host): x [N,16,16,16,1] ->
+    """Fused front of a 'gcr' DoubleConv on 16^3 single-channel samples (rf_unet_front16_fwd): x [N,16,16,16,1] ->
     the operand planes cl_norm_split_halo(relu(conv(GroupNorm(x))), GroupNorm 2) would produce, as a split tuple for
     tc_conv3d_halo.  gn1_w / gn1_b: floats; conv_w_host: contiguous CPU fp32 [8,1,3,3,3]; gn2_w / gn2_b: device [8]."""
     x = _dev(x, name="x")
@@ -688,9 +696,9 @@ def unet_front16(x, gn1_w, gn1_b, eps1, conv_w_host, gn2_w, gn2_b, groups2, eps2
         hi = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
         lo = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
     with torch.cuda.device(x.device), _timed("rf_unet_front16_fwd", flops=2.0 * N * 4096 * 27 * 8):
-        check(L.rf_unet_front16_fwd_host(x.data_ptr(), float(gn1_w), float(gn1_b), float(eps1), conv_w_host.data_ptr(), gn2_w.data_ptr(),
+        check(L.rf_unet_front16_fwd(x.data_ptr(), float(gn1_w), float(gn1_b), float(eps1), conv_w_host.data_ptr(), gn2_w.data_ptr(),
                                          gn2_b.data_ptr(), int(groups2), float(eps2), float(scale), hi.data_ptr(), lo.data_ptr(), N,
-                                         int(bool(wp)), _stream(x)), "rf_unet_front16_fwd_host")
+                                         int(bool(wp)), _stream(x)), "rf_unet_front16_fwd")
     _count()
     shape = _SplitShape((N, 16, 16, 16, 8, 0, 1))
     shape.wp = bool(wp)
@@ -722,7 +730,7 @@ def tc_conv_halo_wp_pool_supported(N, D, H, W, cout, c1, c2):
     """Whether the W-pair variant can max-pool 2x2x2 in its epilogue for this 'same' 3x3x3 layer (D, H, W: input extents)."""
     if tc_conv_halo_wp_mode() == "0":
         return False
-    return bool(_lib.lib().rf_tc_conv3d_halo_wp_pool_supported(int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2)))
+    return bool(_halo_query("rf_tc_conv3d_halo_wp_pool_supported", int(N), int(D), int(H), int(W), int(cout), int(c1), int(c2)))
 
 
 def tc_conv3d_halo(split, img, bias, cout, act=ACT_NONE, slope=0.0, out_ncdhw=False, out_scale=1.0, pool=False):
@@ -758,7 +766,7 @@ def tc_conv3d_halo(split, img, bias, cout, act=ACT_NONE, slope=0.0, out_ncdhw=Fa
 
 def tc_conv_halo_gn_supported(N, D, H, W, cout, c1, c2, groups2, pad=1):
     """Whether the shifted-window kernel can apply the next layer's GroupNorm in its epilogue (one whole sample per item)."""
-    r = _lib.lib().rf_tc_conv3d_halo_gn_supported(int(N), int(D), int(H), int(W), int(pad), int(cout), int(c1), int(c2), int(groups2))
+    r = _halo_query("rf_tc_conv3d_halo_gn_supported", int(N), int(D), int(H), int(W), int(pad), int(cout), int(c1), int(c2), int(groups2))
     return r >= (1 if os.environ.get("RF_HALO_GN", "") == "1" else 2)  # RF_HALO_GN=1: wherever it runs (tests)
 
 

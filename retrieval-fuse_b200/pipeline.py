@@ -267,7 +267,7 @@ class RefinementPipeline(RetrievalPipeline):
         cur = torch.cuda.current_stream(self.device)
         if not hasattr(self, "_side_stream"):
             self._side_stream = torch.cuda.Stream(device=self.device)
-        side = self._side_stream
+        side = cur if getattr(self, "serial_streams", False) else self._side_stream  # (serial_streams: per-op timing passes)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             x_in.record_stream(side)

@@ -361,7 +361,7 @@ def test_valid_conv_w_pairs(dev, N, S, Cin, Cout):
 def test_fused_front_of_first_double_conv(dev, N, groups, wp, monkeypatch):
     """model/unet.py:103-144 DoubleConv(1, 16, encoder=True, 'gcr') on 16^3 patches (first block of the retrieval U-Net,
     model/refinement.py:64-73): the fused front kernel (GroupNorm -> 1->8 conv -> ReLU -> statistics -> normalise -> operand
-    split, rf_unet_front16_fwd_host) + second conv against torch CPU in fp64 / fp32 and against the unfused launches."""
+    split, rf_unet_front16_fwd) + second conv against torch CPU in fp64 / fp32 and against the unfused launches."""
     from retrieval_fuse_b200 import ops
     from retrieval_fuse_b200.model import unet as U
     monkeypatch.setenv("RF_HALO_WP", wp)
