@@ -124,6 +124,9 @@ PROTOTYPES = {
     "rf_attention_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "rf_attention_fuse_fwd": (c_int, [c_void_p, c_void_p, _ptr4, _ptr4, _ptr4, _ptr4, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "rf_attention_fuse_patched_fwd": (c_int, [c_void_p, c_void_p, _ptr4, _ptr4, _ptr4, _ptr4, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
+                                              c_void_p]),
     "rf_attention_features": (c_int, [c_void_p, c_void_p, c_void_p, _ptr4, _ptr4, _ptr4, _ptr4, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "rf_sobel_normals": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),

@@ -30,6 +30,41 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Row geometry of the epilogue.  P > 1: the candidates' rows (pf, pu) are in (b, k, patch, local sub-patch) order - the
+// retrieval U-Net's P^3 patches per volume were unfolded without folding them into the volume first (Fold3D then
+// Unfold3D is a permutation of rows).  out_cl: the blended rows are stored as the channels-last volume [B,S,S,S,nf]
+// (what the decoder's first convolution reads) instead of rows [R,V] that a Fold3D would have to re-index.
+struct AttnGeo {
+    int P, out_cl, nf, E, Rp;
+    FastDiv d_nf, d_E, d_Rp, d_ps;  // ps = Rp / P sub-patches per patch side
+};
+
+// Unfold3D(2, C) of patches [NP, C, 8,8,8] -> rows [NP * 64, C * 8]: one CTA per patch.  Both sides of a patch are ONE
+// contiguous run of C * 512 floats, the (c, x, y, z) -> (lx, ly, lz, c, ex, ey, ez) transposition happens in shared
+// memory (x stride 66, c stride 532 floats: the float2 reads of a half-warp hit 16 different bank pairs).
+__global__ void __launch_bounds__(256) unfold_e2_patch8_kernel(const float* __restrict__ in, float* __restrict__ out, int C) {
+    extern __shared__ float sm_patch[];
+    const float4* pin = reinterpret_cast<const float4*>(in + (long)blockIdx.x * C * 512);
+    float4* pout = reinterpret_cast<float4*>(out + (long)blockIdx.x * C * 512);
+    for (int i = threadIdx.x; i < C * 128; i += blockDim.x) {
+        const float4 v = __ldg(pin + i);
+        const int c = i >> 7, rem = i & 127, x = rem >> 4, yz = (rem & 15) << 2;
+        float* d = sm_patch + c * 532 + x * 66 + yz;
+        *reinterpret_cast<float2*>(d) = make_float2(v.x, v.y);
+        *reinterpret_cast<float2*>(d + 2) = make_float2(v.z, v.w);
+    }
+    __syncthreads();
+    const int C2 = 2 * C;
+    for (int o = threadIdx.x; o < 64 * C2; o += blockDim.x) {
+        const int row = o / C2, j = o - row * C2;
+        const int lx = row >> 4, ly = (row >> 2) & 3, lz = row & 3, c = j >> 1, ex = j & 1;
+        const float* s0 = sm_patch + c * 532 + (2 * lx + ex) * 66 + 16 * ly + 2 * lz;
+        const float2 a = *reinterpret_cast<const float2*>(s0);
+        const float2 bq = *reinterpret_cast<const float2*>(s0 + 8);
+        pout[o] = make_float4(a.x, a.y, bq.x, bq.y);
+    }
+}
+
 // xf [R,32], pf [(b,k,r),32], xu [R,V], pu [(b,k,r),V] -> orows [R,V]
 // One warp per row.  KT = compile-time bound on K: the K feature rows and (for KT <= 8) the first 128 values of the
 // row's own and of its K candidate vectors are requested BEFORE the score / softmax chain, so that one warp has all
@@ -40,12 +75,42 @@ __global__ void __launch_bounds__(256) attention_epilogue_kernel(const float* __
                                                                  const float* __restrict__ xu, const float* __restrict__ pu,
                                                                  const float* __restrict__ noise, float* __restrict__ orows,
                                                                  long R, int rp3, int K, int V, int normalize, int mode,
-                                                                 int blend, float sharp) {
+                                                                 int blend, float sharp, const AttnGeo g) {
     const long row = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= R) return;
-    const long b = row / rp3, rr = row % rp3;
+    const long b = row / rp3;
+    unsigned rr = (unsigned)(row % rp3);
+    unsigned px = 0, py = 0, pz = 0;
+    if (g.P > 1 || g.out_cl) {
+        unsigned t = rr;
+        pz = fd_divmod(t, g.d_Rp);
+        py = fd_divmod(t, g.d_Rp);
+        px = t;
+    }
+    if (g.P > 1) {
+        // candidate rows come from Unfold3D run on the P^3 un-folded patches of each volume: (patch, local sub-patch) order
+        const unsigned ps = g.d_ps.d;
+        const unsigned qx = fd_div(px, g.d_ps), qy = fd_div(py, g.d_ps), qz = fd_div(pz, g.d_ps);
+        rr = ((qx * g.P + qy) * g.P + qz) * (ps * ps * ps) + ((px - qx * ps) * ps + (py - qy * ps)) * ps + (pz - qz * ps);
+    }
     const long prow0 = b * K * rp3 + rr;  // candidate k lives at prow0 + k * rp3
+    // channels-last output: the warp's i-th value is element (e, c) = (i / nf, i % nf) of the sub-patch, i.e. feature
+    // c * E^3 + e of the row; its 2 * nf (E = 2) consecutive values are one contiguous piece of out [B,S,S,S,nf]
+    const int E3 = g.E * g.E * g.E;
+    const long S = (long)g.Rp * g.E;
+    auto feat_of = [&](int i) -> int {
+        if (!g.out_cl) return i;
+        const unsigned e = fd_div((unsigned)i, g.d_nf);
+        return (int)(((unsigned)i - e * g.nf) * E3 + e);
+    };
+    auto out_addr = [&](int i) -> long {
+        if (!g.out_cl) return row * (long)V + i;
+        unsigned e = fd_div((unsigned)i, g.d_nf);
+        const unsigned c = (unsigned)i - e * g.nf;
+        const unsigned ez = fd_divmod(e, g.d_E), ey = fd_divmod(e, g.d_E), ex = e;
+        return ((((b * S + px * g.E + ex) * S + py * g.E + ey) * S + pz * g.E + ez) * g.nf) + c;
+    };
     constexpr bool kPrefetch = KT <= 8;
     constexpr int PF = kPrefetch ? KT : 1;
 
@@ -58,10 +123,11 @@ __global__ void __launch_bounds__(256) attention_epilogue_kernel(const float* __
     if (kPrefetch) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int v = lane + 32 * j;
-            xr[j] = v < V ? __ldg(xrow + v) : 0.f;
+            const int i = lane + 32 * j;
+            const int v = i < V ? feat_of(i) : 0;
+            xr[j] = i < V ? __ldg(xrow + v) : 0.f;
 #pragma unroll
-            for (int k = 0; k < PF; ++k) pr[k][j] = (k < K && v < V) ? __ldg(pu + (prow0 + (long)k * rp3) * V + v) : 0.f;
+            for (int k = 0; k < PF; ++k) pr[k][j] = (k < K && i < V) ? __ldg(pu + (prow0 + (long)k * rp3) * V + v) : 0.f;
         }
     }
 
@@ -105,7 +171,6 @@ __global__ void __launch_bounds__(256) attention_epilogue_kernel(const float* __
         const float hard = lane == arg ? 1.f : 0.f;
         w = lane < K ? (hard - y) + y : 0.f;
     }
-    float* orow = orows + row * V;
     float wk[KT];
 #pragma unroll
     for (int k = 0; k < KT; ++k) wk[k] = __shfl_sync(0xffffffffu, w, k);
@@ -118,17 +183,18 @@ __global__ void __launch_bounds__(256) attention_epilogue_kernel(const float* __
 #pragma unroll
             for (int k = 0; k < PF; ++k)
                 if (k < K) acc = fmaf(wk[k], pr[k][j], acc);
-            if (v < V) orow[v] = blend ? (xr[j] * (1.f - sw) + acc * sw) : (xr[j] + acc * sw);
+            if (v < V) orows[out_addr(v)] = blend ? (xr[j] * (1.f - sw) + acc * sw) : (xr[j] + acc * sw);
         }
         v0 = 128;
     }
-    for (int v = v0 + lane; v < V; v += 32) {
+    for (int i = v0 + lane; i < V; i += 32) {
+        const int v = feat_of(i);
         float acc = 0.f;
 #pragma unroll
         for (int k = 0; k < KT; ++k)
             if (k < K) acc = fmaf(wk[k], __ldg(pu + (prow0 + (long)k * rp3) * V + v), acc);
         const float x = xrow[v];
-        orow[v] = blend ? (x * (1.f - sw) + acc * sw) : (x + acc * sw);
+        orows[out_addr(i)] = blend ? (x * (1.f - sw) + acc * sw) : (x + acc * sw);
     }
 }
 
@@ -198,40 +264,71 @@ extern "C" size_t rf_attention_workspace_bytes(int B, int nf, int S, int E, int 
     return attn_ws_layout(B, nf, S, E, K, nullptr, nullptr);
 }
 
-extern "C" int rf_attention_fuse_fwd(const float* x_back, const float* x_retr, const float* const* theta_wt_host,
-                                     const float* const* theta_b_host, const float* const* phi_wt_host,
-                                     const float* const* phi_b_host, const void* const* theta_img_host,
-                                     const void* const* phi_img_host, const float* gumbel_noise, float* out, int B, int nf,
-                                     int S, int E, int K, int normalize, int mode, int blend, void* workspace,
-                                     size_t workspace_bytes, void* stream) {
+extern "C" int rf_attention_fuse_patched_fwd(const float* x_back, const float* x_retr, const float* const* theta_wt_host,
+                                             const float* const* theta_b_host, const float* const* phi_wt_host,
+                                             const float* const* phi_b_host, const void* const* theta_img_host,
+                                             const void* const* phi_img_host, const float* gumbel_noise, float* out, int B,
+                                             int nf, int S, int E, int K, int normalize, int mode, int blend, int patch_grid,
+                                             int out_channels_last, void* workspace, size_t workspace_bytes, void* stream) {
     RF_CHECK_ARG(x_back && x_retr && out && theta_wt_host && theta_b_host && phi_wt_host && phi_b_host && workspace,
                  "rf_attention_fuse_fwd: null pointer");
     RF_CHECK_ARG(B > 0 && nf > 0 && S > 0 && E > 0 && S % E == 0, "rf_attention_fuse_fwd: bad shape");
     RF_CHECK_ARG(K >= 1 && K <= 32, "rf_attention_fuse_fwd: K=%d unsupported (1..32)", K);
     RF_CHECK_ARG(mode == 0 || (mode == 1 && gumbel_noise), "rf_attention_fuse_fwd: retrieval mode needs the Gumbel noise");
     RF_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "rf_attention_fuse_fwd: workspace must be 256-byte aligned");
+    const int P = patch_grid < 1 ? 1 : patch_grid;
+    RF_CHECK_ARG(S % P == 0 && (S / P) % E == 0, "rf_attention_fuse_fwd: patch grid %d does not tile S=%d into multiples of E=%d", P, S, E);
     AttnWs ws;
     const size_t need = attn_ws_layout(B, nf, S, E, K, &ws, (char*)workspace);
     RF_CHECK_ARG(workspace_bytes >= need, "rf_attention_fuse_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
     const int Rp = S / E, rp3 = Rp * Rp * Rp, V = nf * E * E * E;
     const long R = (long)B * rp3;
+    RF_CHECK_ARG(R * K * (long)V < (1L << 40), "rf_attention_fuse_fwd: too many rows");
     int rc;
     if ((rc = rf_unfold3d(x_back, ws.xu, B, nf, S, E, stream))) return rc;
-    if ((rc = rf_unfold3d(x_retr, ws.pu, B * K, nf, S, E, stream))) return rc;
+    if (P > 1) {
+        // x_retr = the un-folded patches [B*K*P^3, nf, S/P, S/P, S/P]: their rows in (patch, local) order, no Fold3D
+        const long NP = (long)B * K * P * P * P;
+        RF_CHECK_ARG(NP < (1L << 31), "rf_attention_fuse_fwd: too many patches");
+        if (S / P == 8 && E == 2 && (((uintptr_t)x_retr | (uintptr_t)ws.pu) & 15) == 0 && (size_t)nf * 532 * sizeof(float) <= 48 * 1024) {
+            unfold_e2_patch8_kernel<<<(unsigned)NP, 256, (size_t)nf * 532 * sizeof(float), (cudaStream_t)stream>>>(x_retr, ws.pu, nf);
+            RF_LAUNCH_OK("unfold_e2_patch8_kernel");
+        } else if ((rc = rf_unfold3d(x_retr, ws.pu, (int)NP, nf, S / P, E, stream))) {
+            return rc;
+        }
+    } else if ((rc = rf_unfold3d(x_retr, ws.pu, B * K, nf, S, E, stream))) {
+        return rc;
+    }
     if ((rc = run_mlp(ws.xu, R, V, theta_wt_host, theta_b_host, theta_img_host, ws.ha, ws.hb, ws.xf, stream))) return rc;
     if ((rc = run_mlp(ws.pu, R * K, V, phi_wt_host, phi_b_host, phi_img_host, ws.ha, ws.hb, ws.pf, stream))) return rc;
     const float sharp = (float)(FEAT * E * E * E * 4);  // model/attention.py:105
     const unsigned egrid = (unsigned)rf_cdivl(R * 32, 256);
+    AttnGeo g;
+    g.P = P; g.out_cl = out_channels_last ? 1 : 0; g.nf = nf; g.E = E; g.Rp = Rp;
+    g.d_nf = make_fastdiv(nf); g.d_E = make_fastdiv(E); g.d_Rp = make_fastdiv(Rp); g.d_ps = make_fastdiv(Rp / P);
+    float* erows = g.out_cl ? out : ws.orows;  // channels-last: the epilogue stores the volume itself
 #define RF_ATTN_EPI(KT)                                                                                         \
     attention_epilogue_kernel<KT><<<egrid, 256, 0, (cudaStream_t)stream>>>(ws.xf, ws.pf, ws.xu, ws.pu, gumbel_noise, \
-                                                                            ws.orows, R, rp3, K, V, normalize, mode, blend, sharp)
+                                                                            erows, R, rp3, K, V, normalize, mode, blend, sharp, g)
     if (K <= 4) RF_ATTN_EPI(4);
     else if (K <= 8) RF_ATTN_EPI(8);
     else if (K <= 16) RF_ATTN_EPI(16);
     else RF_ATTN_EPI(32);
 #undef RF_ATTN_EPI
     RF_LAUNCH_OK("attention_epilogue_kernel");
+    if (g.out_cl) return 0;
     return rf_fold3d(ws.orows, out, B, nf, Rp, E, stream);
+}
+
+extern "C" int rf_attention_fuse_fwd(const float* x_back, const float* x_retr, const float* const* theta_wt_host,
+                                     const float* const* theta_b_host, const float* const* phi_wt_host,
+                                     const float* const* phi_b_host, const void* const* theta_img_host,
+                                     const void* const* phi_img_host, const float* gumbel_noise, float* out, int B, int nf,
+                                     int S, int E, int K, int normalize, int mode, int blend, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+    return rf_attention_fuse_patched_fwd(x_back, x_retr, theta_wt_host, theta_b_host, phi_wt_host, phi_b_host, theta_img_host,
+                                         phi_img_host, gumbel_noise, out, B, nf, S, E, K, normalize, mode, blend, 1, 0,
+                                         workspace, workspace_bytes, stream);
 }
 
 extern "C" int rf_attention_features(const float* x, const float* t, const uint8_t* occ, const float* const* theta_wt_host,

@@ -20,6 +20,7 @@
 //                         Epilogue: bias + activation, fp32 channels-last
 //                         (next layer) or NCDHW (module boundary) stores.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "rf_common.cuh"
 
@@ -176,6 +177,224 @@ __global__ void __launch_bounds__(256) cl_gn_partial_kernel(const float* __restr
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         atomicAdd(&sums[((long)n * c_tot + c_off + c) * 2], sh[c] * weight);
         atomicAdd(&sums[((long)n * c_tot + c_off + c) * 2 + 1], sh[C + c] * weight);
+    }
+}
+
+// Same reduction for C % 4 == 0 (every GroupNorm of the U-Nets): a thread keeps one channel QUAD and reads float4s, four
+// of them in flight.  The scalar kernel above has 2048 threads x 4 loads x 4 B = 32 KiB in flight per SM, less than the
+// ~52 KiB HBM's latency-bandwidth product asks of an SM (it measured 2.5 - 3.3 TB/s on the 0.5 - 1 GB tensors of a
+// 64-chunk step); 16-byte loads put 4x the bytes behind the same number of requests.
+__global__ void __launch_bounds__(256) cl_gn_partial_vec4_kernel(const float* __restrict__ x, long S, int C, int slices, double weight,
+                                                                 int c_off, int c_tot, double* __restrict__ sums) {
+    const int n = blockIdx.x / slices, sl = blockIdx.x % slices;
+    const long per = (S + slices - 1) / slices;
+    const long v0 = sl * per, v1 = v0 + per < S ? v0 + per : S;
+    extern __shared__ double sh[];  // [2][C]
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sh[c] = 0.0;
+    __syncthreads();
+    const int C4 = C >> 2;
+    const int T = (256 / C4) * C4;  // active threads: whole rows of channel quads
+    if ((int)threadIdx.x < T && v1 > v0) {
+        const long total = (v1 - v0) * C4;
+        const float4* base = reinterpret_cast<const float4*>(x + ((long)n * S + v0) * C);
+        const int q = threadIdx.x % C4;
+        double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+        long e = threadIdx.x;
+        auto acc = [&](const float4& f) {
+            const double a0 = (double)f.x, a1 = (double)f.y, a2 = (double)f.z, a3 = (double)f.w;
+            s1[0] += a0; s2[0] += a0 * a0;
+            s1[1] += a1; s2[1] += a1 * a1;
+            s1[2] += a2; s2[2] += a2 * a2;
+            s1[3] += a3; s2[3] += a3 * a3;
+        };
+        for (; e + 3L * T < total; e += 4L * T) {
+            float4 f0 = __ldg(base + e);
+            const float4 f1 = __ldg(base + e + T), f2 = __ldg(base + e + 2L * T), f3 = __ldg(base + e + 3L * T);
+            // ptxas sinks each load to right above its first use (one load in flight per thread) to save registers; a
+            // value-preserving dependency of the first use on ALL four loads keeps them in flight together
+            f0.x = fmaf(0.f, f1.w, fmaf(0.f, f2.w, fmaf(0.f, f3.w, f0.x)));
+            acc(f0); acc(f1); acc(f2); acc(f3);
+        }
+        for (; e < total; e += T) acc(__ldg(base + e));
+        if (C4 <= 32 && (32 % C4) == 0) {
+            // T is a multiple of 32 here: lanes l, l + C4, ... of a warp hold the same quad - fold them with shuffles
+            for (int o = 16; o >= C4; o >>= 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+                    s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+                }
+            }
+            if ((int)(threadIdx.x & 31) < C4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    atomicAdd(&sh[4 * q + j], s1[j]);
+                    atomicAdd(&sh[C + 4 * q + j], s2[j]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(&sh[4 * q + j], s1[j]);
+                atomicAdd(&sh[C + 4 * q + j], s2[j]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(&sums[((long)n * c_tot + c_off + c) * 2], sh[c] * weight);
+        atomicAdd(&sums[((long)n * c_tot + c_off + c) * 2 + 1], sh[C + c] * weight);
+    }
+}
+
+// The same reduction fed by bulk copies (cp.async.bulk global -> shared, mbarrier completion): the CTA's slice streams
+// through a two-stage ring of 16 KiB chunks that one thread keeps full, the 256 threads reduce each chunk from shared
+// memory (conflict-free 16-byte reads).  No load sits in a register while it is in flight, so neither the register
+// allocator nor the instruction scheduler decides how many bytes an SM has outstanding: up to six CTAs x 32 KiB.
+constexpr int GN_CHUNK4 = 1024, GN_STAGES = 2;  // float4s per stage
+__global__ void __launch_bounds__(256) cl_gn_partial_bulk_kernel(const float* __restrict__ x, long S, int C, int slices, double weight,
+                                                                 int c_off, int c_tot, double* __restrict__ sums) {
+    extern __shared__ __align__(128) uint8_t gn_smem[];
+    const float4* buf = reinterpret_cast<const float4*>(gn_smem);                              // [GN_STAGES][GN_CHUNK4]
+    const uint32_t bar0 = smem_u32(gn_smem + (size_t)GN_STAGES * GN_CHUNK4 * 16);
+    const uint32_t sbuf = smem_u32(gn_smem);
+    const int n = blockIdx.x / slices, sl = blockIdx.x % slices;
+    const long per = (S + slices - 1) / slices;
+    const long v0 = sl * per, v1 = v0 + per < S ? v0 + per : S;
+    const int C4 = C >> 2;
+    const int T = (256 / C4) * C4;               // active threads: whole rows of channel quads
+    const int chunk4 = (GN_CHUNK4 / C4) * C4;    // chunks start on a row boundary: a thread keeps ONE quad
+    const long total4 = v1 > v0 ? (v1 - v0) * C4 : 0;
+    const int n_chunks = (int)((total4 + chunk4 - 1) / chunk4);
+    const float4* base = reinterpret_cast<const float4*>(x + ((long)n * S + v0) * C);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int st = 0; st < GN_STAGES; ++st) mbar_init(bar0 + 8 * st, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int i) {
+        const int st = i % GN_STAGES;
+        const long left = total4 - (long)i * chunk4;
+        const uint32_t bytes = (uint32_t)(left < chunk4 ? left : chunk4) * 16u;
+        mbar_arrive_expect_tx(bar0 + 8 * st, bytes);
+        bulk_g2s(sbuf + (uint32_t)st * GN_CHUNK4 * 16u, base + (long)i * chunk4, bytes, bar0 + 8 * st);
+    };
+    if (tid == 0)
+        for (int i = 0; i < GN_STAGES && i < n_chunks; ++i) issue(i);
+    double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = 0; i < n_chunks; ++i) {
+        const int st = i % GN_STAGES;
+        mbar_wait(bar0 + 8 * st, (uint32_t)(i / GN_STAGES) & 1u);
+        const long left = total4 - (long)i * chunk4;
+        const int n4 = (int)(left < chunk4 ? left : chunk4);
+        const float4* b = buf + st * GN_CHUNK4;
+        if (tid < T) {
+#pragma unroll 4
+            for (int f = tid; f < n4; f += T) {
+                const float4 v = b[f];
+                const double a0 = (double)v.x, a1 = (double)v.y, a2 = (double)v.z, a3 = (double)v.w;
+                s1[0] += a0; s2[0] += a0 * a0;
+                s1[1] += a1; s2[1] += a1 * a1;
+                s1[2] += a2; s2[2] += a2 * a2;
+                s1[3] += a3; s2[3] += a3 * a3;
+            }
+        }
+        __syncthreads();  // the stage is consumed: refill it
+        if (tid == 0 && i + GN_STAGES < n_chunks) issue(i + GN_STAGES);
+    }
+    // Per-thread sums -> per-channel sums without shared-memory atomics (fp64 atomicAdd on shared memory is a CAS loop):
+    // "owners" park their 8 sums in slots of the (consumed) chunk ring, slot % C4 == the owner's quad; thread t < 2C
+    // then adds up the slots of its channel.
+    double* part = reinterpret_cast<double*>(gn_smem);  // [owners][8]
+    int n_owners = 0;
+    if (n_chunks > 0) {
+        const bool fold = C4 <= 32 && (32 % C4) == 0;   // T = 256: lanes l, l + C4, ... of a warp hold the same quad
+        if (fold) {
+            for (int o = 16; o >= C4; o >>= 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+                    s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+                }
+            }
+        }
+        n_owners = fold ? 8 * C4 : T;
+        const int slot = fold ? ((tid & 31) < C4 ? (tid >> 5) * C4 + (tid & 31) : -1) : (tid < T ? tid : -1);
+        if (slot >= 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                part[slot * 8 + j] = s1[j];
+                part[slot * 8 + 4 + j] = s2[j];
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < 2 * C && n_owners > 0; t += blockDim.x) {
+        const int which = t >= C, c = which ? t - C : t, q = c >> 2, j = c & 3;
+        double acc = 0.0;
+        for (int k = q; k < n_owners; k += C4) acc += part[k * 8 + which * 4 + j];
+        atomicAdd(&sums[((long)n * c_tot + c_off + c) * 2 + which], acc * weight);
+    }
+}
+
+// Small samples (one CTA per sample is mostly launch, barrier and reduction latency: 0.3 - 1.7 TB/s on the 4^3 and 2^3
+// levels): one WARP per sample, eight float4 loads in flight per lane, no shared memory and no block barrier.  Needs
+// 32 % (C / 4) == 0 so that a lane keeps one channel quad.
+template <int U>
+__device__ __forceinline__ void gn_warp_batch(const float4* __restrict__ p, double (&s1)[4], double (&s2)[4]) {
+    float4 v[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) v[k] = __ldg(p + 32 * k);
+    // value-preserving dependency of the first use on all U loads (see cl_gn_partial_vec4_kernel)
+    float d = v[0].x;
+#pragma unroll
+    for (int k = 1; k < U; ++k) d = fmaf(0.f, v[k].w, d);
+    v[0].x = d;
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+        const double a0 = (double)v[k].x, a1 = (double)v[k].y, a2 = (double)v[k].z, a3 = (double)v[k].w;
+        s1[0] += a0; s2[0] += a0 * a0;
+        s1[1] += a1; s2[1] += a1 * a1;
+        s1[2] += a2; s2[2] += a2 * a2;
+        s1[3] += a3; s2[3] += a3 * a3;
+    }
+}
+
+// direct != 0: this launch is the only writer of its (sample, channel) sums - plain stores, no memset needed before.
+__global__ void __launch_bounds__(256) cl_gn_partial_warp_kernel(const float* __restrict__ x, long S, int C, long N, double weight,
+                                                                 int c_off, int c_tot, double* __restrict__ sums, int direct) {
+    const long n = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    const int C4 = C >> 2;
+    const long total4 = S * C4;
+    const float4* base = reinterpret_cast<const float4*>(x + n * S * C);
+    double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+    long f = lane;
+    for (; f + 7 * 32 < total4; f += 8 * 32) gn_warp_batch<8>(base + f, s1, s2);
+    if (f + 3 * 32 < total4) { gn_warp_batch<4>(base + f, s1, s2); f += 4 * 32; }
+    if (f + 32 < total4) { gn_warp_batch<2>(base + f, s1, s2); f += 2 * 32; }
+    if (f < total4) gn_warp_batch<1>(base + f, s1, s2);
+    for (int o = 16; o >= C4; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+        }
+    }
+    if (lane < C4) {
+        double* dst = sums + (n * c_tot + c_off + 4 * lane) * 2;
+        if (direct) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(dst + 2 * j) = make_double2(s1[j] * weight, s2[j] * weight);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(dst + 2 * j, s1[j] * weight);
+                atomicAdd(dst + 2 * j + 1, s2[j] * weight);
+            }
+        }
     }
 }
 
@@ -562,19 +781,44 @@ extern "C" int rf_cl_gn_stats(const float* x, const float* x2, int C2, const flo
     RF_CHECK_ARG(C2 == 0 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "rf_cl_gn_stats: upsampled input needs even extents");
     cudaStream_t s = (cudaStream_t)stream;
     double* sums = (double*)workspace;
-    RF_CUDA_OK(cudaMemsetAsync(sums, 0, rf_cl_gn_stats_workspace_bytes(N, C), s));
     const long S = (long)D * H * W;
+    static const int mode = [] { const char* e = getenv("RF_GN_MODE"); return e ? atoi(e) : 2; }();  // tuning aid: 0 scalar, 1 float4 loads, 2 warp per small sample / bulk copies, 3 bulk copies
+    // many small samples: one warp per sample (a lane must keep one channel quad: 32 % (C / 4) == 0)
+    auto warp_ok = [&](const float* src, long Ssrc, int Csrc) {
+        const int C4src = Csrc >> 2;
+        return mode == 2 && Csrc > 0 && (Csrc & 3) == 0 && C4src <= 32 && (32 % C4src) == 0 && ((uintptr_t)src & 15) == 0 &&
+               N >= 148 * 8 && Ssrc * Csrc * 4 <= 64 * 1024;
+    };
+    const int C1 = C - C2;
+    // every (sample, channel) sum has exactly one writer when all sources take the warp kernel: plain stores, no memset
+    const bool direct = (C1 == 0 || warp_ok(x, S, C1)) && (C2 == 0 || warp_ok(x2, S / 8, C2));
+    if (!direct) RF_CUDA_OK(cudaMemsetAsync(sums, 0, rf_cl_gn_stats_workspace_bytes(N, C), s));
     auto launch = [&](const float* src, long Ssrc, int Csrc, double weight, int c_off) -> int {
         // enough CTAs to fill the chip, but at least ~4k elements per CTA
-        long slices = (148L * 4 + N - 1) / N;
+        long slices = (148L * 8 + N - 1) / N;
         const long max_slices = (Ssrc * Csrc + 4095) / 4096;
         if (slices > max_slices) slices = max_slices;
         if (slices < 1) slices = 1;
+        if (warp_ok(src, Ssrc, Csrc)) {
+            cl_gn_partial_warp_kernel<<<(unsigned)rf_cdivl((long)N * 32, 256), 256, 0, s>>>(src, Ssrc, Csrc, N, weight, c_off, C, sums, direct ? 1 : 0);
+            RF_LAUNCH_OK("cl_gn_partial_warp_kernel");
+            return 0;
+        }
+        if (mode >= 2 && (Csrc & 3) == 0 && Csrc <= 512 && ((uintptr_t)src & 15) == 0) {
+            const size_t smem = (size_t)GN_STAGES * GN_CHUNK4 * 16 + 8 * GN_STAGES;
+            cl_gn_partial_bulk_kernel<<<(unsigned)(N * slices), 256, smem, s>>>(src, Ssrc, Csrc, (int)slices, weight, c_off, C, sums);
+            RF_LAUNCH_OK("cl_gn_partial_bulk_kernel");
+            return 0;
+        }
+        if (mode >= 1 && (Csrc & 3) == 0 && Csrc <= 1024 && ((uintptr_t)src & 15) == 0) {
+            cl_gn_partial_vec4_kernel<<<(unsigned)(N * slices), 256, 2 * Csrc * sizeof(double), s>>>(src, Ssrc, Csrc, (int)slices, weight, c_off, C, sums);
+            RF_LAUNCH_OK("cl_gn_partial_vec4_kernel");
+            return 0;
+        }
         cl_gn_partial_kernel<<<(unsigned)(N * slices), 256, 2 * Csrc * sizeof(double), s>>>(src, Ssrc, Csrc, (int)slices, weight, c_off, C, sums);
         RF_LAUNCH_OK("cl_gn_partial_kernel");
         return 0;
     };
-    const int C1 = C - C2;
     if (C1 > 0) { const int rc = launch(x, S, C1, 1.0, 0); if (rc) return rc; }
     if (C2 > 0) { const int rc = launch(x2, S / 8, C2, 8.0, C1); if (rc) return rc; }
     cl_gn_finalize_kernel<<<rf_cdiv((long)N * C, 256), 256, 0, s>>>(sums, gamma, gn_mu, gn_a, N, C, groups, (double)S, eps);

@@ -101,12 +101,27 @@ class PatchedAttentionBlock(nn.Module):
         return ops.attention_features(x_predicted, x_target, occupancy, ab._branch(ab.theta), ab._branch(ab.phi),
                                       self.patch_extent, normalize=ab.normalize)
 
-    def forward(self, x_predicted, x_retrieved, gumbel_noise=None):
+    def forward(self, x_predicted, x_retrieved, gumbel_noise=None, patch_grid=1, out_channels_last=False):
         """x_predicted [B,F,S,S,S], x_retrieved [B*K,F,S,S,S] -> [B,F,S,S,S].
         In retrieval (Gumbel) mode the noise [B*R^3, K] may be injected; when it
-        is not, it is drawn on the device as torch's gumbel_softmax does."""
+        is not, it is drawn on the device as torch's gumbel_softmax does.
+        Inference shortcuts (not in the reference's signature): patch_grid = P > 1 takes the retrieval U-Net's
+        un-folded patches [B*K*P^3,F,S/P,S/P,S/P] (the Fold3D of train_refinement.py:112 becomes index arithmetic),
+        out_channels_last returns [B,S,S,S,F] for the decoder's channels-last path."""
         ab = self.attention_blocks_layer
         K = self.num_nearest_neighbors
+        if patch_grid > 1 or out_channels_last:
+            if ops.grad_needed(x_predicted, x_retrieved, *ab.parameters()):
+                raise ValueError("patch_grid / out_channels_last are inference shortcuts; fold the patches for training")
+            if x_retrieved.shape[0] != x_predicted.shape[0] * K * patch_grid ** 3:
+                raise ValueError(f"x_retrieved has {x_retrieved.shape[0]} patches, expected B*K*P^3")
+            mode = 1 if ab.retrieval_mode else 0
+            if mode == 1 and gumbel_noise is None:
+                rows = x_predicted.shape[0] * self.num_patch_x ** 3
+                gumbel_noise = -torch.empty(rows, K, device=x_predicted.device, dtype=torch.float32).exponential_().log()
+            return ops.attention_fuse(x_predicted, x_retrieved, ab._branch(ab.theta), ab._branch(ab.phi), self.patch_extent, K,
+                                      normalize=ab.normalize, mode=mode, blend=ab.blend_mode, gumbel_noise=gumbel_noise,
+                                      patch_grid=patch_grid, out_channels_last=out_channels_last)
         if x_retrieved.shape[0] != x_predicted.shape[0] * K:
             raise ValueError(f"x_retrieved has {x_retrieved.shape[0]} volumes, expected B*K = {x_predicted.shape[0] * K}")
         if x_predicted.shape[2] != self.num_patch_x * self.patch_extent:

@@ -73,10 +73,21 @@ class Superresolution08FinalDecoder(RfModule):
             nn.Tanh(),
         ])
 
-    def forward(self, x):
+    def tc_path(self, nf):
+        """True when forward() takes the channels-last tensor-core path (and therefore accepts channels-last input)."""
+        from . import unet as U
+        return bool(U.USE_TENSOR_CORES and self.network[0].basic_module.tc_ok(0, nf))
+
+    def forward(self, x, channels_last_input=False):
+        """channels_last_input: x is [B,S,S,S,nf] (the attention's channels-last result); inference only."""
         from . import unet as U
         head = self.network[1]
         nf = head.in_channels
+        if channels_last_input:
+            if not (x.is_cuda and self.tc_path(nf)) or ops.grad_needed(x, *self.parameters()):
+                raise ValueError("channels-last decoder input needs the tensor-core inference path")
+            h = self.network[0].forward_cl(x)
+            return ops.cl_pointwise_head(h, head.weight, head.bias, act=ops.ACT_TANH)
         if ops.grad_needed(x, *self.parameters()):  # training: DoubleConv + (1x1x1 conv, bias, tanh) as differentiable ops
             from ..autograd import ConvGnAct
             h = self.network[0](x)

@@ -1040,28 +1040,36 @@ def _img_array(branch):
     return ptr_array([im.data_ptr() for im in branch[2]])
 
 
-def attention_fuse(x_back, x_retr, theta, phi, E, K, normalize=True, mode=0, blend=True, gumbel_noise=None):
-    """model/attention.py:141-157. theta/phi: (4 wt [in,out], 4 biases[, 4 tensor-core weight images])."""
+def attention_fuse(x_back, x_retr, theta, phi, E, K, normalize=True, mode=0, blend=True, gumbel_noise=None, patch_grid=1,
+                   out_channels_last=False):
+    """model/attention.py:141-157. theta/phi: (4 wt [in,out], 4 biases[, 4 tensor-core weight images]).
+    patch_grid P > 1: x_retr is the retrieval U-Net's un-folded patch batch [B*K*P^3, nf, S/P,S/P,S/P] (Fold3D's input,
+    train_refinement.py:112); out_channels_last: the result is [B,S,S,S,nf], the decoder's channels-last operand
+    (rf_attention_fuse_patched_fwd)."""
     _forward_only(x_back, x_retr)
     x_back = _dev(x_back, name="x_predicted")
     x_retr = _dev(x_retr, name="x_retrieved")
     B, nf, S = x_back.shape[0], x_back.shape[1], x_back.shape[2]
-    assert x_retr.shape[0] == B * K and x_retr.shape[1] == nf and x_retr.shape[2] == S
+    P = max(1, int(patch_grid))
+    assert S % P == 0 and x_retr.shape[0] == B * K * P ** 3 and x_retr.shape[1] == nf and x_retr.shape[2] == S // P
     L = _lib.lib()
     ws_bytes = L.rf_attention_workspace_bytes(B, nf, S, E, K)
     ws = torch.empty(ws_bytes, device=x_back.device, dtype=torch.uint8)
-    out = torch.empty_like(x_back)
+    out = (torch.empty((B, S, S, S, nf), device=x_back.device, dtype=torch.float32) if out_channels_last
+           else torch.empty_like(x_back))
     if gumbel_noise is not None:
         gumbel_noise = _dev(gumbel_noise, name="gumbel_noise")
     with torch.cuda.device(x_back.device), _timed("rf_attention_fuse_fwd", nbytes=(K + 2.0) * nf * S ** 3 * 4 * B):
-        check(L.rf_attention_fuse_fwd(x_back.data_ptr(), x_retr.data_ptr(),
-                                      ptr_array([w.data_ptr() for w in theta[0]]),
-                                      ptr_array([b.data_ptr() for b in theta[1]]),
-                                      ptr_array([w.data_ptr() for w in phi[0]]),
-                                      ptr_array([b.data_ptr() for b in phi[1]]), _img_array(theta), _img_array(phi),
-                                      _ptr(gumbel_noise), out.data_ptr(), B, nf, S, E, K, int(bool(normalize)), int(mode), int(bool(blend)), ws.data_ptr(),
-                                      ws_bytes, _stream(x_back)), "rf_attention_fuse_fwd")
-    _count(12)
+        check(L.rf_attention_fuse_patched_fwd(x_back.data_ptr(), x_retr.data_ptr(),
+                                              ptr_array([w.data_ptr() for w in theta[0]]),
+                                              ptr_array([b.data_ptr() for b in theta[1]]),
+                                              ptr_array([w.data_ptr() for w in phi[0]]),
+                                              ptr_array([b.data_ptr() for b in phi[1]]), _img_array(theta), _img_array(phi),
+                                              _ptr(gumbel_noise), out.data_ptr(), B, nf, S, E, K, int(bool(normalize)), int(mode),
+                                              int(bool(blend)), P, int(bool(out_channels_last)), ws.data_ptr(), ws_bytes,
+                                              _stream(x_back)), "rf_attention_fuse_patched_fwd")
+    n_mlp = 1 if (len(theta) > 2 and theta[2] is not None) else 4   # launches per MLP: fused chain or four linears
+    _count(2 + 2 * n_mlp + 1 + (0 if out_channels_last else 1))
     return out
 
 

@@ -258,8 +258,11 @@ class RefinementPipeline(RetrievalPipeline):
             x = self.patched_attention_block(x_back, x_retr, gumbel_noise)
             return self.decoder(x), x_back, x_retr, x
 
-    def refine(self, x_in, retrieval, gumbel_noise=None):
-        """x_in [B,1,s,s,s] normalised, retrieval [B,K',64,64,64] normalised -> pred [B,1,64,64,64] in [-1,1]."""
+    def refine(self, x_in, retrieval, gumbel_noise=None, intermediates=True):
+        """x_in [B,1,s,s,s] normalised, retrieval [B,K',64,64,64] normalised -> pred [B,1,64,64,64] in [-1,1].
+        Returns (pred, x_back, x_retr, x_attended).  intermediates=False (inference: refine_graphed, infer*): the
+        Fold3D before the attention and the Fold3D + layout change after it are folded into the attention call
+        (rf_attention_fuse_patched_fwd) and x_retr / x_attended are returned as None; pred is bit-identical."""
         nf = self.retrieval_backbone.nf
         B, S = retrieval.shape[0], retrieval.shape[2]
         # the input U-Net (a few dozen tiny launches on B chunks) and the retrieval U-Net are independent until the
@@ -275,6 +278,13 @@ class RefinementPipeline(RetrievalPipeline):
         retr = retrieval[:, :self.K].reshape(B * self.K, 1, S, S, S)   # get_retrievals (:255-257)
         patches = ops.unfold3d(retr, 16)                                # Unfold3D(16, 1) (:34)
         feats = self.retrieval_backbone(patches)                        # [B*K*64, nf, 8,8,8]
+        if (not intermediates and self.decoder.tc_path(nf) and feats.is_cuda
+                and not ops.grad_needed(x_in, retrieval, feats, x_back, *self.patched_attention_block.parameters(),
+                                        *self.decoder.parameters())):
+            cur.wait_stream(side)
+            x_back.record_stream(cur)
+            x_cl = self.patched_attention_block(x_back, feats, gumbel_noise, patch_grid=4, out_channels_last=True)
+            return self.decoder(x_cl, channels_last_input=True), x_back, None, None
         x_retr = ops.fold3d(feats, 4, 8, nf)                            # Fold3D(4, 8, nf) (:37)
         cur.wait_stream(side)
         x_back.record_stream(cur)
@@ -299,7 +309,7 @@ class RefinementPipeline(RetrievalPipeline):
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):  # warm-up: weight images, function attributes, allocator, operand planes
                 for _ in range(2):
-                    self.refine(sx, sr)
+                    self.refine(sx, sr, intermediates=False)
             torch.cuda.current_stream(self.device).wait_stream(side)
             for _ in range(3):
                 if self._graphs_gen != ops.persistent_generation():
@@ -308,7 +318,7 @@ class RefinementPipeline(RetrievalPipeline):
                     self._graphs_gen = ops.persistent_generation()
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    out = self.refine(sx, sr)[0]
+                    out = self.refine(sx, sr, intermediates=False)[0]
                 if self._graphs_gen == ops.persistent_generation():  # nothing was freed while capturing
                     self._graphs[key] = (graph, sx, sr, out)
                     break
@@ -351,7 +361,7 @@ class RefinementPipeline(RetrievalPipeline):
             if graphed:
                 pred[lo:hi].copy_(self.refine_graphed(x_in[lo:hi], retr[lo:hi]))
             else:
-                pred[lo:hi].copy_(self.refine(x_in[lo:hi], retr[lo:hi])[0])
+                pred[lo:hi].copy_(self.refine(x_in[lo:hi], retr[lo:hi], intermediates=False)[0])
         mark()
         return pred
 

@@ -603,6 +603,38 @@ def test_attention(dev, nf, K, mode):
         assert np.array_equal(of.cpu().numpy(), g[tag + ".feat_occ"])
 
 
+@pytest.mark.parametrize("nf,K,mode,B,P,S", [(16, 4, 0, 3, 4, 32), (12, 8, 1, 2, 4, 32), (16, 16, 0, 1, 4, 32), (8, 2, 0, 2, 2, 8),
+                                             (16, 4, 0, 2, 1, 32)])
+def test_attention_on_unfolded_patches_channels_last(dev, nf, K, mode, B, P, S):
+    """rf_attention_fuse_patched_fwd: the Fold3D(P, S/P, nf) of train_refinement.py:112 taken as index arithmetic on the
+    retrieval U-Net's patch batch, and the result stored channels-last for the decoder - bit-identical to
+    Fold3D -> PatchedAttentionBlock.forward -> permute (same MLP rows, same score / blend arithmetic, other row order).
+    Covers the dedicated 8^3-patch unfold (S/P = 8), the generic one (S/P = 4), K above the prefetching variants, the
+    Gumbel mode and P = 1 (channels-last store only)."""
+    from retrieval_fuse_b200 import ops
+    from retrieval_fuse_b200.model import get_attention_block
+    E = 2
+    cfg = dict(nf=nf, attn_patch_extent=4, K=K, attn_normalize=True, attn_use_switching=True, attn_retrieval_mode=bool(mode),
+               attn_no_output_mapping=True, attn_blend=True, attn_num_patch=S // E)
+    m, _ = load(get_attention_block(cfg), O.attention_shapes(nf, E), dev)
+    g = torch.Generator().manual_seed(nf * 100 + K * 10 + P)
+    xb = torch.randn(B, nf, S, S, S, generator=g).to(dev)
+    feats = torch.randn(B * K * P ** 3, nf, S // P, S // P, S // P, generator=g).to(dev)
+    folded = ops.fold3d(feats, P, S // P, nf) if P > 1 else feats
+    if P > 1:  # a candidate that equals the prediction on part of the volume: scores near 1, the switch opens
+        folded[1, :, : S // 2] = xb[0, :, : S // 2]
+        feats = ops.unfold3d(folded, S // P)
+    noise = (-torch.empty(B * (S // E) ** 3, K).exponential_(generator=g).log()).to(dev) if mode else None
+    want = m(xb, folded, noise)
+    got = m(xb, feats, noise, patch_grid=P, out_channels_last=True)
+    assert got.shape == (B, S, S, S, nf)
+    assert torch.equal(got.permute(0, 4, 1, 2, 3), want), f"max |diff| {float((got.permute(0, 4, 1, 2, 3) - want).abs().max()):.2e}"
+    if P > 1:
+        got2 = m(xb, feats, noise, patch_grid=P)
+        assert torch.equal(got2, want)
+    assert float((want - xb).abs().max()) > 1e-3  # the attention did blend something in
+
+
 def test_attention_block_forward_on_sub_patches(dev):
     """AttentionBlock.forward(x, p) (model/attention.py:84-113) called directly on unfolded sub-patches, as
     PatchedAttentionBlock does internally: x [b, C, 2,2,2], p [b, K, C, 2,2,2]; K must match the configuration."""
@@ -670,6 +702,49 @@ def test_refine_full_forward(dev):
     assert ours32 <= 2 * ref_noise + 1e-5, f"fp32 path |ours-fp64| {ours32:.3e} vs reference's fp32 noise {ref_noise:.3e}"
     close(pipe.pred_to_df(pred32), O.network_pred_to_df(torch.from_numpy(g["pred"]), trunc), what="TSDF (df units), fp32 path")
     print(f"refine_full: df err {df_err:.2e}, tanh-domain |ours-fp64| tc {ours:.2e} / fp32 {ours32:.2e}, reference fp32 noise {ref_noise:.2e}")
+
+
+def test_refine_inference_shortcut_is_bit_identical(dev):
+    """RefinementPipeline.refine(intermediates=False) - what refine_graphed / infer* run: no Fold3D before the attention,
+    no Fold3D + layout change after it - returns the same bits as the module-by-module forward."""
+    from retrieval_fuse_b200.pipeline import FRONT3D_SR, RefinementPipeline
+    pipe = RefinementPipeline(FRONT3D_SR, bank=None, device=dev, weight_seed=7)
+    g = torch.Generator().manual_seed(11)
+    x_in = torch.randn(3, 1, 8, 8, 8, generator=g).to(dev)
+    retr = (torch.randn(3, 4, 64, 64, 64, generator=g) * 0.5).to(dev)
+    want = pipe.refine(x_in, retr)
+    got = pipe.refine(x_in, retr, intermediates=False)
+    assert got[2] is None and got[3] is None
+    assert torch.equal(got[0], want[0]), f"max |diff| {float((got[0] - want[0]).abs().max()):.2e}"
+    assert torch.equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("N,S,C1,C2", [(5, 8, 16, 0), (3, 8, 32, 64), (2, 16, 8, 0), (7, 4, 56, 0), (2, 32, 12, 0), (3, 2, 128, 0),
+                                       (1, 64, 16, 0), (4, 8, 6, 0)])
+def test_groupnorm_statistics_vector_loads(dev, N, S, C1, C2):
+    """model/unet.py:79-100 GroupNorm statistics on channels-last tensors (rf_cl_gn_stats): the float4 reduction
+    (channels a multiple of 4, incl. the virtual upsample + concat of a join) against an fp64 evaluation."""
+    from retrieval_fuse_b200 import ops
+    g = torch.Generator().manual_seed(N * 1000 + S * 10 + C1)
+    x = (torch.randn(N, S, S, S, C1, generator=g) * 1.7 + 0.3)
+    C = C1 + C2
+    groups = next(k for k in (8, 4, 2, 1) if C % k == 0)  # groups may straddle the two sources (96 = 32 + 64 in 8 groups)
+    gamma = torch.rand(C, generator=g) + 0.5
+    full = x.permute(0, 4, 1, 2, 3).double()
+    x2 = None
+    if C2:
+        x2 = torch.randn(N, S // 2, S // 2, S // 2, C2, generator=g) * 0.6 - 0.2
+        up = torch.nn.functional.interpolate(x2.permute(0, 4, 1, 2, 3).double(), scale_factor=2, mode="nearest")
+        full = torch.cat([full, up], 1)
+    mu, a = ops.cl_gn_stats(x.to(dev), gamma.to(dev), groups, 1e-5, x2=None if x2 is None else x2.to(dev))
+    fg = full.reshape(N, groups, -1)
+    mean = fg.mean(-1)
+    rstd = 1.0 / torch.sqrt(fg.var(-1, unbiased=False) + 1e-5)
+    cpg = C // groups
+    want_mu = mean.repeat_interleave(cpg, 1)
+    want_a = rstd.repeat_interleave(cpg, 1) * gamma.double()[None]
+    assert float((mu.cpu().double() - want_mu).abs().max()) <= 2e-6
+    assert float(((a.cpu().double() - want_a) / want_a).abs().max()) <= 2e-6
 
 
 # --------------------------------------------------------------------------- a10-a12
