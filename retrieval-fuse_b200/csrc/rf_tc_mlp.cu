@@ -76,8 +76,9 @@ struct MlpArgs {
     uint32_t act_bytes, tmem_cols;
 };
 
-// TMEM columns [c0, c1) of the finished layer (bias, activation) -> operand planes, chunks from 0
-__device__ __forceinline__ void convert_slab(const MlpArgs& a, int l, int c0, int c1, uint32_t tmem_base, uint8_t* act_hi, int tid) {
+// TMEM columns [c0, c1) of the finished layer (bias, activation) -> operand planes, chunks from 0.  Variant of the
+// one-CTA-per-SM kernel (168 registers): the block's 64 biases are prefetched next to the TMEM loads.
+__device__ __forceinline__ void convert_slab_prefetch(const MlpArgs& a, int l, int c0, int c1, uint32_t tmem_base, uint8_t* act_hi, int tid) {
     const int row = tid & 127, half = tid >> 7, q = (tid >> 5) & 3;
     const float* bias = a.bias[l];
     const int N = a.N[l];
@@ -114,6 +115,53 @@ __device__ __forceinline__ void convert_slab(const MlpArgs& a, int l, int c0, in
             uint32_t h[4], lw[4];
 #pragma unroll
             for (int e = 0; e < 8; e += 2) split_f16x2(v[8 * c + e], v[8 * c + e + 1], h[e >> 1], lw[e >> 1]);
+            uint8_t* p = act_hi + (size_t)(((cb - c0) >> 3) + c) * PLANE + row * 16;
+            *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(p + a.act_bytes) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// TMEM columns [c0, c1) of the finished layer (bias, activation) -> operand planes, chunks from 0
+__device__ __forceinline__ void convert_slab(const MlpArgs& a, int l, int c0, int c1, uint32_t tmem_base, uint8_t* act_hi, int tid) {
+    const int row = tid & 127, half = tid >> 7, q = (tid >> 5) & 3;
+    const float* bias = a.bias[l];
+    const int N = a.N[l];
+    // 64 columns per step: four TMEM loads in flight before the one wait.  The biases are NOT prefetched into registers
+    // next to them (v[64] + bv[64] under the 96-register cap of the two-CTA variant spilled 368 bytes per thread and the
+    // conversions took 12 000 of a tile's 68 000 cycles per layer): each 8-column chunk fetches its two float4s (the same
+    // address in every lane, L1-resident) right where it adds them.
+    const int n_blocks = (c1 - c0 + 63) >> 6;
+    for (int b = half; b < n_blocks; b += 2) {
+        const int cb = c0 + 64 * b;
+        float v[64];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tc_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb + 16 * j), v + 16 * j);
+        tc_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {  // eight 8-channel chunks
+            if (cb + 8 * c >= c1) break;
+            const int cc = cb + 8 * c;
+            float w[8];
+            if (bias && cc + 8 <= N) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cc));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cc + 4));
+                w[0] = v[8 * c] + b0.x; w[1] = v[8 * c + 1] + b0.y; w[2] = v[8 * c + 2] + b0.z; w[3] = v[8 * c + 3] + b0.w;
+                w[4] = v[8 * c + 4] + b1.x; w[5] = v[8 * c + 5] + b1.y; w[6] = v[8 * c + 6] + b1.z; w[7] = v[8 * c + 7] + b1.w;
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) w[t] = v[8 * c + t] + ((bias && cc + t < N) ? __ldg(bias + cc + t) : 0.f);
+            }
+            rf_act_vec(w, a.act, a.slope);
+            if (cc + 8 > N) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (cc + t >= N) w[t] = 0.f;  // padded output channels feed zero weights, keep them finite and zero
+            }
+            uint32_t h[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) split_f16x2(w[e], w[e + 1], h[e >> 1], lw[e >> 1]);
             uint8_t* p = act_hi + (size_t)(((cb - c0) >> 3) + c) * PLANE + row * 16;
             *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(p + a.act_bytes) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -186,6 +234,48 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_mlp_kernel(const MlpArgs a) 
             {
                 const int nch = a.K0p >> 3;
                 const bool vec = (a.ldx & 3) == 0;
+                const bool fast = vec && (a.K0 & 7) == 0 && (long)(tile + 1) * TM <= a.M;  // whole chunks, whole tile
+                if (fast) {
+                    // Four items (eight 16-byte loads) in flight per thread.  ptxas sinks every load to right above its
+                    // first use - the plain loop below runs load -> split -> store one item at a time, 12 100 of a tile's
+                    // 41 600 cycles on the attention shape - so the first split is made to depend on ALL eight loads by a
+                    // value-preserving fma (0 * clamp(v) + x: finite whatever the inputs hold).
+                    for (int i0 = tid; i0 < TM * nch; i0 += 4 * WORKERS) {
+                        float4 v[4][2];
+                        int dst_off[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u * WORKERS;
+                            const bool ok = i < TM * nch;
+                            const int ii = ok ? i : i0;
+                            const int r_lo = ii & 7, c = (ii >> 3) % nch, r_hi = ii / (8 * nch);
+                            const int row = r_hi * 8 + r_lo;
+                            const float* src = a.x + ((long)tile * TM + row) * a.ldx + c * 8;
+                            v[u][0] = __ldg(reinterpret_cast<const float4*>(src));
+                            v[u][1] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                            dst_off[u] = ok ? c * PLANE + row * 16 : -1;
+                        }
+                        float d = v[0][0].x;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (u > 0) d = fmaf(0.f, fminf(fmaxf(v[u][0].w, -1.f), 1.f), d);
+                            d = fmaf(0.f, fminf(fmaxf(v[u][1].w, -1.f), 1.f), d);
+                        }
+                        v[0][0].x = d;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (dst_off[u] < 0) continue;
+                            uint32_t h[4], lw[4];
+                            split_f16x2(v[u][0].x, v[u][0].y, h[0], lw[0]);
+                            split_f16x2(v[u][0].z, v[u][0].w, h[1], lw[1]);
+                            split_f16x2(v[u][1].x, v[u][1].y, h[2], lw[2]);
+                            split_f16x2(v[u][1].z, v[u][1].w, h[3], lw[3]);
+                            uint8_t* p = act_hi + dst_off[u];
+                            *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+                            *reinterpret_cast<uint4*>(p + a.act_bytes) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        }
+                    }
+                } else
 #pragma unroll 4
                 for (int i = tid; i < TM * nch; i += WORKERS) {  // (unrolled: the rows' loads are issued together)
                     const int r_lo = i & 7, c = (i >> 3) % nch, r_hi = i / (8 * nch);
@@ -227,7 +317,8 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_mlp_kernel(const MlpArgs a) 
                 for (int ks0 = 0; ks0 < nks; ks0 += a.act_chunks / 2) {  // slabs of 16 k steps = 256 input channels
                     const int ks1 = min(nks, ks0 + a.act_chunks / 2);
                     if (ks0 > 0) {  // next 256 input channels: still in TMEM as the previous layer's columns
-                        convert_slab(a, l - 1, ks0 * 16, ks1 * 16, tmem_base, act_hi, tid);
+                        if (RES == 1) convert_slab_prefetch(a, l - 1, ks0 * 16, ks1 * 16, tmem_base, act_hi, tid);
+                        else convert_slab(a, l - 1, ks0 * 16, ks1 * 16, tmem_base, act_hi, tid);
                         tc_fence_before();
                         workers_sync();
                         tc_fence_after();
@@ -241,22 +332,35 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_mlp_kernel(const MlpArgs a) 
                         const uint32_t a0 = ((sACT & 0x3FFFFu) >> 4) | ((uint32_t)(PLANE >> 4) << 16);   // LBO = one chunk plane
                         const uint32_t b_lbo = (uint32_t)Np << 16;                    // LBO = Np rows x 16 B
                         const uint32_t d = tmem_u + (uint32_t)(iss * 128);
-                        for (int ks = ks0; ks < ks1; ++ks, ++kt) {
-                            const uint32_t sl = kt % (uint32_t)a.nbw;
-                            mbar_wait_warp(bar_wfull + 8 * sl, (kt / (uint32_t)a.nbw) & 1u);
+                        // Everything a k step needs is carried incrementally (ring slot, its parity, both descriptor words):
+                        // recomputing kt % nbw, the slot address and the layer's widths from the kernel parameters took ~70
+                        // dependent uniform-datapath instructions and three constant loads per step - ~150 cycles per MMA
+                        // against 64 in the tensor pipe, with ONE issuer on the layers of <= 128 columns.
+                        uint32_t nbw = (uint32_t)a.nbw, slot16 = a.slot_bytes >> 4;
+                        uint32_t lo_a = a.act_bytes >> 4, lo_b = (uint32_t)(2 * Np);   // lo blocks: act_bytes / 2 * Np * 16 bytes further
+                        asm volatile("" : "+r"(nbw), "+r"(slot16), "+r"(lo_a), "+r"(lo_b));  // registers, not constant-bank reloads in the loop
+                        const uint32_t db0 = (((sW & 0x3FFFFu) >> 4) | b_lbo) + (uint32_t)(iss * 128);  // (slots never carry into the LBO field)
+                        uint32_t sl = kt % nbw, par = (kt / nbw) & 1u;
+                        uint32_t da = a0, db = db0 + sl * slot16;
+                        uint32_t bar_f = bar_wfull + 8 * sl, bar_e = bar_wempty + 8 * sl;
+                        uint32_t acc = ks0 > 0 ? 1u : 0u;
+                        for (int ks = ks0; ks < ks1; ++ks) {
+                            mbar_wait_warp(bar_f, par);
                             tc_fence_after();
                             if (active) {
-                                const uint32_t da = a0 + (uint32_t)(ks - ks0) * (2u * PLANE >> 4);
-                                const uint32_t db = ((((sW + sl * a.slot_bytes) & 0x3FFFFu) >> 4) | b_lbo) + (uint32_t)(iss * 128);
-                                const uint32_t db_lo = db + (uint32_t)(2 * Np);       // lo block: 2 * Np * 16 bytes further
-                                tc_mma2(d, da, a_hi32, db_lo, b_hi32, idesc, ks > 0 ? 1u : 0u, leader);            // hi * lo
-                                tc_mma2(d, da + (a.act_bytes >> 4), a_hi32, db, b_hi32, idesc, 1u, leader);          // lo * hi
-                                tc_mma2(d, da, a_hi32, db, b_hi32, idesc, 1u, leader);                             // hi * hi
-                                if (leader) tc_commit(bar_wempty + 8 * sl);
+                                tc_mma2(d, da, a_hi32, db + lo_b, b_hi32, idesc, acc, leader);      // hi * lo
+                                tc_mma2(d, da + lo_a, a_hi32, db, b_hi32, idesc, 1u, leader);       // lo * hi
+                                tc_mma2(d, da, a_hi32, db, b_hi32, idesc, 1u, leader);              // hi * hi
+                                if (leader) tc_commit(bar_e);
                             } else if (leader) {
-                                mbar_arrive(bar_wempty + 8 * sl);
+                                mbar_arrive(bar_e);
                             }
+                            acc = 1u;
+                            da += 2u * PLANE >> 4;
+                            ++sl; db += slot16; bar_f += 8; bar_e += 8;
+                            if (sl == nbw) { sl = 0; par ^= 1u; db = db0; bar_f = bar_wfull; bar_e = bar_wempty; }
                         }
+                        kt += (uint32_t)(ks1 - ks0);
                         if (leader) {
                             if (active) tc_commit(bar_mma);
                             else mbar_arrive(bar_mma);
@@ -272,7 +376,8 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_mlp_kernel(const MlpArgs a) 
                 if (dbg) g_mlp_dbg[3 + 3 * l] = clock64();
                 // ---- layer epilogue
                 if (l + 1 < a.n_layers) {
-                    convert_slab(a, l, 0, min(Np, 16 * 16), tmem_base, act_hi, tid);
+                    if (RES == 1) convert_slab_prefetch(a, l, 0, min(Np, 16 * 16), tmem_base, act_hi, tid);
+                    else convert_slab(a, l, 0, min(Np, 16 * 16), tmem_base, act_hi, tid);
                     tc_fence_before();
                     workers_sync();
                     tc_fence_after();
