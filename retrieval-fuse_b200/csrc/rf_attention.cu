@@ -37,6 +37,7 @@ __device__ __forceinline__ float warp_max(float v) {
 struct AttnGeo {
     int P, out_cl, nf, E, Rp;
     FastDiv d_nf, d_E, d_Rp, d_ps;  // ps = Rp / P sub-patches per patch side
+    int pow2, s_nf, s_E, s_Rp, s_ps, s_P;  // all five are powers of two (nf = 16, E = 2, 16^3 sub-patches in 4^3 patches): shifts
 };
 
 // Unfold3D(2, C) of patches [NP, C, 8,8,8] -> rows [NP * 64, C * 8]: one CTA per patch.  Both sides of a patch are ONE
@@ -82,17 +83,31 @@ __global__ void __launch_bounds__(256) attention_epilogue_kernel(const float* __
     const long b = row / rp3;
     unsigned rr = (unsigned)(row % rp3);
     unsigned px = 0, py = 0, pz = 0;
+    // (the index arithmetic of a row is of the order of its ~300 other instructions: shifts where every extent is a
+    // power of two, multiply-high division otherwise)
     if (g.P > 1 || g.out_cl) {
-        unsigned t = rr;
-        pz = fd_divmod(t, g.d_Rp);
-        py = fd_divmod(t, g.d_Rp);
-        px = t;
+        if (g.pow2) {
+            pz = rr & (g.Rp - 1);
+            py = (rr >> g.s_Rp) & (g.Rp - 1);
+            px = rr >> (2 * g.s_Rp);
+        } else {
+            unsigned t = rr;
+            pz = fd_divmod(t, g.d_Rp);
+            py = fd_divmod(t, g.d_Rp);
+            px = t;
+        }
     }
     if (g.P > 1) {
         // candidate rows come from Unfold3D run on the P^3 un-folded patches of each volume: (patch, local sub-patch) order
         const unsigned ps = g.d_ps.d;
-        const unsigned qx = fd_div(px, g.d_ps), qy = fd_div(py, g.d_ps), qz = fd_div(pz, g.d_ps);
-        rr = ((qx * g.P + qy) * g.P + qz) * (ps * ps * ps) + ((px - qx * ps) * ps + (py - qy * ps)) * ps + (pz - qz * ps);
+        if (g.pow2) {
+            const unsigned m = ps - 1;
+            rr = ((((px >> g.s_ps) << g.s_P | (py >> g.s_ps)) << g.s_P | (pz >> g.s_ps)) << (3 * g.s_ps)) |
+                 ((((px & m) << g.s_ps) | (py & m)) << g.s_ps) | (pz & m);
+        } else {
+            const unsigned qx = fd_div(px, g.d_ps), qy = fd_div(py, g.d_ps), qz = fd_div(pz, g.d_ps);
+            rr = ((qx * g.P + qy) * g.P + qz) * (ps * ps * ps) + ((px - qx * ps) * ps + (py - qy * ps)) * ps + (pz - qz * ps);
+        }
     }
     const long prow0 = b * K * rp3 + rr;  // candidate k lives at prow0 + k * rp3
     // channels-last output: the warp's i-th value is element (e, c) = (i / nf, i % nf) of the sub-patch, i.e. feature
@@ -101,18 +116,33 @@ __global__ void __launch_bounds__(256) attention_epilogue_kernel(const float* __
     const long S = (long)g.Rp * g.E;
     auto feat_of = [&](int i) -> int {
         if (!g.out_cl) return i;
+        if (g.pow2) return ((i & (g.nf - 1)) << (3 * g.s_E)) | (i >> g.s_nf);
         const unsigned e = fd_div((unsigned)i, g.d_nf);
         return (int)(((unsigned)i - e * g.nf) * E3 + e);
     };
+    const long out_base = g.out_cl ? (((b * S + px * g.E) * S + py * g.E) * S + pz * g.E) * g.nf : row * (long)V;
     auto out_addr = [&](int i) -> long {
-        if (!g.out_cl) return row * (long)V + i;
-        unsigned e = fd_div((unsigned)i, g.d_nf);
-        const unsigned c = (unsigned)i - e * g.nf;
-        const unsigned ez = fd_divmod(e, g.d_E), ey = fd_divmod(e, g.d_E), ex = e;
-        return ((((b * S + px * g.E + ex) * S + py * g.E + ey) * S + pz * g.E + ez) * g.nf) + c;
+        if (!g.out_cl) return out_base + i;
+        unsigned e, c, ex, ey, ez;
+        if (g.pow2) {
+            e = (unsigned)i >> g.s_nf; c = (unsigned)i & (g.nf - 1);
+            ez = e & (g.E - 1); ey = (e >> g.s_E) & (g.E - 1); ex = e >> (2 * g.s_E);
+        } else {
+            e = fd_div((unsigned)i, g.d_nf);
+            c = (unsigned)i - e * g.nf;
+            ez = fd_divmod(e, g.d_E); ey = fd_divmod(e, g.d_E); ex = e;
+        }
+        return out_base + ((ex * S + ey) * S + ez) * g.nf + c;
     };
     constexpr bool kPrefetch = KT <= 8;
     constexpr int PF = kPrefetch ? KT : 1;
+    // channels-last store of a row that fits the prefetch registers: the loads stay in feature order (one 512-byte run
+    // per vector; reading them in (e, c) order touched every sector of the run four times) and the blended row is
+    // transposed through a per-warp shared-memory line (xor swizzle: conflict-free writes, two-way reads at nf = 16)
+    const bool via_smem = kPrefetch && g.out_cl && V <= 128;
+    __shared__ float tr_line[8][128];
+    float* tr = tr_line[threadIdx.x >> 5];
+    auto swz = [](int v) { return v ^ ((v >> 5) & 7); };
 
     float xv = __ldg(xf + row * FEAT + lane);
     float pvk[KT];
@@ -124,7 +154,7 @@ __global__ void __launch_bounds__(256) attention_epilogue_kernel(const float* __
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int i = lane + 32 * j;
-            const int v = i < V ? feat_of(i) : 0;
+            const int v = i < V ? (via_smem ? i : feat_of(i)) : 0;
             xr[j] = i < V ? __ldg(xrow + v) : 0.f;
 #pragma unroll
             for (int k = 0; k < PF; ++k) pr[k][j] = (k < K && i < V) ? __ldg(pu + (prow0 + (long)k * rp3) * V + v) : 0.f;
@@ -183,7 +213,17 @@ __global__ void __launch_bounds__(256) attention_epilogue_kernel(const float* __
 #pragma unroll
             for (int k = 0; k < PF; ++k)
                 if (k < K) acc = fmaf(wk[k], pr[k][j], acc);
-            if (v < V) orows[out_addr(v)] = blend ? (xr[j] * (1.f - sw) + acc * sw) : (xr[j] + acc * sw);
+            const float o = blend ? (xr[j] * (1.f - sw) + acc * sw) : (xr[j] + acc * sw);
+            if (via_smem) tr[swz(v)] = o;
+            else if (v < V) orows[out_addr(v)] = o;
+        }
+        if (via_smem) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = lane + 32 * j;
+                if (i < V) orows[out_addr(i)] = tr[swz(feat_of(i))];
+            }
         }
         v0 = 128;
     }
@@ -306,6 +346,9 @@ extern "C" int rf_attention_fuse_patched_fwd(const float* x_back, const float* x
     AttnGeo g;
     g.P = P; g.out_cl = out_channels_last ? 1 : 0; g.nf = nf; g.E = E; g.Rp = Rp;
     g.d_nf = make_fastdiv(nf); g.d_E = make_fastdiv(E); g.d_Rp = make_fastdiv(Rp); g.d_ps = make_fastdiv(Rp / P);
+    auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
+    g.s_nf = lg(nf); g.s_E = lg(E); g.s_Rp = lg(Rp); g.s_ps = lg(Rp / P); g.s_P = lg(P);
+    g.pow2 = (g.s_nf >= 0 && g.s_E >= 0 && g.s_Rp >= 0 && g.s_ps >= 0 && g.s_P >= 0) ? 1 : 0;
     float* erows = g.out_cl ? out : ws.orows;  // channels-last: the epilogue stores the volume itself
 #define RF_ATTN_EPI(KT)                                                                                         \
     attention_epilogue_kernel<KT><<<egrid, 256, 0, (cudaStream_t)stream>>>(ws.xf, ws.pf, ws.xu, ws.pu, gumbel_noise, \
