@@ -369,13 +369,17 @@ int rf_attention_fuse_fwd(const float* x_back, const float* x_retr, const float*
  *     Fold3D's input, patches in (PX,PY,PZ) order); Fold3D followed by Unfold3D(E) is a permutation of rows, which
  *     the score / blend stage applies as index arithmetic.
  *   out_channels_last != 0: out is [B,S,S,S,nf] (the decoder's channels-last operand) instead of [B,nf,S,S,S].
- * P <= 1 and out_channels_last == 0 is rf_attention_fuse_fwd. */
+ *   output_mapping != NULL: attn_no_output_mapping = False (model/attention.py:56-57,95,108): g and o are 1x1x1
+ *     convolutions around the weighted sum; both are linear and per voxel, so the caller passes their composition
+ *     {Wo Wg [nf,nf] row-major, Wo bg [nf], bo [nf]} (device pointers in a host array); needs out_channels_last == 0.
+ * P <= 1, out_channels_last == 0 and output_mapping == NULL is rf_attention_fuse_fwd. */
 int rf_attention_fuse_patched_fwd(const float* x_back, const float* x_retr, const float* const* theta_wt_host,
                                   const float* const* theta_b_host, const float* const* phi_wt_host,
                                   const float* const* phi_b_host, const void* const* theta_img_host,
                                   const void* const* phi_img_host, const float* gumbel_noise, float* out, int B, int nf,
                                   int S, int E, int K, int normalize, int mode, int blend, int patch_grid,
-                                  int out_channels_last, void* workspace, size_t workspace_bytes, void* stream);
+                                  int out_channels_last, const float* const* output_mapping, void* workspace,
+                                  size_t workspace_bytes, void* stream);
 /* model/attention.py:132-139 get_features: theta(unfold(x)), phi(unfold(t)),
  * any(occupancy) per sub-patch.  x,t [B,nf,S,S,S]; occ [B,1,S,S,S] uint8;
  * x_feat,p_feat [B*R^3,32]; occ_any [B*R^3] uint8. */

@@ -717,10 +717,15 @@ def final_decoder_forward(x, sd, nf, order="gcr"):
 # ---------------------------------------------------------------------------
 
 
-def attention_shapes(nf, e, cf_feat=32):
-    """PatchedAttentionBlock state_dict with attn_no_output_mapping=True."""
+def attention_shapes(nf, e, cf_feat=32, output_mapping=False):
+    """PatchedAttentionBlock state_dict; output_mapping: attn_no_output_mapping=False adds the g / o 1x1x1
+    convolutions (model/attention.py:56-57)."""
     n_in = nf * e ** 3
     shapes = {"attention_blocks_layer.sig_scale": (1,), "attention_blocks_layer.sig_shift": (1,)}
+    if output_mapping:
+        for m in ("g", "o"):
+            shapes[f"attention_blocks_layer.{m}.weight"] = (nf, nf, 1, 1, 1)
+            shapes[f"attention_blocks_layer.{m}.bias"] = (nf,)
     for br in ("theta", "phi"):
         w = [n_in, 128, 128, 128, cf_feat]  # model/attention.py:35-41
         for i in range(4):
@@ -741,7 +746,8 @@ def _attn_mlp(x, sd, br):
 
 
 def attention_block_forward(x, p, sd, normalize=True, retrieval_mode=False, blend=True, gumbel_noise=None):
-    """model/attention.py:84-113 AttentionBlock.forward with g = o = Identity.
+    """model/attention.py:84-113 AttentionBlock.forward; g = o = Identity unless the state dict holds their 1x1x1
+    convolutions (attn_no_output_mapping=False, :56-57,95,108).
     x: [b, C, e,e,e]; p: [b, k, C, e,e,e].  In retrieval mode the Gumbel noise
     must be supplied ([b,k]); gumbel_softmax(hard=True) forward value is
     y_hard - y_soft + y_soft (torch/nn/functional.py gumbel_softmax)."""
@@ -751,7 +757,12 @@ def attention_block_forward(x, p, sd, normalize=True, retrieval_mode=False, blen
     if normalize:
         xf = F.normalize(xf, dim=1)
         pf = F.normalize(pf, dim=2)
-    g = p.reshape(b, k, -1)
+    mapped = "attention_blocks_layer.g.weight" in sd
+    if mapped:  # g = Conv3d(C, C, 1): per-voxel channel mixing + bias of every candidate (:95)
+        wg, bg = sd["attention_blocks_layer.g.weight"].flatten(1), sd["attention_blocks_layer.g.bias"]
+        g = (torch.einsum("oc,bkcs->bkos", wg, p.reshape(b, k, c, -1)) + bg[None, None, :, None]).reshape(b, k, -1)
+    else:
+        g = p.reshape(b, k, -1)
     scores = torch.einsum("ij,ijk->ik", xf, pf.permute(0, 2, 1))
     switch = F.relu(scores.max(dim=1, keepdim=True).values)  # MaxPool1d(K) over all k, then ReLU (:99)
     if retrieval_mode:
@@ -764,6 +775,9 @@ def attention_block_forward(x, p, sd, normalize=True, retrieval_mode=False, blen
         sharp = (32 * e * e * e) * 4  # cf_feat * e^3 * 4 (:105)
         w = F.softmax(sharp * scores, dim=1)
     ws = torch.einsum("ij,ijk->ik", w, g)
+    if mapped:  # o = Conv3d(C, C, 1) on the weighted sum (:108)
+        wo, bo = sd["attention_blocks_layer.o.weight"].flatten(1), sd["attention_blocks_layer.o.bias"]
+        ws = (torch.einsum("oc,bcs->bos", wo, ws.reshape(b, c, -1)) + bo[None, :, None]).reshape(b, -1)
     xv = x.reshape(b, -1)
     if blend:
         out = xv * (1 - switch) + ws * switch

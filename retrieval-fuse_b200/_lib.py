@@ -125,8 +125,8 @@ PROTOTYPES = {
     "rf_attention_fuse_fwd": (c_int, [c_void_p, c_void_p, _ptr4, _ptr4, _ptr4, _ptr4, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "rf_attention_fuse_patched_fwd": (c_int, [c_void_p, c_void_p, _ptr4, _ptr4, _ptr4, _ptr4, c_void_p, c_void_p, c_void_p, c_void_p,
-                                              c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
-                                              c_void_p]),
+                                              c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                              c_size_t, c_void_p]),
     "rf_attention_features": (c_int, [c_void_p, c_void_p, c_void_p, _ptr4, _ptr4, _ptr4, _ptr4, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "rf_sobel_normals": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),

@@ -165,6 +165,9 @@ def attention_mlp(encoder, x):
 def patched_attention(block, x_predicted, x_retrieved, gumbel_noise=None):
     """Differentiable forward of PatchedAttentionBlock (model/attention.py:141-157)."""
     ab = block.attention_blocks_layer
+    if ab.output_mapping() is not None:
+        raise NotImplementedError("training through attn_no_output_mapping=False (the g / o 1x1x1 convolutions) is not "
+                                  "implemented; the forward is (rf_attention_fuse_patched_fwd)")
     E, K, nf = block.patch_extent, block.num_nearest_neighbors, block.nf
     B, S = x_predicted.shape[0], x_predicted.shape[2]
     Rp = S // E

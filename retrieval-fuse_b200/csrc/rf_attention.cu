@@ -38,6 +38,7 @@ struct AttnGeo {
     int P, out_cl, nf, E, Rp;
     FastDiv d_nf, d_E, d_Rp, d_ps;  // ps = Rp / P sub-patches per patch side
     int pow2, s_nf, s_E, s_Rp, s_ps, s_P;  // all five are powers of two (nf = 16, E = 2, 16^3 sub-patches in 4^3 patches): shifts
+    float* side;  // != NULL (g / o output mapping follows): store the un-blended weighted sum and (switch, sum of weights) per row
 };
 
 // Unfold3D(2, C) of patches [NP, C, 8,8,8] -> rows [NP * 64, C * 8]: one CTA per patch.  Both sides of a patch are ONE
@@ -204,6 +205,11 @@ __global__ void __launch_bounds__(256) attention_epilogue_kernel(const float* __
     float wk[KT];
 #pragma unroll
     for (int k = 0; k < KT; ++k) wk[k] = __shfl_sync(0xffffffffu, w, k);
+    const bool raw = g.side != nullptr;
+    if (raw) {
+        const float sumw = warp_sum(w);
+        if (lane == 0) *reinterpret_cast<float2*>(g.side + 2 * row) = make_float2(sw, sumw);
+    }
     int v0 = 0;
     if (kPrefetch) {
 #pragma unroll
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(256) attention_epilogue_kernel(const float* __
 #pragma unroll
             for (int k = 0; k < PF; ++k)
                 if (k < K) acc = fmaf(wk[k], pr[k][j], acc);
-            const float o = blend ? (xr[j] * (1.f - sw) + acc * sw) : (xr[j] + acc * sw);
+            const float o = raw ? acc : blend ? (xr[j] * (1.f - sw) + acc * sw) : (xr[j] + acc * sw);
             if (via_smem) tr[swz(v)] = o;
             else if (v < V) orows[out_addr(v)] = o;
         }
@@ -234,7 +240,34 @@ __global__ void __launch_bounds__(256) attention_epilogue_kernel(const float* __
         for (int k = 0; k < KT; ++k)
             if (k < K) acc = fmaf(wk[k], __ldg(pu + (prow0 + (long)k * rp3) * V + v), acc);
         const float x = xrow[v];
-        orows[out_addr(i)] = blend ? (x * (1.f - sw) + acc * sw) : (x + acc * sw);
+        orows[out_addr(i)] = raw ? acc : blend ? (x * (1.f - sw) + acc * sw) : (x + acc * sw);
+    }
+}
+
+// model/attention.py:56-57,95,108-109 with attn_no_output_mapping = False: g and o are 1x1x1 convolutions (channel mixing
+// + bias) around the weighted sum.  Both are linear and act per voxel, so o(sum_k w_k g(p_k)) =
+// (Wo Wg) sum_k w_k p_k + (Wo bg) sum_k w_k + bo: the epilogue above leaves the plain weighted sum in orows and
+// (switch, sum_k w_k) in side; this kernel mixes the channels of each row (one warp per row, the row staged in shared
+// memory) and blends.  mix = Wo Wg [nf, nf] row-major, mix_bg = Wo bg [nf], bo [nf].
+__global__ void __launch_bounds__(256) attention_output_mapping_kernel(float* __restrict__ orows, const float* __restrict__ xu,
+                                                                       const float* __restrict__ side, const float* __restrict__ mix,
+                                                                       const float* __restrict__ mix_bg, const float* __restrict__ bo,
+                                                                       long R, int V, int nf, int E3, int blend) {
+    extern __shared__ float map_lines[];
+    const long row = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= R) return;
+    float* line = map_lines + (threadIdx.x >> 5) * V;
+    for (int v = lane; v < V; v += 32) line[v] = orows[row * V + v];
+    __syncwarp();
+    const float2 ss = *reinterpret_cast<const float2*>(side + 2 * row);
+    const float sw = ss.x, sumw = ss.y;
+    for (int v = lane; v < V; v += 32) {
+        const int co = v / E3, e = v - co * E3;
+        float acc = fmaf(__ldg(mix_bg + co), sumw, __ldg(bo + co));
+        for (int c = 0; c < nf; ++c) acc = fmaf(__ldg(mix + co * nf + c), line[c * E3 + e], acc);
+        const float x = __ldg(xu + row * V + v);
+        orows[row * V + v] = blend ? (x * (1.f - sw) + acc * sw) : (x + acc * sw);
     }
 }
 
@@ -309,7 +342,8 @@ extern "C" int rf_attention_fuse_patched_fwd(const float* x_back, const float* x
                                              const float* const* phi_b_host, const void* const* theta_img_host,
                                              const void* const* phi_img_host, const float* gumbel_noise, float* out, int B,
                                              int nf, int S, int E, int K, int normalize, int mode, int blend, int patch_grid,
-                                             int out_channels_last, void* workspace, size_t workspace_bytes, void* stream) {
+                                             int out_channels_last, const float* const* output_mapping_host, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
     RF_CHECK_ARG(x_back && x_retr && out && theta_wt_host && theta_b_host && phi_wt_host && phi_b_host && workspace,
                  "rf_attention_fuse_fwd: null pointer");
     RF_CHECK_ARG(B > 0 && nf > 0 && S > 0 && E > 0 && S % E == 0, "rf_attention_fuse_fwd: bad shape");
@@ -317,6 +351,10 @@ extern "C" int rf_attention_fuse_patched_fwd(const float* x_back, const float* x
     RF_CHECK_ARG(mode == 0 || (mode == 1 && gumbel_noise), "rf_attention_fuse_fwd: retrieval mode needs the Gumbel noise");
     RF_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "rf_attention_fuse_fwd: workspace must be 256-byte aligned");
     const int P = patch_grid < 1 ? 1 : patch_grid;
+    const bool mapped = output_mapping_host != nullptr;  // {Wo Wg [nf,nf], Wo bg [nf], bo [nf]}
+    RF_CHECK_ARG(!mapped || (output_mapping_host[0] && output_mapping_host[1] && output_mapping_host[2] && !out_channels_last),
+                 "rf_attention_fuse_fwd: output mapping needs its three tensors and the NCDHW result layout");
+    RF_CHECK_ARG(!mapped || (size_t)8 * nf * E * E * E * sizeof(float) <= 48 * 1024, "rf_attention_fuse_fwd: rows too long for the output mapping");
     RF_CHECK_ARG(S % P == 0 && (S / P) % E == 0, "rf_attention_fuse_fwd: patch grid %d does not tile S=%d into multiples of E=%d", P, S, E);
     AttnWs ws;
     const size_t need = attn_ws_layout(B, nf, S, E, K, &ws, (char*)workspace);
@@ -349,6 +387,7 @@ extern "C" int rf_attention_fuse_patched_fwd(const float* x_back, const float* x
     auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
     g.s_nf = lg(nf); g.s_E = lg(E); g.s_Rp = lg(Rp); g.s_ps = lg(Rp / P); g.s_P = lg(P);
     g.pow2 = (g.s_nf >= 0 && g.s_E >= 0 && g.s_Rp >= 0 && g.s_ps >= 0 && g.s_P >= 0) ? 1 : 0;
+    g.side = mapped ? ws.ha : nullptr;  // (the hidden-activation buffers are free once both MLPs have run; >= R * 128 floats)
     float* erows = g.out_cl ? out : ws.orows;  // channels-last: the epilogue stores the volume itself
 #define RF_ATTN_EPI(KT)                                                                                         \
     attention_epilogue_kernel<KT><<<egrid, 256, 0, (cudaStream_t)stream>>>(ws.xf, ws.pf, ws.xu, ws.pu, gumbel_noise, \
@@ -359,6 +398,11 @@ extern "C" int rf_attention_fuse_patched_fwd(const float* x_back, const float* x
     else RF_ATTN_EPI(32);
 #undef RF_ATTN_EPI
     RF_LAUNCH_OK("attention_epilogue_kernel");
+    if (mapped) {
+        attention_output_mapping_kernel<<<egrid, 256, (size_t)8 * V * sizeof(float), (cudaStream_t)stream>>>(
+            ws.orows, ws.xu, ws.ha, output_mapping_host[0], output_mapping_host[1], output_mapping_host[2], R, V, nf, E * E * E, blend);
+        RF_LAUNCH_OK("attention_output_mapping_kernel");
+    }
     if (g.out_cl) return 0;
     return rf_fold3d(ws.orows, out, B, nf, Rp, E, stream);
 }
@@ -370,7 +414,7 @@ extern "C" int rf_attention_fuse_fwd(const float* x_back, const float* x_retr, c
                                      int S, int E, int K, int normalize, int mode, int blend, void* workspace,
                                      size_t workspace_bytes, void* stream) {
     return rf_attention_fuse_patched_fwd(x_back, x_retr, theta_wt_host, theta_b_host, phi_wt_host, phi_b_host, theta_img_host,
-                                         phi_img_host, gumbel_noise, out, B, nf, S, E, K, normalize, mode, blend, 1, 0,
+                                         phi_img_host, gumbel_noise, out, B, nf, S, E, K, normalize, mode, blend, 1, 0, nullptr,
                                          workspace, workspace_bytes, stream);
 }
 

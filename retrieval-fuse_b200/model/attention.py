@@ -7,6 +7,32 @@ from .. import ops
 from ._base import RfModule
 
 
+class Conv3dAttentionOutput(nn.Conv3d):
+    """model/attention.py:5-15: the g / o 1x1x1 convolutions of attn_no_output_mapping=False (near-identity init)."""
+
+    def __init__(self, nf_in, nf_out):
+        super().__init__(nf_in, nf_out, kernel_size=1, stride=1, padding=0)
+
+    def reset_parameters(self) -> None:
+        nn.init.dirac_(self.weight)
+        with torch.no_grad():
+            self.weight[:] = self.weight[:] + torch.randn_like(self.weight[:]) * 0.01
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+
+class Conv3dAttentionFeature(nn.Conv3d):
+    """model/attention.py:18-26 (defined by the reference, used by none of its modules)."""
+
+    def __init__(self, nf_in, nf_out):
+        super().__init__(nf_in, nf_out, kernel_size=1, stride=1, padding=0)
+
+    def reset_parameters(self) -> None:
+        nn.init.normal_(self.weight, 0, 0.01)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+
 class AttentionFeatureEncoder(nn.Module):
     """model/attention.py:29-46 (parameter container; the MLP runs inside
     rf_attention_fuse_fwd / rf_attention_features)."""
@@ -28,17 +54,14 @@ class AttentionBlock(RfModule):
     def __init__(self, num_output_channels, patch_extent, K, normalize, use_switching, retrieval_mode,
                  no_output_mapping, blend):
         super().__init__()
-        if not no_output_mapping:
-            raise NotImplementedError("attn_no_output_mapping=False (1x1x1 g/o convs) is not used by any shipped "
-                                      "config and is not implemented by the rf_b200 kernels")
         self.cf_op = num_output_channels
         self.cf_feat = 32
         self.patch_extent = patch_extent
         self.K = K
         self.theta = AttentionFeatureEncoder(num_output_channels, self.cf_feat, patch_extent)
         self.phi = AttentionFeatureEncoder(num_output_channels, self.cf_feat, patch_extent)
-        self.g = nn.Identity()
-        self.o = nn.Identity()
+        self.g = Conv3dAttentionOutput(num_output_channels, self.cf_op) if not no_output_mapping else nn.Identity()
+        self.o = Conv3dAttentionOutput(self.cf_op, num_output_channels) if not no_output_mapping else nn.Identity()
         self.init_scale = 35
         self.init_shift = -27
         # unused in the reference's forward (:97-99) but part of its state_dict
@@ -60,6 +83,21 @@ class AttentionBlock(RfModule):
             imgs = [self._wcache.derived((tag, j), [m.weight], ops.tc_mlp_weight_image) for j, m in enumerate(lin)]
         return [self._wt(m.weight) for m in lin], [m.bias for m in lin], imgs
 
+    def output_mapping(self):
+        """None for g = o = Identity; else (Wo Wg [nf,nf], Wo bg [nf], bo [nf]): both 1x1x1 convolutions are linear and act
+        per voxel, so o(sum_k w_k g(p_k)) = (Wo Wg) sum_k w_k p_k + (Wo bg) sum_k w_k + bo (model/attention.py:95,108)."""
+        if isinstance(self.g, nn.Identity):
+            return None
+        if self.retrieval_mode:
+            # the reference cannot run this combination either (its forward raises): in retrieval mode the weighted sum
+            # stays 2-D (model/attention.py:103, no reshape) and o = Conv3d rejects it
+            raise ValueError("attn_no_output_mapping=False has no retrieval (Gumbel) mode in the reference (model/attention.py:103)")
+
+        def compose(wg, bg, wo, bo):
+            wg2, wo2 = wg.detach().float().flatten(1), wo.detach().float().flatten(1)
+            return ((wo2 @ wg2).contiguous(), (wo2 @ bg.detach().float()).contiguous(), bo.detach().float().contiguous())
+        return self._wcache.derived(("output_mapping",), [self.g.weight, self.g.bias, self.o.weight, self.o.bias], compose)
+
     def forward(self, x, p, gumbel_noise=None):
         """model/attention.py:84-113.  x [b, C, E,E,E] predicted sub-patches, p [b, K, C, E,E,E] their K retrieved
         candidates -> [b, C, E,E,E].  Every sub-patch is handed to rf_attention_fuse_fwd as a volume of edge E (one
@@ -75,7 +113,7 @@ class AttentionBlock(RfModule):
             gumbel_noise = -torch.empty(b, k, device=x.device, dtype=torch.float32).exponential_().log()
         return ops.attention_fuse(x.reshape(b, c, e, e, e), p.reshape(b * k, c, e, e, e), self._branch(self.theta),
                                   self._branch(self.phi), e, k, normalize=self.normalize, mode=mode, blend=self.blend_mode,
-                                  gumbel_noise=gumbel_noise)
+                                  gumbel_noise=gumbel_noise, output_mapping=self.output_mapping())
 
     def get_regularization_losses(self):
         return ((self.sig_scale - self.init_scale) ** 2 + (self.sig_shift - self.init_shift) ** 2) if self.use_switching else 0
@@ -119,9 +157,12 @@ class PatchedAttentionBlock(nn.Module):
             if mode == 1 and gumbel_noise is None:
                 rows = x_predicted.shape[0] * self.num_patch_x ** 3
                 gumbel_noise = -torch.empty(rows, K, device=x_predicted.device, dtype=torch.float32).exponential_().log()
+            if out_channels_last and ab.output_mapping() is not None:
+                raise ValueError("out_channels_last is not available with attn_no_output_mapping=False")
             return ops.attention_fuse(x_predicted, x_retrieved, ab._branch(ab.theta), ab._branch(ab.phi), self.patch_extent, K,
                                       normalize=ab.normalize, mode=mode, blend=ab.blend_mode, gumbel_noise=gumbel_noise,
-                                      patch_grid=patch_grid, out_channels_last=out_channels_last)
+                                      patch_grid=patch_grid, out_channels_last=out_channels_last,
+                                      output_mapping=ab.output_mapping())
         if x_retrieved.shape[0] != x_predicted.shape[0] * K:
             raise ValueError(f"x_retrieved has {x_retrieved.shape[0]} volumes, expected B*K = {x_predicted.shape[0] * K}")
         if x_predicted.shape[2] != self.num_patch_x * self.patch_extent:
@@ -135,7 +176,8 @@ class PatchedAttentionBlock(nn.Module):
             gumbel_noise = -torch.empty(rows, K, device=x_predicted.device, dtype=torch.float32).exponential_().log()
         return ops.attention_fuse(x_predicted, x_retrieved.reshape(-1, self.nf, *x_retrieved.shape[2:]),
                                   ab._branch(ab.theta), ab._branch(ab.phi), self.patch_extent, K,
-                                  normalize=ab.normalize, mode=mode, blend=ab.blend_mode, gumbel_noise=gumbel_noise)
+                                  normalize=ab.normalize, mode=mode, blend=ab.blend_mode, gumbel_noise=gumbel_noise,
+                                  output_mapping=ab.output_mapping())
 
 
 class Fold3D(nn.Module):

@@ -1041,11 +1041,12 @@ def _img_array(branch):
 
 
 def attention_fuse(x_back, x_retr, theta, phi, E, K, normalize=True, mode=0, blend=True, gumbel_noise=None, patch_grid=1,
-                   out_channels_last=False):
+                   out_channels_last=False, output_mapping=None):
     """model/attention.py:141-157. theta/phi: (4 wt [in,out], 4 biases[, 4 tensor-core weight images]).
     patch_grid P > 1: x_retr is the retrieval U-Net's un-folded patch batch [B*K*P^3, nf, S/P,S/P,S/P] (Fold3D's input,
     train_refinement.py:112); out_channels_last: the result is [B,S,S,S,nf], the decoder's channels-last operand
-    (rf_attention_fuse_patched_fwd)."""
+    (rf_attention_fuse_patched_fwd).  output_mapping = (Wo Wg [nf,nf], Wo bg [nf], bo [nf]): the composed g / o 1x1x1
+    convolutions of attn_no_output_mapping=False (model/attention.py:56-57)."""
     _forward_only(x_back, x_retr)
     x_back = _dev(x_back, name="x_predicted")
     x_retr = _dev(x_retr, name="x_retrieved")
@@ -1066,10 +1067,11 @@ def attention_fuse(x_back, x_retr, theta, phi, E, K, normalize=True, mode=0, ble
                                               ptr_array([w.data_ptr() for w in phi[0]]),
                                               ptr_array([b.data_ptr() for b in phi[1]]), _img_array(theta), _img_array(phi),
                                               _ptr(gumbel_noise), out.data_ptr(), B, nf, S, E, K, int(bool(normalize)), int(mode),
-                                              int(bool(blend)), P, int(bool(out_channels_last)), ws.data_ptr(), ws_bytes,
-                                              _stream(x_back)), "rf_attention_fuse_patched_fwd")
+                                              int(bool(blend)), P, int(bool(out_channels_last)),
+                                              None if output_mapping is None else ptr_array([t.data_ptr() for t in output_mapping]),
+                                              ws.data_ptr(), ws_bytes, _stream(x_back)), "rf_attention_fuse_patched_fwd")
     n_mlp = 1 if (len(theta) > 2 and theta[2] is not None) else 4   # launches per MLP: fused chain or four linears
-    _count(2 + 2 * n_mlp + 1 + (0 if out_channels_last else 1))
+    _count(2 + 2 * n_mlp + 1 + (0 if out_channels_last else 1) + (0 if output_mapping is None else 1))
     return out
 
 

@@ -19,6 +19,8 @@ ENC_CASES = [  # (class, nf, n_patches)
     ("PatchNorm32", 8, 2), ("PCPatch32", 8, 2), ("PCPatch48", 10, 2), ("PCPatch64", 8, 1),
 ]
 ATTN_CASES = [(16, 4, False), (12, 8, False), (16, 4, True), (16, 1, False)]  # (nf, K, gumbel)
+ATTN_MAPPING_CASES = [(16, 4, False), (12, 8, False)]  # attn_no_output_mapping=False (g / o 1x1x1 convolutions; softmax mode only: the
+# reference itself fails in retrieval mode, model/attention.py:103 hands o() a 2-D tensor)
 UNET_CASES = [("sr08", "Superresolution08UNetBackbone", 16, 4, 8), ("sr16", "Superresolution16UNetBackbone", 16, 4, 16),
               ("surface", "SurfaceReconstructionUNetBackbone", 12, 5, 128)]
 

@@ -635,6 +635,39 @@ def test_attention_on_unfolded_patches_channels_last(dev, nf, K, mode, B, P, S):
     assert float((want - xb).abs().max()) > 1e-3  # the attention did blend something in
 
 
+@pytest.mark.parametrize("nf,K,mode", C.ATTN_MAPPING_CASES)
+def test_attention_with_output_mapping(dev, nf, K, mode):
+    """attn_no_output_mapping=False (model/attention.py:56-57,95,108): g / o 1x1x1 convolutions around the weighted sum,
+    composed into one channel-mixing pass after the score stage (rf_attention_fuse_patched_fwd, output_mapping).  Against
+    the reference's own output, an fp64 evaluation of the oracle (pinned to the same golden), and - for the patch-order
+    entry - bit-identical to the folded call."""
+    from retrieval_fuse_b200 import ops
+    from retrieval_fuse_b200.model import get_attention_block
+    g = np.load(os.path.join(GOLD, "attention_mapping.npz"))
+    tag = C.attention_tag(nf, K, mode) + ".mapped"
+    cfg = dict(nf=nf, attn_patch_extent=4, K=K, attn_normalize=True, attn_use_switching=True, attn_retrieval_mode=mode,
+               attn_no_output_mapping=False, attn_blend=True, attn_num_patch=16)
+    m, sd = load(get_attention_block(cfg), O.attention_shapes(nf, 2, output_mapping=True), dev)
+    xb, xr, _ = C.attention_inputs(nf, K, mode)
+    y = m(xb.to(dev), xr.to(dev))
+    sd64 = {k: v.double() for k, v in sd.items()}
+    y64 = O.patched_attention_forward(xb.double(), xr.double(), sd64, nf, 16, 2, K, retrieval_mode=mode)
+    y32 = O.patched_attention_forward(xb, xr, sd, nf, 16, 2, K, retrieval_mode=mode)
+    ref_noise = float((y32.double() - y64).abs().max())
+    ours = float((y.cpu().double() - y64).abs().max())
+    assert ours <= max(2 * ref_noise, TOL), f"{tag}: |ours-fp64| {ours:.3e} vs reference fp32 noise {ref_noise:.3e}"
+    diff = np.abs(y[:, :, ::2, ::2, ::2].cpu().numpy() - g[tag])
+    assert float(np.mean(diff > TOL)) <= 1e-4 and float(diff.max()) <= max(10 * ref_noise, 1e-3), (tag, diff.max())
+    feats = ops.unfold3d(xr.to(dev), 8)  # the same candidates as the un-folded 8^3 patches of a 4^3 grid
+    assert torch.equal(m(xb.to(dev), feats, patch_grid=4), y)
+    with pytest.raises(ValueError):
+        m(xb.to(dev), feats, patch_grid=4, out_channels_last=True)
+    # the reference has no retrieval (Gumbel) mode with the mapping: model/attention.py:103 hands o() a 2-D tensor
+    mg = get_attention_block(dict(cfg, attn_retrieval_mode=True)).to(dev).eval()  # constructs, as the reference's does
+    with pytest.raises(ValueError):
+        mg(xb.to(dev), xr.to(dev))
+
+
 def test_attention_block_forward_on_sub_patches(dev):
     """AttentionBlock.forward(x, p) (model/attention.py:84-113) called directly on unfolded sub-patches, as
     PatchedAttentionBlock does internally: x [b, C, 2,2,2], p [b, K, C, 2,2,2]; K must match the configuration."""

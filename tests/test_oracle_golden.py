@@ -121,6 +121,18 @@ def test_attention(nf, K, mode):
         assert np.array_equal(of.numpy(), g[tag + ".feat_occ"])
 
 
+@pytest.mark.parametrize("nf,K,mode", C.ATTN_MAPPING_CASES)
+def test_attention_with_output_mapping(nf, K, mode):
+    """attn_no_output_mapping=False: the g / o 1x1x1 convolutions (model/attention.py:56-57,95,108) against the
+    reference's own PatchedAttentionBlock (tests/golden/make_golden_attention_mapping.py)."""
+    g = np.load(os.path.join(GOLD, "attention_mapping.npz"))
+    tag = C.attention_tag(nf, K, mode) + ".mapped"
+    sd = synth(O.attention_shapes(nf, 2, output_mapping=True))
+    xb, xr, _ = C.attention_inputs(nf, K, mode)
+    y = O.patched_attention_forward(xb, xr, sd, nf, 16, 2, K, retrieval_mode=mode)
+    np.testing.assert_allclose(y[:, :, ::2, ::2, ::2].numpy(), g[tag], rtol=0, atol=TOL)
+
+
 def test_refine_full_forward():
     """BASELINE config 1: the parity anchor."""
     g = np.load(os.path.join(GOLD, "refine_full.npz"))
