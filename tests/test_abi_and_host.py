@@ -82,6 +82,12 @@ def test_state_dict_keys_match_reference():
         chk(tag, M.get_attention_block(dict(nf=int(nf), attn_patch_extent=4, K=int(K), attn_normalize=True,
                                             attn_use_switching=True, attn_retrieval_mode=mode == "gumbel",
                                             attn_no_output_mapping=True, attn_blend=True, attn_num_patch=16)))
+    # attn_no_output_mapping=False: the g / o convolutions' keys (tests/golden/make_golden_attention_mapping.py asserts that
+    # this oracle table equals the reference module's state_dict)
+    mapped = M.get_attention_block(dict(nf=12, attn_patch_extent=4, K=8, attn_normalize=True, attn_use_switching=True,
+                                        attn_retrieval_mode=False, attn_no_output_mapping=False, attn_blend=True, attn_num_patch=16))
+    assert ({k: tuple(v.shape) for k, v in mapped.state_dict().items()} ==
+            {k: tuple(v) for k, v in O.attention_shapes(12, 2, output_mapping=True).items()})
     fi, ft = M.get_retrieval_networks(dict(network_input="2+1", network_target="16+8", nf_input=32, nf_target=8, latent_dim=64))
     assert type(fi).__name__ == "Patch04" and type(ft).__name__ == "Patch32"
     fi, ft = M.get_retrieval_networks(dict(network_input="pc_32+8", network_target="16+4", nf_input=10, nf_target=12, latent_dim=64))
@@ -90,9 +96,12 @@ def test_state_dict_keys_match_reference():
 
 def test_unsupported_configs_fail_loudly():
     import retrieval_fuse_b200.model as M
-    with pytest.raises(NotImplementedError):
-        M.get_attention_block(dict(nf=16, attn_patch_extent=4, K=4, attn_normalize=True, attn_use_switching=True,
-                                   attn_retrieval_mode=False, attn_no_output_mapping=False, attn_blend=True, attn_num_patch=16))
+    # attn_no_output_mapping=False is supported (softmax mode); with the Gumbel mode the reference's own forward raises
+    # (model/attention.py:103) - the module constructs, its composed output mapping is refused
+    blk = M.get_attention_block(dict(nf=16, attn_patch_extent=4, K=4, attn_normalize=True, attn_use_switching=True,
+                                     attn_retrieval_mode=True, attn_no_output_mapping=False, attn_blend=True, attn_num_patch=16))
+    with pytest.raises(ValueError):
+        blk.attention_blocks_layer.output_mapping()
     with pytest.raises(NotImplementedError):
         M.get_retrieval_backbone(dict(nf=16, retrieval_fmaps=16, retrieval_num_level=4, layer_order="cbr"))
 
