@@ -72,12 +72,16 @@ __global__ void __launch_bounds__(256) unfold_e2_patch8_kernel(const float* __re
 // row's own and of its K candidate vectors are requested BEFORE the score / softmax chain, so that one warp has all
 // of its ~(K + 1) * 5 loads in flight at once (with a run-time K loop the loads were serialised behind the warp
 // reductions: 1.35 TB/s on the 113 MB of this stage).
-template <int KT>
+// kExact: K == KT and V == 128 (nf = 16, E = 2: the shipped configurations) - every k < K / v < V guard and the row
+// pitch fold at compile time.  The general instantiation executed 1 086 instructions per row, half of them integer
+// address arithmetic and guards, and ran at 77 % issue utilisation with DRAM at 36 % (profiles/r02s4_attention_64chunks).
+template <int KT, bool kExact>
 __global__ void __launch_bounds__(256) attention_epilogue_kernel(const float* __restrict__ xf, const float* __restrict__ pf,
                                                                  const float* __restrict__ xu, const float* __restrict__ pu,
                                                                  const float* __restrict__ noise, float* __restrict__ orows,
-                                                                 long R, int rp3, int K, int V, int normalize, int mode,
+                                                                 long R, int rp3, int K_, int V_, int normalize, int mode,
                                                                  int blend, float sharp, const AttnGeo g) {
+    const int K = kExact ? KT : K_, V = kExact ? 128 : V_;
     const long row = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= R) return;
@@ -389,13 +393,15 @@ extern "C" int rf_attention_fuse_patched_fwd(const float* x_back, const float* x
     g.pow2 = (g.s_nf >= 0 && g.s_E >= 0 && g.s_Rp >= 0 && g.s_ps >= 0 && g.s_P >= 0) ? 1 : 0;
     g.side = mapped ? ws.ha : nullptr;  // (the hidden-activation buffers are free once both MLPs have run; >= R * 128 floats)
     float* erows = g.out_cl ? out : ws.orows;  // channels-last: the epilogue stores the volume itself
-#define RF_ATTN_EPI(KT)                                                                                         \
-    attention_epilogue_kernel<KT><<<egrid, 256, 0, (cudaStream_t)stream>>>(ws.xf, ws.pf, ws.xu, ws.pu, gumbel_noise, \
-                                                                            erows, R, rp3, K, V, normalize, mode, blend, sharp, g)
-    if (K <= 4) RF_ATTN_EPI(4);
-    else if (K <= 8) RF_ATTN_EPI(8);
-    else if (K <= 16) RF_ATTN_EPI(16);
-    else RF_ATTN_EPI(32);
+#define RF_ATTN_EPI(KT, EX)                                                                                         \
+    attention_epilogue_kernel<KT, EX><<<egrid, 256, 0, (cudaStream_t)stream>>>(ws.xf, ws.pf, ws.xu, ws.pu, gumbel_noise, \
+                                                                                erows, R, rp3, K, V, normalize, mode, blend, sharp, g)
+    if (K == 4 && V == 128) RF_ATTN_EPI(4, true);
+    else if (K == 8 && V == 128) RF_ATTN_EPI(8, true);
+    else if (K <= 4) RF_ATTN_EPI(4, false);
+    else if (K <= 8) RF_ATTN_EPI(8, false);
+    else if (K <= 16) RF_ATTN_EPI(16, false);
+    else RF_ATTN_EPI(32, false);
 #undef RF_ATTN_EPI
     RF_LAUNCH_OK("attention_epilogue_kernel");
     if (mapped) {

@@ -72,6 +72,7 @@ struct MlpArgs {
     float slope, eps;
     uint32_t slot_bytes;
     int nbw, n_tiles;
+    int n_iss;             // issuer warps in use: ceil(widest layer / 128)
     int act_chunks;        // 8-channel chunk planes resident per hi / lo (32 = 256 channels; 16 when no layer is wider than 128)
     uint32_t act_bytes, tmem_cols;
 };
@@ -188,8 +189,8 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_mlp_kernel(const MlpArgs a) 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int tid = threadIdx.x;
     if (tid == 0) {
-        for (int s = 0; s < a.nbw; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 4); }
-        mbar_init(bar_mma, 4);
+        for (int s = 0; s < a.nbw; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, (uint32_t)a.n_iss); }
+        mbar_init(bar_mma, (uint32_t)a.n_iss);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -220,7 +221,10 @@ __global__ void __launch_bounds__(NTHREADS, RES) tc_mlp_kernel(const MlpArgs a) 
     } else {
         // ---- 8 worker warps: loaders / epilogue; warps 1..4 are also the MMA issuers (128 accumulator columns each)
         const int iss = warp - 1;
-        const bool issuer = iss >= 0 && iss < 4;
+        // n_iss = issuer warps that own accumulator columns in the chain's widest layer (1 for the attention's 128-wide
+        // chains): the others do not take part in the weight ring at all - they used to poll every k step's "full" barrier
+        // only to release the slot again, 15 % of the kernel's samples sat on those polls (profiles/r02s4_attention_64chunks)
+        const bool issuer = iss >= 0 && iss < a.n_iss;
         const uint32_t leader = elect_one();
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         uint8_t* act_hi = smem_al;  // sACT == base
@@ -548,6 +552,7 @@ extern "C" int rf_tc_mlp_fwd(const float* x, int ldx, const void* const* images_
     // shared-memory footprint that lets two CTAs share an SM
     static const int force_wide = [] { const char* e = getenv("RF_MLP_WIDE"); return e ? atoi(e) : 0; }();  // tuning aid
     const bool narrow = !force_wide && max_np <= 128 && a.K0p <= 128;
+    a.n_iss = (max_np + 127) / 128;
     a.act_chunks = narrow ? 16 : ACT_CHUNKS;
     a.act_bytes = (uint32_t)a.act_chunks * PLANE;
     a.tmem_cols = narrow ? 128u : 512u;
