@@ -148,6 +148,9 @@ class PatchedAttentionBlock(nn.Module):
         out_channels_last returns [B,S,S,S,F] for the decoder's channels-last path."""
         ab = self.attention_blocks_layer
         K = self.num_nearest_neighbors
+        if x_predicted.shape[0] == 0:  # empty batch: what torch's ops would return
+            S = x_predicted.shape[2]
+            return x_predicted.new_empty((0, S, S, S, self.nf) if out_channels_last else x_predicted.shape)
         if patch_grid > 1 or out_channels_last:
             if ops.grad_needed(x_predicted, x_retrieved, *ab.parameters()):
                 raise ValueError("patch_grid / out_channels_last are inference shortcuts; fold the patches for training")

@@ -633,6 +633,8 @@ def test_attention_on_unfolded_patches_channels_last(dev, nf, K, mode, B, P, S):
         got2 = m(xb, feats, noise, patch_grid=P)
         assert torch.equal(got2, want)
     assert float((want - xb).abs().max()) > 1e-3  # the attention did blend something in
+    assert m(xb[:0], feats[:0], noise, patch_grid=P, out_channels_last=True).shape == (0, S, S, S, nf)
+    assert m(xb[:0], folded[:0], noise).shape == (0, nf, S, S, S)
 
 
 @pytest.mark.parametrize("nf,K,mode", C.ATTN_MAPPING_CASES)
