@@ -345,6 +345,14 @@ int rf_compose_gather(const float* rows, const int* dst_extents, const float* sc
                       int P, int K, int n_scenes, const int scene_size[3], const int chunk_size[3], float trunc,
                       float ratio, float norm_sub, float norm_div, void* stream);
 
+/* rf_compose_gather followed by Unfold3D(16, 1) of its result (trainer/train_refinement.py:110-111), in one pass:
+ * out is [n_chunks, K, P, ex, ey, ez], every destination block stored contiguously in patch order.  The caller
+ * guarantees that the P blocks have equal extents and tile the chunk in Unfold3D's patch order ((x, y, z) row-major);
+ * a block whose extents do not fit that layout is skipped. */
+int rf_compose_gather_patches(const float* rows, const int* dst_extents, const float* scene_store, float* out, int n_chunks,
+                              int P, int K, int n_scenes, const int scene_size[3], const int chunk_size[3], float trunc,
+                              float ratio, float norm_sub, float norm_div, void* stream);
+
 /* ---- a14  patch attention ------------------------------------------------ */
 
 /* model/attention.py:141-157 PatchedAttentionBlock.forward with

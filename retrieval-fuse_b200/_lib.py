@@ -121,6 +121,8 @@ PROTOTYPES = {
                                    c_void_p]),
     "rf_compose_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, _int3, _int3,
                                   c_float, c_float, c_float, c_float, c_void_p]),
+    "rf_compose_gather_patches": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, _int3, _int3,
+                                          c_float, c_float, c_float, c_float, c_void_p]),
     "rf_attention_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "rf_attention_fuse_fwd": (c_int, [c_void_p, c_void_p, _ptr4, _ptr4, _ptr4, _ptr4, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),

@@ -435,7 +435,7 @@ extern "C" int rf_recompose_patches(const float* patches, float* out, int B, int
 __global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ rows, const int* __restrict__ dst_ext,
                                                       const float* __restrict__ store, float* __restrict__ out, int P,
                                                       int K, int n_scenes, Int3 ssz, Int3 csz, float trunc, float ratio,
-                                                      float norm_sub, float norm_div, float norm_rcp) {
+                                                      float norm_sub, float norm_div, float norm_rcp, int patch_major) {
     const int p = blockIdx.x, k = blockIdx.y, c = blockIdx.z;
     const float* row = rows + (((long)c * P + p) * K + k) * 8;
     const int scene = (int)row[0];
@@ -447,7 +447,11 @@ __global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ 
     // the sentinel block is a float64 numpy array in the reference (:161), so the
     // product is rounded to fp32 only once, on assignment
     const float fill = (float)((double)trunc * (double)ratio);
-    float* o = out + ((long)c * K + k) * csz.v[0] * csz.v[1] * csz.v[2];
+    // patch_major: out is [chunk, k, patch, ex, ey, ez] - every destination block contiguous, i.e. what Unfold3D(16, 1)
+    // (trainer/train_refinement.py:110-111) makes of the composed volume when equal blocks tile it in patch order
+    const long cvol = (long)csz.v[0] * csz.v[1] * csz.v[2];
+    if (patch_major && (long)ex * ey * ez * P != cvol) return;  // (the host checked the tiling; never write out of the slot)
+    float* o = out + ((long)c * K + k) * cvol + (patch_major ? (long)p * ex * ey * ez : 0L);
     const float* s = store + (long)(scene < 0 ? 0 : scene) * ssz.v[0] * ssz.v[1] * ssz.v[2];
     const int n = ex * ey * ez;
     // fast path: the whole block lies inside the scene and every z-run is 16-byte aligned on both sides -> float4 moves
@@ -472,7 +476,8 @@ __global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ 
                     if (pow2) { z = (i & (ez4 - 1)) << 2; y = (i >> sh_z) & (ey - 1); x = i >> sh_zy; }   // 16^3 blocks: no divisions
                     else { z = (i % ez4) << 2; y = (i / ez4) % ey; x = i / (ez4 * ey); }
                     v[u] = __ldg(reinterpret_cast<const float4*>(s + ((long)(X0 + x) * ssz.v[1] + (Y0 + y)) * ssz.v[2] + Z0 + z));
-                    dsti[u] = ((long)(de[0] + x) * csz.v[1] + (de[2] + y)) * csz.v[2] + (de[4] + z);
+                    dsti[u] = patch_major ? ((long)x * ey + y) * ez + z
+                                          : ((long)(de[0] + x) * csz.v[1] + (de[2] + y)) * csz.v[2] + (de[4] + z);
                 }
             }
 #pragma unroll
@@ -501,14 +506,13 @@ __global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ 
             sx < ssz.v[0] && sy < ssz.v[1] && sz < ssz.v[2])
             v = __fmul_rn(s[((long)sx * ssz.v[1] + sy) * ssz.v[2] + sz], ratio);
         if (norm_div != 0.f) v = __fdiv_rn(__fsub_rn(v, norm_sub), norm_div);
-        o[((long)(de[0] + x) * csz.v[1] + (de[2] + y)) * csz.v[2] + (de[4] + z)] = v;
+        o[patch_major ? (long)i : ((long)(de[0] + x) * csz.v[1] + (de[2] + y)) * csz.v[2] + (de[4] + z)] = v;
     }
 }
 
-extern "C" int rf_compose_gather(const float* rows, const int* dst_extents, const float* scene_store, float* out,
-                                 int n_chunks, int P, int K, int n_scenes, const int scene_size[3],
-                                 const int chunk_size[3], float trunc, float ratio, float norm_sub,
-                                 float norm_div, void* stream) {
+static int compose_launch(const float* rows, const int* dst_extents, const float* scene_store, float* out, int n_chunks, int P,
+                          int K, int n_scenes, const int scene_size[3], const int chunk_size[3], float trunc, float ratio,
+                          float norm_sub, float norm_div, int patch_major, void* stream) {
     RF_CHECK_ARG(rows && dst_extents && scene_store && out && scene_size && chunk_size, "rf_compose_gather: null pointer");
     RF_CHECK_ARG(n_chunks > 0 && P > 0 && K > 0 && n_scenes > 0 && K <= 65535 && n_chunks <= 65535,
                  "rf_compose_gather: bad sizes");
@@ -516,9 +520,26 @@ extern "C" int rf_compose_gather(const float* rows, const int* dst_extents, cons
     for (int a = 0; a < 3; ++a) { s.v[a] = scene_size[a]; c.v[a] = chunk_size[a]; }
     dim3 grid(P, K, n_chunks);
     compose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, dst_extents, scene_store, out, P, K, n_scenes, s, c,
-                                                          trunc, ratio, norm_sub, norm_div, rf_host_rcp_for_div(norm_div));
+                                                          trunc, ratio, norm_sub, norm_div, rf_host_rcp_for_div(norm_div),
+                                                          patch_major);
     RF_LAUNCH_OK("compose_kernel");
     return 0;
+}
+
+extern "C" int rf_compose_gather(const float* rows, const int* dst_extents, const float* scene_store, float* out,
+                                 int n_chunks, int P, int K, int n_scenes, const int scene_size[3],
+                                 const int chunk_size[3], float trunc, float ratio, float norm_sub,
+                                 float norm_div, void* stream) {
+    return compose_launch(rows, dst_extents, scene_store, out, n_chunks, P, K, n_scenes, scene_size, chunk_size, trunc, ratio,
+                          norm_sub, norm_div, 0, stream);
+}
+
+extern "C" int rf_compose_gather_patches(const float* rows, const int* dst_extents, const float* scene_store, float* out,
+                                         int n_chunks, int P, int K, int n_scenes, const int scene_size[3],
+                                         const int chunk_size[3], float trunc, float ratio, float norm_sub,
+                                         float norm_div, void* stream) {
+    return compose_launch(rows, dst_extents, scene_store, out, n_chunks, P, K, n_scenes, scene_size, chunk_size, trunc, ratio,
+                          norm_sub, norm_div, 1, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -1007,10 +1007,13 @@ def knn_demote_rows(idx2k, d2k, meta, query_scene, K):
 
 
 def compose_gather(rows, dst_extents, scene_store, n_chunks, chunk_size, trunc, ratio, prefill=False, norm_sub=0.0,
-                   norm_div=0.0):
+                   norm_div=0.0, patch_block=None):
     """util/retrieval.py:145-164 for non-overlapping patches.
     rows [n_chunks*P,K,8]; dst_extents int32 [P,6]; scene_store [S,sx,sy,sz] -> [n_chunks,K,cx,cy,cz].
-    prefill=True initialises the output with `trunc` (:148) for scenes whose patch list does not tile the chunk."""
+    prefill=True initialises the output with `trunc` (:148) for scenes whose patch list does not tile the chunk.
+    patch_block = (ex, ey, ez): the P destination blocks all have these extents and tile the chunk in Unfold3D's patch
+    order (the caller checked) -> [n_chunks,K,P,ex,ey,ez], i.e. Unfold3D(ex, 1) of the composed volumes without the pass
+    over them (rf_compose_gather_patches)."""
     rows = _dev(rows, name="rows")
     dst_extents = _dev(dst_extents, torch.int32, "dst_extents")
     scene_store = _dev(scene_store, name="scene_store")
@@ -1018,10 +1021,15 @@ def compose_gather(rows, dst_extents, scene_store, n_chunks, chunk_size, trunc, 
     K = rows.shape[1]
     assert rows.shape[0] == n_chunks * P
     shape = (n_chunks, K) + tuple(int(v) for v in chunk_size)
+    if patch_block is not None:
+        pb = tuple(int(v) for v in patch_block)
+        assert P * pb[0] * pb[1] * pb[2] == shape[2] * shape[3] * shape[4], "patch blocks do not tile the chunk"
+        shape = (n_chunks, K, P) + pb
     out = (torch.full(shape, float(trunc), device=rows.device, dtype=torch.float32) if prefill
            else torch.empty(shape, device=rows.device, dtype=torch.float32))
+    fn = _lib.lib().rf_compose_gather if patch_block is None else _lib.lib().rf_compose_gather_patches
     with torch.cuda.device(rows.device), _timed("rf_compose_gather", nbytes=2.0 * out.numel() * 4):
-        check(_lib.lib().rf_compose_gather(rows.data_ptr(), dst_extents.data_ptr(), scene_store.data_ptr(),
+        check(fn(rows.data_ptr(), dst_extents.data_ptr(), scene_store.data_ptr(),
                                            out.data_ptr(), n_chunks, P, K, scene_store.shape[0],
                                            int3(scene_store.shape[1:]), int3(chunk_size), float(trunc), float(ratio),
                                            float(norm_sub), float(norm_div), _stream(rows)), "rf_compose_gather")

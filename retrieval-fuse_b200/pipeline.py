@@ -126,6 +126,9 @@ class RetrievalPipeline:
         ext = [[x * ps, x * ps + ps, y * ps, y * ps + ps, z * ps, z * ps + ps]
                for x in range(n) for y in range(n) for z in range(n)]
         self.dst_extents = torch.tensor(ext, dtype=torch.int32, device=self.device)
+        # the target patches tile the chunk in Unfold3D's patch order and have the edge the retrieval U-Net reads (16):
+        # compose can hand the refinement its Unfold3D(16, 1) patches directly (rf_compose_gather_patches)
+        self.patch_block = (ps, ps, ps) if (ps == 16 and n * ps == d["target_chunk_size"]) else None
         self._pinned = {}
 
     # ---- a1 + a5/a6 + a9
@@ -157,15 +160,20 @@ class RetrievalPipeline:
         return self.lookup(q, self.expand_scene(chunk_scene), method)
 
     # ---- a12
-    def compose(self, rows, n_chunks, normalize=False):
+    def compose(self, rows, n_chunks, normalize=False, patches=False):
         """rows [n_chunks*P,K,8] -> [n_chunks,K,64,64,64] raw TSDF (or the
-        dataloader-normalised volumes the refinement nets consume)."""
+        dataloader-normalised volumes the refinement nets consume).
+        patches=True (needs self.patch_block): [n_chunks,K,P,16,16,16] - the Unfold3D(16, 1) patches of those volumes
+        (trainer/train_refinement.py:110-111), which refine() accepts in place of the volumes."""
         assert self.scene_store is not None, "compose needs the GPU-resident scene store"
         d = self.ds
         c = d["target_chunk_size"]
+        if patches and self.patch_block is None:
+            raise ValueError("compose(patches=True): the target patches do not tile the chunk in 16^3 blocks")
         return ops.compose_gather(rows, self.dst_extents, self.scene_store, n_chunks, (c, c, c), self.target_trunc, 1.0,
                                   norm_sub=d["target_mean"] if normalize else 0.0,
-                                  norm_div=d["target_std"] if normalize else 0.0)
+                                  norm_div=d["target_std"] if normalize else 0.0,
+                                  patch_block=self.patch_block if patches else None)
 
     # ---- reference-facing host call: host buffers in, host buffers out
     def _pin(self, key, shape, dtype):
@@ -259,7 +267,8 @@ class RefinementPipeline(RetrievalPipeline):
             return self.decoder(x), x_back, x_retr, x
 
     def refine(self, x_in, retrieval, gumbel_noise=None, intermediates=True):
-        """x_in [B,1,s,s,s] normalised, retrieval [B,K',64,64,64] normalised -> pred [B,1,64,64,64] in [-1,1].
+        """x_in [B,1,s,s,s] normalised, retrieval [B,K',64,64,64] normalised (or its Unfold3D(16, 1) patches
+        [B,K',64,16,16,16] from compose(patches=True)) -> pred [B,1,64,64,64] in [-1,1].
         Returns (pred, x_back, x_retr, x_attended).  intermediates=False (inference: refine_graphed, infer*): the
         Fold3D before the attention and the Fold3D + layout change after it are folded into the attention call
         (rf_attention_fuse_patched_fwd) and x_retr / x_attended are returned as None; pred is bit-identical."""
@@ -275,8 +284,11 @@ class RefinementPipeline(RetrievalPipeline):
         with torch.cuda.stream(side):
             x_in.record_stream(side)
             x_back = self.unet_backbone(x_in)
-        retr = retrieval[:, :self.K].reshape(B * self.K, 1, S, S, S)   # get_retrievals (:255-257)
-        patches = ops.unfold3d(retr, 16)                                # Unfold3D(16, 1) (:34)
+        if retrieval.dim() == 6:   # compose(patches=True): [B,K',P,16,16,16], already Unfold3D(16, 1) of the volumes
+            patches = retrieval[:, :self.K].reshape(-1, 1, *retrieval.shape[3:])
+        else:
+            retr = retrieval[:, :self.K].reshape(B * self.K, 1, S, S, S)   # get_retrievals (:255-257)
+            patches = ops.unfold3d(retr, 16)                                # Unfold3D(16, 1) (:34)
         feats = self.retrieval_backbone(patches)                        # [B*K*64, nf, 8,8,8]
         if (not intermediates and self.decoder.tc_path(nf) and feats.is_cuda
                 and not ops.grad_needed(x_in, retrieval, feats, x_back, *self.patched_attention_block.parameters(),
@@ -350,7 +362,7 @@ class RefinementPipeline(RetrievalPipeline):
         mark()
         rows, _ = self.lookup(q, self.expand_scene(chunk_scene), method)
         mark()
-        retr = self.compose(rows, B, normalize=True)
+        retr = self.compose(rows, B, normalize=True, patches=self.patch_block is not None)
         x_in = self.normalize_input(chunks)
         mark()
         rb = refine_batch or B

@@ -1129,6 +1129,14 @@ def test_compose_bit_exact(dev):
     d = FRONT3D_SR["dataset"]
     gotn = pipe.compose(torch.from_numpy(rows).to(dev), B, normalize=True)
     assert np.array_equal(gotn.cpu().numpy(), ((want - d["target_mean"]) / d["target_std"]).astype(np.float32))
+    # compose straight into the refinement's Unfold3D(16, 1) patches (rf_compose_gather_patches): the same values, every
+    # 16^3 block contiguous in patch order; rows with the -1 sentinel scene and rows the store cannot serve included
+    from retrieval_fuse_b200 import ops
+    for norm in (False, True):
+        vol = pipe.compose(torch.from_numpy(rows).to(dev), B, normalize=norm)
+        pat = pipe.compose(torch.from_numpy(rows).to(dev), B, normalize=norm, patches=True)
+        assert pat.shape == (B, K, 64, 16, 16, 16)
+        assert torch.equal(pat.reshape(B * K * 64, 1, 16, 16, 16), ops.unfold3d(vol.reshape(B * K, 1, 64, 64, 64), 16))
 
 
 @pytest.mark.skipif(not os.environ.get("RF_EXPERIMENTAL"), reason="round-2 experiment (model.unet.W_PACK), not yet verified on hardware")
