@@ -128,8 +128,15 @@ __device__ __forceinline__ void rf_act_vec(float (&v)[N], int act, float slope) 
 #pragma unroll
         for (int e = 0; e < N; ++e) v[e] = fmaxf(v[e], 0.f);
     } else if (act == RF_ACT_LEAKY) {
+        if (slope > 0.f && slope <= 1.f) {
+            // max(v, v * slope): the same value for every input (v * slope <= v iff v >= 0 when 0 < slope <= 1, rounding is
+            // monotonic, signed zeros, infinities and NaN included), one instruction fewer per element than compare + select
 #pragma unroll
-        for (int e = 0; e < N; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
+            for (int e = 0; e < N; ++e) v[e] = fmaxf(v[e], v[e] * slope);
+        } else {
+#pragma unroll
+            for (int e = 0; e < N; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
+        }
     } else if (act == RF_ACT_TANH) {
 #pragma unroll  // (a rolled loop would index v dynamically and push the whole vector to local memory)
         for (int e = 0; e < N; ++e) v[e] = tanhf(v[e]);
