@@ -225,6 +225,30 @@ def test_oracle_reindex_properties():
     inv()
 
 
+def test_row_permutations_the_inference_shortcuts_rely_on():
+    """Index identities behind two GPU shortcuts, stated on the oracle's fold / unfold (pure re-indexing, CPU):
+    (1) rf_attention_fuse_patched_fwd: Unfold3D(E) of Fold3D(P, s, nf)(patches) is a permutation of the rows of Unfold3D(E)
+        applied to the un-folded patch batch - row (b, px, py, pz) of the former is row
+        ((b * P^3 + patch) * (s/E)^3 + local) of the latter (csrc/rf_attention.cu, AttnGeo with P > 1);
+    (2) rf_compose_gather_patches: destination blocks of edge 16 that tile the chunk in x-major order, stored
+        contiguously, are Unfold3D(16, 1) of the composed volume (trainer/train_refinement.py:110-111)."""
+    rng = np.random.default_rng(5)
+    for nf, P, s, E, BK in ((16, 4, 8, 2, 3), (12, 2, 4, 2, 2), (4, 2, 8, 4, 1)):
+        patches = rng.random((BK * P ** 3, nf, s, s, s)).astype(np.float32)
+        vol_rows = O.unfold3d(O.fold3d(patches, P, s, nf), E)          # what the reference's attention sees
+        pat_rows = O.unfold3d(patches, E)                               # what the shortcut unfolds
+        Rp, ps = P * s // E, s // E
+        r = np.arange(Rp ** 3)
+        px, py, pz = r // (Rp * Rp), (r // Rp) % Rp, r % Rp
+        mapped = (((px // ps) * P + py // ps) * P + pz // ps) * ps ** 3 + ((px % ps) * ps + py % ps) * ps + pz % ps
+        for b in range(BK):
+            assert np.array_equal(vol_rows[b * Rp ** 3 + r], pat_rows[b * Rp ** 3 + mapped])
+    vol = rng.random((2, 1, 64, 64, 64)).astype(np.float32)
+    blocks = np.stack([vol[:, 0, 16 * x:16 * x + 16, 16 * y:16 * y + 16, 16 * z:16 * z + 16]
+                       for x in range(4) for y in range(4) for z in range(4)], axis=1)   # [B, 64 blocks (x-major), 16,16,16]
+    assert np.array_equal(blocks.reshape(-1, 1, 16, 16, 16), O.unfold3d(vol, 16))
+
+
 def test_oracle_knn_and_demotion_properties():
     """Random small banks: the C oracle equals a brute-force float64 sort under (d, id); demotion is a stable
     partition (util/retrieval.py:94-97) that keeps K entries and never reorders inside the two classes."""
