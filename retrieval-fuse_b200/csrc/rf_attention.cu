@@ -6,10 +6,13 @@
 // are kept in (b, k, r) order (the order Unfold3D produces on x_retr), the
 // reference's permute to (b, r, k) is only an indexing change.
 //
-// Stage plan (round 1): unfold -> theta / phi MLPs through the implicit-GEMM
-// kernel -> one warp-per-row epilogue (normalise, scores, ReLU-max switch,
-// softmax(1024 s) or hard Gumbel arg-max, weighted sum of the raw candidate
-// vectors, blend) -> fold.
+// Stage plan: unfold -> theta / phi MLPs (one fused tcgen05 chain each, rf_tc_mlp.cu; fp32 FMA layers as the fallback)
+// -> one warp-per-row score / blend stage (normalise, scores, ReLU-max switch, softmax(1024 s) or hard Gumbel
+// arg-max, weighted sum of the raw candidate vectors, blend) -> fold.
+// rf_attention_fuse_patched_fwd (round 2) drops the re-indexing passes around it: the candidates may arrive as the
+// retrieval U-Net's un-folded patches (rows in (patch, local) order, mapped by index arithmetic), the result may be
+// stored as the channels-last volume the decoder reads, and the g / o 1x1x1 convolutions of
+// attn_no_output_mapping=False are one composed channel-mixing pass over the weighted-sum rows.
 #include <float.h>
 
 #include "rf_common.cuh"

@@ -2,9 +2,11 @@
 // the conv patch encoders, on channels-last activations.
 //
 // Pipeline of one SingleConv (GroupNorm -> Conv3d -> ReLU):
-//   cl_gn_stats_kernel    per (sample, group) mean / rstd of the fp32
-//                         channels-last input (the skip concat and the nearest
-//                         2x upsampling are virtual: two source tensors)
+//   cl_gn_partial_*       per (sample, channel) fp64 sums of the fp32 channels-last input
+//   + cl_gn_finalize      (the skip concat and the nearest 2x upsampling are virtual: two
+//                         source tensors) -> per (sample, group) mean / rstd.  One warp per
+//                         sample for many small samples, a cp.async.bulk ring through shared
+//                         memory otherwise, scalar loads as the fallback (rf_cl_gn_stats)
 //   cl_norm_split_kernel  y = (x-mu)*a+beta, split into fp16 hi/lo, channels
 //                         padded to a multiple of 8 -> [N,D,H,W,Cp] x 2.  The
 //                         normalisation runs ONCE per element here instead of
