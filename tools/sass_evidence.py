@@ -1,7 +1,8 @@
 """Build-time evidence (no GPU needed): per kernel of librf_b200.so the register count, spill / stack bytes, static
 shared memory (cuobjdump -res-usage) and the counts of the SASS mnemonics that prove the Blackwell path
 (B200_PROFILING.md: tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, bulk copies -> UBLKCP / UTMALDG, mbarrier ->
-SYNCS, legacy tensor path -> HMMA).  Writes profiles/r01_sass_evidence.txt.
+SYNCS, legacy tensor path -> HMMA).  Writes profiles/r02s4_sass_evidence.txt (the round-1 state is kept in
+profiles/r01_sass_evidence.txt).
 
     python tools/sass_evidence.py
 """
@@ -12,7 +13,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "retrieval-fuse_b200", "librf_b200.so")
-OUT = os.path.join(ROOT, "profiles", "r01_sass_evidence.txt")
+OUT = os.path.join(ROOT, "profiles", "r02s4_sass_evidence.txt")
 MNEMONICS = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "HMMA", "DFMA", "DADD", "DMUL",
              "LDG", "STG", "LDS", "STS", "SHFL", "FFMA", "MUFU"]
 
